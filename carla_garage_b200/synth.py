@@ -1,0 +1,120 @@
+"""Seeded synthetic inputs, labels and weights of the TransFuser++ step (SURVEY.md §8d "Synthetic inputs").
+
+There is no dataset and no released checkpoint offline, so every test / bench uses these generators.  They are
+pure functions of (shape, seed) on the CPU torch generator, hence identical in the build container (where the
+reference itself can be run on them to make golden vectors) and on the GPU box.
+"""
+import math
+import zlib
+
+import numpy as np
+import torch
+
+N_POINTS = 60000  # 600 k pts/s / 20 Hz * 2 half-sweeps (team_code/config.py:96-99, sensor_agent.py:381)
+
+
+def _gen(seed, tag=''):
+  g = torch.Generator(device='cpu')
+  g.manual_seed((int(seed) * 1000003 + zlib.crc32(tag.encode())) % (2**63 - 1))
+  return g
+
+
+def make_point_clouds(batch, seed=1234, n_points=N_POINTS):
+  """(B, N, 3) float32: x,y ~ U(-40,40), z ~ U(-1,4)."""
+  g = _gen(seed, 'points')
+  xy = torch.rand(batch, n_points, 2, generator=g) * 80.0 - 40.0
+  z = torch.rand(batch, n_points, 1, generator=g) * 5.0 - 1.0
+  return torch.cat([xy, z], dim=2).contiguous()
+
+
+def make_inputs(batch, seed=1234, lidar_channels=1):
+  """rgb (B,3,256,1024) integer-valued f32, lidar_bev (B,C,256,256) in {0,.2,..,1}, target_point, ego_vel, command.
+
+  ``lidar_bev`` here is drawn directly (sparse multiples of 0.2); ``make_point_clouds`` + the pillar-scatter
+  kernel give the real thing where the test covers K1 as well.
+  """
+  g = _gen(seed, 'inputs')
+  rgb = torch.randint(0, 256, (batch, 3, 256, 1024), generator=g).float()
+  occ = (torch.rand(batch, lidar_channels, 256, 256, generator=g) < 0.35).float()
+  lidar = occ * torch.randint(1, 6, (batch, lidar_channels, 256, 256), generator=g).float() / 5.0
+  target_point = torch.randn(batch, 2, generator=g) * 10.0
+  ego_vel = torch.rand(batch, 1, generator=g) * 8.0
+  command = torch.nn.functional.one_hot(torch.randint(0, 6, (batch,), generator=g), 6).float()
+  return dict(rgb=rgb, lidar_bev=lidar, target_point=target_point, ego_vel=ego_vel, command=command)
+
+
+def make_labels(batch, seed=1234):
+  """Label tensors with the shapes/dtypes train.py:693-766 moves to the device.  CenterNet targets are drawn
+  the way data.py:698-791 / gaussian_target.py:11-61 produce them (gaussian blobs, peak == 1 at box centres)."""
+  g = _gen(seed, 'labels')
+  lab = {}
+  lab['target_speed'] = torch.randint(0, 4, (batch,), generator=g)
+  lab['checkpoint'] = torch.cumsum(torch.rand(batch, 10, 2, generator=g), dim=1)
+  lab['semantic'] = torch.randint(0, 7, (batch, 256, 1024), generator=g)
+  lab['bev_semantic'] = torch.randint(0, 11, (batch, 256, 256), generator=g)
+  lab['depth'] = torch.rand(batch, 256, 1024, generator=g)
+  hm = torch.zeros(batch, 4, 64, 64)
+  wh = torch.zeros(batch, 2, 64, 64)
+  off = torch.zeros(batch, 2, 64, 64)
+  ycls = torch.zeros(batch, 64, 64, dtype=torch.long)
+  yres = torch.zeros(batch, 1, 64, 64)
+  pw = torch.zeros(batch, 2, 64, 64)
+  avg = torch.zeros(batch)
+  yy, xx = torch.meshgrid(torch.arange(64.0), torch.arange(64.0), indexing='ij')
+  for b in range(batch):
+    n = int(torch.randint(0, 31, (1,), generator=g))
+    avg[b] = max(1, n)
+    for _ in range(n):
+      cx, cy = (int(v) for v in torch.randint(0, 64, (2,), generator=g))
+      cls = int(torch.randint(0, 4, (1,), generator=g))
+      sigma = 0.5 + 2.0 * float(torch.rand(1, generator=g))
+      blob = torch.exp(-((xx - cx)**2 + (yy - cy)**2) / (2 * sigma * sigma))
+      blob[blob < 1e-4] = 0
+      hm[b, cls] = torch.maximum(hm[b, cls], blob)
+      hm[b, cls, cy, cx] = 1.0
+      wh[b, :, cy, cx] = torch.rand(2, generator=g) * 8 + 1
+      off[b, :, cy, cx] = torch.rand(2, generator=g)
+      ycls[b, cy, cx] = int(torch.randint(0, 12, (1,), generator=g))
+      yres[b, 0, cy, cx] = (float(torch.rand(1, generator=g)) - 0.5) * (2 * math.pi / 12)
+      pw[b, :, cy, cx] = 1.0
+  lab.update(center_heatmap=hm, wh=wh, offset=off, yaw_class=ycls, yaw_res=yres, pixel_weight=pw, avg_factor=avg)
+  return lab
+
+
+def make_state_dict(shapes, seed=0, fixed=None):
+  """Deterministic, well-conditioned weights for every key in ``shapes`` (name -> shape).
+
+  All BN affine/running stats, position embeddings and queries are *randomised* (the reference zero/one-inits them,
+  which would hide residual-branch and BN bugs, SURVEY.md §7 hard part 4).  ``fixed`` holds tensors copied verbatim
+  (``valid_bev_pixels`` masks, loss class weights)."""
+  fixed = fixed or {}
+  sd = {}
+  for name in sorted(shapes):
+    shape = tuple(shapes[name])
+    if name in fixed:
+      sd[name] = fixed[name].clone()
+      continue
+    g = _gen(seed, name)
+    leaf = name.rsplit('.', 1)[-1]
+    if leaf == 'num_batches_tracked':
+      t = torch.zeros(shape, dtype=torch.long)
+    elif leaf == 'running_var':
+      t = torch.rand(shape, generator=g) + 0.5
+    elif leaf == 'running_mean':
+      t = torch.randn(shape, generator=g) * 0.1
+    elif leaf == 'pos_emb':
+      t = torch.randn(shape, generator=g) * 0.1
+    elif leaf in ('checkpoint_query', 'wp_query', 'extra_sensor_pos_embed', 'tp_pos_embed'):
+      t = torch.rand(shape, generator=g)
+    elif 'gru.' in name:
+      t = (torch.rand(shape, generator=g) * 2 - 1) / 8.0
+    elif len(shape) >= 2:
+      fan_in = int(np.prod(shape[1:]))
+      gain = 2.0 if len(shape) == 4 else 1.0
+      t = torch.randn(shape, generator=g) * math.sqrt(gain / fan_in)
+    elif leaf == 'weight':  # 1-D weights: BatchNorm / LayerNorm gains
+      t = torch.rand(shape, generator=g) * 0.4 + 0.8
+    else:  # biases
+      t = torch.randn(shape, generator=g) * 0.05
+    sd[name] = t
+  return sd

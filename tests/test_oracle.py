@@ -1,0 +1,113 @@
+"""CPU tests: the oracle restatement against the golden vectors made from the unmodified reference
+(tests/golden/make_golden.py), and — in the build container only — against the live reference modules."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from carla_garage_b200 import compat, synth
+from oracle import tfpp_oracle as orc
+from oracle import regnety
+from tests.golden.sampling import sample
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def rel(a, b):
+  a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+  return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_regnety_geometry():
+  widths, depths, groups = regnety.regnet_widths()
+  assert widths == [72, 216, 576, 1512] and depths == [2, 5, 13, 1] and groups == [24] * 4
+  m = regnety.RegNetYFeatures(3)
+  n = sum(p.numel() for p in m.parameters())
+  assert n == 17923338  # 17.92 M
+  assert [i['num_chs'] for i in m.feature_info.info] == [32, 72, 216, 576, 1512]
+  y = m(torch.zeros(1, 3, 64, 64))
+  assert [t.shape[1:] for t in y] == [(32, 32, 32), (72, 16, 16), (216, 8, 8), (576, 4, 4), (1512, 2, 2)]
+
+
+def test_pillar_scatter_oracle_vs_golden():
+  g = np.load(os.path.join(GOLDEN, 'pillar_scatter.npz'))
+  pts = synth.make_point_clouds(2, seed=7).numpy()
+  clouds = dict(cloud0=pts[0], cloud1=pts[1], edge=g['edge_points'], empty=np.zeros((0, 3), np.float32))
+  for name, cloud in clouds.items():
+    for gp in (0, 1):
+      out = orc.lidar_to_histogram_features(cloud, bool(gp))
+      want = g[f'{name}_gp{gp}'].astype(np.float32) / 5.0
+      assert out.shape == want.shape and out.dtype == np.float32
+      assert np.array_equal(out, want), (name, gp)
+  # survey-recorded known answers of the reference function
+  rng = np.random.default_rng(0)
+  cloud = np.stack([rng.uniform(-40, 40, 60000), rng.uniform(-40, 40, 60000), rng.uniform(-1, 4, 60000)], 1)
+  out = orc.lidar_to_histogram_features(cloud, False)
+  assert abs(float(out.sum()) - 5831.2002) < 1e-2 and int((out > 0).sum()) == 23606 and out.max() == 1.0
+
+
+def test_valid_bev_pixels_vs_golden():
+  want = np.load(os.path.join(GOLDEN, 'valid_bev_pixels.npz'))['valid']
+  got = orc.valid_bev_pixels().numpy()
+  assert got.shape == (1, 1, 256, 256)
+  assert np.array_equal(got.astype(np.uint8), want)
+
+
+def test_forward_eval_vs_golden(oracle_state):
+  g = np.load(os.path.join(GOLDEN, 'forward_eval_b2.npz'))
+  inp = synth.make_inputs(2, seed=11)
+  taps = {}
+  torch.set_num_threads(os.cpu_count())
+  with torch.no_grad():
+    out = orc.forward(oracle_state, **inp, taps=taps)
+  assert rel(out[1], g['pred_target_speed']) < 1e-4
+  assert rel(out[2], g['pred_checkpoint']) < 1e-4
+  assert rel(sample(out[3]), g['pred_semantic']) < 1e-4
+  assert rel(sample(out[4]), g['pred_bev_semantic']) < 1e-4
+  assert rel(sample(out[5]), g['pred_depth']) < 1e-4
+  for n, t in zip(('heatmap', 'wh', 'offset', 'yaw_class', 'yaw_res'), out[6][:5]):
+    assert rel(sample(t), g['bb_' + n]) < 1e-4, n
+    assert abs(float(t.norm()) / float(g['norm_bb_' + n]) - 1) < 1e-4
+  for k in ('img_stem', 'lid_stem', 'img_s1_pre', 'lid_s4_pre', 'bev_feature_grid', 'fused_features',
+            'image_feature_grid', 'joined'):
+    assert rel(sample(taps[k]), g['tap_' + k]) < 1e-4, k
+  boxes = orc.decode_heatmap(*out[6][:5])
+  assert boxes.shape == (2, 100, 9)
+  assert rel(boxes, g['boxes']) < 1e-4
+
+
+def test_train_losses_vs_golden(oracle_state):
+  g = np.load(os.path.join(GOLDEN, 'train_b2.npz'))
+  inp = synth.make_inputs(2, seed=11)
+  lab = synth.make_labels(2, seed=13)
+  sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v)
+        for k, v in oracle_state.items()}
+  torch.set_num_threads(os.cpu_count())
+  out = orc.forward(sd, **inp, training=True)
+  # forward() detaches; run the differentiable path explicitly
+  loss = orc.compute_loss(oracle_state, out, lab)
+  for k in orc.LOSS_KEYS:
+    assert abs(float(loss[k]) - float(g[k])) <= 2e-4 * max(1.0, abs(float(g[k]))), k
+  assert abs(float(orc.total_loss(loss)) - float(g['total'])) < 2e-4
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not compat.reference_available(), reason='needs /root/reference (build container)')
+def test_oracle_vs_live_reference(oracle_state):
+  compat.install(regnety.timm_factory)
+  from config import GlobalConfig  # pylint: disable=import-outside-toplevel
+  from model import LidarCenterNet  # pylint: disable=import-outside-toplevel
+  net = LidarCenterNet(GlobalConfig()).eval()
+  net.load_state_dict(oracle_state, strict=True)
+  inp = synth.make_inputs(1, seed=5)
+  with torch.no_grad():
+    want = net(**inp)
+    got = orc.forward(oracle_state, **inp)
+  for i in (1, 2, 3, 4, 5):
+    assert rel(got[i], want[i]) < 1e-5, i
+  for a, b in zip(got[6][:5], want[6][:5]):
+    assert rel(a, b) < 1e-5
+  pts = synth.make_point_clouds(1, seed=3).numpy()[0]
+  for gp in (False, True):
+    assert np.array_equal(orc.lidar_to_histogram_features(pts, gp), net.data.lidar_to_histogram_features(pts, gp))
