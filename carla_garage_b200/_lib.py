@@ -1,0 +1,83 @@
+"""ctypes binding of libtfpp.so (include/tfpp.h).  Fails loudly when the library is missing: there is no CPU or
+torch fallback anywhere in the product path."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libtfpp.so')
+_lib = None
+
+c_int, c_float, c_ll, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_void_p
+
+
+class ConvGemmArgs(ctypes.Structure):
+  """tfpp_conv_gemm_args (include/tfpp.h)."""
+  _fields_ = [
+      ('a', c_void_p), ('a_batch', c_int), ('height', c_int), ('width', c_int), ('a_channels', c_int),
+      ('a_batch_stride', c_ll),
+      ('w', c_void_p), ('w_taps', c_int), ('w_kdim', c_int), ('n', c_int),
+      ('batch', c_int), ('k_per_tile', c_int), ('a_c_per_ntile', c_int), ('bn', c_int),
+      ('tw', c_int), ('th', c_int), ('nb', c_int), ('ntaps', c_int),
+      ('tap_dx', c_int * 9), ('tap_dy', c_int * 9), ('tap_db', c_int * 9), ('tap_w', c_int * 9),
+      ('out', c_void_p), ('out_f32', c_int),
+      ('o_sb', c_ll), ('o_sy', c_ll), ('o_sx', c_ll), ('o_sn', c_ll),
+      ('res1', c_void_p), ('res1_f32', c_int),
+      ('r1_sb', c_ll), ('r1_sy', c_ll), ('r1_sx', c_ll), ('r1_sn', c_ll),
+      ('res2', c_void_p), ('res2_f32', c_int),
+      ('r2_sb', c_ll), ('r2_sy', c_ll), ('r2_sx', c_ll), ('r2_sn', c_ll),
+      ('scale', c_void_p), ('shift', c_void_p), ('act', c_int), ('act_n_limit', c_int),
+      ('stat_sum', c_void_p), ('stat_sq', c_void_p),
+  ]
+
+
+P, I, F, L = c_void_p, c_int, c_float, c_ll
+_PROTOS = {
+    'tfpp_abi_version': [],
+    'tfpp_pillar_scatter': [P, I, I, P, P, I, F, F, F, F, F, I, F, F, P],
+    'tfpp_conv_gemm': [ctypes.POINTER(ConvGemmArgs), P],
+    'tfpp_stem_conv': [P, P, P, P, P, P, I, P, P, P, I, I, I, I, P],
+    'tfpp_bn_finalize': [P, P, P, P, P, P, P, P, P, P, I, F, F, F, P],
+    'tfpp_scale_shift_act': [P, P, P, P, P, P, I, P, P, I, I, I, P],
+    'tfpp_se_gate': [P, I, P, P, P, P, P, P, I, I, I, P],
+    'tfpp_channel_scale': [P, P, P, I, I, I, P],
+    'tfpp_parity_split': [P, P, I, I, I, I, P],
+    'tfpp_avgpool_tokens': [P, P, P, I, I, I, I, I, I, I, I, I, P],
+    'tfpp_bilinear': [P, I, L, L, P, P, I, I, I, I, I, I, P],
+    'tfpp_bilinear_nchw_mask': [P, P, P, I, I, I, I, I, I, I, P],
+    'tfpp_nchw_f32_to_nhwc_bf16': [P, P, I, I, I, P],
+    'tfpp_nhwc_bf16_to_nchw_f32': [P, P, I, I, I, P],
+    'tfpp_layernorm': [P, I, P, P, P, P, P, P, I, I, F, P],
+    'tfpp_fusion_attn': [P, P, I, I, I, I, P],
+    'tfpp_small_mha': [P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, P],
+    'tfpp_extra_sensor_token': [P, P, F, F, I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    'tfpp_planner_head': [P] * 17 + [I, I, I, I, I, P],
+    'tfpp_decode_heatmap': [P, L, P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, F, F, P],
+}
+
+
+def exported_symbols():
+  return sorted(_PROTOS) + ['tfpp_last_error']
+
+
+def load():
+  """Load libtfpp.so once; raise if it was not built (run `python __graft_entry__.py`)."""
+  global _lib  # pylint: disable=global-statement
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise RuntimeError(f'{LIB_PATH} is missing: build the CUDA extension first (python __graft_entry__.py). '
+                       'carla_garage_b200 has no CPU/torch fallback.')
+  lib = ctypes.CDLL(LIB_PATH)
+  lib.tfpp_last_error.restype = ctypes.c_char_p
+  lib.tfpp_last_error.argtypes = []
+  for name, args in _PROTOS.items():
+    fn = getattr(lib, name)
+    fn.restype = c_int
+    fn.argtypes = args
+  _lib = lib
+  return lib
+
+
+def check(rc, what):
+  if rc != 0:
+    raise RuntimeError(f'{what} failed (rc={rc}): {load().tfpp_last_error().decode()}')

@@ -1,0 +1,91 @@
+// K1 — LiDAR point cloud -> BEV occupancy histogram ("pillar scatter").
+//
+// Reference: CARLA_Data.lidar_to_histogram_features, team_code/data.py:873-906 (two np.histogramdd calls on the
+// CPU, clip at hist_max_per_pixel, divide, transpose).  Here: one thread per point, 12-byte point loads, u32
+// atomicAdd into a (B,2,H,W) count grid, then a clip/scale pass that writes the [ch][y_bin][x_bin] f32 image.
+// Integer-exact: counts are integers, outputs are k/5.  HBM-bound: 12 B per point in, 4 B x H x W per channel out.
+#include "../../include/tfpp.h"
+#include "common.cuh"
+
+namespace {
+
+struct ScatterCfg {
+  float min_x, max_x, min_y, max_y, ppm, split_z, max_z;
+  int nx, ny;
+};
+
+__global__ void __launch_bounds__(256) pillar_count_kernel(const float* __restrict__ pts, long long total,
+                                                           int n_points, uint32_t* __restrict__ counts, ScatterCfg c) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
+    // data.py:896-898: drop z >= max_height; "below" is z <= split (compared in the cloud's dtype, f32 here)
+    if (!(z < c.max_z)) continue;
+    // np.histogramdd semantics (data.py:887): half-open bins [e_i, e_{i+1}), last bin closed; NaN never counted.
+    if (!(x >= c.min_x && x <= c.max_x && y >= c.min_y && y <= c.max_y)) continue;
+    // edges are exact multiples of 1/ppm (0.25): floor(x * ppm) is exact in f32, no rounding at bin borders
+    int bx = static_cast<int>(floorf(x * c.ppm)) - static_cast<int>(c.min_x * c.ppm);
+    int by = static_cast<int>(floorf(y * c.ppm)) - static_cast<int>(c.min_y * c.ppm);
+    bx = min(bx, c.nx - 1);
+    by = min(by, c.ny - 1);
+    const int ch = (z <= c.split_z) ? 0 : 1;
+    const int b = static_cast<int>(i / n_points);
+    // stored transposed already: [b][ch][y_bin][x_bin]  (data.py:893 `.T`)
+    atomicAdd(counts + ((static_cast<long long>(b) * 2 + ch) * c.ny + by) * c.nx + bx, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) pillar_finalize_kernel(const uint32_t* __restrict__ counts,
+                                                              float* __restrict__ out, long long total, int plane,
+                                                              int use_ground_plane, int hist_max) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n_ch = use_ground_plane ? 2 : 1;
+  const long long b = i / (static_cast<long long>(n_ch) * plane);
+  const long long rem = i - b * n_ch * plane;
+  const int ch = static_cast<int>(rem / plane);
+  const long long pix = rem - static_cast<long long>(ch) * plane;
+  const int src_ch = use_ground_plane ? ch : 1;  // data.py:901-904: [below, above] or [above]
+  uint32_t cnt = counts[(b * 2 + src_ch) * plane + pix];
+  cnt = cnt > static_cast<uint32_t>(hist_max) ? static_cast<uint32_t>(hist_max) : cnt;
+  // float64 division then cast to f32 in the reference (data.py:889,905); k/5 rounds identically via f32 division
+  out[i] = static_cast<float>(static_cast<double>(cnt) / static_cast<double>(hist_max));
+}
+
+}  // namespace
+
+extern "C" int tfpp_pillar_scatter(const float* points, int batch, int n_points, uint32_t* counts, float* out,
+                                   int use_ground_plane, float min_x, float max_x, float min_y, float max_y,
+                                   float pixels_per_meter, int hist_max, float split_z, float max_z,
+                                   tfpp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TFPP_CHECK_ARG(batch >= 0 && n_points >= 0, "negative sizes");
+  TFPP_CHECK_ARG(counts != nullptr && out != nullptr, "null output");
+  TFPP_CHECK_ARG(hist_max > 0 && pixels_per_meter > 0, "bad histogram config");
+  ScatterCfg c;
+  c.min_x = min_x; c.max_x = max_x; c.min_y = min_y; c.max_y = max_y;
+  c.ppm = pixels_per_meter; c.split_z = split_z; c.max_z = max_z;
+  c.nx = static_cast<int>((max_x - min_x) * pixels_per_meter);
+  c.ny = static_cast<int>((max_y - min_y) * pixels_per_meter);
+  const int plane = c.nx * c.ny;
+  if (batch == 0) return TFPP_OK;
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(uint32_t) * 2ull * plane * batch, stream);
+  if (e != cudaSuccess) {
+    tfpp_set_error("memset: %s", cudaGetErrorString(e));
+    return TFPP_ERR_CUDA;
+  }
+  const long long total = static_cast<long long>(batch) * n_points;
+  if (total > 0) {
+    TFPP_CHECK_ARG(points != nullptr, "null points");
+    long long blocks = ceil_div_ll(total, 256);
+    const long long cap = static_cast<long long>(TFPP_NUM_SMS) * 16;
+    if (blocks > cap) blocks = cap;
+    pillar_count_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(points, total, n_points, counts, c);
+    TFPP_CHECK_LAUNCH();
+  }
+  const long long out_total = static_cast<long long>(batch) * (use_ground_plane ? 2 : 1) * plane;
+  pillar_finalize_kernel<<<static_cast<int>(ceil_div_ll(out_total, 256)), 256, 0, stream>>>(
+      counts, out, out_total, plane, use_ground_plane, hist_max);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}

@@ -1,0 +1,558 @@
+// tcgen05 implicit-GEMM convolution / linear kernel for sm_100a.
+//
+//   out[pixel, n] = act(scale[n] * sum_{tap, c} A[pixel + shift(tap), c0 + c] * W[n, tap, c] + shift[n] + res1 + res2)
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane issues
+// tcgen05.mma, accumulators live in TMEM, double buffered), warps 2-5 = epilogue (tcgen05.ld -> registers ->
+// fused BatchNorm/bias/activation/residual/statistics -> global).  A tiles are 128 pixels x 64 channels fetched with
+// 4-D TMA boxes (C, W, H, B) so that 3x3 taps are plain coordinate shifts with hardware zero fill (= conv padding);
+// B tiles are BN x 64 boxes of the (N, taps, K) weight tensor.  Both land in the canonical K-major SWIZZLE_128B
+// layout the UMMA shared-memory descriptors expect.
+//
+// Replaces (reference, torch library dispatches): timm RegNet 1x1 / grouped 3x3 convs iterated at
+// team_code/transfuser.py:216-219, nn.Linear at transfuser.py:352-359,391-396, the 1x1 channel maps at
+// transfuser.py:233,237, FPN/decoder/head convs (transfuser.py:131-137, transfuser_utils.py:675-704,
+// model.py:75-90,148, center_net.py:43-47) and the decoder projections (model.py:137-143).
+#include <cuda.h>
+
+#include "../../include/tfpp.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                         // bf16 elements = 128 bytes = one SWIZZLE_128B row
+constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;                      // 2 accumulator stages x 256 columns
+constexpr int kAccStride = 256;
+
+struct KParams {
+  int batch, height, width;
+  int kc_per_tap, a_c_per_ntile;
+  int n, bn, n_tiles, m_tiles_x, m_tiles_y, m_tiles_b;
+  int tw, th, nb;
+  int ntaps;
+  int tap_dx[9], tap_dy[9], tap_db[9], tap_w[9];
+  int stages, b_stage_bytes;
+  void* out;
+  int out_f32;
+  long long o_sb, o_sy, o_sx, o_sn;
+  const void* res1;
+  int res1_f32;
+  long long r1_sb, r1_sy, r1_sx, r1_sn;
+  const void* res2;
+  int res2_f32;
+  long long r2_sb, r2_sy, r2_sx, r2_sn;
+  const float* scale;
+  const float* shift;
+  int act, act_n_limit;
+  float* stat_sum;
+  float* stat_sq;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30) (unused for swizzled K-major, 1), SBO>>4 [32,46) = 1024 B between 8-row core-matrix groups,
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10)/[10,13),
+// a/b major K (0) [15]/[16], N>>3 [17,23), M>>4 [24,29).
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Column sums over the 32 lanes of a warp for 16 columns at once (recursive halving: 16 shuffles instead of 80).
+// On return lane L holds in v[0] the total of column ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
+__device__ __forceinline__ float warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float a = v[i], b = v[i + half];
+      const float send = hi ? a : b;
+      const float keep = hi ? b : a;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
+__device__ __forceinline__ float load_res(const void* p, int is_f32, long long off) {
+  return is_f32 ? static_cast<const float*>(p)[off] : bf2f(static_cast<const bf16*>(p)[off]);
+}
+
+struct TileCoord {
+  int n0, x0, y0, b0, n_tile;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  t.n0 = t.n_tile * p.bn;
+  t.x0 = (m % p.m_tiles_x) * p.tw;
+  m /= p.m_tiles_x;
+  t.y0 = (m % p.m_tiles_y) * p.th;
+  t.b0 = (m / p.m_tiles_y) * p.nb;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const KParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A 16 KB | B b_stage_bytes)] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = kABytes + p.b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.n_tiles * p.m_tiles_x * p.m_tiles_y * p.m_tiles_b;
+  const int k_iters = p.ntaps * p.kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = kABytes + p.bn * kBlockK * 2;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int c_base = t.n_tile * p.a_c_per_ntile;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, tx_bytes);
+            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            tma_load_4d(smem_u32(sa), &tmap_a, fb, c_base + kc * kBlockK, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap],
+                        t.b0 + p.tap_db[tap]);
+            tma_load_3d(smem_u32(sa + kABytes), &tmap_b, fb, kc * kBlockK, p.tap_w[tap], t.n0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.bn);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kABytes);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            // advance 16 bf16 = 32 bytes inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 2..5)
+    const int lane_group = warp & 3;             // TMEM lanes [32*lane_group, +32) are accessible to this warp
+    const int row = lane_group * 32 + lane;      // tile row == pixel
+    const int pix_per_img = p.th * p.tw;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int bl = row / pix_per_img;
+      const int rem = row - bl * pix_per_img;
+      const int yy = t.y0 + rem / p.tw;
+      const int xx = t.x0 + rem % p.tw;
+      const int bb = t.b0 + bl;
+      const bool valid = (bb < p.batch) && (yy < p.height) && (xx < p.width);
+      const long long o_base = bb * p.o_sb + yy * p.o_sy + xx * p.o_sx;
+      const long long r1_base = bb * p.r1_sb + yy * p.r1_sy + xx * p.r1_sx;
+      const long long r2_base = bb * p.r2_sb + yy * p.r2_sy + xx * p.r2_sx;
+
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + acc * kAccStride;
+      for (int c = 0; c < p.bn; c += 16) {
+        float v[16];
+        const int n = t.n0 + c;
+        if (n >= p.n) break;  // warp-uniform: remaining columns are padding
+        __syncwarp();
+        tmem_ld16(taddr + c, v);
+        if (p.stat_sum != nullptr) {
+          float s[16], q[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = valid ? v[j] : 0.f;
+            s[j] = a;
+            q[j] = a * a;
+          }
+          const float cs = warp_colsum16(s, lane);
+          const float cq = warp_colsum16(q, lane);
+          const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          if ((lane & 1) == 0 && n + col < p.n) {
+            atomicAdd(p.stat_sum + n + col, cs);
+            atomicAdd(p.stat_sq + n + col, cq);
+          }
+        }
+        if (p.out != nullptr && valid) {
+        const bool full = (n + 16 <= p.n);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (full || n + j < p.n) {
+            float a = v[j];
+            if (p.scale) a *= __ldg(p.scale + n + j);
+            if (p.shift) a += __ldg(p.shift + n + j);
+            v[j] = a;
+          }
+        }
+        if (p.res1) {
+          if (full && p.r1_sn == 1 && !p.res1_f32) {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const bf16*>(p.res1) + r1_base + n);
+            const uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
+            const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = unpack_bf16x2(w[j]);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full || n + j < p.n) v[j] += load_res(p.res1, p.res1_f32, r1_base + (n + j) * p.r1_sn);
+          }
+        }
+        if (p.res2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (full || n + j < p.n) v[j] += load_res(p.res2, p.res2_f32, r2_base + (n + j) * p.r2_sn);
+        }
+        if (p.act != ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (p.act_n_limit == 0 || n + j < p.act_n_limit) v[j] = apply_act(v[j], p.act);
+        }
+        if (full && p.o_sn == 1 && !p.out_f32) {
+          uint4 u0, u1;
+          u0.x = pack_bf16x2(v[0], v[1]);
+          u0.y = pack_bf16x2(v[2], v[3]);
+          u0.z = pack_bf16x2(v[4], v[5]);
+          u0.w = pack_bf16x2(v[6], v[7]);
+          u1.x = pack_bf16x2(v[8], v[9]);
+          u1.y = pack_bf16x2(v[10], v[11]);
+          u1.z = pack_bf16x2(v[12], v[13]);
+          u1.w = pack_bf16x2(v[14], v[15]);
+          uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_base + n);
+          op[0] = u0;
+          op[1] = u1;
+        } else if (full && p.o_sn == 1 && p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o_base + n);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (full || n + j < p.n) {
+              const long long off = o_base + (n + j) * p.o_sn;
+              if (p.out_f32)
+                static_cast<float*>(p.out)[off] = v[j];
+              else
+                static_cast<bf16*>(p.out)[off] = f2bf(v[j]);
+            }
+          }
+        }
+        }  // valid
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    tfpp_set_error("cuTensorMapEncodeTiled entry point not available");
+    return TFPP_ERR_DRIVER;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tfpp_set_error("cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
+                   (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1],
+                   box[2]);
+    return TFPP_ERR_DRIVER;
+  }
+  return TFPP_OK;
+}
+
+}  // namespace
+
+extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TFPP_CHECK_ARG(a != nullptr && a->a != nullptr && a->w != nullptr, "null operand");
+  TFPP_CHECK_ARG(a->bn >= 16 && a->bn <= 256 && a->bn % 16 == 0, "bn must be a multiple of 16 in [16,256]");
+  TFPP_CHECK_ARG(a->tw * a->th * a->nb == kBlockM, "tw*th*nb must be 128");
+  TFPP_CHECK_ARG(a->tw <= 256 && a->th <= 256 && a->nb <= 256, "tile extents must be <= 256");
+  TFPP_CHECK_ARG(a->ntaps >= 1 && a->ntaps <= 9, "1..9 taps");
+  TFPP_CHECK_ARG(a->a_channels % 8 == 0 && a->w_kdim % 8 == 0, "channel counts must be multiples of 8 (16 B TMA strides)");
+  TFPP_CHECK_ARG((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
+                 "operands must be 16 B aligned");
+  TFPP_CHECK_ARG(a->a_batch_stride % 8 == 0, "a_batch_stride must be a multiple of 8 elements");
+  TFPP_CHECK_ARG(a->k_per_tile >= 1 && a->k_per_tile <= a->w_kdim, "k_per_tile must be <= w_kdim");
+  TFPP_CHECK_ARG(a->out != nullptr || a->stat_sum != nullptr, "nothing to produce");
+  TFPP_CHECK_ARG((a->stat_sum == nullptr) == (a->stat_sq == nullptr), "stat_sum and stat_sq go together");
+
+  KParams p;
+  p.batch = a->batch;
+  p.height = a->height;
+  p.width = a->width;
+  p.kc_per_tap = ceil_div(a->k_per_tile, kBlockK);
+  p.a_c_per_ntile = a->a_c_per_ntile;
+  p.n = a->n;
+  p.bn = a->bn;
+  p.n_tiles = ceil_div(a->n, a->bn);
+  p.tw = a->tw;
+  p.th = a->th;
+  p.nb = a->nb;
+  p.m_tiles_x = ceil_div(a->width, a->tw);
+  p.m_tiles_y = ceil_div(a->height, a->th);
+  p.m_tiles_b = ceil_div(a->batch, a->nb);
+  p.ntaps = a->ntaps;
+  for (int i = 0; i < 9; ++i) {
+    p.tap_dx[i] = a->tap_dx[i];
+    p.tap_dy[i] = a->tap_dy[i];
+    p.tap_db[i] = a->tap_db[i];
+    p.tap_w[i] = a->tap_w[i];
+  }
+  p.b_stage_bytes = ((a->bn * kBlockK * 2 + 1023) / 1024) * 1024;
+  const int stage_bytes = kABytes + p.b_stage_bytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  p.out = a->out;
+  p.out_f32 = a->out_f32;
+  p.o_sb = a->o_sb; p.o_sy = a->o_sy; p.o_sx = a->o_sx; p.o_sn = a->o_sn;
+  p.res1 = a->res1; p.res1_f32 = a->res1_f32;
+  p.r1_sb = a->r1_sb; p.r1_sy = a->r1_sy; p.r1_sx = a->r1_sx; p.r1_sn = a->r1_sn;
+  p.res2 = a->res2; p.res2_f32 = a->res2_f32;
+  p.r2_sb = a->r2_sb; p.r2_sy = a->r2_sy; p.r2_sx = a->r2_sx; p.r2_sn = a->r2_sn;
+  p.scale = a->scale;
+  p.shift = a->shift;
+  p.act = a->act;
+  p.act_n_limit = a->act_n_limit;
+  p.stat_sum = a->stat_sum;
+  p.stat_sq = a->stat_sq;
+
+  CUtensorMap tmap_a, tmap_b;
+  {
+    const cuuint64_t c = a->a_channels, w = a->width, h = a->height, b = a->a_batch;
+    const cuuint64_t dims[4] = {c, w, h, b};
+    const cuuint64_t img = a->a_batch_stride > 0 ? (cuuint64_t)a->a_batch_stride : h * w * c;
+    const cuuint64_t strides[3] = {c * 2, w * c * 2, img * 2};
+    const cuuint32_t box[4] = {kBlockK, (cuuint32_t)a->tw, (cuuint32_t)a->th, (cuuint32_t)a->nb};
+    int rc = encode_map(&tmap_a, a->a, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t k = a->w_kdim, t = a->w_taps, n = a->n;
+    const cuuint64_t dims[3] = {k, t, n};
+    const cuuint64_t strides[2] = {k * 2, t * k * 2};
+    const cuuint32_t box[3] = {kBlockK, 1, (cuuint32_t)a->bn};
+    int rc = encode_map(&tmap_b, a->w, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      tfpp_set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+      return TFPP_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int num_tiles = p.n_tiles * p.m_tiles_x * p.m_tiles_y * p.m_tiles_b;
+  int sms = TFPP_NUM_SMS;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int cached_sms = 0;
+    if (cached_sms == 0) cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cached_sms > 0) sms = cached_sms;
+  }
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, p);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}

@@ -1,0 +1,381 @@
+"""Thin torch-tensor wrappers over the C ABI (include/tfpp.h).  torch is used for device memory and the current
+stream only; every computation happens in libtfpp.so.  No fallback: a missing library or a CPU tensor raises."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvGemmArgs, check
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_GELU = 0, 1, 2, 3
+
+TAPS_1X1 = ((0, 0, 0, 0),)
+TAPS_3X3 = tuple((kx - 1, ky - 1, 0, ky * 3 + kx) for ky in range(3) for kx in range(3))
+
+
+def taps_3x3_stride2(batch):
+  """3x3 / stride 2 / pad 1 on parity planes (tfpp_parity_split): input row 2*oy+ky-1 lives in plane (ky+1)&1 at
+  plane row oy + (-1 if ky == 0 else 0); same for columns."""
+  taps = []
+  for ky in range(3):
+    for kx in range(3):
+      py, dy = (1, -1) if ky == 0 else ((0, 0) if ky == 1 else (1, 0))
+      px, dx = (1, -1) if kx == 0 else ((0, 0) if kx == 1 else (1, 0))
+      taps.append((dx, dy, (py * 2 + px) * batch, ky * 3 + kx))
+  return tuple(taps)
+
+
+def _stream():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+  return None if t is None else t.data_ptr()
+
+
+def _dev(t, dtype=None):
+  if not t.is_cuda:
+    raise RuntimeError('carla_garage_b200 ops need CUDA tensors (there is no CPU fallback)')
+  if dtype is not None and t.dtype != dtype:
+    raise RuntimeError(f'expected {dtype}, got {t.dtype}')
+  if not t.is_contiguous():
+    raise RuntimeError('expected a contiguous tensor')
+  return t
+
+
+def pick_tile(height, width):
+  """128-pixel tile (tw, th, nb) of one conv_gemm CTA."""
+  if width >= 128:
+    return 128, 1, 1
+  tw = 1
+  while tw * 2 <= width:
+    tw *= 2
+  if tw < width:  # non power-of-two narrow maps: next power of two, masked
+    tw *= 2
+  th = 1
+  while th * 2 <= height and tw * th * 2 <= 128:
+    th *= 2
+  if th < height and tw * th * 2 <= 128:
+    th *= 2
+  return tw, th, 128 // (tw * th)
+
+
+def pick_bn(n):
+  best = None
+  for bn in range(16, 257, 16):
+    padded = -(-n // bn) * bn
+    key = (padded, -bn)
+    if best is None or key < best[0]:
+      best = (key, bn)
+  return best[1]
+
+
+def nhwc_strides(h, w, c):
+  return (h * w * c, w * c, c, 1)
+
+
+def nchw_strides(h, w, c):
+  return (c * h * w, w, 1, h * w)
+
+
+def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1, k_per_tile=None, a_c_per_ntile=0, bn=None, out=None, out_f32=False,
+              out_layout='nhwc', out_strides=None, res1=None, res1_strides=None, res2=None, res2_strides=None,
+              scale=None, shift=None, act=ACT_NONE, act_n_limit=0, stats=None, no_output=False):
+  """out[pixel, n] = act(scale[n] * sum_{tap,c} a[pixel + tap, c] * w[n, tap, c] + shift[n] + res1 + res2).
+
+  a: (Ba, H, W, C) bf16 NHWC; w: (N, taps, K) bf16.  Returns a new (B,H,W,N) bf16 / (B,N,H,W) f32 tensor unless
+  ``out`` (+ ``out_strides`` in elements (sb, sy, sx, sn)) is given.  stats = (sum, sumsq) f32 (N,) accumulators.
+  """
+  _dev(w, BF16)
+  if a_shape is None:  # contiguous NHWC tensor
+    _dev(a, BF16)
+    ab, h, wd, c = a.shape
+  else:  # strided slab inside a larger bf16 buffer: a_shape = (Ba, H, W, C), images a_batch_stride elements apart
+    ab, h, wd, c = a_shape
+  n, wt, kd = w.shape
+  b = ab if batch is None else batch
+  tw, th, nb = pick_tile(h, wd)
+  args = ConvGemmArgs()
+  args.a, args.a_batch, args.height, args.width, args.a_channels = a.data_ptr(), ab, h, wd, c
+  args.a_batch_stride = a_batch_stride
+  args.w, args.w_taps, args.w_kdim, args.n = w.data_ptr(), wt, kd, n
+  args.batch = b
+  args.k_per_tile = kd if k_per_tile is None else k_per_tile
+  args.a_c_per_ntile = a_c_per_ntile
+  args.bn = pick_bn(n) if bn is None else bn
+  args.tw, args.th, args.nb = tw, th, nb
+  args.ntaps = len(taps)
+  for i, (dx, dy, db, tw_) in enumerate(taps):
+    args.tap_dx[i], args.tap_dy[i], args.tap_db[i], args.tap_w[i] = dx, dy, db, tw_
+  if no_output:
+    out = None
+    args.out = None
+  else:
+    if out is None:
+      if out_layout == 'nhwc':
+        out = torch.empty((b, h, wd, n), dtype=F32 if out_f32 else BF16, device=a.device)
+        out_strides = nhwc_strides(h, wd, n)
+      else:
+        out = torch.empty((b, n, h, wd), dtype=F32 if out_f32 else BF16, device=a.device)
+        out_strides = nchw_strides(h, wd, n)
+    args.out = out.data_ptr()
+    args.out_f32 = int(out.dtype == F32)
+    args.o_sb, args.o_sy, args.o_sx, args.o_sn = out_strides
+  for name, r, rs in (('1', res1, res1_strides), ('2', res2, res2_strides)):
+    if r is not None:
+      if rs is None:
+        rs = nhwc_strides(h, wd, n)
+      setattr(args, f'res{name}', r.data_ptr())
+      setattr(args, f'res{name}_f32', int(r.dtype == F32))
+      for f, v in zip(('sb', 'sy', 'sx', 'sn'), rs):
+        setattr(args, f'r{name}_{f}', v)
+  args.scale = _p(scale)
+  args.shift = _p(shift)
+  args.act = act
+  args.act_n_limit = act_n_limit
+  if stats is not None:
+    args.stat_sum, args.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
+  check(_lib.load().tfpp_conv_gemm(ctypes.byref(args), _stream()), 'tfpp_conv_gemm')
+  return out
+
+
+def linear(x, w, bias=None, act=ACT_NONE, res=None, out_f32=False, out=None, row_map=None, res2=None,
+           res2_strides=None, stats=None):
+  """x: (rows, K) bf16, w: (N, K) bf16 -> (rows, N) bf16|f32.  res: same addressing as out, added before act.
+  row_map = (rows_per_group, group_stride_rows): output/res row r -> (r // rpg) * gsr + r % rpg (``out`` required)."""
+  rows, k = x.shape
+  n = w.shape[0]
+  if row_map is None:
+    a4 = x.view(1, 1, rows, k)
+    st = (0, 0, n, 1)
+    if out is None:
+      out = torch.empty((rows, n), dtype=F32 if out_f32 else BF16, device=x.device)
+  else:
+    rpg, gsr = row_map
+    a4 = x.view(rows // rpg, 1, rpg, k)
+    st = (gsr * n, 0, n, 1)
+    assert out is not None
+  conv_gemm(a4, w.view(n, 1, k), shift=bias, act=act, res1=res, res1_strides=st if res is not None else None, out=out,
+            out_strides=st, res2=res2, res2_strides=res2_strides, stats=stats)
+  return out
+
+
+def pillar_scatter(points, use_ground_plane=False, min_x=-32.0, max_x=32.0, min_y=-32.0, max_y=32.0,
+                   pixels_per_meter=4.0, hist_max=5, split_z=0.2, max_z=100.0):
+  """points (B, N, 3) f32 cuda -> (B, 1|2, 256, 256) f32 (data.py:873-906)."""
+  _dev(points, F32)
+  b, n, _ = points.shape
+  nx = int((max_x - min_x) * pixels_per_meter)
+  ny = int((max_y - min_y) * pixels_per_meter)
+  counts = torch.empty((b, 2, ny, nx), dtype=torch.int32, device=points.device)
+  out = torch.empty((b, 2 if use_ground_plane else 1, ny, nx), dtype=F32, device=points.device)
+  check(_lib.load().tfpp_pillar_scatter(points.data_ptr(), b, n, counts.data_ptr(), out.data_ptr(),
+                                        int(use_ground_plane), min_x, max_x, min_y, max_y, pixels_per_meter, hist_max,
+                                        split_z, max_z, _stream()), 'tfpp_pillar_scatter')
+  return out
+
+
+def stem_conv(x, w, in_scale=None, in_shift=None, scale=None, shift=None, act=ACT_NONE, stats=None):
+  _dev(x, F32)
+  _dev(w, F32)
+  b, cin, h, wd = x.shape
+  out = torch.empty((b, h // 2, wd // 2, 32), dtype=BF16, device=x.device)
+  check(_lib.load().tfpp_stem_conv(x.data_ptr(), w.data_ptr(), _p(in_scale), _p(in_shift), _p(scale), _p(shift), act,
+                                   out.data_ptr(), _p(stats[0]) if stats else None, _p(stats[1]) if stats else None, b,
+                                   cin, h, wd, _stream()), 'tfpp_stem_conv')
+  return out
+
+
+def bn_finalize(stat_sum, stat_sq, gamma, beta, running_mean, running_var, count, eps=1e-5, momentum=0.1,
+                save=False):
+  c = stat_sum.numel()
+  scale = torch.empty(c, dtype=F32, device=stat_sum.device)
+  shift = torch.empty_like(scale)
+  mean = torch.empty_like(scale) if save else None
+  invstd = torch.empty_like(scale) if save else None
+  check(_lib.load().tfpp_bn_finalize(stat_sum.data_ptr(), stat_sq.data_ptr(), _p(gamma), _p(beta), _p(running_mean),
+                                     _p(running_var), scale.data_ptr(), shift.data_ptr(), _p(mean), _p(invstd), c,
+                                     float(count), eps, momentum, _stream()), 'tfpp_bn_finalize')
+  return scale, shift, mean, invstd
+
+
+def scale_shift_act(x, scale=None, shift=None, act=ACT_NONE, res=None, pool_sum=None, out=None, res_scale=None,
+                    res_shift=None):
+  _dev(x, BF16)
+  b, h, w, c = x.shape
+  y = torch.empty_like(x) if out is None else out
+  check(_lib.load().tfpp_scale_shift_act(x.data_ptr(), _p(res), _p(scale), _p(shift), _p(res_scale), _p(res_shift), act,
+                                         y.data_ptr(), _p(pool_sum),
+                                         b, h * w, c, _stream()), 'tfpp_scale_shift_act')
+  return y
+
+
+def se_gate(pool_sum, hw, w1, b1, w2, b2, want_hidden=False):
+  b, c = pool_sum.shape
+  rd = w1.shape[0]
+  gate = torch.empty((b, c), dtype=F32, device=pool_sum.device)
+  hidden = torch.empty((b, rd), dtype=F32, device=pool_sum.device) if want_hidden else None
+  check(_lib.load().tfpp_se_gate(pool_sum.data_ptr(), hw, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                 gate.data_ptr(), _p(hidden), b, c, rd, _stream()), 'tfpp_se_gate')
+  return (gate, hidden) if want_hidden else gate
+
+
+def channel_scale(x, gate, out=None):
+  _dev(x, BF16)
+  b, h, w, c = x.shape
+  y = torch.empty_like(x) if out is None else out
+  check(_lib.load().tfpp_channel_scale(x.data_ptr(), gate.data_ptr(), y.data_ptr(), b, h * w, c, _stream()),
+        'tfpp_channel_scale')
+  return y
+
+
+def parity_split(x):
+  _dev(x, BF16)
+  b, h, w, c = x.shape
+  y = torch.empty((4 * b, h // 2, w // 2, c), dtype=BF16, device=x.device)
+  check(_lib.load().tfpp_parity_split(x.data_ptr(), y.data_ptr(), b, h, w, c, _stream()), 'tfpp_parity_split')
+  return y
+
+
+def avgpool_tokens(x, out, ph, pw, row0, pos_emb=None):
+  """x (B,H,W,C) bf16 -> rows [row0, row0+ph*pw) of out (B, rows, C) f32|bf16 (+ pos_emb (rows, C) f32)."""
+  _dev(x, BF16)
+  b, h, w, c = x.shape
+  check(_lib.load().tfpp_avgpool_tokens(x.data_ptr(), _p(pos_emb), out.data_ptr(), int(out.dtype == F32), b, h, w, c,
+                                        ph, pw, out.shape[1], row0, _stream()), 'tfpp_avgpool_tokens')
+  return out
+
+
+def bilinear(src, batch, sh, sw, dh, dw, channels, src_batch_stride=None, src_row_stride=None, add=None, src_offset=0):
+  """Resize a (B,sh,sw,C) slab (f32/bf16; element strides) to NHWC bf16 (B,dh,dw,C) (+ add)."""
+  if src_batch_stride is None:
+    src_batch_stride = sh * sw * channels
+  if src_row_stride is None:
+    src_row_stride = channels
+  out = torch.empty((batch, dh, dw, channels), dtype=BF16, device=src.device)
+  ptr = src.data_ptr() + src_offset * src.element_size()
+  check(_lib.load().tfpp_bilinear(ptr, int(src.dtype == F32), src_batch_stride, src_row_stride, _p(add), out.data_ptr(),
+                                  batch, sh, sw, dh, dw, channels, _stream()), 'tfpp_bilinear')
+  return out
+
+
+def bilinear_nchw_mask(src, channels, dh, dw, mask=None):
+  _dev(src, BF16)
+  b, sh, sw, cs = src.shape
+  out = torch.empty((b, channels, dh, dw), dtype=F32, device=src.device)
+  check(_lib.load().tfpp_bilinear_nchw_mask(src.data_ptr(), _p(mask), out.data_ptr(), b, sh, sw, cs, channels, dh, dw,
+                                            _stream()), 'tfpp_bilinear_nchw_mask')
+  return out
+
+
+def nchw_to_nhwc(x):
+  _dev(x, F32)
+  b, c, h, w = x.shape
+  y = torch.empty((b, h, w, c), dtype=BF16, device=x.device)
+  check(_lib.load().tfpp_nchw_f32_to_nhwc_bf16(x.data_ptr(), y.data_ptr(), b, c, h * w, _stream()), 'nchw_to_nhwc')
+  return y
+
+
+def nhwc_to_nchw(x):
+  _dev(x, BF16)
+  b, h, w, c = x.shape
+  y = torch.empty((b, c, h, w), dtype=F32, device=x.device)
+  check(_lib.load().tfpp_nhwc_bf16_to_nchw_f32(x.data_ptr(), y.data_ptr(), b, c, h * w, _stream()), 'nhwc_to_nchw')
+  return y
+
+
+def layernorm(x, gamma, beta, want_bf16=True, want_f32=False, eps=1e-5, save=False):
+  rows, c = x.shape
+  yb = torch.empty((rows, c), dtype=BF16, device=x.device) if want_bf16 else None
+  yf = torch.empty((rows, c), dtype=F32, device=x.device) if want_f32 else None
+  mean = torch.empty(rows, dtype=F32, device=x.device) if save else None
+  rstd = torch.empty(rows, dtype=F32, device=x.device) if save else None
+  check(_lib.load().tfpp_layernorm(x.data_ptr(), int(x.dtype == F32), gamma.data_ptr(), beta.data_ptr(), _p(yb), _p(yf),
+                                   _p(mean), _p(rstd), rows, c, eps, _stream()), 'tfpp_layernorm')
+  return yb, yf, mean, rstd
+
+
+def fusion_attn(qkv, batch, tokens, channels, heads):
+  _dev(qkv, BF16)
+  out = torch.empty((batch * tokens, channels), dtype=BF16, device=qkv.device)
+  check(_lib.load().tfpp_fusion_attn(qkv.data_ptr(), out.data_ptr(), batch, tokens, channels, heads, _stream()),
+        'tfpp_fusion_attn')
+  return out
+
+
+def small_mha(q, k, v, batch, heads, tq, tk, head_dim, q_strides, k_strides, v_strides, q_off=0, k_off=0, v_off=0):
+  """bf16 views given as (tensor, element offset, (batch stride, row stride)); returns (B*tq, heads*head_dim) bf16."""
+  d = heads * head_dim
+  out = torch.empty((batch * tq, d), dtype=BF16, device=q.device)
+  check(_lib.load().tfpp_small_mha(q.data_ptr() + 2 * q_off, q_strides[0], q_strides[1], k.data_ptr() + 2 * k_off,
+                                   k_strides[0], k_strides[1], v.data_ptr() + 2 * v_off, v_strides[0], v_strides[1],
+                                   out.data_ptr(), tq * d, d, batch, heads, tq, tk, head_dim, _stream()),
+        'tfpp_small_mha')
+  return out
+
+
+def extra_sensor_token(ego_vel, command, vel_mean, vel_var, use_batch_stats, running_mean, running_var, w0, b0, w1, b1,
+                       pos, mem_bf16, mem_f32, rows_per_batch, row):
+  b = ego_vel.shape[0]
+  check(_lib.load().tfpp_extra_sensor_token(ego_vel.data_ptr(), command.data_ptr(), float(vel_mean), float(vel_var),
+                                            int(use_batch_stats), _p(running_mean), _p(running_var), w0.data_ptr(),
+                                            b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), pos.data_ptr(), _p(mem_bf16),
+                                            _p(mem_f32), b, command.shape[1], w0.shape[0], w1.shape[0], rows_per_batch,
+                                            row, _stream()), 'tfpp_extra_sensor_token')
+
+
+def planner_head(joined, target_point, w_enc, b_enc, w_ih, w_hh, b_ih, b_hh, w_dec, b_dec, w_ts0, b_ts0, w_ts1, b_ts1,
+                 want_h=False):
+  _dev(joined, F32)
+  b, nq, d = joined.shape
+  n_wp = nq - 1
+  hs = w_hh.shape[1]
+  n_speed = w_ts1.shape[0]
+  cp = torch.empty((b, n_wp, 2), dtype=F32, device=joined.device)
+  ts = torch.empty((b, n_speed), dtype=F32, device=joined.device)
+  h_all = torch.empty((b, n_wp, hs), dtype=F32, device=joined.device) if want_h else None
+  check(_lib.load().tfpp_planner_head(joined.data_ptr(), target_point.data_ptr(), w_enc.data_ptr(), b_enc.data_ptr(),
+                                      w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
+                                      w_dec.data_ptr(), b_dec.data_ptr(), w_ts0.data_ptr(), b_ts0.data_ptr(),
+                                      w_ts1.data_ptr(), b_ts1.data_ptr(), cp.data_ptr(), ts.data_ptr(), _p(h_all), b,
+                                      n_wp, d, hs, n_speed, _stream()), 'tfpp_planner_head')
+  return (cp, ts, h_all) if want_h else (cp, ts)
+
+
+def decode_heatmap(heat, wh, offset, yaw_cls, yaw_res, k=100, img_h=256, img_w=256):
+  """NCHW f32 maps (possibly channel-slice views with a batch stride) -> (B, k, 9) f32 (center_net.py:172-237)."""
+  b, n_cls, h, w = heat.shape
+  out = torch.empty((b, k, 9), dtype=F32, device=heat.device)
+  for t in (heat, wh, offset, yaw_cls, yaw_res):
+    if t.dtype != F32 or t.stride()[1:] != (h * w, w, 1):
+      raise RuntimeError('decode_heatmap expects NCHW f32 maps with contiguous channel planes')
+  check(_lib.load().tfpp_decode_heatmap(heat.data_ptr(), heat.stride(0), wh.data_ptr(), wh.stride(0), offset.data_ptr(),
+                                        offset.stride(0), yaw_cls.data_ptr(), yaw_cls.stride(0), yaw_res.data_ptr(),
+                                        yaw_res.stride(0), out.data_ptr(), b, n_cls, h, w, yaw_cls.shape[1], k,
+                                        float(img_w / w), float(img_h / h), _stream()), 'tfpp_decode_heatmap')
+  return out
+
+
+# ---------------------------------------------------------------------------------------------- weight packing
+# (load-time plumbing: layout changes of parameters, no activations involved)
+def pack_conv_weight(w):
+  """(Cout, Cin, kh, kw) f32 -> (Cout, kh*kw, Cin) bf16."""
+  co, ci, kh, kw = w.shape
+  return w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(BF16).contiguous()
+
+
+def pack_grouped_conv_weight(w, group_width=24, groups_per_tile=2):
+  """(Cout, gw, 3, 3) f32 grouped conv -> (Cout, 9, 64) bf16, dense within each 48-channel n-tile: column j of row n
+  multiplies input channel (n // 48) * 48 + j; zero outside the row's own group."""
+  co, gw, kh, kw = w.shape
+  assert gw == group_width and kh == 3 and kw == 3
+  tile = group_width * groups_per_tile
+  out = torch.zeros((co, 9, 64), dtype=F32, device=w.device)
+  wt = w.detach().permute(0, 2, 3, 1).reshape(co, 9, gw)
+  n = torch.arange(co, device=w.device)
+  base = ((n % tile) // gw) * gw  # column offset of the row's group inside its tile
+  idx = base[:, None] + torch.arange(gw, device=w.device)[None, :]
+  out.scatter_(2, idx[:, None, :].expand(co, 9, gw), wt)
+  return out.to(BF16).contiguous()

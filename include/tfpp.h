@@ -1,0 +1,161 @@
+/* C ABI of libtfpp.so — the B200 (sm_100a) kernels under the TransFuser++ nn.Module surface.
+ *
+ * The reference (autonomousvision/carla_garage) has no native code and no FFI: its hot path is a
+ * chain of torch library dispatches inside team_code/{transfuser,model,center_net}.py.  The drop-in boundary a user
+ * sees is therefore the Python class surface (carla_garage_b200.nn mirrors it); this header is the boundary UNDER
+ * it: plain pointers + sizes + a CUDA stream, int return code (0 = ok, see tfpp_last_error()), no torch types, no
+ * allocation, no global mutable state except the last-error string (thread-local).  Every entry point names the
+ * reference call site(s) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Layout conventions: feature maps are NHWC bf16 (B,H,W,C contiguous); token matrices are (rows, C) bf16 or f32;
+ * user-facing model inputs/outputs stay NCHW f32 like the reference's.
+ */
+#ifndef TFPP_H_
+#define TFPP_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tfpp_stream_t; /* cudaStream_t */
+
+const char* tfpp_last_error(void);
+int tfpp_abi_version(void);
+
+/* ---- K1: LiDAR points -> BEV histogram.  team_code/data.py:873-906 (np.histogramdd x2, clip 5, /5, .T) ----
+ * points: (B, n_points, 3) f32 device; counts: (B, 2, 256, 256) u32 workspace (zeroed inside);
+ * out: (B, C, H, W) f32, C = 2 if use_ground_plane else 1, index [b][ch][y_bin][x_bin]. */
+int tfpp_pillar_scatter(const float* points, int batch, int n_points, uint32_t* counts, float* out,
+                        int use_ground_plane, float min_x, float max_x, float min_y, float max_y,
+                        float pixels_per_meter, int hist_max, float split_z, float max_z, tfpp_stream_t stream);
+
+/* ---- tcgen05 implicit-GEMM convolution / linear layer --------------------------------------------------------
+ * out[pixel, n] = act( scale[n] * sum_{tap,c} A[pixel + shift(tap), c0(n) + c] * Wt[n, tap, c] + shift[n]
+ *                      + res1[pixel, n] + res2[pixel, n] )
+ * Replaces: timm RegNet 1x1 / grouped 3x3 convs (transfuser.py:216-219), nn.Linear in SelfAttention/Block
+ * (transfuser.py:352-359,391-396), 1x1 channel maps (transfuser.py:233,237), FPN + decoder + head convs
+ * (transfuser.py:131-137, transfuser_utils.py:675-704, model.py:75-90,148, center_net.py:43-47), decoder
+ * projections (model.py:137-143).  A is NHWC bf16 (a_batch, H, W, a_channels); weights are bf16
+ * (N, taps, w_kdim) K-major.  Pixel tiles are th x tw x nb = 128 rows. */
+typedef struct {
+  const void* a;
+  int a_batch, height, width, a_channels; /* A tensor extents (a_batch may be 4*batch for stride-2 parity planes) */
+  long long a_batch_stride;               /* elements between A images; 0 = contiguous (height*width*a_channels) */
+  const void* w;
+  int w_taps, w_kdim, n; /* weights (n, w_taps, w_kdim) bf16 */
+  int batch;             /* output batch */
+  int k_per_tile;        /* input channels reduced per n-tile (dense: a_channels; grouped: <= 64) */
+  int a_c_per_ntile;     /* A channel offset added per n-tile (0 dense, 48 grouped) */
+  int bn;                /* n tile: multiple of 16, <= 256 */
+  int tw, th, nb;        /* pixel tile */
+  int ntaps;
+  int tap_dx[9], tap_dy[9], tap_db[9], tap_w[9];
+  void* out;
+  int out_f32;
+  long long o_sb, o_sy, o_sx, o_sn; /* element strides of out */
+  const void* res1;
+  int res1_f32;
+  long long r1_sb, r1_sy, r1_sx, r1_sn;
+  const void* res2;
+  int res2_f32;
+  long long r2_sb, r2_sy, r2_sx, r2_sn;
+  const float* scale; /* per output channel, may be NULL (=1) */
+  const float* shift; /* per output channel, may be NULL (=0) */
+  int act;            /* 0 none, 1 relu, 2 sigmoid, 3 gelu(erf) */
+  int act_n_limit;    /* activation applies to channels < act_n_limit (0 = all) */
+  float* stat_sum;    /* optional per-channel sum / sum of squares of the raw accumulator (BatchNorm batch stats) */
+  float* stat_sq;
+} tfpp_conv_gemm_args;
+
+int tfpp_conv_gemm(const tfpp_conv_gemm_args* args, tfpp_stream_t stream);
+
+/* ---- stem conv: timm RegNet stem ConvNormAct(in,32,k3,s2,p1) fused with normalize_imagenet ---------------------
+ * (team_code/transfuser.py:146-149,164-167; transfuser_utils.py:542-551).  x: NCHW f32 (B,cin<=3,H,W), w: f32
+ * (32,cin,3,3); in_scale/in_shift: per-input-channel affine applied before zero padding (NULL = identity);
+ * scale/shift: per-output-channel affine (folded eval BatchNorm) + act; out: NHWC bf16 (B,H/2,W/2,32);
+ * stat_sum/stat_sq (32 f32 each, optional): batch statistics of the raw conv output (training BatchNorm). */
+int tfpp_stem_conv(const float* x, const float* w, const float* in_scale, const float* in_shift, const float* scale,
+                   const float* shift, int act, void* out, float* stat_sum, float* stat_sq, int batch, int cin,
+                   int height, int width, tfpp_stream_t stream);
+
+/* ---- BatchNorm2d (training semantics; timm BatchNormAct2d) ----------------------------------------------------
+ * sum / sq: per-channel sums from the conv epilogue; writes the affine (scale, shift) the apply pass uses, the saved
+ * mean / invstd for backward, and updates running stats (momentum 0.1, unbiased variance). */
+int tfpp_bn_finalize(const float* sum, const float* sq, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd,
+                     int channels, float count, float eps, float momentum, tfpp_stream_t stream);
+
+/* y = act(x * scale[c] + shift[c] (+ res)), NHWC bf16; pool_sum (B,C) f32 optional: per-sample channel sums of y
+ * (the squeeze of timm SEModule).  Any of scale/shift (together) and res may be NULL; res_scale/res_shift (together,
+ * optional) apply a per-channel affine to res first (the BatchNorm of the RegNet downsample branch). */
+int tfpp_scale_shift_act(const void* x, const void* res, const float* scale, const float* shift, const float* res_scale,
+                         const float* res_shift, int act, void* y, float* pool_sum, int batch, int hw, int channels,
+                         tfpp_stream_t stream);
+
+/* timm SEModule excite: gate = sigmoid(fc2(relu(fc1(pool_sum / hw)))); w1 (rd,C), w2 (C,rd) f32. */
+int tfpp_se_gate(const float* pool_sum, int hw, const float* w1, const float* b1, const float* w2, const float* b2,
+                 float* gate, float* hidden, int batch, int channels, int rd, tfpp_stream_t stream);
+
+/* y[b,p,c] = x[b,p,c] * gate[b,c] (SE scale). */
+int tfpp_channel_scale(const void* x, const float* gate, void* y, int batch, int hw, int channels, tfpp_stream_t stream);
+
+/* (B,H,W,C) -> (4B,H/2,W/2,C) parity planes (plane q=(y&1)*2+(x&1) at batch q*B+b): stride-2 convs become taps. */
+int tfpp_parity_split(const void* x, void* y, int batch, int height, int width, int channels, tfpp_stream_t stream);
+
+/* AdaptiveAvgPool2d -> token rows (+pos_emb): transfuser.py:230-231,317-325. out rows [row0, row0+ph*pw) of
+ * (B, rows_per_batch, C), f32 or bf16. */
+int tfpp_avgpool_tokens(const void* x, const float* pos_emb, void* out, int out_f32, int batch, int height, int width,
+                        int channels, int ph, int pw, int rows_per_batch, int row0, tfpp_stream_t stream);
+
+/* F.interpolate(bilinear, align_corners=False) of a (B,sh,sw,C) source (f32 or bf16, arbitrary batch/row element
+ * strides) to NHWC bf16 (B,dh,dw,C), optionally + add (transfuser.py:239-255,119-123; transfuser_utils.py:699-701). */
+int tfpp_bilinear(const void* src, int src_f32, long long src_batch_stride, long long src_row_stride, const void* add,
+                  void* out, int batch, int sh, int sw, int dh, int dw, int channels, tfpp_stream_t stream);
+
+/* bev_semantic_decoder tail: resize NHWC bf16 (B,sh,sw,src_channels) -> NCHW f32 (B,channels,dh,dw) * mask(dh,dw)
+ * (model.py:88-90,385). */
+int tfpp_bilinear_nchw_mask(const void* src, const float* mask, float* out, int batch, int sh, int sw, int src_channels,
+                            int channels, int dh, int dw, tfpp_stream_t stream);
+
+int tfpp_nchw_f32_to_nhwc_bf16(const float* x, void* y, int batch, int channels, int hw, tfpp_stream_t stream);
+int tfpp_nhwc_bf16_to_nchw_f32(const void* x, float* y, int batch, int channels, int hw, tfpp_stream_t stream);
+
+/* ---- token-side kernels ---------------------------------------------------------------------------------------
+ * nn.LayerNorm (transfuser.py:288,388-389; model.py:123,137-143): x f32 or bf16 (rows,C) -> bf16 and/or f32. */
+int tfpp_layernorm(const void* x, int x_f32, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                   float* save_mean, float* save_rstd, int rows, int channels, float eps, tfpp_stream_t stream);
+
+/* SelfAttention core (transfuser.py:367-376): qkv (B,T,3C) bf16 [q|k|v] -> out (B,T,C) bf16. T<=320, T%16==0. */
+int tfpp_fusion_attn(const void* qkv, void* out, int batch, int tokens, int channels, int heads, tfpp_stream_t stream);
+
+/* nn.MultiheadAttention core of the planner decoder (model.py:137-143): bf16 row-strided q/k/v views. */
+int tfpp_small_mha(const void* q, long long q_sb, long long q_sr, const void* k, long long k_sb, long long k_sr,
+                   const void* v, long long v_sb, long long v_sr, void* out, long long o_sb, long long o_sr, int batch,
+                   int heads, int tq, int tk, int head_dim, tfpp_stream_t stream);
+
+/* extra-sensor memory token (model.py:308-319): BatchNorm1d(1,affine=False)(ego_vel) ++ command -> MLP -> +pos. */
+int tfpp_extra_sensor_token(const float* ego_vel, const float* command, float vel_mean, float vel_var,
+                            int use_batch_stats, float* running_mean, float* running_var, const float* w0,
+                            const float* b0, const float* w1, const float* b1, const float* pos, void* mem_bf16,
+                            float* mem_f32, int batch, int n_cmd, int hidden, int d_model, int rows_per_batch, int row,
+                            tfpp_stream_t stream);
+
+/* GRUWaypointsPredictorInterFuser + target_speed_network (model.py:118-119,357-358,857-867). joined (B,n_wp+1,D) f32. */
+int tfpp_planner_head(const float* joined, const float* target_point, const float* w_enc, const float* b_enc,
+                      const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* w_dec,
+                      const float* b_dec, const float* w_ts0, const float* b_ts0, const float* w_ts1,
+                      const float* b_ts1, float* checkpoints, float* speed_logits, float* h_all, int batch, int n_wp,
+                      int d_model, int hidden, int n_speed, tfpp_stream_t stream);
+
+/* LidarCenterNetHead.decode_heatmap (center_net.py:172-237): NCHW f32 maps (batch strides in elements) ->
+ * (B,k,9) [x,y,w,h,yaw,vel,brake,cls,score]. */
+int tfpp_decode_heatmap(const float* heat, long long heat_sb, const float* wh, long long wh_sb, const float* offset,
+                        long long off_sb, const float* yaw_cls, long long ycls_sb, const float* yaw_res,
+                        long long yres_sb, float* out, int batch, int n_cls, int height, int width, int n_bins, int k,
+                        float width_ratio, float height_ratio, tfpp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFPP_H_ */

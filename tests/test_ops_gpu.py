@@ -1,0 +1,263 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI (carla_garage_b200.ops), against
+fp32 torch restatements of the same op evaluated on the bf16-rounded operands the kernel sees."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+@pytest.fixture(scope='module')
+def ops():
+  if not torch.cuda.is_available():
+    pytest.skip('no CUDA device')
+  from carla_garage_b200 import ops as o
+  return o
+
+
+def rel(a, b):
+  a, b = a.double().cpu(), b.double().cpu()
+  return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+  g = torch.Generator().manual_seed(seed)
+  return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def bf(x):
+  return x.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def test_pillar_scatter_bit_exact(ops):
+  from carla_garage_b200 import synth
+  from oracle import tfpp_oracle as orc
+  g = np.load(os.path.join(GOLDEN, 'pillar_scatter.npz'))
+  pts = synth.make_point_clouds(2, seed=7)
+  for gp in (0, 1):
+    out = ops.pillar_scatter(pts.cuda(), use_ground_plane=bool(gp)).cpu().numpy()
+    for b in range(2):
+      want = g[f'cloud{b}_gp{gp}'].astype(np.float32) / 5.0
+      assert np.array_equal(out[b], want)
+      assert np.array_equal(out[b], orc.lidar_to_histogram_features(pts[b].numpy(), bool(gp)))
+    edge = torch.from_numpy(g['edge_points']).cuda()[None]
+    out = ops.pillar_scatter(edge, use_ground_plane=bool(gp)).cpu().numpy()[0]
+    assert np.array_equal(out, g[f'edge_gp{gp}'].astype(np.float32) / 5.0)
+    empty = torch.zeros((1, 0, 3), device='cuda')
+    out = ops.pillar_scatter(empty, use_ground_plane=bool(gp)).cpu().numpy()
+    assert out.shape == (1, 1 + gp, 256, 256) and not out.any()
+  # size-independent property at full size: total mass <= points, every value is k/5
+  big = synth.make_point_clouds(8, seed=99).cuda()
+  out = ops.pillar_scatter(big, use_ground_plane=True)
+  vals = torch.unique(torch.round(out * 5))
+  assert set(vals.tolist()) <= {0.0, 1.0, 2.0, 3.0, 4.0, 5.0}
+  assert float(out.sum()) * 5 <= 8 * synth.N_POINTS
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 GEMM
+@pytest.mark.parametrize('rows,k,n', [(128, 64, 16), (256, 128, 64), (320, 72, 216), (1000, 216, 72), (640, 1512, 576),
+                                      (352, 256, 2048), (64, 2048, 256), (37, 576, 1512)])
+def test_linear_shapes(ops, rows, k, n):
+  x, w, b = bf(rnd(rows, k, seed=1)), bf(rnd(n, k, seed=2, scale=k**-0.5)), rnd(n, seed=3)
+  want = x.float() @ w.float().t() + b
+  got = ops.linear(x, w, bias=b, out_f32=True)
+  torch.cuda.synchronize()
+  assert rel(got, want) < 2e-3
+  got = ops.linear(x, w, bias=b, act=ops.ACT_RELU)
+  assert rel(got.float(), F.relu(want)) < 6e-3
+
+
+def test_linear_residual_rowmap_stats(ops):
+  rows, k, n = 4 * 64, 216, 72
+  x, w = bf(rnd(rows, k, seed=4)), bf(rnd(n, k, seed=5, scale=k**-0.5))
+  res = rnd(4 * 320, n, seed=6)
+  out = torch.zeros(4 * 320, n, device='cuda')
+  pos = rnd(320, n, seed=7)
+  ops.linear(x, w, res=res, out=out, row_map=(64, 320), res2=pos[256:], res2_strides=(0, 0, n, 1))
+  want = torch.zeros_like(out)
+  y = (x.float() @ w.float().t()).view(4, 64, n)
+  want.view(4, 320, n)[:, :64] = y + res.view(4, 320, n)[:, :64] + pos[256:]
+  assert rel(out, want) < 2e-3
+  s, q = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+  ops.linear(x, w, stats=(s, q), out_f32=True)
+  yy = x.float() @ w.float().t()
+  assert rel(s, yy.sum(0)) < 1e-3 and rel(q, (yy * yy).sum(0)) < 1e-3
+
+
+def conv_ref(x_nhwc, w, stride=1, groups=1):
+  return F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w.float(), None, stride=stride, padding=w.shape[-1] // 2,
+                  groups=groups).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize('b,h,w,cin,cout', [(2, 8, 32, 1512, 128), (2, 64, 64, 64, 320), (1, 16, 64, 32, 32),
+                                            (3, 8, 8, 72, 64), (1, 32, 128, 128, 7)])
+def test_conv3x3(ops, b, h, w, cin, cout):
+  x = bf(rnd(b, h, w, cin, seed=8))
+  wt = rnd(cout, cin, 3, 3, seed=9, scale=(9 * cin)**-0.5)
+  bias = rnd(cout, seed=10)
+  wp = ops.pack_conv_weight(wt)
+  got = ops.conv_gemm(x, wp, taps=ops.TAPS_3X3, shift=bias, act=ops.ACT_RELU)
+  want = F.relu(conv_ref(x, wp.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)) + bias)
+  assert rel(got.float(), want) < 6e-3
+  got = ops.conv_gemm(x, wp, taps=ops.TAPS_3X3, shift=bias, out_layout='nchw', out_f32=True)
+  want = (conv_ref(x, wp.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)) + bias).permute(0, 3, 1, 2)
+  assert rel(got, want) < 2e-3
+
+
+@pytest.mark.parametrize('b,h,w,c', [(2, 16, 64, 72), (1, 32, 32, 216), (2, 8, 8, 1512), (1, 8, 32, 576)])
+def test_grouped_conv(ops, b, h, w, c):
+  x = bf(rnd(b, h, w, c, seed=11))
+  wt = rnd(c, 24, 3, 3, seed=12, scale=(9 * 24)**-0.5)
+  wp = ops.pack_grouped_conv_weight(wt)
+  got = ops.conv_gemm(x, wp, taps=ops.TAPS_3X3, k_per_tile=48, a_c_per_ntile=48, bn=48)
+  want = conv_ref(x, bf(wt), groups=c // 24)
+  assert rel(got.float(), want) < 6e-3
+  # stride 2 through parity planes
+  xs = ops.parity_split(x)
+  got = ops.conv_gemm(xs, wp, batch=b, taps=ops.taps_3x3_stride2(b), k_per_tile=48, a_c_per_ntile=48, bn=48)
+  want = conv_ref(x, bf(wt), stride=2, groups=c // 24)
+  assert got.shape == want.shape
+  assert rel(got.float(), want) < 6e-3
+  # 1x1 stride 2 (downsample) reads parity plane 0
+  w1 = bf(rnd(40, c, seed=13, scale=c**-0.5))
+  got = ops.conv_gemm(xs, w1.view(40, 1, c), batch=b)
+  want = x.float()[:, ::2, ::2] @ w1.float().t()
+  assert rel(got.float(), want) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------ feature-map kernels
+def test_stem_bn_se(ops):
+  b = 2
+  x = torch.randint(0, 256, (b, 3, 32, 64), generator=torch.Generator().manual_seed(1)).float().cuda()
+  w = rnd(32, 3, 3, 3, seed=14, scale=0.2)
+  a = torch.tensor([1 / (255 * 0.229), 1 / (255 * 0.224), 1 / (255 * 0.225)]).cuda()
+  s = torch.tensor([-0.485 / 0.229, -0.456 / 0.224, -0.406 / 0.225]).cuda()
+  st = (torch.zeros(32, device='cuda'), torch.zeros(32, device='cuda'))
+  raw = ops.stem_conv(x, w, a, s, stats=st)
+  xn = x * a.view(1, 3, 1, 1) + s.view(1, 3, 1, 1)
+  want = F.conv2d(xn, w, None, stride=2, padding=1)
+  assert rel(raw.float().permute(0, 3, 1, 2), want) < 4e-3
+  assert rel(st[0], want.sum((0, 2, 3))) < 1e-3 and rel(st[1], (want * want).sum((0, 2, 3))) < 1e-3
+  gamma, beta = rnd(32, seed=15).abs() + 0.5, rnd(32, seed=16)
+  rm, rv = torch.zeros(32, device='cuda'), torch.ones(32, device='cuda')
+  cnt = b * 16 * 32
+  scale, shift, mean, invstd = ops.bn_finalize(st[0], st[1], gamma, beta, rm, rv, cnt, save=True)
+  rm2, rv2 = torch.zeros(32, device='cuda'), torch.ones(32, device='cuda')
+  want_bn = F.batch_norm(want, rm2, rv2, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+  assert rel(rm, rm2) < 1e-3 and rel(rv, rv2) < 1e-3
+  pool = torch.zeros(b, 32, device='cuda')
+  y = ops.scale_shift_act(raw, scale, shift, ops.ACT_RELU, pool_sum=pool)
+  assert rel(y.float().permute(0, 3, 1, 2), F.relu(want_bn)) < 1e-2
+  assert rel(pool / (16 * 32), y.float().mean((1, 2))) < 1e-3
+  w1, b1, w2, b2 = rnd(8, 32, seed=17), rnd(8, seed=18), rnd(32, 8, seed=19), rnd(32, seed=20)
+  gate = ops.se_gate(pool, 16 * 32, w1, b1, w2, b2)
+  m = y.float().mean((1, 2))
+  want_gate = torch.sigmoid(F.relu(m @ w1.t() + b1) @ w2.t() + b2)
+  assert rel(gate, want_gate) < 1e-4
+  z = ops.channel_scale(y, gate)
+  assert rel(z.float(), y.float() * want_gate[:, None, None, :]) < 5e-3
+  # eval-mode fused path
+  y2 = ops.stem_conv(x, w, a, s, scale=scale, shift=shift, act=ops.ACT_RELU)
+  assert rel(y2.float(), y.float()) < 1e-2
+
+
+def test_pool_bilinear_layout(ops):
+  b, h, w, c = 2, 16, 64, 72
+  x = bf(rnd(b, h, w, c, seed=21))
+  pos = rnd(320, c, seed=22)
+  tok = torch.zeros(b, 320, c, device='cuda')
+  ops.avgpool_tokens(x, tok, 8, 32, 0, pos_emb=pos)
+  want = F.adaptive_avg_pool2d(x.float().permute(0, 3, 1, 2), (8, 32)).permute(0, 2, 3, 1).reshape(b, 256, c) + pos[:256]
+  assert rel(tok[:, :256], want) < 1e-5
+  up = ops.bilinear(tok, b, 8, 32, h, w, c, src_batch_stride=320 * c, src_row_stride=c, add=x)
+  want = x.float() + F.interpolate(tok[:, :256].view(b, 8, 32, c).permute(0, 3, 1, 2), size=(h, w), mode='bilinear',
+                                   align_corners=False).permute(0, 2, 3, 1)
+  assert rel(up.float(), want) < 5e-3
+  up2 = ops.bilinear(x, b, h, w, h * 4, w * 4, c)
+  want = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=4, mode='bilinear',
+                       align_corners=False).permute(0, 2, 3, 1)
+  assert rel(up2.float(), want) < 5e-3
+  mask = (rnd(64, 256, seed=23) > 0).float()
+  o = ops.bilinear_nchw_mask(x, 11, 64, 256, mask)
+  want = F.interpolate(x.float().permute(0, 3, 1, 2)[:, :11], size=(64, 256), mode='bilinear',
+                       align_corners=False) * mask
+  assert rel(o, want) < 1e-5
+  xn = rnd(b, c, h, w, seed=24)
+  assert rel(ops.nhwc_to_nchw(ops.nchw_to_nhwc(xn)), bf(xn).float()) == 0.0
+
+
+def test_layernorm_attention(ops):
+  rows, c = 640, 216
+  x = rnd(rows, c, seed=25)
+  g, bt = rnd(c, seed=26).abs() + 0.5, rnd(c, seed=27)
+  yb, yf, _, _ = ops.layernorm(x, g, bt, want_f32=True)
+  want = F.layer_norm(x, (c,), g, bt, 1e-5)
+  assert rel(yf, want) < 1e-5 and rel(yb.float(), want) < 5e-3
+  for c in (72, 216, 576, 1512):
+    b, t, heads = 2, 320, 4
+    qkv = bf(rnd(b, t, 3 * c, seed=28))
+    out = ops.fusion_attn(qkv, b, t, c, heads).view(b, t, c)
+    q, k, v = [u.float().view(b, t, heads, c // heads).transpose(1, 2) for u in qkv.split(c, dim=2)]
+    att = F.softmax(q @ k.transpose(-2, -1) / math.sqrt(c // heads), dim=-1)
+    want = (att @ v).transpose(1, 2).reshape(b, t, c)
+    assert rel(out.float(), want) < 1e-2, c
+
+
+def test_planner_kernels(ops):
+  b, d = 3, 256
+  q, mem = bf(rnd(b, 11, d, seed=29)), bf(rnd(b, 65, 2 * d, seed=30))
+  out = ops.small_mha(q, mem, mem, b, 8, 11, 65, 32, (11 * d, d), (65 * 2 * d, 2 * d), (65 * 2 * d, 2 * d), v_off=d)
+  qh = q.float().view(b, 11, 8, 32).transpose(1, 2)
+  kh = mem.float()[..., :d].reshape(b, 65, 8, 32).transpose(1, 2)
+  vh = mem.float()[..., d:].reshape(b, 65, 8, 32).transpose(1, 2)
+  want = (F.softmax(qh @ kh.transpose(-2, -1) / math.sqrt(32), -1) @ vh).transpose(1, 2).reshape(b * 11, d)
+  assert rel(out.float(), want) < 5e-3
+  # extra sensor token (eval and batch-stat modes)
+  vel, cmd = rnd(b, 1, seed=31).abs() * 4, F.one_hot(torch.tensor([0, 3, 5]), 6).float().cuda()
+  w0, b0, w1, b1, pos = rnd(128, 7, seed=32), rnd(128, seed=33), rnd(256, 128, seed=34, scale=0.1), rnd(256, seed=35), \
+      rnd(1, 256, seed=36)
+  mem_f = torch.zeros(b, 65, 256, device='cuda')
+  ops.extra_sensor_token(vel, cmd, 2.0, 1.5, False, None, None, w0, b0, w1, b1, pos, None, mem_f, 65, 64)
+  vn = (vel - 2.0) / math.sqrt(1.5 + 1e-5)
+  want = F.relu(F.relu(torch.cat([vn, cmd], 1) @ w0.t() + b0) @ w1.t() + b1) + pos
+  assert rel(mem_f[:, 64], want) < 1e-5
+  ops.extra_sensor_token(vel, cmd, 0.0, 1.0, True, None, None, w0, b0, w1, b1, pos, None, mem_f, 65, 64)
+  vn = (vel - vel.mean()) / torch.sqrt(vel.var(unbiased=False) + 1e-5)
+  want = F.relu(F.relu(torch.cat([vn, cmd], 1) @ w0.t() + b0) @ w1.t() + b1) + pos
+  assert rel(mem_f[:, 64], want) < 1e-5
+  # GRU + target speed vs torch.nn.GRU
+  gru = torch.nn.GRU(256, 64, batch_first=True).cuda()
+  enc, dec = torch.nn.Linear(2, 64).cuda(), torch.nn.Linear(64, 2).cuda()
+  ts = torch.nn.Sequential(torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 4)).cuda()
+  joined, tp = rnd(b, 11, 256, seed=37), rnd(b, 2, seed=38) * 10
+  with torch.no_grad():
+    o, _ = gru(joined[:, :10], enc(tp).unsqueeze(0))
+    want_cp = torch.cumsum(dec(o), 1)
+    want_ts = ts(joined[:, 10])
+  cp, tsl = ops.planner_head(joined, tp, enc.weight, enc.bias, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0,
+                             gru.bias_hh_l0, dec.weight, dec.bias, ts[0].weight, ts[0].bias, ts[2].weight, ts[2].bias)
+  assert rel(cp, want_cp) < 1e-4 and rel(tsl, want_ts) < 1e-4
+
+
+def test_decode_heatmap(ops):
+  from oracle import tfpp_oracle as orc
+  b = 3
+  maps = torch.rand(b, 21, 64, 64, generator=torch.Generator().manual_seed(3)).cuda()
+  maps[:, 20] -= 0.5
+  heat, wh, off, ycls, yres = maps[:, 0:4], maps[:, 4:6], maps[:, 6:8], maps[:, 8:20], maps[:, 20:21]
+  got = ops.decode_heatmap(heat, wh, off, ycls, yres).cpu()
+  want = orc.decode_heatmap(heat.cpu().contiguous(), wh.cpu().contiguous(), off.cpu().contiguous(),
+                            ycls.cpu().contiguous(), yres.cpu().contiguous())
+  assert got.shape == (b, 100, 9)
+  assert torch.equal(got[..., 8], want[..., 8])          # scores bit-exact
+  assert torch.equal(got[..., 7], want[..., 7])          # classes
+  assert rel(got, want) < 1e-6
+  g = np.load(os.path.join(GOLDEN, 'forward_eval_b2.npz'))
+  assert g['boxes'].shape == (2, 100, 9)
