@@ -30,11 +30,24 @@ class ConvGemmArgs(ctypes.Structure):
   ]
 
 
+class WgradArgs(ctypes.Structure):
+  """tfpp_wgrad_args (include/tfpp.h)."""
+  _fields_ = [
+      ('dy', c_void_p), ('x', c_void_p), ('dw', c_void_p),
+      ('batch', c_int), ('height', c_int), ('width', c_int), ('cout', c_int),
+      ('x_batch', c_int), ('x_channels', c_int), ('x_batch_stride', c_ll),
+      ('cin', c_int), ('group_width', c_int), ('dw_s_co', c_ll), ('dw_s_tap', c_ll), ('dw_s_ci', c_ll), ('ntaps', c_int),
+      ('tap_dx', c_int * 9), ('tap_dy', c_int * 9), ('tap_db', c_int * 9), ('tap_w', c_int * 9),
+      ('tw', c_int), ('th', c_int), ('nb', c_int), ('bn', c_int), ('splits', c_int),
+  ]
+
+
 P, I, F, L = c_void_p, c_int, c_float, c_ll
 _PROTOS = {
     'tfpp_abi_version': [],
     'tfpp_pillar_scatter': [P, I, I, P, P, I, F, F, F, F, F, I, F, F, P],
     'tfpp_conv_gemm': [ctypes.POINTER(ConvGemmArgs), P],
+    'tfpp_conv_wgrad': [ctypes.POINTER(WgradArgs), P],
     'tfpp_stem_conv': [P, P, P, P, P, P, I, P, P, P, I, I, I, I, P],
     'tfpp_bn_finalize': [P, P, P, P, P, P, P, P, P, P, I, F, F, F, P],
     'tfpp_scale_shift_act': [P, P, P, P, P, P, I, P, P, I, I, I, P],
@@ -52,6 +65,28 @@ _PROTOS = {
     'tfpp_extra_sensor_token': [P, P, F, F, I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
     'tfpp_planner_head': [P] * 17 + [I, I, I, I, I, P],
     'tfpp_decode_heatmap': [P, L, P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, F, F, P],
+    'tfpp_bn_bwd': [P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P],
+    'tfpp_se_bwd': [P, P, P, P, P, I, P, P, P, P, P, P, P, P, I, I, I, P],
+    'tfpp_act_bwd': [P, P, I, I, I, F, P, P, I, I, I, I, P],
+    'tfpp_bilinear_bwd': [P, P, I, L, L, I, I, I, I, I, I, I, P],
+    'tfpp_bilinear_nchw_mask_bwd': [P, P, P, I, I, I, I, I, I, I, P],
+    'tfpp_pool_bwd_add': [P, P, I, P, I, I, I, I, I, I, I, I, P],
+    'tfpp_parity_merge': [P, P, I, I, I, I, P],
+    'tfpp_add_bf16': [P, P, P, L, P],
+    'tfpp_cast_f32_bf16': [P, P, L, P],
+    'tfpp_cast_rows': [P, P, P, I, I, I, I, I, P],
+    'tfpp_batch_reduce': [P, P, I, L, P],
+    'tfpp_stem_wgrad': [P, P, P, P, P, I, I, I, I, P],
+    'tfpp_layernorm_bwd': [P, I, P, P, P, P, P, P, P, P, I, I, P],
+    'tfpp_fusion_attn_bwd': [P, P, P, P, I, I, I, I, P],
+    'tfpp_small_mha_bwd': [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, I, P],
+    'tfpp_extra_sensor_token_bwd': [P, P, F, F, I, P, P, P, P, P, L, P, P, P, P, P, I, I, I, I, P],
+    'tfpp_planner_head_bwd': [P] * 28 + [I, I, I, I, I, P],
+    'tfpp_ce_map_loss': [P, P, P, F, P, P, P, P, I, I, I, I, P],
+    'tfpp_l1_sigmoid_loss': [P, P, F, P, P, P, I, L, P],
+    'tfpp_center_head_loss': [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
+    'tfpp_planner_loss': [P, P, P, P, P, F, F, P, P, P, I, I, I, P],
+    'tfpp_adamw_amsgrad': [P, P, P, P, P, L, F, F, F, F, F, I, F, P],
 }
 
 

@@ -1,0 +1,642 @@
+// Backward kernels of the feature-map ops (adjoints of featmap.cu): BatchNorm(+ReLU,+SE gate,+SE squeeze) backward,
+// squeeze-excite backward, activation/bias backward, bilinear and average-pool adjoints, stem weight gradient.
+// All HBM-bound; NHWC bf16 activations/gradients, fp32 reductions.  They replace the autograd graph torch builds for
+// team_code/train.py:898 (loss.backward()) over the modules cited in featmap.cu.
+#include "../../include/tfpp.h"
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void load8(const bf16* p, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, const float* v) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                            pack_bf16x2(v[6], v[7]));
+}
+
+// ---------------------------------------------------------------------------------------------- BatchNorm backward
+// forward: y = act(xhat * gamma + beta (+ res)), xhat = (raw - mean) * invstd, then optionally out = y * gate[b,c]
+// and pool[b,c] = sum_p y.  Incoming: dy (grad wrt y*gate if gate given), pool_grad[b,c] (grad wrt every y of (b,c)).
+//   dz = (dy * gate + pool_grad) * act'(y);  s1[c] = sum dz;  s2[c] = sum dz * xhat
+//   draw = gamma * invstd * (dz - s1/N - xhat * s2/N);  dgamma = s2;  dbeta = s1
+// pass 1 (reduce) / pass 2 (apply); grid (chunks, B), 8 channels per thread.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                            const bf16* __restrict__ raw, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd,
+                                                            const float* __restrict__ gate,
+                                                            const float* __restrict__ pool_grad, int act,
+                                                            float* __restrict__ s1, float* __restrict__ s2, int HW,
+                                                            int C, int pix_per_block) {
+  extern __shared__ float sm[];  // [2][C]
+  float* a1 = sm;
+  float* a2 = sm + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int b = blockIdx.y, c8n = C / 8;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  const long long base = static_cast<long long>(b) * HW * C;
+  const int items = (p1 - p0) * c8n;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int pix = p0 + it / c8n, c0 = (it % c8n) * 8;
+    const long long off = base + static_cast<long long>(pix) * C + c0;
+    float d[8], yy[8], r[8];
+    load8(dy + off, d);
+    load8(raw + off, r);
+    if (act == ACT_RELU) load8(y + off, yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float dz = d[j];
+      if (gate) dz *= __ldg(gate + static_cast<long long>(b) * C + c);
+      if (pool_grad) dz += __ldg(pool_grad + static_cast<long long>(b) * C + c);
+      if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
+      atomicAdd(&a1[c], dz);
+      atomicAdd(&a2[c], dz * (r[j] - __ldg(mean + c)) * __ldg(invstd + c));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(s1 + i, a1[i]);
+    atomicAdd(s2 + i, a2[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                           const bf16* __restrict__ raw, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ s1,
+                                                           const float* __restrict__ s2, const float* __restrict__ gate,
+                                                           const float* __restrict__ pool_grad, int act, float inv_n,
+                                                           bf16* __restrict__ draw, bf16* __restrict__ dz_out,
+                                                           long long total8, int HW, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8n = C / 8;
+  const int c0 = static_cast<int>(i % c8n) * 8;
+  const long long pix = i / c8n;
+  const int b = static_cast<int>(pix / HW);
+  float d[8], yy[8], r[8], o[8], z[8];
+  load8(dy + i * 8, d);
+  load8(raw + i * 8, r);
+  if (act == ACT_RELU) load8(y + i * 8, yy);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float dz = d[j];
+    if (gate) dz *= __ldg(gate + static_cast<long long>(b) * C + c);
+    if (pool_grad) dz += __ldg(pool_grad + static_cast<long long>(b) * C + c);
+    if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
+    z[j] = dz;
+    const float is = __ldg(invstd + c);
+    const float xh = (r[j] - __ldg(mean + c)) * is;
+    o[j] = __ldg(gamma + c) * is * (dz - __ldg(s1 + c) * inv_n - xh * __ldg(s2 + c) * inv_n);
+  }
+  store8(draw + i * 8, o);
+  if (dz_out) store8(dz_out + i * 8, z);
+}
+
+// ---------------------------------------------------------------------------------------------- SE backward
+// dgate_sum[b,c] = sum_p da2s[b,p,c] * a2[b,p,c]
+__global__ void __launch_bounds__(256) se_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a2,
+                                                            float* __restrict__ dgate_sum, int HW, int C,
+                                                            int pix_per_block) {
+  extern __shared__ float sm[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int b = blockIdx.y, c8n = C / 8;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  const long long base = static_cast<long long>(b) * HW * C;
+  const int items = (p1 - p0) * c8n;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int pix = p0 + it / c8n, c0 = (it % c8n) * 8;
+    const long long off = base + static_cast<long long>(pix) * C + c0;
+    float d[8], a[8];
+    load8(dout + off, d);
+    load8(a2 + off, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sm[c0 + j], d[j] * a[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dgate_sum + static_cast<long long>(b) * C + i, sm[i]);
+}
+
+// gate = sigmoid(W2 relu(W1 mean + b1) + b2), mean = pool_sum / hw.  One block per sample; parameter gradients are
+// accumulated with atomics across samples.  Output pool_grad[b,c] = dL/d(pool_sum[b,c]) (already divided by hw).
+__global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restrict__ dgate_sum,
+                                                          const float* __restrict__ gate,
+                                                          const float* __restrict__ hidden,
+                                                          const float* __restrict__ pool_sum, float inv_hw,
+                                                          const float* __restrict__ w1, const float* __restrict__ w2,
+                                                          float* __restrict__ dw1, float* __restrict__ db1,
+                                                          float* __restrict__ dw2, float* __restrict__ db2,
+                                                          float* __restrict__ pool_grad, int C, int R) {
+  extern __shared__ float sm[];
+  float* ds = sm;        // C
+  float* dpre = sm + C;  // R
+  float* mean = dpre + R;  // C
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = gate[static_cast<long long>(b) * C + c];
+    const float v = dgate_sum[static_cast<long long>(b) * C + c] * g * (1.f - g);
+    ds[c] = v;
+    mean[c] = pool_sum[static_cast<long long>(b) * C + c] * inv_hw;
+    atomicAdd(db2 + c, v);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < R; r += nw) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(ds[c], w2[static_cast<long long>(c) * R + r], a);
+    a = warp_sum(a);
+    if (lane == 0) {
+      const float h = hidden[static_cast<long long>(b) * R + r];
+      const float v = h > 0.f ? a : 0.f;
+      dpre[r] = v;
+      atomicAdd(db1 + r, v);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * R; i += blockDim.x) {
+    const int c = i / R, r = i % R;
+    atomicAdd(dw2 + i, ds[c] * hidden[static_cast<long long>(b) * R + r]);  // dw2 (C,R)
+  }
+  for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    atomicAdd(dw1 + i, dpre[r] * mean[c]);  // dw1 (R,C)
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < R; ++r) a = fmaf(dpre[r], w1[static_cast<long long>(r) * C + c], a);
+    pool_grad[static_cast<long long>(b) * C + c] = a * inv_hw;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- activation / bias
+// dz = dy * act'(y), dbias[c] += sum dz.  dy, y: NHWC bf16 (C channels) or NCHW f32; dz: NHWC bf16 with Cp >= C
+// channels (zero padded) so it can feed the TMA-based GEMMs (Cp % 8 == 0).
+__global__ void __launch_bounds__(256) act_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ y,
+                                                      int nchw_f32, int act, int act_n_limit, float dy_scale,
+                                                      bf16* __restrict__ dz, float* __restrict__ dbias, long long npix,
+                                                      int HW, int C, int Cp) {
+  extern __shared__ float sm[];  // Cp
+  for (int i = threadIdx.x; i < Cp; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const long long total = npix * Cp;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = static_cast<int>(i % Cp);
+    const long long pix = i / Cp;
+    float v = 0.f;
+    if (c < C) {
+      float d, yy;
+      if (nchw_f32 == 1) {
+        const long long b = pix / HW, hw = pix % HW;
+        const long long off = (b * C + c) * HW + hw;
+        d = static_cast<const float*>(dy)[off];
+        yy = y ? static_cast<const float*>(y)[off] : 0.f;
+      } else if (nchw_f32 == 2) {
+        d = static_cast<const float*>(dy)[pix * C + c];
+        yy = y ? bf2f(static_cast<const bf16*>(y)[pix * C + c]) : 0.f;
+      } else {
+        d = bf2f(static_cast<const bf16*>(dy)[pix * C + c]);
+        yy = y ? bf2f(static_cast<const bf16*>(y)[pix * C + c]) : 0.f;
+      }
+      d *= dy_scale;
+      const int a = (act_n_limit == 0 || c < act_n_limit) ? act : ACT_NONE;
+      if (a == ACT_RELU) d = yy > 0.f ? d : 0.f;
+      else if (a == ACT_SIGMOID) d = d * yy * (1.f - yy);
+      v = d;
+      if (dbias) atomicAdd(&sm[c], v);
+    }
+    if (dz) dz[i] = f2bf(v);
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sm[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- bilinear adjoint
+// dsrc[b,sy,sx,c] (+)= sum over destination pixels whose interpolation stencil touches (sy,sx).
+__device__ __forceinline__ void bl_coef(int d, int dn, int sn, int& i0, int& i1, float& l) {
+  const float f = fmaxf((d + 0.5f) * (static_cast<float>(sn) / dn) - 0.5f, 0.f);
+  i0 = min(static_cast<int>(f), sn - 1);
+  i1 = min(i0 + 1, sn - 1);
+  l = f - i0;
+}
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const bf16* __restrict__ dout, void* __restrict__ dsrc,
+                                                           int dsrc_f32, long long s_sb, long long s_srow,
+                                                           int accumulate, int B, int sh, int sw, int dh, int dw, int C) {
+  const int c8n = C / 8;
+  const long long total = static_cast<long long>(B) * sh * sw * c8n;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c0 = static_cast<int>(i % c8n) * 8;
+  long long t = i / c8n;
+  const int sx = static_cast<int>(t % sw);
+  t /= sw;
+  const int sy = static_cast<int>(t % sh);
+  const int b = static_cast<int>(t / sh);
+  const int ry = (dh + sh - 1) / sh, rx = (dw + sw - 1) / sw;
+  const int ylo = max(0, (sy - 1) * ry - 1), yhi = min(dh - 1, (sy + 2) * ry);
+  const int xlo = max(0, (sx - 1) * rx - 1), xhi = min(dw - 1, (sx + 2) * rx);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int y = ylo; y <= yhi; ++y) {
+    int y0, y1;
+    float ly;
+    bl_coef(y, dh, sh, y0, y1, ly);
+    const float wy = (y0 == sy ? 1.f - ly : 0.f) + (y1 == sy ? ly : 0.f);
+    if (wy == 0.f) continue;
+    for (int x = xlo; x <= xhi; ++x) {
+      int x0, x1;
+      float lx;
+      bl_coef(x, dw, sw, x0, x1, lx);
+      const float wx = (x0 == sx ? 1.f - lx : 0.f) + (x1 == sx ? lx : 0.f);
+      if (wx == 0.f) continue;
+      float d[8];
+      load8(dout + ((static_cast<long long>(b) * dh + y) * dw + x) * C + c0, d);
+      const float wgt = wy * wx;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, d[j], acc[j]);
+    }
+  }
+  const long long off = b * s_sb + (static_cast<long long>(sy) * sw + sx) * s_srow + c0;
+  if (dsrc_f32) {
+    float* p = static_cast<float*>(dsrc) + off;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = accumulate ? p[j] + acc[j] : acc[j];
+  } else {
+    bf16* p = static_cast<bf16*>(dsrc) + off;
+    if (accumulate) {
+      float o[8];
+      load8(p, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += o[j];
+    }
+    store8(p, acc);
+  }
+}
+
+// adjoint of bilinear_nchw_mask: dsrc[b,sy,sx,c] = sum_dest w * mask * dout_nchw_f32[b,c,y,x]; dsrc NHWC bf16 (Cs pad)
+__global__ void __launch_bounds__(256) bilinear_nchw_mask_bwd_kernel(const float* __restrict__ dout,
+                                                                     const float* __restrict__ mask,
+                                                                     bf16* __restrict__ dsrc, int B, int sh, int sw,
+                                                                     int Cs, int C, int dh, int dw) {
+  const long long total = static_cast<long long>(B) * sh * sw * Cs;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % Cs);
+  long long t = i / Cs;
+  const int sx = static_cast<int>(t % sw);
+  t /= sw;
+  const int sy = static_cast<int>(t % sh);
+  const int b = static_cast<int>(t / sh);
+  float acc = 0.f;
+  if (c < C) {
+    const int ry = (dh + sh - 1) / sh, rx = (dw + sw - 1) / sw;
+    const int ylo = max(0, (sy - 1) * ry - 1), yhi = min(dh - 1, (sy + 2) * ry);
+    const int xlo = max(0, (sx - 1) * rx - 1), xhi = min(dw - 1, (sx + 2) * rx);
+    for (int y = ylo; y <= yhi; ++y) {
+      int y0, y1;
+      float ly;
+      bl_coef(y, dh, sh, y0, y1, ly);
+      const float wy = (y0 == sy ? 1.f - ly : 0.f) + (y1 == sy ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int x = xlo; x <= xhi; ++x) {
+        int x0, x1;
+        float lx;
+        bl_coef(x, dw, sw, x0, x1, lx);
+        const float wx = (x0 == sx ? 1.f - lx : 0.f) + (x1 == sx ? lx : 0.f);
+        if (wx == 0.f) continue;
+        const float m = mask ? __ldg(mask + static_cast<long long>(y) * dw + x) : 1.f;
+        acc = fmaf(wy * wx * m, dout[((static_cast<long long>(b) * C + c) * dh + y) * dw + x], acc);
+      }
+    }
+  }
+  dsrc[i] = f2bf(acc);
+}
+
+// adjoint of avgpool_tokens fused with the residual pass-through: out = dout + dtok[b, token(y,x), :] / window
+__global__ void __launch_bounds__(256) pool_bwd_add_kernel(const bf16* __restrict__ dout, const void* __restrict__ dtok,
+                                                           int dtok_f32, bf16* __restrict__ out, int B, int H, int W,
+                                                           int C, int ph, int pw, int rows_per_batch, int row0) {
+  const int c8n = C / 8;
+  const long long total = static_cast<long long>(B) * H * W * c8n;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c0 = static_cast<int>(i % c8n) * 8;
+  long long t = i / c8n;
+  const int x = static_cast<int>(t % W);
+  t /= W;
+  const int y = static_cast<int>(t % H);
+  const int b = static_cast<int>(t / H);
+  const int wh = H / ph, ww = W / pw;
+  const int row = row0 + (y / wh) * pw + (x / ww);
+  const float inv = 1.f / static_cast<float>(wh * ww);
+  const long long toff = (static_cast<long long>(b) * rows_per_batch + row) * C + c0;
+  float v[8], d[8];
+  if (dtok_f32) {
+    const float* p = static_cast<const float*>(dtok) + toff;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[j] * inv;
+  } else {
+    load8(static_cast<const bf16*>(dtok) + toff, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= inv;
+  }
+  if (dout) {
+    load8(dout + i * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += d[j];
+  }
+  store8(out + i * 8, v);
+}
+
+// y = a + b (bf16 NHWC gradients meeting at a fork)
+__global__ void __launch_bounds__(256) add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                       bf16* __restrict__ y, long long total8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  float u[8], v[8];
+  load8(a + i * 8, u);
+  load8(b + i * 8, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) u[j] += v[j];
+  store8(y + i * 8, u);
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y,
+                                                            long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = f2bf(x[i]);
+}
+
+// strided row gather + cast: out[g*rows + r, :] = bf16(x[g, row0 + r, :]); dbias[c] += column sums
+__global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ x, bf16* __restrict__ out,
+                                                        float* __restrict__ dbias, int groups, int group_rows, int row0,
+                                                        int rows, int C) {
+  extern __shared__ float sm[];
+  if (dbias) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+  }
+  const long long total = static_cast<long long>(groups) * rows * C;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = static_cast<int>(i % C);
+    const long long r = i / C;
+    const long long g = r / rows, rr = r % rows;
+    const float v = x[(g * group_rows + row0 + rr) * C + c];
+    out[i] = f2bf(v);
+    if (dbias) atomicAdd(&sm[c], v);
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sm[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) batch_reduce_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                           int batch, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int b = 0; b < batch; ++b) a += x[b * n + i];
+  out[i] += a;
+}
+
+// adjoint of parity_split: (4B,H/2,W/2,C) planes -> (B,H,W,C)
+__global__ void __launch_bounds__(256) parity_merge_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                           long long total8, int B, int H, int W, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8n = C / 8;
+  const int c8 = static_cast<int>(i % c8n);
+  long long pix = i / c8n;
+  const int xx = static_cast<int>(pix % W);
+  pix /= W;
+  const int yy = static_cast<int>(pix % H);
+  const int b = static_cast<int>(pix / H);
+  const int q = (yy & 1) * 2 + (xx & 1);
+  const long long src = (((static_cast<long long>(q) * B + b) * (H / 2) + (yy >> 1)) * (W / 2) + (xx >> 1)) * C + c8 * 8;
+  *reinterpret_cast<uint4*>(y + i * 8) = *reinterpret_cast<const uint4*>(x + src);
+}
+
+// ---------------------------------------------------------------------------------------------- stem weight gradient
+// dW[o][c][ky][kx] = sum_{b,oy,ox} draw[b,oy,ox,o] * xin[b,c,2oy+ky-1,2ox+kx-1]   (xin = normalised image, zero pad)
+// One block per (c, ky, kx) x pixel chunk; 32 output channels per thread row.
+template <int CIN>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ draw,
+                                                         const float* __restrict__ in_scale,
+                                                         const float* __restrict__ in_shift, float* __restrict__ dw,
+                                                         int B, int H, int W) {
+  __shared__ float acc[32];
+  if (threadIdx.x < 32) acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int tap = blockIdx.y;  // c*9 + ky*3 + kx
+  const int c = tap / 9, ky = (tap % 9) / 3, kx = tap % 3;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  const float a = in_scale ? in_scale[c] : 1.f, sft = in_shift ? in_shift[c] : 0.f;
+  float l[32];
+#pragma unroll
+  for (int o = 0; o < 32; ++o) l[o] = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int ox = static_cast<int>(idx % Wo), oy = static_cast<int>((idx / Wo) % Ho);
+    const int b = static_cast<int>(idx / (static_cast<long long>(Wo) * Ho));
+    const int iy = oy * 2 + ky - 1, ix = ox * 2 + kx - 1;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const float v = x[((static_cast<long long>(b) * CIN + c) * H + iy) * W + ix] * a + sft;
+    const uint4* dp = reinterpret_cast<const uint4*>(draw + idx * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 u = __ldg(dp + q);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        l[q * 8 + 2 * j] = fmaf(v, f.x, l[q * 8 + 2 * j]);
+        l[q * 8 + 2 * j + 1] = fmaf(v, f.y, l[q * 8 + 2 * j + 1]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 0; o < 32; ++o) {
+    const float s = warp_sum(l[o]);
+    if (lane == 0) atomicAdd(&acc[o], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) atomicAdd(dw + (static_cast<long long>(threadIdx.x) * CIN + c) * 9 + ky * 3 + kx, acc[threadIdx.x]);
+}
+
+}  // namespace
+
+#define STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
+
+static void chunking(int batch, int hw, int* chunks, int* pix_per_block) {
+  int ch = ceil_div(TFPP_NUM_SMS * 4, batch);
+  int ppb = ceil_div(hw, ch);
+  if (ppb < 8) ppb = 8;
+  *chunks = ceil_div(hw, ppb);
+  *pix_per_block = ppb;
+}
+
+extern "C" int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const float* mean, const float* invstd,
+                           const float* gamma, const float* gate, const float* pool_grad, int act, float* s1, float* s2,
+                           void* draw, void* dz_out, int batch, int hw, int channels, tfpp_stream_t stream_) {
+  STREAM;
+  TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
+  int chunks, ppb;
+  chunking(batch, hw, &chunks, &ppb);
+  dim3 grid(chunks, batch);
+  bn_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 2 * channels, stream>>>(
+      static_cast<const bf16*>(dy), static_cast<const bf16*>(y), static_cast<const bf16*>(raw), mean, invstd, gate,
+      pool_grad, act, s1, s2, hw, channels, ppb);
+  TFPP_CHECK_LAUNCH();
+  const long long total8 = static_cast<long long>(batch) * hw * channels / 8;
+  bn_bwd_apply_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(dy), static_cast<const bf16*>(y), static_cast<const bf16*>(raw), mean, invstd, gamma, s1,
+      s2, gate, pool_grad, act, 1.f / (static_cast<float>(batch) * hw), static_cast<bf16*>(draw),
+      static_cast<bf16*>(dz_out), total8, hw, channels);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_se_bwd(const void* dout, const void* a2, const float* gate, const float* hidden,
+                           const float* pool_sum, int hw, const float* w1, const float* w2, float* dgate_sum, float* dw1,
+                           float* db1, float* dw2, float* db2, float* pool_grad, int batch, int channels, int rd,
+                           tfpp_stream_t stream_) {
+  STREAM;
+  TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
+  int chunks, ppb;
+  chunking(batch, hw, &chunks, &ppb);
+  dim3 grid(chunks, batch);
+  se_bwd_reduce_kernel<<<grid, 256, sizeof(float) * channels, stream>>>(static_cast<const bf16*>(dout),
+                                                                        static_cast<const bf16*>(a2), dgate_sum, hw,
+                                                                        channels, ppb);
+  TFPP_CHECK_LAUNCH();
+  se_gate_bwd_kernel<<<batch, 256, sizeof(float) * (2 * channels + rd), stream>>>(
+      dgate_sum, gate, hidden, pool_sum, 1.f / hw, w1, w2, dw1, db1, dw2, db2, pool_grad, channels, rd);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_act_bwd(const void* dy, const void* y, int nchw_f32, int act, int act_n_limit, float dy_scale,
+                            void* dz, float* dbias, int batch, int hw, int channels, int channels_padded,
+                            tfpp_stream_t stream_) {
+  STREAM;
+  const long long npix = static_cast<long long>(batch) * hw;
+  long long blocks = ceil_div_ll(npix * channels_padded, 256 * 4);
+  if (blocks > TFPP_NUM_SMS * 8) blocks = TFPP_NUM_SMS * 8;
+  if (blocks < 1) blocks = 1;
+  act_bwd_kernel<<<static_cast<int>(blocks), 256, sizeof(float) * channels_padded, stream>>>(
+      dy, y, nchw_f32, act, act_n_limit, dy_scale, static_cast<bf16*>(dz), dbias, npix, hw, channels, channels_padded);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_bilinear_bwd(const void* dout, void* dsrc, int dsrc_f32, long long src_batch_stride,
+                                 long long src_row_stride, int accumulate, int batch, int sh, int sw, int dh, int dw,
+                                 int channels, tfpp_stream_t stream_) {
+  STREAM;
+  TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
+  const long long total = static_cast<long long>(batch) * sh * sw * (channels / 8);
+  bilinear_bwd_kernel<<<static_cast<int>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(dout), dsrc, dsrc_f32, src_batch_stride, src_row_stride, accumulate, batch, sh, sw, dh,
+      dw, channels);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_bilinear_nchw_mask_bwd(const float* dout, const float* mask, void* dsrc, int batch, int sh, int sw,
+                                           int src_channels, int channels, int dh, int dw, tfpp_stream_t stream_) {
+  STREAM;
+  const long long total = static_cast<long long>(batch) * sh * sw * src_channels;
+  bilinear_nchw_mask_bwd_kernel<<<static_cast<int>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
+      dout, mask, static_cast<bf16*>(dsrc), batch, sh, sw, src_channels, channels, dh, dw);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_pool_bwd_add(const void* dout, const void* dtok, int dtok_f32, void* out, int batch, int height,
+                                 int width, int channels, int ph, int pw, int rows_per_batch, int row0,
+                                 tfpp_stream_t stream_) {
+  STREAM;
+  TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
+  const long long total = static_cast<long long>(batch) * height * width * (channels / 8);
+  pool_bwd_add_kernel<<<static_cast<int>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(dout), dtok, dtok_f32, static_cast<bf16*>(out), batch, height, width, channels, ph, pw,
+      rows_per_batch, row0);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_add_bf16(const void* a, const void* b, void* y, long long n, tfpp_stream_t stream_) {
+  STREAM;
+  TFPP_CHECK_ARG(n % 8 == 0, "n must be a multiple of 8");
+  add_bf16_kernel<<<static_cast<int>(ceil_div_ll(n / 8, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(a), static_cast<const bf16*>(b), static_cast<bf16*>(y), n / 8);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_cast_f32_bf16(const float* x, void* y, long long n, tfpp_stream_t stream_) {
+  STREAM;
+  cast_f32_bf16_kernel<<<static_cast<int>(ceil_div_ll(n, 256)), 256, 0, stream>>>(x, static_cast<bf16*>(y), n);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_cast_rows(const float* x, void* out, float* dbias, int groups, int group_rows, int row0, int rows,
+                              int channels, tfpp_stream_t stream_) {
+  STREAM;
+  const long long total = static_cast<long long>(groups) * rows * channels;
+  long long blocks = ceil_div_ll(total, 256 * 4);
+  if (blocks > TFPP_NUM_SMS * 8) blocks = TFPP_NUM_SMS * 8;
+  if (blocks < 1) blocks = 1;
+  cast_rows_kernel<<<static_cast<int>(blocks), 256, dbias ? sizeof(float) * channels : 0, stream>>>(
+      x, static_cast<bf16*>(out), dbias, groups, group_rows, row0, rows, channels);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_batch_reduce(const float* x, float* out, int batch, long long n, tfpp_stream_t stream_) {
+  STREAM;
+  batch_reduce_kernel<<<static_cast<int>(ceil_div_ll(n, 256)), 256, 0, stream>>>(x, out, batch, n);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_parity_merge(const void* x, void* y, int batch, int height, int width, int channels,
+                                 tfpp_stream_t stream_) {
+  STREAM;
+  TFPP_CHECK_ARG(channels % 8 == 0 && height % 2 == 0 && width % 2 == 0, "need C%8==0 and even H, W");
+  const long long total8 = static_cast<long long>(batch) * height * width * channels / 8;
+  parity_merge_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(y), total8, batch, height, width, channels);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_stem_wgrad(const float* x, const void* draw, const float* in_scale, const float* in_shift,
+                               float* dw, int batch, int cin, int height, int width, tfpp_stream_t stream_) {
+  STREAM;
+  TFPP_CHECK_ARG(cin >= 1 && cin <= 3, "stem supports 1..3 input channels");
+  dim3 grid(TFPP_NUM_SMS, cin * 9);
+  const bf16* d = static_cast<const bf16*>(draw);
+  if (cin == 1) stem_wgrad_kernel<1><<<grid, 256, 0, stream>>>(x, d, in_scale, in_shift, dw, batch, height, width);
+  else if (cin == 2) stem_wgrad_kernel<2><<<grid, 256, 0, stream>>>(x, d, in_scale, in_shift, dw, batch, height, width);
+  else stem_wgrad_kernel<3><<<grid, 256, 0, stream>>>(x, d, in_scale, in_shift, dw, batch, height, width);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}

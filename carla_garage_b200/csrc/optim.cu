@@ -1,0 +1,41 @@
+// Fused AdamW(amsgrad=True) step.  Reference: optim.AdamW(lr, amsgrad=True) at team_code/train.py:527-531 (torch
+// defaults betas (0.9, 0.999), eps 1e-8, weight_decay 0.01).  One pass over (param, grad, exp_avg, exp_avg_sq,
+// max_exp_avg_sq): 5 reads + 4 writes of fp32 per element, HBM-bound.
+#include "../../include/tfpp.h"
+#include "common.cuh"
+
+namespace {
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v,
+                                                    float* __restrict__ vmax, long long n, float lr, float beta1,
+                                                    float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+                                                    float grad_scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gr = g[i] * grad_scale;
+  float pv = p[i];
+  pv *= (1.f - lr * wd);                       // decoupled weight decay
+  const float mv = beta1 * m[i] + (1.f - beta1) * gr;
+  const float vv = beta2 * v[i] + (1.f - beta2) * gr * gr;
+  const float vm = fmaxf(vmax[i], vv);
+  m[i] = mv;
+  v[i] = vv;
+  vmax[i] = vm;
+  const float denom = sqrtf(vm) / bc2_sqrt + eps;
+  p[i] = pv - (lr / bc1) * (mv / denom);
+}
+}  // namespace
+
+extern "C" int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                  float* max_exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps,
+                                  float weight_decay, int step, float grad_scale, tfpp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TFPP_CHECK_ARG(step >= 1, "step counts from 1");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  adamw_kernel<<<static_cast<int>(ceil_div_ll(n, 256)), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq,
+                                                                          max_exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                          weight_decay, bc1, sqrtf(bc2), grad_scale);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}

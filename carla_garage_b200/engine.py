@@ -83,6 +83,7 @@ class Engine:
     self.cfg = (model or backbone or head).config
     self._consts = {}
     self.tape = None  # list of saved activations when a backward pass will follow
+    self.debug_taps = None  # dict: name -> NHWC bf16 intermediate (tests only)
 
   @classmethod
   def for_backbone(cls, backbone):
@@ -110,6 +111,10 @@ class Engine:
   def _save(self, **kw):
     if self.tape is not None:
       self.tape.append(kw)
+
+  def _tap(self, name, t):
+    if self.debug_taps is not None:
+      self.debug_taps[name] = t
 
   def conv_bn(self, a, cna, training, *, taps=ops.TAPS_1X1, batch=None, grouped=False, act=ACT_NONE, res=None,
               res_bn=None, want_pool=False):
@@ -285,10 +290,16 @@ class Engine:
     lidar = lidar.float().contiguous()
     img = self.stem(image, bb.image_encoder['stem'], training, cfg.normalize_imagenet)
     lid = self.stem(lidar, bb.lidar_encoder['stem'], training, False)
+    self._tap('img_stem', img)
+    self._tap('lid_stem', lid)
     for i in range(4):
       img = self.regnet_stage(img, bb.image_encoder[f's{i + 1}'], training)
       lid = self.regnet_stage(lid, bb.lidar_encoder[f's{i + 1}'], training)
+      self._tap(f'img_s{i + 1}_pre', img)
+      self._tap(f'lid_s{i + 1}_pre', lid)
       img, lid = self.fuse(img, lid, i, training)
+      self._tap(f'img_s{i + 1}', img)
+      self._tap(f'lid_s{i + 1}', lid)
     feats = None
     if cfg.detect_boxes or cfg.use_bev_semantic:
       # top_down (transfuser.py:131-137)
@@ -304,6 +315,9 @@ class Engine:
       self._save(op='bilinear', src=p4)
       feats = self.conv_bias(p4u, bb.up_conv4, ACT_RELU)
     grid = img if (cfg.use_semantic or cfg.use_depth) else None
+    self._tap('bev_feature_grid', feats)
+    self._tap('fused_features', lid)
+    self._tap('image_feature_grid', grid)
     return feats, lid, grid
 
   # ------------------------------------------------------------------------------------------------ heads
@@ -410,6 +424,7 @@ class Engine:
                            cd.decoder.weight, cd.decoder.bias, tsn[0].weight, tsn[0].bias, tsn[2].weight, tsn[2].bias,
                            want_h=self.tape is not None)
     self._save(op='planner_head', x=x, joined=joined, stats=(mj, rj), res=res)
+    self._tap('joined', joined.view(b, nq, d))
     return res[0], res[1]
 
   # ------------------------------------------------------------------------------------------------ full model

@@ -5,7 +5,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ConvGemmArgs, check
+from ._lib import ConvGemmArgs, WgradArgs, check
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -63,13 +63,11 @@ def pick_tile(height, width):
 
 
 def pick_bn(n):
-  best = None
-  for bn in range(16, 257, 16):
-    padded = -(-n // bn) * bn
-    key = (padded, -bn)
-    if best is None or key < best[0]:
-      best = (key, bn)
-  return best[1]
+  """N tile (multiple of 16, <= 256): the largest tile whose padded width is within 4 % of the minimum (large tiles
+  re-read the A operand fewer times; padding columns are wasted MMA work)."""
+  cands = [(-(-n // bn) * bn, bn) for bn in range(16, 257, 16)]
+  min_pad = min(p for p, _ in cands)
+  return max(bn for p, bn in cands if p <= min_pad * 1.04)
 
 
 def nhwc_strides(h, w, c):
@@ -138,6 +136,49 @@ def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1
   if stats is not None:
     args.stat_sum, args.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
   check(_lib.load().tfpp_conv_gemm(ctypes.byref(args), _stream()), 'tfpp_conv_gemm')
+  return out
+
+
+def pick_tile64(height, width):
+  tw, th, nb = pick_tile(height, width)
+  if nb >= 2:
+    return tw, th, nb // 2
+  if th >= 2:
+    return tw, th // 2, nb
+  return tw // 2, th, nb
+
+
+def conv_wgrad(dy, x, *, cin=None, taps=TAPS_1X1, w_taps=None, group_width=0, x_batch_stride=0, x_shape=None, bn=0,
+               splits=0, out=None, out_strides=None, dy_shape=None):
+  """dw[co, tap, ci] = sum_pixels dy[pixel, co] * x[pixel + tap, ci]; dy (B,H,W,Cout) bf16, x (Bx,H,W,Cx) bf16.
+  Returns fp32 (Cout, w_taps, cin) (dense) or (Cout, w_taps, group_width) (grouped); accumulates into ``out``."""
+  if dy_shape is None:
+    _dev(dy, BF16)
+    b, h, w, cout = dy.shape
+  else:
+    b, h, w, cout = dy_shape
+  if x_shape is None:
+    _dev(x, BF16)
+    xb, _, _, cx = x.shape
+  else:
+    xb, _, _, cx = x_shape
+  cin = cx if cin is None else cin
+  w_taps = len(taps) if w_taps is None else w_taps
+  if out is None:
+    kdim = group_width if group_width else cin
+    out = torch.zeros((cout, w_taps, kdim), dtype=F32, device=dy.device)
+    out_strides = (w_taps * kdim, kdim, 1)
+  a = WgradArgs()
+  a.dy, a.x, a.dw = dy.data_ptr(), x.data_ptr(), out.data_ptr()
+  a.batch, a.height, a.width, a.cout = b, h, w, cout
+  a.x_batch, a.x_channels, a.x_batch_stride = xb, cx, x_batch_stride
+  a.cin, a.group_width, a.ntaps = cin, group_width, len(taps)
+  a.dw_s_co, a.dw_s_tap, a.dw_s_ci = out_strides
+  for i, (dx, dy_, db, tw_) in enumerate(taps):
+    a.tap_dx[i], a.tap_dy[i], a.tap_db[i], a.tap_w[i] = dx, dy_, db, tw_
+  a.tw, a.th, a.nb = pick_tile64(h, w)
+  a.bn, a.splits = bn, splits
+  check(_lib.load().tfpp_conv_wgrad(ctypes.byref(a), _stream()), 'tfpp_conv_wgrad')
   return out
 
 

@@ -112,9 +112,34 @@ def make_state_dict(shapes, seed=0, fixed=None):
       fan_in = int(np.prod(shape[1:]))
       gain = 2.0 if len(shape) == 4 else 1.0
       t = torch.randn(shape, generator=g) * math.sqrt(gain / fan_in)
+    elif name.endswith('conv3.bn.weight'):
+      # last BatchNorm of a residual branch: timm zero-inits it and trained nets keep it small; ~0.2 keeps the
+      # residual branch exercised without the DC build-up that makes a random RegNet amplify rounding noise ~7x/stage
+      t = torch.rand(shape, generator=g) * 0.2 + 0.1
     elif leaf == 'weight':  # 1-D weights: BatchNorm / LayerNorm gains
       t = torch.rand(shape, generator=g) * 0.4 + 0.8
     else:  # biases
       t = torch.randn(shape, generator=g) * 0.05
     sd[name] = t
+  return sd
+
+
+def golden_state(golden_dir):
+  """The seeded + BatchNorm-calibrated state_dict every golden vector was generated with
+  (tests/golden/make_golden.py): make_state_dict(seed 0) + the fixed buffers + running stats from bn_calib.npz."""
+  import json
+  import os
+  shapes = json.load(open(os.path.join(golden_dir, 'state_dict_keys.json')))['shapes']
+  valid = torch.from_numpy(np.load(os.path.join(golden_dir, 'valid_bev_pixels.npz'))['valid']).float()
+  fixed = {
+      'valid_bev_pixels': valid,
+      'valid_bev_pixels_inv': 1.0 - valid,
+      'loss_speed.weight': torch.tensor([0.866605263873406, 7.4527377240841775, 1.2281629310898465, 0.5269622904065803]),
+      'loss_semantic.weight': torch.ones(7),
+      'loss_bev_semantic.weight': torch.ones(11),
+  }
+  sd = make_state_dict(shapes, seed=0, fixed=fixed)
+  calib = np.load(os.path.join(golden_dir, 'bn_calib.npz'))
+  for k in calib.files:
+    sd[k] = torch.from_numpy(calib[k]).clone()
   return sd

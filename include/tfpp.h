@@ -70,6 +70,31 @@ typedef struct {
 
 int tfpp_conv_gemm(const tfpp_conv_gemm_args* args, tfpp_stream_t stream);
 
+/* ---- tcgen05 weight-gradient GEMM ------------------------------------------------------------------------------
+ * dw[co, tap_w, ci] += sum_pixels dy[pixel, co] * x[pixel + shift(tap), ci]   (fp32 atomics: zero dw first)
+ * dy: NHWC bf16 (batch, height, width, cout); x: NHWC bf16 (x_batch, height, width, x_channels) (x_batch = 4*batch for
+ * stride-2 parity planes, taps as in tfpp_conv_gemm).  dw is addressed through element strides, so it can be the
+ * parameter's own (cout, cin, kh, kw) gradient.  Grouped (group_width > 0): input channel ci of group g pairs with
+ * output channels of group g only and the ci index of dw is local to the group.  Replaces autograd's convolution_backward (weight) / addmm of train.py:898. */
+typedef struct {
+  const void* dy;
+  const void* x;
+  float* dw;
+  int batch, height, width, cout;
+  int x_batch, x_channels;
+  long long x_batch_stride; /* elements, 0 = contiguous */
+  int cin;                  /* dense: number of input channels written (<= x_channels) */
+  int group_width;          /* 0 = dense */
+  long long dw_s_co, dw_s_tap, dw_s_ci; /* element strides of dw: (co, tap_w, ci) -> co*s_co + tap*s_tap + ci*s_ci */
+  int ntaps;
+  int tap_dx[9], tap_dy[9], tap_db[9], tap_w[9];
+  int tw, th, nb;           /* 64-pixel tile */
+  int bn;                   /* ci tile (dense), 0 = auto */
+  int splits;               /* pixel-range splits, 0 = auto */
+} tfpp_wgrad_args;
+
+int tfpp_conv_wgrad(const tfpp_wgrad_args* args, tfpp_stream_t stream);
+
 /* ---- stem conv: timm RegNet stem ConvNormAct(in,32,k3,s2,p1) fused with normalize_imagenet ---------------------
  * (team_code/transfuser.py:146-149,164-167; transfuser_utils.py:542-551).  x: NCHW f32 (B,cin<=3,H,W), w: f32
  * (32,cin,3,3); in_scale/in_shift: per-input-channel affine applied before zero padding (NULL = identity);
@@ -154,6 +179,93 @@ int tfpp_decode_heatmap(const float* heat, long long heat_sb, const float* wh, l
                         long long off_sb, const float* yaw_cls, long long ycls_sb, const float* yaw_res,
                         long long yres_sb, float* out, int batch, int n_cls, int height, int width, int n_bins, int k,
                         float width_ratio, float height_ratio, tfpp_stream_t stream);
+
+/* ==== backward / training kernels (adjoints of the ops above; they replace the autograd graph that
+ * team_code/train.py:898 `loss.backward()` walks, and optim.AdamW(amsgrad=True).step() of train.py:527-531,908) ==== */
+
+/* BatchNorm(+ReLU)(+SE gate / squeeze) backward. dy,y,raw NHWC bf16; gate,pool_grad (B,C) f32 optional;
+ * s1,s2 (C) f32 zeroed by the caller: on return s1 = dbeta, s2 = dgamma. draw = grad wrt the conv output; dz_out
+ * (optional) = masked incoming gradient (grad of the residual input of the block). */
+int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const float* mean, const float* invstd,
+                const float* gamma, const float* gate, const float* pool_grad, int act, float* s1, float* s2, void* draw,
+                void* dz_out, int batch, int hw, int channels, tfpp_stream_t stream);
+
+/* SE backward: dout = grad wrt (a2 * gate); outputs pool_grad (B,C) = dL/d(pool_sum) and fc1/fc2 gradients (+=). */
+int tfpp_se_bwd(const void* dout, const void* a2, const float* gate, const float* hidden, const float* pool_sum, int hw,
+                const float* w1, const float* w2, float* dgate_sum, float* dw1, float* db1, float* dw2, float* db2,
+                float* pool_grad, int batch, int channels, int rd, tfpp_stream_t stream);
+
+/* dz = dy_scale * dy * act'(y) -> NHWC bf16 (channels_padded), dbias += column sums.
+ * layout: 0 = dy,y NHWC bf16; 1 = NCHW f32; 2 = NHWC f32 (token matrices). dz may be NULL (bias gradient only). */
+int tfpp_act_bwd(const void* dy, const void* y, int layout, int act, int act_n_limit, float dy_scale, void* dz,
+                 float* dbias, int batch, int hw, int channels, int channels_padded, tfpp_stream_t stream);
+
+/* adjoints of tfpp_bilinear / tfpp_bilinear_nchw_mask / tfpp_avgpool_tokens(+residual) / tfpp_parity_split */
+int tfpp_bilinear_bwd(const void* dout, void* dsrc, int dsrc_f32, long long src_batch_stride, long long src_row_stride,
+                      int accumulate, int batch, int sh, int sw, int dh, int dw, int channels, tfpp_stream_t stream);
+int tfpp_bilinear_nchw_mask_bwd(const float* dout, const float* mask, void* dsrc, int batch, int sh, int sw,
+                                int src_channels, int channels, int dh, int dw, tfpp_stream_t stream);
+int tfpp_pool_bwd_add(const void* dout, const void* dtok, int dtok_f32, void* out, int batch, int height, int width,
+                      int channels, int ph, int pw, int rows_per_batch, int row0, tfpp_stream_t stream);
+int tfpp_parity_merge(const void* x, void* y, int batch, int height, int width, int channels, tfpp_stream_t stream);
+int tfpp_add_bf16(const void* a, const void* b, void* y, long long n, tfpp_stream_t stream);
+int tfpp_cast_f32_bf16(const float* x, void* y, long long n, tfpp_stream_t stream);
+/* out (groups*rows, C) bf16 = rows [row0, row0+rows) of every group of x (groups, group_rows, C) f32; dbias += sums */
+int tfpp_cast_rows(const float* x, void* out, float* dbias, int groups, int group_rows, int row0, int rows,
+                   int channels, tfpp_stream_t stream);
+/* out (n) += sum_b x (batch, n) f32 */
+int tfpp_batch_reduce(const float* x, float* out, int batch, long long n, tfpp_stream_t stream);
+
+/* stem conv weight gradient: dw (32,cin,3,3) f32 += ; draw NHWC bf16 (B,H/2,W/2,32). */
+int tfpp_stem_wgrad(const float* x, const void* draw, const float* in_scale, const float* in_shift, float* dw, int batch,
+                    int cin, int height, int width, tfpp_stream_t stream);
+
+int tfpp_layernorm_bwd(const void* dy, int dy_f32, const float* x, const float* mean, const float* rstd,
+                       const float* gamma, const float* dres, float* dx, float* dgamma, float* dbeta, int rows,
+                       int channels, tfpp_stream_t stream);
+
+/* fusion attention backward: dqkv (B,T,3C) bf16; dkv_ws (B,T,2C) f32 workspace (zeroed inside). */
+int tfpp_fusion_attn_bwd(const void* qkv, const void* dout, void* dqkv, float* dkv_ws, int batch, int tokens,
+                         int channels, int heads, tfpp_stream_t stream);
+
+int tfpp_small_mha_bwd(const void* q, long long q_sb, long long q_sr, const void* k, long long k_sb, long long k_sr,
+                       const void* v, long long v_sb, long long v_sr, const void* dout, long long o_sb, long long o_sr,
+                       void* dq, long long dq_sb, long long dq_sr, void* dk, long long dk_sb, long long dk_sr, void* dv,
+                       long long dv_sb, long long dv_sr, int accumulate_kv, int batch, int heads, int tq, int tk,
+                       int head_dim, tfpp_stream_t stream);
+
+int tfpp_extra_sensor_token_bwd(const float* ego_vel, const float* command, float vel_mean, float vel_var,
+                                int use_batch_stats, const float* w0, const float* b0, const float* w1, const float* b1,
+                                const float* dmem, long long dmem_stride, float* dw0, float* db0, float* dw1, float* db1,
+                                float* dpos, int batch, int n_cmd, int hidden, int d_model, tfpp_stream_t stream);
+
+int tfpp_planner_head_bwd(const float* joined, const float* target_point, const float* h_all, const float* w_enc,
+                          const float* b_enc, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                          const float* w_dec, const float* w_ts0, const float* b_ts0, const float* w_ts1,
+                          const float* dcp, const float* dlogits, float* djoined, float* dw_enc, float* db_enc,
+                          float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, float* dw_dec, float* db_dec,
+                          float* dw_ts0, float* db_ts0, float* dw_ts1, float* db_ts1, int batch, int n_wp, int d_model,
+                          int hidden, int n_speed, tfpp_stream_t stream);
+
+/* fused losses (model.py:394-445, center_net.py:77-123): scalar loss sums + d(weighted loss)/d(pre-activation) */
+int tfpp_ce_map_loss(const float* logits, const long long* labels, const float* valid, float grad_scale,
+                     float* loss_sum, void* dz_nhwc, float* dz_nchw, float* dbias, int batch, int classes,
+                     int channels_padded, int hw, tfpp_stream_t stream);
+int tfpp_l1_sigmoid_loss(const float* p, const float* target, float grad_scale, float* loss_sum, void* dz_nhwc,
+                         float* dbias, int channels_padded, long long n, tfpp_stream_t stream);
+int tfpp_center_head_loss(const float* maps, const float* t_heat, const float* t_wh, const float* t_off,
+                          const long long* t_ycls, const float* t_yres, const float* pix_w, const float* avg_factor,
+                          const float* w5, float* losses, void* dz, float* dbias, int batch, int hw, int n_cls,
+                          int n_bins, int channels_padded, tfpp_stream_t stream);
+int tfpp_planner_loss(const float* logits, const long long* labels, const float* class_w, const float* cp,
+                      const float* cp_t, float w_ts, float w_cp, float* losses, float* dlogits, float* dcp, int batch,
+                      int n_cls, int n_cp, tfpp_stream_t stream);
+
+/* AdamW(amsgrad=True), torch semantics; grad_scale multiplies the gradient first (1/world_size after a sum
+ * all-reduce). */
+int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
+                       long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                       float grad_scale, tfpp_stream_t stream);
 
 #ifdef __cplusplus
 }

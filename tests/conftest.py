@@ -26,18 +26,7 @@ def state_shapes():
 
 
 @pytest.fixture(scope='session')
-def oracle_state(state_shapes):
-  """The seeded state_dict every golden forward was made with (tests/golden/make_golden.py)."""
-  import numpy as np
-  import torch
+def oracle_state():
+  """The seeded, BatchNorm-calibrated state_dict every golden forward was made with (tests/golden/make_golden.py)."""
   from carla_garage_b200 import synth
-  from oracle import tfpp_oracle as orc
-  valid = torch.from_numpy(np.load(os.path.join(GOLDEN, 'valid_bev_pixels.npz'))['valid']).float()
-  fixed = {
-      'valid_bev_pixels': valid,
-      'valid_bev_pixels_inv': 1.0 - valid,
-      'loss_speed.weight': torch.tensor(orc.DEFAULT_CFG['target_speed_weights']),
-      'loss_semantic.weight': torch.ones(7),
-      'loss_bev_semantic.weight': torch.ones(11),
-  }
-  return synth.make_state_dict(state_shapes, seed=0, fixed=fixed)
+  return synth.golden_state(GOLDEN)

@@ -60,6 +60,26 @@ def main():
   net.load_state_dict(sd, strict=True)
   B = 2
   inp = synth.make_inputs(B, seed=11)
+  # Calibrate the BatchNorm running statistics like a trained checkpoint's would be (running stats == statistics of
+  # the data): one training-mode pass with momentum 1.  Purely random running stats make the eval-mode residual
+  # stream grow ~1.4x per block (7.8e5 after stage 3), an ill-conditioned network no bf16 path can track.
+  net.train()
+  bns = [m for m in net.modules() if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d))]
+  for m in bns:
+    m.momentum = 1.0
+  for m in net.modules():
+    if isinstance(m, torch.nn.Dropout):
+      m.p = 0.0
+    if isinstance(m, torch.nn.MultiheadAttention):
+      m.dropout = 0.0
+  with torch.no_grad():
+    net(**inp)  # calibrate on the evaluation batch itself: eval-mode statistics == batch statistics
+  for m in bns:
+    m.momentum = 0.1
+  calib = {k: v.clone() for k, v in net.state_dict().items() if k.endswith('running_mean') or k.endswith('running_var')}
+  np.savez_compressed(os.path.join(OUT, 'bn_calib.npz'), **{k: v.numpy() for k, v in calib.items()})
+  sd.update(calib)
+  net.load_state_dict(sd, strict=True)
   taps = {}
   hooks = []
   bb = net.backbone
@@ -100,6 +120,23 @@ def main():
     g['norm_' + n] = np.array(float(t.norm()))
   boxes = net.head.get_bboxes(*out[6])
   g['boxes'] = boxes.numpy()
+  # noise floor of bf16 storage on this state (oracle/bf16_emulation.py); the oracle == reference to 1e-6
+  from oracle import bf16_emulation  # pylint: disable=import-outside-toplevel
+  etaps = {}
+  eout = bf16_emulation.forward(sd, inp, taps=etaps)
+
+  def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+  for k, t in etaps.items():
+    if k in taps:
+      g['bf16floor_' + k] = np.array(rel(t, taps[k]))
+  for n, i in (('pred_target_speed', 1), ('pred_checkpoint', 2), ('pred_semantic', 3), ('pred_bev_semantic', 4),
+               ('pred_depth', 5)):
+    g['bf16floor_' + n] = np.array(rel(eout[i], out[i]))
+  for n, a, b in zip(('heatmap', 'wh', 'offset', 'yaw_class', 'yaw_res'), eout[6][:5], out[6][:5]):
+    g['bf16floor_bb_' + n] = np.array(rel(a, b))
+  print({k: float(v) for k, v in g.items() if k.startswith('bf16floor_')})
   np.savez_compressed(os.path.join(OUT, 'forward_eval_b2.npz'), **g)
 
   # ---- train mode (batch-stat BN), dropout disabled, losses + a few gradients ----

@@ -261,3 +261,37 @@ def test_decode_heatmap(ops):
   assert rel(got, want) < 1e-6
   g = np.load(os.path.join(GOLDEN, 'forward_eval_b2.npz'))
   assert g['boxes'].shape == (2, 100, 9)
+
+
+# ------------------------------------------------------------------------------------------------ backward GEMMs
+@pytest.mark.parametrize('b,h,w,cin,cout', [(2, 8, 32, 1512, 128), (2, 64, 64, 64, 320), (4, 16, 64, 72, 216),
+                                            (3, 8, 8, 576, 576), (1, 1, 640, 216, 864)])
+def test_wgrad_dense(ops, b, h, w, cin, cout):
+  x, dy = bf(rnd(b, h, w, cin, seed=40)), bf(rnd(b, h, w, cout, seed=41))
+  xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+  for k, taps in ((1, ops.TAPS_1X1), (3, ops.TAPS_3X3)):
+    if k == 3 and h == 1:
+      continue
+    wt = torch.zeros(cout, cin, k, k, device='cuda', requires_grad=True)
+    y = F.conv2d(xf, wt, None, padding=k // 2)
+    (gw,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+    got = ops.conv_wgrad(dy, x, taps=taps)  # (cout, taps, cin)
+    want = gw.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    assert rel(got, want) < 2e-3, (k, rel(got, want))
+
+
+@pytest.mark.parametrize('b,h,w,c', [(2, 16, 64, 72), (1, 32, 32, 216), (2, 8, 8, 1512)])
+def test_wgrad_grouped_and_stride2(ops, b, h, w, c):
+  x, dy = bf(rnd(b, h, w, c, seed=42)), bf(rnd(b, h, w, c, seed=43))
+  xf = x.float().permute(0, 3, 1, 2)
+  wt = torch.zeros(c, 24, 3, 3, device='cuda', requires_grad=True)
+  y = F.conv2d(xf, wt, None, padding=1, groups=c // 24)
+  (gw,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+  got = ops.conv_wgrad(dy, x, taps=ops.TAPS_3X3, group_width=24)
+  assert rel(got, gw.permute(0, 2, 3, 1).reshape(c, 9, 24)) < 2e-3
+  # stride 2: dy at half resolution, x as parity planes
+  dy2 = bf(rnd(b, h // 2, w // 2, c, seed=44))
+  y = F.conv2d(xf, wt, None, stride=2, padding=1, groups=c // 24)
+  (gw,) = torch.autograd.grad(y, wt, dy2.float().permute(0, 3, 1, 2))
+  got = ops.conv_wgrad(dy2, ops.parity_split(x), taps=ops.taps_3x3_stride2(b), group_width=24)
+  assert rel(got, gw.permute(0, 2, 3, 1).reshape(c, 9, 24)) < 2e-3
