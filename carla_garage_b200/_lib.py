@@ -34,7 +34,7 @@ class WgradArgs(ctypes.Structure):
   """tfpp_wgrad_args (include/tfpp.h)."""
   _fields_ = [
       ('dy', c_void_p), ('x', c_void_p), ('dw', c_void_p),
-      ('batch', c_int), ('height', c_int), ('width', c_int), ('cout', c_int),
+      ('batch', c_int), ('height', c_int), ('width', c_int), ('cout', c_int), ('cout_valid', c_int),
       ('x_batch', c_int), ('x_channels', c_int), ('x_batch_stride', c_ll),
       ('cin', c_int), ('group_width', c_int), ('dw_s_co', c_ll), ('dw_s_tap', c_ll), ('dw_s_ci', c_ll), ('ntaps', c_int),
       ('tap_dx', c_int * 9), ('tap_dy', c_int * 9), ('tap_db', c_int * 9), ('tap_w', c_int * 9),
@@ -113,6 +113,20 @@ def load():
   return lib
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
+_KERNELS_PER_CALL = {'tfpp_pillar_scatter': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 2, 'tfpp_fusion_attn_bwd': 2}
+_LAUNCHES = [0]
+
+
+def reset_launch_count():
+  _LAUNCHES[0] = 0
+
+
+def launch_count():
+  return _LAUNCHES[0]
+
+
 def check(rc, what):
+  _LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 1)
   if rc != 0:
     raise RuntimeError(f'{what} failed (rc={rc}): {load().tfpp_last_error().decode()}')

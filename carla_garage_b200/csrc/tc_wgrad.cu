@@ -191,7 +191,7 @@ extern "C" int tfpp_conv_wgrad(const tfpp_wgrad_args* a, tfpp_stream_t stream_) 
   p.p_tiles = p.p_tiles_x * p.p_tiles_y * p.p_tiles_b;
   p.grouped = a->group_width > 0;
   p.group_width = a->group_width;
-  p.cout = a->cout;
+  p.cout = a->cout_valid > 0 ? a->cout_valid : a->cout;
   p.cin = a->cin;
   p.ntaps = a->ntaps;
   p.s_co = a->dw_s_co; p.s_tap = a->dw_s_tap; p.s_ci = a->dw_s_ci;

@@ -12,6 +12,7 @@ from . import ops
 from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_GELU, BF16, F32
 
 _PACK_CACHE = {}
+PARAM_EPOCH = [0]  # bumped by the fused optimizer (it updates parameter storage without touching version counters)
 
 
 def packed(params, kind, *extra):
@@ -19,7 +20,7 @@ def packed(params, kind, *extra):
   load_state_dict, .to(device))."""
   params = params if isinstance(params, (tuple, list)) else (params,)
   key = (kind,) + tuple(id(p) for p in params) + extra
-  ver = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)  # pylint: disable=protected-access
+  ver = (PARAM_EPOCH[0],) + tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)  # pylint: disable=protected-access
   hit = _PACK_CACHE.get(key)
   if hit is not None and hit[0] == ver:
     return hit[1]
@@ -30,6 +31,33 @@ def packed(params, kind, *extra):
       out = ops.pack_grouped_conv_weight(params[0])
     elif kind == 'linear':
       out = params[0].detach().reshape(params[0].shape[0], -1).to(BF16).contiguous()
+    elif kind == 'conv_t':  # dgrad operand (Cin, taps, Cout padded to a multiple of 8)
+      w = ops.pack_conv_weight_t(params[0])
+      pad = (-w.shape[2]) % 8
+      out = torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
+    elif kind == 'gconv_t':
+      out = ops.pack_grouped_conv_weight_t(params[0])
+    elif kind == 'linear_t':  # (N,K) -> (K, N padded to 8)
+      w = params[0].detach().reshape(params[0].shape[0], -1).t().to(BF16).contiguous()
+      pad = (-w.shape[1]) % 8
+      out = torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
+    elif kind == 'rows_t':
+      out = params[0].detach()[extra[0]:extra[1]].t().to(BF16).contiguous()
+    elif kind == 'cat_linear_t':
+      out = torch.cat([p.detach().reshape(p.shape[0], -1) for p in params], dim=0).t().to(BF16).contiguous()
+    elif kind == 'cat_conv_t':  # several convs stacked along Cout -> (Cin, taps, sum Cout)
+      out = torch.cat([ops.pack_conv_weight_t(p) for p in params], dim=2).contiguous()
+    elif kind == 'blockdiag_1x1_t':  # transpose of blockdiag_1x1: (sum K_i, 1, sum N_i padded to 8)
+      n = sum(p.shape[0] for p in params)
+      k = sum(p.shape[1] for p in params)
+      npad = n + ((-n) % 8)
+      out = torch.zeros((k, 1, npad), dtype=F32, device=params[0].device)
+      r = c = 0
+      for p in params:
+        out[c:c + p.shape[1], 0, r:r + p.shape[0]] = p.detach().reshape(p.shape[0], p.shape[1]).t()
+        r += p.shape[0]
+        c += p.shape[1]
+      out = out.to(BF16).contiguous()
     elif kind == 'rows':  # row slice of a (N,K) matrix
       out = params[0].detach()[extra[0]:extra[1]].to(BF16).contiguous()
     elif kind == 'rows_f32':
@@ -117,7 +145,7 @@ class Engine:
       self.debug_taps[name] = t
 
   def conv_bn(self, a, cna, training, *, taps=ops.TAPS_1X1, batch=None, grouped=False, act=ACT_NONE, res=None,
-              res_bn=None, want_pool=False):
+              res_bn=None, want_pool=False, a_src=None):
     """ConvNormAct (timm ConvBnAct): conv -> BatchNorm2d -> act, optionally (+ res) before act and per-sample channel
     sums for squeeze-excite.  Training: batch statistics from the GEMM epilogue, one apply pass.  Eval: everything in
     the GEMM epilogue.  res_bn = (raw, scale, shift): residual that still needs its own BatchNorm affine."""
@@ -140,8 +168,8 @@ class Engine:
                                 pool_sum=pool)
       else:
         y = ops.scale_shift_act(raw, scale, shift, act, res=res, pool_sum=pool)
-      self._save(op='conv_bn', a=a, raw=raw, y=y, scale=scale, mean=mean, invstd=invstd, cna=cna, taps=taps,
-                 batch=batch, grouped=grouped, act=act, res=res, res_bn=res_bn, count=count)
+      self._save(op='conv_bn', a=a, a_src=a_src, raw=raw, y=y, mean=mean, invstd=invstd, cna=cna, taps=taps,
+                 batch=batch, grouped=grouped, act=act, res=res, res_bn=res_bn)
       return (y, pool) if want_pool else y
     scale, shift = packed((bn.weight, bn.bias, bn.running_mean, bn.running_var), 'bn_eval', bn.eps)
     y = ops.conv_gemm(a, w, taps=taps, batch=batch, scale=scale, shift=shift, act=act, res1=res, **gkw)
@@ -167,21 +195,23 @@ class Engine:
     a1 = self.conv_bn(x, blk.conv1, training, act=ACT_RELU)
     if s == 2:
       a1p = ops.parity_split(a1)
-      self._save(op='parity_split', x=a1)
       a2, pool = self.conv_bn(a1p, blk.conv2, training, taps=ops.taps_3x3_stride2(b), batch=b, grouped=True,
-                              act=ACT_RELU, want_pool=True)
+                              act=ACT_RELU, want_pool=True, a_src=a1)
       ho, wo = h // 2, w // 2
     else:
       a2, pool = self.conv_bn(a1, blk.conv2, training, taps=ops.TAPS_3X3, grouped=True, act=ACT_RELU, want_pool=True)
       ho, wo = h, w
     se = blk.se
-    gate = ops.se_gate(pool, ho * wo, se.fc1.weight, se.fc1.bias, se.fc2.weight, se.fc2.bias)
+    hidden = None
+    if self.tape is not None:
+      gate, hidden = ops.se_gate(pool, ho * wo, se.fc1.weight, se.fc1.bias, se.fc2.weight, se.fc2.bias,
+                                 want_hidden=True)
+    else:
+      gate = ops.se_gate(pool, ho * wo, se.fc1.weight, se.fc1.bias, se.fc2.weight, se.fc2.bias)
     a2s = ops.channel_scale(a2, gate)
-    self._save(op='se', a2=a2, pool=pool, gate=gate, se=se, hw=ho * wo)
+    self._save(op='se', a2=a2, a2s=a2s, pool=pool, gate=gate, hidden=hidden, se=se, hw=ho * wo)
     if blk.downsample is not None:
       xp = ops.parity_split(x) if s == 2 else x
-      if s == 2:
-        self._save(op='parity_split', x=x)
       ds = blk.downsample
       if training:
         # raw downsample conv + its batch statistics; its BatchNorm affine is applied inside conv3's apply pass
@@ -193,8 +223,7 @@ class Engine:
                                                    ds.bn.running_var, count, eps=ds.bn.eps, momentum=ds.bn.momentum,
                                                    save=self.tape is not None)
         ds.bn.num_batches_tracked += 1
-        self._save(op='downsample', a=xp, raw=raw_d, scale=sd, mean=mean_d, invstd=invstd_d, cna=ds, batch=b,
-                   count=count)
+        self._save(op='downsample', a=xp, x_src=x, stride=s, raw=raw_d, mean=mean_d, invstd=invstd_d, cna=ds, batch=b)
         return self.conv_bn(a2s, blk.conv3, training, act=ACT_RELU, res_bn=(raw_d, sd, td))
       shortcut = self.conv_bn(xp, ds, training, batch=b)
       return self.conv_bn(a2s, blk.conv3, training, act=ACT_RELU, res=shortcut)
@@ -224,8 +253,8 @@ class Engine:
                                                    save=self.tape is not None)
       bn.num_batches_tracked += 1
       y = ops.scale_shift_act(raw, scale, shift, ACT_RELU)
-      self._save(op='stem', x=x, raw=raw, y=y, scale=scale, mean=mean, invstd=invstd, cna=cna, in_scale=in_scale,
-                 in_shift=in_shift, count=count)
+      self._save(op='stem', x=x, raw=raw, y=y, mean=mean, invstd=invstd, cna=cna, in_scale=in_scale,
+                 in_shift=in_shift)
       return y
     scale, shift = packed((bn.weight, bn.bias, bn.running_mean, bn.running_var), 'bn_eval', bn.eps)
     return ops.stem_conv(x, w, in_scale, in_shift, scale=scale, shift=shift, act=ACT_RELU)
@@ -250,8 +279,8 @@ class Engine:
     l2i = bb.lidar_channel_to_img[i]
     ops.linear(lid_pool.view(b * n_lid, cl), packed(l2i.weight, 'linear'), bias=packed(l2i.bias, 'f32'),
                out=x.view(-1)[n_img * c:], row_map=(n_lid, t), res2=pos[n_img:], res2_strides=(0, 0, c, 1))
-    self._save(op='tokenise', img=img, lid=lid, lid_pool=lid_pool, i=i)
     x = x.view(b * t, c)
+    self._save(op='tokenise', img=img, lid=lid, lid_pool=lid_pool, i=i, x0=x, b=b, t=t, c=c, cl=cl)
     heads = cfg.n_head
     for blk in gpt.blocks:
       at = blk.attn
@@ -264,8 +293,8 @@ class Engine:
       h2, _, mean2, rstd2 = ops.layernorm(x1, blk.ln2.weight, blk.ln2.bias, save=self.tape is not None)
       m = ops.linear(h2, packed(blk.mlp[0].weight, 'linear'), bias=packed(blk.mlp[0].bias, 'f32'), act=ACT_RELU)
       x2 = ops.linear(m, packed(blk.mlp[2].weight, 'linear'), bias=packed(blk.mlp[2].bias, 'f32'), res=x1, out_f32=True)
-      self._save(op='gpt_block', x=x, h=h, qkv=qkv, y=y, x1=x1, h2=h2, m=m, blk=blk, mean1=mean1, rstd1=rstd1,
-                 mean2=mean2, rstd2=rstd2, b=b, t=t, c=c)
+      self._save(op='gpt_block', x=x, h=h, qkv=qkv, y=y, x1=x1, h2=h2, m=m, x2=x2, blk=blk, mean1=mean1, rstd1=rstd1,
+                 mean2=mean2, rstd2=rstd2, b=b, t=t, c=c, heads=heads)
       x = x2
     xf, _, meanf, rstdf = ops.layernorm(x, gpt.ln_f.weight, gpt.ln_f.bias, save=self.tape is not None)
     # image tokens: bilinear up-sample straight out of the token matrix + residual add (transfuser.py:239-242,254)
@@ -276,7 +305,8 @@ class Engine:
     ops.conv_gemm(xf.view(-1)[n_img * c:], packed(i2l.weight, 'linear').view(cl, 1, c), a_shape=(b, 1, n_lid, c),
                   a_batch_stride=t * c, shift=packed(i2l.bias, 'f32'), out=lid_tok, out_strides=(n_lid * cl, 0, cl, 1))
     lid_out = ops.bilinear(lid_tok, b, ph_l, pw_l, hl, wl, cl, add=lid)
-    self._save(op='untokenise', x=x, xf=xf, lid_tok=lid_tok, i=i, meanf=meanf, rstdf=rstdf, b=b)
+    self._save(op='untokenise', x=x, xf=xf, lid_tok=lid_tok, i=i, meanf=meanf, rstdf=rstdf, b=b, t=t, c=c, cl=cl,
+               img=img, lid=lid, img_out=img_out, lid_out=lid_out)
     return img_out, lid_out
 
   # ------------------------------------------------------------------------------------------------ backbone
@@ -307,12 +337,12 @@ class Engine:
       p5 = self.conv_bias(lid, bb.c5_conv, ACT_RELU)
       up = cfg.bev_upsample_factor
       p5u = ops.bilinear(p5, b, p5.shape[1], p5.shape[2], p5.shape[1] * up, p5.shape[2] * up, p5.shape[3])
-      self._save(op='bilinear', src=p5)
+      self._save(op='bilinear', src=p5, out=p5u)
       p4 = self.conv_bias(p5u, bb.up_conv5, ACT_RELU)
       th = cfg.lidar_resolution_height // cfg.bev_down_sample_factor
       tw = cfg.lidar_resolution_width // cfg.bev_down_sample_factor
       p4u = ops.bilinear(p4, b, p4.shape[1], p4.shape[2], th, tw, p4.shape[3])
-      self._save(op='bilinear', src=p4)
+      self._save(op='bilinear', src=p4, out=p4u)
       feats = self.conv_bias(p4u, bb.up_conv4, ACT_RELU)
     grid = img if (cfg.use_semantic or cfg.use_depth) else None
     self._tap('bev_feature_grid', feats)
@@ -328,12 +358,12 @@ class Engine:
     x = self.conv_bias(x, dec.deconv1[2], ACT_RELU)
     s0 = dec.scale_factor_0
     xu = ops.bilinear(x, b, x.shape[1], x.shape[2], x.shape[1] * s0, x.shape[2] * s0, x.shape[3])
-    self._save(op='bilinear', src=x)
+    self._save(op='bilinear', src=x, out=xu)
     x = self.conv_bias(xu, dec.deconv2[0], ACT_RELU)
     x = self.conv_bias(x, dec.deconv2[2], ACT_RELU)
     s1 = dec.scale_factor_1
     xu = ops.bilinear(x, b, x.shape[1], x.shape[2], x.shape[1] * s1, x.shape[2] * s1, x.shape[3])
-    self._save(op='bilinear', src=x)
+    self._save(op='bilinear', src=x, out=xu)
     x = self.conv_bias(xu, dec.deconv3[0], ACT_RELU)
     return self.conv_bias(x, dec.deconv3[2], act_last, out_layout='nchw', out_f32=True)
 
@@ -351,7 +381,7 @@ class Engine:
     b1 = packed(tuple(c.bias for c in convs1), 'cat_f32')
     ncls = convs1[0].weight.shape[0]
     out = ops.conv_gemm(h, w1, shift=b1, act=ACT_SIGMOID, act_n_limit=ncls, out_layout='nchw', out_f32=True)
-    self._save(op='center_head', feat=feat, h=h, out=out)
+    self._save(op='center_head', feat=feat, h=h, out=out, convs0=convs0, convs1=convs1)
     sizes = [c.weight.shape[0] for c in convs1]
     views, o = [], 0
     for s in sizes:
@@ -386,11 +416,12 @@ class Engine:
     nq = m.checkpoint_query.shape[1]
     x, xb = packed(m.checkpoint_query, 'repeat_rows', b)
     memf = mem.view(b * n_mem, d)
-    wkv = packed(tuple(l.multihead_attn.in_proj_weight for l in layers), 'cat_rows', d, 3 * d)
-    bkv = packed(tuple(l.multihead_attn.in_proj_bias for l in layers), 'cat_rows_f32', d, 3 * d)
-    kv_all = ops.linear(memf, wkv, bias=bkv)  # (B*65, L*2d): [k_l | v_l] per layer
-    kvw = kv_all.shape[1]
-    self._save(op='planner_mem', fused=fused, mem=mem, kv_all=kv_all)
+    kvs = []
+    for l in layers:  # K/V projections of the (layer-independent) memory: one small GEMM per layer
+      kvs.append(ops.linear(memf, packed(l.multihead_attn.in_proj_weight, 'rows', d, 3 * d),
+                            bias=packed(l.multihead_attn.in_proj_bias, 'rows_f32', d, 3 * d)))
+    self._save(op='planner_mem', fused=fused, mem=mem, kvs=kvs, b=b, n_pix=n_pix, n_mem=n_mem, d=d, x0=x,
+               ego_vel=ego_vel, command=command, training=training, posenc=posenc)
     for li, l in enumerate(layers):
       act = ACT_RELU if l.activation is torch.nn.functional.relu else ACT_GELU
       qkv = ops.linear(xb, packed(l.self_attn.in_proj_weight, 'linear'), bias=packed(l.self_attn.in_proj_bias, 'f32'))
@@ -402,8 +433,9 @@ class Engine:
                                       save=self.tape is not None)
       q2 = ops.linear(x1b, packed(l.multihead_attn.in_proj_weight, 'rows', 0, d),
                       bias=packed(l.multihead_attn.in_proj_bias, 'rows_f32', 0, d))
-      ca = ops.small_mha(q2, kv_all, kv_all, b, heads, nq, n_mem, hd, (nq * d, d), (n_mem * kvw, kvw), (n_mem * kvw, kvw),
-                         k_off=li * 2 * d, v_off=li * 2 * d + d)
+      kv = kvs[li]
+      ca = ops.small_mha(q2, kv, kv, b, heads, nq, n_mem, hd, (nq * d, d), (n_mem * 2 * d, 2 * d), (n_mem * 2 * d, 2 * d),
+                         v_off=d)
       t2 = ops.linear(ca, packed(l.multihead_attn.out_proj.weight, 'linear'),
                       bias=packed(l.multihead_attn.out_proj.bias, 'f32'), res=x1, out_f32=True)
       x2b, x2, m2, r2 = ops.layernorm(t2, l.norm2.weight, l.norm2.bias, want_f32=True, eps=l.norm2.eps,
@@ -412,8 +444,9 @@ class Engine:
       t3 = ops.linear(ff, packed(l.linear2.weight, 'linear'), bias=packed(l.linear2.bias, 'f32'), res=x2, out_f32=True)
       x3b, x3, m3, r3 = ops.layernorm(t3, l.norm3.weight, l.norm3.bias, want_f32=True, eps=l.norm3.eps,
                                       save=self.tape is not None)
-      self._save(op='dec_layer', li=li, xb=xb, qkv=qkv, sa=sa, t1=t1, x1b=x1b, q2=q2, ca=ca, t2=t2, x2b=x2b, ff=ff, t3=t3,
-                 stats=(m1, r1, m2, r2, m3, r3), act=act)
+      self._save(op='dec_layer', li=li, layer=l, x_in=x, xb=xb, qkv=qkv, sa=sa, t1=t1, x1=x1, x1b=x1b, q2=q2, kv=kv, ca=ca,
+                 t2=t2, x2=x2, x2b=x2b, ff=ff, t3=t3, x3=x3, stats=(m1, r1, m2, r2, m3, r3), act=act, b=b, nq=nq,
+                 n_mem=n_mem, d=d, heads=heads, hd=hd)
       x, xb = x3, x3b
     _, joined, mj, rj = ops.layernorm(x, m.join.norm.weight, m.join.norm.bias, want_bf16=False, want_f32=True,
                                       eps=m.join.norm.eps, save=self.tape is not None)
@@ -423,7 +456,8 @@ class Engine:
                            cd.gru.weight_ih_l0, cd.gru.weight_hh_l0, cd.gru.bias_ih_l0, cd.gru.bias_hh_l0,
                            cd.decoder.weight, cd.decoder.bias, tsn[0].weight, tsn[0].bias, tsn[2].weight, tsn[2].bias,
                            want_h=self.tape is not None)
-    self._save(op='planner_head', x=x, joined=joined, stats=(mj, rj), res=res)
+    self._save(op='planner_head', x=x, joined=joined, stats=(mj, rj), res=res, target_point=target_point, b=b, nq=nq,
+               d=d)
     self._tap('joined', joined.view(b, nq, d))
     return res[0], res[1]
 
@@ -446,7 +480,7 @@ class Engine:
       ncls = dec[2].weight.shape[0]
       pred_bev_semantic = ops.bilinear_nchw_mask(x, ncls, cfg.lidar_resolution_height, cfg.lidar_resolution_width,
                                                  packed(m.valid_bev_pixels, 'f32'))
-      self._save(op='bev_tail', src=x)
+      self._save(op='bev_tail', src=x, out=pred_bev_semantic, ncls=ncls)
     if cfg.detect_boxes:
       pred_bounding_box = self.center_head_forward(feats)
     return (None, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth, pred_bounding_box,

@@ -27,6 +27,25 @@ def taps_3x3_stride2(batch):
   return tuple(taps)
 
 
+_PROFILE = None
+
+
+def profile_gemm_launches(fn):
+  """Run fn() once with CUDA events (on the launching stream) around every tcgen05 GEMM launch; returns the summed
+  device time, the algorithmic FLOPs and the achieved TFLOP/s of that kernel family."""
+  global _PROFILE  # pylint: disable=global-statement
+  _PROFILE = []
+  try:
+    fn()
+    torch.cuda.synchronize()
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in _PROFILE)
+    flop = sum(f for _, _, f in _PROFILE)
+    n = len(_PROFILE)
+  finally:
+    _PROFILE = None
+  return {'ms': ms, 'gflop': flop / 1e9, 'launches': n, 'tflops': flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+
+
 def _stream():
   return torch.cuda.current_stream().cuda_stream
 
@@ -135,7 +154,14 @@ def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1
   args.act_n_limit = act_n_limit
   if stats is not None:
     args.stat_sum, args.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
+  if _PROFILE is not None:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
   check(_lib.load().tfpp_conv_gemm(ctypes.byref(args), _stream()), 'tfpp_conv_gemm')
+  if _PROFILE is not None:
+    e1.record()
+    k_alg = 24 if a_c_per_ntile else args.k_per_tile
+    _PROFILE.append((e0, e1, 2.0 * b * h * wd * n * k_alg * len(taps)))
   return out
 
 
@@ -149,7 +175,7 @@ def pick_tile64(height, width):
 
 
 def conv_wgrad(dy, x, *, cin=None, taps=TAPS_1X1, w_taps=None, group_width=0, x_batch_stride=0, x_shape=None, bn=0,
-               splits=0, out=None, out_strides=None, dy_shape=None):
+               splits=0, out=None, out_strides=None, dy_shape=None, cout_valid=0):
   """dw[co, tap, ci] = sum_pixels dy[pixel, co] * x[pixel + tap, ci]; dy (B,H,W,Cout) bf16, x (Bx,H,W,Cx) bf16.
   Returns fp32 (Cout, w_taps, cin) (dense) or (Cout, w_taps, group_width) (grouped); accumulates into ``out``."""
   if dy_shape is None:
@@ -166,11 +192,11 @@ def conv_wgrad(dy, x, *, cin=None, taps=TAPS_1X1, w_taps=None, group_width=0, x_
   w_taps = len(taps) if w_taps is None else w_taps
   if out is None:
     kdim = group_width if group_width else cin
-    out = torch.zeros((cout, w_taps, kdim), dtype=F32, device=dy.device)
+    out = torch.zeros((cout_valid or cout, w_taps, kdim), dtype=F32, device=dy.device)
     out_strides = (w_taps * kdim, kdim, 1)
   a = WgradArgs()
   a.dy, a.x, a.dw = dy.data_ptr(), x.data_ptr(), out.data_ptr()
-  a.batch, a.height, a.width, a.cout = b, h, w, cout
+  a.batch, a.height, a.width, a.cout, a.cout_valid = b, h, w, cout, cout_valid
   a.x_batch, a.x_channels, a.x_batch_stride = xb, cx, x_batch_stride
   a.cin, a.group_width, a.ntaps = cin, group_width, len(taps)
   a.dw_s_co, a.dw_s_tap, a.dw_s_ci = out_strides
@@ -178,7 +204,13 @@ def conv_wgrad(dy, x, *, cin=None, taps=TAPS_1X1, w_taps=None, group_width=0, x_
     a.tap_dx[i], a.tap_dy[i], a.tap_db[i], a.tap_w[i] = dx, dy_, db, tw_
   a.tw, a.th, a.nb = pick_tile64(h, w)
   a.bn, a.splits = bn, splits
+  if _PROFILE is not None:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
   check(_lib.load().tfpp_conv_wgrad(ctypes.byref(a), _stream()), 'tfpp_conv_wgrad')
+  if _PROFILE is not None:
+    e1.record()
+    _PROFILE.append((e0, e1, 2.0 * b * h * w * (cout_valid or cout) * (group_width or cin) * len(taps)))
   return out
 
 
@@ -420,3 +452,139 @@ def pack_grouped_conv_weight(w, group_width=24, groups_per_tile=2):
   idx = base[:, None] + torch.arange(gw, device=w.device)[None, :]
   out.scatter_(2, idx[:, None, :].expand(co, 9, gw), wt)
   return out.to(BF16).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------- backward wrappers
+TAPS_3X3_DGRAD = tuple((1 - kx, 1 - ky, 0, ky * 3 + kx) for ky in range(3) for kx in range(3))
+
+
+def taps_dgrad_stride2(py, px):
+  """Taps of the stride-2 3x3 dgrad for the input parity plane (py, px): input row 2u+py receives W[ky] * dY[u+dy]
+  for ky == py+1 (mod 2): py=0 -> (ky=1, dy=0); py=1 -> (ky=0, dy=+1), (ky=2, dy=0)."""
+  ys = ((1, 0),) if py == 0 else ((0, 1), (2, 0))
+  xs = ((1, 0),) if px == 0 else ((0, 1), (2, 0))
+  return tuple((dx, dy, 0, ky * 3 + kx) for ky, dy in ys for kx, dx in xs)
+
+
+def pack_conv_weight_t(w):
+  """(Cout, Cin, kh, kw) f32 -> (Cin, kh*kw, Cout) bf16 (dgrad operand; taps not flipped, see TAPS_3X3_DGRAD)."""
+  co, ci, kh, kw = w.shape
+  return w.detach().permute(1, 2, 3, 0).reshape(ci, kh * kw, co).to(BF16).contiguous()
+
+
+def pack_grouped_conv_weight_t(w, group_width=24):
+  """Grouped (Cout, gw, 3, 3) -> dgrad pack (C, 9, 64): in/out swapped inside each group."""
+  co, gw, kh, kw = w.shape
+  g = co // gw
+  wt = w.detach().view(g, gw, gw, kh, kw).permute(0, 2, 1, 3, 4).reshape(co, gw, kh, kw)
+  return pack_grouped_conv_weight(wt, group_width)
+
+
+def bn_bwd(dy, y, raw, mean, invstd, gamma, act, dgamma, dbeta, gate=None, pool_grad=None, want_dz=False):
+  b, h, w, c = raw.shape
+  draw = torch.empty_like(raw)
+  dz = torch.empty_like(raw) if want_dz else None
+  check(_lib.load().tfpp_bn_bwd(dy.data_ptr(), _p(y), raw.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                gamma.data_ptr(), _p(gate), _p(pool_grad), act, dbeta.data_ptr(), dgamma.data_ptr(),
+                                draw.data_ptr(), _p(dz), b, h * w, c, _stream()), 'tfpp_bn_bwd')
+  return draw, dz
+
+
+def se_bwd(dout, a2, gate, hidden, pool_sum, hw, w1, w2, dw1, db1, dw2, db2):
+  b, c = gate.shape
+  rd = w1.shape[0]
+  dgate = torch.zeros((b, c), dtype=F32, device=gate.device)
+  pool_grad = torch.empty((b, c), dtype=F32, device=gate.device)
+  check(_lib.load().tfpp_se_bwd(dout.data_ptr(), a2.data_ptr(), gate.data_ptr(), hidden.data_ptr(), pool_sum.data_ptr(),
+                                hw, w1.data_ptr(), w2.data_ptr(), dgate.data_ptr(), dw1.data_ptr(), db1.data_ptr(),
+                                dw2.data_ptr(), db2.data_ptr(), pool_grad.data_ptr(), b, c, rd, _stream()),
+        'tfpp_se_bwd')
+  return pool_grad
+
+
+def act_bwd(dy, y, act, batch, hw, channels, layout=0, act_n_limit=0, dy_scale=1.0, dbias=None, channels_padded=None,
+            want_dz=True):
+  cp = channels if channels_padded is None else channels_padded
+  dz = torch.empty((batch * hw, cp), dtype=BF16, device=dy.device) if want_dz else None
+  check(_lib.load().tfpp_act_bwd(dy.data_ptr(), _p(y), layout, act, act_n_limit, dy_scale, _p(dz), _p(dbias), batch, hw,
+                                 channels, cp, _stream()), 'tfpp_act_bwd')
+  return dz
+
+
+def bilinear_bwd(dout, dsrc, batch, sh, sw, dh, dw, channels, src_batch_stride=None, src_row_stride=None,
+                 accumulate=False, dsrc_offset=0):
+  if src_batch_stride is None:
+    src_batch_stride = sh * sw * channels
+  if src_row_stride is None:
+    src_row_stride = channels
+  ptr = dsrc.data_ptr() + dsrc_offset * dsrc.element_size()
+  check(_lib.load().tfpp_bilinear_bwd(dout.data_ptr(), ptr, int(dsrc.dtype == F32), src_batch_stride, src_row_stride,
+                                      int(accumulate), batch, sh, sw, dh, dw, channels, _stream()), 'tfpp_bilinear_bwd')
+  return dsrc
+
+
+def bilinear_nchw_mask_bwd(dout, mask, batch, sh, sw, src_channels, channels, dh, dw):
+  dsrc = torch.empty((batch, sh, sw, src_channels), dtype=BF16, device=dout.device)
+  check(_lib.load().tfpp_bilinear_nchw_mask_bwd(dout.data_ptr(), _p(mask), dsrc.data_ptr(), batch, sh, sw, src_channels,
+                                                channels, dh, dw, _stream()), 'tfpp_bilinear_nchw_mask_bwd')
+  return dsrc
+
+
+def pool_bwd_add(dout, dtok, shape, ph, pw, rows_per_batch, row0):
+  b, h, w, c = shape
+  out = torch.empty(shape, dtype=BF16, device=dtok.device)
+  check(_lib.load().tfpp_pool_bwd_add(_p(dout), dtok.data_ptr(), int(dtok.dtype == F32), out.data_ptr(), b, h, w, c, ph,
+                                      pw, rows_per_batch, row0, _stream()), 'tfpp_pool_bwd_add')
+  return out
+
+
+def add_bf16(a, b, out=None):
+  out = torch.empty_like(a) if out is None else out
+  check(_lib.load().tfpp_add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), 'tfpp_add_bf16')
+  return out
+
+
+def cast_rows(x, groups, group_rows, row0, rows, channels, dbias=None):
+  out = torch.empty((groups * rows, channels), dtype=BF16, device=x.device)
+  check(_lib.load().tfpp_cast_rows(x.data_ptr(), out.data_ptr(), _p(dbias), groups, group_rows, row0, rows, channels,
+                                   _stream()), 'tfpp_cast_rows')
+  return out
+
+
+def batch_reduce(x, out, batch):
+  check(_lib.load().tfpp_batch_reduce(x.data_ptr(), out.data_ptr(), batch, out.numel(), _stream()), 'tfpp_batch_reduce')
+
+
+def stem_wgrad(x, draw, in_scale, in_shift, dw):
+  b, cin, h, w = x.shape
+  check(_lib.load().tfpp_stem_wgrad(x.data_ptr(), draw.data_ptr(), _p(in_scale), _p(in_shift), dw.data_ptr(), b, cin, h,
+                                    w, _stream()), 'tfpp_stem_wgrad')
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
+  rows, c = x.shape
+  dx = torch.empty((rows, c), dtype=F32, device=x.device)
+  check(_lib.load().tfpp_layernorm_bwd(dy.data_ptr(), int(dy.dtype == F32), x.data_ptr(), mean.data_ptr(),
+                                       rstd.data_ptr(), gamma.data_ptr(), _p(dres), dx.data_ptr(), dgamma.data_ptr(),
+                                       dbeta.data_ptr(), rows, c, _stream()), 'tfpp_layernorm_bwd')
+  return dx
+
+
+def fusion_attn_bwd(qkv, dout, batch, tokens, channels, heads):
+  dqkv = torch.empty_like(qkv)
+  ws = torch.empty((batch * tokens, 2 * channels), dtype=F32, device=qkv.device)
+  check(_lib.load().tfpp_fusion_attn_bwd(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), batch, tokens,
+                                         channels, heads, _stream()), 'tfpp_fusion_attn_bwd')
+  return dqkv
+
+
+def small_mha_bwd(q, k, v, dout, dq, dk, dv, batch, heads, tq, tk, head_dim, q_st, k_st, v_st, dq_st, dk_st, dv_st,
+                  offs=(0, 0, 0, 0, 0, 0), accumulate_kv=False):
+  """offs: element offsets of (q, k, v, dq, dk, dv) inside their buffers; *_st = (batch stride, row stride)."""
+  d = heads * head_dim
+  p = lambda t, o: t.data_ptr() + 2 * o
+  check(_lib.load().tfpp_small_mha_bwd(p(q, offs[0]), q_st[0], q_st[1], p(k, offs[1]), k_st[0], k_st[1], p(v, offs[2]),
+                                       v_st[0], v_st[1], dout.data_ptr(), tq * d, d, p(dq, offs[3]), dq_st[0], dq_st[1],
+                                       p(dk, offs[4]), dk_st[0], dk_st[1], p(dv, offs[5]), dv_st[0], dv_st[1],
+                                       int(accumulate_kv), batch, heads, tq, tk, head_dim, _stream()),
+        'tfpp_small_mha_bwd')

@@ -1,0 +1,662 @@
+"""Training step of TransFuser++ on the libtfpp.so kernels: fused losses, hand-scheduled backward over the engine's
+tape, flat fp32 master parameters with a fused AdamW(amsgrad) step and a bucketed NCCL all-reduce of the flat
+gradient.  Replaces Engine.train's inner loop (team_code/train.py:883-916): forward, sum of weighted losses
+(train.py:452-456,889-896), loss.backward() (train.py:898), optimizer.step() (train.py:908) and DDP's gradient
+all-reduce (train.py:516).  Dropout (embd/attn/resid_pdrop = 0.1 and nn.TransformerDecoderLayer's 0.1) is not applied
+— see DESIGN.md "Dropout".
+"""
+import torch
+
+from . import engine as eng_mod
+from . import ops
+from .engine import packed
+from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32
+
+LOSS_KEYS = ('loss_target_speed', 'loss_checkpoint', 'loss_semantic', 'loss_bev_semantic', 'loss_depth',
+             'loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res')
+
+
+def _pad8(n):
+  return n + ((-n) % 8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# flat parameter / gradient / optimizer state
+# ---------------------------------------------------------------------------------------------------------------
+class FlatState:
+  """All trainable parameters re-pointed into ONE fp32 buffer (+ one gradient buffer, + AdamW state buffers).
+
+  Adjacency groups make fused weight-gradient GEMMs write straight into the parameter gradients: (query, key, value)
+  weights / biases of every fusion attention, and the five CenterNet head convs (3x3 weights, 3x3 biases, 1x1 biases).
+  """
+
+  def __init__(self, model):
+    self.model = model
+    params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    by_name = dict(params)
+    ordered, used = [], set()
+
+    def take(names):
+      for n in names:
+        if n in by_name and n not in used:
+          ordered.append((n, by_name[n]))
+          used.add(n)
+
+    for i in range(4):
+      for l in range(len(model.backbone.transformers[i].blocks)):
+        base = f'backbone.transformers.{i}.blocks.{l}.attn.'
+        take([base + 'query.weight', base + 'key.weight', base + 'value.weight'])
+        take([base + 'query.bias', base + 'key.bias', base + 'value.bias'])
+    if hasattr(model, 'head'):
+      heads = model.head.head_names()
+      take([f'head.{h}.0.weight' for h in heads])
+      take([f'head.{h}.0.bias' for h in heads])
+      take([f'head.{h}.2.bias' for h in heads])
+    take([n for n, _ in params])
+    self.names = [n for n, _ in ordered]
+    self.params = [p for _, p in ordered]
+    total = sum(p.numel() for p in self.params)
+    dev = self.params[0].device
+    self.flat = torch.empty(total, dtype=F32, device=dev)
+    self.grad = torch.zeros(total, dtype=F32, device=dev)
+    self.offsets = {}
+    off = 0
+    for n, p in ordered:
+      k = p.numel()
+      self.flat[off:off + k].copy_(p.detach().reshape(-1))
+      p.data = self.flat[off:off + k].view(p.shape)
+      p.grad = self.grad[off:off + k].view(p.shape)
+      self.offsets[id(p)] = (off, k)
+      off += k
+    self.exp_avg = torch.zeros_like(self.flat)
+    self.exp_avg_sq = torch.zeros_like(self.flat)
+    self.max_exp_avg_sq = torch.zeros_like(self.flat)
+    self.step_count = 0
+
+  def g(self, p):
+    """fp32 gradient view of parameter p (same shape)."""
+    off, k = self.offsets[id(p)]
+    return self.grad[off:off + k].view(p.shape)
+
+  def g_span(self, first, last):
+    """contiguous gradient region from parameter ``first`` to parameter ``last`` (adjacency group)."""
+    o0, _ = self.offsets[id(first)]
+    o1, k1 = self.offsets[id(last)]
+    return self.grad[o0:o1 + k1]
+
+  def zero_grad(self):
+    self.grad.zero_()
+
+  def adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, grad_scale=1.0):
+    """optim.AdamW(amsgrad=True).step() (train.py:527-531,908) as one fused kernel over the flat buffers."""
+    from . import _lib  # pylint: disable=import-outside-toplevel
+    self.step_count += 1
+    _lib.check(_lib.load().tfpp_adamw_amsgrad(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                              self.exp_avg_sq.data_ptr(), self.max_exp_avg_sq.data_ptr(),
+                                              self.flat.numel(), lr, betas[0], betas[1], eps, weight_decay,
+                                              self.step_count, grad_scale, ops._stream()),  # pylint: disable=protected-access
+               'tfpp_adamw_amsgrad')
+    eng_mod.PARAM_EPOCH[0] += 1  # parameter storage changed: cached bf16 weight packs must be rebuilt
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------------------------
+def compute_losses(eng, st, outputs, labels, weights):
+  """Fused loss + seed-gradient kernels.  Returns (dict of 10 loss scalars (0-dim device tensors), seeds).
+  ``weights``: dict loss key -> float (train.py:452-456: 1/10 each).  seeds: id(tensor) -> gradient record."""
+  from . import _lib  # pylint: disable=import-outside-toplevel
+  lib = _lib.load()
+  m, cfg = eng.m, eng.cfg
+  _, pred_ts, pred_cp, pred_sem, pred_bev, pred_depth, bb = outputs[:7]
+  dev = pred_ts.device
+  b = pred_ts.shape[0]
+  sums = torch.zeros(16, dtype=F32, device=dev)
+  stream = ops._stream()  # pylint: disable=protected-access
+  seeds = {}
+  losses = {}
+  # target speed CE + checkpoint L1 (model.py:416-420)
+  dlogits = torch.empty_like(pred_ts)
+  dcp = torch.empty_like(pred_cp)
+  _lib.check(lib.tfpp_planner_loss(pred_ts.data_ptr(), labels['target_speed'].data_ptr(),
+                                   packed(m.loss_speed.weight, 'f32').data_ptr(), pred_cp.data_ptr(),
+                                   labels['checkpoint'].data_ptr(), weights['loss_target_speed'],
+                                   weights['loss_checkpoint'], sums[0:2].data_ptr(), dlogits.data_ptr(), dcp.data_ptr(),
+                                   b, pred_ts.shape[1], pred_cp.shape[1] * pred_cp.shape[2], stream), 'planner_loss')
+  losses['loss_target_speed'], losses['loss_checkpoint'] = sums[0], sums[1]
+  seeds['planner'] = (dcp, dlogits)
+  # semantic CE (model.py:423)
+  hw = pred_sem.shape[2] * pred_sem.shape[3]
+  ncls = pred_sem.shape[1]
+  cp = _pad8(ncls)
+  dz = torch.empty((b, pred_sem.shape[2], pred_sem.shape[3], cp), dtype=BF16, device=dev)
+  conv = m.semantic_decoder.deconv3[2]
+  _lib.check(lib.tfpp_ce_map_loss(pred_sem.data_ptr(), labels['semantic'].data_ptr(), None,
+                                  weights['loss_semantic'] / (b * hw), sums[2:3].data_ptr(), dz.data_ptr(), None,
+                                  st.g(conv.bias).data_ptr(), b, ncls, cp, hw, stream), 'ce semantic')
+  losses['loss_semantic'] = sums[2] / (b * hw)
+  seeds[id(pred_sem)] = dz
+  # BEV semantic CE with the frustum mask as ignore_index (model.py:426-431)
+  hwb = pred_bev.shape[2] * pred_bev.shape[3]
+  nb = pred_bev.shape[1]
+  valid = packed(m.valid_bev_pixels, 'f32')
+  n_valid = eng._const('n_valid_bev', lambda: m.valid_bev_pixels.detach().sum().cpu(), 'cpu')  # pylint: disable=protected-access
+  count = float(n_valid) * b
+  dbev = torch.empty_like(pred_bev)
+  _lib.check(lib.tfpp_ce_map_loss(pred_bev.data_ptr(), labels['bev_semantic'].data_ptr(), valid.data_ptr(),
+                                  weights['loss_bev_semantic'] / count, sums[3:4].data_ptr(), None, dbev.data_ptr(),
+                                  None, b, nb, 16, hwb, stream), 'ce bev')
+  losses['loss_bev_semantic'] = sums[3] / count
+  seeds[id(pred_bev)] = dbev
+  # depth L1 on the sigmoid output (model.py:379,434)
+  n = pred_depth.numel()
+  dzd = torch.empty((b, pred_depth.shape[1], pred_depth.shape[2], 8), dtype=BF16, device=dev)
+  convd = m.depth_decoder.deconv3[2]
+  _lib.check(lib.tfpp_l1_sigmoid_loss(pred_depth.data_ptr(), labels['depth'].data_ptr(), weights['loss_depth'] / n,
+                                      sums[4:5].data_ptr(), dzd.data_ptr(), st.g(convd.bias).data_ptr(), 8, n, stream),
+             'l1 depth')
+  losses['loss_depth'] = sums[4] / n
+  seeds['depth'] = dzd
+  # CenterNet head losses (center_net.py:77-123)
+  maps = bb[0]._base if bb[0]._base is not None else bb[0]  # the fused (B,21,64,64) buffer  pylint: disable=protected-access
+  hwc = maps.shape[2] * maps.shape[3]
+  w5 = torch.tensor([weights[k] for k in ('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class',
+                                           'loss_yaw_res')], dtype=F32, device=dev)
+  dzh = torch.empty((b, maps.shape[2], maps.shape[3], 24), dtype=BF16, device=dev)
+  heads = m.head.head_names()
+  bias_first, bias_last = getattr(m.head, heads[0])[2].bias, getattr(m.head, heads[-1])[2].bias
+  _lib.check(lib.tfpp_center_head_loss(maps.data_ptr(), labels['center_heatmap'].data_ptr(), labels['wh'].data_ptr(),
+                                       labels['offset'].data_ptr(), labels['yaw_class'].data_ptr(),
+                                       labels['yaw_res'].data_ptr(), labels['pixel_weight'].data_ptr(),
+                                       labels['avg_factor'].data_ptr(), w5.data_ptr(), sums[5:10].data_ptr(),
+                                       dzh.data_ptr(), st.g_span(bias_first, bias_last).data_ptr(), b, hwc,
+                                       cfg.num_bb_classes, cfg.num_dir_bins, 24, stream), 'center loss')
+  for i, k in enumerate(('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res')):
+    losses[k] = sums[5 + i]
+  seeds['center'] = dzh
+  return losses, seeds
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward over the tape
+# ---------------------------------------------------------------------------------------------------------------
+class Backward:
+
+  def __init__(self, eng, st):
+    self.eng, self.st = eng, st
+    self.G = {}        # id(forward tensor) -> gradient tensor (bf16 NHWC / f32 token matrices)
+    self.pending = {}  # id(a2) -> (gate, pool_grad) from the SE record
+
+  def add(self, t, g):
+    k = id(t)
+    if k in self.G:
+      if g.dtype == BF16:
+        ops.add_bf16(self.G[k], g, out=self.G[k])
+      else:
+        self.G[k].add_(g)
+    else:
+      self.G[k] = g
+
+  # -- generic pieces ------------------------------------------------------------------------------------------
+  def linear_bwd(self, dy_b, x, w_param_grad, wt_packed, n, k, *, res=None, out_f32=True, need_dx=True, cout_valid=0,
+                 x_slab=None):
+    """dy_b (rows, Np) bf16, x (rows, K) bf16 [or slab], weight grad region (n, k) fp32 contiguous.
+    Returns dx (rows, k) (f32 by default, + res)."""
+    rows = dy_b.shape[0]
+    npad = dy_b.shape[1]
+    if x_slab is None:
+      ops.conv_wgrad(dy_b.view(1, 1, rows, npad), x.view(1, 1, rows, k), out=w_param_grad, out_strides=(k, 0, 1),
+                     cout_valid=cout_valid or n)
+    else:
+      buf, off, (groups, rows_pg), gstride = x_slab
+      ops.conv_wgrad(dy_b.view(groups, 1, rows_pg, npad), buf.view(-1)[off:], x_shape=(groups, 1, rows_pg, k),
+                     x_batch_stride=gstride, out=w_param_grad, out_strides=(k, 0, 1), cout_valid=cout_valid or n)
+    if not need_dx:
+      return None
+    return ops.linear(dy_b, wt_packed, res=res, out_f32=out_f32)
+
+  def conv_dgrad(self, dz, conv_weight, taps_kind, shape_out, res=None):
+    """dz (B,H,W,Cp) bf16 -> grad wrt the conv input (B,H,W,Cin) bf16 for a dense stride-1 conv."""
+    wt = packed(conv_weight, 'conv_t')
+    taps = ops.TAPS_3X3_DGRAD if taps_kind == 3 else ops.TAPS_1X1
+    return ops.conv_gemm(dz, wt, taps=taps, res1=res)
+
+  # -- handlers ------------------------------------------------------------------------------------------------
+  def conv_bias(self, r, seeds):
+    st = self.st
+    conv, y, a, act = r['conv'], r['y'], r['a'], r['act']
+    cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+    k = conv.weight.shape[-1]
+    cp = _pad8(cout)
+    b, h, w = a.shape[0], a.shape[1], a.shape[2]
+    if id(y) in seeds:  # final output: the loss kernel produced dz (and the bias gradient)
+      dz = seeds.pop(id(y))
+    else:
+      dy = self.G.pop(id(y))
+      if y.dtype == F32:  # NCHW f32 output consumed by something other than a loss
+        raise RuntimeError('unexpected f32 intermediate')
+      if act == ACT_NONE and cp == cout:
+        dz = dy
+        ops.act_bwd(dy, None, ACT_NONE, b, h * w, cout, dbias=st.g(conv.bias), want_dz=False)
+      else:
+        dz = ops.act_bwd(dy, y, act, b, h * w, cout, dbias=st.g(conv.bias), channels_padded=cp).view(b, h, w, cp)
+    ops.conv_wgrad(dz.view(b, h, w, cp), a, cin=cin, taps=r['taps'], w_taps=k * k, out=st.g(conv.weight),
+                   out_strides=(cin * k * k, 1, k * k), cout_valid=cout)
+    self.G[id(a)] = self.conv_dgrad(dz.view(b, h, w, cp), conv.weight, k, None, res=self.G.get(id(a)))
+
+  def conv_bn(self, r):
+    st = self.st
+    cna, a, raw, y, act = r['cna'], r['a'], r['raw'], r['y'], r['act']
+    bn, conv = cna.bn, cna.conv
+    dy = self.G.pop(id(y))
+    gate = pool_grad = None
+    if id(y) in self.pending:
+      gate, pool_grad = self.pending.pop(id(y))
+    want_dz = r['res'] is not None or r['res_bn'] is not None
+    draw, dz = ops.bn_bwd(dy, y, raw, r['mean'], r['invstd'], bn.weight, act, st.g(bn.weight), st.g(bn.bias), gate=gate,
+                          pool_grad=pool_grad, want_dz=want_dz)
+    if r['res'] is not None:
+      self.add(r['res'], dz)
+    if r['res_bn'] is not None:
+      self.G[id(r['res_bn'][0])] = dz
+    self.conv_grads(draw, a, r['a_src'], conv, r['taps'], r['batch'], r['grouped'])
+
+  def conv_grads(self, draw, a, a_src, conv, taps, batch, grouped):
+    """weight gradient + input gradient of a bias-free conv given the gradient of its raw output."""
+    st = self.st
+    k = conv.weight.shape[-1]
+    cout = conv.weight.shape[0]
+    b, ho, wo, _ = draw.shape
+    if grouped:
+      gw = conv.weight.shape[1]
+      ops.conv_wgrad(draw, a, taps=taps, w_taps=9, group_width=gw, out=st.g(conv.weight), out_strides=(gw * 9, 1, 9))
+      wt = packed(conv.weight, 'gconv_t')
+      gk = dict(k_per_tile=48, a_c_per_ntile=48, bn=48)
+      if a_src is None:  # stride 1
+        self.G[id(a)] = ops.conv_gemm(draw, wt, taps=ops.TAPS_3X3_DGRAD, res1=self.G.get(id(a)), **gk)
+      else:  # stride 2: one launch per input parity plane, written at its positions of the full-resolution gradient
+        h, w, c = a_src.shape[1], a_src.shape[2], a_src.shape[3]
+        da = self.G.get(id(a_src))
+        have = da is not None
+        if not have:
+          da = torch.empty_like(a_src)
+        for py in range(2):
+          for px in range(2):
+            off = (py * w + px) * c
+            view = da.view(-1)[off:]
+            strides = (h * w * c, 2 * w * c, 2 * c, 1)
+            ops.conv_gemm(draw, wt, taps=ops.taps_dgrad_stride2(py, px), out=view, out_strides=strides,
+                          res1=view if have else None, res1_strides=strides if have else None, **gk)
+        self.G[id(a_src)] = da
+    else:
+      cin = conv.weight.shape[1]
+      ops.conv_wgrad(draw, a, cin=cin, taps=taps, w_taps=k * k, out=st.g(conv.weight),
+                     out_strides=(cin * k * k, 1, k * k))
+      wt = packed(conv.weight, 'conv_t')
+      if a_src is None:
+        tp = ops.TAPS_3X3_DGRAD if k == 3 else ops.TAPS_1X1
+        self.G[id(a)] = ops.conv_gemm(draw, wt, taps=tp, res1=self.G.get(id(a)))
+      else:  # 1x1 stride 2 (downsample): only the even/even positions receive gradient
+        h, w, c = a_src.shape[1], a_src.shape[2], a_src.shape[3]
+        da = self.G.get(id(a_src))
+        have = da is not None
+        if not have:
+          da = torch.zeros_like(a_src)
+        strides = (h * w * c, 2 * w * c, 2 * c, 1)
+        ops.conv_gemm(draw, wt, out=da, out_strides=strides, res1=da, res1_strides=strides)
+        self.G[id(a_src)] = da
+
+  def downsample(self, r):
+    st = self.st
+    cna = r['cna']
+    dz = self.G.pop(id(r['raw']))
+    draw, _ = ops.bn_bwd(dz, None, r['raw'], r['mean'], r['invstd'], cna.bn.weight, ACT_NONE, st.g(cna.bn.weight),
+                         st.g(cna.bn.bias))
+    self.conv_grads(draw, r['a'], r['x_src'] if r['stride'] == 2 else None, cna.conv, ops.TAPS_1X1, r['batch'], False)
+
+  def se(self, r):
+    st = self.st
+    se = r['se']
+    da2s = self.G.pop(id(r['a2s']))
+    pool_grad = ops.se_bwd(da2s, r['a2'], r['gate'], r['hidden'], r['pool'], r['hw'], se.fc1.weight, se.fc2.weight,
+                           st.g(se.fc1.weight), st.g(se.fc1.bias), st.g(se.fc2.weight), st.g(se.fc2.bias))
+    self.pending[id(r['a2'])] = (r['gate'], pool_grad)
+    self.G[id(r['a2'])] = da2s
+
+  def stem(self, r):
+    st = self.st
+    cna = r['cna']
+    dy = self.G.pop(id(r['y']), None)
+    if dy is None:
+      return
+    draw, _ = ops.bn_bwd(dy, r['y'], r['raw'], r['mean'], r['invstd'], cna.bn.weight, ACT_RELU, st.g(cna.bn.weight),
+                         st.g(cna.bn.bias))
+    ops.stem_wgrad(r['x'], draw, r['in_scale'], r['in_shift'], st.g(cna.conv.weight))
+
+  def bilinear(self, r):
+    src, out = r['src'], r['out']
+    dout = self.G.pop(id(out))
+    b, sh, sw, c = src.shape
+    dsrc = self.G.get(id(src))
+    have = dsrc is not None
+    if not have:
+      dsrc = torch.empty_like(src)
+    ops.bilinear_bwd(dout, dsrc, b, sh, sw, out.shape[1], out.shape[2], c, accumulate=have)
+    self.G[id(src)] = dsrc
+
+  def untokenise(self, r):
+    """adjoint of: img_out = img + up(xf[:, :n_img]); lid_out = lid + up(conv1x1(xf[:, n_img:]))."""
+    st, eng = self.st, self.eng
+    bb, cfg = eng.bb, eng.cfg
+    i, b, t, c, cl = r['i'], r['b'], r['t'], r['c'], r['cl']
+    gpt = bb.transformers[i]
+    n_img = cfg.img_vert_anchors * cfg.img_horz_anchors
+    n_lid = t - n_img
+    dimg = self.G.pop(id(r['img_out']))
+    dlid = self.G.pop(id(r['lid_out']))
+    # pass-through of the residual adds
+    self.add(r['img'], dimg)
+    self.add(r['lid'], dlid)
+    dxf = torch.empty((b * t, c), dtype=F32, device=dimg.device)
+    hi, wi = dimg.shape[1], dimg.shape[2]
+    ops.bilinear_bwd(dimg, dxf, b, cfg.img_vert_anchors, cfg.img_horz_anchors, hi, wi, c, src_batch_stride=t * c,
+                     src_row_stride=c)
+    dlid_tok = torch.empty((b, cfg.lidar_vert_anchors, cfg.lidar_horz_anchors, cl), dtype=BF16, device=dimg.device)
+    ops.bilinear_bwd(dlid, dlid_tok, b, cfg.lidar_vert_anchors, cfg.lidar_horz_anchors, dlid.shape[1], dlid.shape[2], cl)
+    i2l = bb.img_channel_to_lidar[i]
+    dlt = dlid_tok.view(b * n_lid, cl)
+    ops.act_bwd(dlt, None, ACT_NONE, 1, b * n_lid, cl, dbias=st.g(i2l.bias), want_dz=False)
+    # weight gradient: x = xf slab rows n_img.. of every sample
+    xf = r['xf']
+    ops.conv_wgrad(dlt.view(b, 1, n_lid, cl), xf.view(-1)[n_img * c:], x_shape=(b, 1, n_lid, c), x_batch_stride=t * c,
+                   out=st.g(i2l.weight), out_strides=(c, 0, 1))
+    # dxf[:, n_img:] = dlt @ W_i2l  (written into the slab)
+    ops.linear(dlt, packed(i2l.weight, 'linear_t'), out=dxf.view(-1)[n_img * c:], row_map=(n_lid, t))
+    dx = ops.layernorm_bwd(dxf, r['x'], r['meanf'], r['rstdf'], gpt.ln_f.weight, st.g(gpt.ln_f.weight),
+                           st.g(gpt.ln_f.bias))
+    self.G[id(r['x'])] = dx
+
+  def gpt_block(self, r):
+    st = self.st
+    blk, b, t, c = r['blk'], r['b'], r['t'], r['c']
+    at = blk.attn
+    rows = b * t
+    dx2 = self.G.pop(id(r['x2']))
+    # x2 = x1 + mlp2(m); m = relu(mlp1(h2)); h2 = LN2(x1)
+    l1, l2 = blk.mlp[0], blk.mlp[2]
+    dz2 = ops.act_bwd(dx2, None, ACT_NONE, 1, rows, c, layout=2, dbias=st.g(l2.bias))
+    dm = self.linear_bwd(dz2, r['m'], st.g(l2.weight), packed(l2.weight, 'linear_t'), c, 4 * c, out_f32=False)
+    dzm = ops.act_bwd(dm, r['m'], ACT_RELU, 1, rows, 4 * c, dbias=st.g(l1.bias))
+    dh2 = self.linear_bwd(dzm, r['h2'], st.g(l1.weight), packed(l1.weight, 'linear_t'), 4 * c, c)
+    dx1 = ops.layernorm_bwd(dh2, r['x1'], r['mean2'], r['rstd2'], blk.ln2.weight, st.g(blk.ln2.weight),
+                            st.g(blk.ln2.bias), dres=dx2)
+    # x1 = x + proj(y); y = attn(qkv); qkv = lin(h); h = LN1(x)
+    dzp = ops.act_bwd(dx1, None, ACT_NONE, 1, rows, c, layout=2, dbias=st.g(at.proj.bias))
+    dy = self.linear_bwd(dzp, r['y'], st.g(at.proj.weight), packed(at.proj.weight, 'linear_t'), c, c, out_f32=False)
+    dqkv = ops.fusion_attn_bwd(r['qkv'], dy, b, t, c, r['heads'])
+    ops.act_bwd(dqkv, None, ACT_NONE, 1, rows, 3 * c, dbias=st.g_span(at.query.bias, at.value.bias), want_dz=False)
+    wt = packed((at.query.weight, at.key.weight, at.value.weight), 'cat_linear_t')
+    dh = self.linear_bwd(dqkv, r['h'], st.g_span(at.query.weight, at.value.weight), wt, 3 * c, c)
+    dx = ops.layernorm_bwd(dh, r['x'], r['mean1'], r['rstd1'], blk.ln1.weight, st.g(blk.ln1.weight),
+                           st.g(blk.ln1.bias), dres=dx1)
+    self.G[id(r['x'])] = dx
+
+  def tokenise(self, r):
+    st, eng = self.st, self.eng
+    bb, cfg = eng.bb, eng.cfg
+    i, b, t, c, cl = r['i'], r['b'], r['t'], r['c'], r['cl']
+    gpt = bb.transformers[i]
+    n_img = cfg.img_vert_anchors * cfg.img_horz_anchors
+    n_lid = t - n_img
+    dx = self.G.pop(id(r['x0']))
+    # pos_emb gradient = sum over the batch
+    ops.batch_reduce(dx, st.g(gpt.pos_emb).view(-1), b)
+    img, lid = r['img'], r['lid']
+    self.G[id(img)] = ops.pool_bwd_add(self.G.get(id(img)), dx, tuple(img.shape), cfg.img_vert_anchors,
+                                       cfg.img_horz_anchors, t, 0)
+    l2i = bb.lidar_channel_to_img[i]
+    dzl = ops.cast_rows(dx, b, t, n_img, n_lid, c, dbias=st.g(l2i.bias))
+    dpool = self.linear_bwd(dzl, r['lid_pool'].view(b * n_lid, cl), st.g(l2i.weight), packed(l2i.weight, 'linear_t'), c,
+                            cl, out_f32=False)
+    self.G[id(lid)] = ops.pool_bwd_add(self.G.get(id(lid)), dpool, tuple(lid.shape), cfg.lidar_vert_anchors,
+                                       cfg.lidar_horz_anchors, n_lid, 0)
+
+  def center_head(self, r, seeds):
+    st = self.st
+    feat, h = r['feat'], r['h']
+    convs0, convs1 = r['convs0'], r['convs1']
+    dz = seeds.pop('center')  # (B,64,64,24) bf16, 1x1-conv bias gradients already accumulated by the loss kernel
+    b, hh, ww, _ = dz.shape
+    n1 = sum(c.weight.shape[0] for c in convs1)
+    k1 = sum(c.weight.shape[1] for c in convs1)
+    tmp = ops.conv_wgrad(dz, h, cin=k1, cout_valid=n1)  # (21, 1, 320) fp32
+    rr = cc = 0
+    for c in convs1:
+      n, k = c.weight.shape[0], c.weight.shape[1]
+      st.g(c.weight).view(n, k).add_(tmp[rr:rr + n, 0, cc:cc + k])
+      rr += n
+      cc += k
+    dh = ops.conv_gemm(dz, packed(tuple(c.weight for c in convs1), 'blockdiag_1x1_t'))
+    n0 = k1
+    dzh = ops.act_bwd(dh, h, ACT_RELU, b, hh * ww, n0, dbias=st.g_span(convs0[0].bias, convs0[-1].bias)).view(b, hh, ww, n0)
+    cin = convs0[0].weight.shape[1]
+    ops.conv_wgrad(dzh, feat, cin=cin, taps=ops.TAPS_3X3, w_taps=9, out=st.g_span(convs0[0].weight, convs0[-1].weight),
+                   out_strides=(cin * 9, 1, 9))
+    wt = packed(tuple(c.weight for c in convs0), 'cat_conv_t')
+    self.G[id(feat)] = ops.conv_gemm(dzh, wt, taps=ops.TAPS_3X3_DGRAD, res1=self.G.get(id(feat)))
+
+  def bev_tail(self, r, seeds):
+    src, out = r['src'], r['out']
+    dbev = seeds.pop(id(out))
+    b, sh, sw, _ = src.shape
+    ncls = r['ncls']
+    cp = _pad8(ncls)
+    dz = ops.bilinear_nchw_mask_bwd(dbev, packed(self.eng.m.valid_bev_pixels, 'f32'), b, sh, sw, cp, ncls, out.shape[2],
+                                    out.shape[3])
+    # hand it to the 1x1 conv record as a seed; its bias gradient is the column sum of dz
+    conv = self.eng.m.bev_semantic_decoder[2]
+    tmpb = torch.zeros(cp, dtype=F32, device=dz.device)
+    ops.act_bwd(dz, None, ACT_NONE, b, sh * sw, cp, dbias=tmpb, want_dz=False)
+    self.st.g(conv.bias).add_(tmpb[:ncls])
+    seeds[id(src)] = dz
+
+  def planner_head(self, r, seeds):
+    from . import _lib  # pylint: disable=import-outside-toplevel
+    st, m = self.st, self.eng.m
+    dcp, dlogits = seeds.pop('planner')
+    b, nq, d = r['b'], r['nq'], r['d']
+    cd, tsn = m.checkpoint_decoder, m.target_speed_network
+    joined = r['joined']
+    h_all = r['res'][2]
+    djoined = torch.empty_like(joined)
+    g = st.g
+    tp = r['target_point'].float().contiguous()
+    _lib.check(_lib.load().tfpp_planner_head_bwd(
+        joined.data_ptr(), tp.data_ptr(), h_all.data_ptr(), cd.encoder.weight.data_ptr(), cd.encoder.bias.data_ptr(),
+        cd.gru.weight_ih_l0.data_ptr(), cd.gru.weight_hh_l0.data_ptr(), cd.gru.bias_ih_l0.data_ptr(),
+        cd.gru.bias_hh_l0.data_ptr(), cd.decoder.weight.data_ptr(), tsn[0].weight.data_ptr(), tsn[0].bias.data_ptr(),
+        tsn[2].weight.data_ptr(), dcp.data_ptr(), dlogits.data_ptr(), djoined.data_ptr(), g(cd.encoder.weight).data_ptr(),
+        g(cd.encoder.bias).data_ptr(), g(cd.gru.weight_ih_l0).data_ptr(), g(cd.gru.weight_hh_l0).data_ptr(),
+        g(cd.gru.bias_ih_l0).data_ptr(), g(cd.gru.bias_hh_l0).data_ptr(), g(cd.decoder.weight).data_ptr(),
+        g(cd.decoder.bias).data_ptr(), g(tsn[0].weight).data_ptr(), g(tsn[0].bias).data_ptr(),
+        g(tsn[2].weight).data_ptr(), g(tsn[2].bias).data_ptr(), b, nq - 1, d, cd.hidden_size, tsn[2].weight.shape[0],
+        ops._stream()), 'planner_head_bwd')  # pylint: disable=protected-access
+    mj, rj = r['stats']
+    dx = ops.layernorm_bwd(djoined.view(b * nq, d), r['x'], mj, rj, m.join.norm.weight, g(m.join.norm.weight),
+                           g(m.join.norm.bias))
+    self.G[id(r['x'])] = dx
+
+  def dec_layer(self, r):
+    st = self.st
+    l, b, nq, n_mem, d, heads, hd = r['layer'], r['b'], r['nq'], r['n_mem'], r['d'], r['heads'], r['hd']
+    g = st.g
+    rows = b * nq
+    m1, r1, m2, r2, m3, r3 = r['stats']
+    dx3 = self.G.pop(id(r['x3']))
+    # x3 = LN3(t3), t3 = x2 + lin2(ff), ff = act(lin1(x2b))
+    dt3 = ops.layernorm_bwd(dx3, r['t3'], m3, r3, l.norm3.weight, g(l.norm3.weight), g(l.norm3.bias))
+    dz = ops.act_bwd(dt3, None, ACT_NONE, 1, rows, d, layout=2, dbias=g(l.linear2.bias))
+    ffw = l.linear1.weight.shape[0]
+    dff = self.linear_bwd(dz, r['ff'], g(l.linear2.weight), packed(l.linear2.weight, 'linear_t'), d, ffw, out_f32=False)
+    if r['act'] != ACT_RELU:
+      raise NotImplementedError('GELU decoder feed-forward backward is not built (the reference runs ReLU)')
+    dzf = ops.act_bwd(dff, r['ff'], ACT_RELU, 1, rows, ffw, dbias=g(l.linear1.bias))
+    dx2 = self.linear_bwd(dzf, r['x2b'], g(l.linear1.weight), packed(l.linear1.weight, 'linear_t'), ffw, d, res=dt3)
+    # x2 = LN2(t2), t2 = x1 + out_proj(ca), ca = mha(q2(x1b), kv)
+    dt2 = ops.layernorm_bwd(dx2, r['t2'], m2, r2, l.norm2.weight, g(l.norm2.weight), g(l.norm2.bias))
+    mh = l.multihead_attn
+    dz = ops.act_bwd(dt2, None, ACT_NONE, 1, rows, d, layout=2, dbias=g(mh.out_proj.bias))
+    dca = self.linear_bwd(dz, r['ca'], g(mh.out_proj.weight), packed(mh.out_proj.weight, 'linear_t'), d, d,
+                          out_f32=False)
+    kv = r['kv']
+    dq2 = torch.empty((rows, d), dtype=BF16, device=kv.device)
+    dkv = torch.empty_like(kv)
+    ops.small_mha_bwd(r['q2'], kv, kv, dca, dq2, dkv, dkv, b, heads, nq, n_mem, hd, (nq * d, d), (n_mem * 2 * d, 2 * d),
+                      (n_mem * 2 * d, 2 * d), (nq * d, d), (n_mem * 2 * d, 2 * d), (n_mem * 2 * d, 2 * d),
+                      offs=(0, 0, d, 0, 0, d))
+    # q projection (rows [0,d) of in_proj) and k/v projections (rows [d,3d)) of the cross attention
+    ipw, ipb = g(mh.in_proj_weight), g(mh.in_proj_bias)
+    ops.act_bwd(dq2, None, ACT_NONE, 1, rows, d, dbias=ipb[:d], want_dz=False)
+    dx1 = self.linear_bwd(dq2, r['x1b'], ipw[:d], packed(mh.in_proj_weight, 'rows_t', 0, d), d, d, res=dt2)
+    ops.act_bwd(dkv, None, ACT_NONE, 1, b * n_mem, 2 * d, dbias=ipb[d:], want_dz=False)
+    mem = self.eng_mem
+    dmem = self.linear_bwd(dkv, mem, ipw[d:], packed(mh.in_proj_weight, 'rows_t', d, 3 * d), 2 * d, d,
+                           res=self.G.get('dmem'))
+    self.G['dmem'] = dmem
+    # x1 = LN1(t1), t1 = x + out_proj(sa), sa = mha(qkv(xb))
+    dt1 = ops.layernorm_bwd(dx1, r['t1'], m1, r1, l.norm1.weight, g(l.norm1.weight), g(l.norm1.bias))
+    sa = l.self_attn
+    dz = ops.act_bwd(dt1, None, ACT_NONE, 1, rows, d, layout=2, dbias=g(sa.out_proj.bias))
+    dsa = self.linear_bwd(dz, r['sa'], g(sa.out_proj.weight), packed(sa.out_proj.weight, 'linear_t'), d, d,
+                          out_f32=False)
+    qkv = r['qkv']
+    dqkv = torch.empty_like(qkv)
+    s3 = (nq * 3 * d, 3 * d)
+    ops.small_mha_bwd(qkv, qkv, qkv, dsa, dqkv, dqkv, dqkv, b, heads, nq, nq, hd, s3, s3, s3, s3, s3, s3,
+                      offs=(0, d, 2 * d, 0, d, 2 * d))
+    ops.act_bwd(dqkv, None, ACT_NONE, 1, rows, 3 * d, dbias=g(sa.in_proj_bias), want_dz=False)
+    dx = self.linear_bwd(dqkv, r['xb'], g(sa.in_proj_weight), packed(sa.in_proj_weight, 'linear_t'), 3 * d, d, res=dt1)
+    self.G[id(r['x_in'])] = dx
+
+  def planner_mem(self, r):
+    from . import _lib  # pylint: disable=import-outside-toplevel
+    st, m = self.st, self.eng.m
+    g = st.g
+    b, n_pix, n_mem, d = r['b'], r['n_pix'], r['n_mem'], r['d']
+    # queries: checkpoint_query repeated over the batch
+    dx0 = self.G.pop(id(r['x0']))
+    ops.batch_reduce(dx0, g(m.checkpoint_query).view(-1), b)
+    dmem = self.G.pop('dmem')  # (B*n_mem, d) f32
+    # extra sensor token = row n_pix of every sample
+    ese, vn = m.extra_sensor_encoder, m.velocity_normalization
+    training = r['training']
+    _lib.check(_lib.load().tfpp_extra_sensor_token_bwd(
+        r['ego_vel'].float().contiguous().data_ptr(), r['command'].float().contiguous().data_ptr(),
+        0.0 if training else float(vn.running_mean[0]), 1.0 if training else float(vn.running_var[0]), int(training),
+        ese[0].weight.data_ptr(), ese[0].bias.data_ptr(), ese[2].weight.data_ptr(), ese[2].bias.data_ptr(),
+        dmem.data_ptr() + 4 * n_pix * d, n_mem * d, g(ese[0].weight).data_ptr(), g(ese[0].bias).data_ptr(),
+        g(ese[2].weight).data_ptr(), g(ese[2].bias).data_ptr(), g(m.extra_sensor_pos_embed).data_ptr(), b,
+        r['command'].shape[1], ese[0].weight.shape[0], d, ops._stream()), 'extra_sensor_bwd')  # pylint: disable=protected-access
+    # pixel tokens: change_channel 1x1 conv (+ constant positional encoding)
+    cc = m.change_channel
+    fused = r['fused']
+    cf = fused.shape[3]
+    dz = ops.cast_rows(dmem, b, n_mem, 0, n_pix, d, dbias=g(cc.bias))
+    dfused = self.linear_bwd(dz, fused.view(b * n_pix, cf), g(cc.weight).view(d, cf), packed(cc.weight, 'linear_t'), d,
+                             cf, out_f32=False)
+    self.add(fused, dfused.view(fused.shape))
+
+  # -- driver --------------------------------------------------------------------------------------------------
+  def run(self, tape, seeds):
+    eng = self.eng
+    # seeds of the perspective decoders are keyed by the output tensors of their last conv_bias records
+    for r in tape:
+      if r['op'] == 'planner_mem':
+        self.eng_mem = r['mem'].view(-1, r['d'])
+    depth_seed = seeds.pop('depth', None)
+    depth_conv = eng.m.depth_decoder.deconv3[2] if hasattr(eng.m, 'depth_decoder') else None
+    for r in reversed(tape):
+      op = r['op']
+      if op == 'conv_bias':
+        if depth_seed is not None and r['conv'] is depth_conv:
+          seeds[id(r['y'])] = depth_seed
+          depth_seed = None
+        self.conv_bias(r, seeds)
+      elif op == 'conv_bn':
+        self.conv_bn(r)
+      elif op == 'downsample':
+        self.downsample(r)
+      elif op == 'se':
+        self.se(r)
+      elif op == 'stem':
+        self.stem(r)
+      elif op == 'bilinear':
+        self.bilinear(r)
+      elif op == 'untokenise':
+        self.untokenise(r)
+      elif op == 'gpt_block':
+        self.gpt_block(r)
+      elif op == 'tokenise':
+        self.tokenise(r)
+      elif op == 'center_head':
+        self.center_head(r, seeds)
+      elif op == 'bev_tail':
+        self.bev_tail(r, seeds)
+      elif op == 'planner_head':
+        self.planner_head(r, seeds)
+      elif op == 'dec_layer':
+        self.dec_layer(r)
+      elif op == 'planner_mem':
+        self.planner_mem(r)
+      else:
+        raise RuntimeError(f'no backward handler for {op}')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# trainer
+# ---------------------------------------------------------------------------------------------------------------
+class Trainer:
+  """One process per GPU.  step(batch) = forward + fused losses + backward + (bucketed all-reduce) + AdamW."""
+
+  def __init__(self, model, lr=3e-4, weight_decay=0.01, loss_weights=None, process_group=None, bucket_mb=64):
+    self.model = model
+    self.eng = model.engine
+    self.st = FlatState(model)
+    self.lr, self.wd = lr, weight_decay
+    w = loss_weights or {k: 1.0 for k in LOSS_KEYS}
+    tot = sum(w.values())
+    self.loss_weights = {k: v / tot for k, v in w.items()}  # train.py:452-456
+    self.pg = process_group
+    self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    self.bucket_elems = bucket_mb * 1024 * 1024 // 4
+
+  def forward_backward(self, inputs, labels):
+    eng, st = self.eng, self.st
+    st.zero_grad()
+    eng.tape = []
+    try:
+      out = eng.forward(inputs['rgb'], inputs['lidar_bev'], inputs['target_point'], inputs['ego_vel'],
+                        inputs['command'], training=True)
+      losses, seeds = compute_losses(eng, st, out, labels, self.loss_weights)
+      Backward(eng, st).run(eng.tape, seeds)
+    finally:
+      eng.tape = None
+    return out, losses
+
+  def allreduce(self):
+    """DDP semantics (train.py:516): sum-all-reduce the flat gradient in buckets, averaged by world size inside the
+    AdamW kernel (grad_scale)."""
+    if self.world == 1:
+      return
+    g = self.st.grad
+    works = []
+    for s in range(0, g.numel(), self.bucket_elems):
+      works.append(torch.distributed.all_reduce(g[s:s + self.bucket_elems], group=self.pg, async_op=True))
+    for w in works:
+      w.wait()
+
+  def step(self, inputs, labels):
+    out, losses = self.forward_backward(inputs, labels)
+    self.allreduce()
+    self.st.adamw_step(self.lr, weight_decay=self.wd, grad_scale=1.0 / self.world)
+    return out, losses

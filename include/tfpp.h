@@ -80,7 +80,8 @@ typedef struct {
   const void* dy;
   const void* x;
   float* dw;
-  int batch, height, width, cout;
+  int batch, height, width, cout; /* cout = channels of dy (may be zero-padded to a multiple of 8) */
+  int cout_valid;                 /* rows of dw actually written (0 = cout) */
   int x_batch, x_channels;
   long long x_batch_stride; /* elements, 0 = contiguous */
   int cin;                  /* dense: number of input channels written (<= x_channels) */
