@@ -615,6 +615,16 @@ class Backward:
 # ---------------------------------------------------------------------------------------------------------------
 # trainer
 # ---------------------------------------------------------------------------------------------------------------
+def allreduce_flat(grad, group, bucket_elems):
+  """Sum-all-reduce a flat gradient buffer in buckets (async, then wait): DDP's exchange step (train.py:516) without
+  the per-parameter hooks.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+  works = []
+  for s in range(0, grad.numel(), bucket_elems):
+    works.append(torch.distributed.all_reduce(grad[s:s + bucket_elems], group=group, async_op=True))
+  for w in works:
+    w.wait()
+
+
 class Trainer:
   """One process per GPU.  step(batch) = forward + fused losses + backward + (bucketed all-reduce) + AdamW."""
 
@@ -648,12 +658,7 @@ class Trainer:
     AdamW kernel (grad_scale)."""
     if self.world == 1:
       return
-    g = self.st.grad
-    works = []
-    for s in range(0, g.numel(), self.bucket_elems):
-      works.append(torch.distributed.all_reduce(g[s:s + self.bucket_elems], group=self.pg, async_op=True))
-    for w in works:
-      w.wait()
+    allreduce_flat(self.st.grad, self.pg, self.bucket_elems)
 
   def step(self, inputs, labels):
     out, losses = self.forward_backward(inputs, labels)

@@ -78,3 +78,73 @@ def test_adamw_step_matches_torch(trainer):
     st.adamw_step(3e-4)
   assert rel(p.detach(), ref_p.detach()) < 1e-6
   del synth
+
+
+def _block_backward_case(trainer, oracle_state, kind):
+  """Backward of ONE component given the oracle's exact input and an exact upstream gradient, against torch
+  autograd through the oracle (CPU fp32).  This is where the backward kernels are held to a tight bound; the
+  end-to-end gradient test above can only be as tight as the bf16 noise floor of a random deep network."""
+  from carla_garage_b200 import ops, synth
+  from carla_garage_b200.training import Backward
+  from oracle import tfpp_oracle as orc
+  net, eng, st = trainer.model, trainer.eng, trainer.st
+  net.load_state_dict(oracle_state, strict=True)
+  net.train()
+  sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v)
+        for k, v in oracle_state.items()}
+  g = torch.Generator().manual_seed(7)
+  to_dev = lambda t: ops.nchw_to_nhwc(t.detach().cuda().contiguous())
+  st.zero_grad()
+  eng.tape = []
+  try:
+    if kind in ('s2.b1', 's2.b2'):
+      stride = 2 if kind == 's2.b1' else 1
+      cin = 72 if kind == 's2.b1' else 216
+      hw = (32, 64) if kind == 's2.b1' else (16, 32)
+      x = (torch.randn(2, cin, *hw, generator=g).relu() + 0.1 * torch.randn(2, cin, *hw, generator=g)).requires_grad_(True)
+      prefix = 'backbone.image_encoder.' + kind
+      want = orc.regnet_block(sd, prefix, x, True, stride=stride)
+      dy = torch.randn(want.shape, generator=g)
+      want.backward(dy)
+      blk = net.backbone.image_encoder['s2'][0 if kind == 's2.b1' else 1]
+      xd = to_dev(x)
+      y = eng.regnet_block(xd, blk, True)
+      bw = Backward(eng, st)
+      bw.G[id(y)] = to_dev(dy)
+      bw.run(eng.tape, {})
+      got_dx = ops.nhwc_to_nchw(bw.G[id(xd)])
+      names = [n for n in sd if n.startswith(prefix + '.') and sd[n].is_floating_point() and 'running' not in n]
+    else:  # fusion block of scale 1 (C = 216)
+      xi = torch.randn(2, 216, 32, 128, generator=g).requires_grad_(True)
+      xl = torch.randn(2, 216, 32, 32, generator=g).requires_grad_(True)
+      wi, wl = orc.fuse_features(sd, 'backbone', xi, xl, 1, orc.DEFAULT_CFG)
+      di, dl = torch.randn(wi.shape, generator=g), torch.randn(wl.shape, generator=g)
+      (wi * di).sum().add((wl * dl).sum()).backward()
+      xid, xld = to_dev(xi), to_dev(xl)
+      yi, yl = eng.fuse(xid, xld, 1, True)
+      bw = Backward(eng, st)
+      bw.G[id(yi)], bw.G[id(yl)] = to_dev(di), to_dev(dl)
+      bw.run(eng.tape, {})
+      got_dx = ops.nhwc_to_nchw(bw.G[id(xid)])
+      x = xi
+      assert rel(ops.nhwc_to_nchw(bw.G[id(xld)]), xl.grad) < 2e-2
+      names = [n for n in sd if (n.startswith('backbone.transformers.1.') or n.startswith('backbone.lidar_channel_to_img.1.')
+                                 or n.startswith('backbone.img_channel_to_lidar.1.'))]
+  finally:
+    eng.tape = None
+  torch.cuda.synchronize()
+  report = {'dx': rel(got_dx, x.grad)}
+  params = dict(net.named_parameters())
+  for n in names:
+    if sd[n].grad is None:
+      continue
+    report[n] = rel(params[n].grad, sd[n].grad)
+  print('\n'.join(f'  {kind} {k}: {v:.2e}' for k, v in report.items()))
+  return report
+
+
+@pytest.mark.parametrize('kind', ['s2.b1', 's2.b2', 'fuse1'])
+def test_component_backward_vs_oracle_autograd(trainer, oracle_state, kind):
+  report = _block_backward_case(trainer, oracle_state, kind)
+  for k, v in report.items():
+    assert v < 3e-2, (k, v)
