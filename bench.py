@@ -168,9 +168,18 @@ def main():
       ms = float(t)
     return ms
 
-  # ---- device-resident throughput
+  # ---- device-resident throughput.  N=1: the whole step (K1 + fwd + losses + bwd + AdamW) replays from one CUDA
+  # graph; N>1: eager launches (the NCCL all-reduce stays outside graph capture in this round).
+  dev_pts = host_pts.cuda()
+  use_graph = world == 1 and os.environ.get('TFPP_NO_GRAPH', '0') != '1'
+  if use_graph:
+    tr.capture(dev_in, dev_lab, points=dev_pts)
+
   def step_resident():
-    tr.step(dev_in, dev_lab)
+    if use_graph:
+      tr.replay()
+    else:
+      tr.step(dev_in, dev_lab)
 
   for _ in range(warmup):
     step_resident()
@@ -178,9 +187,10 @@ def main():
   th = threading.Thread(target=_clock_sampler, args=(stop, samples), daemon=True)
   if rank == 0:
     th.start()
+  launches_per_step = tr.launches_per_step if use_graph else None
   _lib.reset_launch_count()
   ms = timed(step_resident, args.steps)
-  launches = _lib.launch_count()
+  launches = _lib.launch_count() if not use_graph else launches_per_step * args.steps
   stop.set()
   value = world * b * args.steps / (ms / 1e3)
 
@@ -190,6 +200,10 @@ def main():
   loss_host = torch.zeros(10, pin_memory=True)
 
   def step_e2e():
+    if use_graph:
+      _, gl = tr.replay({k: v for k, v in host_in.items() if k != 'lidar_bev'}, host_lab, host_pts)
+      loss_host.copy_(gl, non_blocking=True)
+      return
     inp = {k: v.cuda(non_blocking=True) for k, v in host_in.items() if k != 'lidar_bev'}
     inp['lidar_bev'] = ops.pillar_scatter(host_pts.cuda(non_blocking=True))
     lab = {k: v.cuda(non_blocking=True) for k, v in host_lab.items()}
@@ -220,12 +234,38 @@ def main():
 
   if rank != 0:
     return
+  # ---- second half of BASELINE.json's metric: forward ms/frame at batch 1 (the agent's 20 Hz loop), graph replay
+  from carla_garage_b200.inference import GraphedForward
+  net.eval()
+  one = {k: v[:1].contiguous() for k, v in dev_in.items()}
+  gf = GraphedForward(net, one)
+  for _ in range(5):
+    gf(**one)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  torch.cuda.synchronize()
+  e0.record()
+  for _ in range(50):
+    gf(**one)
+  e1.record()
+  torch.cuda.synchronize()
+  fwd_ms = e0.elapsed_time(e1) / 50
+  inference = {'fwd_ms_per_frame': fwd_ms, 'batch': 1, 'mode': 'eval, CUDA-graph replay, inputs resident'}
   cpu = None
   if not args.no_cpu_baseline:
     threads = os.cpu_count() or 1
     rate, sec = cpu_reference_step_rate(2, 2, 1, threads)
     cpu = {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
            'sample': f'2 train steps of batch 2 ({sec:.1f} s each) of oracle/tfpp_oracle.py on the host cores'}
+    from oracle import tfpp_oracle as orc
+    sd = synth.golden_state(os.path.join(ROOT, 'tests', 'golden'))
+    one_cpu = {k: v[:1] for k, v in synth.make_inputs(1, seed=1234).items()}
+    with torch.no_grad():
+      orc.forward(sd, **one_cpu)
+      t0 = time.perf_counter()
+      for _ in range(3):
+        orc.forward(sd, **one_cpu)
+    inference['cpu_ref_ms_per_frame'] = (time.perf_counter() - t0) / 3 * 1e3
+    inference['cpu_cores'] = threads
   line = {
       'metric': 'train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
       'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -233,13 +273,14 @@ def main():
       'config': {'workload': 'TransFuser++ train step bf16, RegNetY-3.2GF backbones, batch=32 per GPU',
                  'global_batch': world * b, 'per_gpu_batch': b, 'parallelism': f'dp{world}',
                  'l2': 'per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed',
-                 'dropout': 'off (see DESIGN.md)', 'model_tflop_per_step': world * b * FLOP_PER_SAMPLE_TRAIN / 1e12},
+                 'dropout': 'off (see DESIGN.md)', 'cuda_graph': bool(use_graph), 'model_tflop_per_step': world * b * FLOP_PER_SAMPLE_TRAIN / 1e12},
       'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 40,
               'ms_per_step': ms_e2e / args.steps},
       'gpu_launches': launches,
       'clocks': _clock_summary(samples),
       'roofline': roof,
       'cpu_baseline': cpu,
+      'inference': inference,
       'model_flops_utilisation': (b * FLOP_PER_SAMPLE_TRAIN / (ms / args.steps / 1e3)) / 1e12 /
                                  peaks.get('bf16_tflops_sustained', 1400.0),
   }

@@ -66,7 +66,7 @@ _PROTOS = {
     'tfpp_planner_head': [P] * 17 + [I, I, I, I, I, P],
     'tfpp_decode_heatmap': [P, L, P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, F, F, P],
     'tfpp_bn_bwd': [P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P],
-    'tfpp_se_bwd': [P, P, P, P, P, I, P, P, P, P, P, P, P, P, I, I, I, P],
+    'tfpp_se_bwd': [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, I, I, I, P],
     'tfpp_act_bwd': [P, P, I, I, I, F, P, P, I, I, I, I, P],
     'tfpp_bilinear_bwd': [P, P, I, L, L, I, I, I, I, I, I, I, P],
     'tfpp_bilinear_nchw_mask_bwd': [P, P, P, I, I, I, I, I, I, I, P],
@@ -86,7 +86,7 @@ _PROTOS = {
     'tfpp_l1_sigmoid_loss': [P, P, F, P, P, P, I, L, P],
     'tfpp_center_head_loss': [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
     'tfpp_planner_loss': [P, P, P, P, P, F, F, P, P, P, I, I, I, P],
-    'tfpp_adamw_amsgrad': [P, P, P, P, P, L, F, F, F, F, F, I, F, P],
+    'tfpp_adamw_amsgrad': [P, P, P, P, P, L, F, F, F, F, F, I, F, P, P],
 }
 
 
@@ -114,7 +114,7 @@ def load():
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
-_KERNELS_PER_CALL = {'tfpp_pillar_scatter': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 2, 'tfpp_fusion_attn_bwd': 2}
+_KERNELS_PER_CALL = {'tfpp_adamw_amsgrad': 2, 'tfpp_pillar_scatter': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 3, 'tfpp_fusion_attn_bwd': 2}
 _LAUNCHES = [0]
 
 

@@ -135,52 +135,57 @@ __global__ void __launch_bounds__(256) scale_shift_act_kernel(const bf16* __rest
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   const long long base = static_cast<long long>(b) * HW * C;
-  const int items = (p1 - p0) * c8n;
-  // a thread keeps the same channel group when blockDim.x % c8n == 0; otherwise it walks (still correct)
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int pix = p0 + it / c8n;
-    const int c0 = (it % c8n) * 8;
-    const long long off = base + static_cast<long long>(pix) * C + c0;
-    const uint4 u = *reinterpret_cast<const uint4*>(x + off);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float v[8];
+  // a thread owns one 8-channel group and walks pixels: per-thread constants, register accumulation of the SE squeeze
+  const int rows_pp = blockDim.x / c8n;
+  const int cg = threadIdx.x % c8n, prow = threadIdx.x / c8n;
+  if (prow < rows_pp) {
+    const int c0 = cg * 8;
+    float sc[8], sh[8], rsc[8], rsh[8], pl[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(w[j]);
-      v[2 * j] = f.x;
-      v[2 * j + 1] = f.y;
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = scale ? __ldg(scale + c0 + j) : 1.f;
+      sh[j] = scale ? __ldg(shift + c0 + j) : 0.f;
+      rsc[j] = res_scale ? __ldg(res_scale + c0 + j) : 1.f;
+      rsh[j] = res_scale ? __ldg(res_shift + c0 + j) : 0.f;
+      pl[j] = 0.f;
     }
-    if (scale != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = v[j] * __ldg(scale + c0 + j) + __ldg(shift + c0 + j);
-    }
-    if (res != nullptr) {
-      const uint4 r = *reinterpret_cast<const uint4*>(res + off);
-      const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+    for (int pix = p0 + prow; pix < p1; pix += rows_pp) {
+      const long long off = base + static_cast<long long>(pix) * C + c0;
+      const uint4 u = *reinterpret_cast<const uint4*>(x + off);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      float v[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float2 f = unpack_bf16x2(rw[j]);
-        if (res_scale != nullptr) {
-          f.x = f.x * __ldg(res_scale + c0 + 2 * j) + __ldg(res_shift + c0 + 2 * j);
-          f.y = f.y * __ldg(res_scale + c0 + 2 * j + 1) + __ldg(res_shift + c0 + 2 * j + 1);
-        }
-        v[2 * j] += f.x;
-        v[2 * j + 1] += f.y;
+        const float2 f = unpack_bf16x2(w[j]);
+        v[2 * j] = f.x * sc[2 * j] + sh[2 * j];
+        v[2 * j + 1] = f.y * sc[2 * j + 1] + sh[2 * j + 1];
       }
-    }
-    uint32_t o[4];
+      if (res != nullptr) {
+        const uint4 r = *reinterpret_cast<const uint4*>(res + off);
+        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a0 = apply_act(v[2 * j], act), a1 = apply_act(v[2 * j + 1], act);
-      o[j] = pack_bf16x2(a0, a1);
-      if (pool_sum != nullptr) {
-        // SE squeezes the tensor the next layer will actually read (bf16-rounded)
-        const float2 f = unpack_bf16x2(o[j]);
-        atomicAdd(&spool[c0 + 2 * j], f.x);
-        atomicAdd(&spool[c0 + 2 * j + 1], f.y);
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(rw[j]);
+          v[2 * j] += f.x * rsc[2 * j] + rsh[2 * j];
+          v[2 * j + 1] += f.y * rsc[2 * j + 1] + rsh[2 * j + 1];
+        }
       }
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[j] = pack_bf16x2(apply_act(v[2 * j], act), apply_act(v[2 * j + 1], act));
+        if (pool_sum != nullptr) {  // SE squeezes the tensor the next layer will actually read (bf16-rounded)
+          const float2 f = unpack_bf16x2(o[j]);
+          pl[2 * j] += f.x;
+          pl[2 * j + 1] += f.y;
+        }
+      }
+      *reinterpret_cast<uint4*>(y + off) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    *reinterpret_cast<uint4*>(y + off) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (pool_sum != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&spool[c0 + j], pl[j]);
+    }
   }
   if (pool_sum != nullptr) {
     __syncthreads();
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
   extern __shared__ float sm[];
   float* mean = sm;      // C
   float* hid = sm + C;   // R
-  const int b = blockIdx.x;
+  const int b = blockIdx.x;  // blockIdx.y = slice of the gate outputs (the small hidden layer is recomputed per slice)
   for (int i = threadIdx.x; i < C; i += blockDim.x) mean[i] = pool_sum[static_cast<long long>(b) * C + i] * inv_hw;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -208,11 +213,13 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
     if (lane == 0) {
       const float h = fmaxf(a + b1[r], 0.f);
       hid[r] = h;
-      if (hidden_out) hidden_out[static_cast<long long>(b) * R + r] = h;
+      if (hidden_out && blockIdx.y == 0) hidden_out[static_cast<long long>(b) * R + r] = h;
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  const int per = (C + gridDim.y - 1) / gridDim.y;
+  const int cbeg = blockIdx.y * per, cend = min(C, cbeg + per);
+  for (int c = cbeg + threadIdx.x; c < cend; c += blockDim.x) {
     float a = b2[c];
     for (int r = 0; r < R; ++r) a = fmaf(w2[static_cast<long long>(c) * R + r], hid[r], a);
     gate[static_cast<long long>(b) * C + c] = 1.f / (1.f + __expf(-a));
@@ -460,7 +467,7 @@ extern "C" int tfpp_scale_shift_act(const void* x, const void* res, const float*
                                     const float* res_scale, const float* res_shift, int act, void* y, float* pool_sum,
                                     int batch, int hw, int channels, tfpp_stream_t stream_) {
   STREAM;
-  TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
+  TFPP_CHECK_ARG(channels % 8 == 0 && channels <= 2048, "channels must be a multiple of 8, <= 2048");
   TFPP_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift go together");
   // aim for >= 2 waves of CTAs over the whole batch
   int chunks = ceil_div(TFPP_NUM_SMS * 4, batch);
@@ -480,7 +487,7 @@ extern "C" int tfpp_se_gate(const float* pool_sum, int hw, const float* w1, cons
                             const float* b2, float* gate, float* hidden, int batch, int channels, int rd,
                             tfpp_stream_t stream_) {
   STREAM;
-  se_gate_kernel<<<batch, 256, sizeof(float) * (channels + rd), stream>>>(pool_sum, 1.f / hw, w1, b1, w2, b2, gate,
+  se_gate_kernel<<<dim3(batch, 4), 256, sizeof(float) * (channels + rd), stream>>>(pool_sum, 1.f / hw, w1, b1, w2, b2, gate,
                                                                           hidden, channels, rd);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;

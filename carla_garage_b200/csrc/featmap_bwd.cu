@@ -43,23 +43,39 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
   const int b = blockIdx.y, c8n = C / 8;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
   const long long base = static_cast<long long>(b) * HW * C;
-  const int items = (p1 - p0) * c8n;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int pix = p0 + it / c8n, c0 = (it % c8n) * 8;
-    const long long off = base + static_cast<long long>(pix) * C + c0;
-    float d[8], yy[8], r[8];
-    load8(dy + off, d);
-    load8(raw + off, r);
-    if (act == ACT_RELU) load8(y + off, yy);
+  // a thread owns one 8-channel group and walks pixels (blockDim.x / c8n pixels per pass): register accumulation,
+  // contiguous 16-byte loads across the block, one shared-memory atomic per channel per thread at the end
+  const int rows_pp = blockDim.x / c8n;
+  const int cg = threadIdx.x % c8n, prow = threadIdx.x / c8n;
+  if (prow < rows_pp) {
+    const int c0 = cg * 8;
+    float l1[8], l2[8], mu[8], is[8], gt[8], pg[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      float dz = d[j];
-      if (gate) dz *= __ldg(gate + static_cast<long long>(b) * C + c);
-      if (pool_grad) dz += __ldg(pool_grad + static_cast<long long>(b) * C + c);
-      if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
-      atomicAdd(&a1[c], dz);
-      atomicAdd(&a2[c], dz * (r[j] - __ldg(mean + c)) * __ldg(invstd + c));
+      l1[j] = l2[j] = 0.f;
+      mu[j] = __ldg(mean + c0 + j);
+      is[j] = __ldg(invstd + c0 + j);
+      gt[j] = gate ? __ldg(gate + static_cast<long long>(b) * C + c0 + j) : 1.f;
+      pg[j] = pool_grad ? __ldg(pool_grad + static_cast<long long>(b) * C + c0 + j) : 0.f;
+    }
+    for (int pix = p0 + prow; pix < p1; pix += rows_pp) {
+      const long long off = base + static_cast<long long>(pix) * C + c0;
+      float d[8], yy[8], r[8];
+      load8(dy + off, d);
+      load8(raw + off, r);
+      if (act == ACT_RELU) load8(y + off, yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dz = d[j] * gt[j] + pg[j];
+        if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
+        l1[j] += dz;
+        l2[j] = fmaf(dz, (r[j] - mu[j]) * is[j], l2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&a1[c0 + j], l1[j]);
+      atomicAdd(&a2[c0 + j], l2[j]);
     }
   }
   __syncthreads();
@@ -114,41 +130,45 @@ __global__ void __launch_bounds__(256) se_bwd_reduce_kernel(const bf16* __restri
   const int b = blockIdx.y, c8n = C / 8;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
   const long long base = static_cast<long long>(b) * HW * C;
-  const int items = (p1 - p0) * c8n;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int pix = p0 + it / c8n, c0 = (it % c8n) * 8;
-    const long long off = base + static_cast<long long>(pix) * C + c0;
-    float d[8], a[8];
-    load8(dout + off, d);
-    load8(a2 + off, a);
+  const int rows_pp = blockDim.x / c8n;
+  const int cg = threadIdx.x % c8n, prow = threadIdx.x / c8n;
+  if (prow < rows_pp) {
+    const int c0 = cg * 8;
+    float l[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int pix = p0 + prow; pix < p1; pix += rows_pp) {
+      const long long off = base + static_cast<long long>(pix) * C + c0;
+      float d[8], a[8];
+      load8(dout + off, d);
+      load8(a2 + off, a);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sm[c0 + j], d[j] * a[j]);
+      for (int j = 0; j < 8; ++j) l[j] = fmaf(d[j], a[j], l[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sm[c0 + j], l[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dgate_sum + static_cast<long long>(b) * C + i, sm[i]);
 }
 
-// gate = sigmoid(W2 relu(W1 mean + b1) + b2), mean = pool_sum / hw.  One block per sample; parameter gradients are
-// accumulated with atomics across samples.  Output pool_grad[b,c] = dL/d(pool_sum[b,c]) (already divided by hw).
+// gate = sigmoid(W2 relu(W1 mean + b1) + b2), mean = pool_sum / hw.
+// Pass 1 (one block per sample): ds = dgate * g(1-g), dpre = relu'(hid) * (W2^T ds), pool_grad = W1^T dpre / hw; ds and
+// dpre go to a workspace.  Pass 2 (grid over weight elements): dW2 = ds^T hid, dW1 = dpre^T mean, db = column sums —
+// a batch-contraction without atomics.
 __global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restrict__ dgate_sum,
                                                           const float* __restrict__ gate,
-                                                          const float* __restrict__ hidden,
-                                                          const float* __restrict__ pool_sum, float inv_hw,
+                                                          const float* __restrict__ hidden, float inv_hw,
                                                           const float* __restrict__ w1, const float* __restrict__ w2,
-                                                          float* __restrict__ dw1, float* __restrict__ db1,
-                                                          float* __restrict__ dw2, float* __restrict__ db2,
+                                                          float* __restrict__ ds_out, float* __restrict__ dpre_out,
                                                           float* __restrict__ pool_grad, int C, int R) {
   extern __shared__ float sm[];
   float* ds = sm;        // C
   float* dpre = sm + C;  // R
-  float* mean = dpre + R;  // C
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float g = gate[static_cast<long long>(b) * C + c];
     const float v = dgate_sum[static_cast<long long>(b) * C + c] * g * (1.f - g);
     ds[c] = v;
-    mean[c] = pool_sum[static_cast<long long>(b) * C + c] * inv_hw;
-    atomicAdd(db2 + c, v);
+    ds_out[static_cast<long long>(b) * C + c] = v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -157,25 +177,49 @@ __global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restric
     for (int c = lane; c < C; c += 32) a = fmaf(ds[c], w2[static_cast<long long>(c) * R + r], a);
     a = warp_sum(a);
     if (lane == 0) {
-      const float h = hidden[static_cast<long long>(b) * R + r];
-      const float v = h > 0.f ? a : 0.f;
+      const float v = hidden[static_cast<long long>(b) * R + r] > 0.f ? a : 0.f;
       dpre[r] = v;
-      atomicAdd(db1 + r, v);
+      dpre_out[static_cast<long long>(b) * R + r] = v;
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * R; i += blockDim.x) {
-    const int c = i / R, r = i % R;
-    atomicAdd(dw2 + i, ds[c] * hidden[static_cast<long long>(b) * R + r]);  // dw2 (C,R)
-  }
-  for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
-    const int r = i / C, c = i % C;
-    atomicAdd(dw1 + i, dpre[r] * mean[c]);  // dw1 (R,C)
-  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f;
     for (int r = 0; r < R; ++r) a = fmaf(dpre[r], w1[static_cast<long long>(r) * C + c], a);
     pool_grad[static_cast<long long>(b) * C + c] = a * inv_hw;
+  }
+}
+
+__global__ void __launch_bounds__(256) se_param_grad_kernel(const float* __restrict__ ds, const float* __restrict__ dpre,
+                                                            const float* __restrict__ hidden,
+                                                            const float* __restrict__ pool_sum, float inv_hw,
+                                                            float* __restrict__ dw1, float* __restrict__ db1,
+                                                            float* __restrict__ dw2, float* __restrict__ db2, int B,
+                                                            int C, int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * R) {
+    {  // dw2 (C, R)
+      const int c = i / R, r = i % R;
+      float a = 0.f;
+      for (int b = 0; b < B; ++b) a = fmaf(ds[b * C + c], hidden[b * R + r], a);
+      dw2[i] += a;
+    }
+    {  // dw1 (R, C)
+      const int r = i / C, c = i % C;
+      float a = 0.f;
+      for (int b = 0; b < B; ++b) a = fmaf(dpre[b * R + r], pool_sum[b * C + c] * inv_hw, a);
+      dw1[i] += a;
+    }
+  }
+  if (i < C) {
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a += ds[b * C + i];
+    db2[i] += a;
+  }
+  if (i < R) {
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a += dpre[b * R + i];
+    db1[i] += a;
   }
 }
 
@@ -495,7 +539,7 @@ extern "C" int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const
                            const float* gamma, const float* gate, const float* pool_grad, int act, float* s1, float* s2,
                            void* draw, void* dz_out, int batch, int hw, int channels, tfpp_stream_t stream_) {
   STREAM;
-  TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
+  TFPP_CHECK_ARG(channels % 8 == 0 && channels <= 2048, "channels must be a multiple of 8, <= 2048");
   int chunks, ppb;
   chunking(batch, hw, &chunks, &ppb);
   dim3 grid(chunks, batch);
@@ -513,9 +557,9 @@ extern "C" int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const
 }
 
 extern "C" int tfpp_se_bwd(const void* dout, const void* a2, const float* gate, const float* hidden,
-                           const float* pool_sum, int hw, const float* w1, const float* w2, float* dgate_sum, float* dw1,
-                           float* db1, float* dw2, float* db2, float* pool_grad, int batch, int channels, int rd,
-                           tfpp_stream_t stream_) {
+                           const float* pool_sum, int hw, const float* w1, const float* w2, float* dgate_sum, float* ws,
+                           float* dw1, float* db1, float* dw2, float* db2, float* pool_grad, int batch, int channels,
+                           int rd, tfpp_stream_t stream_) {
   STREAM;
   TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
   int chunks, ppb;
@@ -525,8 +569,14 @@ extern "C" int tfpp_se_bwd(const void* dout, const void* a2, const float* gate, 
                                                                         static_cast<const bf16*>(a2), dgate_sum, hw,
                                                                         channels, ppb);
   TFPP_CHECK_LAUNCH();
-  se_gate_bwd_kernel<<<batch, 256, sizeof(float) * (2 * channels + rd), stream>>>(
-      dgate_sum, gate, hidden, pool_sum, 1.f / hw, w1, w2, dw1, db1, dw2, db2, pool_grad, channels, rd);
+  // workspace for ds (B,C) and dpre (B,rd): dgate_sum is (B,C) and consumed in place; dpre lives behind pool_grad
+  float* ds_ws = dgate_sum;  // overwritten with ds by pass 1 (each element read then written by the same thread)
+  float* dpre_ws = ws;
+  se_gate_bwd_kernel<<<batch, 256, sizeof(float) * (channels + rd), stream>>>(dgate_sum, gate, hidden, 1.f / hw, w1, w2,
+                                                                              ds_ws, dpre_ws, pool_grad, channels, rd);
+  TFPP_CHECK_LAUNCH();
+  se_param_grad_kernel<<<ceil_div(channels * rd, 256), 256, 0, stream>>>(ds_ws, dpre_ws, hidden, pool_sum, 1.f / hw, dw1,
+                                                                         db1, dw2, db2, batch, channels, rd);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

@@ -9,9 +9,15 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float* __restrict__ m, float* __restrict__ v,
                                                     float* __restrict__ vmax, long long n, float lr, float beta1,
                                                     float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                    float grad_scale) {
+                                                    float grad_scale, const float* __restrict__ dev_state) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (dev_state != nullptr) {  // CUDA-graph friendly: step count and learning rate live on the device
+    const float t = dev_state[0];
+    lr = dev_state[1];
+    bc1 = 1.f - powf(beta1, t);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  }
   const float gr = g[i] * grad_scale;
   float pv = p[i];
   pv *= (1.f - lr * wd);                       // decoupled weight decay
@@ -24,18 +30,22 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   const float denom = sqrtf(vm) / bc2_sqrt + eps;
   p[i] = pv - (lr / bc1) * (mv / denom);
 }
+__global__ void adamw_tick_kernel(float* dev_state) { dev_state[0] += 1.f; }
 }  // namespace
 
 extern "C" int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                                   float* max_exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps,
-                                  float weight_decay, int step, float grad_scale, tfpp_stream_t stream_) {
+                                  float weight_decay, int step, float grad_scale, float* dev_state,
+                                  tfpp_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  TFPP_CHECK_ARG(step >= 1, "step counts from 1");
+  TFPP_CHECK_ARG(step >= 1 || dev_state != nullptr, "step counts from 1");
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  if (dev_state != nullptr) adamw_tick_kernel<<<1, 1, 0, stream>>>(dev_state);
   adamw_kernel<<<static_cast<int>(ceil_div_ll(n, 256)), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq,
                                                                           max_exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                                          weight_decay, bc1, sqrtf(bc2), grad_scale);
+                                                                          weight_decay, bc1, sqrtf(bc2), grad_scale,
+                                                                          dev_state);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

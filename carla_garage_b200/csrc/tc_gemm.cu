@@ -81,6 +81,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* sstat = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [2][stat_stride] BatchNorm partial sums
+  const int stat_stride = p.n_tiles * p.bn;
+  if (p.stat_sum != nullptr)
+    for (int i = threadIdx.x; i < 2 * stat_stride; i += blockDim.x) sstat[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -192,35 +196,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const long long r1_base = bb * p.r1_sb + yy * p.r1_sy + xx * p.r1_sx;
       const long long r2_base = bb * p.r2_sb + yy * p.r2_sy + xx * p.r2_sx;
 
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + acc * kAccStride;
-      for (int c = 0; c < p.bn; c += 16) {
-        float v[16];
+      // one 32-column slab of the accumulator: statistics, affine, residuals, activation, store
+      auto process = [&](float* v, int c) {
         const int n = t.n0 + c;
-        if (n >= p.n) break;  // warp-uniform: remaining columns are padding
-        __syncwarp();
-        tmem_ld16(taddr + c, v);
+        if (n >= p.n) return;  // warp-uniform: padding columns
         if (p.stat_sum != nullptr) {
-          float s[16], q[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = valid ? v[j] : 0.f;
-            s[j] = a;
-            q[j] = a * a;
-          }
-          const float cs = warp_colsum16(s, lane);
-          const float cq = warp_colsum16(q, lane);
-          const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          if ((lane & 1) == 0 && n + col < p.n) {
-            atomicAdd(p.stat_sum + n + col, cs);
-            atomicAdd(p.stat_sq + n + col, cq);
+          for (int hf = 0; hf < 2; ++hf) {
+            if (n + hf * 16 < p.n) {
+              float s[16], q[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float a = valid ? v[hf * 16 + j] : 0.f;
+                s[j] = a;
+                q[j] = a * a;
+              }
+              const float cs = warp_colsum16(s, lane);
+              const float cq = warp_colsum16(q, lane);
+              const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              if ((lane & 1) == 0) {  // per-CTA accumulation in shared memory; flushed once at the end
+                atomicAdd(&sstat[n + hf * 16 + col], cs);
+                atomicAdd(&sstat[stat_stride + n + hf * 16 + col], cq);
+              }
+            }
           }
         }
-        if (p.out != nullptr && valid) {
-        const bool full = (n + 16 <= p.n);
+        if (p.out == nullptr || !valid) return;
+        const bool full = (n + 32 <= p.n);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 32; ++j) {
           if (full || n + j < p.n) {
             float a = v[j];
             if (p.scale) a *= __ldg(p.scale + n + j);
@@ -231,50 +235,63 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (p.res1) {
           if (full && p.r1_sn == 1 && !p.res1_f32) {
             const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const bf16*>(p.res1) + r1_base + n);
-            const uint4 u0 = __ldg(rp), u1 = __ldg(rp + 1);
-            const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 f = unpack_bf16x2(w[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
+            for (int qd = 0; qd < 4; ++qd) {
+              const uint4 u = __ldg(rp + qd);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(w[j]);
+                v[qd * 8 + 2 * j] += f.x;
+                v[qd * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          } else if (full && p.r1_sn == 1 && p.res1_f32) {
+            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res1) + r1_base + n);
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd) {
+              const float4 u = __ldg(rp + qd);
+              v[qd * 4] += u.x; v[qd * 4 + 1] += u.y; v[qd * 4 + 2] += u.z; v[qd * 4 + 3] += u.w;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < 32; ++j)
               if (full || n + j < p.n) v[j] += load_res(p.res1, p.res1_f32, r1_base + (n + j) * p.r1_sn);
           }
         }
         if (p.res2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
+          for (int j = 0; j < 32; ++j)
             if (full || n + j < p.n) v[j] += load_res(p.res2, p.res2_f32, r2_base + (n + j) * p.r2_sn);
         }
         if (p.act != ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
+          for (int j = 0; j < 32; ++j)
             if (p.act_n_limit == 0 || n + j < p.act_n_limit) v[j] = apply_act(v[j], p.act);
         }
         if (full && p.o_sn == 1 && !p.out_f32) {
-          uint4 u0, u1;
-          u0.x = pack_bf16x2(v[0], v[1]);
-          u0.y = pack_bf16x2(v[2], v[3]);
-          u0.z = pack_bf16x2(v[4], v[5]);
-          u0.w = pack_bf16x2(v[6], v[7]);
-          u1.x = pack_bf16x2(v[8], v[9]);
-          u1.y = pack_bf16x2(v[10], v[11]);
-          u1.z = pack_bf16x2(v[12], v[13]);
-          u1.w = pack_bf16x2(v[14], v[15]);
           uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_base + n);
-          op[0] = u0;
-          op[1] = u1;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            op[qd] = make_uint4(pack_bf16x2(v[qd * 8], v[qd * 8 + 1]), pack_bf16x2(v[qd * 8 + 2], v[qd * 8 + 3]),
+                                pack_bf16x2(v[qd * 8 + 4], v[qd * 8 + 5]), pack_bf16x2(v[qd * 8 + 6], v[qd * 8 + 7]));
         } else if (full && p.o_sn == 1 && p.out_f32) {
           float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o_base + n);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else if (p.o_sn == 1 && !p.out_f32 && (p.n - n) >= 16 && ((o_base + n) & 7) == 0) {
+          // 16-column tail (bn / N are multiples of 8 for every NHWC bf16 output of the model)
+          uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_base + n);
+#pragma unroll
+          for (int qd = 0; qd < 2; ++qd)
+            op[qd] = make_uint4(pack_bf16x2(v[qd * 8], v[qd * 8 + 1]), pack_bf16x2(v[qd * 8 + 2], v[qd * 8 + 3]),
+                                pack_bf16x2(v[qd * 8 + 4], v[qd * 8 + 5]), pack_bf16x2(v[qd * 8 + 6], v[qd * 8 + 7]));
+#pragma unroll
+          for (int j = 16; j < 32; ++j)
+            if (n + j < p.n) static_cast<bf16*>(p.out)[o_base + (n + j)] = f2bf(v[j]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 32; ++j) {
             if (full || n + j < p.n) {
               const long long off = o_base + (n + j) * p.o_sn;
               if (p.out_f32)
@@ -284,7 +301,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
         }
-        }  // valid
+      };
+
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + acc * kAccStride;
+      const int ncols = min(p.bn, p.n - t.n0);
+      const int nchunks = (ncols + 31) / 32;
+      // software-pipelined TMEM reads: the load of slab i+1 is in flight while slab i is processed
+      uint32_t ra[32], rb[32];
+      __syncwarp();
+      tmem_ld32_issue(taddr, ra);
+      tmem_ld_wait32(ra);
+      for (int c = 0; c < nchunks; c += 2) {
+        const bool has_b = (c + 1 < nchunks), has_a2 = (c + 2 < nchunks);
+        __syncwarp();
+        if (has_b) tmem_ld32_issue(taddr + (c + 1) * 32, rb);
+        {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+          process(v, c * 32);
+        }
+        __syncwarp();
+        if (has_b) {
+          tmem_ld_wait32(rb);
+          if (has_a2) tmem_ld32_issue(taddr + (c + 2) * 32, ra);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rb[j]);
+          process(v, (c + 1) * 32);
+          __syncwarp();
+          if (has_a2) tmem_ld_wait32(ra);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -292,6 +341,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
+      }
+    }
+    if (p.stat_sum != nullptr) {
+      // flush the per-CTA statistics: one global atomic per column per CTA instead of one per warp per tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = (warp - 2) * 32 + lane;
+      for (int i = et; i < p.n; i += 128) {
+        const float a = sstat[i], b2 = sstat[stat_stride + i];
+        if (a != 0.f || b2 != 0.f) {
+          atomicAdd(p.stat_sum + i, a);
+          atomicAdd(p.stat_sq + i, b2);
+        }
       }
     }
   }
@@ -381,7 +442,9 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
     if (rc) return rc;
   }
 
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t stat_bytes = a->stat_sum ? sizeof(float) * 2 * p.n_tiles * p.bn : 0;
+  TFPP_CHECK_ARG(stat_bytes <= 20 * 1024, "too many channels for the shared-memory statistics buffer");
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + stat_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -88,6 +88,8 @@ def packed(params, kind, *extra):
       out = (scale.contiguous(), (b - m * scale).contiguous())
     elif kind == 'f32':
       out = params[0].detach().float().contiguous()
+    elif kind == 'host_floats':  # one device->host read, cached until the buffers change
+      out = tuple(float(p.detach().reshape(-1)[0]) for p in params)
     elif kind == 'repeat_rows':  # (1, T, C) parameter repeated over the batch: f32 and bf16 copies
       t = params[0].detach().float().reshape(-1, params[0].shape[-1]).repeat(extra[0], 1).contiguous()
       out = (t, t.to(BF16))
@@ -404,8 +406,9 @@ class Engine:
                row_map=(n_pix, n_mem), res2=posenc, res2_strides=(0, 0, d, 1))
     vn = m.velocity_normalization
     ese = m.extra_sensor_encoder
-    ops.extra_sensor_token(ego_vel.float().contiguous(), command.float().contiguous(), float(vn.running_mean[0]) if not training else 0.0,
-                           float(vn.running_var[0]) if not training else 1.0, training, vn.running_mean if training else None,
+    vmean, vvar = (0.0, 1.0) if training else packed((vn.running_mean, vn.running_var), 'host_floats')
+    ops.extra_sensor_token(ego_vel.float().contiguous(), command.float().contiguous(), vmean, vvar, training,
+                           vn.running_mean if training else None,
                            vn.running_var if training else None, ese[0].weight, ese[0].bias, ese[2].weight, ese[2].bias,
                            packed(m.extra_sensor_pos_embed, 'f32'), mem, None, n_mem, n_pix)
     if training:

@@ -495,8 +495,10 @@ def se_bwd(dout, a2, gate, hidden, pool_sum, hw, w1, w2, dw1, db1, dw2, db2):
   rd = w1.shape[0]
   dgate = torch.zeros((b, c), dtype=F32, device=gate.device)
   pool_grad = torch.empty((b, c), dtype=F32, device=gate.device)
+  ws = torch.empty((b, rd), dtype=F32, device=gate.device)
   check(_lib.load().tfpp_se_bwd(dout.data_ptr(), a2.data_ptr(), gate.data_ptr(), hidden.data_ptr(), pool_sum.data_ptr(),
-                                hw, w1.data_ptr(), w2.data_ptr(), dgate.data_ptr(), dw1.data_ptr(), db1.data_ptr(),
+                                hw, w1.data_ptr(), w2.data_ptr(), dgate.data_ptr(), ws.data_ptr(), dw1.data_ptr(),
+                                db1.data_ptr(),
                                 dw2.data_ptr(), db2.data_ptr(), pool_grad.data_ptr(), b, c, rd, _stream()),
         'tfpp_se_bwd')
   return pool_grad

@@ -191,10 +191,11 @@ int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const float* mea
                 const float* gamma, const float* gate, const float* pool_grad, int act, float* s1, float* s2, void* draw,
                 void* dz_out, int batch, int hw, int channels, tfpp_stream_t stream);
 
-/* SE backward: dout = grad wrt (a2 * gate); outputs pool_grad (B,C) = dL/d(pool_sum) and fc1/fc2 gradients (+=). */
+/* SE backward: dout = grad wrt (a2 * gate); outputs pool_grad (B,C) = dL/d(pool_sum) and fc1/fc2 gradients (+=).
+ * dgate_sum (B,C) f32 zeroed by the caller and ws (B,rd) f32 are workspaces. */
 int tfpp_se_bwd(const void* dout, const void* a2, const float* gate, const float* hidden, const float* pool_sum, int hw,
-                const float* w1, const float* w2, float* dgate_sum, float* dw1, float* db1, float* dw2, float* db2,
-                float* pool_grad, int batch, int channels, int rd, tfpp_stream_t stream);
+                const float* w1, const float* w2, float* dgate_sum, float* ws, float* dw1, float* db1, float* dw2,
+                float* db2, float* pool_grad, int batch, int channels, int rd, tfpp_stream_t stream);
 
 /* dz = dy_scale * dy * act'(y) -> NHWC bf16 (channels_padded), dbias += column sums.
  * layout: 0 = dy,y NHWC bf16; 1 = NCHW f32; 2 = NHWC f32 (token matrices). dz may be NULL (bias gradient only). */
@@ -263,10 +264,11 @@ int tfpp_planner_loss(const float* logits, const long long* labels, const float*
                       int n_cls, int n_cp, tfpp_stream_t stream);
 
 /* AdamW(amsgrad=True), torch semantics; grad_scale multiplies the gradient first (1/world_size after a sum
- * all-reduce). */
+ * all-reduce).  dev_state (optional, 2 floats on the device: [step count, learning rate]) replaces the host-side
+ * `step` / `lr` so the launch can be replayed from a CUDA graph; the count is incremented by the call. */
 int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
                        long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                       float grad_scale, tfpp_stream_t stream);
+                       float grad_scale, float* dev_state, tfpp_stream_t stream);
 
 #ifdef __cplusplus
 }
