@@ -48,6 +48,8 @@ _PROTOS = {
     'tfpp_pillar_scatter': [P, I, I, P, P, I, F, F, F, F, F, I, F, F, P],
     'tfpp_conv_gemm': [ctypes.POINTER(ConvGemmArgs), P],
     'tfpp_conv_wgrad': [ctypes.POINTER(WgradArgs), P],
+    'tfpp_smallc_conv3x3': [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
+    'tfpp_smallc_wgrad3x3': [P, P, P, L, L, L, I, I, I, I, I, I, P],
     'tfpp_stem_conv': [P, P, P, P, P, P, I, P, P, P, I, I, I, I, P],
     'tfpp_bn_finalize': [P, P, P, P, P, P, P, P, P, P, I, F, F, F, P],
     'tfpp_scale_shift_act': [P, P, P, P, P, P, I, P, P, I, I, I, P],

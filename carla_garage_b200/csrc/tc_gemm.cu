@@ -197,13 +197,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const long long r2_base = bb * p.r2_sb + yy * p.r2_sy + xx * p.r2_sx;
 
       // one 32-column slab of the accumulator: statistics, affine, residuals, activation, store
+      const int nend = min(p.n, t.n0 + p.bn);  // columns [n0, nend) of this tile are real outputs
       auto process = [&](float* v, int c) {
         const int n = t.n0 + c;
-        if (n >= p.n) return;  // warp-uniform: padding columns
+        if (n >= nend) return;  // warp-uniform: padding columns
         if (p.stat_sum != nullptr) {
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
-            if (n + hf * 16 < p.n) {
+            if (n + hf * 16 < nend) {
               float s[16], q[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -222,10 +223,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if (p.out == nullptr || !valid) return;
-        const bool full = (n + 32 <= p.n);
+        const bool full = (n + 32 <= nend);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (full || n + j < p.n) {
+          if (full || n + j < nend) {
             float a = v[j];
             if (p.scale) a *= __ldg(p.scale + n + j);
             if (p.shift) a += __ldg(p.shift + n + j);
@@ -256,13 +257,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (full || n + j < p.n) v[j] += load_res(p.res1, p.res1_f32, r1_base + (n + j) * p.r1_sn);
+              if (full || n + j < nend) v[j] += load_res(p.res1, p.res1_f32, r1_base + (n + j) * p.r1_sn);
           }
         }
         if (p.res2) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (full || n + j < p.n) v[j] += load_res(p.res2, p.res2_f32, r2_base + (n + j) * p.r2_sn);
+            if (full || n + j < nend) v[j] += load_res(p.res2, p.res2_f32, r2_base + (n + j) * p.r2_sn);
         }
         if (p.act != ACT_NONE) {
 #pragma unroll
@@ -279,7 +280,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o_base + n);
 #pragma unroll
           for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else if (p.o_sn == 1 && !p.out_f32 && (p.n - n) >= 16 && ((o_base + n) & 7) == 0) {
+        } else if (p.o_sn == 1 && !p.out_f32 && (nend - n) >= 16 && ((o_base + n) & 7) == 0) {
           // 16-column tail (bn / N are multiples of 8 for every NHWC bf16 output of the model)
           uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_base + n);
 #pragma unroll
@@ -288,11 +289,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 pack_bf16x2(v[qd * 8 + 4], v[qd * 8 + 5]), pack_bf16x2(v[qd * 8 + 6], v[qd * 8 + 7]));
 #pragma unroll
           for (int j = 16; j < 32; ++j)
-            if (n + j < p.n) static_cast<bf16*>(p.out)[o_base + (n + j)] = f2bf(v[j]);
+            if (n + j < nend) static_cast<bf16*>(p.out)[o_base + (n + j)] = f2bf(v[j]);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (full || n + j < p.n) {
+            if (full || n + j < nend) {
               const long long off = o_base + (n + j) * p.o_sn;
               if (p.out_f32)
                 static_cast<float*>(p.out)[off] = v[j];

@@ -35,6 +35,12 @@ def packed(params, kind, *extra):
       w = ops.pack_conv_weight_t(params[0])
       pad = (-w.shape[2]) % 8
       out = torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
+    elif kind == 'conv_rows_pad':  # (Cout,Cin,3,3) -> (Cout padded to extra[0], 9, Cin) bf16
+      w = ops.pack_conv_weight(params[0])
+      out = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, extra[0] - w.shape[0])).contiguous()
+    elif kind == 'conv_dgrad_smallc':  # (Cout,Cin,3,3) -> (Cin, 9 flipped taps, Cout padded to extra[0]) bf16
+      w = params[0].detach().flip(2, 3).permute(1, 2, 3, 0).reshape(params[0].shape[1], 9, params[0].shape[0])
+      out = torch.nn.functional.pad(w, (0, extra[0] - w.shape[2])).to(BF16).contiguous()
     elif kind == 'gconv_t':
       out = ops.pack_grouped_conv_weight_t(params[0])
     elif kind == 'linear_t':  # (N,K) -> (K, N padded to 8)
@@ -184,8 +190,16 @@ class Engine:
     """nn.Conv2d with bias (+activation) as one implicit-GEMM launch."""
     k = conv.weight.shape[-1]
     taps = taps or (ops.TAPS_3X3 if k == 3 else ops.TAPS_1X1)
-    y = ops.conv_gemm(a, packed(conv.weight, 'conv'), taps=taps, shift=packed(conv.bias, 'f32'), act=act, **kw)
-    self._save(op='conv_bias', a=a, y=y, conv=conv, act=act, taps=taps, kw=kw)
+    cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+    cpad = 8 if cout <= 8 else (16 if cout <= 16 else 32)
+    smallc = (k == 3 and cout <= 32 and ops.smallc_supported(cin, cpad) and a.shape[1] * a.shape[2] >= 4096 and
+              (kw.get('out_layout') == 'nchw' or cout == cpad) and not set(kw) - {'out_layout', 'out_f32'})
+    if smallc:  # high-resolution, few channels: haloed shared-memory tile kernel (HBM-bound layers)
+      y = ops.smallc_conv3x3(a, packed(conv.weight, 'conv_rows_pad', cpad), bias=packed(conv.bias, 'f32'), act=act,
+                             n_valid=cout, out_nchw_f32=kw.get('out_layout') == 'nchw')
+    else:
+      y = ops.conv_gemm(a, packed(conv.weight, 'conv'), taps=taps, shift=packed(conv.bias, 'f32'), act=act, **kw)
+    self._save(op='conv_bias', a=a, y=y, conv=conv, act=act, taps=taps, kw=kw, smallc=smallc)
     return y
 
   # ------------------------------------------------------------------------------------------------ RegNet

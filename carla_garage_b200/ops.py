@@ -590,3 +590,34 @@ def small_mha_bwd(q, k, v, dout, dq, dk, dv, batch, heads, tq, tk, head_dim, q_s
                                        p(dk, offs[4]), dk_st[0], dk_st[1], p(dv, offs[5]), dv_st[0], dv_st[1],
                                        int(accumulate_kv), batch, heads, tq, tk, head_dim, _stream()),
         'tfpp_small_mha_bwd')
+
+
+# ---------------------------------------------------------------------------------------------- small-channel convs
+def smallc_supported(cin, cout_pad):
+  return (cin, cout_pad) in ((32, 32), (32, 16), (32, 8), (16, 32))
+
+
+def smallc_conv3x3(x, w, bias=None, act=ACT_NONE, act_n_limit=0, n_valid=None, out_nchw_f32=False):
+  """x (B,H,W,Cin) bf16, w (Cout_pad, 9, Cin) bf16 -> NHWC bf16 (B,H,W,Cout_pad) or NCHW f32 (B,n_valid,H,W)."""
+  _dev(x, BF16)
+  _dev(w, BF16)
+  b, h, wd, cin = x.shape
+  cout = w.shape[0]
+  n_valid = cout if n_valid is None else n_valid
+  if out_nchw_f32:
+    out = torch.empty((b, n_valid, h, wd), dtype=F32, device=x.device)
+  else:
+    out = torch.empty((b, h, wd, cout), dtype=BF16, device=x.device)
+  check(_lib.load().tfpp_smallc_conv3x3(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), int(out_nchw_f32), n_valid,
+                                        act, act_n_limit, b, h, wd, cin, cout, _stream()), 'tfpp_smallc_conv3x3')
+  return out
+
+
+def smallc_wgrad3x3(dy, x, out, out_strides, co_valid):
+  _dev(dy, BF16)
+  _dev(x, BF16)
+  b, h, w, cop = dy.shape
+  check(_lib.load().tfpp_smallc_wgrad3x3(dy.data_ptr(), x.data_ptr(), out.data_ptr(), out_strides[0], out_strides[1],
+                                         out_strides[2], co_valid, b, h, w, cop, x.shape[3], _stream()),
+        'tfpp_smallc_wgrad3x3')
+  return out

@@ -132,7 +132,7 @@ def compute_losses(eng, st, outputs, labels, weights):
   # semantic CE (model.py:423)
   hw = pred_sem.shape[2] * pred_sem.shape[3]
   ncls = pred_sem.shape[1]
-  cp = _pad8(ncls)
+  cp = 16  # multiple of 16: the small-channel dgrad / wgrad kernels take 16- or 32-channel gradients
   dz = torch.empty((b, pred_sem.shape[2], pred_sem.shape[3], cp), dtype=BF16, device=dev)
   conv = m.semantic_decoder.deconv3[2]
   _lib.check(lib.tfpp_ce_map_loss(pred_sem.data_ptr(), labels['semantic'].data_ptr(), None,
@@ -154,10 +154,10 @@ def compute_losses(eng, st, outputs, labels, weights):
   seeds[id(pred_bev)] = dbev
   # depth L1 on the sigmoid output (model.py:379,434)
   n = pred_depth.numel()
-  dzd = torch.empty((b, pred_depth.shape[1], pred_depth.shape[2], 8), dtype=BF16, device=dev)
+  dzd = torch.empty((b, pred_depth.shape[1], pred_depth.shape[2], 16), dtype=BF16, device=dev)
   convd = m.depth_decoder.deconv3[2]
   _lib.check(lib.tfpp_l1_sigmoid_loss(pred_depth.data_ptr(), labels['depth'].data_ptr(), weights['loss_depth'] / n,
-                                      sums[4:5].data_ptr(), dzd.data_ptr(), st.g(convd.bias).data_ptr(), 8, n, stream),
+                                      sums[4:5].data_ptr(), dzd.data_ptr(), st.g(convd.bias).data_ptr(), 16, n, stream),
              'l1 depth')
   losses['loss_depth'] = sums[4] / n
   seeds['depth'] = dzd
@@ -240,14 +240,25 @@ class Backward:
       dy = self.G.pop(id(y))
       if y.dtype == F32:  # NCHW f32 output consumed by something other than a loss
         raise RuntimeError('unexpected f32 intermediate')
+      if r.get('smallc'):
+        cp = 16 if cout <= 16 else 32
       if act == ACT_NONE and cp == cout:
         dz = dy
         ops.act_bwd(dy, None, ACT_NONE, b, h * w, cout, dbias=st.g(conv.bias), want_dz=False)
       else:
         dz = ops.act_bwd(dy, y, act, b, h * w, cout, dbias=st.g(conv.bias), channels_padded=cp).view(b, h, w, cp)
-    ops.conv_wgrad(dz.view(b, h, w, cp), a, cin=cin, taps=r['taps'], w_taps=k * k, out=st.g(conv.weight),
+    dz = dz.view(b, h, w, -1)
+    cp = dz.shape[3]
+    if r.get('smallc') and cp in (16, 32):
+      ops.smallc_wgrad3x3(dz, a, st.g(conv.weight), (cin * 9, 1, 9), cout)
+      da = ops.smallc_conv3x3(dz, packed(conv.weight, 'conv_dgrad_smallc', cp))
+      if id(a) in self.G:
+        ops.add_bf16(self.G[id(a)], da, out=da)
+      self.G[id(a)] = da
+      return
+    ops.conv_wgrad(dz, a, cin=cin, taps=r['taps'], w_taps=k * k, out=st.g(conv.weight),
                    out_strides=(cin * k * k, 1, k * k), cout_valid=cout)
-    self.G[id(a)] = self.conv_dgrad(dz.view(b, h, w, cp), conv.weight, k, None, res=self.G.get(id(a)))
+    self.G[id(a)] = self.conv_dgrad(dz, conv.weight, k, None, res=self.G.get(id(a)))
 
   def conv_bn(self, r):
     st = self.st

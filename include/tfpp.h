@@ -96,6 +96,18 @@ typedef struct {
 
 int tfpp_conv_wgrad(const tfpp_wgrad_args* args, tfpp_stream_t stream);
 
+/* ---- small-channel 3x3 convolutions at high resolution (PerspectiveDecoder tail, transfuser_utils.py:690-704) ------
+ * x NHWC bf16 (B,H,W,cin), w bf16 (cout, 9, cin) (tap = ky*3+kx reads x[y+ky-1][x+kx-1]; rows >= n_valid zero),
+ * out NHWC bf16 (B,H,W,cout) or NCHW f32 (B,n_valid,H,W).  (cin, cout) in {(32,32),(32,16),(32,8),(16,32)}.
+ * The input-gradient is the same call with the transposed, spatially flipped weight pack. */
+int tfpp_smallc_conv3x3(const void* x, const void* w, const float* bias, void* out, int out_nchw_f32, int n_valid,
+                        int act, int act_n_limit, int batch, int height, int width, int cin, int cout,
+                        tfpp_stream_t stream);
+/* dw[co, tap, ci] += sum_pixels dy[pix, co] * x[pix + tap, ci]; dy (B,H,W,cout_padded), x (B,H,W,cin=32). */
+int tfpp_smallc_wgrad3x3(const void* dy, const void* x, float* dw, long long s_co, long long s_tap, long long s_ci,
+                         int co_valid, int batch, int height, int width, int cout_padded, int cin,
+                         tfpp_stream_t stream);
+
 /* ---- stem conv: timm RegNet stem ConvNormAct(in,32,k3,s2,p1) fused with normalize_imagenet ---------------------
  * (team_code/transfuser.py:146-149,164-167; transfuser_utils.py:542-551).  x: NCHW f32 (B,cin<=3,H,W), w: f32
  * (32,cin,3,3); in_scale/in_shift: per-input-channel affine applied before zero padding (NULL = identity);

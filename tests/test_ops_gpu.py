@@ -295,3 +295,46 @@ def test_wgrad_grouped_and_stride2(ops, b, h, w, c):
   (gw,) = torch.autograd.grad(y, wt, dy2.float().permute(0, 3, 1, 2))
   got = ops.conv_wgrad(dy2, ops.parity_split(x), taps=ops.taps_3x3_stride2(b), group_width=24)
   assert rel(got, gw.permute(0, 2, 3, 1).reshape(c, 9, 24)) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ small-channel convs
+@pytest.mark.parametrize('cin,cout,h,w', [(32, 32, 64, 256), (32, 7, 48, 96), (32, 1, 40, 70), (16, 32, 64, 128)])
+def test_smallc_conv3x3(ops, cin, cout, h, w):
+  b = 2
+  x = bf(rnd(b, h, w, cin, seed=50))
+  wt = rnd(cout, cin, 3, 3, seed=51, scale=(9 * cin)**-0.5)
+  bias = rnd(cout, seed=52)
+  cpad = 8 if cout <= 8 else (16 if cout <= 16 else 32)
+  wp = torch.nn.functional.pad(ops.pack_conv_weight(wt), (0, 0, 0, 0, 0, cpad - cout)).contiguous()
+  want = conv_ref(x, bf(wt)) + bias  # NHWC
+  if cout == cpad:
+    got = ops.smallc_conv3x3(x, wp, bias=bias, act=ops.ACT_RELU)
+    assert rel(got.float(), F.relu(want)) < 6e-3
+  got = ops.smallc_conv3x3(x, wp, bias=bias, n_valid=cout, out_nchw_f32=True, act=ops.ACT_SIGMOID, act_n_limit=1)
+  w2 = want.permute(0, 3, 1, 2).clone()
+  w2[:, :1] = torch.sigmoid(w2[:, :1])
+  assert got.shape == (b, cout, h, w)
+  assert rel(got, w2) < 2e-3
+
+
+@pytest.mark.parametrize('cop,co_valid,h,w', [(32, 32, 64, 256), (16, 7, 48, 96), (16, 1, 40, 70)])
+def test_smallc_wgrad_and_dgrad(ops, cop, co_valid, h, w):
+  b, cin = 2, 32
+  x = bf(rnd(b, h, w, cin, seed=53))
+  dy = bf(rnd(b, h, w, cop, seed=54))
+  dy[..., co_valid:] = 0
+  wt = torch.zeros(co_valid, cin, 3, 3, device='cuda', requires_grad=True)
+  xin = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+  y = F.conv2d(xin, wt, None, padding=1)
+  gw, = torch.autograd.grad(y, wt, dy.float()[..., :co_valid].permute(0, 3, 1, 2))
+  out = torch.zeros(co_valid, cin, 3, 3, device='cuda')
+  ops.smallc_wgrad3x3(dy, x, out, (cin * 9, 1, 9), co_valid)
+  assert rel(out, gw) < 2e-3
+  # dgrad through the same forward kernel with the flipped / transposed pack
+  wr = rnd(co_valid, cin, 3, 3, seed=55, scale=0.1)
+  wd = wr.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, 9, co_valid)
+  wd = torch.nn.functional.pad(wd, (0, cop - co_valid)).to(torch.bfloat16).contiguous()
+  got = ops.smallc_conv3x3(dy, wd)
+  y2 = F.conv2d(xin, bf(wr).float(), None, padding=1)
+  gx, = torch.autograd.grad(y2, xin, dy.float()[..., :co_valid].permute(0, 3, 1, 2))
+  assert rel(got.float().permute(0, 3, 1, 2), gx) < 6e-3

@@ -1,0 +1,17 @@
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from carla_garage_b200 import ops
+which = sys.argv[1] if len(sys.argv) > 1 else 'qkv'
+if which == 'qkv':
+  x = torch.randn(10240, 1512, device='cuda').to(torch.bfloat16); w = torch.randn(4536, 1512, device='cuda').to(torch.bfloat16)
+  f = lambda: ops.linear(x, w)
+elif which == 'dec5':
+  x = torch.randn(32, 256, 1024, 32, device='cuda').to(torch.bfloat16); w = torch.randn(32, 9, 32, device='cuda').to(torch.bfloat16)
+  f = lambda: ops.conv_gemm(x, w, taps=ops.TAPS_3X3)
+elif which == 's1stats':
+  x = torch.randn(32, 64, 256, 72, device='cuda').to(torch.bfloat16); w = torch.randn(72, 1, 72, device='cuda').to(torch.bfloat16)
+  st = (torch.zeros(72, device='cuda'), torch.zeros(72, device='cuda'))
+  f = lambda: ops.conv_gemm(x, w, stats=st)
+for _ in range(4): f()
+torch.cuda.synchronize()
