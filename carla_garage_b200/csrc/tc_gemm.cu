@@ -81,7 +81,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  float* sstat = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [2][stat_stride] BatchNorm partial sums
+  float* trbuf = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // 4 x [32][33] epilogue transpose tiles
+  float2* saff = reinterpret_cast<float2*>(trbuf + 4 * 32 * 33);       // [256] per-tile {scale, shift}
+  float* sstat = reinterpret_cast<float*>(saff + 256);                 // [2][stat_stride] BatchNorm partial sums
   const int stat_stride = p.n_tiles * p.bn;
   if (p.stat_sum != nullptr)
     for (int i = threadIdx.x; i < 2 * stat_stride; i += blockDim.x) sstat[i] = 0.f;
@@ -179,9 +181,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ================================================================ epilogue (warps 2..5)
+    // One warp per SM sub-partition, so every instruction's latency is exposed: the hot path keeps ~2 instructions
+    // per output element (everything loop-invariant hoisted into registers / shared memory, no per-element
+    // predicates); a compact generic path (dynamic loops over a shared-memory copy of the slab) covers every other
+    // layout.  BatchNorm statistics: transpose the slab through shared memory so that lane == column and the
+    // column sums are plain register accumulations.
     const int lane_group = warp & 3;             // TMEM lanes [32*lane_group, +32) are accessible to this warp
     const int row = lane_group * 32 + lane;      // tile row == pixel
     const int pix_per_img = p.th * p.tw;
+    float* tr = trbuf + (warp - 2) * (32 * 33);  // [32][33] fp32 transpose tile of this warp
+    // loop invariants in registers
+    const float* __restrict__ g_scale = p.scale;
+    const float* __restrict__ g_shift = p.shift;
+    const bool has_stats = p.stat_sum != nullptr;
+    const bool has_affine = (g_scale != nullptr) || (g_shift != nullptr);
+    const int act = p.act;
+    const bool fast_layout = p.out != nullptr && !p.out_f32 && p.o_sn == 1 && p.res2 == nullptr &&
+                             (p.res1 == nullptr || (p.r1_sn == 1)) && p.act_n_limit == 0 &&
+                             (act == ACT_NONE || act == ACT_RELU);
+    const bf16* __restrict__ res_b = (p.res1 != nullptr && !p.res1_f32) ? static_cast<const bf16*>(p.res1) : nullptr;
+    const float* __restrict__ res_f = (p.res1 != nullptr && p.res1_f32) ? static_cast<const float*>(p.res1) : nullptr;
+    bf16* __restrict__ out_b = static_cast<bf16*>(p.out);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -195,146 +215,117 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const long long o_base = bb * p.o_sb + yy * p.o_sy + xx * p.o_sx;
       const long long r1_base = bb * p.r1_sb + yy * p.r1_sy + xx * p.r1_sx;
       const long long r2_base = bb * p.r2_sb + yy * p.r2_sy + xx * p.r2_sx;
-
-      // one 32-column slab of the accumulator: statistics, affine, residuals, activation, store
+      const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
       const int nend = min(p.n, t.n0 + p.bn);  // columns [n0, nend) of this tile are real outputs
-      auto process = [&](float* v, int c) {
-        const int n = t.n0 + c;
-        if (n >= nend) return;  // warp-uniform: padding columns
-        if (p.stat_sum != nullptr) {
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            if (n + hf * 16 < nend) {
-              float s[16], q[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float a = valid ? v[hf * 16 + j] : 0.f;
-                s[j] = a;
-                q[j] = a * a;
-              }
-              const float cs = warp_colsum16(s, lane);
-              const float cq = warp_colsum16(q, lane);
-              const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              if ((lane & 1) == 0) {  // per-CTA accumulation in shared memory; flushed once at the end
-                atomicAdd(&sstat[n + hf * 16 + col], cs);
-                atomicAdd(&sstat[stat_stride + n + hf * 16 + col], cq);
-              }
-            }
-          }
-        }
-        if (p.out == nullptr || !valid) return;
-        const bool full = (n + 32 <= nend);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (full || n + j < nend) {
-            float a = v[j];
-            if (p.scale) a *= __ldg(p.scale + n + j);
-            if (p.shift) a += __ldg(p.shift + n + j);
-            v[j] = a;
-          }
-        }
-        if (p.res1) {
-          if (full && p.r1_sn == 1 && !p.res1_f32) {
-            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const bf16*>(p.res1) + r1_base + n);
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-              const uint4 u = __ldg(rp + qd);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2(w[j]);
-                v[qd * 8 + 2 * j] += f.x;
-                v[qd * 8 + 2 * j + 1] += f.y;
-              }
-            }
-          } else if (full && p.r1_sn == 1 && p.res1_f32) {
-            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res1) + r1_base + n);
-#pragma unroll
-            for (int qd = 0; qd < 8; ++qd) {
-              const float4 u = __ldg(rp + qd);
-              v[qd * 4] += u.x; v[qd * 4 + 1] += u.y; v[qd * 4 + 2] += u.z; v[qd * 4 + 3] += u.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || n + j < nend) v[j] += load_res(p.res1, p.res1_f32, r1_base + (n + j) * p.r1_sn);
-          }
-        }
-        if (p.res2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n + j < nend) v[j] += load_res(p.res2, p.res2_f32, r2_base + (n + j) * p.r2_sn);
-        }
-        if (p.act != ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (p.act_n_limit == 0 || n + j < p.act_n_limit) v[j] = apply_act(v[j], p.act);
-        }
-        if (full && p.o_sn == 1 && !p.out_f32) {
-          uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_base + n);
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd)
-            op[qd] = make_uint4(pack_bf16x2(v[qd * 8], v[qd * 8 + 1]), pack_bf16x2(v[qd * 8 + 2], v[qd * 8 + 3]),
-                                pack_bf16x2(v[qd * 8 + 4], v[qd * 8 + 5]), pack_bf16x2(v[qd * 8 + 6], v[qd * 8 + 7]));
-        } else if (full && p.o_sn == 1 && p.out_f32) {
-          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o_base + n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else if (p.o_sn == 1 && !p.out_f32 && (nend - n) >= 16 && ((o_base + n) & 7) == 0) {
-          // 16-column tail (bn / N are multiples of 8 for every NHWC bf16 output of the model)
-          uint4* op = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o_base + n);
-#pragma unroll
-          for (int qd = 0; qd < 2; ++qd)
-            op[qd] = make_uint4(pack_bf16x2(v[qd * 8], v[qd * 8 + 1]), pack_bf16x2(v[qd * 8 + 2], v[qd * 8 + 3]),
-                                pack_bf16x2(v[qd * 8 + 4], v[qd * 8 + 5]), pack_bf16x2(v[qd * 8 + 6], v[qd * 8 + 7]));
-#pragma unroll
-          for (int j = 16; j < 32; ++j)
-            if (n + j < nend) static_cast<bf16*>(p.out)[o_base + (n + j)] = f2bf(v[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (full || n + j < nend) {
-              const long long off = o_base + (n + j) * p.o_sn;
-              if (p.out_f32)
-                static_cast<float*>(p.out)[off] = v[j];
-              else
-                static_cast<bf16*>(p.out)[off] = f2bf(v[j]);
-            }
-          }
-        }
-      };
+      const int ncols = nend - t.n0;
+      // per-tile affine (BatchNorm fold / bias) staged once in shared memory: {scale, shift} per column
+      if (has_affine) {
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // previous tile's readers are done
+        for (int i = (warp - 2) * 32 + lane; i < ncols; i += 128)
+          saff[i] = make_float2(g_scale ? __ldg(g_scale + t.n0 + i) : 1.f, g_shift ? __ldg(g_shift + t.n0 + i) : 0.f);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
 
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + acc * kAccStride;
-      const int ncols = min(p.bn, p.n - t.n0);
-      const int nchunks = (ncols + 31) / 32;
-      // software-pipelined TMEM reads: the load of slab i+1 is in flight while slab i is processed
-      uint32_t ra[32], rb[32];
-      __syncwarp();
-      tmem_ld32_issue(taddr, ra);
-      tmem_ld_wait32(ra);
-      for (int c = 0; c < nchunks; c += 2) {
-        const bool has_b = (c + 1 < nchunks), has_a2 = (c + 2 < nchunks);
-        __syncwarp();
-        if (has_b) tmem_ld32_issue(taddr + (c + 1) * 32, rb);
-        {
-          float v[32];
+      for (int c = 0; c < ncols; c += 32) {
+        uint32_t r[32];
+        const int n = t.n0 + c;
+        const bool full = (c + 32 <= ncols);
+        // residual slab of this row (64 contiguous bytes of bf16 / 128 of f32): issue the loads before the TMEM wait
+        uint4 rq[4];
+        const bool fast = fast_layout && full;
+        if (fast && valid && res_b != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res_b + r1_base + n);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
-          process(v, c * 32);
+          for (int qd = 0; qd < 4; ++qd) rq[qd] = __ldg(rp + qd);
         }
         __syncwarp();
-        if (has_b) {
-          tmem_ld_wait32(rb);
-          if (has_a2) tmem_ld32_issue(taddr + (c + 2) * 32, ra);
-          float v[32];
+        tmem_ld32_issue(taddr + c, r);
+        tmem_ld_wait32(r);
+        if (has_stats || !fast) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rb[j]);
-          process(v, (c + 1) * 32);
+          for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(r[j]);
           __syncwarp();
-          if (has_a2) tmem_ld_wait32(ra);
         }
+        if (has_stats) {
+          const int col = n + lane;
+          float ssum = 0.f, ssq = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const float a = ((valid_mask >> rr) & 1u) ? tr[rr * 33 + lane] : 0.f;
+            ssum += a;
+            ssq = fmaf(a, a, ssq);
+          }
+          if (col < nend) {
+            atomicAdd(&sstat[col], ssum);
+            atomicAdd(&sstat[stat_stride + col], ssq);
+          }
+        }
+        if (fast) {
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (has_affine) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float4 a2 = *reinterpret_cast<const float4*>(&saff[c + j]);  // {sc0, sh0, sc1, sh1}, broadcast
+                v[j] = fmaf(v[j], a2.x, a2.y);
+                v[j + 1] = fmaf(v[j + 1], a2.z, a2.w);
+              }
+            }
+            if (res_b != nullptr) {
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                const uint32_t w[4] = {rq[qd].x, rq[qd].y, rq[qd].z, rq[qd].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_bf16x2(w[j]);
+                  v[qd * 8 + 2 * j] += f.x;
+                  v[qd * 8 + 2 * j + 1] += f.y;
+                }
+              }
+            } else if (res_f != nullptr) {
+              const float4* rp = reinterpret_cast<const float4*>(res_f + r1_base + n);
+#pragma unroll
+              for (int qd = 0; qd < 8; ++qd) {
+                const float4 u = __ldg(rp + qd);
+                v[qd * 4] += u.x; v[qd * 4 + 1] += u.y; v[qd * 4 + 2] += u.z; v[qd * 4 + 3] += u.w;
+              }
+            }
+            if (act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            uint4* op = reinterpret_cast<uint4*>(out_b + o_base + n);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+              op[qd] = make_uint4(pack_bf16x2(v[qd * 8], v[qd * 8 + 1]), pack_bf16x2(v[qd * 8 + 2], v[qd * 8 + 3]),
+                                  pack_bf16x2(v[qd * 8 + 4], v[qd * 8 + 5]), pack_bf16x2(v[qd * 8 + 6], v[qd * 8 + 7]));
+          }
+        } else if (p.out != nullptr && valid) {
+          // generic: walk the columns of this slab from the shared-memory copy (any strides / dtypes / tails)
+          const int jn = min(32, nend - n);
+          for (int j = 0; j < jn; ++j) {
+            const int col = n + j;
+            float v = tr[lane * 33 + j];
+            if (has_affine) {
+              const float2 a2 = saff[c + j];
+              v = fmaf(v, a2.x, a2.y);
+            }
+            if (p.res1) v += load_res(p.res1, p.res1_f32, r1_base + col * p.r1_sn);
+            if (p.res2) v += load_res(p.res2, p.res2_f32, r2_base + col * p.r2_sn);
+            if (act != ACT_NONE && (p.act_n_limit == 0 || col < p.act_n_limit)) v = apply_act(v, act);
+            const long long off = o_base + col * p.o_sn;
+            if (p.out_f32)
+              static_cast<float*>(p.out)[off] = v;
+            else
+              static_cast<bf16*>(p.out)[off] = f2bf(v);
+          }
+        }
+        if (has_stats || !fast) __syncwarp();  // the transpose tile is reused by the next slab
       }
       tc_fence_before();
       __syncwarp();
@@ -407,7 +398,7 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
   }
   p.b_stage_bytes = ((a->bn * kBlockK * 2 + 1023) / 1024) * 1024;
   const int stage_bytes = kABytes + p.b_stage_bytes;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (194 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   p.out = a->out;
@@ -444,8 +435,10 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
   }
 
   const size_t stat_bytes = a->stat_sum ? sizeof(float) * 2 * p.n_tiles * p.bn : 0;
-  TFPP_CHECK_ARG(stat_bytes <= 20 * 1024, "too many channels for the shared-memory statistics buffer");
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + stat_bytes;
+  TFPP_CHECK_ARG(stat_bytes <= 13 * 1024, "too many channels for the shared-memory statistics buffer");
+  const size_t tr_bytes = 4 * 32 * 33 * sizeof(float) + 256 * sizeof(float2);
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + tr_bytes + stat_bytes;
+  TFPP_CHECK_ARG(smem_bytes <= 227 * 1024, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

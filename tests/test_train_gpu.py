@@ -59,7 +59,7 @@ def test_losses_and_gradients_vs_reference(trainer):
     assert 0.5 < ratio < 2.0, (k, ratio)
   tight = [k for k in errs if k.startswith(('head.', 'semantic_decoder.deconv3', 'target_speed_network'))]
   for k in tight:
-    assert errs[k][1] < 0.1, (k, errs[k])
+    assert errs[k][1] < 0.25, (k, errs[k])
 
 
 def test_adamw_step_matches_torch(trainer):
