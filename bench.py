@@ -128,7 +128,7 @@ def main():
   torch.cuda.set_device(local_rank)
   pg = None
   if world > 1:
-    dist.init_process_group('nccl', init_method='env://')
+    dist.init_process_group('nccl', init_method='env://', device_id=torch.device('cuda', local_rank))
     pg = dist.group.WORLD
   from carla_garage_b200 import _lib, ops, synth
   from carla_garage_b200.config import GlobalConfig
@@ -171,7 +171,7 @@ def main():
   # ---- device-resident throughput.  N=1: the whole step (K1 + fwd + losses + bwd + AdamW) replays from one CUDA
   # graph; N>1: eager launches (the NCCL all-reduce stays outside graph capture in this round).
   dev_pts = host_pts.cuda()
-  use_graph = world == 1 and os.environ.get('TFPP_NO_GRAPH', '0') != '1'
+  use_graph = (world == 1 or os.environ.get('TFPP_GRAPH_NCCL', '0') == '1') and os.environ.get('TFPP_NO_GRAPH', '0') != '1'
   if use_graph:
     tr.capture(dev_in, dev_lab, points=dev_pts)
 
@@ -223,8 +223,14 @@ def main():
   except Exception:  # pylint: disable=broad-except
     pass
   roof = None
+  if world > 1:  # every collective of the run is behind us: the rest is rank-local work on rank 0
+    barrier()
+    dist.destroy_process_group()
   if rank == 0:
+    # rank-local instrumented step: no collective inside (the other ranks are not running it)
+    tr_world, tr.world = tr.world, 1
     prof = ops.profile_gemm_launches(lambda: tr.step(dev_in, dev_lab))
+    tr.world = tr_world
     peak = peaks.get('bf16_tflops_sustained', 1400.0)
     roof = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel + wgrad_kernel (tcgen05)',
             'achieved': prof['tflops'], 'peak': peak, 'unit': 'TFLOP/s', 'frac': prof['tflops'] / peak,

@@ -68,6 +68,7 @@ _PROTOS = {
     'tfpp_planner_head': [P] * 17 + [I, I, I, I, I, P],
     'tfpp_decode_heatmap': [P, L, P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, F, F, P],
     'tfpp_bn_bwd': [P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P],
+    'tfpp_gather_pack': [P, P, P, L, I, P],
     'tfpp_se_bwd': [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, I, I, I, P],
     'tfpp_act_bwd': [P, P, I, I, I, F, P, P, I, I, I, I, P],
     'tfpp_bilinear_bwd': [P, P, I, L, L, I, I, I, I, I, I, I, P],
@@ -116,7 +117,7 @@ def load():
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
-_KERNELS_PER_CALL = {'tfpp_adamw_amsgrad': 2, 'tfpp_pillar_scatter': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 3, 'tfpp_fusion_attn_bwd': 2}
+_KERNELS_PER_CALL = {'tfpp_adamw_amsgrad': 2, 'tfpp_pillar_scatter': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 4, 'tfpp_se_gate': 2, 'tfpp_fusion_attn_bwd': 2}
 _LAUNCHES = [0]
 
 

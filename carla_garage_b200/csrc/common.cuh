@@ -39,6 +39,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// 16-byte streaming load (no L1 allocation: every byte of these feature maps is touched exactly once per kernel)
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(t);

@@ -5,6 +5,7 @@
 // Reference call sites are cited per entry point.
 #include "../../include/tfpp.h"
 #include "common.cuh"
+#include "se_kernels.cuh"
 
 namespace {
 
@@ -149,38 +150,54 @@ __global__ void __launch_bounds__(256) scale_shift_act_kernel(const bf16* __rest
       rsh[j] = res_scale ? __ldg(res_shift + c0 + j) : 0.f;
       pl[j] = 0.f;
     }
-    for (int pix = p0 + prow; pix < p1; pix += rows_pp) {
-      const long long off = base + static_cast<long long>(pix) * C + c0;
-      const uint4 u = *reinterpret_cast<const uint4*>(x + off);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-      float v[8];
+    // U pixel rows per trip: all loads are issued before any is consumed (2*U 16-byte requests in flight per thread),
+    // which is what it takes to cover HBM latency at ~512 resident threads per SM
+    constexpr int U = 4;
+    for (int pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+      uint4 u[U], r[U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(w[j]);
-        v[2 * j] = f.x * sc[2 * j] + sh[2 * j];
-        v[2 * j + 1] = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+      for (int k = 0; k < U; ++k) {
+        const int px = pix + k * rows_pp;
+        if (px < p1) {
+          const long long off = base + static_cast<long long>(px) * C + c0;
+          u[k] = ld_stream16(x + off);
+          if (res != nullptr) r[k] = ld_stream16(res + off);
+        }
       }
-      if (res != nullptr) {
-        const uint4 r = *reinterpret_cast<const uint4*>(res + off);
-        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int px = pix + k * rows_pp;
+        if (px >= p1) break;
+        const long long off = base + static_cast<long long>(px) * C + c0;
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        float v[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(rw[j]);
-          v[2 * j] += f.x * rsc[2 * j] + rsh[2 * j];
-          v[2 * j + 1] += f.y * rsc[2 * j + 1] + rsh[2 * j + 1];
+          const float2 f = unpack_bf16x2(w[j]);
+          v[2 * j] = f.x * sc[2 * j] + sh[2 * j];
+          v[2 * j + 1] = f.y * sc[2 * j + 1] + sh[2 * j + 1];
         }
-      }
-      uint32_t o[4];
+        if (res != nullptr) {
+          const uint32_t rw[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        o[j] = pack_bf16x2(apply_act(v[2 * j], act), apply_act(v[2 * j + 1], act));
-        if (pool_sum != nullptr) {  // SE squeezes the tensor the next layer will actually read (bf16-rounded)
-          const float2 f = unpack_bf16x2(o[j]);
-          pl[2 * j] += f.x;
-          pl[2 * j + 1] += f.y;
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(rw[j]);
+            v[2 * j] += f.x * rsc[2 * j] + rsh[2 * j];
+            v[2 * j + 1] += f.y * rsc[2 * j + 1] + rsh[2 * j + 1];
+          }
         }
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = pack_bf16x2(apply_act(v[2 * j], act), apply_act(v[2 * j + 1], act));
+          if (pool_sum != nullptr) {  // SE squeezes the tensor the next layer will actually read (bf16-rounded)
+            const float2 f = unpack_bf16x2(o[j]);
+            pl[2 * j] += f.x;
+            pl[2 * j + 1] += f.y;
+          }
+        }
+        *reinterpret_cast<uint4*>(y + off) = make_uint4(o[0], o[1], o[2], o[3]);
       }
-      *reinterpret_cast<uint4*>(y + off) = make_uint4(o[0], o[1], o[2], o[3]);
     }
     if (pool_sum != nullptr) {
 #pragma unroll
@@ -193,58 +210,36 @@ __global__ void __launch_bounds__(256) scale_shift_act_kernel(const bf16* __rest
   }
 }
 
-// timm SEModule (oracle/regnety.py): gate = sigmoid(fc2(relu(fc1(mean_hw(x))))).  One block per sample.
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ pool_sum, float inv_hw,
-                                                      const float* __restrict__ w1, const float* __restrict__ b1,
-                                                      const float* __restrict__ w2, const float* __restrict__ b2,
-                                                      float* __restrict__ gate, float* __restrict__ hidden_out, int C,
-                                                      int R) {
-  extern __shared__ float sm[];
-  float* mean = sm;      // C
-  float* hid = sm + C;   // R
-  const int b = blockIdx.x;  // blockIdx.y = slice of the gate outputs (the small hidden layer is recomputed per slice)
-  for (int i = threadIdx.x; i < C; i += blockDim.x) mean[i] = pool_sum[static_cast<long long>(b) * C + i] * inv_hw;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int r = warp; r < R; r += nwarps) {
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(w1[static_cast<long long>(r) * C + c], mean[c], a);
-    a = warp_sum(a);
-    if (lane == 0) {
-      const float h = fmaxf(a + b1[r], 0.f);
-      hid[r] = h;
-      if (hidden_out && blockIdx.y == 0) hidden_out[static_cast<long long>(b) * R + r] = h;
-    }
-  }
-  __syncthreads();
-  const int per = (C + gridDim.y - 1) / gridDim.y;
-  const int cbeg = blockIdx.y * per, cend = min(C, cbeg + per);
-  for (int c = cbeg + threadIdx.x; c < cend; c += blockDim.x) {
-    float a = b2[c];
-    for (int r = 0; r < R; ++r) a = fmaf(w2[static_cast<long long>(c) * R + r], hid[r], a);
-    gate[static_cast<long long>(b) * C + c] = 1.f / (1.f + __expf(-a));
-  }
-}
-
 // y[b,p,c] = x[b,p,c] * gate[b,c]
 __global__ void __launch_bounds__(256) channel_scale_kernel(const bf16* __restrict__ x, const float* __restrict__ gate,
                                                             bf16* __restrict__ y, long long total8, int HW, int C) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
+  constexpr int U = 4;  // 16-byte groups per thread, strided by the block so every request stays coalesced
+  const long long i0 = static_cast<long long>(blockIdx.x) * (blockDim.x * U) + threadIdx.x;
   const int c8n = C / 8;
-  const int c0 = static_cast<int>(i % c8n) * 8;
-  const long long pix = i / c8n;
-  const int b = static_cast<int>(pix / HW);
-  const uint4 u = *reinterpret_cast<const uint4*>(x + i * 8);
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-  uint32_t o[4];
-  const float* g = gate + static_cast<long long>(b) * C + c0;
+  uint4 u[U];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = unpack_bf16x2(w[j]);
-    o[j] = pack_bf16x2(f.x * __ldg(g + 2 * j), f.y * __ldg(g + 2 * j + 1));
+  for (int k = 0; k < U; ++k) {
+    const long long i = i0 + static_cast<long long>(k) * blockDim.x;
+    if (i < total8) u[k] = ld_stream16(x + i * 8);
   }
-  *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const long long i = i0 + static_cast<long long>(k) * blockDim.x;
+    if (i >= total8) break;
+    const int c0 = static_cast<int>(i % c8n) * 8;
+    const int b = static_cast<int>((i / c8n) / HW);
+    const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+    uint32_t o[4];
+    const float4* g = reinterpret_cast<const float4*>(gate + static_cast<long long>(b) * C + c0);
+    const float4 g0 = __ldg(g), g1 = __ldg(g + 1);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      o[j] = pack_bf16x2(f.x * gg[2 * j], f.y * gg[2 * j + 1]);
+    }
+    *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 // (B,H,W,C) -> (4B,H/2,W/2,C): plane q = (y&1)*2 + (x&1) stored at batch q*B + b.  Turns stride-2 3x3 / 1x1
@@ -469,8 +464,9 @@ extern "C" int tfpp_scale_shift_act(const void* x, const void* res, const float*
   STREAM;
   TFPP_CHECK_ARG(channels % 8 == 0 && channels <= 2048, "channels must be a multiple of 8, <= 2048");
   TFPP_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift go together");
-  // aim for >= 2 waves of CTAs over the whole batch
-  int chunks = ceil_div(TFPP_NUM_SMS * 4, batch);
+  // two full waves of (up to) three resident CTAs per SM, never a partial extra wave
+  int chunks = TFPP_NUM_SMS * 6 / batch;
+  if (chunks < 1) chunks = 1;
   int pix_per_block = ceil_div(hw, chunks);
   if (pix_per_block < 8) pix_per_block = 8;
   chunks = ceil_div(hw, pix_per_block);
@@ -487,8 +483,13 @@ extern "C" int tfpp_se_gate(const float* pool_sum, int hw, const float* w1, cons
                             const float* b2, float* gate, float* hidden, int batch, int channels, int rd,
                             tfpp_stream_t stream_) {
   STREAM;
-  se_gate_kernel<<<dim3(batch, 4), 256, sizeof(float) * (channels + rd), stream>>>(pool_sum, 1.f / hw, w1, b1, w2, b2, gate,
-                                                                          hidden, channels, rd);
+  TFPP_CHECK_ARG(hidden != nullptr && rd <= 2048, "hidden workspace (B,rd) is required; rd <= 2048");
+  // gate = sigmoid(fc2(relu(fc1(mean_hw(x))))): two batched contractions (se_kernels.cuh)
+  se_contract_c_kernel<SE_FWD><<<dim3(ceil_div(rd, 8), ceil_div(batch, 8)), 256, 0, stream>>>(
+      pool_sum, nullptr, 1.f / hw, w1, channels, 1, b1, nullptr, hidden, nullptr, batch, channels, rd);
+  TFPP_CHECK_LAUNCH();
+  se_contract_r_kernel<SE_FWD><<<dim3(ceil_div(channels, 128), ceil_div(batch, 8)), 128, sizeof(float) * rd * 8, stream>>>(
+      hidden, w2, rd, 1, b2, 1.f, gate, batch, channels, rd);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }
@@ -498,7 +499,7 @@ extern "C" int tfpp_channel_scale(const void* x, const float* gate, void* y, int
   STREAM;
   TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
   const long long total8 = static_cast<long long>(batch) * hw * channels / 8;
-  channel_scale_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, stream>>>(
+  channel_scale_kernel<<<static_cast<int>(ceil_div_ll(total8, 256 * 4)), 256, 0, stream>>>(
       static_cast<const bf16*>(x), gate, static_cast<bf16*>(y), total8, hw, channels);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;

@@ -4,11 +4,21 @@
 // team_code/train.py:898 (loss.backward()) over the modules cited in featmap.cu.
 #include "../../include/tfpp.h"
 #include "common.cuh"
+#include "se_kernels.cuh"
 
 namespace {
 
 __device__ __forceinline__ void load8(const bf16* p, float* v) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -58,18 +68,33 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
       gt[j] = gate ? __ldg(gate + static_cast<long long>(b) * C + c0 + j) : 1.f;
       pg[j] = pool_grad ? __ldg(pool_grad + static_cast<long long>(b) * C + c0 + j) : 0.f;
     }
-    for (int pix = p0 + prow; pix < p1; pix += rows_pp) {
-      const long long off = base + static_cast<long long>(pix) * C + c0;
-      float d[8], yy[8], r[8];
-      load8(dy + off, d);
-      load8(raw + off, r);
-      if (act == ACT_RELU) load8(y + off, yy);
+    constexpr int U = 2;  // pixel rows per trip; every load of the trip is in flight before the first is consumed
+    for (int pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+      uint4 ud[U], ur[U], uy[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float dz = d[j] * gt[j] + pg[j];
-        if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
-        l1[j] += dz;
-        l2[j] = fmaf(dz, (r[j] - mu[j]) * is[j], l2[j]);
+      for (int k = 0; k < U; ++k) {
+        const int px = pix + k * rows_pp;
+        if (px < p1) {
+          const long long off = base + static_cast<long long>(px) * C + c0;
+          ud[k] = ld_stream16(dy + off);
+          ur[k] = ld_stream16(raw + off);
+          if (act == ACT_RELU) uy[k] = ld_stream16(y + off);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (pix + k * rows_pp >= p1) break;
+        float d[8], yy[8], r[8];
+        unpack8(ud[k], d);
+        unpack8(ur[k], r);
+        if (act == ACT_RELU) unpack8(uy[k], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dz = d[j] * gt[j] + pg[j];
+          if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
+          l1[j] += dz;
+          l2[j] = fmaf(dz, (r[j] - mu[j]) * is[j], l2[j]);
+        }
       }
     }
 #pragma unroll
@@ -91,32 +116,61 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
                                                            const float* __restrict__ gamma, const float* __restrict__ s1,
                                                            const float* __restrict__ s2, const float* __restrict__ gate,
                                                            const float* __restrict__ pool_grad, int act, float inv_n,
-                                                           bf16* __restrict__ draw, bf16* __restrict__ dz_out,
-                                                           long long total8, int HW, int C) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int c8n = C / 8;
-  const int c0 = static_cast<int>(i % c8n) * 8;
-  const long long pix = i / c8n;
-  const int b = static_cast<int>(pix / HW);
-  float d[8], yy[8], r[8], o[8], z[8];
-  load8(dy + i * 8, d);
-  load8(raw + i * 8, r);
-  if (act == ACT_RELU) load8(y + i * 8, yy);
+                                                           bf16* __restrict__ draw, bf16* __restrict__ dz_out, int HW,
+                                                           int C, int pix_per_block) {
+  // same walk as the reduce pass: a thread keeps its 8 channels' constants in registers and streams pixels
+  //   draw = k0 * dz + k1 * raw + k2,  k0 = gamma*invstd, k1 = -k0*invstd*s2/N, k2 = -k0*s1/N - k1*mean
+  const int b = blockIdx.y, c8n = C / 8;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  const long long base = static_cast<long long>(b) * HW * C;
+  const int rows_pp = blockDim.x / c8n;
+  const int cg = threadIdx.x % c8n, prow = threadIdx.x / c8n;
+  if (prow >= rows_pp) return;
+  const int c0 = cg * 8;
+  float k0[8], k1[8], k2[8], gt[8], pg[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
-    float dz = d[j];
-    if (gate) dz *= __ldg(gate + static_cast<long long>(b) * C + c);
-    if (pool_grad) dz += __ldg(pool_grad + static_cast<long long>(b) * C + c);
-    if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
-    z[j] = dz;
     const float is = __ldg(invstd + c);
-    const float xh = (r[j] - __ldg(mean + c)) * is;
-    o[j] = __ldg(gamma + c) * is * (dz - __ldg(s1 + c) * inv_n - xh * __ldg(s2 + c) * inv_n);
+    k0[j] = __ldg(gamma + c) * is;
+    k1[j] = -k0[j] * is * __ldg(s2 + c) * inv_n;
+    k2[j] = -k0[j] * __ldg(s1 + c) * inv_n - k1[j] * __ldg(mean + c);
+    gt[j] = gate ? __ldg(gate + static_cast<long long>(b) * C + c) : 1.f;
+    pg[j] = pool_grad ? __ldg(pool_grad + static_cast<long long>(b) * C + c) : 0.f;
   }
-  store8(draw + i * 8, o);
-  if (dz_out) store8(dz_out + i * 8, z);
+  constexpr int U = 2;
+  for (int pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+    uint4 ud[U], ur[U], uy[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int px = pix + k * rows_pp;
+      if (px < p1) {
+        const long long off = base + static_cast<long long>(px) * C + c0;
+        ud[k] = ld_stream16(dy + off);
+        ur[k] = ld_stream16(raw + off);
+        if (act == ACT_RELU) uy[k] = ld_stream16(y + off);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int px = pix + k * rows_pp;
+      if (px >= p1) break;
+      const long long off = base + static_cast<long long>(px) * C + c0;
+      float d[8], yy[8], r[8], o[8], z[8];
+      unpack8(ud[k], d);
+      unpack8(ur[k], r);
+      if (act == ACT_RELU) unpack8(uy[k], yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dz = d[j] * gt[j] + pg[j];
+        if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
+        z[j] = dz;
+        o[j] = fmaf(k0[j], dz, fmaf(k1[j], r[j], k2[j]));
+      }
+      store8(draw + off, o);
+      if (dz_out) store8(dz_out + off, z);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- SE backward
@@ -135,13 +189,27 @@ __global__ void __launch_bounds__(256) se_bwd_reduce_kernel(const bf16* __restri
   if (prow < rows_pp) {
     const int c0 = cg * 8;
     float l[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int pix = p0 + prow; pix < p1; pix += rows_pp) {
-      const long long off = base + static_cast<long long>(pix) * C + c0;
-      float d[8], a[8];
-      load8(dout + off, d);
-      load8(a2 + off, a);
+    constexpr int U = 4;
+    for (int pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+      uint4 ud[U], ua[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) l[j] = fmaf(d[j], a[j], l[j]);
+      for (int k = 0; k < U; ++k) {
+        const int px = pix + k * rows_pp;
+        if (px < p1) {
+          const long long off = base + static_cast<long long>(px) * C + c0;
+          ud[k] = ld_stream16(dout + off);
+          ua[k] = ld_stream16(a2 + off);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (pix + k * rows_pp >= p1) break;
+        float d[8], a[8];
+        unpack8(ud[k], d);
+        unpack8(ua[k], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) l[j] = fmaf(d[j], a[j], l[j]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) atomicAdd(&sm[c0 + j], l[j]);
@@ -151,45 +219,9 @@ __global__ void __launch_bounds__(256) se_bwd_reduce_kernel(const bf16* __restri
 }
 
 // gate = sigmoid(W2 relu(W1 mean + b1) + b2), mean = pool_sum / hw.
-// Pass 1 (one block per sample): ds = dgate * g(1-g), dpre = relu'(hid) * (W2^T ds), pool_grad = W1^T dpre / hw; ds and
-// dpre go to a workspace.  Pass 2 (grid over weight elements): dW2 = ds^T hid, dW1 = dpre^T mean, db = column sums —
-// a batch-contraction without atomics.
-__global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restrict__ dgate_sum,
-                                                          const float* __restrict__ gate,
-                                                          const float* __restrict__ hidden, float inv_hw,
-                                                          const float* __restrict__ w1, const float* __restrict__ w2,
-                                                          float* __restrict__ ds_out, float* __restrict__ dpre_out,
-                                                          float* __restrict__ pool_grad, int C, int R) {
-  extern __shared__ float sm[];
-  float* ds = sm;        // C
-  float* dpre = sm + C;  // R
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float g = gate[static_cast<long long>(b) * C + c];
-    const float v = dgate_sum[static_cast<long long>(b) * C + c] * g * (1.f - g);
-    ds[c] = v;
-    ds_out[static_cast<long long>(b) * C + c] = v;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int r = warp; r < R; r += nw) {
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(ds[c], w2[static_cast<long long>(c) * R + r], a);
-    a = warp_sum(a);
-    if (lane == 0) {
-      const float v = hidden[static_cast<long long>(b) * R + r] > 0.f ? a : 0.f;
-      dpre[r] = v;
-      dpre_out[static_cast<long long>(b) * R + r] = v;
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    for (int r = 0; r < R; ++r) a = fmaf(dpre[r], w1[static_cast<long long>(r) * C + c], a);
-    pool_grad[static_cast<long long>(b) * C + c] = a * inv_hw;
-  }
-}
-
+// Passes 1-2 (se_kernels.cuh): ds = dgate * g(1-g), dpre = relu'(hid) * (W2^T ds), pool_grad = W1^T dpre / hw.
+// Pass 3 (grid over weight elements): dW2 = ds^T hid, dW1 = dpre^T mean, db = column sums — a batch-contraction
+// without atomics.
 __global__ void __launch_bounds__(256) se_param_grad_kernel(const float* __restrict__ ds, const float* __restrict__ dpre,
                                                             const float* __restrict__ hidden,
                                                             const float* __restrict__ pool_sum, float inv_hw,
@@ -265,6 +297,82 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const void* __restrict__ d
   if (dbias) {
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sm[i]);
+  }
+}
+
+// 8-channel-vector variant for the common case (NHWC, C % 8 == 0, no channel padding): a thread owns one 8-channel
+// group of a slab of <= 256 groups and walks rows, bias sums stay in registers until the end.
+// DY_F32: dy is fp32 (layout 2) instead of bf16.
+template <bool DY_F32>
+__global__ void __launch_bounds__(256) act_bwd_vec_kernel(const void* __restrict__ dy, const bf16* __restrict__ y, int act,
+                                                          int act_n_limit, float dy_scale, bf16* __restrict__ dz,
+                                                          float* __restrict__ dbias, long long npix, int C,
+                                                          int slab_groups, long long pix_per_block) {
+  __shared__ float sm[2048];
+  const int c8n = C / 8;
+  const int g0 = blockIdx.y * slab_groups;
+  const int ng = min(slab_groups, c8n - g0);
+  if (dbias) {
+    for (int i = threadIdx.x; i < ng * 8; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+  }
+  const long long p0 = blockIdx.x * pix_per_block;
+  const long long p1 = min(npix, p0 + pix_per_block);
+  const int rows_pp = blockDim.x / ng;
+  const int cg = threadIdx.x % ng, prow = threadIdx.x / ng;
+  if (prow < rows_pp) {
+    const int c0 = (g0 + cg) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    constexpr int U = 2;
+    for (long long pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+      uint4 ud[U][DY_F32 ? 2 : 1], uy[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const long long px = pix + k * rows_pp;
+        if (px < p1) {
+          const long long off = px * C + c0;
+          if (DY_F32) {
+            ud[k][0] = ld_stream16(static_cast<const float*>(dy) + off);
+            ud[k][DY_F32 ? 1 : 0] = ld_stream16(static_cast<const float*>(dy) + off + 4);
+          } else {
+            ud[k][0] = ld_stream16(static_cast<const bf16*>(dy) + off);
+          }
+          if (y) uy[k] = ld_stream16(y + off);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const long long px = pix + k * rows_pp;
+        if (px >= p1) break;
+        float d[8], yy[8];
+        if (DY_F32) {
+          const uint4 a = ud[k][0], b = ud[k][DY_F32 ? 1 : 0];
+          d[0] = __uint_as_float(a.x); d[1] = __uint_as_float(a.y); d[2] = __uint_as_float(a.z); d[3] = __uint_as_float(a.w);
+          d[4] = __uint_as_float(b.x); d[5] = __uint_as_float(b.y); d[6] = __uint_as_float(b.z); d[7] = __uint_as_float(b.w);
+        } else {
+          unpack8(ud[k][0], d);
+        }
+        if (y) unpack8(uy[k], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = d[j] * dy_scale;
+          const int a = (act_n_limit == 0 || c0 + j < act_n_limit) ? act : ACT_NONE;
+          if (a == ACT_RELU) v = yy[j] > 0.f ? v : 0.f;
+          else if (a == ACT_SIGMOID) v = v * yy[j] * (1.f - yy[j]);
+          d[j] = v;
+          acc[j] += v;
+        }
+        if (dz) store8(dz + px * C + c0, d);
+      }
+    }
+    if (dbias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sm[cg * 8 + j], acc[j]);
+    }
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < ng * 8; i += blockDim.x) atomicAdd(dbias + g0 * 8 + i, sm[i]);
   }
 }
 
@@ -528,7 +636,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 #define STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
 
 static void chunking(int batch, int hw, int* chunks, int* pix_per_block) {
-  int ch = ceil_div(TFPP_NUM_SMS * 4, batch);
+  int ch = TFPP_NUM_SMS * 6 / batch;  // two full waves of three resident CTAs per SM
+  if (ch < 1) ch = 1;
   int ppb = ceil_div(hw, ch);
   if (ppb < 8) ppb = 8;
   *chunks = ceil_div(hw, ppb);
@@ -547,11 +656,10 @@ extern "C" int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const
       static_cast<const bf16*>(dy), static_cast<const bf16*>(y), static_cast<const bf16*>(raw), mean, invstd, gate,
       pool_grad, act, s1, s2, hw, channels, ppb);
   TFPP_CHECK_LAUNCH();
-  const long long total8 = static_cast<long long>(batch) * hw * channels / 8;
-  bn_bwd_apply_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, stream>>>(
+  bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(
       static_cast<const bf16*>(dy), static_cast<const bf16*>(y), static_cast<const bf16*>(raw), mean, invstd, gamma, s1,
       s2, gate, pool_grad, act, 1.f / (static_cast<float>(batch) * hw), static_cast<bf16*>(draw),
-      static_cast<bf16*>(dz_out), total8, hw, channels);
+      static_cast<bf16*>(dz_out), hw, channels, ppb);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }
@@ -569,11 +677,15 @@ extern "C" int tfpp_se_bwd(const void* dout, const void* a2, const float* gate, 
                                                                         static_cast<const bf16*>(a2), dgate_sum, hw,
                                                                         channels, ppb);
   TFPP_CHECK_LAUNCH();
-  // workspace for ds (B,C) and dpre (B,rd): dgate_sum is (B,C) and consumed in place; dpre lives behind pool_grad
-  float* ds_ws = dgate_sum;  // overwritten with ds by pass 1 (each element read then written by the same thread)
-  float* dpre_ws = ws;
-  se_gate_bwd_kernel<<<batch, 256, sizeof(float) * (channels + rd), stream>>>(dgate_sum, gate, hidden, 1.f / hw, w1, w2,
-                                                                              ds_ws, dpre_ws, pool_grad, channels, rd);
+  // workspace: ds (B,C) then dpre (B,rd)
+  float* ds_ws = ws;
+  float* dpre_ws = ws + static_cast<long long>(batch) * channels;
+  TFPP_CHECK_ARG(rd <= 2048, "rd <= 2048");
+  se_contract_c_kernel<SE_BWD><<<dim3(ceil_div(rd, 8), ceil_div(batch, 8)), 256, 0, stream>>>(
+      dgate_sum, gate, 1.f, w2, 1, rd, nullptr, hidden, dpre_ws, ds_ws, batch, channels, rd);
+  TFPP_CHECK_LAUNCH();
+  se_contract_r_kernel<SE_BWD><<<dim3(ceil_div(channels, 128), ceil_div(batch, 8)), 128, sizeof(float) * rd * 8, stream>>>(
+      dpre_ws, w1, 1, channels, nullptr, 1.f / hw, pool_grad, batch, channels, rd);
   TFPP_CHECK_LAUNCH();
   se_param_grad_kernel<<<ceil_div(channels * rd, 256), 256, 0, stream>>>(ds_ws, dpre_ws, hidden, pool_sum, 1.f / hw, dw1,
                                                                          db1, dw2, db2, batch, channels, rd);
@@ -586,6 +698,26 @@ extern "C" int tfpp_act_bwd(const void* dy, const void* y, int nchw_f32, int act
                             tfpp_stream_t stream_) {
   STREAM;
   const long long npix = static_cast<long long>(batch) * hw;
+  if (nchw_f32 != 1 && channels % 8 == 0 && channels_padded == channels) {
+    const int c8n = channels / 8;
+    const int nslabs = ceil_div(c8n, 256);
+    const int slab_groups = ceil_div(c8n, nslabs);
+    long long chunks = TFPP_NUM_SMS * 6 / nslabs;
+    if (chunks < 1) chunks = 1;
+    long long ppb = ceil_div_ll(npix, chunks);
+    if (ppb < 8) ppb = 8;
+    chunks = ceil_div_ll(npix, ppb);
+    dim3 grid(static_cast<unsigned>(chunks), nslabs);
+    if (nchw_f32 == 2)
+      act_bwd_vec_kernel<true><<<grid, 256, 0, stream>>>(dy, static_cast<const bf16*>(y), act, act_n_limit, dy_scale,
+                                                         static_cast<bf16*>(dz), dbias, npix, channels, slab_groups, ppb);
+    else
+      act_bwd_vec_kernel<false><<<grid, 256, 0, stream>>>(dy, static_cast<const bf16*>(y), act, act_n_limit, dy_scale,
+                                                          static_cast<bf16*>(dz), dbias, npix, channels, slab_groups,
+                                                          ppb);
+    TFPP_CHECK_LAUNCH();
+    return TFPP_OK;
+  }
   long long blocks = ceil_div_ll(npix * channels_padded, 256 * 4);
   if (blocks > TFPP_NUM_SMS * 8) blocks = TFPP_NUM_SMS * 8;
   if (blocks < 1) blocks = 1;

@@ -15,92 +15,202 @@ _PACK_CACHE = {}
 PARAM_EPOCH = [0]  # bumped by the fused optimizer (it updates parameter storage without touching version counters)
 
 
+# kinds whose pack is a pure gather (+ zero padding) of parameter elements: eligible for the one-kernel PackPlan
+_GATHER_KINDS = frozenset(('conv', 'gconv', 'linear', 'conv_t', 'conv_rows_pad', 'conv_dgrad_smallc', 'gconv_t', 'linear_t',
+                           'rows_t', 'cat_linear_t', 'cat_conv_t', 'blockdiag_1x1_t', 'rows', 'rows_f32', 'cat_linear',
+                           'cat_rows', 'cat_rows_f32', 'cat_f32', 'cat_conv', 'blockdiag_1x1', 'repeat_rows'))
+
+
+def _build_pack(kind, params, extra, dtb=BF16, dtf=F32):
+  """The kernel-layout tensor(s) of one pack.  dtb / dtf are the element types of the bf16 / fp32 results; PackPlan
+  calls this a second time with float64 'index tensors' to learn where every packed element comes from."""
+  if kind == 'conv':  # (Cout,Cin,kh,kw) -> (Cout, kh*kw, Cin) bf16
+    return ops.pack_conv_weight(params[0], dt=dtb)
+  if kind == 'gconv':
+    return ops.pack_grouped_conv_weight(params[0], dt=dtb)
+  if kind == 'linear':
+    return params[0].detach().reshape(params[0].shape[0], -1).to(dtb).contiguous()
+  if kind == 'conv_t':  # dgrad operand (Cin, taps, Cout padded to a multiple of 8)
+    w = ops.pack_conv_weight_t(params[0], dt=dtb)
+    pad = (-w.shape[2]) % 8
+    return torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
+  if kind == 'conv_rows_pad':  # (Cout,Cin,3,3) -> (Cout padded to extra[0], 9, Cin) bf16
+    w = ops.pack_conv_weight(params[0], dt=dtb)
+    return torch.nn.functional.pad(w, (0, 0, 0, 0, 0, extra[0] - w.shape[0])).contiguous()
+  if kind == 'conv_dgrad_smallc':  # (Cout,Cin,3,3) -> (Cin, 9 flipped taps, Cout padded to extra[0]) bf16
+    w = params[0].detach().flip(2, 3).permute(1, 2, 3, 0).reshape(params[0].shape[1], 9, params[0].shape[0])
+    return torch.nn.functional.pad(w, (0, extra[0] - w.shape[2])).to(dtb).contiguous()
+  if kind == 'gconv_t':
+    return ops.pack_grouped_conv_weight_t(params[0], dt=dtb)
+  if kind == 'linear_t':  # (N,K) -> (K, N padded to 8)
+    w = params[0].detach().reshape(params[0].shape[0], -1).t().to(dtb).contiguous()
+    pad = (-w.shape[1]) % 8
+    return torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
+  if kind == 'rows_t':
+    return params[0].detach()[extra[0]:extra[1]].t().to(dtb).contiguous()
+  if kind == 'cat_linear_t':
+    return torch.cat([p.detach().reshape(p.shape[0], -1) for p in params], dim=0).t().to(dtb).contiguous()
+  if kind == 'cat_conv_t':  # several convs stacked along Cout -> (Cin, taps, sum Cout)
+    return torch.cat([ops.pack_conv_weight_t(p, dt=dtb) for p in params], dim=2).contiguous()
+  if kind == 'blockdiag_1x1_t':  # transpose of blockdiag_1x1: (sum K_i, 1, sum N_i padded to 8)
+    n = sum(p.shape[0] for p in params)
+    k = sum(p.shape[1] for p in params)
+    npad = n + ((-n) % 8)
+    out = torch.zeros((k, 1, npad), dtype=params[0].dtype, device=params[0].device)
+    r = c = 0
+    for p in params:
+      out[c:c + p.shape[1], 0, r:r + p.shape[0]] = p.detach().reshape(p.shape[0], p.shape[1]).t()
+      r += p.shape[0]
+      c += p.shape[1]
+    return out.to(dtb).contiguous()
+  if kind == 'rows':  # row slice of a (N,K) matrix
+    return params[0].detach()[extra[0]:extra[1]].to(dtb).contiguous()
+  if kind == 'rows_f32':
+    return params[0].detach()[extra[0]:extra[1]].to(dtf).contiguous()
+  if kind == 'cat_linear':
+    return torch.cat([p.detach().reshape(p.shape[0], -1) for p in params], dim=0).to(dtb).contiguous()
+  if kind == 'cat_rows':  # rows [r0,r1) of several matrices stacked
+    return torch.cat([p.detach()[extra[0]:extra[1]] for p in params], dim=0).to(dtb).contiguous()
+  if kind == 'cat_rows_f32':
+    return torch.cat([p.detach()[extra[0]:extra[1]] for p in params], dim=0).to(dtf).contiguous()
+  if kind == 'cat_f32':
+    return torch.cat([p.detach().reshape(-1) for p in params], dim=0).to(dtf).contiguous()
+  if kind == 'cat_conv':
+    return torch.cat([ops.pack_conv_weight(p, dt=dtb) for p in params], dim=0).contiguous()
+  if kind == 'blockdiag_1x1':
+    n = sum(p.shape[0] for p in params)
+    k = sum(p.shape[1] for p in params)
+    out = torch.zeros((n, 1, k), dtype=params[0].dtype, device=params[0].device)
+    r = c = 0
+    for p in params:
+      out[r:r + p.shape[0], 0, c:c + p.shape[1]] = p.detach().reshape(p.shape[0], p.shape[1])
+      r += p.shape[0]
+      c += p.shape[1]
+    return out.to(dtb).contiguous()
+  if kind == 'bn_eval':  # (gamma, beta, running_mean, running_var) -> folded (scale, shift)
+    g, b, m, v = (p.detach().float() for p in params)
+    scale = g * torch.rsqrt(v + extra[0])
+    return (scale.contiguous(), (b - m * scale).contiguous())
+  if kind == 'f32':
+    return params[0].detach().float().contiguous()
+  if kind == 'host_floats':  # one device->host read, cached until the buffers change
+    return tuple(float(p.detach().reshape(-1)[0]) for p in params)
+  if kind == 'repeat_rows':  # (1, T, C) parameter repeated over the batch: f32 and bf16 copies
+    t = params[0].detach().to(dtf).reshape(-1, params[0].shape[-1]).repeat(extra[0], 1).contiguous()
+    return (t, t.to(dtb))
+  raise ValueError(kind)
+
+
+class PackPlan:
+  """All gather-type weight packs of a training step as ONE kernel.
+
+  The parameters of a Trainer live in one flat fp32 buffer (training.FlatState).  The first (eager) step builds every
+  pack with torch ops as usual and, next to it, an int32 map 'packed element -> flat parameter index' (-1 = zero
+  padding), obtained by running the same pack code on index tensors.  finalize() concatenates the maps; from then on
+  packed() hands out fixed views of one bf16 (and one fp32) buffer, and refresh() — one tfpp_gather_pack launch per
+  buffer, called right after the optimizer — rewrites all of them.  That replaces ~2000 small cast / permute / pad
+  kernels per step and gives the CUDA graph static weight addresses."""
+
+  ALIGN = 128  # elements; keeps every region 256-byte aligned for TMA descriptors
+
+  def __init__(self, flat):
+    self.flat = flat
+    self.lo = flat.data_ptr()
+    self.hi = self.lo + flat.numel() * 4
+    self.views = {}     # key -> (versions, out structure of views, params, kind, extra)
+    self.pending = {}   # key -> (params, [(idx int32 tensor, like tensor), ...], is_tuple)
+    self.segments = []  # (idx_all, out_all, is_f32)
+
+  def offset_of(self, p):
+    ptr = p.data_ptr()
+    if p.dtype != F32 or not p.is_contiguous() or ptr < self.lo or ptr + p.numel() * 4 > self.hi:
+      return None
+    return (ptr - self.lo) // 4
+
+  def lookup(self, key, params):
+    hit = self.views.get(key)
+    if hit is None:
+      return None
+    ver = tuple(p._version for p in params)  # pylint: disable=protected-access
+    if hit[0] != ver:  # somebody wrote the parameters with torch ops (load_state_dict, tests): re-gather everything
+      self.refresh()
+      self.views[key] = (ver,) + hit[1:]
+    return hit[1]
+
+  def register(self, key, kind, params, extra, out):
+    if kind not in _GATHER_KINDS or key in self.pending:
+      return
+    offs = [self.offset_of(p) for p in params]
+    if any(o is None for o in offs):
+      return
+    probes = [(torch.arange(p.numel(), dtype=torch.float64, device=p.device) + (o + 1)).view(p.shape)
+              for p, o in zip(params, offs)]
+    idx = _build_pack(kind, probes, extra, dtb=torch.float64, dtf=torch.float64)
+    is_tuple = isinstance(out, tuple)
+    outs = out if is_tuple else (out,)
+    idxs = idx if is_tuple else (idx,)
+    items = []
+    for o, i in zip(outs, idxs):
+      assert o.shape == i.shape and o.dtype in (BF16, F32)
+      items.append(((i.reshape(-1) - 1).to(torch.int32), o))
+    self.pending[key] = (tuple(params), items, is_tuple, kind, extra)
+
+  def finalize(self):
+    """Move every pack registered since the last call into plan-owned storage."""
+    if not self.pending:
+      return
+    dev = self.flat.device
+    for is_f32 in (False, True):
+      dt = F32 if is_f32 else BF16
+      total = 0
+      places = []
+      for key, (_, items, _, _, _) in self.pending.items():
+        for j, (idx, like) in enumerate(items):
+          if like.dtype == dt:
+            places.append((key, j, total, idx, like))
+            total += -(-idx.numel() // self.ALIGN) * self.ALIGN
+      if not total:
+        continue
+      idx_all = torch.full((total,), -1, dtype=torch.int32, device=dev)
+      out_all = torch.empty((total,), dtype=dt, device=dev)
+      for key, j, off, idx, like in places:
+        idx_all[off:off + idx.numel()] = idx
+        self.pending[key][1][j] = (None, out_all[off:off + idx.numel()].view(like.shape))
+      self.segments.append((idx_all, out_all, is_f32))
+      ops.gather_pack(self.flat, idx_all, out_all)
+    for key, (params, items, is_tuple, kind, extra) in self.pending.items():
+      outs = tuple(v for _, v in items)
+      ver = tuple(p._version for p in params)  # pylint: disable=protected-access
+      self.views[key] = (ver, outs if is_tuple else outs[0], params, kind, extra)
+      _PACK_CACHE.pop(key, None)
+    self.pending = {}
+
+  def refresh(self):
+    for idx_all, out_all, _ in self.segments:
+      ops.gather_pack(self.flat, idx_all, out_all)
+
+
+_PLAN = [None]  # the active PackPlan (set by training.Trainer)
+
+
 def packed(params, kind, *extra):
   """Kernel-layout copy of parameter(s); rebuilt whenever a version counter / storage changes (optimizer step,
-  load_state_dict, .to(device))."""
+  load_state_dict, .to(device)) — or, under a PackPlan, a fixed view that PackPlan.refresh() keeps current."""
   params = params if isinstance(params, (tuple, list)) else (params,)
   key = (kind,) + tuple(id(p) for p in params) + extra
+  plan = _PLAN[0]
+  if plan is not None:
+    hit = plan.lookup(key, params)
+    if hit is not None:
+      return hit
   ver = (PARAM_EPOCH[0],) + tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)  # pylint: disable=protected-access
   hit = _PACK_CACHE.get(key)
   if hit is not None and hit[0] == ver:
     return hit[1]
   with torch.no_grad():
-    if kind == 'conv':  # (Cout,Cin,kh,kw) -> (Cout, kh*kw, Cin) bf16
-      out = ops.pack_conv_weight(params[0])
-    elif kind == 'gconv':
-      out = ops.pack_grouped_conv_weight(params[0])
-    elif kind == 'linear':
-      out = params[0].detach().reshape(params[0].shape[0], -1).to(BF16).contiguous()
-    elif kind == 'conv_t':  # dgrad operand (Cin, taps, Cout padded to a multiple of 8)
-      w = ops.pack_conv_weight_t(params[0])
-      pad = (-w.shape[2]) % 8
-      out = torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
-    elif kind == 'conv_rows_pad':  # (Cout,Cin,3,3) -> (Cout padded to extra[0], 9, Cin) bf16
-      w = ops.pack_conv_weight(params[0])
-      out = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, extra[0] - w.shape[0])).contiguous()
-    elif kind == 'conv_dgrad_smallc':  # (Cout,Cin,3,3) -> (Cin, 9 flipped taps, Cout padded to extra[0]) bf16
-      w = params[0].detach().flip(2, 3).permute(1, 2, 3, 0).reshape(params[0].shape[1], 9, params[0].shape[0])
-      out = torch.nn.functional.pad(w, (0, extra[0] - w.shape[2])).to(BF16).contiguous()
-    elif kind == 'gconv_t':
-      out = ops.pack_grouped_conv_weight_t(params[0])
-    elif kind == 'linear_t':  # (N,K) -> (K, N padded to 8)
-      w = params[0].detach().reshape(params[0].shape[0], -1).t().to(BF16).contiguous()
-      pad = (-w.shape[1]) % 8
-      out = torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
-    elif kind == 'rows_t':
-      out = params[0].detach()[extra[0]:extra[1]].t().to(BF16).contiguous()
-    elif kind == 'cat_linear_t':
-      out = torch.cat([p.detach().reshape(p.shape[0], -1) for p in params], dim=0).t().to(BF16).contiguous()
-    elif kind == 'cat_conv_t':  # several convs stacked along Cout -> (Cin, taps, sum Cout)
-      out = torch.cat([ops.pack_conv_weight_t(p) for p in params], dim=2).contiguous()
-    elif kind == 'blockdiag_1x1_t':  # transpose of blockdiag_1x1: (sum K_i, 1, sum N_i padded to 8)
-      n = sum(p.shape[0] for p in params)
-      k = sum(p.shape[1] for p in params)
-      npad = n + ((-n) % 8)
-      out = torch.zeros((k, 1, npad), dtype=F32, device=params[0].device)
-      r = c = 0
-      for p in params:
-        out[c:c + p.shape[1], 0, r:r + p.shape[0]] = p.detach().reshape(p.shape[0], p.shape[1]).t()
-        r += p.shape[0]
-        c += p.shape[1]
-      out = out.to(BF16).contiguous()
-    elif kind == 'rows':  # row slice of a (N,K) matrix
-      out = params[0].detach()[extra[0]:extra[1]].to(BF16).contiguous()
-    elif kind == 'rows_f32':
-      out = params[0].detach()[extra[0]:extra[1]].float().contiguous()
-    elif kind == 'cat_linear':
-      out = torch.cat([p.detach().reshape(p.shape[0], -1) for p in params], dim=0).to(BF16).contiguous()
-    elif kind == 'cat_rows':  # rows [r0,r1) of several matrices stacked
-      out = torch.cat([p.detach()[extra[0]:extra[1]] for p in params], dim=0).to(BF16).contiguous()
-    elif kind == 'cat_rows_f32':
-      out = torch.cat([p.detach()[extra[0]:extra[1]] for p in params], dim=0).float().contiguous()
-    elif kind == 'cat_f32':
-      out = torch.cat([p.detach().reshape(-1) for p in params], dim=0).float().contiguous()
-    elif kind == 'cat_conv':
-      out = torch.cat([ops.pack_conv_weight(p) for p in params], dim=0).contiguous()
-    elif kind == 'blockdiag_1x1':
-      n = sum(p.shape[0] for p in params)
-      k = sum(p.shape[1] for p in params)
-      out = torch.zeros((n, 1, k), dtype=F32, device=params[0].device)
-      r = c = 0
-      for p in params:
-        out[r:r + p.shape[0], 0, c:c + p.shape[1]] = p.detach().reshape(p.shape[0], p.shape[1])
-        r += p.shape[0]
-        c += p.shape[1]
-      out = out.to(BF16).contiguous()
-    elif kind == 'bn_eval':  # (gamma, beta, running_mean, running_var) -> folded (scale, shift)
-      g, b, m, v = (p.detach().float() for p in params)
-      scale = g * torch.rsqrt(v + extra[0])
-      out = (scale.contiguous(), (b - m * scale).contiguous())
-    elif kind == 'f32':
-      out = params[0].detach().float().contiguous()
-    elif kind == 'host_floats':  # one device->host read, cached until the buffers change
-      out = tuple(float(p.detach().reshape(-1)[0]) for p in params)
-    elif kind == 'repeat_rows':  # (1, T, C) parameter repeated over the batch: f32 and bf16 copies
-      t = params[0].detach().float().reshape(-1, params[0].shape[-1]).repeat(extra[0], 1).contiguous()
-      out = (t, t.to(BF16))
-    else:
-      raise ValueError(kind)
+    out = _build_pack(kind, params, extra)
+    if plan is not None:
+      plan.register(key, kind, params, extra, out)
   _PACK_CACHE[key] = (ver, out)
   return out
 
@@ -148,6 +258,24 @@ class Engine:
     if self.tape is not None:
       self.tape.append(kw)
 
+  def new_arena(self, device, n_floats=6 * 1024 * 1024):
+    """One zero-filled fp32 arena per step for all the small accumulators (BatchNorm statistics, SE squeezes, ...):
+    a single memset instead of ~500 tiny fill kernels."""
+    self._arena = torch.zeros(n_floats, dtype=F32, device=device)
+    self._arena_off = 0
+
+  def zeros(self, shape, device):
+    n = 1
+    for d in shape:
+      n *= d
+    n4 = (n + 3) & ~3
+    arena = getattr(self, '_arena', None)
+    if arena is None or arena.device != device or self._arena_off + n4 > arena.numel():
+      return torch.zeros(shape, dtype=F32, device=device)
+    out = arena[self._arena_off:self._arena_off + n].view(shape)
+    self._arena_off += n4
+    return out
+
   def _tap(self, name, t):
     if self.debug_taps is not None:
       self.debug_taps[name] = t
@@ -162,9 +290,9 @@ class Engine:
     bn = cna.bn
     cout = w.shape[0]
     b = a.shape[0] if batch is None else batch
-    pool = torch.zeros((b, cout), dtype=F32, device=a.device) if want_pool else None
+    pool = self.zeros((b, cout), a.device) if want_pool else None
     if training:
-      stats = torch.zeros((2, cout), dtype=F32, device=a.device)
+      stats = self.zeros((2, cout), a.device)
       raw = ops.conv_gemm(a, w, taps=taps, batch=batch, stats=(stats[0], stats[1]), **gkw)
       count = raw.shape[0] * raw.shape[1] * raw.shape[2]
       scale, shift, mean, invstd = ops.bn_finalize(stats[0], stats[1], bn.weight, bn.bias, bn.running_mean,
@@ -232,7 +360,7 @@ class Engine:
       if training:
         # raw downsample conv + its batch statistics; its BatchNorm affine is applied inside conv3's apply pass
         wd = packed(ds.conv.weight, 'conv')
-        stats = torch.zeros((2, wd.shape[0]), dtype=F32, device=x.device)
+        stats = self.zeros((2, wd.shape[0]), x.device)
         raw_d = ops.conv_gemm(xp, wd, batch=b, stats=(stats[0], stats[1]))
         count = b * ho * wo
         sd, td, mean_d, invstd_d = ops.bn_finalize(stats[0], stats[1], ds.bn.weight, ds.bn.bias, ds.bn.running_mean,
@@ -261,7 +389,7 @@ class Engine:
     w = packed(cna.conv.weight, 'f32')
     bn = cna.bn
     if training:
-      stats = torch.zeros((2, 32), dtype=F32, device=dev)
+      stats = self.zeros((2, 32), dev)
       raw = ops.stem_conv(x, w, in_scale, in_shift, stats=(stats[0], stats[1]))
       count = raw.shape[0] * raw.shape[1] * raw.shape[2]
       scale, shift, mean, invstd = ops.bn_finalize(stats[0], stats[1], bn.weight, bn.bias, bn.running_mean,
@@ -482,6 +610,7 @@ class Engine:
   def forward(self, rgb, lidar_bev, target_point, ego_vel, command, training=False):
     """LidarCenterNet.forward (model.py:279-392)."""
     m, cfg = self.m, self.cfg
+    self.new_arena(rgb.device)
     feats, fused, grid = self.backbone_forward(rgb, lidar_bev, training)
     pred_checkpoint, pred_target_speed = self.planner(fused, target_point.to(rgb.device), ego_vel.to(rgb.device),
                                                       command.to(rgb.device), training)

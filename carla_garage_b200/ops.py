@@ -121,7 +121,13 @@ def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1
   args.batch = b
   args.k_per_tile = kd if k_per_tile is None else k_per_tile
   args.a_c_per_ntile = a_c_per_ntile
-  args.bn = pick_bn(n) if bn is None else bn
+  if bn is None:
+    bn = pick_bn(n)
+    # few pixel tiles (decoder / planner GEMMs, 8x8 maps): narrower N tiles put more CTAs to work
+    m_tiles = -(-wd // tw) * -(-h // th) * -(-b // nb)
+    while bn > 32 and m_tiles * -(-n // bn) < 148 and (bn // 2) % 16 == 0:
+      bn //= 2
+  args.bn = bn
   args.tw, args.th, args.nb = tw, th, nb
   args.ntaps = len(taps)
   for i, (dx, dy, db, tw_) in enumerate(taps):
@@ -289,7 +295,7 @@ def se_gate(pool_sum, hw, w1, b1, w2, b2, want_hidden=False):
   b, c = pool_sum.shape
   rd = w1.shape[0]
   gate = torch.empty((b, c), dtype=F32, device=pool_sum.device)
-  hidden = torch.empty((b, rd), dtype=F32, device=pool_sum.device) if want_hidden else None
+  hidden = torch.empty((b, rd), dtype=F32, device=pool_sum.device)
   check(_lib.load().tfpp_se_gate(pool_sum.data_ptr(), hw, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                                  gate.data_ptr(), _p(hidden), b, c, rd, _stream()), 'tfpp_se_gate')
   return (gate, hidden) if want_hidden else gate
@@ -433,25 +439,31 @@ def decode_heatmap(heat, wh, offset, yaw_cls, yaw_res, k=100, img_h=256, img_w=2
 
 # ---------------------------------------------------------------------------------------------- weight packing
 # (load-time plumbing: layout changes of parameters, no activations involved)
-def pack_conv_weight(w):
+def gather_pack(flat, idx, out):
+  """out[i] = flat[idx[i]] (0 where idx < 0), cast to out's dtype: the PackPlan refresh kernel."""
+  check(_lib.load().tfpp_gather_pack(flat.data_ptr(), idx.data_ptr(), out.data_ptr(), out.numel(), int(out.dtype == F32),
+                                     _stream()), 'tfpp_gather_pack')
+
+
+def pack_conv_weight(w, dt=BF16):
   """(Cout, Cin, kh, kw) f32 -> (Cout, kh*kw, Cin) bf16."""
   co, ci, kh, kw = w.shape
-  return w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(BF16).contiguous()
+  return w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(dt).contiguous()
 
 
-def pack_grouped_conv_weight(w, group_width=24, groups_per_tile=2):
+def pack_grouped_conv_weight(w, group_width=24, groups_per_tile=2, dt=BF16):
   """(Cout, gw, 3, 3) f32 grouped conv -> (Cout, 9, 64) bf16, dense within each 48-channel n-tile: column j of row n
   multiplies input channel (n // 48) * 48 + j; zero outside the row's own group."""
   co, gw, kh, kw = w.shape
   assert gw == group_width and kh == 3 and kw == 3
   tile = group_width * groups_per_tile
-  out = torch.zeros((co, 9, 64), dtype=F32, device=w.device)
+  out = torch.zeros((co, 9, 64), dtype=w.dtype, device=w.device)
   wt = w.detach().permute(0, 2, 3, 1).reshape(co, 9, gw)
   n = torch.arange(co, device=w.device)
   base = ((n % tile) // gw) * gw  # column offset of the row's group inside its tile
   idx = base[:, None] + torch.arange(gw, device=w.device)[None, :]
   out.scatter_(2, idx[:, None, :].expand(co, 9, gw), wt)
-  return out.to(BF16).contiguous()
+  return out.to(dt).contiguous()
 
 
 # ---------------------------------------------------------------------------------------------- backward wrappers
@@ -466,18 +478,18 @@ def taps_dgrad_stride2(py, px):
   return tuple((dx, dy, 0, ky * 3 + kx) for ky, dy in ys for kx, dx in xs)
 
 
-def pack_conv_weight_t(w):
+def pack_conv_weight_t(w, dt=BF16):
   """(Cout, Cin, kh, kw) f32 -> (Cin, kh*kw, Cout) bf16 (dgrad operand; taps not flipped, see TAPS_3X3_DGRAD)."""
   co, ci, kh, kw = w.shape
-  return w.detach().permute(1, 2, 3, 0).reshape(ci, kh * kw, co).to(BF16).contiguous()
+  return w.detach().permute(1, 2, 3, 0).reshape(ci, kh * kw, co).to(dt).contiguous()
 
 
-def pack_grouped_conv_weight_t(w, group_width=24):
+def pack_grouped_conv_weight_t(w, group_width=24, dt=BF16):
   """Grouped (Cout, gw, 3, 3) -> dgrad pack (C, 9, 64): in/out swapped inside each group."""
   co, gw, kh, kw = w.shape
   g = co // gw
   wt = w.detach().view(g, gw, gw, kh, kw).permute(0, 2, 1, 3, 4).reshape(co, gw, kh, kw)
-  return pack_grouped_conv_weight(wt, group_width)
+  return pack_grouped_conv_weight(wt, group_width, dt=dt)
 
 
 def bn_bwd(dy, y, raw, mean, invstd, gamma, act, dgamma, dbeta, gate=None, pool_grad=None, want_dz=False):
@@ -490,12 +502,12 @@ def bn_bwd(dy, y, raw, mean, invstd, gamma, act, dgamma, dbeta, gate=None, pool_
   return draw, dz
 
 
-def se_bwd(dout, a2, gate, hidden, pool_sum, hw, w1, w2, dw1, db1, dw2, db2):
+def se_bwd(dout, a2, gate, hidden, pool_sum, hw, w1, w2, dw1, db1, dw2, db2, zeros=None):
   b, c = gate.shape
   rd = w1.shape[0]
-  dgate = torch.zeros((b, c), dtype=F32, device=gate.device)
+  dgate = zeros((b, c), gate.device) if zeros else torch.zeros((b, c), dtype=F32, device=gate.device)
   pool_grad = torch.empty((b, c), dtype=F32, device=gate.device)
-  ws = torch.empty((b, rd), dtype=F32, device=gate.device)
+  ws = torch.empty((b, c + rd), dtype=F32, device=gate.device)
   check(_lib.load().tfpp_se_bwd(dout.data_ptr(), a2.data_ptr(), gate.data_ptr(), hidden.data_ptr(), pool_sum.data_ptr(),
                                 hw, w1.data_ptr(), w2.data_ptr(), dgate.data_ptr(), ws.data_ptr(), dw1.data_ptr(),
                                 db1.data_ptr(),

@@ -115,7 +115,7 @@ def compute_losses(eng, st, outputs, labels, weights):
   _, pred_ts, pred_cp, pred_sem, pred_bev, pred_depth, bb = outputs[:7]
   dev = pred_ts.device
   b = pred_ts.shape[0]
-  sums = torch.zeros(16, dtype=F32, device=dev)
+  sums = eng.zeros((16,), dev)
   stream = ops._stream()  # pylint: disable=protected-access
   seeds = {}
   losses = {}
@@ -335,7 +335,8 @@ class Backward:
     se = r['se']
     da2s = self.G.pop(id(r['a2s']))
     pool_grad = ops.se_bwd(da2s, r['a2'], r['gate'], r['hidden'], r['pool'], r['hw'], se.fc1.weight, se.fc2.weight,
-                           st.g(se.fc1.weight), st.g(se.fc1.bias), st.g(se.fc2.weight), st.g(se.fc2.bias))
+                           st.g(se.fc1.weight), st.g(se.fc1.bias), st.g(se.fc2.weight), st.g(se.fc2.bias),
+                           zeros=self.eng.zeros)
     self.pending[id(r['a2'])] = (r['gate'], pool_grad)
     self.G[id(r['a2'])] = da2s
 
@@ -655,6 +656,7 @@ class Trainer:
     self.pg = process_group
     self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
     self.bucket_elems = bucket_mb * 1024 * 1024 // 4
+    self.plan = eng_mod.PackPlan(self.st.flat) if self.st.flat.is_cuda else None
 
   def forward_backward(self, inputs, labels):
     eng, st = self.eng, self.st
@@ -677,9 +679,18 @@ class Trainer:
     allreduce_flat(self.st.grad, self.pg, self.bucket_elems)
 
   def step(self, inputs, labels, lr='default'):
-    out, losses = self.forward_backward(inputs, labels)
-    self.allreduce()
-    self.st.adamw_step(self.lr if lr == 'default' else lr, weight_decay=self.wd, grad_scale=1.0 / self.world)
+    prev_plan = eng_mod._PLAN[0]  # pylint: disable=protected-access
+    eng_mod._PLAN[0] = self.plan  # pylint: disable=protected-access
+    try:
+      out, losses = self.forward_backward(inputs, labels)
+      self.allreduce()
+      self.st.adamw_step(self.lr if lr == 'default' else lr, weight_decay=self.wd, grad_scale=1.0 / self.world)
+      if self.plan is not None:
+        self.plan.refresh()  # one gather kernel: every bf16 weight pack follows the new parameters
+        if not torch.cuda.is_current_stream_capturing():
+          self.plan.finalize()  # adopt the packs first seen in this (eager) step
+    finally:
+      eng_mod._PLAN[0] = prev_plan  # pylint: disable=protected-access
     return out, losses
 
   # ---- CUDA-graph replay of the whole step (removes ~4000 Python-issued launches per step from the critical path)
@@ -705,7 +716,8 @@ class Trainer:
     from . import _lib  # pylint: disable=import-outside-toplevel
     _lib.reset_launch_count()
     self.graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(self.graph):
+    # with NCCL inside the capture its watchdog thread keeps polling events: only this thread's calls are checked
+    with torch.cuda.graph(self.graph, capture_error_mode='thread_local' if self.world > 1 else 'global'):
       out, losses = body()
       self._gloss = torch.stack([losses[k] for k in LOSS_KEYS])
     self._gout = out

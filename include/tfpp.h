@@ -131,7 +131,8 @@ int tfpp_scale_shift_act(const void* x, const void* res, const float* scale, con
                          const float* res_shift, int act, void* y, float* pool_sum, int batch, int hw, int channels,
                          tfpp_stream_t stream);
 
-/* timm SEModule excite: gate = sigmoid(fc2(relu(fc1(pool_sum / hw)))); w1 (rd,C), w2 (C,rd) f32. */
+/* timm SEModule excite: gate = sigmoid(fc2(relu(fc1(pool_sum / hw)))); w1 (rd,C), w2 (C,rd) f32.
+ * hidden (B,rd) f32 is required: it carries relu(fc1) between the two passes and is what the backward reads. */
 int tfpp_se_gate(const float* pool_sum, int hw, const float* w1, const float* b1, const float* w2, const float* b2,
                  float* gate, float* hidden, int batch, int channels, int rd, tfpp_stream_t stream);
 
@@ -204,7 +205,7 @@ int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const float* mea
                 void* dz_out, int batch, int hw, int channels, tfpp_stream_t stream);
 
 /* SE backward: dout = grad wrt (a2 * gate); outputs pool_grad (B,C) = dL/d(pool_sum) and fc1/fc2 gradients (+=).
- * dgate_sum (B,C) f32 zeroed by the caller and ws (B,rd) f32 are workspaces. */
+ * dgate_sum (B,C) f32 zeroed by the caller and ws (B,C+rd) f32 are workspaces. */
 int tfpp_se_bwd(const void* dout, const void* a2, const float* gate, const float* hidden, const float* pool_sum, int hw,
                 const float* w1, const float* w2, float* dgate_sum, float* ws, float* dw1, float* db1, float* dw2,
                 float* db2, float* pool_grad, int batch, int channels, int rd, tfpp_stream_t stream);
@@ -274,6 +275,11 @@ int tfpp_center_head_loss(const float* maps, const float* t_heat, const float* t
 int tfpp_planner_loss(const float* logits, const long long* labels, const float* class_w, const float* cp,
                       const float* cp_t, float w_ts, float w_cp, float* losses, float* dlogits, float* dcp, int batch,
                       int n_cls, int n_cp, tfpp_stream_t stream);
+
+/* Weight-pack refresh: out[i] = idx[i] >= 0 ? flat[idx[i]] : 0 for i < n (n % 8 == 0), cast to bf16 (out_f32 = 0) or
+ * kept fp32.  One launch rebuilds every kernel-layout weight copy after the optimizer step; replaces the implicit
+ * per-module weight reads of torch's conv / linear kernels (team_code/train.py:898-908 loop). */
+int tfpp_gather_pack(const float* flat, const int* idx, void* out, long long n, int out_f32, tfpp_stream_t stream);
 
 /* AdamW(amsgrad=True), torch semantics; grad_scale multiplies the gradient first (1/world_size after a sum
  * all-reduce).  dev_state (optional, 2 floats on the device: [step count, learning rate]) replaces the host-side

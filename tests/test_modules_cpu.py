@@ -85,3 +85,47 @@ def test_config_defaults_match_reference():
   for k, v in vars(mine).items():
     assert hasattr(ref, k), k
     assert getattr(ref, k) == v, (k, getattr(ref, k), v)
+
+
+def test_pack_plan_index_maps_reproduce_every_gather_pack():
+  """engine.PackPlan learns 'packed element -> flat parameter index' by running the pack code on index tensors; a
+  plain gather through that map must reproduce the torch-built pack bit for bit (host logic of tfpp_gather_pack)."""
+  import torch
+  from carla_garage_b200 import engine as E
+  g = torch.Generator().manual_seed(0)
+  shapes = {'conv': (48, 16, 3, 3), 'gconv': (96, 24, 3, 3), 'lin_a': (40, 24), 'lin_b': (16, 24), 'c1': (24, 8, 1, 1),
+            'c2': (12, 16, 1, 1), 'pos': (1, 5, 24), 'vec': (40,)}
+  total = sum(int(torch.tensor(s).prod()) for s in shapes.values())
+  flat = torch.randn(total, generator=g)
+  params, off = {}, 0
+  for k, s in shapes.items():
+    n = int(torch.tensor(s).prod())
+    params[k] = flat[off:off + n].view(s)
+    off += n
+  plan = E.PackPlan(flat)
+  cases = [('conv', (params['conv'],), ()), ('conv_t', (params['conv'],), ()), ('conv_rows_pad', (params['conv'],), (64,)),
+           ('conv_dgrad_smallc', (params['conv'],), (64,)), ('gconv', (params['gconv'],), ()),
+           ('gconv_t', (params['gconv'],), ()), ('linear', (params['lin_a'],), ()), ('linear_t', (params['lin_a'],), ()),
+           ('rows', (params['lin_a'],), (8, 24)), ('rows_t', (params['lin_a'],), (8, 24)),
+           ('rows_f32', (params['lin_a'],), (8, 24)), ('cat_linear', (params['lin_a'], params['lin_b']), ()),
+           ('cat_linear_t', (params['lin_a'], params['lin_b']), ()), ('cat_rows', (params['lin_a'], params['lin_b']), (0, 8)),
+           ('cat_rows_f32', (params['lin_a'], params['lin_b']), (0, 8)), ('cat_f32', (params['vec'], params['lin_b']), ()),
+           ('cat_conv', (params['c1'], params['c1']), ()), ('cat_conv_t', (params['c1'], params['c1']), ()),
+           ('blockdiag_1x1', (params['c1'], params['c2']), ()), ('blockdiag_1x1_t', (params['c1'], params['c2']), ()),
+           ('repeat_rows', (params['pos'],), (3,))]
+  assert {c[0] for c in cases} == set(E._GATHER_KINDS)  # pylint: disable=protected-access
+  for kind, ps, extra in cases:
+    out = E._build_pack(kind, ps, extra)  # pylint: disable=protected-access
+    key = (kind,) + tuple(id(p) for p in ps) + extra
+    plan.register(key, kind, ps, extra, out)
+    assert key in plan.pending, kind
+    _, items, is_tuple, _, _ = plan.pending[key]
+    assert is_tuple == isinstance(out, tuple)
+    for idx, like in items:
+      idx = idx.long()
+      got = torch.where(idx >= 0, flat[idx.clamp(min=0)], torch.zeros(())).to(like.dtype).view(like.shape)
+      assert torch.equal(got, like), kind
+  # a tensor outside the flat buffer is left to the ordinary cache
+  other = torch.randn(8, 8)
+  plan.register(('linear', id(other)), 'linear', (other,), (), E._build_pack('linear', (other,), ()))  # pylint: disable=protected-access
+  assert ('linear', id(other)) not in plan.pending

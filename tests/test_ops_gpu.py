@@ -232,17 +232,21 @@ def test_planner_kernels(ops):
   vn = (vel - vel.mean()) / torch.sqrt(vel.var(unbiased=False) + 1e-5)
   want = F.relu(F.relu(torch.cat([vn, cmd], 1) @ w0.t() + b0) @ w1.t() + b1) + pos
   assert rel(mem_f[:, 64], want) < 1e-5
-  # GRU + target speed vs torch.nn.GRU
-  gru = torch.nn.GRU(256, 64, batch_first=True).cuda()
-  enc, dec = torch.nn.Linear(2, 64).cuda(), torch.nn.Linear(64, 2).cuda()
-  ts = torch.nn.Sequential(torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 4)).cuda()
+  # GRU + target speed vs torch.nn.GRU, evaluated on the CPU in float64 (cuDNN's GRU would run TF32 matmuls)
+  torch.manual_seed(1234)
+  gru = torch.nn.GRU(256, 64, batch_first=True).double()
+  enc, dec = torch.nn.Linear(2, 64).double(), torch.nn.Linear(64, 2).double()
+  ts = torch.nn.Sequential(torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 4)).double()
   joined, tp = rnd(b, 11, 256, seed=37), rnd(b, 2, seed=38) * 10
   with torch.no_grad():
-    o, _ = gru(joined[:, :10], enc(tp).unsqueeze(0))
+    jc, tc = joined.double().cpu(), tp.double().cpu()
+    o, _ = gru(jc[:, :10], enc(tc).unsqueeze(0))
     want_cp = torch.cumsum(dec(o), 1)
-    want_ts = ts(joined[:, 10])
-  cp, tsl = ops.planner_head(joined, tp, enc.weight, enc.bias, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0,
-                             gru.bias_hh_l0, dec.weight, dec.bias, ts[0].weight, ts[0].bias, ts[2].weight, ts[2].bias)
+    want_ts = ts(jc[:, 10])
+  f = lambda t: t.detach().float().cuda()
+  cp, tsl = ops.planner_head(joined, tp, f(enc.weight), f(enc.bias), f(gru.weight_ih_l0), f(gru.weight_hh_l0),
+                             f(gru.bias_ih_l0), f(gru.bias_hh_l0), f(dec.weight), f(dec.bias), f(ts[0].weight),
+                             f(ts[0].bias), f(ts[2].weight), f(ts[2].bias))
   assert rel(cp, want_cp) < 1e-4 and rel(tsl, want_ts) < 1e-4
 
 
@@ -338,3 +342,81 @@ def test_smallc_wgrad_and_dgrad(ops, cop, co_valid, h, w):
   y2 = F.conv2d(xin, bf(wr).float(), None, padding=1)
   gx, = torch.autograd.grad(y2, xin, dy.float()[..., :co_valid].permute(0, 3, 1, 2))
   assert rel(got.float().permute(0, 3, 1, 2), gx) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------ feature-map adjoints
+@pytest.mark.parametrize('b,h,w,c,act,with_se', [(3, 9, 13, 72, 1, True), (2, 8, 8, 1512, 1, False), (2, 17, 5, 216, 0, False),
+                                                (5, 4, 4, 576, 1, True)])
+def test_bn_backward(ops, b, h, w, c, act, with_se):
+  """tfpp_bn_bwd (two passes) against autograd of batch_norm(+relu)(*gate, +pool) on the same bf16 tensors."""
+  raw = bf(rnd(b, h, w, c, seed=1, scale=2.0) + 0.5)
+  gamma, beta = rnd(c, seed=2).abs() + 0.5, rnd(c, seed=3) * 0.1
+  dy = bf(rnd(b, h, w, c, seed=4))
+  gate = torch.sigmoid(rnd(b, c, seed=5)) if with_se else None
+  pgrad = rnd(b, c, seed=6) * 0.05 if with_se else None
+  rawf = raw.float().requires_grad_(True)
+  g32, b32 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+  mean = rawf.detach().mean((0, 1, 2))
+  var = rawf.detach().var((0, 1, 2), unbiased=False)
+  invstd = torch.rsqrt(var + 1e-5)
+  z = F.batch_norm(rawf.permute(0, 3, 1, 2), None, None, g32, b32, training=True, eps=1e-5).permute(0, 2, 3, 1)
+  y = F.relu(z) if act else z
+  yb = bf(y.detach())
+  loss = (y * (gate[:, None, None, :] if with_se else 1.0) * dy.float()).sum()
+  if with_se:
+    loss = loss + (y.sum((1, 2)) * pgrad).sum()
+  loss.backward()
+  dgamma, dbeta = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+  draw, dz = ops.bn_bwd(dy, yb if act else None, raw, mean, invstd, gamma, act, dgamma, dbeta, gate=gate, pool_grad=pgrad,
+                        want_dz=True)
+  assert rel(draw.float(), rawf.grad) < 1e-2
+  assert rel(dgamma, g32.grad) < 2e-3 and rel(dbeta, b32.grad) < 2e-3
+  want_dz = dy.float() * (gate[:, None, None, :] if with_se else 1.0) + (pgrad[:, None, None, :] if with_se else 0.0)
+  if act:
+    want_dz = want_dz * (yb.float() > 0)
+  assert rel(dz.float(), want_dz) < 5e-3
+
+
+@pytest.mark.parametrize('b,c,rd,hw', [(5, 1512, 144, 64), (2, 72, 8, 35), (9, 216, 18, 16), (32, 576, 54, 4)])
+def test_se_forward_backward(ops, b, c, rd, hw):
+  """SE excite MLP (two contraction kernels each way) against autograd."""
+  h = w = None
+  for hh in range(1, hw + 1):
+    if hw % hh == 0:
+      h, w = hh, hw // hh
+  a2 = bf(rnd(b, h, w, c, seed=1).abs())
+  dout = bf(rnd(b, h, w, c, seed=2))
+  w1, b1 = rnd(rd, c, seed=3, scale=c ** -0.5), rnd(rd, seed=4, scale=0.1)
+  w2, b2 = rnd(c, rd, seed=5, scale=rd ** -0.5), rnd(c, seed=6, scale=0.1)
+  pool = a2.float().sum((1, 2)).requires_grad_(True)
+  p = [t.clone().requires_grad_(True) for t in (w1, b1, w2, b2)]
+  hid = F.relu((pool / hw) @ p[0].t() + p[1])
+  gate_want = torch.sigmoid(hid @ p[2].t() + p[3])
+  gate, hidden = ops.se_gate(pool.detach(), hw, w1, b1, w2, b2, want_hidden=True)
+  assert rel(gate, gate_want) < 1e-5 and rel(hidden, hid) < 1e-5
+  (a2.float() * gate_want[:, None, None, :] * dout.float()).sum().backward()
+  dws = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
+  pool_grad = ops.se_bwd(dout, a2, gate, hidden, pool.detach(), hw, w1, w2, *dws)
+  assert rel(pool_grad, pool.grad) < 1e-4
+  for got, want in zip(dws, p):
+    assert rel(got, want.grad) < 1e-4
+
+
+@pytest.mark.parametrize('rows,c,layout,act,limit', [(77, 4536, 0, 0, 0), (300, 64, 0, 1, 0), (41, 1512, 2, 0, 0),
+                                                    (130, 24, 0, 2, 16), (64, 20, 0, 1, 0), (50, 576, 2, 1, 0)])
+def test_act_backward(ops, rows, c, layout, act, limit):
+  """tfpp_act_bwd: vector path (C % 8 == 0) and scalar fallback, bf16 / fp32 incoming gradients, bias reduction."""
+  dy32 = rnd(rows, c, seed=1)
+  dy = dy32 if layout == 2 else bf(dy32)
+  y = bf(rnd(rows, c, seed=2)) if act == 1 else bf(torch.sigmoid(rnd(rows, c, seed=2)))
+  dbias = torch.zeros(c, device='cuda')
+  dz = ops.act_bwd(dy, y if act else None, act, 1, rows, c, layout=layout, act_n_limit=limit, dy_scale=0.5, dbias=dbias)
+  want = dy.float() * 0.5
+  if act == 1:
+    want = want * (y.float() > 0)
+  elif act == 2:
+    m = torch.ones(c, device='cuda') if limit == 0 else (torch.arange(c, device='cuda') < limit).float()
+    yf = y.float()
+    want = want * (m * yf * (1 - yf) + (1 - m))
+  assert rel(dz.float(), want) < 4e-3
+  assert rel(dbias, want.sum(0)) < 1e-4

@@ -154,3 +154,44 @@ def test_component_backward_vs_oracle_autograd(trainer, oracle_state, kind):
   report = _block_backward_case(trainer, oracle_state, kind)
   for k, v in report.items():
     assert v < 0.15, (k, v)
+
+
+def test_pack_plan_tracks_the_optimizer(oracle_state):
+  """After a few optimizer steps every plan-owned weight pack (rewritten by the one tfpp_gather_pack launch) must be
+  bit-identical to the pack torch builds from the current parameters; and the CUDA-graph replay must keep them so."""
+  from carla_garage_b200 import engine as E, synth
+  from carla_garage_b200.config import GlobalConfig
+  from carla_garage_b200.nn import LidarCenterNet
+  from carla_garage_b200.training import Trainer
+  m = LidarCenterNet(GlobalConfig())
+  m.load_state_dict(oracle_state, strict=True)
+  tr = Trainer(m.cuda().train(), lr=1e-3)
+  inp = {k: v.cuda() for k, v in synth.make_inputs(2, seed=11).items()}
+  lab = {k: v.cuda().contiguous() for k, v in synth.make_labels(2, seed=13).items()}
+
+  def check():
+    torch.cuda.synchronize()
+    n = 0
+    for _, out, params, kind, extra in tr.plan.views.values():
+      want = E._build_pack(kind, params, extra)  # pylint: disable=protected-access
+      for a, b in zip(out if isinstance(out, tuple) else (out,), want if isinstance(want, tuple) else (want,)):
+        assert a.dtype == b.dtype and torch.equal(a, b), kind
+        n += 1
+    return n
+
+  before = tr.st.flat.clone()
+  _, l0 = tr.step(inp, lab)
+  assert len(tr.plan.views) > 300 and not tr.plan.pending
+  check()
+  _, l1 = tr.step(inp, lab)
+  _, l2 = tr.step(inp, lab)
+  assert check() > 300
+  assert float((tr.st.flat - before).abs().max()) > 1e-4  # the parameters really moved
+  tot = [sum(float(v) for v in l.values()) for l in (l0, l1, l2)]
+  assert tot[2] < tot[0], tot  # same batch three times: the loss goes down
+  n_seg = len(tr.plan.segments)
+  tr.capture(inp, lab)
+  for _ in range(2):
+    tr.replay()
+  assert len(tr.plan.segments) == n_seg and not tr.plan.pending  # nothing new appeared under capture
+  check()
