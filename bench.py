@@ -189,7 +189,12 @@ def main():
     th.start()
   launches_per_step = tr.launches_per_step if use_graph else None
   _lib.reset_launch_count()
+  prof_range = os.environ.get('TFPP_PROFILE_STEP', '0') == '1'  # ncu --profile-from-start off: timed steps only
+  if prof_range:
+    torch.cuda.profiler.start()
   ms = timed(step_resident, args.steps)
+  if prof_range:
+    torch.cuda.profiler.stop()
   launches = _lib.launch_count() if not use_graph else launches_per_step * args.steps
   stop.set()
   value = world * b * args.steps / (ms / 1e3)

@@ -68,6 +68,7 @@ _PROTOS = {
     'tfpp_planner_head': [P] * 17 + [I, I, I, I, I, P],
     'tfpp_decode_heatmap': [P, L, P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, F, F, P],
     'tfpp_bn_bwd': [P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P],
+    'tfpp_gconv3x3': [P, P, P, P, P, I, P, P, I, I, I, I, I, P],
     'tfpp_gather_pack': [P, P, P, L, I, P],
     'tfpp_se_bwd': [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, I, I, I, P],
     'tfpp_act_bwd': [P, P, I, I, I, F, P, P, I, I, I, I, P],

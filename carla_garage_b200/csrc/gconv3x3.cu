@@ -1,0 +1,287 @@
+// Grouped 3x3 convolution of the RegNetY bottleneck (timm regnet.Bottleneck.conv2: group width 24, stride 1 or 2;
+// oracle/regnety.py) and its input gradient.
+//
+// Per output pixel a group is a 216-long dot product for each of 24 channels: 18 flop per byte moved — an HBM-bound
+// layer.  The implicit-GEMM tcgen05 path re-reads every input tile nine times through L2 and pads K from 24 to 64, so
+// it ran ~10x above the traffic floor.  Here a CTA stages one haloed pixel tile of a 72-channel slab (3 groups) in
+// shared memory ONCE (cp.async, zero fill = padding), each warp owns one group with that group's 9 x 24 x 24 weights
+// resident in registers as mma fragments, and the nine shifted products run on mma.sync (m16n8k16 + m16n8k8 = K 24)
+// straight out of the tile via ldmatrix.  HBM traffic = input once (x ~1.3 halo, mostly L2 hits) + output once.
+// BatchNorm batch statistics (training) or the folded BatchNorm affine + ReLU (eval) ride in the epilogue.
+// The input gradient of a stride-1 conv is the same kernel with the transposed, spatially flipped weight pack.
+#include "../../include/tfpp.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int GW = 24;                  // group width (RegNetY-3.2GF: 24 for every stage)
+constexpr int SLAB_C = 72;              // channels per CTA work item = 3 groups
+constexpr int PIX_BYTES = SLAB_C * 2;   // 144 B per pixel in the tile: ldmatrix rows fall on distinct bank quads
+constexpr int HALO_MAX = 340;           // pixels: 10 x 34, 18 x 18, 34 x 10 (stride 1) / 9 x 33, 17 x 17, 5 x 65 (stride 2)
+constexpr int kWarps = 6;               // 2 warps per group
+constexpr int kThreadsG = kWarps * 32;
+constexpr int STAGE_BYTES = 16 * GW * 2;  // per-warp output staging: 16 pixels x 24 channels bf16
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma1688(float* c, const uint32_t* a, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t* r, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(saddr));
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t saddr, const void* gmem, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gmem), "r"(sz) : "memory");
+}
+
+struct GConvParams {
+  const bf16* x;       // (B,H,W,C) NHWC
+  const bf16* w;       // (C/24, 9, 24, 24): [group][tap = ky*3+kx][out channel][in channel]
+  bf16* out;           // (B,Ho,Wo,C)
+  const float* scale;  // optional per-channel affine (eval-mode BatchNorm fold)
+  const float* shift;
+  int act;
+  float* stat_sum;     // optional BatchNorm batch statistics of the raw output (C each)
+  float* stat_sq;
+  int B, H, W, C, Ho, Wo;
+  int tw_log2, th;     // output tile: th rows x (1 << tw_log2) columns
+  int tiles_x, tiles_y, slabs;
+};
+
+template <int STRIDE>
+__global__ void __launch_bounds__(kThreadsG, 2) gconv3x3_kernel(const GConvParams p) {
+  constexpr int TPIX = STRIDE == 1 ? 256 : 64;   // output pixels per tile
+  constexpr int MT = TPIX / 16;                  // m tiles of 16 pixels per group
+  constexpr int MT_PER_WARP = MT / 2;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* halo_base = smem_raw;                                   // [2][HALO_MAX][144 B]
+  uint8_t* stage_base = smem_raw + 2 * HALO_MAX * PIX_BYTES;       // [kWarps][768 B]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
+  const int group = warp >> 1, half = warp & 1;
+  const int tw = 1 << p.tw_log2, th = p.th;
+  const int hw = (tw - 1) * STRIDE + 3, hh = (th - 1) * STRIDE + 3;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int tiles_total = tiles_per_img * p.B;
+  const int n_items = tiles_total * p.slabs;
+
+  auto load_tile = [&](int item, int buf) {
+    const int slab = item / tiles_total;
+    const int tile = item - slab * tiles_total;
+    const int b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    const int iy0 = (r / p.tiles_x) * th * STRIDE - 1, ix0 = (r % p.tiles_x) * tw * STRIDE - 1;
+    const uint32_t dst0 = smem_u32(halo_base + buf * (HALO_MAX * PIX_BYTES));
+    const bf16* src0 = p.x + static_cast<long long>(b) * p.H * p.W * p.C + slab * SLAB_C;
+    const int n_chunks = hh * hw * 9;
+    for (int i = threadIdx.x; i < n_chunks; i += kThreadsG) {
+      const int pix = i / 9, ch = i - pix * 9;
+      const int hy = pix / hw, hx = pix - hy * hw;
+      const int yy = iy0 + hy, xx = ix0 + hx;
+      const bool ok = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+      const bf16* src = src0 + (static_cast<long long>(ok ? yy : 0) * p.W + (ok ? xx : 0)) * p.C + ch * 8;
+      cp_async16_zfill(dst0 + pix * PIX_BYTES + ch * 16, src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // tap offsets inside the halo tile (bytes)
+  int tapoff[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) tapoff[t] = ((t / 3) * hw + (t % 3)) * PIX_BYTES;
+
+  uint32_t wk16[9][3][2], wk8[9][3];   // this warp's group weights as mma B fragments
+  float sc[3][2], sh[3][2];
+  float ssum[3][2], ssq[3][2];
+  int cur_slab = -1;
+  const bool has_stats = p.stat_sum != nullptr;
+  const bool has_affine = p.scale != nullptr;
+
+  auto flush_stats = [&](int slab) {
+    if (!has_stats) return;
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a = ssum[nt][e], b2 = ssq[nt][e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+        }
+        if (gq == 0) {
+          const int c = slab * SLAB_C + group * GW + nt * 8 + 2 * t4 + e;
+          atomicAdd(p.stat_sum + c, a);
+          atomicAdd(p.stat_sq + c, b2);
+        }
+        ssum[nt][e] = ssq[nt][e] = 0.f;
+      }
+  };
+
+  int buf = 0;
+  int item = blockIdx.x;
+  if (item < n_items) load_tile(item, 0);
+  for (; item < n_items; item += gridDim.x, buf ^= 1) {
+    const int next = item + gridDim.x;
+    if (next < n_items) {
+      load_tile(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int slab = item / tiles_total;
+    const int tile = item - slab * tiles_total;
+    if (slab != cur_slab) {
+      if (cur_slab >= 0) flush_stats(cur_slab);
+      cur_slab = slab;
+      const uint32_t* wg = reinterpret_cast<const uint32_t*>(p.w) +
+                           static_cast<long long>(slab * 3 + group) * (9 * GW * GW / 2);
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          const uint32_t* row = wg + (t * GW + nt * 8 + gq) * (GW / 2);   // [co][ci] row, 12 words
+          wk16[t][nt][0] = __ldg(row + t4);
+          wk16[t][nt][1] = __ldg(row + 4 + t4);
+          wk8[t][nt] = __ldg(row + 8 + t4);
+        }
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = slab * SLAB_C + group * GW + nt * 8 + 2 * t4 + e;
+          sc[nt][e] = has_affine ? __ldg(p.scale + c) : 1.f;
+          sh[nt][e] = has_affine ? __ldg(p.shift + c) : 0.f;
+          ssum[nt][e] = ssq[nt][e] = 0.f;
+        }
+    }
+    const int b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    const int oy0 = (r / p.tiles_x) * th, ox0 = (r % p.tiles_x) * tw;
+    const uint32_t halo = smem_u32(halo_base + buf * (HALO_MAX * PIX_BYTES));
+    uint8_t* stage = stage_base + warp * STAGE_BYTES;
+    bf16* out_img = p.out + static_cast<long long>(b) * p.Ho * p.Wo * p.C + slab * SLAB_C + group * GW;
+
+#pragma unroll 1
+    for (int u = 0; u < MT_PER_WARP; ++u) {
+      const int mt = half * MT_PER_WARP + u;
+      // ldmatrix row address of this lane: pixel q of the m tile, channel sub-block by matrix index
+      const int mat = lane >> 3, rr = lane & 7;
+      const int q = mt * 16 + (mat & 1) * 8 + rr;
+      const int ty = q >> p.tw_log2, tx = q & (tw - 1);
+      const uint32_t a_base = halo + ((ty * STRIDE) * hw + tx * STRIDE) * PIX_BYTES + group * (GW * 2);
+      const uint32_t a16 = a_base + (mat >> 1) * 16;   // x4: k 0-7 / 8-15
+      const uint32_t a8 = a_base + 32;                 // x2: k 16-23 (lanes 16-31 repeat valid addresses)
+      float acc[3][4];
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        uint32_t a[4], a2[2];
+        ldsm_x4(a, a16 + tapoff[t]);
+        ldsm_x2(a2, a8 + tapoff[t]);
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          mma16816(acc[nt], a, wk16[t][nt][0], wk16[t][nt][1]);
+          mma1688(acc[nt], a2, wk8[t][nt]);
+        }
+      }
+      // epilogue: rows gq and gq + 8 of the m tile
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int qo = mt * 16 + gq + hf * 8;
+        const int oy = oy0 + (qo >> p.tw_log2), ox = ox0 + (qo & (tw - 1));
+        const bool ok = oy < p.Ho && ox < p.Wo;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          float v0 = acc[nt][hf * 2], v1 = acc[nt][hf * 2 + 1];
+          if (has_stats && ok) {
+            ssum[nt][0] += v0;
+            ssum[nt][1] += v1;
+            ssq[nt][0] = fmaf(v0, v0, ssq[nt][0]);
+            ssq[nt][1] = fmaf(v1, v1, ssq[nt][1]);
+          }
+          if (has_affine) {
+            v0 = fmaf(v0, sc[nt][0], sh[nt][0]);
+            v1 = fmaf(v1, sc[nt][1], sh[nt][1]);
+          }
+          if (p.act == ACT_RELU) {
+            v0 = fmaxf(v0, 0.f);
+            v1 = fmaxf(v1, 0.f);
+          }
+          *reinterpret_cast<uint32_t*>(stage + (gq + hf * 8) * (GW * 2) + nt * 16 + t4 * 4) = pack_bf16x2(v0, v1);
+        }
+      }
+      __syncwarp();
+      // 16 pixels x 48 B = 48 chunks of 16 B: coalesced-as-possible vector stores
+#pragma unroll
+      for (int j = lane; j < 48; j += 32) {
+        const int px = j / 3, part = j - px * 3;
+        const int qo = mt * 16 + px;
+        const int oy = oy0 + (qo >> p.tw_log2), ox = ox0 + (qo & (tw - 1));
+        if (oy < p.Ho && ox < p.Wo) {
+          const uint4 v = *reinterpret_cast<const uint4*>(stage + j * 16);
+          *reinterpret_cast<uint4*>(out_img + (static_cast<long long>(oy) * p.Wo + ox) * p.C + part * 8) = v;
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();  // everyone is done with `buf` before the next iteration's prefetch overwrites it
+  }
+  if (cur_slab >= 0) flush_stats(cur_slab);
+}
+
+}  // namespace
+
+extern "C" int tfpp_gconv3x3(const void* x, const void* w, void* out, const float* scale, const float* shift, int act,
+                             float* stat_sum, float* stat_sq, int batch, int height, int width, int channels, int stride,
+                             tfpp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TFPP_CHECK_ARG(channels % SLAB_C == 0, "channels must be a multiple of 72 (3 groups of width 24)");
+  TFPP_CHECK_ARG(stride == 1 || stride == 2, "stride 1 or 2");
+  TFPP_CHECK_ARG(stride == 1 || (height % 2 == 0 && width % 2 == 0), "stride 2 needs even H, W");
+  TFPP_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift go together");
+  TFPP_CHECK_ARG((stat_sum == nullptr) == (stat_sq == nullptr), "stat_sum and stat_sq go together");
+  TFPP_CHECK_ARG(act == ACT_NONE || act == ACT_RELU, "activation: none or relu");
+  GConvParams p;
+  p.x = static_cast<const bf16*>(x); p.w = static_cast<const bf16*>(w); p.out = static_cast<bf16*>(out);
+  p.scale = scale; p.shift = shift; p.act = act; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
+  p.B = batch; p.H = height; p.W = width; p.C = channels;
+  p.Ho = height / stride; p.Wo = width / stride;
+  const int tpix = stride == 1 ? 256 : 64;
+  const int tw_max = stride == 1 ? 32 : 16;
+  int tw_log2 = 3;  // at least 8 wide (an m tile is 16 consecutive tile pixels: 1 or 2 rows)
+  while ((1 << tw_log2) < p.Wo && (1 << tw_log2) < tw_max) ++tw_log2;
+  p.tw_log2 = tw_log2;
+  p.th = tpix >> tw_log2;
+  p.tiles_x = ceil_div(p.Wo, 1 << tw_log2);
+  p.tiles_y = ceil_div(p.Ho, p.th);
+  p.slabs = channels / SLAB_C;
+  const long long items = static_cast<long long>(p.tiles_x) * p.tiles_y * batch * p.slabs;
+  if (items == 0) return TFPP_OK;
+  const size_t smem = 2 * HALO_MAX * PIX_BYTES + kWarps * STAGE_BYTES;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gconv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(gconv3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    attr = true;
+  }
+  const int grid = static_cast<int>(items < 2 * TFPP_NUM_SMS ? items : 2 * TFPP_NUM_SMS);
+  if (stride == 1) gconv3x3_kernel<1><<<grid, kThreadsG, smem, stream>>>(p);
+  else gconv3x3_kernel<2><<<grid, kThreadsG, smem, stream>>>(p);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}

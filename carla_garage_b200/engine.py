@@ -16,7 +16,7 @@ PARAM_EPOCH = [0]  # bumped by the fused optimizer (it updates parameter storage
 
 
 # kinds whose pack is a pure gather (+ zero padding) of parameter elements: eligible for the one-kernel PackPlan
-_GATHER_KINDS = frozenset(('conv', 'gconv', 'linear', 'conv_t', 'conv_rows_pad', 'conv_dgrad_smallc', 'gconv_t', 'linear_t',
+_GATHER_KINDS = frozenset(('conv', 'gconv', 'gconv_halo', 'gconv_halo_t', 'linear', 'conv_t', 'conv_rows_pad', 'conv_dgrad_smallc', 'gconv_t', 'linear_t',
                            'rows_t', 'cat_linear_t', 'cat_conv_t', 'blockdiag_1x1_t', 'rows', 'rows_f32', 'cat_linear',
                            'cat_rows', 'cat_rows_f32', 'cat_f32', 'cat_conv', 'blockdiag_1x1', 'repeat_rows'))
 
@@ -28,6 +28,10 @@ def _build_pack(kind, params, extra, dtb=BF16, dtf=F32):
     return ops.pack_conv_weight(params[0], dt=dtb)
   if kind == 'gconv':
     return ops.pack_grouped_conv_weight(params[0], dt=dtb)
+  if kind == 'gconv_halo':  # (C,24,3,3) -> (C/24, 9, 24, 24) for tfpp_gconv3x3
+    return ops.pack_gconv_halo(params[0], dt=dtb)
+  if kind == 'gconv_halo_t':  # its input-gradient operand
+    return ops.pack_gconv_halo(params[0], transpose=True, dt=dtb)
   if kind == 'linear':
     return params[0].detach().reshape(params[0].shape[0], -1).to(dtb).contiguous()
   if kind == 'conv_t':  # dgrad operand (Cin, taps, Cout padded to a multiple of 8)
@@ -280,20 +284,27 @@ class Engine:
     if self.debug_taps is not None:
       self.debug_taps[name] = t
 
-  def conv_bn(self, a, cna, training, *, taps=ops.TAPS_1X1, batch=None, grouped=False, act=ACT_NONE, res=None,
+  def conv_bn(self, a, cna, training, *, taps=ops.TAPS_1X1, batch=None, grouped=False, stride=1, act=ACT_NONE, res=None,
               res_bn=None, want_pool=False, a_src=None):
     """ConvNormAct (timm ConvBnAct): conv -> BatchNorm2d -> act, optionally (+ res) before act and per-sample channel
-    sums for squeeze-excite.  Training: batch statistics from the GEMM epilogue, one apply pass.  Eval: everything in
-    the GEMM epilogue.  res_bn = (raw, scale, shift): residual that still needs its own BatchNorm affine."""
-    w = packed(cna.conv.weight, 'gconv' if grouped else 'conv')
-    gkw = dict(k_per_tile=48, a_c_per_ntile=48, bn=48) if grouped else {}
+    sums for squeeze-excite.  Training: batch statistics from the conv epilogue, one apply pass.  Eval: everything in
+    the conv epilogue.  res_bn = (raw, scale, shift): residual that still needs its own BatchNorm affine.
+    grouped: the RegNet 3x3 group conv (stride 1 or 2) on the haloed-tile kernel; everything else is an implicit GEMM."""
     bn = cna.bn
-    cout = w.shape[0]
+    cout = cna.conv.weight.shape[0]
+    if grouped:
+      assert ops.gconv3x3_supported(cout, cna.conv.weight.shape[1]), 'group width 24, channels % 72 == 0'
+      w = packed(cna.conv.weight, 'gconv_halo')
+    else:
+      w = packed(cna.conv.weight, 'conv')
     b = a.shape[0] if batch is None else batch
     pool = self.zeros((b, cout), a.device) if want_pool else None
     if training:
       stats = self.zeros((2, cout), a.device)
-      raw = ops.conv_gemm(a, w, taps=taps, batch=batch, stats=(stats[0], stats[1]), **gkw)
+      if grouped:
+        raw = ops.gconv3x3(a, w, stride, stats=(stats[0], stats[1]))
+      else:
+        raw = ops.conv_gemm(a, w, taps=taps, batch=batch, stats=(stats[0], stats[1]))
       count = raw.shape[0] * raw.shape[1] * raw.shape[2]
       scale, shift, mean, invstd = ops.bn_finalize(stats[0], stats[1], bn.weight, bn.bias, bn.running_mean,
                                                    bn.running_var, count, eps=bn.eps, momentum=bn.momentum,
@@ -305,10 +316,14 @@ class Engine:
       else:
         y = ops.scale_shift_act(raw, scale, shift, act, res=res, pool_sum=pool)
       self._save(op='conv_bn', a=a, a_src=a_src, raw=raw, y=y, mean=mean, invstd=invstd, cna=cna, taps=taps,
-                 batch=batch, grouped=grouped, act=act, res=res, res_bn=res_bn)
+                 batch=batch, grouped=grouped, stride=stride, act=act, res=res, res_bn=res_bn)
       return (y, pool) if want_pool else y
     scale, shift = packed((bn.weight, bn.bias, bn.running_mean, bn.running_var), 'bn_eval', bn.eps)
-    y = ops.conv_gemm(a, w, taps=taps, batch=batch, scale=scale, shift=shift, act=act, res1=res, **gkw)
+    if grouped:
+      assert res is None
+      y = ops.gconv3x3(a, w, stride, scale=scale, shift=shift, act=act)
+    else:
+      y = ops.conv_gemm(a, w, taps=taps, batch=batch, scale=scale, shift=shift, act=act, res1=res)
     if want_pool:
       ops.scale_shift_act(y, pool_sum=pool, out=y)
       return y, pool
@@ -337,14 +352,8 @@ class Engine:
     b, h, w, _ = x.shape
     s = blk.stride
     a1 = self.conv_bn(x, blk.conv1, training, act=ACT_RELU)
-    if s == 2:
-      a1p = ops.parity_split(a1)
-      a2, pool = self.conv_bn(a1p, blk.conv2, training, taps=ops.taps_3x3_stride2(b), batch=b, grouped=True,
-                              act=ACT_RELU, want_pool=True, a_src=a1)
-      ho, wo = h // 2, w // 2
-    else:
-      a2, pool = self.conv_bn(a1, blk.conv2, training, taps=ops.TAPS_3X3, grouped=True, act=ACT_RELU, want_pool=True)
-      ho, wo = h, w
+    a2, pool = self.conv_bn(a1, blk.conv2, training, grouped=True, stride=s, act=ACT_RELU, want_pool=True)
+    ho, wo = h // s, w // s
     se = blk.se
     hidden = None
     if self.tape is not None:

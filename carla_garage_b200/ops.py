@@ -1,6 +1,7 @@
 """Thin torch-tensor wrappers over the C ABI (include/tfpp.h).  torch is used for device memory and the current
 stream only; every computation happens in libtfpp.so.  No fallback: a missing library or a CPU tensor raises."""
 import ctypes
+import os
 
 import torch
 
@@ -38,9 +39,20 @@ def profile_gemm_launches(fn):
   try:
     fn()
     torch.cuda.synchronize()
-    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in _PROFILE)
-    flop = sum(f for _, _, f in _PROFILE)
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in _PROFILE)
+    flop = sum(f for _, _, f, _ in _PROFILE)
     n = len(_PROFILE)
+    dump = os.environ.get('TFPP_GEMM_DUMP')
+    if dump:  # per-launch shapes and times, aggregated by shape (kernel-tuning aid)
+      agg = {}
+      for e0, e1, f, desc in _PROFILE:
+        a = agg.setdefault(desc, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += e0.elapsed_time(e1)
+        a[2] += f
+      with open(dump, 'w', encoding='utf-8') as fh:
+        for desc, (cnt, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+          fh.write(f'{t:9.3f} ms  n={cnt:4d}  avg {t / cnt * 1e3:8.1f} us  {f / t / 1e9 if t else 0:8.1f} TFLOP/s  {desc}\n')
   finally:
     _PROFILE = None
   return {'ms': ms, 'gflop': flop / 1e9, 'launches': n, 'tflops': flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
@@ -167,7 +179,8 @@ def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1
   if _PROFILE is not None:
     e1.record()
     k_alg = 24 if a_c_per_ntile else args.k_per_tile
-    _PROFILE.append((e0, e1, 2.0 * b * h * wd * n * k_alg * len(taps)))
+    _PROFILE.append((e0, e1, 2.0 * b * h * wd * n * k_alg * len(taps),
+                     f'gemm  b{b} {h}x{wd} n{n} k{kd} taps{len(taps)} bn{bn} grp{int(bool(a_c_per_ntile))} stats{int(stats is not None)}'))
   return out
 
 
@@ -216,7 +229,8 @@ def conv_wgrad(dy, x, *, cin=None, taps=TAPS_1X1, w_taps=None, group_width=0, x_
   check(_lib.load().tfpp_conv_wgrad(ctypes.byref(a), _stream()), 'tfpp_conv_wgrad')
   if _PROFILE is not None:
     e1.record()
-    _PROFILE.append((e0, e1, 2.0 * b * h * w * (cout_valid or cout) * (group_width or cin) * len(taps)))
+    _PROFILE.append((e0, e1, 2.0 * b * h * w * (cout_valid or cout) * (group_width or cin) * len(taps),
+                     f'wgrad b{b} {h}x{w} cout{cout} cin{cin} taps{len(taps)} grp{group_width}'))
   return out
 
 
@@ -439,6 +453,37 @@ def decode_heatmap(heat, wh, offset, yaw_cls, yaw_res, k=100, img_h=256, img_w=2
 
 # ---------------------------------------------------------------------------------------------- weight packing
 # (load-time plumbing: layout changes of parameters, no activations involved)
+def gconv3x3_supported(channels, group_width):
+  return group_width == 24 and channels % 72 == 0
+
+
+def gconv3x3(x, w, stride=1, scale=None, shift=None, act=ACT_NONE, stats=None):
+  """Grouped 3x3 conv (group width 24, pad 1) on the haloed-tile kernel.  x (B,H,W,C) bf16, w (C/24, 9, 24, 24) bf16
+  (pack_gconv_halo); returns (B,H/stride,W/stride,C) bf16.  stats = (sum, sumsq) f32 (C) accumulate the raw output."""
+  _dev(x, BF16)
+  _dev(w, BF16)
+  b, h, wd, c = x.shape
+  out = torch.empty((b, h // stride, wd // stride, c), dtype=BF16, device=x.device)
+  check(_lib.load().tfpp_gconv3x3(x.data_ptr(), w.data_ptr(), out.data_ptr(), _p(scale), _p(shift), act,
+                                  _p(stats[0]) if stats is not None else None,
+                                  _p(stats[1]) if stats is not None else None, b, h, wd, c, stride, _stream()),
+        'tfpp_gconv3x3')
+  return out
+
+
+def pack_gconv_halo(w, transpose=False, dt=BF16):
+  """(C, 24, 3, 3) grouped conv weight -> (C/24, 9, 24, 24) = [group][ky*3+kx][out][in]; transpose=True gives the
+  input-gradient operand: in/out swapped inside each group and the taps spatially flipped."""
+  c, gw, kh, kw = w.shape
+  g = c // gw
+  wg = w.detach().view(g, gw, gw, kh, kw)  # [g][co][ci][ky][kx]
+  if transpose:
+    wg = wg.flip(3, 4).permute(0, 3, 4, 2, 1)  # [g][ky'][kx'][ci][co]
+  else:
+    wg = wg.permute(0, 3, 4, 1, 2)  # [g][ky][kx][co][ci]
+  return wg.reshape(g, kh * kw, gw, gw).to(dt).contiguous()
+
+
 def gather_pack(flat, idx, out):
   """out[i] = flat[idx[i]] (0 where idx < 0), cast to out's dtype: the PackPlan refresh kernel."""
   check(_lib.load().tfpp_gather_pack(flat.data_ptr(), idx.data_ptr(), out.data_ptr(), out.numel(), int(out.dtype == F32),

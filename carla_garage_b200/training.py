@@ -275,27 +275,35 @@ class Backward:
       self.add(r['res'], dz)
     if r['res_bn'] is not None:
       self.G[id(r['res_bn'][0])] = dz
-    self.conv_grads(draw, a, r['a_src'], conv, r['taps'], r['batch'], r['grouped'])
+    self.conv_grads(draw, a, r['a_src'], conv, r['taps'], r['batch'], r['grouped'], r.get('stride', 1))
 
-  def conv_grads(self, draw, a, a_src, conv, taps, batch, grouped):
+  def conv_grads(self, draw, a, a_src, conv, taps, batch, grouped, stride=1):
     """weight gradient + input gradient of a bias-free conv given the gradient of its raw output."""
     st = self.st
     k = conv.weight.shape[-1]
     cout = conv.weight.shape[0]
     b, ho, wo, _ = draw.shape
-    if grouped:
+    if grouped:  # RegNet 3x3 group conv; a = the full-resolution input whatever the stride
       gw = conv.weight.shape[1]
-      ops.conv_wgrad(draw, a, taps=taps, w_taps=9, group_width=gw, out=st.g(conv.weight), out_strides=(gw * 9, 1, 9))
-      wt = packed(conv.weight, 'gconv_t')
-      gk = dict(k_per_tile=48, a_c_per_ntile=48, bn=48)
-      if a_src is None:  # stride 1
-        self.G[id(a)] = ops.conv_gemm(draw, wt, taps=ops.TAPS_3X3_DGRAD, res1=self.G.get(id(a)), **gk)
-      else:  # stride 2: one launch per input parity plane, written at its positions of the full-resolution gradient
-        h, w, c = a_src.shape[1], a_src.shape[2], a_src.shape[3]
-        da = self.G.get(id(a_src))
+      gout, gstr = st.g(conv.weight), (gw * 9, 1, 9)
+      if stride == 1:
+        ops.conv_wgrad(draw, a, taps=ops.TAPS_3X3, w_taps=9, group_width=gw, out=gout, out_strides=gstr)
+        da = ops.gconv3x3(draw, packed(conv.weight, 'gconv_halo_t'))  # same kernel, transposed + flipped weights
+        if id(a) in self.G:
+          ops.add_bf16(self.G[id(a)], da, out=da)
+        self.G[id(a)] = da
+      else:
+        # stride 2: weight gradient against the parity planes of the input, input gradient as one implicit GEMM per
+        # input parity plane written at its positions of the full-resolution gradient
+        ops.conv_wgrad(draw, ops.parity_split(a), taps=ops.taps_3x3_stride2(b), w_taps=9, group_width=gw, out=gout,
+                       out_strides=gstr)
+        wt = packed(conv.weight, 'gconv_t')
+        gk = dict(k_per_tile=48, a_c_per_ntile=48, bn=48)
+        h, w, c = a.shape[1], a.shape[2], a.shape[3]
+        da = self.G.get(id(a))
         have = da is not None
         if not have:
-          da = torch.empty_like(a_src)
+          da = torch.empty_like(a)
         for py in range(2):
           for px in range(2):
             off = (py * w + px) * c
@@ -303,7 +311,7 @@ class Backward:
             strides = (h * w * c, 2 * w * c, 2 * c, 1)
             ops.conv_gemm(draw, wt, taps=ops.taps_dgrad_stride2(py, px), out=view, out_strides=strides,
                           res1=view if have else None, res1_strides=strides if have else None, **gk)
-        self.G[id(a_src)] = da
+        self.G[id(a)] = da
     else:
       cin = conv.weight.shape[1]
       ops.conv_wgrad(draw, a, cin=cin, taps=taps, w_taps=k * k, out=st.g(conv.weight),

@@ -276,6 +276,16 @@ int tfpp_planner_loss(const float* logits, const long long* labels, const float*
                       const float* cp_t, float w_ts, float w_cp, float* losses, float* dlogits, float* dcp, int batch,
                       int n_cls, int n_cp, tfpp_stream_t stream);
 
+/* Grouped 3x3 convolution of the RegNetY bottleneck (timm regnet.Bottleneck.conv2, group width 24; stride 1 or 2,
+ * padding 1) on a haloed shared-memory tile: x (B,H,W,C) NHWC bf16, C % 72 == 0; w (C/24, 9, 24, 24) bf16 =
+ * [group][ky*3+kx][out][in]; out (B,H/stride,W/stride,C) bf16.  Optional: per-channel affine + ReLU (eval-mode
+ * BatchNorm fold) and BatchNorm batch statistics of the raw output (stat_sum/stat_sq, C floats each, +=).  The input
+ * gradient of the stride-1 conv is the same call on dY with the transposed, spatially flipped pack.
+ * Replaces nn.Conv2d(groups=C/24) + BatchNorm2d statistics in timm's regnet.Bottleneck (oracle/regnety.py). */
+int tfpp_gconv3x3(const void* x, const void* w, void* out, const float* scale, const float* shift, int act,
+                  float* stat_sum, float* stat_sq, int batch, int height, int width, int channels, int stride,
+                  tfpp_stream_t stream);
+
 /* Weight-pack refresh: out[i] = idx[i] >= 0 ? flat[idx[i]] : 0 for i < n (n % 8 == 0), cast to bf16 (out_f32 = 0) or
  * kept fp32.  One launch rebuilds every kernel-layout weight copy after the optimizer step; replaces the implicit
  * per-module weight reads of torch's conv / linear kernels (team_code/train.py:898-908 loop). */

@@ -105,7 +105,8 @@ def test_pack_plan_index_maps_reproduce_every_gather_pack():
   plan = E.PackPlan(flat)
   cases = [('conv', (params['conv'],), ()), ('conv_t', (params['conv'],), ()), ('conv_rows_pad', (params['conv'],), (64,)),
            ('conv_dgrad_smallc', (params['conv'],), (64,)), ('gconv', (params['gconv'],), ()),
-           ('gconv_t', (params['gconv'],), ()), ('linear', (params['lin_a'],), ()), ('linear_t', (params['lin_a'],), ()),
+           ('gconv_t', (params['gconv'],), ()), ('gconv_halo', (params['gconv'],), ()),
+           ('gconv_halo_t', (params['gconv'],), ()), ('linear', (params['lin_a'],), ()), ('linear_t', (params['lin_a'],), ()),
            ('rows', (params['lin_a'],), (8, 24)), ('rows_t', (params['lin_a'],), (8, 24)),
            ('rows_f32', (params['lin_a'],), (8, 24)), ('cat_linear', (params['lin_a'], params['lin_b']), ()),
            ('cat_linear_t', (params['lin_a'], params['lin_b']), ()), ('cat_rows', (params['lin_a'], params['lin_b']), (0, 8)),

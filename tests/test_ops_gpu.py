@@ -420,3 +420,33 @@ def test_act_backward(ops, rows, c, layout, act, limit):
     want = want * (m * yf * (1 - yf) + (1 - m))
   assert rel(dz.float(), want) < 4e-3
   assert rel(dbias, want.sum(0)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ haloed-tile group conv
+@pytest.mark.parametrize('b,h,w,c,stride', [(2, 16, 64, 72, 1), (1, 8, 8, 216, 1), (3, 20, 12, 144, 1), (2, 64, 64, 72, 2),
+                                            (1, 16, 16, 576, 2), (2, 10, 36, 72, 2), (1, 8, 32, 1512, 1)])
+def test_gconv3x3_forward_stats_affine(ops, b, h, w, c, stride):
+  """tfpp_gconv3x3 against F.conv2d(groups=C/24) on the bf16-rounded operands; BatchNorm statistics; eval affine+ReLU."""
+  x = bf(rnd(b, h, w, c, seed=1))
+  wt = rnd(c, 24, 3, 3, seed=2, scale=0.1)
+  wp = ops.pack_gconv_halo(wt)
+  want = F.conv2d(x.float().permute(0, 3, 1, 2), bf(wt).float(), stride=stride, padding=1, groups=c // 24)
+  st = (torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda'))
+  y = ops.gconv3x3(x, wp, stride, stats=st)
+  assert y.shape == (b, h // stride, w // stride, c)
+  assert rel(y.float().permute(0, 3, 1, 2), want) < 4e-3
+  assert rel(st[0], want.sum((0, 2, 3))) < 2e-3 and rel(st[1], (want * want).sum((0, 2, 3))) < 2e-3
+  sc, sh = rnd(c, seed=3).abs() + 0.5, rnd(c, seed=4)
+  y2 = ops.gconv3x3(x, wp, stride, scale=sc, shift=sh, act=ops.ACT_RELU)
+  assert rel(y2.float().permute(0, 3, 1, 2), F.relu(want * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))) < 4e-3
+
+
+@pytest.mark.parametrize('b,h,w,c', [(2, 16, 32, 72), (1, 8, 8, 216), (2, 24, 20, 144)])
+def test_gconv3x3_input_gradient(ops, b, h, w, c):
+  """stride-1 input gradient = the same kernel on dY with the transposed / flipped pack, against autograd."""
+  x = rnd(b, c, h, w, seed=1).requires_grad_(True)
+  wt = rnd(c, 24, 3, 3, seed=2, scale=0.1)
+  dy = bf(rnd(b, h, w, c, seed=3))
+  F.conv2d(x, bf(wt).float(), padding=1, groups=c // 24).backward(dy.float().permute(0, 3, 1, 2))
+  got = ops.gconv3x3(dy, ops.pack_gconv_halo(wt, transpose=True))
+  assert rel(got.float().permute(0, 3, 1, 2), x.grad) < 4e-3

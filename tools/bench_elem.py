@@ -61,3 +61,12 @@ for (h, w, cin, cout, tag) in ((256, 1024, 32, 32, 'dec5'), (256, 1024, 32, 8, '
   ms = timeit(lambda: ops.smallc_conv3x3(x, wt), iters=5)
   m = B * h * w
   rec(f'smallc_conv3x3 {tag} {cin}->{cout}  ({2.0*m*cin*cout*9/ms/1e9:.0f} TFLOP/s)', ms, 2.0 * m * (cin + cout))
+# RegNet group convs on the haloed-tile kernel (image branch shapes; stride 2 = first block of the stage)
+for (h, w, c, stride, tag) in ((128, 512, 72, 2, 's1.b1'), (64, 256, 72, 1, 's1'), (64, 256, 216, 2, 's2.b1'), (32, 128, 216, 1, 's2'),
+                               (16, 64, 576, 1, 's3'), (8, 32, 1512, 1, 's4'), (16, 16, 576, 1, 's3 lidar')):
+  x = bf(B, h, w, c)
+  wp = ops.pack_gconv_halo(torch.randn(c, 24, 3, 3, device='cuda'))
+  st = (torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda'))
+  ms = timeit(lambda: ops.gconv3x3(x, wp, stride, stats=st), iters=5)
+  m = B * (h // stride) * (w // stride)
+  rec(f'gconv3x3+stats {tag} {h}x{w} C={c} s{stride}  ({2.0*m*c*24*9/ms/1e9:.0f} TFLOP/s)', ms, 2.0 * (B * h * w * c + m * c))
