@@ -69,6 +69,8 @@ _PROTOS = {
     'tfpp_decode_heatmap': [P, L, P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, F, F, P],
     'tfpp_bn_bwd': [P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P],
     'tfpp_gconv3x3': [P, P, P, P, P, I, P, P, I, I, I, I, I, P],
+    'tfpp_gconv3x3_wgrad': [P, P, P, P, I, I, I, I, I, P],
+    'tfpp_gconv3x3_wgrad_workspace': [I, I, I, I, I],
     'tfpp_gather_pack': [P, P, P, L, I, P],
     'tfpp_se_bwd': [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, I, I, I, P],
     'tfpp_act_bwd': [P, P, I, I, I, F, P, P, I, I, I, I, P],
@@ -111,14 +113,14 @@ def load():
   lib.tfpp_last_error.argtypes = []
   for name, args in _PROTOS.items():
     fn = getattr(lib, name)
-    fn.restype = c_int
+    fn.restype = c_ll if name.endswith('_workspace') else c_int
     fn.argtypes = args
   _lib = lib
   return lib
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
-_KERNELS_PER_CALL = {'tfpp_adamw_amsgrad': 2, 'tfpp_pillar_scatter': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 4, 'tfpp_se_gate': 2, 'tfpp_fusion_attn_bwd': 2}
+_KERNELS_PER_CALL = {'tfpp_adamw_amsgrad': 2, 'tfpp_pillar_scatter': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 4, 'tfpp_se_gate': 2, 'tfpp_gconv3x3_wgrad': 2, 'tfpp_fusion_attn_bwd': 2}
 _LAUNCHES = [0]
 
 

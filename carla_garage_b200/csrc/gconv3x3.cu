@@ -244,7 +244,146 @@ __global__ void __launch_bounds__(kThreadsG, 2) gconv3x3_kernel(const GConvParam
   if (cur_slab >= 0) flush_stats(cur_slab);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient: dW[co][ci][tap] += sum_pixels dY[pix][co] * X[pix*stride + tap - 1][ci] inside each group of 24.
+// grid = (CTAs per slab, slabs).  A CTA stages the dY tile and the haloed X tile of one 72-channel slab, contracts
+// over the tile's pixels with mma.sync (operands fetched with ldmatrix.trans: pixel-major storage -> channel-major
+// fragments) and keeps its share of the 3 x 9 x 24 x 24 products in registers across all its tiles: warp = (group,
+// kernel row).  Partials go to a workspace with plain stores; a second tiny kernel adds them into dW (no atomics).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWarpsW = 9;
+constexpr int kThreadsW = kWarpsW * 32;
+constexpr int SLAB_W = SLAB_C * GW * 9;   // 15552 weight-gradient elements per slab, torch layout [co][ci][ky][kx]
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t* r, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(saddr));
+}
+
+struct GWgradParams {
+  const bf16* dy;   // (B,Ho,Wo,C)
+  const bf16* x;    // (B,H,W,C)
+  float* part;      // workspace [slabs][gridDim.x][SLAB_W]
+  int B, H, W, C, Ho, Wo;
+  int tw_log2, th;
+  int tiles_x, tiles_y;
+};
+
+template <int STRIDE>
+__global__ void __launch_bounds__(kThreadsW, 2) gconv3x3_wgrad_kernel(const GWgradParams p) {
+  constexpr int TPIX = STRIDE == 1 ? 256 : 64;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* xs = smem_raw;                           // [HALO_MAX][144 B]
+  uint8_t* dys = smem_raw + HALO_MAX * PIX_BYTES;   // [TPIX][144 B]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
+  const int group = warp / 3, ky = warp - group * 3;
+  const int slab = blockIdx.y;
+  const int tw = 1 << p.tw_log2, th = p.th;
+  const int hw = (tw - 1) * STRIDE + 3, hh = (th - 1) * STRIDE + 3;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int tiles_total = tiles_per_img * p.B;
+  float acc[3][2][3][4];   // [kx][m tile][n tile][frag]
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 3; ++n) acc[a][m][n][0] = acc[a][m][n][1] = acc[a][m][n][2] = acc[a][m][n][3] = 0.f;
+  const uint32_t xs_u = smem_u32(xs), dys_u = smem_u32(dys);
+  const int mat = lane >> 3, rr = lane & 7;
+
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+    const int b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    const int oy0 = (r / p.tiles_x) * th, ox0 = (r % p.tiles_x) * tw;
+    __syncthreads();  // previous tile fully consumed
+    {
+      const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+      const bf16* src0 = p.x + static_cast<long long>(b) * p.H * p.W * p.C + slab * SLAB_C;
+      for (int i = threadIdx.x; i < hh * hw * 9; i += kThreadsW) {
+        const int pix = i / 9, ch = i - pix * 9;
+        const int hy = pix / hw, hx = pix - hy * hw;
+        const int yy = iy0 + hy, xx = ix0 + hx;
+        const bool ok = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        cp_async16_zfill(xs_u + pix * PIX_BYTES + ch * 16,
+                         src0 + (static_cast<long long>(ok ? yy : 0) * p.W + (ok ? xx : 0)) * p.C + ch * 8, ok);
+      }
+      const bf16* dsrc0 = p.dy + static_cast<long long>(b) * p.Ho * p.Wo * p.C + slab * SLAB_C;
+      for (int i = threadIdx.x; i < TPIX * 9; i += kThreadsW) {
+        const int q = i / 9, ch = i - q * 9;
+        const int oy = oy0 + (q >> p.tw_log2), ox = ox0 + (q & (tw - 1));
+        const bool ok = oy < p.Ho && ox < p.Wo;
+        cp_async16_zfill(dys_u + q * PIX_BYTES + ch * 16,
+                         dsrc0 + (static_cast<long long>(ok ? oy : 0) * p.Wo + (ok ? ox : 0)) * p.C + ch * 8, ok);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ks = 0; ks < TPIX / 16; ++ks) {
+      // A fragments (m = out channel of the group, k = 16 tile pixels): m tile 0 = channels 0-15, m tile 1 = 16-23
+      uint32_t a0[4], a1[4];
+      {
+        const int q = ks * 16 + (mat >> 1) * 8 + rr;
+        ldsm_x4_t(a0, dys_u + q * PIX_BYTES + group * (GW * 2) + (mat & 1) * 16);
+        uint32_t t2[2];
+        const int q2 = ks * 16 + (mat & 1) * 8 + rr;
+        ldsm_x2_t(t2, dys_u + q2 * PIX_BYTES + group * (GW * 2) + 32);
+        a1[0] = t2[0]; a1[1] = 0u; a1[2] = t2[1]; a1[3] = 0u;
+      }
+      // B fragments (k = the same pixels shifted by the tap, n = in channel of the group)
+      const int qb = ks * 16 + (mat & 1) * 8 + rr;
+      const int ty = qb >> p.tw_log2, tx = qb & (tw - 1);
+      const uint32_t xrow = xs_u + ((ty * STRIDE + ky) * hw + tx * STRIDE) * PIX_BYTES + group * (GW * 2);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        uint32_t b01[4], b2[2];
+        ldsm_x4_t(b01, xrow + kx * PIX_BYTES + (mat >> 1) * 16);   // n tiles 0, 1: {b0,b1} each
+        ldsm_x2_t(b2, xrow + kx * PIX_BYTES + 32);                 // n tile 2
+        mma16816(acc[kx][0][0], a0, b01[0], b01[1]);
+        mma16816(acc[kx][0][1], a0, b01[2], b01[3]);
+        mma16816(acc[kx][0][2], a0, b2[0], b2[1]);
+        mma16816(acc[kx][1][0], a1, b01[0], b01[1]);
+        mma16816(acc[kx][1][1], a1, b01[2], b01[3]);
+        mma16816(acc[kx][1][2], a1, b2[0], b2[1]);
+      }
+    }
+  }
+  // partials: torch layout inside the slab, element (co, ci, tap) at (co * 24 + ci) * 9 + tap
+  float* dst = p.part + (static_cast<long long>(slab) * gridDim.x + blockIdx.x) * SLAB_W;
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int co = m * 16 + gq + (e >> 1) * 8;
+          const int ci = n * 8 + 2 * t4 + (e & 1);
+          if (co < GW) dst[((group * GW + co) * GW + ci) * 9 + ky * 3 + kx] = acc[kx][m][n][e];
+        }
+}
+
+__global__ void __launch_bounds__(256) gconv3x3_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
+                                                                    int ctas, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long slab = i / SLAB_W, e = i - slab * SLAB_W;
+  const float* src = part + slab * ctas * SLAB_W + e;
+  float a = 0.f;
+  for (int k = 0; k < ctas; ++k) a += src[static_cast<long long>(k) * SLAB_W];
+  dw[i] += a;
+}
+
 }  // namespace
+
+static void gconv_tile(int stride, int wo, int* tw_log2, int* th);
 
 extern "C" int tfpp_gconv3x3(const void* x, const void* w, void* out, const float* scale, const float* shift, int act,
                              float* stat_sum, float* stat_sq, int batch, int height, int width, int channels, int stride,
@@ -261,12 +400,9 @@ extern "C" int tfpp_gconv3x3(const void* x, const void* w, void* out, const floa
   p.scale = scale; p.shift = shift; p.act = act; p.stat_sum = stat_sum; p.stat_sq = stat_sq;
   p.B = batch; p.H = height; p.W = width; p.C = channels;
   p.Ho = height / stride; p.Wo = width / stride;
-  const int tpix = stride == 1 ? 256 : 64;
-  const int tw_max = stride == 1 ? 32 : 16;
-  int tw_log2 = 3;  // at least 8 wide (an m tile is 16 consecutive tile pixels: 1 or 2 rows)
-  while ((1 << tw_log2) < p.Wo && (1 << tw_log2) < tw_max) ++tw_log2;
+  int tw_log2;
+  gconv_tile(stride, p.Wo, &tw_log2, &p.th);
   p.tw_log2 = tw_log2;
-  p.th = tpix >> tw_log2;
   p.tiles_x = ceil_div(p.Wo, 1 << tw_log2);
   p.tiles_y = ceil_div(p.Ho, p.th);
   p.slabs = channels / SLAB_C;
@@ -282,6 +418,63 @@ extern "C" int tfpp_gconv3x3(const void* x, const void* w, void* out, const floa
   const int grid = static_cast<int>(items < 2 * TFPP_NUM_SMS ? items : 2 * TFPP_NUM_SMS);
   if (stride == 1) gconv3x3_kernel<1><<<grid, kThreadsG, smem, stream>>>(p);
   else gconv3x3_kernel<2><<<grid, kThreadsG, smem, stream>>>(p);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+static void gconv_tile(int stride, int wo, int* tw_log2, int* th) {
+  const int tpix = stride == 1 ? 256 : 64;
+  const int tw_max = stride == 1 ? 32 : 16;
+  int l = 3;  // at least 8 wide (an m tile is 16 consecutive tile pixels: 1 or 2 rows)
+  while ((1 << l) < wo && (1 << l) < tw_max) ++l;
+  *tw_log2 = l;
+  *th = tpix >> l;
+}
+
+extern "C" long long tfpp_gconv3x3_wgrad_workspace(int batch, int height, int width, int channels, int stride) {
+  int l, th;
+  gconv_tile(stride, width / stride, &l, &th);
+  const long long tiles = static_cast<long long>(ceil_div(width / stride, 1 << l)) * ceil_div(height / stride, th) * batch;
+  const int slabs = channels / SLAB_C;
+  long long ctas = 2 * TFPP_NUM_SMS / slabs;
+  if (ctas < 1) ctas = 1;
+  if (ctas > tiles) ctas = tiles;
+  return ctas * slabs * SLAB_W;   // floats
+}
+
+extern "C" int tfpp_gconv3x3_wgrad(const void* dy, const void* x, float* dw, float* workspace, int batch, int height,
+                                   int width, int channels, int stride, tfpp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TFPP_CHECK_ARG(channels % SLAB_C == 0, "channels must be a multiple of 72 (3 groups of width 24)");
+  TFPP_CHECK_ARG(stride == 1 || stride == 2, "stride 1 or 2");
+  TFPP_CHECK_ARG(stride == 1 || (height % 2 == 0 && width % 2 == 0), "stride 2 needs even H, W");
+  GWgradParams p;
+  p.dy = static_cast<const bf16*>(dy); p.x = static_cast<const bf16*>(x); p.part = workspace;
+  p.B = batch; p.H = height; p.W = width; p.C = channels; p.Ho = height / stride; p.Wo = width / stride;
+  gconv_tile(stride, p.Wo, &p.tw_log2, &p.th);
+  p.tiles_x = ceil_div(p.Wo, 1 << p.tw_log2);
+  p.tiles_y = ceil_div(p.Ho, p.th);
+  const long long tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * batch;
+  if (tiles == 0) return TFPP_OK;
+  const int slabs = channels / SLAB_C;
+  long long ctas = 2 * TFPP_NUM_SMS / slabs;
+  if (ctas < 1) ctas = 1;
+  if (ctas > tiles) ctas = tiles;
+  const int tpix = stride == 1 ? 256 : 64;
+  const size_t smem = static_cast<size_t>(HALO_MAX + tpix) * PIX_BYTES;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gconv3x3_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HALO_MAX + 256) * PIX_BYTES);
+    cudaFuncSetAttribute(gconv3x3_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (HALO_MAX + 64) * PIX_BYTES);
+    attr = true;
+  }
+  dim3 grid(static_cast<unsigned>(ctas), slabs);
+  if (stride == 1) gconv3x3_wgrad_kernel<1><<<grid, kThreadsW, smem, stream>>>(p);
+  else gconv3x3_wgrad_kernel<2><<<grid, kThreadsW, smem, stream>>>(p);
+  TFPP_CHECK_LAUNCH();
+  const long long total = static_cast<long long>(slabs) * SLAB_W;
+  gconv3x3_wgrad_reduce_kernel<<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
+      workspace, dw, static_cast<int>(ctas), total);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

@@ -471,6 +471,19 @@ def gconv3x3(x, w, stride=1, scale=None, shift=None, act=ACT_NONE, stats=None):
   return out
 
 
+def gconv3x3_wgrad(dy, x, dw, stride=1):
+  """dw (C,24,3,3) f32 (torch layout, contiguous) += weight gradient of gconv3x3(x, w, stride) given dy."""
+  _dev(dy, BF16)
+  _dev(x, BF16)
+  b, h, wd, c = x.shape
+  assert dw.dtype == F32 and dw.is_contiguous() and dw.numel() == c * 24 * 9
+  lib = _lib.load()
+  ws = torch.empty(lib.tfpp_gconv3x3_wgrad_workspace(b, h, wd, c, stride), dtype=F32, device=x.device)
+  check(lib.tfpp_gconv3x3_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), b, h, wd, c, stride, _stream()),
+        'tfpp_gconv3x3_wgrad')
+  return dw
+
+
 def pack_gconv_halo(w, transpose=False, dt=BF16):
   """(C, 24, 3, 3) grouped conv weight -> (C/24, 9, 24, 24) = [group][ky*3+kx][out][in]; transpose=True gives the
   input-gradient operand: in/out swapped inside each group and the taps spatially flipped."""

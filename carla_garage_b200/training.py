@@ -285,18 +285,16 @@ class Backward:
     b, ho, wo, _ = draw.shape
     if grouped:  # RegNet 3x3 group conv; a = the full-resolution input whatever the stride
       gw = conv.weight.shape[1]
-      gout, gstr = st.g(conv.weight), (gw * 9, 1, 9)
+      gout = st.g(conv.weight)
+      ops.gconv3x3_wgrad(draw, a, gout, stride)
       if stride == 1:
-        ops.conv_wgrad(draw, a, taps=ops.TAPS_3X3, w_taps=9, group_width=gw, out=gout, out_strides=gstr)
         da = ops.gconv3x3(draw, packed(conv.weight, 'gconv_halo_t'))  # same kernel, transposed + flipped weights
         if id(a) in self.G:
           ops.add_bf16(self.G[id(a)], da, out=da)
         self.G[id(a)] = da
       else:
-        # stride 2: weight gradient against the parity planes of the input, input gradient as one implicit GEMM per
-        # input parity plane written at its positions of the full-resolution gradient
-        ops.conv_wgrad(draw, ops.parity_split(a), taps=ops.taps_3x3_stride2(b), w_taps=9, group_width=gw, out=gout,
-                       out_strides=gstr)
+        # stride 2: input gradient as one implicit GEMM per input parity plane, written at its positions of the
+        # full-resolution gradient
         wt = packed(conv.weight, 'gconv_t')
         gk = dict(k_per_tile=48, a_c_per_ntile=48, bn=48)
         h, w, c = a.shape[1], a.shape[2], a.shape[3]

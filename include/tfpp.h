@@ -286,6 +286,12 @@ int tfpp_gconv3x3(const void* x, const void* w, void* out, const float* scale, c
                   float* stat_sum, float* stat_sq, int batch, int height, int width, int channels, int stride,
                   tfpp_stream_t stream);
 
+/* Weight gradient of tfpp_gconv3x3: dw (C,24,3,3) f32 torch layout += sum over pixels of dY x X inside each group.
+ * workspace: tfpp_gconv3x3_wgrad_workspace(...) floats of scratch (per-CTA partial sums, reduced without atomics). */
+long long tfpp_gconv3x3_wgrad_workspace(int batch, int height, int width, int channels, int stride);
+int tfpp_gconv3x3_wgrad(const void* dy, const void* x, float* dw, float* workspace, int batch, int height, int width,
+                        int channels, int stride, tfpp_stream_t stream);
+
 /* Weight-pack refresh: out[i] = idx[i] >= 0 ? flat[idx[i]] : 0 for i < n (n % 8 == 0), cast to bf16 (out_f32 = 0) or
  * kept fp32.  One launch rebuilds every kernel-layout weight copy after the optimizer step; replaces the implicit
  * per-module weight reads of torch's conv / linear kernels (team_code/train.py:898-908 loop). */

@@ -450,3 +450,17 @@ def test_gconv3x3_input_gradient(ops, b, h, w, c):
   F.conv2d(x, bf(wt).float(), padding=1, groups=c // 24).backward(dy.float().permute(0, 3, 1, 2))
   got = ops.gconv3x3(dy, ops.pack_gconv_halo(wt, transpose=True))
   assert rel(got.float().permute(0, 3, 1, 2), x.grad) < 4e-3
+
+
+@pytest.mark.parametrize('b,h,w,c,stride', [(2, 16, 32, 72, 1), (3, 8, 8, 216, 1), (2, 24, 20, 144, 1), (2, 32, 64, 72, 2),
+                                            (1, 16, 16, 216, 2), (2, 12, 40, 72, 2)])
+def test_gconv3x3_weight_gradient(ops, b, h, w, c, stride):
+  """tfpp_gconv3x3_wgrad (+= into the torch-layout gradient) against autograd of F.conv2d(groups=C/24)."""
+  x = bf(rnd(b, h, w, c, seed=1))
+  dy = bf(rnd(b, h // stride, w // stride, c, seed=2))
+  wt = rnd(c, 24, 3, 3, seed=3, scale=0.1).requires_grad_(True)
+  F.conv2d(x.float().permute(0, 3, 1, 2), wt, stride=stride, padding=1, groups=c // 24).backward(
+      dy.float().permute(0, 3, 1, 2))
+  dw = torch.full((c, 24, 3, 3), 0.5, device='cuda')
+  ops.gconv3x3_wgrad(dy, x, dw, stride)
+  assert rel(dw - 0.5, wt.grad) < 3e-3

@@ -20,6 +20,11 @@ elif which == 'grouped':
   x = torch.randn(32, 64, 256, 72, device='cuda').to(torch.bfloat16)
   wp = ops.pack_grouped_conv_weight(torch.randn(72, 24, 3, 3, device='cuda'))
   f = lambda: ops.conv_gemm(x, wp, taps=ops.TAPS_3X3, k_per_tile=48, a_c_per_ntile=48, bn=48)
+elif which == 'gconv':
+  x = torch.randn(32, 64, 256, 72, device='cuda').to(torch.bfloat16)
+  wp = ops.pack_gconv_halo(torch.randn(72, 24, 3, 3, device='cuda'))
+  st = (torch.zeros(72, device='cuda'), torch.zeros(72, device='cuda'))
+  f = lambda: ops.gconv3x3(x, wp, 1, stats=st)
 elif which == 'ssa':
   x = torch.randn(32, 64, 256, 72, device='cuda').to(torch.bfloat16); y = torch.empty_like(x)
   sc, sh = torch.rand(72, device='cuda'), torch.rand(72, device='cuda')
