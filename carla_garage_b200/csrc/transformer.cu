@@ -39,162 +39,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   }
 }
 
-// ------------------------------------------------------------------------------------------------ fusion attention
-// SelfAttention core, transfuser.py:367-376: per (batch, head): softmax(Q K^T / sqrt(hd)) V over T <= 320 tokens.
-// qkv is the fused projection output (B, T, 3C) bf16 laid out [q | k | v], head h owning channels [h*hd, (h+1)*hd).
-// One CTA per (64-query tile, head, batch); 8 warps.  Scores never leave the SM:
-//   pass 1  S = Q K^T on mma.sync m16n8k16 (bf16 in, fp32 accumulate), hd streamed in 64-wide chunks through smem
-//   pass 2  row softmax with warp shuffles (fp32), probabilities kept as bf16 in smem
-//   pass 3  O = P V on mma.sync, V streamed in 64-column chunks (stored transposed in smem)
-constexpr int kAttT = 320;          // max tokens
-constexpr int kAttQ = 64;           // queries per CTA
-constexpr int kAttChunk = 64;       // head-dim chunk
-constexpr int kAttPitchK = kAttChunk + 8;   // bf16 elements per smem row of Q/K chunk (bank-conflict-free)
-constexpr int kAttPitchP = kAttT + 8;       // bf16 elements per row of P / Vt
-constexpr int kAttPitchS = kAttT + 4;       // fp32 elements per row of S
-
-__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, const uint32_t* b) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
-__global__ void __launch_bounds__(256) fusion_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T,
-                                                          int C, int heads, float scale) {
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  float* S = reinterpret_cast<float*>(att_smem);                                   // [64][kAttPitchS]
-  bf16* P = reinterpret_cast<bf16*>(S + kAttQ * kAttPitchS);                       // [64][kAttPitchP]
-  bf16* KV = P + kAttQ * kAttPitchP;                                               // K chunk [320][72] / Vt [64][328]
-  bf16* Qs = KV + kAttT * kAttPitchK;                                              // [64][72]
-  const int hd = C / heads;
-  const int q0 = blockIdx.x * kAttQ, h = blockIdx.y, b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-  const long long row_stride = 3ll * C;
-  const bf16* base = qkv + static_cast<long long>(b) * T * row_stride;
-  const int n_chunks = (hd + kAttChunk - 1) / kAttChunk;
-  const int Tp = (T + 15) & ~15;
-
-  // ---- pass 1: S = Q K^T.  warp -> (16-row block rb, key half kh)
-  const int rb = warp & 3, kh = warp >> 2;
-  const int keys_per_half = Tp / 2;                 // multiple of 8 (T multiple of 16)
-  const int ntile_max = (kAttT / 2) / 8;            // 20
-  float acc[ntile_max][4];
-#pragma unroll
-  for (int i = 0; i < ntile_max; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  const int ntiles = keys_per_half / 8;
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    const int d0 = ch * kAttChunk;
-    __syncthreads();
-    // stage Q chunk (64 x 64) and K chunk (Tp x 64) as bf16 pairs; zero beyond hd / beyond T
-    for (int i = threadIdx.x; i < kAttQ * (kAttChunk / 2); i += blockDim.x) {
-      const int r = i / (kAttChunk / 2), d = (i % (kAttChunk / 2)) * 2;
-      uint32_t v = 0;
-      if (q0 + r < T && d0 + d < hd)
-        v = *reinterpret_cast<const uint32_t*>(base + (q0 + r) * row_stride + h * hd + d0 + d);
-      *reinterpret_cast<uint32_t*>(Qs + r * kAttPitchK + d) = v;
-    }
-    for (int i = threadIdx.x; i < Tp * (kAttChunk / 2); i += blockDim.x) {
-      const int r = i / (kAttChunk / 2), d = (i % (kAttChunk / 2)) * 2;
-      uint32_t v = 0;
-      if (r < T && d0 + d < hd) v = *reinterpret_cast<const uint32_t*>(base + r * row_stride + C + h * hd + d0 + d);
-      *reinterpret_cast<uint32_t*>(KV + r * kAttPitchK + d) = v;
-    }
-    __syncthreads();
-    const int kmax = min(kAttChunk, ((hd - d0) + 15) & ~15);
-    for (int k0 = 0; k0 < kmax; k0 += 16) {
-      uint32_t a[4];
-      const bf16* qp = Qs + (rb * 16 + g) * kAttPitchK + k0 + 2 * t4;
-      a[0] = *reinterpret_cast<const uint32_t*>(qp);
-      a[1] = *reinterpret_cast<const uint32_t*>(qp + 8 * kAttPitchK);
-      a[2] = *reinterpret_cast<const uint32_t*>(qp + 8);
-      a[3] = *reinterpret_cast<const uint32_t*>(qp + 8 * kAttPitchK + 8);
-#pragma unroll
-      for (int nt = 0; nt < ntile_max; ++nt) {
-        if (nt < ntiles) {
-          const bf16* kp = KV + (kh * keys_per_half + nt * 8 + g) * kAttPitchK + k0 + 2 * t4;
-          uint32_t bfrag[2];
-          bfrag[0] = *reinterpret_cast<const uint32_t*>(kp);
-          bfrag[1] = *reinterpret_cast<const uint32_t*>(kp + 8);
-          mma_bf16_16816(acc[nt], a, bfrag);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int nt = 0; nt < ntile_max; ++nt) {
-    if (nt < ntiles) {
-      const int col = kh * keys_per_half + nt * 8 + 2 * t4;
-      float* s0 = S + (rb * 16 + g) * kAttPitchS + col;
-      s0[0] = acc[nt][0] * scale;
-      s0[1] = acc[nt][1] * scale;
-      s0[8 * kAttPitchS] = acc[nt][2] * scale;
-      s0[8 * kAttPitchS + 1] = acc[nt][3] * scale;
-    }
-  }
-  __syncthreads();
-
-  // ---- pass 2: softmax over keys (F.softmax(dim=-1), transfuser.py:373); warp per row, 8 rows per warp
-  for (int r = warp; r < kAttQ; r += 8) {
-    const float* srow = S + r * kAttPitchS;
-    float m = -INFINITY;
-    for (int c = lane; c < T; c += 32) m = fmaxf(m, srow[c]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int c = lane; c < T; c += 32) sum += __expf(srow[c] - m);
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    bf16* prow = P + r * kAttPitchP;
-    for (int c = lane; c < Tp; c += 32) prow[c] = f2bf(c < T ? __expf(srow[c] - m) * inv : 0.f);
-  }
-
-  // ---- pass 3: O = P V, 64 output columns at a time; warp -> (row block rb, 32-column half kh)
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    const int d0 = ch * kAttChunk;
-    __syncthreads();
-    // stage V chunk transposed: Vt[col][key]
-    for (int i = threadIdx.x; i < Tp * (kAttChunk / 2); i += blockDim.x) {
-      const int r = i / (kAttChunk / 2), d = (i % (kAttChunk / 2)) * 2;
-      uint32_t v = 0;
-      if (r < T && d0 + d < hd)
-        v = *reinterpret_cast<const uint32_t*>(base + r * row_stride + 2 * C + h * hd + d0 + d);
-      const __nv_bfloat162 pr = *reinterpret_cast<__nv_bfloat162*>(&v);
-      KV[d * kAttPitchP + r] = pr.x;
-      KV[(d + 1) * kAttPitchP + r] = pr.y;
-    }
-    __syncthreads();
-    float o[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    for (int k0 = 0; k0 < Tp; k0 += 16) {
-      uint32_t a[4];
-      const bf16* pp = P + (rb * 16 + g) * kAttPitchP + k0 + 2 * t4;
-      a[0] = *reinterpret_cast<const uint32_t*>(pp);
-      a[1] = *reinterpret_cast<const uint32_t*>(pp + 8 * kAttPitchP);
-      a[2] = *reinterpret_cast<const uint32_t*>(pp + 8);
-      a[3] = *reinterpret_cast<const uint32_t*>(pp + 8 * kAttPitchP + 8);
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const bf16* vp = KV + (kh * 32 + nt * 8 + g) * kAttPitchP + k0 + 2 * t4;
-        uint32_t bfrag[2];
-        bfrag[0] = *reinterpret_cast<const uint32_t*>(vp);
-        bfrag[1] = *reinterpret_cast<const uint32_t*>(vp + 8);
-        mma_bf16_16816(o[nt], a, bfrag);
-      }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int col = d0 + kh * 32 + nt * 8 + 2 * t4;
-      if (col < hd) {  // hd is even, so col + 1 < hd as well
-        const int r0 = q0 + rb * 16 + g;
-        bf16* op = out + (static_cast<long long>(b) * T + r0) * C + h * hd + col;
-        if (r0 < T) *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(o[nt][0], o[nt][1]);
-        if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(op + 8ll * C) = pack_bf16x2(o[nt][2], o[nt][3]);
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ decoder attention
 // nn.MultiheadAttention core inside nn.TransformerDecoderLayer (model.py:137-143): Tq <= 16 queries, Tk <= 128 keys,
 // head_dim 32.  One CTA per (batch, head), one warp per query row.  q/k/v are row-strided f32 or bf16 views.
@@ -393,30 +237,6 @@ extern "C" int tfpp_layernorm(const void* x, int x_f32, const float* gamma, cons
   STREAM;
   layernorm_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, x_f32, gamma, beta, static_cast<bf16*>(y_bf16), y_f32,
                                                           save_mean, save_rstd, rows, channels, eps);
-  TFPP_CHECK_LAUNCH();
-  return TFPP_OK;
-}
-
-extern "C" int tfpp_fusion_attn(const void* qkv, void* out, int batch, int tokens, int channels, int heads,
-                                tfpp_stream_t stream_) {
-  STREAM;
-  TFPP_CHECK_ARG(tokens <= kAttT && tokens % 16 == 0, "tokens must be a multiple of 16 and <= 320");
-  TFPP_CHECK_ARG(channels % heads == 0 && (channels / heads) % 2 == 0, "even head dim required");
-  const size_t smem = sizeof(float) * kAttQ * kAttPitchS + sizeof(bf16) * (kAttQ * kAttPitchP + kAttT * kAttPitchK +
-                                                                            kAttQ * kAttPitchK);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fusion_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (e != cudaSuccess) {
-      tfpp_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return TFPP_ERR_CUDA;
-    }
-    attr_set = true;
-  }
-  const int hd = channels / heads;
-  dim3 grid(ceil_div(tokens, kAttQ), heads, batch);
-  fusion_attn_kernel<<<grid, 256, smem, stream>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), tokens,
-                                                  channels, heads, 1.0f / sqrtf(static_cast<float>(hd)));
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

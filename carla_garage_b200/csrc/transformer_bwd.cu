@@ -52,313 +52,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
   }
 }
 
-// ------------------------------------------------------------------------------------------------ fusion attention bwd
-// Per (64-query tile, head, batch): recompute P = softmax(Q K^T * scale); dP = dO V^T; dS = P * (dP - rowsum(dP * P));
-// dQ = dS K * scale (written, bf16); dK += dS^T Q * scale, dV += P^T dO (fp32 atomics into dkv (B,T,2C): the key/value
-// gradients of one head receive contributions from all 5 query tiles).  mma.sync m16n8k16 bf16, fp32 accumulate.
-constexpr int kAttT = 320;
-constexpr int kAttQ = 64;
-constexpr int kChunk = 64;
-constexpr int kPitchK = kChunk + 8;   // bf16 row pitch of [rows][64] staging tiles
-constexpr int kPitchT = kAttT + 8;    // bf16 row pitch of [64][320] tiles
-constexpr int kPitchS = kAttT + 4;    // f32 row pitch of [64][320]
-constexpr int kPitchQ = kAttQ + 8;    // bf16 row pitch of [rows][64 queries] transposed tiles
-
-__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, const uint32_t* b) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ void load_a(uint32_t* a, const bf16* tile, int pitch, int r0, int k0, int g, int t4) {
-  const bf16* p = tile + (r0 + g) * pitch + k0 + 2 * t4;
-  a[0] = *reinterpret_cast<const uint32_t*>(p);
-  a[1] = *reinterpret_cast<const uint32_t*>(p + 8 * pitch);
-  a[2] = *reinterpret_cast<const uint32_t*>(p + 8);
-  a[3] = *reinterpret_cast<const uint32_t*>(p + 8 * pitch + 8);
-}
-__device__ __forceinline__ void load_b(uint32_t* b, const bf16* tile, int pitch, int n0, int k0, int g, int t4) {
-  const bf16* p = tile + (n0 + g) * pitch + k0 + 2 * t4;
-  b[0] = *reinterpret_cast<const uint32_t*>(p);
-  b[1] = *reinterpret_cast<const uint32_t*>(p + 8);
-}
-
-// stage rows [r_begin, r_begin + nrows) x 64 head-dim columns [d0, d0+64) of a (.., 3C) / (.., C) matrix into
-// tile[r][d] (bf16 pairs), zero outside [0,T) x [0,hd)
-__device__ __forceinline__ void stage_rows(bf16* tile, int pitch, const bf16* src, long long row_stride, int col0,
-                                           int r_begin, int nrows, int T, int d0, int hd) {
-  for (int i = threadIdx.x; i < nrows * (kChunk / 2); i += blockDim.x) {
-    const int r = i / (kChunk / 2), d = (i % (kChunk / 2)) * 2;
-    uint32_t v = 0;
-    if (r_begin + r < T && d0 + d < hd)
-      v = *reinterpret_cast<const uint32_t*>(src + (r_begin + r) * row_stride + col0 + d0 + d);
-    *reinterpret_cast<uint32_t*>(tile + r * pitch + d) = v;
-  }
-}
-// same but transposed: tile[d][r]
-__device__ __forceinline__ void stage_rows_t(bf16* tile, int pitch, const bf16* src, long long row_stride, int col0,
-                                             int r_begin, int nrows, int T, int d0, int hd) {
-  for (int i = threadIdx.x; i < nrows * (kChunk / 2); i += blockDim.x) {
-    const int r = i / (kChunk / 2), d = (i % (kChunk / 2)) * 2;
-    uint32_t v = 0;
-    if (r_begin + r < T && d0 + d < hd)
-      v = *reinterpret_cast<const uint32_t*>(src + (r_begin + r) * row_stride + col0 + d0 + d);
-    const __nv_bfloat162 pr = *reinterpret_cast<__nv_bfloat162*>(&v);
-    tile[d * pitch + r] = pr.x;
-    tile[(d + 1) * pitch + r] = pr.y;
-  }
-}
-
-__global__ void __launch_bounds__(256) fusion_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                                                              bf16* __restrict__ dqkv, float* __restrict__ dkv, int T,
-                                                              int C, int heads, float scale) {
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  bf16* dS = reinterpret_cast<bf16*>(att_smem);             // [64][kPitchT]   P (bf16), then dS in place
-  bf16* PT = dS + kAttQ * kPitchT;                          // [320][kPitchQ]  P^T
-  bf16* dST = PT + kAttT * kPitchQ;                         // [320][kPitchQ]  dS^T
-  bf16* KV = dST + kAttT * kPitchQ;                         // [320][kPitchK] K / V chunk, or [64][kPitchT] transposed
-  bf16* Qs = KV + kAttT * kPitchK;                          // [64][kPitchK] Q / dO chunk, or [64][kPitchQ] transposed
-  float* scratch = reinterpret_cast<float*>(Qs + kAttQ * kPitchK);  // [2][64] cross-warp row reductions
-  const int hd = C / heads;
-  const int q0 = blockIdx.x * kAttQ, h = blockIdx.y, b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-  const long long rs3 = 3ll * C;
-  const bf16* base = qkv + static_cast<long long>(b) * T * rs3;
-  const bf16* dob = dout + static_cast<long long>(b) * T * C;
-  const int n_chunks = (hd + kChunk - 1) / kChunk;
-  const int Tp = (T + 15) & ~15;
-  const int rb = warp & 3, kh = warp >> 2;
-  const int keys_half = Tp / 2, ntiles = keys_half / 8;
-  constexpr int kNt = (kAttT / 2) / 8;  // 20
-  const int r0 = rb * 16 + g;           // this thread's rows: r0 and r0 + 8
-
-  // cross-warp (two key halves) row reduction helper: quad shuffle, then shared scratch
-  auto row_reduce = [&](float v0, float v1, bool is_max, float& o0, float& o1) {
-    if (is_max) {
-      v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
-      v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 2));
-      v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
-      v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 2));
-    } else {
-      v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
-      v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
-      v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-      v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-    }
-    __syncthreads();
-    if (t4 == 0) {
-      scratch[kh * kAttQ + r0] = v0;
-      scratch[kh * kAttQ + r0 + 8] = v1;
-    }
-    __syncthreads();
-    if (is_max) {
-      o0 = fmaxf(scratch[r0], scratch[kAttQ + r0]);
-      o1 = fmaxf(scratch[r0 + 8], scratch[kAttQ + r0 + 8]);
-    } else {
-      o0 = scratch[r0] + scratch[kAttQ + r0];
-      o1 = scratch[r0 + 8] + scratch[kAttQ + r0 + 8];
-    }
-  };
-
-  // ---- two [64 x T] products with the same structure: S = Q K^T (pass 0) and dP = dO V^T (pass 1)
-  for (int pass = 0; pass < 2; ++pass) {
-    float acc[kNt][4];
-#pragma unroll
-    for (int i = 0; i < kNt; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int d0 = ch * kChunk;
-      __syncthreads();
-      if (pass == 0) {
-        stage_rows(Qs, kPitchK, base, rs3, h * hd, q0, kAttQ, T, d0, hd);
-        stage_rows(KV, kPitchK, base, rs3, C + h * hd, 0, Tp, T, d0, hd);
-      } else {
-        stage_rows(Qs, kPitchK, dob, C, h * hd, q0, kAttQ, T, d0, hd);
-        stage_rows(KV, kPitchK, base, rs3, 2 * C + h * hd, 0, Tp, T, d0, hd);
-      }
-      __syncthreads();
-      const int kmax = min(kChunk, ((hd - d0) + 15) & ~15);
-      for (int k0 = 0; k0 < kmax; k0 += 16) {
-        uint32_t a[4];
-        load_a(a, Qs, kPitchK, rb * 16, k0, g, t4);
-#pragma unroll
-        for (int nt = 0; nt < kNt; ++nt) {
-          if (nt < ntiles) {
-            uint32_t bf[2];
-            load_b(bf, KV, kPitchK, kh * keys_half + nt * 8, k0, g, t4);
-            mma16816(acc[nt], a, bf);
-          }
-        }
-      }
-    }
-    if (pass == 0) {
-      // softmax over keys, all in registers (+ two cross-warp reductions); P -> dS buffer (row major) and P^T
-      float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < kNt; ++nt) {
-        if (nt < ntiles) {
-          const int col = kh * keys_half + nt * 8 + 2 * t4;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc[nt][e] = (col + (e & 1) < T) ? acc[nt][e] * scale : -INFINITY;
-          }
-          m0 = fmaxf(m0, fmaxf(acc[nt][0], acc[nt][1]));
-          m1 = fmaxf(m1, fmaxf(acc[nt][2], acc[nt][3]));
-        }
-      }
-      float M0, M1;
-      row_reduce(m0, m1, true, M0, M1);
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < kNt; ++nt) {
-        if (nt < ntiles) {
-          acc[nt][0] = __expf(acc[nt][0] - M0);
-          acc[nt][1] = __expf(acc[nt][1] - M0);
-          acc[nt][2] = __expf(acc[nt][2] - M1);
-          acc[nt][3] = __expf(acc[nt][3] - M1);
-          s0 += acc[nt][0] + acc[nt][1];
-          s1 += acc[nt][2] + acc[nt][3];
-        }
-      }
-      float S0, S1;
-      row_reduce(s0, s1, false, S0, S1);
-      const float i0 = 1.f / S0, i1 = 1.f / S1;
-#pragma unroll
-      for (int nt = 0; nt < kNt; ++nt) {
-        if (nt < ntiles) {
-          const int col = kh * keys_half + nt * 8 + 2 * t4;
-          const float p00 = acc[nt][0] * i0, p01 = acc[nt][1] * i0, p10 = acc[nt][2] * i1, p11 = acc[nt][3] * i1;
-          *reinterpret_cast<uint32_t*>(dS + r0 * kPitchT + col) = pack_bf16x2(p00, p01);
-          *reinterpret_cast<uint32_t*>(dS + (r0 + 8) * kPitchT + col) = pack_bf16x2(p10, p11);
-          PT[col * kPitchQ + r0] = f2bf(p00);
-          PT[(col + 1) * kPitchQ + r0] = f2bf(p01);
-          PT[col * kPitchQ + r0 + 8] = f2bf(p10);
-          PT[(col + 1) * kPitchQ + r0 + 8] = f2bf(p11);
-        }
-      }
-    } else {
-      // dS = P * (dP - rowsum(dP * P)) * scale, in place over P (each thread touches only its own fragment slots)
-      float part0 = 0.f, part1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < kNt; ++nt) {
-        if (nt < ntiles) {
-          const int col = kh * keys_half + nt * 8 + 2 * t4;
-          const float2 pa = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dS + r0 * kPitchT + col));
-          const float2 pb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dS + (r0 + 8) * kPitchT + col));
-          part0 += acc[nt][0] * pa.x + acc[nt][1] * pa.y;
-          part1 += acc[nt][2] * pb.x + acc[nt][3] * pb.y;
-        }
-      }
-      float rs0, rs1;
-      row_reduce(part0, part1, false, rs0, rs1);
-#pragma unroll
-      for (int nt = 0; nt < kNt; ++nt) {
-        if (nt < ntiles) {
-          const int col = kh * keys_half + nt * 8 + 2 * t4;
-          const float2 pa = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dS + r0 * kPitchT + col));
-          const float2 pb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dS + (r0 + 8) * kPitchT + col));
-          const float v00 = pa.x * (acc[nt][0] - rs0) * scale, v01 = pa.y * (acc[nt][1] - rs0) * scale;
-          const float v10 = pb.x * (acc[nt][2] - rs1) * scale, v11 = pb.y * (acc[nt][3] - rs1) * scale;
-          *reinterpret_cast<uint32_t*>(dS + r0 * kPitchT + col) = pack_bf16x2(v00, v01);
-          *reinterpret_cast<uint32_t*>(dS + (r0 + 8) * kPitchT + col) = pack_bf16x2(v10, v11);
-          dST[col * kPitchQ + r0] = f2bf(v00);
-          dST[(col + 1) * kPitchQ + r0] = f2bf(v01);
-          dST[col * kPitchQ + r0 + 8] = f2bf(v10);
-          dST[(col + 1) * kPitchQ + r0 + 8] = f2bf(v11);
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- dQ = dS K  (64 x hd): per 64-column chunk; B operand = K^T chunk staged transposed [d][key]
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    const int d0 = ch * kChunk;
-    __syncthreads();
-    stage_rows_t(KV, kPitchT, base, rs3, C + h * hd, 0, Tp, T, d0, hd);
-    __syncthreads();
-    float o[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    for (int k0 = 0; k0 < Tp; k0 += 16) {
-      uint32_t a[4];
-      load_a(a, dS, kPitchT, rb * 16, k0, g, t4);
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        uint32_t bf[2];
-        load_b(bf, KV, kPitchT, kh * 32 + nt * 8, k0, g, t4);
-        mma16816(o[nt], a, bf);
-      }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int col = d0 + kh * 32 + nt * 8 + 2 * t4;
-      if (col < hd) {
-        const int qr = q0 + r0;
-        bf16* op = dqkv + (static_cast<long long>(b) * T + qr) * rs3 + h * hd + col;
-        if (qr < T) *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(o[nt][0], o[nt][1]);
-        if (qr + 8 < T) *reinterpret_cast<uint32_t*>(op + 8 * rs3) = pack_bf16x2(o[nt][2], o[nt][3]);
-      }
-    }
-  }
-
-  // ---- dK += dS^T Q  and  dV += P^T dO  (T x hd each, contraction over this CTA's 64 queries)
-  // A = dS^T / P^T [key][q]; B = Q^T / dO^T chunk staged transposed [d][q]; warp w owns keys [w*40, w*40+40)? T/8
-  // warps is not a multiple of 16 in general, so each warp walks 16-key blocks round-robin.
-  for (int which = 0; which < 2; ++which) {
-    const bf16* A = which == 0 ? dST : PT;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int d0 = ch * kChunk;
-      __syncthreads();
-      if (which == 0) stage_rows_t(Qs, kPitchQ, base, rs3, h * hd, q0, kAttQ, T, d0, hd);
-      else stage_rows_t(Qs, kPitchQ, dob, C, h * hd, q0, kAttQ, T, d0, hd);
-      __syncthreads();
-      for (int kb = warp; kb < Tp / 16; kb += 8) {
-        float o[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-#pragma unroll
-        for (int k0 = 0; k0 < kAttQ; k0 += 16) {
-          uint32_t a[4];
-          load_a(a, A, kPitchQ, kb * 16, k0, g, t4);
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt) {
-            uint32_t bf[2];
-            load_b(bf, Qs, kPitchQ, nt * 8, k0, g, t4);
-            mma16816(o[nt], a, bf);
-          }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          const int col = d0 + nt * 8 + 2 * t4;
-          if (col < hd) {
-            const int key = kb * 16 + g;
-            float* op = dkv + (static_cast<long long>(b) * T + key) * (2ll * C) + which * C + h * hd + col;
-            if (key < T) {
-              atomicAdd(op, o[nt][0]);
-              atomicAdd(op + 1, o[nt][1]);
-            }
-            if (key + 8 < T) {
-              atomicAdd(op + 8 * 2ll * C, o[nt][2]);
-              atomicAdd(op + 8 * 2ll * C + 1, o[nt][3]);
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
-// dqkv[:, :, C:3C] = bf16(dkv)
-__global__ void __launch_bounds__(256) dkv_cast_kernel(const float* __restrict__ dkv, bf16* __restrict__ dqkv,
-                                                       long long rows, int C) {
-  const long long total = rows * 2 * C;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const long long r = i / (2 * C);
-  const int c = static_cast<int>(i % (2 * C));
-  dqkv[r * 3 * C + C + c] = f2bf(dkv[i]);
-}
-
 // ------------------------------------------------------------------------------------------------ decoder attention bwd
 // One CTA per (batch, head); everything in fp32 shared memory (Tq <= 16, Tk <= 128, hd <= 64).
 __global__ void __launch_bounds__(256) small_mha_bwd_kernel(const bf16* __restrict__ q, long long q_sb, long long q_sr,
@@ -700,41 +393,6 @@ extern "C" int tfpp_layernorm_bwd(const void* dy, int dy_f32, const float* x, co
   STREAM;
   layernorm_bwd_kernel<<<ceil_div(rows, 8), 256, sizeof(float) * 2 * channels, stream>>>(
       dy, dy_f32, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, rows, channels);
-  TFPP_CHECK_LAUNCH();
-  return TFPP_OK;
-}
-
-extern "C" int tfpp_fusion_attn_bwd(const void* qkv, const void* dout, void* dqkv, float* dkv_ws, int batch, int tokens,
-                                    int channels, int heads, tfpp_stream_t stream_) {
-  STREAM;
-  TFPP_CHECK_ARG(tokens <= kAttT && tokens % 16 == 0, "tokens must be a multiple of 16 and <= 320");
-  TFPP_CHECK_ARG(channels % heads == 0 && (channels / heads) % 2 == 0, "even head dim required");
-  const size_t smem = sizeof(bf16) * (kAttQ * kPitchT + 2 * kAttT * kPitchQ + kAttT * kPitchK + kAttQ * kPitchK) +
-                      sizeof(float) * 2 * kAttQ;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fusion_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      tfpp_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return TFPP_ERR_CUDA;
-    }
-    attr_set = true;
-  }
-  TFPP_CHECK_ARG(smem <= 227 * 1024, "fusion_attn_bwd shared memory budget exceeded");
-  cudaError_t e = cudaMemsetAsync(dkv_ws, 0, sizeof(float) * 2ull * channels * tokens * batch, stream);
-  if (e != cudaSuccess) {
-    tfpp_set_error("memset: %s", cudaGetErrorString(e));
-    return TFPP_ERR_CUDA;
-  }
-  const int hd = channels / heads;
-  dim3 grid(ceil_div(tokens, kAttQ), heads, batch);
-  fusion_attn_bwd_kernel<<<grid, 256, smem, stream>>>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout),
-                                                      static_cast<bf16*>(dqkv), dkv_ws, tokens, channels, heads,
-                                                      1.0f / sqrtf(static_cast<float>(hd)));
-  TFPP_CHECK_LAUNCH();
-  const long long rows = static_cast<long long>(batch) * tokens;
-  dkv_cast_kernel<<<static_cast<int>(ceil_div_ll(rows * 2 * channels, 256)), 256, 0, stream>>>(
-      dkv_ws, static_cast<bf16*>(dqkv), rows, channels);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

@@ -165,7 +165,7 @@ int tfpp_nhwc_bf16_to_nchw_f32(const void* x, float* y, int batch, int channels,
 int tfpp_layernorm(const void* x, int x_f32, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                    float* save_mean, float* save_rstd, int rows, int channels, float eps, tfpp_stream_t stream);
 
-/* SelfAttention core (transfuser.py:367-376): qkv (B,T,3C) bf16 [q|k|v] -> out (B,T,C) bf16. T<=320, T%16==0. */
+/* SelfAttention core (transfuser.py:367-376): qkv (B,T,3C) bf16 [q|k|v] -> out (B,T,C) bf16. T<=320, T%32==0. */
 int tfpp_fusion_attn(const void* qkv, void* out, int batch, int tokens, int channels, int heads, tfpp_stream_t stream);
 
 /* nn.MultiheadAttention core of the planner decoder (model.py:137-143): bf16 row-strided q/k/v views. */

@@ -200,8 +200,8 @@ def test_layernorm_attention(ops):
   yb, yf, _, _ = ops.layernorm(x, g, bt, want_f32=True)
   want = F.layer_norm(x, (c,), g, bt, 1e-5)
   assert rel(yf, want) < 1e-5 and rel(yb.float(), want) < 5e-3
-  for c in (72, 216, 576, 1512):
-    b, t, heads = 2, 320, 4
+  for c, b, t in ((72, 2, 320), (216, 2, 320), (576, 2, 320), (1512, 2, 320), (72, 3, 64), (216, 1, 160)):
+    heads = 4
     qkv = bf(rnd(b, t, 3 * c, seed=28))
     out = ops.fusion_attn(qkv, b, t, c, heads).view(b, t, c)
     q, k, v = [u.float().view(b, t, heads, c // heads).transpose(1, 2) for u in qkv.split(c, dim=2)]
@@ -464,3 +464,18 @@ def test_gconv3x3_weight_gradient(ops, b, h, w, c, stride):
   dw = torch.full((c, 24, 3, 3), 0.5, device='cuda')
   ops.gconv3x3_wgrad(dy, x, dw, stride)
   assert rel(dw - 0.5, wt.grad) < 3e-3
+
+
+@pytest.mark.parametrize('c,b,t', [(72, 2, 320), (216, 2, 320), (576, 1, 320), (1512, 1, 320), (72, 3, 64), (216, 1, 160)])
+def test_fusion_attention_backward(ops, c, b, t):
+  """tfpp_fusion_attn_bwd against autograd of softmax(QK^T/sqrt(hd))V on the same bf16 inputs."""
+  heads = 4
+  qkv = bf(rnd(b, t, 3 * c, seed=40))
+  dout = bf(rnd(b, t, c, seed=41))
+  x = qkv.float().requires_grad_(True)
+  q, k, v = [u.view(b, t, heads, c // heads).transpose(1, 2) for u in x.split(c, dim=2)]
+  att = F.softmax(q @ k.transpose(-2, -1) / math.sqrt(c // heads), dim=-1)
+  (att @ v).transpose(1, 2).reshape(b, t, c).backward(dout.float())
+  got = ops.fusion_attn_bwd(qkv, dout, b, t, c, heads).view(b, t, 3 * c).float()
+  for name, sl in (('dq', slice(0, c)), ('dk', slice(c, 2 * c)), ('dv', slice(2 * c, 3 * c))):
+    assert rel(got[..., sl], x.grad[..., sl]) < 2e-2, (name, c)
