@@ -20,7 +20,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                       // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                         // bf16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
@@ -50,6 +50,8 @@ struct KParams {
   int act, act_n_limit;
   float* stat_sum;
   float* stat_sq;
+  int fast_layout;   // bf16/fp32 NHWC output with unit channel stride, <= 1 residual of the same kind, none/ReLU
+  int stat_floats;   // 2 * n_tiles * bn when statistics are requested, else 0
 };
 
 struct TileCoord {
@@ -81,10 +83,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  float* trbuf = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // 4 x [32][33] epilogue transpose tiles
-  float2* saff = reinterpret_cast<float2*>(trbuf + 4 * 32 * 33);       // [256] per-tile {scale, shift}
-  float* sstat = reinterpret_cast<float*>(saff + 256);                 // [2][stat_stride] BatchNorm partial sums
-  const int stat_stride = p.n_tiles * p.bn;
+  float2* saff = reinterpret_cast<float2*>(bars + 2 * kMaxStages + 6);   // [256] per-tile {scale, shift}
+  float* sstat = reinterpret_cast<float*>(saff + 256);                   // [2][stat_stride] BatchNorm partial sums
+  float* trbuf = sstat + p.stat_floats;   // 8 x [32][33] epilogue transpose tiles (only when statistics / generic path)
+  const int stat_stride = p.stat_floats / 2;
   if (p.stat_sum != nullptr)
     for (int i = threadIdx.x; i < 2 * stat_stride; i += blockDim.x) sstat[i] = 0.f;
 
@@ -102,7 +104,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 4);
+      mbar_init(smem_u32(&tempty_bar[s]), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -180,28 +182,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ================================================================ epilogue (warps 2..5)
-    // One warp per SM sub-partition, so every instruction's latency is exposed: the hot path keeps ~2 instructions
-    // per output element (everything loop-invariant hoisted into registers / shared memory, no per-element
-    // predicates); a compact generic path (dynamic loops over a shared-memory copy of the slab) covers every other
-    // layout.  BatchNorm statistics: transpose the slab through shared memory so that lane == column and the
-    // column sums are plain register accumulations.
+    // ================================================================ epilogue (warps 2..9)
+    // Two warps per SM sub-partition share a 32-lane quarter of the accumulator and split its 32-column slabs between
+    // them (even / odd slab).  Every instruction's latency is exposed with so few warps, so the hot path keeps ~2
+    // instructions per output element: loop invariants hoisted, the per-tile affine staged in shared memory, output in
+    // 8-column groups (one 16-byte store for bf16, two for fp32) that also cover ragged last slabs.  A compact generic
+    // path (dynamic loops over a shared-memory copy of the slab) serves every other layout.  BatchNorm statistics:
+    // transpose the slab through shared memory so that lane == column and column sums are register accumulations.
+    const int ew = warp - 2;                     // 0..7
     const int lane_group = warp & 3;             // TMEM lanes [32*lane_group, +32) are accessible to this warp
+    const int half = ew >> 2;                    // slab parity owned by this warp
     const int row = lane_group * 32 + lane;      // tile row == pixel
     const int pix_per_img = p.th * p.tw;
-    float* tr = trbuf + (warp - 2) * (32 * 33);  // [32][33] fp32 transpose tile of this warp
-    // loop invariants in registers
+    float* tr = trbuf + ew * (32 * 33);          // [32][33] fp32 transpose tile of this warp (if allocated)
     const float* __restrict__ g_scale = p.scale;
     const float* __restrict__ g_shift = p.shift;
     const bool has_stats = p.stat_sum != nullptr;
     const bool has_affine = (g_scale != nullptr) || (g_shift != nullptr);
     const int act = p.act;
-    const bool fast_layout = p.out != nullptr && !p.out_f32 && p.o_sn == 1 && p.res2 == nullptr &&
-                             (p.res1 == nullptr || (p.r1_sn == 1)) && p.act_n_limit == 0 &&
-                             (act == ACT_NONE || act == ACT_RELU);
+    const bool fast_layout = p.fast_layout != 0;
+    const bool out_f32 = p.out_f32 != 0;
     const bf16* __restrict__ res_b = (p.res1 != nullptr && !p.res1_f32) ? static_cast<const bf16*>(p.res1) : nullptr;
     const float* __restrict__ res_f = (p.res1 != nullptr && p.res1_f32) ? static_cast<const float*>(p.res1) : nullptr;
     bf16* __restrict__ out_b = static_cast<bf16*>(p.out);
+    float* __restrict__ out_f = static_cast<float*>(p.out);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -220,31 +224,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int ncols = nend - t.n0;
       // per-tile affine (BatchNorm fold / bias) staged once in shared memory: {scale, shift} per column
       if (has_affine) {
-        asm volatile("bar.sync 2, 128;" ::: "memory");  // previous tile's readers are done
-        for (int i = (warp - 2) * 32 + lane; i < ncols; i += 128)
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // previous tile's readers are done
+        for (int i = ew * 32 + lane; i < ncols; i += 256)
           saff[i] = make_float2(g_scale ? __ldg(g_scale + t.n0 + i) : 1.f, g_shift ? __ldg(g_shift + t.n0 + i) : 0.f);
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
 
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + acc * kAccStride;
-      for (int c = 0; c < ncols; c += 32) {
+      for (int c = half * 32; c < ncols; c += 64) {
         uint32_t r[32];
         const int n = t.n0 + c;
-        const bool full = (c + 32 <= ncols);
-        // residual slab of this row (64 contiguous bytes of bf16 / 128 of f32): issue the loads before the TMEM wait
+        const int ng = min(4, (ncols - c) >> 3);   // 8-column groups of this slab that are real outputs (fast path)
+        // residual of this row's slab: issue the loads before the TMEM wait
         uint4 rq[4];
-        const bool fast = fast_layout && full;
-        if (fast && valid && res_b != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(res_b + r1_base + n);
+        float4 rf[8];
+        if (fast_layout && valid) {
+          if (res_b != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res_b + r1_base + n);
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) rq[qd] = __ldg(rp + qd);
+            for (int q = 0; q < 4; ++q)
+              if (q < ng) rq[q] = __ldg(rp + q);
+          } else if (res_f != nullptr) {
+            const float4* rp = reinterpret_cast<const float4*>(res_f + r1_base + n);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < 2 * ng) rf[q] = __ldg(rp + q);
+          }
         }
         __syncwarp();
         tmem_ld32_issue(taddr + c, r);
         tmem_ld_wait32(r);
-        if (has_stats || !fast) {
+        if (has_stats || !fast_layout) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(r[j]);
           __syncwarp();
@@ -252,58 +264,69 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (has_stats) {
           const int col = n + lane;
           float ssum = 0.f, ssq = 0.f;
+          if (valid_mask == 0xffffffffu) {
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            const float a = ((valid_mask >> rr) & 1u) ? tr[rr * 33 + lane] : 0.f;
-            ssum += a;
-            ssq = fmaf(a, a, ssq);
+            for (int rr = 0; rr < 32; ++rr) {
+              const float a = tr[rr * 33 + lane];
+              ssum += a;
+              ssq = fmaf(a, a, ssq);
+            }
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const float a = ((valid_mask >> rr) & 1u) ? tr[rr * 33 + lane] : 0.f;
+              ssum += a;
+              ssq = fmaf(a, a, ssq);
+            }
           }
           if (col < nend) {
             atomicAdd(&sstat[col], ssum);
             atomicAdd(&sstat[stat_stride + col], ssq);
           }
         }
-        if (fast) {
+        if (fast_layout) {
           if (valid) {
-            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (has_affine) {
+            for (int q = 0; q < 4; ++q) {
+              if (q < ng) {
+                float v[8];
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float4 a2 = *reinterpret_cast<const float4*>(&saff[c + j]);  // {sc0, sh0, sc1, sh1}, broadcast
-                v[j] = fmaf(v[j], a2.x, a2.y);
-                v[j + 1] = fmaf(v[j + 1], a2.z, a2.w);
-              }
-            }
-            if (res_b != nullptr) {
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+                if (has_affine) {
 #pragma unroll
-              for (int qd = 0; qd < 4; ++qd) {
-                const uint32_t w[4] = {rq[qd].x, rq[qd].y, rq[qd].z, rq[qd].w};
+                  for (int j = 0; j < 8; j += 2) {
+                    const float4 a2 = *reinterpret_cast<const float4*>(&saff[c + q * 8 + j]);  // {sc0, sh0, sc1, sh1}
+                    v[j] = fmaf(v[j], a2.x, a2.y);
+                    v[j + 1] = fmaf(v[j + 1], a2.z, a2.w);
+                  }
+                }
+                if (res_b != nullptr) {
+                  const uint32_t w[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = unpack_bf16x2(w[j]);
-                  v[qd * 8 + 2 * j] += f.x;
-                  v[qd * 8 + 2 * j + 1] += f.y;
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16x2(w[j]);
+                    v[2 * j] += f.x;
+                    v[2 * j + 1] += f.y;
+                  }
+                } else if (res_f != nullptr) {
+                  v[0] += rf[2 * q].x; v[1] += rf[2 * q].y; v[2] += rf[2 * q].z; v[3] += rf[2 * q].w;
+                  v[4] += rf[2 * q + 1].x; v[5] += rf[2 * q + 1].y; v[6] += rf[2 * q + 1].z; v[7] += rf[2 * q + 1].w;
+                }
+                if (act == ACT_RELU) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (out_f32) {
+                  float4* op = reinterpret_cast<float4*>(out_f + o_base + n + q * 8);
+                  op[0] = make_float4(v[0], v[1], v[2], v[3]);
+                  op[1] = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+                  *reinterpret_cast<uint4*>(out_b + o_base + n + q * 8) =
+                      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                 pack_bf16x2(v[6], v[7]));
                 }
               }
-            } else if (res_f != nullptr) {
-              const float4* rp = reinterpret_cast<const float4*>(res_f + r1_base + n);
-#pragma unroll
-              for (int qd = 0; qd < 8; ++qd) {
-                const float4 u = __ldg(rp + qd);
-                v[qd * 4] += u.x; v[qd * 4 + 1] += u.y; v[qd * 4 + 2] += u.z; v[qd * 4 + 3] += u.w;
-              }
             }
-            if (act == ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            uint4* op = reinterpret_cast<uint4*>(out_b + o_base + n);
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-              op[qd] = make_uint4(pack_bf16x2(v[qd * 8], v[qd * 8 + 1]), pack_bf16x2(v[qd * 8 + 2], v[qd * 8 + 3]),
-                                  pack_bf16x2(v[qd * 8 + 4], v[qd * 8 + 5]), pack_bf16x2(v[qd * 8 + 6], v[qd * 8 + 7]));
           }
         } else if (p.out != nullptr && valid) {
           // generic: walk the columns of this slab from the shared-memory copy (any strides / dtypes / tails)
@@ -325,7 +348,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               static_cast<bf16*>(p.out)[off] = f2bf(v);
           }
         }
-        if (has_stats || !fast) __syncwarp();  // the transpose tile is reused by the next slab
+        if (has_stats || !fast_layout) __syncwarp();  // the transpose tile is reused by the next slab
       }
       tc_fence_before();
       __syncwarp();
@@ -337,9 +360,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     if (p.stat_sum != nullptr) {
       // flush the per-CTA statistics: one global atomic per column per CTA instead of one per warp per tile
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = (warp - 2) * 32 + lane;
-      for (int i = et; i < p.n; i += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int et = ew * 32 + lane;
+      for (int i = et; i < p.n; i += 256) {
         const float a = sstat[i], b2 = sstat[stat_stride + i];
         if (a != 0.f || b2 != 0.f) {
           atomicAdd(p.stat_sum + i, a);
@@ -398,9 +421,6 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
   }
   p.b_stage_bytes = ((a->bn * kBlockK * 2 + 1023) / 1024) * 1024;
   const int stage_bytes = kABytes + p.b_stage_bytes;
-  int stages = (194 * 1024) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  p.stages = stages;
   p.out = a->out;
   p.out_f32 = a->out_f32;
   p.o_sb = a->o_sb; p.o_sy = a->o_sy; p.o_sx = a->o_sx; p.o_sn = a->o_sn;
@@ -434,11 +454,22 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
     if (rc) return rc;
   }
 
-  const size_t stat_bytes = a->stat_sum ? sizeof(float) * 2 * p.n_tiles * p.bn : 0;
+  p.fast_layout = a->out != nullptr && a->o_sn == 1 && a->res2 == nullptr && (a->res1 == nullptr || a->r1_sn == 1) &&
+                  a->act_n_limit == 0 && (a->act == ACT_NONE || a->act == ACT_RELU) && a->n % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->o_sx % 8 == 0 && a->o_sy % 8 == 0 && a->o_sb % 8 == 0 &&
+                  (a->res1 == nullptr || ((reinterpret_cast<uintptr_t>(a->res1) & 15) == 0 && a->r1_sx % 8 == 0 &&
+                                          a->r1_sy % 8 == 0 && a->r1_sb % 8 == 0));
+  p.stat_floats = a->stat_sum ? 2 * p.n_tiles * p.bn : 0;
+  const size_t stat_bytes = sizeof(float) * p.stat_floats;
   TFPP_CHECK_ARG(stat_bytes <= 13 * 1024, "too many channels for the shared-memory statistics buffer");
-  const size_t tr_bytes = 4 * 32 * 33 * sizeof(float) + 256 * sizeof(float2);
-  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + tr_bytes + stat_bytes;
-  TFPP_CHECK_ARG(smem_bytes <= 227 * 1024, "shared memory budget exceeded");
+  const bool need_tr = a->stat_sum != nullptr || !p.fast_layout;
+  const size_t tr_bytes = (need_tr ? 8 * 32 * 33 * sizeof(float) : 0) + 256 * sizeof(float2);
+  const size_t fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + tr_bytes + stat_bytes;
+  int stages = static_cast<int>((227 * 1024 - fixed_bytes) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  TFPP_CHECK_ARG(stages >= 2, "shared memory budget exceeded");
+  p.stages = stages;
+  const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + fixed_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -143,6 +143,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
       const bool row_ok = row < p.m_valid && co < p.cout;
       const int wt = p.tap_w[tap];
+      const bool vec_ok = !p.grouped && p.s_ci == 1 && (p.s_co & 3) == 0 && (p.s_tap & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;
       for (int c = 0; c < p.bn; c += 16) {
         float v[16];
         __syncwarp();
@@ -156,6 +158,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
             if (cw >= g0 && cw < g0 + p.group_width)
               atomicAdd(p.dw + co * p.s_co + wt * p.s_tap + (cw - g0) * p.s_ci, v[j]);
           }
+        } else if (vec_ok && ci0 + c + 16 <= p.cin) {
+          // contiguous input-channel axis (1x1 convs, linears): 16 floats of this row as four 16-byte reductions —
+          // the L2 atomic units are the bottleneck of the split-K epilogue, this issues a quarter of the operations
+          float* dst = p.dw + co * p.s_co + wt * p.s_tap + (ci0 + c);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
+                         "f"(v[j + 2]), "f"(v[j + 3])
+                         : "memory");
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {

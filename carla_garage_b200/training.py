@@ -36,11 +36,17 @@ class FlatState:
     by_name = dict(params)
     ordered, used = [], set()
 
-    def take(names):
+    starts = set()  # first parameter of every adjacency group / every ungrouped parameter: may be preceded by padding
+
+    def take(names, group=True):
+      first = True
       for n in names:
         if n in by_name and n not in used:
           ordered.append((n, by_name[n]))
           used.add(n)
+          if first or not group:
+            starts.add(n)
+          first = False
 
     for i in range(4):
       for l in range(len(model.backbone.transformers[i].blocks)):
@@ -52,22 +58,28 @@ class FlatState:
       take([f'head.{h}.0.weight' for h in heads])
       take([f'head.{h}.0.bias' for h in heads])
       take([f'head.{h}.2.bias' for h in heads])
-    take([n for n, _ in params])
+    take([n for n, _ in params], group=False)
     self.names = [n for n, _ in ordered]
     self.params = [p for _, p in ordered]
-    total = sum(p.numel() for p in self.params)
+    # matrices start on 16-byte boundaries (vector reductions / loads in the weight-gradient and pack kernels); the
+    # padding floats stay zero forever (zero gradient, zero AdamW update)
+    offs, off = [], 0
+    for n, p in ordered:
+      if n in starts and p.ndim >= 2:
+        off += (-off) % 4
+      offs.append(off)
+      off += p.numel()
+    total = off + ((-off) % 4)
     dev = self.params[0].device
-    self.flat = torch.empty(total, dtype=F32, device=dev)
+    self.flat = torch.zeros(total, dtype=F32, device=dev)
     self.grad = torch.zeros(total, dtype=F32, device=dev)
     self.offsets = {}
-    off = 0
-    for n, p in ordered:
+    for (n, p), off in zip(ordered, offs):
       k = p.numel()
       self.flat[off:off + k].copy_(p.detach().reshape(-1))
       p.data = self.flat[off:off + k].view(p.shape)
       p.grad = self.grad[off:off + k].view(p.shape)
       self.offsets[id(p)] = (off, k)
-      off += k
     self.exp_avg = torch.zeros_like(self.flat)
     self.exp_avg_sq = torch.zeros_like(self.flat)
     self.max_exp_avg_sq = torch.zeros_like(self.flat)

@@ -47,7 +47,11 @@ def test_flat_state_layout_cpu():
   heads = net.head.head_names()
   assert st.g_span(getattr(net.head, heads[0])[2].bias, getattr(net.head, heads[-1])[2].bias).numel() == 21
   n_train = sum(p.numel() for p in net.parameters() if p.requires_grad)
-  assert st.flat.numel() == n_train == 120351026 - 2 * 256 * 256
+  assert n_train == 120351026 - 2 * 256 * 256
+  assert n_train <= st.flat.numel() < n_train + 4 * len(st.params)  # 16-byte alignment padding before matrices only
+  for q in st.params:
+    if q.ndim >= 2 and q.numel() % 4 == 0:
+      assert (q.data_ptr() - st.flat.data_ptr()) % 16 == 0 and (q.grad.data_ptr() - st.grad.data_ptr()) % 16 == 0
   # parameters are views of the flat buffer, gradients of the flat gradient
   p = net.change_channel.weight
   assert p.data_ptr() >= st.flat.data_ptr() and p.grad.data_ptr() == st.g(p).data_ptr()
