@@ -245,6 +245,139 @@ __global__ void __launch_bounds__(kThreadsG, 2) gconv3x3_kernel(const GConvParam
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Input gradient of the stride-2 conv:  dX[iy, ix] = sum over the taps (ky, kx) with (iy + 1 - ky, ix + 1 - kx) even of
+// W[.,.,ky,kx]^T dY[(iy + 1 - ky) / 2, (ix + 1 - kx) / 2].  The four input parity classes (iy & 1, ix & 1) use 1, 2, 2
+// and 4 taps.  A CTA stages a (TU+1) x (TV+1) tile of dY once and produces the 2TU x 2TV tile of dX class by class:
+// an m tile is 16 consecutive pixels of one class (stride-1 rows in the dY tile), written back with pixel stride 2.
+// Weights: the same transposed / flipped pack as the stride-1 input gradient (tap' = (2-ky)*3 + (2-kx)).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsG, 2) gconv3x3_dgrad_s2_kernel(const GConvParams p) {
+  constexpr int TPIX = 128;                       // class pixels per tile (TU * TV)
+  constexpr int MT = TPIX / 16;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* halo_base = smem_raw;                                   // [2][HALO_MAX][144 B]
+  uint8_t* stage_base = smem_raw + 2 * HALO_MAX * PIX_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
+  const int group = warp >> 1, half = warp & 1;
+  const int tv = 1 << p.tw_log2, tu = p.th;       // dY tile: tu x tv (+1 halo row / column)
+  const int hw = tv + 1, hh = tu + 1;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int tiles_total = tiles_per_img * p.B;
+  const int n_items = tiles_total * p.slabs;
+  // here p.x = dY (B,H,W,C) with H,W the OUTPUT size of the forward conv; p.out = dX (B,2H,2W,C)
+  auto load_tile = [&](int item, int buf) {
+    const int slab = item / tiles_total;
+    const int tile = item - slab * tiles_total;
+    const int b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    const int u0 = (r / p.tiles_x) * tu, v0 = (r % p.tiles_x) * tv;
+    const uint32_t dst0 = smem_u32(halo_base + buf * (HALO_MAX * PIX_BYTES));
+    const bf16* src0 = p.x + static_cast<long long>(b) * p.H * p.W * p.C + slab * SLAB_C;
+    const int n_chunks = hh * hw * 9;
+    for (int i = threadIdx.x; i < n_chunks; i += kThreadsG) {
+      const int pix = i / 9, ch = i - pix * 9;
+      const int hy = pix / hw, hx = pix - hy * hw;
+      const int yy = u0 + hy, xx = v0 + hx;
+      const bool ok = yy < p.H && xx < p.W;
+      const bf16* src = src0 + (static_cast<long long>(ok ? yy : 0) * p.W + (ok ? xx : 0)) * p.C + ch * 8;
+      cp_async16_zfill(dst0 + pix * PIX_BYTES + ch * 16, src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  uint32_t wk16[9][3][2], wk8[9][3];
+  int cur_slab = -1;
+  const int Wx = 2 * p.W;   // dX width
+  int buf = 0;
+  int item = blockIdx.x;
+  if (item < n_items) load_tile(item, 0);
+  for (; item < n_items; item += gridDim.x, buf ^= 1) {
+    const int next = item + gridDim.x;
+    if (next < n_items) {
+      load_tile(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int slab = item / tiles_total;
+    const int tile = item - slab * tiles_total;
+    if (slab != cur_slab) {
+      cur_slab = slab;
+      const uint32_t* wg = reinterpret_cast<const uint32_t*>(p.w) +
+                           static_cast<long long>(slab * 3 + group) * (9 * GW * GW / 2);
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          const uint32_t* row = wg + (t * GW + nt * 8 + gq) * (GW / 2);
+          wk16[t][nt][0] = __ldg(row + t4);
+          wk16[t][nt][1] = __ldg(row + 4 + t4);
+          wk8[t][nt] = __ldg(row + 8 + t4);
+        }
+    }
+    const int b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    const int u0 = (r / p.tiles_x) * tu, v0 = (r % p.tiles_x) * tv;
+    const uint32_t halo = smem_u32(halo_base + buf * (HALO_MAX * PIX_BYTES));
+    uint8_t* stage = stage_base + warp * STAGE_BYTES;
+    bf16* out_img = p.out + static_cast<long long>(b) * (4ll * p.H * p.W) * p.C + slab * SLAB_C + group * GW;
+    const int mat = lane >> 3, rr = lane & 7;
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      if (((cls == 0 || cls == 3) ? 0 : 1) != half) continue;   // warp half 0: classes (0,0) + (1,1); half 1: the others
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int q = mt * 16 + (mat & 1) * 8 + rr;
+        const int u = q >> p.tw_log2, v = q & (tv - 1);
+        const uint32_t a_base = halo + (u * hw + v) * PIX_BYTES + group * (GW * 2);
+        float acc[3][4];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          if (((ky + py) & 1) == 0) continue;          // iy + 1 - ky must be even
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            if (((kx + px) & 1) == 0) continue;
+            const int doy = (py == 1 && ky == 0) ? 1 : 0, dox = (px == 1 && kx == 0) ? 1 : 0;
+            const int tp = (2 - ky) * 3 + (2 - kx);    // index into the flipped pack
+            uint32_t a[4], a2[2];
+            const uint32_t off = (doy * hw + dox) * PIX_BYTES;
+            ldsm_x4(a, a_base + off + (mat >> 1) * 16);
+            ldsm_x2(a2, a_base + off + 32);
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+              mma16816(acc[nt], a, wk16[tp][nt][0], wk16[tp][nt][1]);
+              mma1688(acc[nt], a2, wk8[tp][nt]);
+            }
+          }
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt)
+            *reinterpret_cast<uint32_t*>(stage + (gq + hf * 8) * (GW * 2) + nt * 16 + t4 * 4) =
+                pack_bf16x2(acc[nt][hf * 2], acc[nt][hf * 2 + 1]);
+        __syncwarp();
+#pragma unroll
+        for (int j = lane; j < 48; j += 32) {
+          const int pxl = j / 3, part = j - pxl * 3;
+          const int qo = mt * 16 + pxl;
+          const int uu = u0 + (qo >> p.tw_log2), vv = v0 + (qo & (tv - 1));
+          if (uu < p.H && vv < p.W) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + j * 16);
+            *reinterpret_cast<uint4*>(out_img + (static_cast<long long>(2 * uu + py) * Wx + 2 * vv + px) * p.C + part * 8) = val;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Weight gradient: dW[co][ci][tap] += sum_pixels dY[pix][co] * X[pix*stride + tap - 1][ci] inside each group of 24.
 // grid = (CTAs per slab, slabs).  A CTA stages the dY tile and the haloed X tile of one 72-channel slab, contracts
 // over the tile's pixels with mma.sync (operands fetched with ldmatrix.trans: pixel-major storage -> channel-major
@@ -475,6 +608,35 @@ extern "C" int tfpp_gconv3x3_wgrad(const void* dy, const void* x, float* dw, flo
   const long long total = static_cast<long long>(slabs) * SLAB_W;
   gconv3x3_wgrad_reduce_kernel<<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
       workspace, dw, static_cast<int>(ctas), total);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+extern "C" int tfpp_gconv3x3_dgrad_s2(const void* dy, const void* w_t, void* dx, int batch, int out_height, int out_width,
+                                      int channels, tfpp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TFPP_CHECK_ARG(channels % SLAB_C == 0, "channels must be a multiple of 72 (3 groups of width 24)");
+  GConvParams p;
+  p.x = static_cast<const bf16*>(dy); p.w = static_cast<const bf16*>(w_t); p.out = static_cast<bf16*>(dx);
+  p.scale = nullptr; p.shift = nullptr; p.act = ACT_NONE; p.stat_sum = nullptr; p.stat_sq = nullptr;
+  p.B = batch; p.H = out_height; p.W = out_width; p.C = channels; p.Ho = 2 * out_height; p.Wo = 2 * out_width;
+  int l = 3;
+  while ((1 << l) < out_width && (1 << l) < 16) ++l;
+  p.tw_log2 = l;
+  p.th = 128 >> l;
+  p.tiles_x = ceil_div(out_width, 1 << l);
+  p.tiles_y = ceil_div(out_height, p.th);
+  p.slabs = channels / SLAB_C;
+  const long long items = static_cast<long long>(p.tiles_x) * p.tiles_y * batch * p.slabs;
+  if (items == 0) return TFPP_OK;
+  const size_t smem = 2 * HALO_MAX * PIX_BYTES + kWarps * STAGE_BYTES;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gconv3x3_dgrad_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    attr = true;
+  }
+  const int grid = static_cast<int>(items < 2 * TFPP_NUM_SMS ? items : 2 * TFPP_NUM_SMS);
+  gconv3x3_dgrad_s2_kernel<<<grid, kThreadsG, smem, stream>>>(p);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

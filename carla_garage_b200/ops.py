@@ -471,6 +471,17 @@ def gconv3x3(x, w, stride=1, scale=None, shift=None, act=ACT_NONE, stats=None):
   return out
 
 
+def gconv3x3_dgrad_s2(dy, w_t):
+  """Input gradient of the stride-2 group conv: dy (B,Ho,Wo,C) bf16, w_t = pack_gconv_halo(w, transpose=True)."""
+  _dev(dy, BF16)
+  _dev(w_t, BF16)
+  b, ho, wo, c = dy.shape
+  dx = torch.empty((b, 2 * ho, 2 * wo, c), dtype=BF16, device=dy.device)
+  check(_lib.load().tfpp_gconv3x3_dgrad_s2(dy.data_ptr(), w_t.data_ptr(), dx.data_ptr(), b, ho, wo, c, _stream()),
+        'tfpp_gconv3x3_dgrad_s2')
+  return dx
+
+
 def gconv3x3_wgrad(dy, x, dw, stride=1):
   """dw (C,24,3,3) f32 (torch layout, contiguous) += weight gradient of gconv3x3(x, w, stride) given dy."""
   _dev(dy, BF16)

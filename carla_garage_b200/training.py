@@ -296,32 +296,13 @@ class Backward:
     cout = conv.weight.shape[0]
     b, ho, wo, _ = draw.shape
     if grouped:  # RegNet 3x3 group conv; a = the full-resolution input whatever the stride
-      gw = conv.weight.shape[1]
       gout = st.g(conv.weight)
       ops.gconv3x3_wgrad(draw, a, gout, stride)
-      if stride == 1:
-        da = ops.gconv3x3(draw, packed(conv.weight, 'gconv_halo_t'))  # same kernel, transposed + flipped weights
-        if id(a) in self.G:
-          ops.add_bf16(self.G[id(a)], da, out=da)
-        self.G[id(a)] = da
-      else:
-        # stride 2: input gradient as one implicit GEMM per input parity plane, written at its positions of the
-        # full-resolution gradient
-        wt = packed(conv.weight, 'gconv_t')
-        gk = dict(k_per_tile=48, a_c_per_ntile=48, bn=48)
-        h, w, c = a.shape[1], a.shape[2], a.shape[3]
-        da = self.G.get(id(a))
-        have = da is not None
-        if not have:
-          da = torch.empty_like(a)
-        for py in range(2):
-          for px in range(2):
-            off = (py * w + px) * c
-            view = da.view(-1)[off:]
-            strides = (h * w * c, 2 * w * c, 2 * c, 1)
-            ops.conv_gemm(draw, wt, taps=ops.taps_dgrad_stride2(py, px), out=view, out_strides=strides,
-                          res1=view if have else None, res1_strides=strides if have else None, **gk)
-        self.G[id(a)] = da
+      wt = packed(conv.weight, 'gconv_halo_t')  # transposed + spatially flipped weights
+      da = ops.gconv3x3(draw, wt) if stride == 1 else ops.gconv3x3_dgrad_s2(draw, wt)
+      if id(a) in self.G:
+        ops.add_bf16(self.G[id(a)], da, out=da)
+      self.G[id(a)] = da
     else:
       cin = conv.weight.shape[1]
       ops.conv_wgrad(draw, a, cin=cin, taps=taps, w_taps=k * k, out=st.g(conv.weight),

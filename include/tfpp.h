@@ -286,6 +286,11 @@ int tfpp_gconv3x3(const void* x, const void* w, void* out, const float* scale, c
                   float* stat_sum, float* stat_sq, int batch, int height, int width, int channels, int stride,
                   tfpp_stream_t stream);
 
+/* Input gradient of the stride-2 tfpp_gconv3x3: dy (B,Ho,Wo,C) bf16, w_t = the transposed / flipped pack (the same one
+ * the stride-1 input gradient uses), dx (B,2Ho,2Wo,C) bf16 (every element written). */
+int tfpp_gconv3x3_dgrad_s2(const void* dy, const void* w_t, void* dx, int batch, int out_height, int out_width,
+                           int channels, tfpp_stream_t stream);
+
 /* Weight gradient of tfpp_gconv3x3: dw (C,24,3,3) f32 torch layout += sum over pixels of dY x X inside each group.
  * workspace: tfpp_gconv3x3_wgrad_workspace(...) floats of scratch (per-CTA partial sums, reduced without atomics). */
 long long tfpp_gconv3x3_wgrad_workspace(int batch, int height, int width, int channels, int stride);

@@ -479,3 +479,15 @@ def test_fusion_attention_backward(ops, c, b, t):
   got = ops.fusion_attn_bwd(qkv, dout, b, t, c, heads).view(b, t, 3 * c).float()
   for name, sl in (('dq', slice(0, c)), ('dk', slice(c, 2 * c)), ('dv', slice(2 * c, 3 * c))):
     assert rel(got[..., sl], x.grad[..., sl]) < 2e-2, (name, c)
+
+
+@pytest.mark.parametrize('b,ho,wo,c', [(2, 16, 32, 72), (1, 8, 8, 216), (2, 12, 20, 144), (1, 4, 16, 576)])
+def test_gconv3x3_stride2_input_gradient(ops, b, ho, wo, c):
+  """tfpp_gconv3x3_dgrad_s2 (parity classes on a dY tile) against autograd of the stride-2 group conv."""
+  x = rnd(b, c, 2 * ho, 2 * wo, seed=1).requires_grad_(True)
+  wt = rnd(c, 24, 3, 3, seed=2, scale=0.1)
+  dy = bf(rnd(b, ho, wo, c, seed=3))
+  F.conv2d(x, bf(wt).float(), stride=2, padding=1, groups=c // 24).backward(dy.float().permute(0, 3, 1, 2))
+  got = ops.gconv3x3_dgrad_s2(dy, ops.pack_gconv_halo(wt, transpose=True))
+  assert got.shape == (b, 2 * ho, 2 * wo, c)
+  assert rel(got.float().permute(0, 3, 1, 2), x.grad) < 4e-3
