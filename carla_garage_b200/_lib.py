@@ -67,7 +67,7 @@ _PROTOS = {
     'tfpp_extra_sensor_token': [P, P, F, F, I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
     'tfpp_planner_head': [P] * 17 + [I, I, I, I, I, P],
     'tfpp_decode_heatmap': [P, L, P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, F, F, P],
-    'tfpp_bn_bwd': [P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P],
+    'tfpp_bn_bwd': [P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P],
     'tfpp_gconv3x3': [P, P, P, P, P, I, P, P, I, I, I, I, I, P],
     'tfpp_gconv3x3_dgrad_s2': [P, P, P, I, I, I, I, P],
     'tfpp_gconv3x3_wgrad': [P, P, P, P, I, I, I, I, I, P],

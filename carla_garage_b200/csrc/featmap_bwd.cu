@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
                                                             const bf16* __restrict__ raw, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd,
                                                             const float* __restrict__ gate,
-                                                            const float* __restrict__ pool_grad, int act,
+                                                            const float* __restrict__ pool_grad,
+                                                            const float* __restrict__ fscale,
+                                                            const float* __restrict__ fshift, int act,
                                                             float* __restrict__ s1, float* __restrict__ s2, int HW,
                                                             int C, int pix_per_block) {
   extern __shared__ float sm[];  // [2][C]
@@ -59,12 +61,17 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
   const int cg = threadIdx.x % c8n, prow = threadIdx.x / c8n;
   if (prow < rows_pp) {
     const int c0 = cg * 8;
-    float l1[8], l2[8], mu[8], is[8], gt[8], pg[8];
+    // ReLU mask: from the saved output y, or (y == nullptr) recomputed from raw with the forward's folded affine —
+    // one tensor less to read
+    const bool mask_from_raw = (act == ACT_RELU) && (y == nullptr);
+    float l1[8], l2[8], mu[8], is[8], gt[8], pg[8], fs[8], fh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       l1[j] = l2[j] = 0.f;
       mu[j] = __ldg(mean + c0 + j);
       is[j] = __ldg(invstd + c0 + j);
+      fs[j] = mask_from_raw ? __ldg(fscale + c0 + j) : 0.f;
+      fh[j] = mask_from_raw ? __ldg(fshift + c0 + j) : 0.f;
       gt[j] = gate ? __ldg(gate + static_cast<long long>(b) * C + c0 + j) : 1.f;
       pg[j] = pool_grad ? __ldg(pool_grad + static_cast<long long>(b) * C + c0 + j) : 0.f;
     }
@@ -78,7 +85,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
           const long long off = base + static_cast<long long>(px) * C + c0;
           ud[k] = ld_stream16(dy + off);
           ur[k] = ld_stream16(raw + off);
-          if (act == ACT_RELU) uy[k] = ld_stream16(y + off);
+          if (act == ACT_RELU && !mask_from_raw) uy[k] = ld_stream16(y + off);
         }
       }
 #pragma unroll
@@ -87,10 +94,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
         float d[8], yy[8], r[8];
         unpack8(ud[k], d);
         unpack8(ur[k], r);
-        if (act == ACT_RELU) unpack8(uy[k], yy);
+        if (act == ACT_RELU && !mask_from_raw) unpack8(uy[k], yy);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float dz = d[j] * gt[j] + pg[j];
+          if (mask_from_raw) yy[j] = fmaf(r[j], fs[j], fh[j]);
           if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
           l1[j] += dz;
           l2[j] = fmaf(dz, (r[j] - mu[j]) * is[j], l2[j]);
@@ -115,7 +123,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
                                                            const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ s1,
                                                            const float* __restrict__ s2, const float* __restrict__ gate,
-                                                           const float* __restrict__ pool_grad, int act, float inv_n,
+                                                           const float* __restrict__ pool_grad,
+                                                           const float* __restrict__ fscale,
+                                                           const float* __restrict__ fshift, int act, float inv_n,
                                                            bf16* __restrict__ draw, bf16* __restrict__ dz_out, int HW,
                                                            int C, int pix_per_block) {
   // same walk as the reduce pass: a thread keeps its 8 channels' constants in registers and streams pixels
@@ -127,10 +137,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
   const int cg = threadIdx.x % c8n, prow = threadIdx.x / c8n;
   if (prow >= rows_pp) return;
   const int c0 = cg * 8;
-  float k0[8], k1[8], k2[8], gt[8], pg[8];
+  const bool mask_from_raw = (act == ACT_RELU) && (y == nullptr);
+  float k0[8], k1[8], k2[8], gt[8], pg[8], fs[8], fh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
+    fs[j] = mask_from_raw ? __ldg(fscale + c) : 0.f;
+    fh[j] = mask_from_raw ? __ldg(fshift + c) : 0.f;
     const float is = __ldg(invstd + c);
     k0[j] = __ldg(gamma + c) * is;
     k1[j] = -k0[j] * is * __ldg(s2 + c) * inv_n;
@@ -148,7 +161,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
         const long long off = base + static_cast<long long>(px) * C + c0;
         ud[k] = ld_stream16(dy + off);
         ur[k] = ld_stream16(raw + off);
-        if (act == ACT_RELU) uy[k] = ld_stream16(y + off);
+        if (act == ACT_RELU && !mask_from_raw) uy[k] = ld_stream16(y + off);
       }
     }
 #pragma unroll
@@ -159,10 +172,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
       float d[8], yy[8], r[8], o[8], z[8];
       unpack8(ud[k], d);
       unpack8(ur[k], r);
-      if (act == ACT_RELU) unpack8(uy[k], yy);
+      if (act == ACT_RELU && !mask_from_raw) unpack8(uy[k], yy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float dz = d[j] * gt[j] + pg[j];
+        if (mask_from_raw) yy[j] = fmaf(r[j], fs[j], fh[j]);
         if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
         z[j] = dz;
         o[j] = fmaf(k0[j], dz, fmaf(k1[j], r[j], k2[j]));
@@ -645,20 +659,23 @@ static void chunking(int batch, int hw, int* chunks, int* pix_per_block) {
 }
 
 extern "C" int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const float* mean, const float* invstd,
-                           const float* gamma, const float* gate, const float* pool_grad, int act, float* s1, float* s2,
-                           void* draw, void* dz_out, int batch, int hw, int channels, tfpp_stream_t stream_) {
+                           const float* gamma, const float* gate, const float* pool_grad, const float* fwd_scale,
+                           const float* fwd_shift, int act, float* s1, float* s2, void* draw, void* dz_out, int batch,
+                           int hw, int channels, tfpp_stream_t stream_) {
   STREAM;
   TFPP_CHECK_ARG(channels % 8 == 0 && channels <= 2048, "channels must be a multiple of 8, <= 2048");
+  TFPP_CHECK_ARG(act != ACT_RELU || y != nullptr || (fwd_scale != nullptr && fwd_shift != nullptr),
+                 "ReLU mask needs y, or the forward scale/shift to recompute it from raw");
   int chunks, ppb;
   chunking(batch, hw, &chunks, &ppb);
   dim3 grid(chunks, batch);
   bn_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 2 * channels, stream>>>(
       static_cast<const bf16*>(dy), static_cast<const bf16*>(y), static_cast<const bf16*>(raw), mean, invstd, gate,
-      pool_grad, act, s1, s2, hw, channels, ppb);
+      pool_grad, fwd_scale, fwd_shift, act, s1, s2, hw, channels, ppb);
   TFPP_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>(
       static_cast<const bf16*>(dy), static_cast<const bf16*>(y), static_cast<const bf16*>(raw), mean, invstd, gamma, s1,
-      s2, gate, pool_grad, act, 1.f / (static_cast<float>(batch) * hw), static_cast<bf16*>(draw),
+      s2, gate, pool_grad, fwd_scale, fwd_shift, act, 1.f / (static_cast<float>(batch) * hw), static_cast<bf16*>(draw),
       static_cast<bf16*>(dz_out), hw, channels, ppb);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;

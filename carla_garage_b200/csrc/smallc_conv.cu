@@ -21,6 +21,14 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, const uint
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t* r, uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(saddr));
+}
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
   const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
@@ -91,28 +99,35 @@ __global__ void __launch_bounds__(256, 2) smallc_conv3x3_kernel(const SmallConvP
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+    const uint32_t halo_u = static_cast<uint32_t>(__cvta_generic_to_shared(halo));
+    const uint32_t wsm_u = static_cast<uint32_t>(__cvta_generic_to_shared(wsm));
+    const int lmat = lane >> 3, lrow = lane & 7;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int ky = tap / 3, kx = tap % 3;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
+        // A: 16 pixels x 16 channels per m tile, one ldmatrix.x4 each (lanes 0-15: pixel rows, lanes 16-31: +8 channels)
         uint32_t a[2][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const bf16* ap = halo + ((warp + ky) * HW_ + (mt * 16 + g + kx)) * P + ks * 16 + 2 * t4;
-          a[mt][0] = *reinterpret_cast<const uint32_t*>(ap);
-          a[mt][1] = *reinterpret_cast<const uint32_t*>(ap + 8 * P);
-          a[mt][2] = *reinterpret_cast<const uint32_t*>(ap + 8);
-          a[mt][3] = *reinterpret_cast<const uint32_t*>(ap + 8 * P + 8);
-        }
+        for (int mt = 0; mt < 2; ++mt)
+          ldsm_x4(a[mt], halo_u + (((warp + ky) * HW_ + mt * 16 + (lane & 15) + kx) * P + ks * 16 + (lane >> 4) * 8) * 2);
+        // B: weight rows (output channels) x 16 input channels: one ldmatrix.x4 feeds two n tiles
+        if (NT >= 2) {
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const bf16* bp = wsm + ((nt * 8 + g) * 9 + tap) * P + ks * 16 + 2 * t4;
-          uint32_t bfr[2];
-          bfr[0] = *reinterpret_cast<const uint32_t*>(bp);
-          bfr[1] = *reinterpret_cast<const uint32_t*>(bp + 8);
-          mma16816(acc[0][nt], a[0], bfr);
-          mma16816(acc[1][nt], a[1], bfr);
+          for (int np = 0; np < NT / 2; ++np) {
+            uint32_t bq[4];
+            ldsm_x4(bq, wsm_u + ((((np * 2 + (lmat >> 1)) * 8 + lrow) * 9 + tap) * P + ks * 16 + (lmat & 1) * 8) * 2);
+            mma16816(acc[0][2 * np], a[0], bq);
+            mma16816(acc[1][2 * np], a[1], bq);
+            mma16816(acc[0][2 * np + 1], a[0], bq + 2);
+            mma16816(acc[1][2 * np + 1], a[1], bq + 2);
+          }
+        } else {
+          uint32_t bq[2];
+          ldsm_x2(bq, wsm_u + ((lrow * 9 + tap) * P + ks * 16 + (lmat & 1) * 8) * 2);
+          mma16816(acc[0][0], a[0], bq);
+          mma16816(acc[1][0], a[1], bq);
         }
       }
     }

@@ -143,7 +143,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
       const bool row_ok = row < p.m_valid && co < p.cout;
       const int wt = p.tap_w[tap];
-      const bool vec_ok = !p.grouped && p.s_ci == 1 && (p.s_co & 3) == 0 && (p.s_tap & 3) == 0 &&
+      const bool vec_ok = !p.grouped && p.s_ci == 1 && (p.s_co & 3) == 0 && ((wt * p.s_tap) & 3) == 0 &&
                           (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;
       for (int c = 0; c < p.bn; c += 16) {
         float v[16];

@@ -315,7 +315,8 @@ class Engine:
                                 pool_sum=pool)
       else:
         y = ops.scale_shift_act(raw, scale, shift, act, res=res, pool_sum=pool)
-      self._save(op='conv_bn', a=a, a_src=a_src, raw=raw, y=y, mean=mean, invstd=invstd, cna=cna, taps=taps,
+      self._save(op='conv_bn', a=a, a_src=a_src, raw=raw, y=y, mean=mean, invstd=invstd, scale=scale, shift=shift,
+                 cna=cna, taps=taps,
                  batch=batch, grouped=grouped, stride=stride, act=act, res=res, res_bn=res_bn)
       return (y, pool) if want_pool else y
     scale, shift = packed((bn.weight, bn.bias, bn.running_mean, bn.running_var), 'bn_eval', bn.eps)
@@ -406,7 +407,8 @@ class Engine:
                                                    save=self.tape is not None)
       bn.num_batches_tracked += 1
       y = ops.scale_shift_act(raw, scale, shift, ACT_RELU)
-      self._save(op='stem', x=x, raw=raw, y=y, mean=mean, invstd=invstd, cna=cna, in_scale=in_scale,
+      self._save(op='stem', x=x, raw=raw, y=y, mean=mean, invstd=invstd, scale=scale, shift=shift, cna=cna,
+                 in_scale=in_scale,
                  in_shift=in_shift)
       return y
     scale, shift = packed((bn.weight, bn.bias, bn.running_mean, bn.running_var), 'bn_eval', bn.eps)

@@ -561,12 +561,16 @@ def pack_grouped_conv_weight_t(w, group_width=24, dt=BF16):
   return pack_grouped_conv_weight(wt, group_width, dt=dt)
 
 
-def bn_bwd(dy, y, raw, mean, invstd, gamma, act, dgamma, dbeta, gate=None, pool_grad=None, want_dz=False):
+def bn_bwd(dy, y, raw, mean, invstd, gamma, act, dgamma, dbeta, gate=None, pool_grad=None, want_dz=False,
+           fwd_affine=None):
+  """fwd_affine = (scale, shift) of the forward BatchNorm fold: with ReLU and y=None the mask is recomputed from raw."""
   b, h, w, c = raw.shape
   draw = torch.empty_like(raw)
   dz = torch.empty_like(raw) if want_dz else None
+  fs, fh = fwd_affine if fwd_affine is not None else (None, None)
   check(_lib.load().tfpp_bn_bwd(dy.data_ptr(), _p(y), raw.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-                                gamma.data_ptr(), _p(gate), _p(pool_grad), act, dbeta.data_ptr(), dgamma.data_ptr(),
+                                gamma.data_ptr(), _p(gate), _p(pool_grad), _p(fs), _p(fh), act, dbeta.data_ptr(),
+                                dgamma.data_ptr(),
                                 draw.data_ptr(), _p(dz), b, h * w, c, _stream()), 'tfpp_bn_bwd')
   return draw, dz
 

@@ -281,8 +281,11 @@ class Backward:
     if id(y) in self.pending:
       gate, pool_grad = self.pending.pop(id(y))
     want_dz = r['res'] is not None or r['res_bn'] is not None
-    draw, dz = ops.bn_bwd(dy, y, raw, r['mean'], r['invstd'], bn.weight, act, st.g(bn.weight), st.g(bn.bias), gate=gate,
-                          pool_grad=pool_grad, want_dz=want_dz)
+    # without a residual the ReLU mask is a function of raw alone: recompute it instead of reading y
+    from_raw = act == ACT_RELU and not want_dz
+    draw, dz = ops.bn_bwd(dy, None if from_raw else y, raw, r['mean'], r['invstd'], bn.weight, act, st.g(bn.weight),
+                          st.g(bn.bias), gate=gate, pool_grad=pool_grad, want_dz=want_dz,
+                          fwd_affine=(r['scale'], r['shift']) if from_raw else None)
     if r['res'] is not None:
       self.add(r['res'], dz)
     if r['res_bn'] is not None:
@@ -345,8 +348,8 @@ class Backward:
     dy = self.G.pop(id(r['y']), None)
     if dy is None:
       return
-    draw, _ = ops.bn_bwd(dy, r['y'], r['raw'], r['mean'], r['invstd'], cna.bn.weight, ACT_RELU, st.g(cna.bn.weight),
-                         st.g(cna.bn.bias))
+    draw, _ = ops.bn_bwd(dy, None, r['raw'], r['mean'], r['invstd'], cna.bn.weight, ACT_RELU, st.g(cna.bn.weight),
+                         st.g(cna.bn.bias), fwd_affine=(r['scale'], r['shift']))
     ops.stem_wgrad(r['x'], draw, r['in_scale'], r['in_shift'], st.g(cna.conv.weight))
 
   def bilinear(self, r):

@@ -199,10 +199,12 @@ int tfpp_decode_heatmap(const float* heat, long long heat_sb, const float* wh, l
 
 /* BatchNorm(+ReLU)(+SE gate / squeeze) backward. dy,y,raw NHWC bf16; gate,pool_grad (B,C) f32 optional;
  * s1,s2 (C) f32 zeroed by the caller: on return s1 = dbeta, s2 = dgamma. draw = grad wrt the conv output; dz_out
- * (optional) = masked incoming gradient (grad of the residual input of the block). */
+ * (optional) = masked incoming gradient (grad of the residual input of the block).  With ReLU and y == NULL the mask
+ * is recomputed as raw * fwd_scale + fwd_shift > 0 (the forward's folded BatchNorm affine): one tensor less to read. */
 int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const float* mean, const float* invstd,
-                const float* gamma, const float* gate, const float* pool_grad, int act, float* s1, float* s2, void* draw,
-                void* dz_out, int batch, int hw, int channels, tfpp_stream_t stream);
+                const float* gamma, const float* gate, const float* pool_grad, const float* fwd_scale,
+                const float* fwd_shift, int act, float* s1, float* s2, void* draw, void* dz_out, int batch, int hw,
+                int channels, tfpp_stream_t stream);
 
 /* SE backward: dout = grad wrt (a2 * gate); outputs pool_grad (B,C) = dL/d(pool_sum) and fc1/fc2 gradients (+=).
  * dgate_sum (B,C) f32 zeroed by the caller and ws (B,C+rd) f32 are workspaces. */

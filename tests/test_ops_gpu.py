@@ -375,6 +375,16 @@ def test_bn_backward(ops, b, h, w, c, act, with_se):
   if act:
     want_dz = want_dz * (yb.float() > 0)
   assert rel(dz.float(), want_dz) < 5e-3
+  if act:  # same result with the ReLU mask recomputed from raw and the forward affine instead of read from y
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    yb2 = ops.scale_shift_act(raw, scale, shift, ops.ACT_RELU)
+    dg2, db2 = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    dg1, db1 = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    d1, _ = ops.bn_bwd(dy, yb2, raw, mean, invstd, gamma, act, dg1, db1, gate=gate, pool_grad=pgrad)
+    d2, _ = ops.bn_bwd(dy, None, raw, mean, invstd, gamma, act, dg2, db2, gate=gate, pool_grad=pgrad,
+                       fwd_affine=(scale, shift))
+    assert rel(d2.float(), d1.float()) < 1e-3 and rel(dg2, dg1) < 1e-4 and rel(db2, db1) < 1e-4
 
 
 @pytest.mark.parametrize('b,c,rd,hw', [(5, 1512, 144, 64), (2, 72, 8, 35), (9, 216, 18, 16), (32, 576, 54, 4)])
