@@ -96,19 +96,26 @@ __global__ void __launch_bounds__(128) se_contract_r_kernel(const float* __restr
   if (c >= C) return;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float* wp = w + static_cast<long long>(c) * w_sc;
-#pragma unroll 4
-  for (int r = 0; r < R; ++r) {
-    const float wv = __ldg(wp + static_cast<long long>(r) * w_sr);
-    const float4 h0 = *reinterpret_cast<const float4*>(hs + r * 8);
-    const float4 h1 = *reinterpret_cast<const float4*>(hs + r * 8 + 4);
-    acc[0] = fmaf(wv, h0.x, acc[0]);
-    acc[1] = fmaf(wv, h0.y, acc[1]);
-    acc[2] = fmaf(wv, h0.z, acc[2]);
-    acc[3] = fmaf(wv, h0.w, acc[3]);
-    acc[4] = fmaf(wv, h1.x, acc[4]);
-    acc[5] = fmaf(wv, h1.y, acc[5]);
-    acc[6] = fmaf(wv, h1.z, acc[6]);
-    acc[7] = fmaf(wv, h1.w, acc[7]);
+  // the weight loads are the latency: 16 of them in flight per thread before the first is consumed
+  for (int r0 = 0; r0 < R; r0 += 16) {
+    float wv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wv[i] = r0 + i < R ? __ldg(wp + static_cast<long long>(r0 + i) * w_sr) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (r0 + i < R) {
+        const float4 h0 = *reinterpret_cast<const float4*>(hs + (r0 + i) * 8);
+        const float4 h1 = *reinterpret_cast<const float4*>(hs + (r0 + i) * 8 + 4);
+        acc[0] = fmaf(wv[i], h0.x, acc[0]);
+        acc[1] = fmaf(wv[i], h0.y, acc[1]);
+        acc[2] = fmaf(wv[i], h0.z, acc[2]);
+        acc[3] = fmaf(wv[i], h0.w, acc[3]);
+        acc[4] = fmaf(wv[i], h1.x, acc[4]);
+        acc[5] = fmaf(wv[i], h1.y, acc[5]);
+        acc[6] = fmaf(wv[i], h1.z, acc[6]);
+        acc[7] = fmaf(wv[i], h1.w, acc[7]);
+      }
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {

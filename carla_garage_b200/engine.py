@@ -262,6 +262,16 @@ class Engine:
     if self.tape is not None:
       self.tape.append(kw)
 
+  def _count_batch(self, bn):
+    """BatchNorm.num_batches_tracked += 1.  Under a Trainer all the counters are views of one int64 buffer that is
+    bumped once per step (training.FlatState.count_batches) instead of one tiny kernel per BatchNorm."""
+    if getattr(self, 'batch_counters_fused', False):
+      return
+    seen = getattr(self, 'bn_seen', None)
+    if seen is not None:
+      seen.append(bn)
+    bn.num_batches_tracked += 1
+
   def new_arena(self, device, n_floats=6 * 1024 * 1024):
     """One zero-filled fp32 arena per step for all the small accumulators (BatchNorm statistics, SE squeezes, ...):
     a single memset instead of ~500 tiny fill kernels."""
@@ -309,7 +319,7 @@ class Engine:
       scale, shift, mean, invstd = ops.bn_finalize(stats[0], stats[1], bn.weight, bn.bias, bn.running_mean,
                                                    bn.running_var, count, eps=bn.eps, momentum=bn.momentum,
                                                    save=self.tape is not None)
-      bn.num_batches_tracked += 1
+      self._count_batch(bn)
       if res_bn is not None:
         y = ops.scale_shift_act(raw, scale, shift, act, res=res_bn[0], res_scale=res_bn[1], res_shift=res_bn[2],
                                 pool_sum=pool)
@@ -376,7 +386,7 @@ class Engine:
         sd, td, mean_d, invstd_d = ops.bn_finalize(stats[0], stats[1], ds.bn.weight, ds.bn.bias, ds.bn.running_mean,
                                                    ds.bn.running_var, count, eps=ds.bn.eps, momentum=ds.bn.momentum,
                                                    save=self.tape is not None)
-        ds.bn.num_batches_tracked += 1
+        self._count_batch(ds.bn)
         self._save(op='downsample', a=xp, x_src=x, stride=s, raw=raw_d, mean=mean_d, invstd=invstd_d, cna=ds, batch=b)
         return self.conv_bn(a2s, blk.conv3, training, act=ACT_RELU, res_bn=(raw_d, sd, td))
       shortcut = self.conv_bn(xp, ds, training, batch=b)
@@ -405,7 +415,7 @@ class Engine:
       scale, shift, mean, invstd = ops.bn_finalize(stats[0], stats[1], bn.weight, bn.bias, bn.running_mean,
                                                    bn.running_var, count, eps=bn.eps, momentum=bn.momentum,
                                                    save=self.tape is not None)
-      bn.num_batches_tracked += 1
+      self._count_batch(bn)
       y = ops.scale_shift_act(raw, scale, shift, ACT_RELU)
       self._save(op='stem', x=x, raw=raw, y=y, mean=mean, invstd=invstd, scale=scale, shift=shift, cna=cna,
                  in_scale=in_scale,
@@ -565,7 +575,7 @@ class Engine:
                            vn.running_var if training else None, ese[0].weight, ese[0].bias, ese[2].weight, ese[2].bias,
                            packed(m.extra_sensor_pos_embed, 'f32'), mem, None, n_mem, n_pix)
     if training:
-      vn.num_batches_tracked += 1
+      self._count_batch(vn)
     layers = m.join.layers
     heads = cfg.num_decoder_heads
     hd = d // heads

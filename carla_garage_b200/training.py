@@ -80,6 +80,15 @@ class FlatState:
       p.data = self.flat[off:off + k].view(p.shape)
       p.grad = self.grad[off:off + k].view(p.shape)
       self.offsets[id(p)] = (off, k)
+    # every BatchNorm's num_batches_tracked as a view of one int64 buffer: one increment kernel per step
+    counters = [(n, b) for n, b in model.named_buffers() if n.endswith('num_batches_tracked')]
+    self.batch_counters = torch.zeros(max(len(counters), 1), dtype=torch.int64, device=dev)
+    self.counter_index = {}
+    for i, (_, b) in enumerate(counters):
+      self.batch_counters[i] = b
+      b.data = self.batch_counters[i]
+      self.counter_index[id(b)] = i
+    self.counter_mask = None  # 0/1 per counter: which BatchNorms a training forward actually runs (learned on step 1)
     self.exp_avg = torch.zeros_like(self.flat)
     self.exp_avg_sq = torch.zeros_like(self.flat)
     self.max_exp_avg_sq = torch.zeros_like(self.flat)
@@ -99,6 +108,16 @@ class FlatState:
 
   def zero_grad(self):
     self.grad.zero_()
+
+  def learn_counter_mask(self, bns):
+    mask = torch.zeros_like(self.batch_counters)
+    for bn in bns:
+      mask[self.counter_index[id(bn.num_batches_tracked)]] += 1
+    self.counter_mask = mask
+
+  def count_batches(self):
+    """one training forward: every BatchNorm it runs counts one more batch"""
+    self.batch_counters += self.counter_mask
 
   def adamw_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, grad_scale=1.0):
     """optim.AdamW(amsgrad=True).step() (train.py:527-531,908) as one fused kernel over the flat buffers."""
@@ -664,6 +683,11 @@ class Trainer:
     eng, st = self.eng, self.st
     st.zero_grad()
     eng.tape = []
+    fused = st.counter_mask is not None
+    eng.batch_counters_fused = fused
+    eng.bn_seen = None if fused else []
+    if fused:
+      st.count_batches()
     try:
       out = eng.forward(inputs['rgb'], inputs['lidar_bev'], inputs['target_point'], inputs['ego_vel'],
                         inputs['command'], training=True)
@@ -671,6 +695,10 @@ class Trainer:
       Backward(eng, st).run(eng.tape, seeds)
     finally:
       eng.tape = None
+      eng.batch_counters_fused = False
+      if not fused and eng.bn_seen is not None and torch.cuda.is_available() and not torch.cuda.is_current_stream_capturing():
+        st.learn_counter_mask(eng.bn_seen)
+      eng.bn_seen = None
     return out, losses
 
   def allreduce(self):

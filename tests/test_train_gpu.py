@@ -187,6 +187,9 @@ def test_pack_plan_tracks_the_optimizer(oracle_state):
   _, l2 = tr.step(inp, lab)
   assert check() > 300
   assert float((tr.st.flat - before).abs().max()) > 1e-4  # the parameters really moved
+  # every BatchNorm counted the three batches (step 1 individually, steps 2-3 through the fused counter buffer)
+  counters = {n: int(b) for n, b in m.named_buffers() if n.endswith('num_batches_tracked')}
+  assert len(counters) == 137 and set(counters.values()) == {3}, {n: v for n, v in counters.items() if v != 3}
   tot = [sum(float(v) for v in l.values()) for l in (l0, l1, l2)]
   assert tot[2] < tot[0], tot  # same batch three times: the loss goes down
   n_seg = len(tr.plan.segments)
