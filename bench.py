@@ -169,11 +169,11 @@ def main():
     return ms
 
   # ---- device-resident throughput.  N=1: the whole step (K1 + fwd + losses + bwd + AdamW) replays from one CUDA
-  # graph; N>1: eager launches (the NCCL all-reduce stays outside graph capture in this round).
+  # graph; N>1: two graphs (forward/backward, optimizer) with the NCCL all-reduce issued eagerly between them.
   dev_pts = host_pts.cuda()
-  use_graph = (world == 1 or os.environ.get('TFPP_GRAPH_NCCL', '0') == '1') and os.environ.get('TFPP_NO_GRAPH', '0') != '1'
+  use_graph = os.environ.get('TFPP_NO_GRAPH', '0') != '1'
   if use_graph:
-    tr.capture(dev_in, dev_lab, points=dev_pts)
+    tr.capture(dev_in, dev_lab, points=dev_pts, split=True if os.environ.get('TFPP_SPLIT_GRAPH', '0') == '1' else None)
 
   def step_resident():
     if use_graph:

@@ -226,8 +226,9 @@ __global__ void __launch_bounds__(256) channel_scale_kernel(const bf16* __restri
   for (int k = 0; k < U; ++k) {
     const long long i = i0 + static_cast<long long>(k) * blockDim.x;
     if (i >= total8) break;
-    const int c0 = static_cast<int>(i % c8n) * 8;
-    const int b = static_cast<int>((i / c8n) / HW);
+    const unsigned iu = static_cast<unsigned>(i);   // total8 < 2^31 (checked on the host): 32-bit divisions
+    const int c0 = static_cast<int>(iu % static_cast<unsigned>(c8n)) * 8;
+    const int b = static_cast<int>((iu / static_cast<unsigned>(c8n)) / static_cast<unsigned>(HW));
     const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
     uint32_t o[4];
     const float4* g = reinterpret_cast<const float4*>(gate + static_cast<long long>(b) * C + c0);
@@ -248,13 +249,14 @@ __global__ void __launch_bounds__(256) parity_split_kernel(const bf16* __restric
                                                            long long total8, int B, int H, int W, int C) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total8) return;
-  const int c8n = C / 8;
-  const int c8 = static_cast<int>(i % c8n);
-  long long pix = i / c8n;
-  const int xx = static_cast<int>(pix % W);
-  pix /= W;
-  const int yy = static_cast<int>(pix % H);
-  const int b = static_cast<int>(pix / H);
+  const unsigned c8n = C / 8;
+  const unsigned iu = static_cast<unsigned>(i);   // total8 < 2^31 (checked on the host): 32-bit divisions
+  const int c8 = static_cast<int>(iu % c8n);
+  unsigned pix = iu / c8n;
+  const int xx = static_cast<int>(pix % static_cast<unsigned>(W));
+  pix /= static_cast<unsigned>(W);
+  const int yy = static_cast<int>(pix % static_cast<unsigned>(H));
+  const int b = static_cast<int>(pix / static_cast<unsigned>(H));
   const int q = (yy & 1) * 2 + (xx & 1);
   const long long dst = (((static_cast<long long>(q) * B + b) * (H / 2) + (yy >> 1)) * (W / 2) + (xx >> 1)) * C + c8 * 8;
   *reinterpret_cast<uint4*>(y + dst) = *reinterpret_cast<const uint4*>(x + i * 8);
@@ -317,16 +319,16 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const void* __restrict__ 
                                                        long long s_srow, const bf16* __restrict__ add,
                                                        bf16* __restrict__ out, int B, int sh, int sw, int dh, int dw,
                                                        int C) {
-  const int c8n = C / 8;
-  const long long total = static_cast<long long>(B) * dh * dw * c8n;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned c8n = C / 8;
+  const unsigned total = static_cast<unsigned>(B) * dh * dw * c8n;   // < 2^31 (checked on the host): 32-bit index math
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c0 = static_cast<int>(i % c8n) * 8;
-  long long t = i / c8n;
-  const int x = static_cast<int>(t % dw);
-  t /= dw;
-  const int y = static_cast<int>(t % dh);
-  const int b = static_cast<int>(t / dh);
+  unsigned t = i / c8n;
+  const int x = static_cast<int>(t % static_cast<unsigned>(dw));
+  t /= static_cast<unsigned>(dw);
+  const int y = static_cast<int>(t % static_cast<unsigned>(dh));
+  const int b = static_cast<int>(t / static_cast<unsigned>(dh));
   const float fy = fmaxf((y + 0.5f) * (static_cast<float>(sh) / dh) - 0.5f, 0.f);
   const float fx = fmaxf((x + 0.5f) * (static_cast<float>(sw) / dw) - 0.5f, 0.f);
   const int y0 = min(static_cast<int>(fy), sh - 1), x0 = min(static_cast<int>(fx), sw - 1);
@@ -499,6 +501,7 @@ extern "C" int tfpp_channel_scale(const void* x, const float* gate, void* y, int
   STREAM;
   TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
   const long long total8 = static_cast<long long>(batch) * hw * channels / 8;
+  TFPP_CHECK_ARG(total8 < (1ll << 31), "tensor too large for the 32-bit index path");
   channel_scale_kernel<<<static_cast<int>(ceil_div_ll(total8, 256 * 4)), 256, 0, stream>>>(
       static_cast<const bf16*>(x), gate, static_cast<bf16*>(y), total8, hw, channels);
   TFPP_CHECK_LAUNCH();
@@ -510,6 +513,7 @@ extern "C" int tfpp_parity_split(const void* x, void* y, int batch, int height, 
   STREAM;
   TFPP_CHECK_ARG(channels % 8 == 0 && height % 2 == 0 && width % 2 == 0, "need C%8==0 and even H, W");
   const long long total8 = static_cast<long long>(batch) * height * width * channels / 8;
+  TFPP_CHECK_ARG(total8 < (1ll << 31), "tensor too large for the 32-bit index path");
   parity_split_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, stream>>>(
       static_cast<const bf16*>(x), static_cast<bf16*>(y), total8, batch, height, width, channels);
   TFPP_CHECK_LAUNCH();
@@ -535,6 +539,7 @@ extern "C" int tfpp_bilinear(const void* src, int src_f32, long long src_batch_s
   STREAM;
   TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
   const long long total = static_cast<long long>(batch) * dh * dw * (channels / 8);
+  TFPP_CHECK_ARG(total < (1ll << 31), "tensor too large for the 32-bit index path");
   bilinear_kernel<<<static_cast<int>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
       src, src_f32, src_batch_stride, src_row_stride, static_cast<const bf16*>(add), static_cast<bf16*>(out), batch, sh,
       sw, dh, dw, channels);

@@ -401,19 +401,22 @@ __device__ __forceinline__ void bl_coef(int d, int dn, int sn, int& i0, int& i1,
 __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const bf16* __restrict__ dout, void* __restrict__ dsrc,
                                                            int dsrc_f32, long long s_sb, long long s_srow,
                                                            int accumulate, int B, int sh, int sw, int dh, int dw, int C) {
-  const int c8n = C / 8;
-  const long long total = static_cast<long long>(B) * sh * sw * c8n;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned c8n = C / 8;
+  const unsigned total = static_cast<unsigned>(B) * sh * sw * c8n;   // < 2^31 (checked on the host): 32-bit index math
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c0 = static_cast<int>(i % c8n) * 8;
-  long long t = i / c8n;
-  const int sx = static_cast<int>(t % sw);
-  t /= sw;
-  const int sy = static_cast<int>(t % sh);
-  const int b = static_cast<int>(t / sh);
-  const int ry = (dh + sh - 1) / sh, rx = (dw + sw - 1) / sw;
-  const int ylo = max(0, (sy - 1) * ry - 1), yhi = min(dh - 1, (sy + 2) * ry);
-  const int xlo = max(0, (sx - 1) * rx - 1), xhi = min(dw - 1, (sx + 2) * rx);
+  unsigned t = i / c8n;
+  const int sx = static_cast<int>(t % static_cast<unsigned>(sw));
+  t /= static_cast<unsigned>(sw);
+  const int sy = static_cast<int>(t % static_cast<unsigned>(sh));
+  const int b = static_cast<int>(t / static_cast<unsigned>(sh));
+  // destination rows / columns whose 2-tap stencil can touch source row sy: |fy - sy| < 1 with fy = (y + .5) * sh/dh - .5
+  const float ryf = static_cast<float>(dh) / sh, rxf = static_cast<float>(dw) / sw;
+  const int ylo = max(0, static_cast<int>(floorf(ryf * (sy - 0.5f) - 0.5f))),
+            yhi = min(dh - 1, static_cast<int>(ceilf(ryf * (sy + 1.5f) - 0.5f)));
+  const int xlo = max(0, static_cast<int>(floorf(rxf * (sx - 0.5f) - 0.5f))),
+            xhi = min(dw - 1, static_cast<int>(ceilf(rxf * (sx + 1.5f) - 0.5f)));
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int y = ylo; y <= yhi; ++y) {
     int y0, y1;
@@ -750,6 +753,7 @@ extern "C" int tfpp_bilinear_bwd(const void* dout, void* dsrc, int dsrc_f32, lon
   STREAM;
   TFPP_CHECK_ARG(channels % 8 == 0, "channels must be a multiple of 8");
   const long long total = static_cast<long long>(batch) * sh * sw * (channels / 8);
+  TFPP_CHECK_ARG(total < (1ll << 31), "tensor too large for the 32-bit index path");
   bilinear_bwd_kernel<<<static_cast<int>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
       static_cast<const bf16*>(dout), dsrc, dsrc_f32, src_batch_stride, src_row_stride, accumulate, batch, sh, sw, dh,
       dw, channels);

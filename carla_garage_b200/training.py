@@ -708,33 +708,54 @@ class Trainer:
       return
     allreduce_flat(self.st.grad, self.pg, self.bucket_elems)
 
-  def step(self, inputs, labels, lr='default'):
+  def _with_plan(self, fn):
     prev_plan = eng_mod._PLAN[0]  # pylint: disable=protected-access
     eng_mod._PLAN[0] = self.plan  # pylint: disable=protected-access
     try:
-      out, losses = self.forward_backward(inputs, labels)
-      self.allreduce()
-      self.st.adamw_step(self.lr if lr == 'default' else lr, weight_decay=self.wd, grad_scale=1.0 / self.world)
-      if self.plan is not None:
-        self.plan.refresh()  # one gather kernel: every bf16 weight pack follows the new parameters
-        if not torch.cuda.is_current_stream_capturing():
-          self.plan.finalize()  # adopt the packs first seen in this (eager) step
+      return fn()
     finally:
       eng_mod._PLAN[0] = prev_plan  # pylint: disable=protected-access
-    return out, losses
 
-  # ---- CUDA-graph replay of the whole step (removes ~4000 Python-issued launches per step from the critical path)
-  def capture(self, inputs, labels, points=None):
-    """Capture pillar scatter (if raw ``points`` are given) + step into one CUDA graph with static input buffers."""
+  def optimizer_step(self, lr='default'):
+    """AdamW over the flat buffers (gradient averaged over the ranks inside the kernel) + weight-pack refresh."""
+    self.st.adamw_step(self.lr if lr == 'default' else lr, weight_decay=self.wd, grad_scale=1.0 / self.world)
+    if self.plan is not None:
+      self.plan.refresh()  # one gather kernel: every bf16 weight pack follows the new parameters
+      if not torch.cuda.is_current_stream_capturing():
+        self.plan.finalize()  # adopt the packs first seen in this (eager) step
+
+  def step(self, inputs, labels, lr='default'):
+    def run():
+      out, losses = self.forward_backward(inputs, labels)
+      self.allreduce()
+      self.optimizer_step(lr)
+      return out, losses
+    return self._with_plan(run)
+
+  # ---- CUDA-graph replay of the step (removes ~2000 Python-issued launches per step from the critical path)
+  def capture(self, inputs, labels, points=None, split=None):
+    """Capture pillar scatter (if raw ``points`` are given) + step with static input buffers.  One rank: ONE CUDA graph
+    for the whole step.  Data parallel (or ``split=True``): two graphs — forward/backward and optimizer — with the NCCL
+    gradient all-reduce issued eagerly between the two replays (collectives stay out of the capture)."""
     self._sin = {k: v.clone() for k, v in inputs.items()}
     self._slab = {k: v.clone() for k, v in labels.items()}
     self._spts = points.clone() if points is not None else None
     self.st.dev_state[1:2].fill_(self.lr)
+    self._split = (self.world > 1) if split is None else bool(split)
 
-    def body():
+    def fwd_bwd():
       if self._spts is not None:
         self._sin['lidar_bev'] = ops.pillar_scatter(self._spts, use_ground_plane=bool(self.eng.cfg.use_ground_plane))
-      return self.step(self._sin, self._slab, lr=None)
+      return self._with_plan(lambda: self.forward_backward(self._sin, self._slab))
+
+    def opt():
+      self._with_plan(lambda: self.optimizer_step(lr=None))
+
+    def body():
+      r = fwd_bwd()
+      self.allreduce()
+      opt()
+      return r
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -746,12 +767,20 @@ class Trainer:
     from . import _lib  # pylint: disable=import-outside-toplevel
     _lib.reset_launch_count()
     self.graph = torch.cuda.CUDAGraph()
-    # with NCCL inside the capture its watchdog thread keeps polling events: only this thread's calls are checked
-    with torch.cuda.graph(self.graph, capture_error_mode='thread_local' if self.world > 1 else 'global'):
-      out, losses = body()
-      self._gloss = torch.stack([losses[k] for k in LOSS_KEYS])
+    self.graph_opt = None
+    if not self._split:
+      with torch.cuda.graph(self.graph):
+        out, losses = body()
+        self._gloss = torch.stack([losses[k] for k in LOSS_KEYS])
+    else:
+      with torch.cuda.graph(self.graph):
+        out, losses = fwd_bwd()
+        self._gloss = torch.stack([losses[k] for k in LOSS_KEYS])
+      self.graph_opt = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self.graph_opt):
+        opt()
     self._gout = out
-    self.launches_per_step = _lib.launch_count()  # libtfpp kernels recorded into the graph
+    self.launches_per_step = _lib.launch_count()  # libtfpp kernels recorded into the graph(s)
     return self
 
   def replay(self, inputs=None, labels=None, points=None):
@@ -766,4 +795,7 @@ class Trainer:
     if points is not None:
       self._spts.copy_(points, non_blocking=True)
     self.graph.replay()
+    if self.graph_opt is not None:
+      self.allreduce()
+      self.graph_opt.replay()
     return self._gout, self._gloss

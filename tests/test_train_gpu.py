@@ -198,3 +198,11 @@ def test_pack_plan_tracks_the_optimizer(oracle_state):
     tr.replay()
   assert len(tr.plan.segments) == n_seg and not tr.plan.pending  # nothing new appeared under capture
   check()
+  # the data-parallel arrangement on one GPU: forward/backward graph + optimizer graph, all-reduce (a no-op here) between
+  tr.capture(inp, lab, split=True)
+  assert tr.graph_opt is not None
+  p0 = tr.st.flat.clone()
+  _, gl = tr.replay()
+  torch.cuda.synchronize()
+  assert torch.isfinite(gl).all() and float((tr.st.flat - p0).abs().max()) > 0
+  check()
