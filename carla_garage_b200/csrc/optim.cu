@@ -5,32 +5,55 @@
 #include "common.cuh"
 
 namespace {
+__device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, float& vmax, float lr, float beta1,
+                                          float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  const float gr = g * grad_scale;
+  const float pv = p * (1.f - lr * wd);        // decoupled weight decay
+  m = beta1 * m + (1.f - beta1) * gr;
+  v = beta2 * v + (1.f - beta2) * gr * gr;
+  vmax = fmaxf(vmax, v);
+  const float denom = sqrtf(vmax) / bc2_sqrt + eps;
+  p = pv - (lr / bc1) * (m / denom);
+}
+
+// 4 elements per thread (16-byte accesses; the flat buffers are padded to a multiple of 4), scalar tail otherwise.
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v,
                                                     float* __restrict__ vmax, long long n, float lr, float beta1,
                                                     float beta2, float eps, float wd, float bc1, float bc2_sqrt,
                                                     float grad_scale, const float* __restrict__ dev_state) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
-  if (dev_state != nullptr) {  // CUDA-graph friendly: step count and learning rate live on the device
-    const float t = dev_state[0];
+  if (dev_state != nullptr) {  // CUDA-graph friendly: step count, learning rate and bias corrections live on the device
     lr = dev_state[1];
-    bc1 = 1.f - powf(beta1, t);
-    bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+    bc1 = dev_state[2];
+    bc2_sqrt = dev_state[3];
   }
-  const float gr = g[i] * grad_scale;
-  float pv = p[i];
-  pv *= (1.f - lr * wd);                       // decoupled weight decay
-  const float mv = beta1 * m[i] + (1.f - beta1) * gr;
-  const float vv = beta2 * v[i] + (1.f - beta2) * gr * gr;
-  const float vm = fmaxf(vmax[i], vv);
-  m[i] = mv;
-  v[i] = vv;
-  vmax[i] = vm;
-  const float denom = sqrtf(vm) / bc2_sqrt + eps;
-  p[i] = pv - (lr / bc1) * (mv / denom);
+  if (i + 4 <= n) {
+    float4 pv = *reinterpret_cast<float4*>(p + i);
+    const float4 gv = *reinterpret_cast<const float4*>(g + i);
+    float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+    float4 xv = *reinterpret_cast<float4*>(vmax + i);
+    adamw_one(pv.x, gv.x, mv.x, vv.x, xv.x, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    adamw_one(pv.y, gv.y, mv.y, vv.y, xv.y, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    adamw_one(pv.z, gv.z, mv.z, vv.z, xv.z, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    adamw_one(pv.w, gv.w, mv.w, vv.w, xv.w, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    *reinterpret_cast<float4*>(p + i) = pv;
+    *reinterpret_cast<float4*>(m + i) = mv;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    *reinterpret_cast<float4*>(vmax + i) = xv;
+  } else {
+    for (long long j = i; j < n; ++j) adamw_one(p[j], g[j], m[j], v[j], vmax[j], lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  }
 }
-__global__ void adamw_tick_kernel(float* dev_state) { dev_state[0] += 1.f; }
+// dev_state = [step, lr, 1 - beta1^step, sqrt(1 - beta2^step)]
+__global__ void adamw_tick_kernel(float* dev_state, float beta1, float beta2) {
+  const float t = dev_state[0] + 1.f;
+  dev_state[0] = t;
+  dev_state[2] = 1.f - powf(beta1, t);
+  dev_state[3] = sqrtf(1.f - powf(beta2, t));
+}
+
 
 // Weight-pack refresh (engine.PackPlan): out[i] = idx[i] >= 0 ? flat[idx[i]] : 0, 8 elements per thread.  Most maps are
 // long contiguous runs (coalesced); the transposed dgrad packs gather with a stride but hit L2 across neighbouring CTAs.
@@ -73,8 +96,10 @@ extern "C" int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_av
   TFPP_CHECK_ARG(step >= 1 || dev_state != nullptr, "step counts from 1");
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
-  if (dev_state != nullptr) adamw_tick_kernel<<<1, 1, 0, stream>>>(dev_state);
-  adamw_kernel<<<static_cast<int>(ceil_div_ll(n, 256)), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq,
+  if (dev_state != nullptr) adamw_tick_kernel<<<1, 1, 0, stream>>>(dev_state, beta1, beta2);
+  TFPP_CHECK_ARG((reinterpret_cast<uintptr_t>(param) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0,
+                 "parameter / gradient buffers must be 16-byte aligned");
+  adamw_kernel<<<static_cast<int>(ceil_div_ll(ceil_div_ll(n, 4), 256)), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq,
                                                                           max_exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                           weight_decay, bc1, sqrtf(bc2), grad_scale,
                                                                           dev_state);

@@ -93,7 +93,8 @@ class FlatState:
     self.exp_avg_sq = torch.zeros_like(self.flat)
     self.max_exp_avg_sq = torch.zeros_like(self.flat)
     self.step_count = 0
-    self.dev_state = torch.zeros(2, dtype=F32, device=dev) if dev.type == 'cuda' else None  # [step, lr]
+    # [step, lr, 1 - beta1^step, sqrt(1 - beta2^step)]: maintained on the device (CUDA-graph replay)
+    self.dev_state = torch.zeros(4, dtype=F32, device=dev) if dev.type == 'cuda' else None
 
   def g(self, p):
     """fp32 gradient view of parameter p (same shape)."""

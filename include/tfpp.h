@@ -305,8 +305,10 @@ int tfpp_gconv3x3_wgrad(const void* dy, const void* x, float* dw, float* workspa
 int tfpp_gather_pack(const float* flat, const int* idx, void* out, long long n, int out_f32, tfpp_stream_t stream);
 
 /* AdamW(amsgrad=True), torch semantics; grad_scale multiplies the gradient first (1/world_size after a sum
- * all-reduce).  dev_state (optional, 2 floats on the device: [step count, learning rate]) replaces the host-side
- * `step` / `lr` so the launch can be replayed from a CUDA graph; the count is incremented by the call. */
+ * all-reduce).  dev_state (optional, 4 floats on the device: [step count, learning rate, 1 - beta1^step,
+ * sqrt(1 - beta2^step)]; the caller sets the first two) replaces the host-side `step` / `lr` so the launch can be
+ * replayed from a CUDA graph; the count is incremented and the bias corrections refreshed by the call.
+ * param / grad / state buffers 16-byte aligned. */
 int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
                        long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                        float grad_scale, float* dev_state, tfpp_stream_t stream);
