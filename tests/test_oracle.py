@@ -58,7 +58,7 @@ def test_forward_eval_vs_golden(oracle_state):
   g = np.load(os.path.join(GOLDEN, 'forward_eval_b2.npz'))
   inp = synth.make_inputs(2, seed=11)
   taps = {}
-  torch.set_num_threads(os.cpu_count())
+  torch.set_num_threads(min(os.cpu_count() or 1, 16))
   with torch.no_grad():
     out = orc.forward(oracle_state, **inp, taps=taps)
   assert rel(out[1], g['pred_target_speed']) < 1e-4
@@ -83,7 +83,7 @@ def test_train_losses_vs_golden(oracle_state):
   lab = synth.make_labels(2, seed=13)
   sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v)
         for k, v in oracle_state.items()}
-  torch.set_num_threads(os.cpu_count())
+  torch.set_num_threads(min(os.cpu_count() or 1, 16))
   out = orc.forward(sd, **inp, training=True)
   # forward() detaches; run the differentiable path explicitly
   loss = orc.compute_loss(oracle_state, out, lab)
