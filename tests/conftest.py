@@ -13,6 +13,9 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 def pytest_configure(config):
   config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
   config.addinivalue_line('markers', 'reference: needs /root/reference (build container only)')
+  # the CPU oracle (torch fp32) collapses when oversubscribed on many-core hosts: 16 threads are ~10x faster than 128
+  import torch
+  torch.set_num_threads(min(os.cpu_count() or 1, 16))
 
 
 @pytest.fixture(scope='session')
