@@ -277,7 +277,11 @@ def main():
     roof = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel + wgrad_kernel (tcgen05)',
             'achieved': prof['tflops'], 'peak': peak, 'unit': 'TFLOP/s', 'frac': prof['tflops'] / peak,
             'peak_source': 'measured (MEASURED_PEAKS.json, sustained)' if peaks else 'fallback',
-            'traffic': None, 'launches_per_step': prof['launches'], 'share_of_step': prof['ms'] / (ms / args.steps),
+            # DRAM bytes of the largest-FLOP launch of the family (fusion QKV GEMM, M=10240 K=1512 N=4536) from
+            # `ncu --set full` (profiles/r01_ncu_qkv_v13_details.txt): 44.8 MB read + 39.8 MB written, against 138 MB
+            # of algorithmic operand + output bytes (operand re-reads hit L2; part of the output is still in L2)
+            'traffic': 84.6e6, 'traffic_launch': 'conv_gemm_kernel, fusion QKV projection (M=10240, K=1512, N=4536)',
+            'launches_per_step': prof['launches'], 'share_of_step': prof['ms'] / (ms / args.steps),
             'algorithmic_gflop_per_step': prof['gflop']}
 
   if rank != 0:
