@@ -230,7 +230,23 @@ extern "C" int tfpp_conv_wgrad(const tfpp_wgrad_args* a, tfpp_stream_t stream_) 
   p.stages = stages;
   p.dw = a->dw;
   const int tiles = p.m_tiles * p.n_tiles * p.ntaps;
-  int splits = a->splits > 0 ? a->splits : ceil_div(2 * TFPP_NUM_SMS, tiles);
+  int splits = a->splits;
+  if (splits <= 0) {
+    // one CTA per SM (200 KB of stages): pick the split count that minimises waves x (pixel blocks per CTA + fixed
+    // prologue/epilogue cost) instead of a fixed 2 CTAs/SM target — 300 CTAs on 148 SMs is three waves, not two
+    const int fixed = 6 + p.bn / 32;   // prologue + TMEM drain + reductions, in units of one 64-pixel k block
+    long long best_cost = -1;
+    splits = 1;
+    const int smax = p.p_tiles < 2 * TFPP_NUM_SMS ? p.p_tiles : 2 * TFPP_NUM_SMS;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const long long waves = ceil_div_ll(static_cast<long long>(tiles) * sp, TFPP_NUM_SMS);
+      const long long cost = waves * (ceil_div(p.p_tiles, sp) + fixed);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        splits = sp;
+      }
+    }
+  }
   if (splits > p.p_tiles) splits = p.p_tiles;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
