@@ -129,7 +129,7 @@ def run_reference(args):
   wu = min(max(args.warmup, 0), 1)
   rate, sec, ran = cpu_reference_step_rate(batch, max(args.steps, 1), wu, threads)
   sample = (f'{ran} train step(s) of batch {batch} ({sec:.1f} s each; time-bounded, {args.steps} requested) of '
-            'oracle/tfpp_oracle.py (torch CPU fp32), {threads} threads (fastest of 8/16/32/64)')
+            f'oracle/tfpp_oracle.py (torch CPU fp32), {threads} threads (fastest of 8/16/32/64)')
   line = {
       'impl': 'reference', 'metric': 'train_samples_per_s', 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus,
       'steps': ran, 'warmup': wu, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
