@@ -6,6 +6,8 @@ tcgen05 implicit-GEMM for every convolution / projection with BatchNorm statisti
 in the epilogue, and small dedicated kernels for everything else.  Each step cites the reference lines it replaces
 (paths relative to /root/reference/team_code).
 """
+import os
+
 import torch
 
 from . import ops
@@ -261,6 +263,12 @@ class Engine:
   def _save(self, **kw):
     if self.tape is not None:
       self.tape.append(kw)
+
+  def side_stream(self, device):
+    key = ('side_stream', str(device))
+    if key not in self._consts:
+      self._consts[key] = torch.cuda.Stream(device=device)
+    return self._consts[key]
 
   def _count_batch(self, bn):
     """BatchNorm.num_batches_tracked += 1.  Under a Trainer all the counters are views of one int64 buffer that is
@@ -633,8 +641,22 @@ class Engine:
     m, cfg = self.m, self.cfg
     self.new_arena(rgb.device)
     feats, fused, grid = self.backbone_forward(rgb, lidar_bev, training)
-    pred_checkpoint, pred_target_speed = self.planner(fused, target_point.to(rgb.device), ego_vel.to(rgb.device),
-                                                      command.to(rgb.device), training)
+    # the planner (≈100 tiny launches on a 65-token memory) and the dense heads are independent consumers of the
+    # backbone: the planner goes to a side stream and overlaps with the high-resolution decoders (fork / join, also
+    # under CUDA-graph capture); its tape records are tagged so the backward pass can do the same
+    tp, ev_, cmd = target_point.to(rgb.device), ego_vel.to(rgb.device), command.to(rgb.device)
+    overlap = rgb.is_cuda and os.environ.get('TFPP_NO_OVERLAP', '0') != '1'
+    if overlap:
+      main, side = torch.cuda.current_stream(), self.side_stream(rgb.device)
+      side.wait_stream(main)
+      first = len(self.tape) if self.tape is not None else 0
+      with torch.cuda.stream(side):
+        pred_checkpoint, pred_target_speed = self.planner(fused, tp, ev_, cmd, training)
+      if self.tape is not None:
+        for r in self.tape[first:]:
+          r['side'] = True
+    else:
+      pred_checkpoint, pred_target_speed = self.planner(fused, tp, ev_, cmd, training)
     pred_semantic = pred_depth = pred_bev_semantic = pred_bounding_box = None
     if cfg.use_semantic:
       pred_semantic = self.perspective_decoder(m.semantic_decoder, grid)
@@ -650,6 +672,8 @@ class Engine:
       self._save(op='bev_tail', src=x, out=pred_bev_semantic, ncls=ncls)
     if cfg.detect_boxes:
       pred_bounding_box = self.center_head_forward(feats)
+    if overlap:
+      main.wait_stream(side)
     return (None, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth, pred_bounding_box,
             None, None, None)
 

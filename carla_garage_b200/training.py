@@ -612,43 +612,71 @@ class Backward:
     for r in tape:
       if r['op'] == 'planner_mem':
         self.eng_mem = r['mem'].view(-1, r['d'])
-    depth_seed = seeds.pop('depth', None)
-    depth_conv = eng.m.depth_decoder.deconv3[2] if hasattr(eng.m, 'depth_decoder') else None
-    for r in reversed(tape):
-      op = r['op']
-      if op == 'conv_bias':
-        if depth_seed is not None and r['conv'] is depth_conv:
-          seeds[id(r['y'])] = depth_seed
-          depth_seed = None
-        self.conv_bias(r, seeds)
-      elif op == 'conv_bn':
-        self.conv_bn(r)
-      elif op == 'downsample':
-        self.downsample(r)
-      elif op == 'se':
-        self.se(r)
-      elif op == 'stem':
-        self.stem(r)
-      elif op == 'bilinear':
-        self.bilinear(r)
-      elif op == 'untokenise':
-        self.untokenise(r)
-      elif op == 'gpt_block':
-        self.gpt_block(r)
-      elif op == 'tokenise':
-        self.tokenise(r)
-      elif op == 'center_head':
-        self.center_head(r, seeds)
-      elif op == 'bev_tail':
-        self.bev_tail(r, seeds)
-      elif op == 'planner_head':
-        self.planner_head(r, seeds)
-      elif op == 'dec_layer':
-        self.dec_layer(r)
-      elif op == 'planner_mem':
-        self.planner_mem(r)
+    self._depth_seed = seeds.pop('depth', None)
+    self._depth_conv = eng.m.depth_decoder.deconv3[2] if hasattr(eng.m, 'depth_decoder') else None
+    side_idx = [i for i, r in enumerate(tape) if r.get('side')]
+    if not side_idx:
+      for r in reversed(tape):
+        self._dispatch(r, seeds)
+      return
+    # the planner records (tagged by Engine.forward) replay on the side stream, concurrently with the dense heads on the
+    # main stream; both only read the loss seeds, write disjoint gradients, and join before the backbone records
+    main, side = torch.cuda.current_stream(), eng.side_stream(self.st.grad.device)
+    keep = list(seeds.values())  # main-stream tensors the side stream reads: keep them allocated until the join
+    ready = torch.cuda.Event()
+    ready.record(main)
+    side.wait_event(ready)
+    lo = min(side_idx)
+    joined = False
+    for idx in range(len(tape) - 1, -1, -1):
+      r = tape[idx]
+      if r.get('side'):
+        with torch.cuda.stream(side):
+          self._dispatch(r, seeds)
       else:
-        raise RuntimeError(f'no backward handler for {op}')
+        if idx < lo and not joined:
+          main.wait_stream(side)
+          joined = True
+        self._dispatch(r, seeds)
+    if not joined:
+      main.wait_stream(side)
+    del keep
+
+  def _dispatch(self, r, seeds):
+    op = r['op']
+    if op == 'conv_bias':
+      if self._depth_seed is not None and r['conv'] is self._depth_conv:
+        seeds[id(r['y'])] = self._depth_seed
+        self._depth_seed = None
+      self.conv_bias(r, seeds)
+    elif op == 'conv_bn':
+      self.conv_bn(r)
+    elif op == 'downsample':
+      self.downsample(r)
+    elif op == 'se':
+      self.se(r)
+    elif op == 'stem':
+      self.stem(r)
+    elif op == 'bilinear':
+      self.bilinear(r)
+    elif op == 'untokenise':
+      self.untokenise(r)
+    elif op == 'gpt_block':
+      self.gpt_block(r)
+    elif op == 'tokenise':
+      self.tokenise(r)
+    elif op == 'center_head':
+      self.center_head(r, seeds)
+    elif op == 'bev_tail':
+      self.bev_tail(r, seeds)
+    elif op == 'planner_head':
+      self.planner_head(r, seeds)
+    elif op == 'dec_layer':
+      self.dec_layer(r)
+    elif op == 'planner_mem':
+      self.planner_mem(r)
+    else:
+      raise RuntimeError(f'no backward handler for {op}')
 
 
 # ---------------------------------------------------------------------------------------------------------------
