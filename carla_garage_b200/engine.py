@@ -264,8 +264,8 @@ class Engine:
     if self.tape is not None:
       self.tape.append(kw)
 
-  def side_stream(self, device):
-    key = ('side_stream', str(device))
+  def side_stream(self, device, which='planner'):
+    key = ('side_stream', which, str(device))
     if key not in self._consts:
       self._consts[key] = torch.cuda.Stream(device=device)
     return self._consts[key]
@@ -491,16 +491,45 @@ class Engine:
       raise RuntimeError('carla_garage_b200 runs on CUDA tensors only (no CPU fallback)')
     image = image.float().contiguous()
     lidar = lidar.float().contiguous()
+    # Training: between two fusion points the LiDAR branch (a quarter of the image branch's pixels: kernels that cannot
+    # fill 148 SMs) runs on a second stream next to the image branch.  Only with a tape: every tensor that crosses
+    # streams is then kept alive by a tape record until the step ends, which is what makes this safe with the caching
+    # allocator; the tape records are tagged so that the backward pass forks / joins the same way.
+    two = self.tape is not None and os.environ.get('TFPP_NO_OVERLAP', '0') != '1'
+    main = torch.cuda.current_stream()
+    side = self.side_stream(image.device, 'lidar') if two else None
+
+    def on_side(fn):
+      if not two:
+        return fn()
+      side.wait_stream(main)
+      first = len(self.tape)
+      with torch.cuda.stream(side):
+        out = fn()
+      for r in self.tape[first:]:
+        r['side'] = 'lidar'
+      return out
+
+    def joined(fn):
+      if not two:
+        return fn()
+      main.wait_stream(side)
+      first = len(self.tape)
+      out = fn()
+      for r in self.tape[first:]:
+        r['needs_side'] = 'lidar'
+      return out
+
+    lid = on_side(lambda: self.stem(lidar, bb.lidar_encoder['stem'], training, False))
     img = self.stem(image, bb.image_encoder['stem'], training, cfg.normalize_imagenet)
-    lid = self.stem(lidar, bb.lidar_encoder['stem'], training, False)
     self._tap('img_stem', img)
     self._tap('lid_stem', lid)
     for i in range(4):
+      lid = on_side(lambda lid=lid: self.regnet_stage(lid, bb.lidar_encoder[f's{i + 1}'], training))
       img = self.regnet_stage(img, bb.image_encoder[f's{i + 1}'], training)
-      lid = self.regnet_stage(lid, bb.lidar_encoder[f's{i + 1}'], training)
       self._tap(f'img_s{i + 1}_pre', img)
       self._tap(f'lid_s{i + 1}_pre', lid)
-      img, lid = self.fuse(img, lid, i, training)
+      img, lid = joined(lambda img=img, lid=lid: self.fuse(img, lid, i, training))
       self._tap(f'img_s{i + 1}', img)
       self._tap(f'lid_s{i + 1}', lid)
     feats = None
@@ -654,7 +683,7 @@ class Engine:
         pred_checkpoint, pred_target_speed = self.planner(fused, tp, ev_, cmd, training)
       if self.tape is not None:
         for r in self.tape[first:]:
-          r['side'] = True
+          r['side'] = 'planner'
     else:
       pred_checkpoint, pred_target_speed = self.planner(fused, tp, ev_, cmd, training)
     pred_semantic = pred_depth = pred_bev_semantic = pred_bounding_box = None

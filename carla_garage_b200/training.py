@@ -614,33 +614,69 @@ class Backward:
         self.eng_mem = r['mem'].view(-1, r['d'])
     self._depth_seed = seeds.pop('depth', None)
     self._depth_conv = eng.m.depth_decoder.deconv3[2] if hasattr(eng.m, 'depth_decoder') else None
-    side_idx = [i for i, r in enumerate(tape) if r.get('side')]
-    if not side_idx:
+    if not any(r.get('side') for r in tape):
       for r in reversed(tape):
         self._dispatch(r, seeds)
       return
-    # the planner records (tagged by Engine.forward) replay on the side stream, concurrently with the dense heads on the
-    # main stream; both only read the loss seeds, write disjoint gradients, and join before the backbone records
-    main, side = torch.cuda.current_stream(), eng.side_stream(self.st.grad.device)
-    keep = list(seeds.values())  # main-stream tensors the side stream reads: keep them allocated until the join
-    ready = torch.cuda.Event()
-    ready.record(main)
-    side.wait_event(ready)
-    lo = min(side_idx)
-    joined = False
+    # Records tagged by Engine.forward replay on their side stream: the planner next to the dense heads, the LiDAR branch
+    # of every stage next to the image branch.  A side segment starts after the main-stream work it depends on (the loss
+    # seeds / the fusion block above it: an event recorded on the main stream at that point), and the main stream joins
+    # a side stream before the first record that consumes its results.  Gradients popped while on a side stream are kept
+    # alive until that join: they were allocated on the main stream, whose allocator would otherwise hand the block out
+    # again while the side stream is still reading it.
+    dev = self.st.grad.device
+    main = torch.cuda.current_stream()
+    streams = {k: eng.side_stream(dev, k) for k in {r['side'] for r in tape if r.get('side')}}
+    keep = {k: [] for k in streams}
+    keep['seeds'] = list(seeds.values())
+    fork = torch.cuda.Event()
+    fork.record(main)
+    first_planner = min((i for i, r in enumerate(tape) if r.get('side') == 'planner'), default=-1)
+    pending_join = set()
+    outer = self
+
+    class KeepDict(dict):
+      def pop(self, *a):  # pylint: disable=arguments-differ
+        v = dict.pop(self, *a)
+        if outer._on_side is not None and torch.is_tensor(v):
+          keep[outer._on_side].append(v)
+        return v
+
+    self.G = KeepDict(self.G)
+    self._on_side = None
+
+    def join(k):
+      main.wait_stream(streams[k])
+      keep[k].clear()
+      pending_join.discard(k)
+
+    prev_side = None
     for idx in range(len(tape) - 1, -1, -1):
       r = tape[idx]
-      if r.get('side'):
-        with torch.cuda.stream(side):
+      k = r.get('side')
+      if k:
+        if prev_side != k:
+          streams[k].wait_event(fork)  # first record of a side segment: wait for the main-stream work above it
+        self._on_side = k
+        with torch.cuda.stream(streams[k]):
           self._dispatch(r, seeds)
+        self._on_side = None
+        pending_join.add(k)
       else:
-        if idx < lo and not joined:
-          main.wait_stream(side)
-          joined = True
+        need = r.get('needs_side')
+        if need and need in pending_join:
+          join(need)
+        if 'planner' in pending_join and idx < first_planner:
+          join('planner')  # the backbone consumes the planner's gradient of the fused features
         self._dispatch(r, seeds)
-    if not joined:
-      main.wait_stream(side)
-    del keep
+        if need:
+          fork = torch.cuda.Event()   # the LiDAR stage below this fusion block may start once it is done
+          fork.record(main)
+      prev_side = k
+    for k in list(pending_join):
+      join(k)
+    self._on_side = None
+    keep.clear()
 
   def _dispatch(self, r, seeds):
     op = r['op']
