@@ -10,7 +10,7 @@ import torch
 from . import engine as eng_mod
 from . import ops
 from .engine import packed
-from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32
+from .ops import ACT_NONE, ACT_RELU, BF16, F32
 
 LOSS_KEYS = ('loss_target_speed', 'loss_checkpoint', 'loss_semantic', 'loss_bev_semantic', 'loss_depth',
              'loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res')
@@ -316,8 +316,6 @@ class Backward:
     """weight gradient + input gradient of a bias-free conv given the gradient of its raw output."""
     st = self.st
     k = conv.weight.shape[-1]
-    cout = conv.weight.shape[0]
-    b, ho, wo, _ = draw.shape
     if grouped:  # RegNet 3x3 group conv; a = the full-resolution input whatever the stride
       gout = st.g(conv.weight)
       ops.gconv3x3_wgrad(draw, a, gout, stride)
