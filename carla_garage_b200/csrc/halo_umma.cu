@@ -1,0 +1,254 @@
+// EXPERIMENTAL — not on the product path in round 1 (engine uses it only with TFPP_HALO_UMMA=1; its tests only run
+// with TFPP_EXPERIMENTAL=1).  Written at the end of round 1 without GPU time left to validate it.
+//
+// Dense 3x3 convolution (stride 1, padding 1) with few channels at high resolution on tcgen05, WITHOUT re-reading the
+// input nine times: the haloed-tile kernels of smallc_conv.cu / gconv3x3.cu are bound by the legacy mma.sync pipe
+// (~540 TFLOP/s, a quarter of tcgen05), and the implicit-GEMM kernel of tc_gemm.cu by nine L2 reads of every tile.
+//
+// Idea: keep the haloed tile in shared memory in channel-chunk-major planes — plane c holds 8 channels (16 bytes) of
+// every tile pixel, pixels linear with a row pitch of PW = 64:  plane[c][y * 64 + x] (16 B each).  In the K-major,
+// NON-swizzled UMMA operand layout a core matrix is 8 rows x 16 B stored contiguously, i.e. exactly 8 consecutive
+// pixels of one plane; SBO = 128 B walks on along the pixels, LBO = plane size walks to the next 8 channels.  So the
+// A operand of tap (ky, kx) for 128 consecutive linear pixels is just a descriptor whose start address is shifted by
+// (ky * 64 + kx) pixels: nine descriptors over ONE tile, no im2col, no copies.  Linear pixels include the two halo
+// columns of each row (x = 62, 63): those outputs are junk and dropped (3 %).
+// One 4-D TMA box {8 ch, 64, 10, 1} per plane writes precisely this layout (hardware zero fill = padding).
+#include "../../include/tfpp.h"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int kThreadsH = 192;            // warp 0: TMA, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int PW = 64;                    // plane row pitch in pixels
+constexpr int TWO = PW - 2;               // output columns per tile (62)
+constexpr int THO = 8;                    // output rows per tile
+constexpr int PH = THO + 2;
+constexpr int MBLK = THO * PW / 128;      // 4 UMMA M blocks of 128 linear pixels
+constexpr int PLANE_BYTES = (PH * PW + 8) * 16;   // + 8 pixels slack: the last taps of the last block read 2 pixels past
+constexpr int kStagesH = 2;
+constexpr int kTmemColsH = 512;
+
+struct HParams {
+  const bf16* w;        // (9, K/8, N, 8) bf16: [tap][k chunk][n][8 k] — already in the shared-memory operand layout
+  const float* bias;    // optional (n_valid)
+  void* out;
+  int out_nchw_f32;     // 0: NHWC bf16 with N channels; 1: NCHW f32 with n_valid channels
+  int n_valid, act, act_n_limit;
+  int B, H, W, K, N;    // K = input channels (16/32/64), N = padded output channels (16/32/48/64)
+  int tiles_x, tiles_y;
+};
+
+__global__ void __launch_bounds__(kThreadsH, 1) halo_umma_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                         const HParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kchunks = p.K / 8;
+  const int stage_bytes = kchunks * PLANE_BYTES;
+  uint8_t* wsm = smem + kStagesH * stage_bytes;                          // [9][K/8][N][8] bf16
+  const int w_bytes = 9 * p.K * p.N * 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + ((w_bytes + 127) & ~127));
+  uint64_t* full_bar = bars;                  // [2] tile landed
+  uint64_t* empty_bar = bars + 2;             // [2] tile consumed by the MMAs
+  uint64_t* tfull_bar = bars + 4;             // [2] accumulators ready
+  uint64_t* tempty_bar = bars + 6;            // [2] accumulators drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int num_tiles = tiles_per_img * p.B;
+
+  // weights -> shared memory (generic proxy), made visible to the async proxy (UMMA) before the first MMA
+  for (int i = threadIdx.x; i < w_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.w) + i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    for (int s = 0; s < kStagesH; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemColsH)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer: one box per 8-channel plane
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int y0 = (r / p.tiles_x) * THO, x0 = (r % p.tiles_x) * TWO;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, static_cast<uint32_t>(kchunks * PH * PW * 16));
+        uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
+        for (int c = 0; c < kchunks; ++c)
+          tma_load_4d(smem_u32(st + c * PLANE_BYTES), &tmap_x, fb, c * 8, x0 - 1, y0 - 1, b);
+        if (++stage == kStagesH) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t idesc = make_idesc_bf16(128, p.N);
+      const uint32_t w_u = smem_u32(wsm);
+      const uint32_t w_tap_bytes = static_cast<uint32_t>(p.K * p.N * 2);
+      const uint32_t w_lbo = static_cast<uint32_t>(p.N * 16);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+        for (int blk = 0; blk < MBLK; ++blk) {
+          const uint32_t d_tmem = tmem_base + acc * 256 + blk * p.N;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint32_t a_start = st + static_cast<uint32_t>(blk * 128 + ky * PW + kx) * 16;
+            for (int kk = 0; kk < p.K / 16; ++kk) {
+              const uint64_t adesc = make_nosw_kmajor_desc(a_start + kk * 2 * PLANE_BYTES, PLANE_BYTES, 128);
+              const uint64_t bdesc = make_nosw_kmajor_desc(w_u + tap * w_tap_bytes + kk * 2 * w_lbo, w_lbo, 128);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | kk) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));    // the tile's planes may be overwritten
+        umma_commit(smem_u32(&tfull_bar[acc]));      // the accumulators are complete
+        if (++stage == kStagesH) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue: lane == linear tile pixel
+    const int lane_group = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int r = tile - b * tiles_per_img;
+      const int y0 = (r / p.tiles_x) * THO, x0 = (r % p.tiles_x) * TWO;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      for (int blk = 0; blk < MBLK; ++blk) {
+        const int m = blk * 128 + lane_group * 32 + lane;   // linear pixel of the tile
+        const int ty = m / PW, tx = m - ty * PW;
+        const int oy = y0 + ty, ox = x0 + tx;
+        const bool valid = tx < TWO && oy < p.H && ox < p.W;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + acc * 256 + blk * p.N;
+        for (int c = 0; c < p.N; c += 16) {
+          float v[16];
+          __syncwarp();
+          tmem_ld16(taddr + c, v);
+          if (!valid) continue;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = c + j;
+            float x = v[j];
+            if (p.bias != nullptr && n < p.n_valid) x += __ldg(p.bias + n);
+            if (p.act != ACT_NONE && (p.act_n_limit == 0 || n < p.act_n_limit)) x = apply_act(x, p.act);
+            v[j] = x;
+          }
+          if (p.out_nchw_f32) {
+            float* o = static_cast<float*>(p.out);
+            const long long hw = static_cast<long long>(p.H) * p.W;
+            const long long base = static_cast<long long>(b) * p.n_valid * hw + static_cast<long long>(oy) * p.W + ox;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c + j < p.n_valid) o[base + (c + j) * hw] = v[j];
+          } else {
+            bf16* o = static_cast<bf16*>(p.out) + ((static_cast<long long>(b) * p.H + oy) * p.W + ox) * p.N + c;
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+            o4[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                               pack_bf16x2(v[6], v[7]));
+            o4[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                               pack_bf16x2(v[14], v[15]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsH) : "memory");
+  }
+}
+
+}  // namespace
+
+extern "C" int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias, void* out, int out_nchw_f32,
+                                 int n_valid, int act, int act_n_limit, int batch, int height, int width, int cin,
+                                 int cout_padded, tfpp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TFPP_CHECK_ARG(cin == 16 || cin == 32 || cin == 64, "cin must be 16, 32 or 64");
+  TFPP_CHECK_ARG(cout_padded % 16 == 0 && cout_padded >= 16 && cout_padded <= 64, "cout_padded must be 16..64, % 16");
+  TFPP_CHECK_ARG(n_valid >= 1 && n_valid <= cout_padded, "n_valid <= cout_padded");
+  TFPP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0, "operands must be 16-byte aligned");
+  HParams p;
+  p.w = static_cast<const bf16*>(w); p.bias = bias; p.out = out; p.out_nchw_f32 = out_nchw_f32;
+  p.n_valid = n_valid; p.act = act; p.act_n_limit = act_n_limit;
+  p.B = batch; p.H = height; p.W = width; p.K = cin; p.N = cout_padded;
+  p.tiles_x = ceil_div(width, TWO);
+  p.tiles_y = ceil_div(height, THO);
+  CUtensorMap tmap;
+  {
+    const cuuint64_t c = cin, w_ = width, h = height, b = batch;
+    const cuuint64_t dims[4] = {c, w_, h, b};
+    const cuuint64_t strides[3] = {c * 2, w_ * c * 2, h * w_ * c * 2};
+    const cuuint32_t box[4] = {8, PW, PH, 1};
+    int rc = encode_map(&tmap, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + static_cast<size_t>(kStagesH) * (cin / 8) * PLANE_BYTES + ((9 * cin * cout_padded * 2 + 127) & ~127) + 256;
+  TFPP_CHECK_ARG(smem <= 227 * 1024, "shared memory budget exceeded");
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(halo_umma_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      tfpp_set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+      return TFPP_ERR_CUDA;
+    }
+    attr = true;
+  }
+  const long long tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * batch;
+  if (tiles == 0) return TFPP_OK;
+  const int grid = static_cast<int>(tiles < TFPP_NUM_SMS ? tiles : TFPP_NUM_SMS);
+  halo_umma_conv3x3_kernel<<<grid, kThreadsH, smem, stream>>>(tmap, p);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}

@@ -14,11 +14,12 @@ from . import ops
 from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_GELU, BF16, F32
 
 _PACK_CACHE = {}
+HALO_UMMA = os.environ.get('TFPP_HALO_UMMA', '0') == '1'  # experimental tcgen05 haloed-tile convs (round 2)
 PARAM_EPOCH = [0]  # bumped by the fused optimizer (it updates parameter storage without touching version counters)
 
 
 # kinds whose pack is a pure gather (+ zero padding) of parameter elements: eligible for the one-kernel PackPlan
-_GATHER_KINDS = frozenset(('conv', 'gconv', 'gconv_halo', 'gconv_halo_t', 'linear', 'conv_t', 'conv_rows_pad', 'conv_dgrad_smallc', 'gconv_t', 'linear_t',
+_GATHER_KINDS = frozenset(('conv', 'gconv', 'gconv_halo', 'gconv_halo_t', 'conv_halo_umma', 'conv_halo_umma_t', 'linear', 'conv_t', 'conv_rows_pad', 'conv_dgrad_smallc', 'gconv_t', 'linear_t',
                            'rows_t', 'cat_linear_t', 'cat_conv_t', 'blockdiag_1x1_t', 'rows', 'rows_f32', 'cat_linear',
                            'cat_rows', 'cat_rows_f32', 'cat_f32', 'cat_conv', 'blockdiag_1x1', 'repeat_rows'))
 
@@ -30,6 +31,10 @@ def _build_pack(kind, params, extra, dtb=BF16, dtf=F32):
     return ops.pack_conv_weight(params[0], dt=dtb)
   if kind == 'gconv':
     return ops.pack_grouped_conv_weight(params[0], dt=dtb)
+  if kind == 'conv_halo_umma':  # experimental tcgen05 haloed-tile conv: (9, Cin/8, extra[0], 8)
+    return ops.pack_halo_umma_weight(params[0], extra[0], dt=dtb)
+  if kind == 'conv_halo_umma_t':  # its input-gradient operand, K padded to extra[0]
+    return ops.pack_halo_umma_weight(params[0], params[0].shape[1], transpose=True, k_pad=extra[0], dt=dtb)
   if kind == 'gconv_halo':  # (C,24,3,3) -> (C/24, 9, 24, 24) for tfpp_gconv3x3
     return ops.pack_gconv_halo(params[0], dt=dtb)
   if kind == 'gconv_halo_t':  # its input-gradient operand
@@ -356,12 +361,18 @@ class Engine:
     cpad = 8 if cout <= 8 else (16 if cout <= 16 else 32)
     smallc = (k == 3 and cout <= 32 and ops.smallc_supported(cin, cpad) and a.shape[1] * a.shape[2] >= 4096 and
               (kw.get('out_layout') == 'nchw' or cout == cpad) and not set(kw) - {'out_layout', 'out_f32'})
-    if smallc:  # high-resolution, few channels: haloed shared-memory tile kernel (HBM-bound layers)
+    npad = 16 if cout <= 16 else 32
+    halo = (smallc and HALO_UMMA and ops.halo_umma_supported(cin, npad) and
+            (kw.get('out_layout') == 'nchw' or cout == npad))
+    if halo:  # EXPERIMENTAL (TFPP_HALO_UMMA=1): the same layers on tcgen05 (csrc/halo_umma.cu)
+      y = ops.halo_conv3x3(a, packed(conv.weight, 'conv_halo_umma', npad), bias=packed(conv.bias, 'f32'), act=act,
+                           n_valid=cout, out_nchw_f32=kw.get('out_layout') == 'nchw')
+    elif smallc:  # high-resolution, few channels: haloed shared-memory tile kernel (HBM-bound layers)
       y = ops.smallc_conv3x3(a, packed(conv.weight, 'conv_rows_pad', cpad), bias=packed(conv.bias, 'f32'), act=act,
                              n_valid=cout, out_nchw_f32=kw.get('out_layout') == 'nchw')
     else:
       y = ops.conv_gemm(a, packed(conv.weight, 'conv'), taps=taps, shift=packed(conv.bias, 'f32'), act=act, **kw)
-    self._save(op='conv_bias', a=a, y=y, conv=conv, act=act, taps=taps, kw=kw, smallc=smallc)
+    self._save(op='conv_bias', a=a, y=y, conv=conv, act=act, taps=taps, kw=kw, smallc=smallc, halo=halo)
     return y
 
   # ------------------------------------------------------------------------------------------------ RegNet

@@ -677,6 +677,43 @@ def small_mha_bwd(q, k, v, dout, dq, dk, dv, batch, heads, tq, tk, head_dim, q_s
         'tfpp_small_mha_bwd')
 
 
+# ---------------------------------------------------------------------------------------------- experimental: halo UMMA
+def pack_halo_umma_weight(w, n_pad, transpose=False, k_pad=None, dt=BF16):
+  """(Cout, Cin, 3, 3) -> (9, K/8, n_pad, 8) = [tap][k chunk][n][8 k], the non-swizzled K-major UMMA operand layout
+  (zero padded to n_pad output and k_pad input channels).  transpose=True: the input-gradient operand (in/out
+  swapped, taps spatially flipped)."""
+  wd = w.detach()
+  if transpose:
+    wd = wd.flip(2, 3).permute(1, 0, 2, 3)
+  n, k = wd.shape[0], wd.shape[1]
+  k_pad = k if k_pad is None else k_pad
+  assert k_pad % 8 == 0 and k <= k_pad and n <= n_pad
+  if k_pad > k or n_pad > n:
+    wd = torch.nn.functional.pad(wd, (0, 0, 0, 0, 0, k_pad - k, 0, n_pad - n))
+  t = wd.permute(2, 3, 1, 0).reshape(9, k_pad // 8, 8, n_pad).permute(0, 1, 3, 2)  # [tap][kc][n][8]
+  return t.to(dt).contiguous()
+
+
+def halo_umma_supported(cin, n_pad):
+  return cin in (16, 32, 64) and n_pad in (16, 32, 48, 64) and 9 * cin * n_pad * 2 + 2 * (cin // 8) * 10368 <= 220 * 1024
+
+
+def halo_conv3x3(x, w_packed, bias=None, act=ACT_NONE, act_n_limit=0, n_valid=None, out_nchw_f32=False):
+  """EXPERIMENTAL tcgen05 haloed-tile 3x3 conv (csrc/halo_umma.cu); same contract as smallc_conv3x3."""
+  _dev(x, BF16)
+  _dev(w_packed, BF16)
+  b, h, wd, cin = x.shape
+  n_pad = w_packed.shape[2]
+  n_valid = n_pad if n_valid is None else n_valid
+  if out_nchw_f32:
+    out = torch.empty((b, n_valid, h, wd), dtype=F32, device=x.device)
+  else:
+    out = torch.empty((b, h, wd, n_pad), dtype=BF16, device=x.device)
+  check(_lib.load().tfpp_halo_conv3x3(x.data_ptr(), w_packed.data_ptr(), _p(bias), out.data_ptr(), int(out_nchw_f32),
+                                      n_valid, act, act_n_limit, b, h, wd, cin, n_pad, _stream()), 'tfpp_halo_conv3x3')
+  return out
+
+
 # ---------------------------------------------------------------------------------------------- small-channel convs
 def smallc_supported(cin, cout_pad):
   return (cin, cout_pad) in ((32, 32), (32, 16), (32, 8), (16, 32))

@@ -283,7 +283,10 @@ class Backward:
     cp = dz.shape[3]
     if r.get('smallc') and cp in (16, 32):
       ops.smallc_wgrad3x3(dz, a, st.g(conv.weight), (cin * 9, 1, 9), cout)
-      da = ops.smallc_conv3x3(dz, packed(conv.weight, 'conv_dgrad_smallc', cp))
+      if r.get('halo') and ops.halo_umma_supported(cp, cin):  # experimental tcgen05 path (TFPP_HALO_UMMA=1)
+        da = ops.halo_conv3x3(dz, packed(conv.weight, 'conv_halo_umma_t', cp))
+      else:
+        da = ops.smallc_conv3x3(dz, packed(conv.weight, 'conv_dgrad_smallc', cp))
       if id(a) in self.G:
         ops.add_bf16(self.G[id(a)], da, out=da)
       self.G[id(a)] = da

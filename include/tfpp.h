@@ -299,6 +299,13 @@ long long tfpp_gconv3x3_wgrad_workspace(int batch, int height, int width, int ch
 int tfpp_gconv3x3_wgrad(const void* dy, const void* x, float* dw, float* workspace, int batch, int height, int width,
                         int channels, int stride, tfpp_stream_t stream);
 
+/* EXPERIMENTAL (not on the default path in round 1, see csrc/halo_umma.cu): dense 3x3 conv, stride 1, pad 1, on tcgen05
+ * from a haloed shared-memory tile held in 8-channel planes (no im2col, the input is read once).  x (B,H,W,cin) NHWC
+ * bf16, cin in {16,32,64}; w (9, cin/8, cout_padded, 8) bf16 = [tap][k chunk][n][8 k] (ops.pack_halo_umma_weight);
+ * out NHWC bf16 (cout_padded channels) or NCHW f32 (n_valid channels).  Same role as tfpp_smallc_conv3x3. */
+int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias, void* out, int out_nchw_f32, int n_valid, int act,
+                      int act_n_limit, int batch, int height, int width, int cin, int cout_padded, tfpp_stream_t stream);
+
 /* Weight-pack refresh: out[i] = idx[i] >= 0 ? flat[idx[i]] : 0 for i < n (n % 8 == 0), cast to bf16 (out_f32 = 0) or
  * kept fp32.  One launch rebuilds every kernel-layout weight copy after the optimizer step; replaces the implicit
  * per-module weight reads of torch's conv / linear kernels (team_code/train.py:898-908 loop). */

@@ -106,7 +106,8 @@ def test_pack_plan_index_maps_reproduce_every_gather_pack():
   cases = [('conv', (params['conv'],), ()), ('conv_t', (params['conv'],), ()), ('conv_rows_pad', (params['conv'],), (64,)),
            ('conv_dgrad_smallc', (params['conv'],), (64,)), ('gconv', (params['gconv'],), ()),
            ('gconv_t', (params['gconv'],), ()), ('gconv_halo', (params['gconv'],), ()),
-           ('gconv_halo_t', (params['gconv'],), ()), ('linear', (params['lin_a'],), ()), ('linear_t', (params['lin_a'],), ()),
+           ('gconv_halo_t', (params['gconv'],), ()), ('conv_halo_umma', (params['conv'],), (64,)),
+           ('conv_halo_umma_t', (params['conv'],), (48,)), ('linear', (params['lin_a'],), ()), ('linear_t', (params['lin_a'],), ()),
            ('rows', (params['lin_a'],), (8, 24)), ('rows_t', (params['lin_a'],), (8, 24)),
            ('rows_f32', (params['lin_a'],), (8, 24)), ('cat_linear', (params['lin_a'], params['lin_b']), ()),
            ('cat_linear_t', (params['lin_a'], params['lin_b']), ()), ('cat_rows', (params['lin_a'], params['lin_b']), (0, 8)),
@@ -130,3 +131,49 @@ def test_pack_plan_index_maps_reproduce_every_gather_pack():
   other = torch.randn(8, 8)
   plan.register(('linear', id(other)), 'linear', (other,), (), E._build_pack('linear', (other,), ()))  # pylint: disable=protected-access
   assert ('linear', id(other)) not in plan.pending
+
+
+def test_halo_umma_layout_math_reproduces_conv3x3():
+  """Host-side model of the experimental halo-UMMA kernel (csrc/halo_umma.cu): channel-chunk-major halo planes with a
+  64-pixel pitch, tap = start-address shift of (ky*64 + kx) pixels, weights packed [tap][k chunk][n][8].  Emulating
+  exactly that addressing in torch must reproduce F.conv2d; junk columns (x = 62, 63) are dropped."""
+  import torch
+  import torch.nn.functional as F
+  from carla_garage_b200 import ops
+  g = torch.Generator().manual_seed(0)
+  cin, cout, n_pad, h, w = 16, 7, 16, 11, 70
+  x = torch.randn(1, h, w, cin, generator=g)
+  wt = torch.randn(cout, cin, 3, 3, generator=g) * 0.1
+  want = F.conv2d(x.permute(0, 3, 1, 2), wt, padding=1)[0]  # (cout, h, w)
+  wp = ops.pack_halo_umma_weight(wt, n_pad, dt=torch.float32)  # (9, K/8, N, 8)
+  PW, THO = 64, 8
+  PH = THO + 2
+  got = torch.zeros(cout, h, w)
+  for y0 in range(0, h, THO):
+    for x0 in range(0, w, PW - 2):
+      # what the TMA box {8, 64, 10, 1} at (c*8, x0-1, y0-1) writes, with zero fill outside the image
+      planes = torch.zeros(cin // 8, PH * PW + 8, 8)
+      for py in range(PH):
+        for px in range(PW):
+          yy, xx = y0 - 1 + py, x0 - 1 + px
+          if 0 <= yy < h and 0 <= xx < w:
+            planes[:, py * PW + px, :] = x[0, yy, xx].view(cin // 8, 8)
+      acc = torch.zeros(THO * PW, n_pad)
+      m = torch.arange(THO * PW)
+      for tap in range(9):
+        ky, kx = divmod(tap, 3)
+        a = planes[:, m + ky * PW + kx, :]                       # (K/8, M, 8): rows = linear pixels shifted by the tap
+        acc += torch.einsum('cmj,cnj->mn', a, wp[tap])           # contraction over (chunk, 8)
+      for mm in range(THO * PW):
+        ty, tx = divmod(mm, PW)
+        if tx < PW - 2 and y0 + ty < h and x0 + tx < w:
+          got[:, y0 + ty, x0 + tx] = acc[mm, :cout]
+  assert torch.allclose(got, want, atol=1e-4), float((got - want).abs().max())
+  # the input-gradient pack: conv of dY with it equals autograd's dX
+  xg = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+  wt2 = torch.randn(16, cin, 3, 3, generator=g) * 0.1
+  dy = torch.randn(1, 16, h, w, generator=g)
+  F.conv2d(xg, wt2, padding=1).backward(dy)
+  wpt = ops.pack_halo_umma_weight(wt2, cin, transpose=True, dt=torch.float32)  # (9, 16/8, cin, 8)
+  w_eq = wpt.permute(2, 1, 3, 0).reshape(cin, 16, 3, 3)  # back to (out = cin, in = 16, ky, kx) of the equivalent conv
+  assert torch.allclose(F.conv2d(dy, w_eq, padding=1), xg.grad, atol=1e-4)

@@ -501,3 +501,28 @@ def test_gconv3x3_stride2_input_gradient(ops, b, ho, wo, c):
   got = ops.gconv3x3_dgrad_s2(dy, ops.pack_gconv_halo(wt, transpose=True))
   assert got.shape == (b, 2 * ho, 2 * wo, c)
   assert rel(got.float().permute(0, 3, 1, 2), x.grad) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ experimental kernels
+@pytest.mark.skipif(os.environ.get('TFPP_EXPERIMENTAL', '0') != '1', reason='experimental kernel, opt-in (round 2)')
+@pytest.mark.parametrize('cin,cout,n_pad,h,w', [(32, 32, 32, 16, 128), (32, 7, 16, 24, 70), (16, 32, 32, 8, 62),
+                                                (64, 32, 32, 9, 130)])
+def test_halo_umma_conv3x3(ops, cin, cout, n_pad, h, w):
+  """tfpp_halo_conv3x3 (tcgen05 over channel-chunk-major halo planes) against F.conv2d; forward and the dgrad pack."""
+  b = 2
+  x = bf(rnd(b, h, w, cin, seed=1))
+  wt = rnd(cout, cin, 3, 3, seed=2, scale=0.1)
+  bias = rnd(cout, seed=3)
+  want = F.conv2d(x.float().permute(0, 3, 1, 2), bf(wt).float(), bias, padding=1)
+  y = ops.halo_conv3x3(x, ops.pack_halo_umma_weight(wt, n_pad), bias=bias, n_valid=cout)
+  assert rel(y.float()[..., :cout].permute(0, 3, 1, 2), want) < 4e-3
+  y2 = ops.halo_conv3x3(x, ops.pack_halo_umma_weight(wt, n_pad), bias=bias, n_valid=cout, act=ops.ACT_RELU,
+                        out_nchw_f32=True)
+  assert rel(y2, F.relu(want)) < 4e-3
+  if cout % 8 == 0 and cout in (16, 32, 64):
+    dy = bf(rnd(b, h, w, cout, seed=4))
+    xg = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.conv2d(xg, bf(wt).float(), padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    cin_pad = cin
+    dx = ops.halo_conv3x3(dy, ops.pack_halo_umma_weight(wt, cin_pad, transpose=True))
+    assert rel(dx.float().permute(0, 3, 1, 2), xg.grad) < 4e-3
