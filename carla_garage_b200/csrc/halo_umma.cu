@@ -1,5 +1,6 @@
-// EXPERIMENTAL — not on the product path in round 1 (engine uses it only with TFPP_HALO_UMMA=1; its tests only run
-// with TFPP_EXPERIMENTAL=1).  Written at the end of round 1 without GPU time left to validate it.
+// EXPERIMENTAL — not on the product path in round 1 (the engine uses it only with TFPP_HALO_UMMA=1).  Written at the
+// very end of round 1: op-level parity against F.conv2d is green on B200 (tests/test_ops_gpu.py::test_halo_umma_conv3x3,
+// profiles/r01_halo_umma_optest_v19.log) but it has not been timed or run inside the training step yet.
 //
 // Dense 3x3 convolution (stride 1, padding 1) with few channels at high resolution on tcgen05, WITHOUT re-reading the
 // input nine times: the haloed-tile kernels of smallc_conv.cu / gconv3x3.cu are bound by the legacy mma.sync pipe

@@ -299,7 +299,7 @@ long long tfpp_gconv3x3_wgrad_workspace(int batch, int height, int width, int ch
 int tfpp_gconv3x3_wgrad(const void* dy, const void* x, float* dw, float* workspace, int batch, int height, int width,
                         int channels, int stride, tfpp_stream_t stream);
 
-/* EXPERIMENTAL (not on the default path in round 1, see csrc/halo_umma.cu): dense 3x3 conv, stride 1, pad 1, on tcgen05
+/* EXPERIMENTAL (op-level parity green on B200, not on the default path in round 1, see csrc/halo_umma.cu): dense 3x3 conv, stride 1, pad 1, on tcgen05
  * from a haloed shared-memory tile held in 8-channel planes (no im2col, the input is read once).  x (B,H,W,cin) NHWC
  * bf16, cin in {16,32,64}; w (9, cin/8, cout_padded, 8) bf16 = [tap][k chunk][n][8 k] (ops.pack_halo_umma_weight);
  * out NHWC bf16 (cout_padded channels) or NCHW f32 (n_valid channels).  Same role as tfpp_smallc_conv3x3. */

@@ -503,8 +503,8 @@ def test_gconv3x3_stride2_input_gradient(ops, b, ho, wo, c):
   assert rel(got.float().permute(0, 3, 1, 2), x.grad) < 4e-3
 
 
-# ------------------------------------------------------------------------------------------------ experimental kernels
-@pytest.mark.skipif(os.environ.get('TFPP_EXPERIMENTAL', '0') != '1', reason='experimental kernel, opt-in (round 2)')
+# ------------------------------------------------------------------------------------------------ tcgen05 haloed-tile conv
+# (op-level parity green on B200, profiles/r01_halo_umma_optest_v19.log; the engine only uses it with TFPP_HALO_UMMA=1)
 @pytest.mark.parametrize('cin,cout,n_pad,h,w', [(32, 32, 32, 16, 128), (32, 7, 16, 24, 70), (16, 32, 32, 8, 62),
                                                 (64, 32, 32, 9, 130)])
 def test_halo_umma_conv3x3(ops, cin, cout, n_pad, h, w):
