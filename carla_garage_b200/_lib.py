@@ -72,6 +72,7 @@ _PROTOS = {
     'tfpp_gconv3x3_dgrad_s2': [P, P, P, I, I, I, I, P],
     'tfpp_gconv3x3_wgrad': [P, P, P, P, I, I, I, I, I, P],
     'tfpp_gconv3x3_wgrad_workspace': [I, I, I, I, I],
+    'tfpp_halo_gconv3x3': [P, P, P, P, P, I, P, P, I, I, I, I, P],
     'tfpp_halo_conv3x3': [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     'tfpp_gather_pack': [P, P, P, L, I, P],
     'tfpp_se_bwd': [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, I, I, I, P],

@@ -209,7 +209,272 @@ __global__ void __launch_bounds__(kThreadsH, 1) halo_umma_conv3x3_kernel(const _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL, NOT YET RUN ON A GPU — the RegNet group conv (width 24, stride 1) on the same plane layout.
+// A 72-channel slab = 3 groups = 9 planes (+ 1 more plane so that the zero-padded K = 32 of the last group reads
+// defined memory: channels 72..79 of the slab window, real data or TMA zero fill, multiplied by zero weight rows).
+// Group g uses planes 3g..3g+3 (K = 32: 24 real channels + 8 that meet zero weights) and its own 9 x [32 k][32 n]
+// weight block (24 real output channels); one CTA works on one slab (grid = CTAs per slab x slabs) so the 55 KB of
+// weights are loaded once.  Tile = 4 rows x 62 columns (2 UMMA blocks of 128 linear pixels), double buffered.
+// Epilogue: 24 of the 32 accumulator columns per group -> bf16 NHWC; BatchNorm batch statistics (sum, sum of squares
+// over the valid pixels) through a shared-memory transpose, accumulated per CTA and flushed once.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GTHO = 4;
+constexpr int GPH = GTHO + 2;
+constexpr int GMBLK = GTHO * PW / 128;                    // 2
+constexpr int GPLANE_BYTES = (GPH * PW + 8) * 16;         // 6272
+constexpr int GPLANES = 10;
+constexpr int GW_BYTES = 3 * 9 * 32 * 32 * 2;             // 55296: [group][tap][k chunk 4][n 32][8]
+
+struct HGParams {
+  const bf16* w;         // (C/24, 9, 4, 32, 8) bf16: [group][tap][k chunk][n][8 k], zero padded from 24 to 32 both ways
+  bf16* out;             // (B,H,W,C)
+  const float* scale;    // optional folded BatchNorm (eval)
+  const float* shift;
+  int act;
+  float* stat_sum;       // optional BatchNorm batch statistics (C each)
+  float* stat_sq;
+  int B, H, W, C;
+  int tiles_x, tiles_y;
+};
+
+__global__ void __launch_bounds__(kThreadsH, 1) halo_umma_gconv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                          const HGParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int stage_bytes = GPLANES * GPLANE_BYTES;                   // 62720
+  uint8_t* wsm = smem + kStagesH * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + GW_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + 2;
+  uint64_t* tfull_bar = bars + 4;
+  uint64_t* tempty_bar = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sstat = reinterpret_cast<float*>(bars + 10);                   // [2][72] per-CTA statistics
+  float* trbuf = sstat + 2 * 72;                                        // 4 x [32][33] transpose tiles
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab = blockIdx.y;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int num_tiles = tiles_per_img * p.B;
+
+  for (int i = threadIdx.x; i < GW_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.w) + static_cast<long long>(slab) * (GW_BYTES / 16) + i);
+  for (int i = threadIdx.x; i < 2 * 72; i += blockDim.x) sstat[i] = 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    for (int s = 0; s < kStagesH; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemColsH)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int y0 = (r / p.tiles_x) * GTHO, x0 = (r % p.tiles_x) * TWO;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, static_cast<uint32_t>(GPLANES * GPH * PW * 16));
+        uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
+        for (int c = 0; c < GPLANES; ++c)
+          tma_load_4d(smem_u32(st + c * GPLANE_BYTES), &tmap_x, fb, slab * 72 + c * 8, x0 - 1, y0 - 1, b);
+        if (++stage == kStagesH) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t idesc = make_idesc_bf16(128, 32);
+      const uint32_t w_u = smem_u32(wsm);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+        for (int g = 0; g < 3; ++g) {
+          for (int blk = 0; blk < GMBLK; ++blk) {
+            const uint32_t d_tmem = tmem_base + acc * 256 + (g * GMBLK + blk) * 32;
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              const uint32_t a_start = st + (g * 3) * GPLANE_BYTES + static_cast<uint32_t>(blk * 128 + ky * PW + kx) * 16;
+              const uint32_t b_start = w_u + (g * 9 + tap) * (32 * 32 * 2);
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t adesc = make_nosw_kmajor_desc(a_start + kk * 2 * GPLANE_BYTES, GPLANE_BYTES, 128);
+                const uint64_t bdesc = make_nosw_kmajor_desc(b_start + kk * 2 * (32 * 16), 32 * 16, 128);
+                umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | kk) ? 1u : 0u);
+              }
+            }
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));
+        umma_commit(smem_u32(&tfull_bar[acc]));
+        if (++stage == kStagesH) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int lane_group = warp & 3;
+    float* tr = trbuf + (warp - 2) * (32 * 33);
+    const bool has_stats = p.stat_sum != nullptr;
+    const bool has_affine = p.scale != nullptr;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int r = tile - b * tiles_per_img;
+      const int y0 = (r / p.tiles_x) * GTHO, x0 = (r % p.tiles_x) * TWO;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      for (int blk = 0; blk < GMBLK; ++blk) {
+        const int m = blk * 128 + lane_group * 32 + lane;
+        const int ty = m / PW, tx = m - ty * PW;
+        const int oy = y0 + ty, ox = x0 + tx;
+        const bool valid = tx < TWO && oy < p.H && ox < p.W;
+        const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+        for (int g = 0; g < 3; ++g) {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + acc * 256 +
+                                 (g * GMBLK + blk) * 32;
+          uint32_t rr[32];
+          __syncwarp();
+          tmem_ld32_issue(taddr, rr);
+          tmem_ld_wait32(rr);
+          const int c0 = slab * 72 + g * 24;
+          if (has_stats) {
+#pragma unroll
+            for (int j = 0; j < 24; ++j) tr[lane * 33 + j] = __uint_as_float(rr[j]);
+            __syncwarp();
+            if (lane < 24) {
+              float ssum = 0.f, ssq = 0.f;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                const float a = ((valid_mask >> q) & 1u) ? tr[q * 33 + lane] : 0.f;
+                ssum += a;
+                ssq = fmaf(a, a, ssq);
+              }
+              atomicAdd(&sstat[g * 24 + lane], ssum);
+              atomicAdd(&sstat[72 + g * 24 + lane], ssq);
+            }
+            __syncwarp();
+          }
+          if (valid) {
+            float v[24];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+              float x = __uint_as_float(rr[j]);
+              if (has_affine) x = fmaf(x, __ldg(p.scale + c0 + j), __ldg(p.shift + c0 + j));
+              if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+              v[j] = x;
+            }
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + ((static_cast<long long>(b) * p.H + oy) * p.W + ox) * p.C + c0);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              o4[q] = make_uint4(pack_bf16x2(v[q * 8], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                                 pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (has_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = (warp - 2) * 32 + lane;
+      for (int i = et; i < 72; i += 128) {
+        atomicAdd(p.stat_sum + slab * 72 + i, sstat[i]);
+        atomicAdd(p.stat_sq + slab * 72 + i, sstat[72 + i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsH) : "memory");
+  }
+}
+
 }  // namespace
+
+extern "C" int tfpp_halo_gconv3x3(const void* x, const void* w, void* out, const float* scale, const float* shift, int act,
+                                  float* stat_sum, float* stat_sq, int batch, int height, int width, int channels,
+                                  tfpp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TFPP_CHECK_ARG(channels % 72 == 0, "channels must be a multiple of 72 (3 groups of width 24)");
+  TFPP_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift go together");
+  TFPP_CHECK_ARG((stat_sum == nullptr) == (stat_sq == nullptr), "stat_sum and stat_sq go together");
+  TFPP_CHECK_ARG(act == ACT_NONE || act == ACT_RELU, "activation: none or relu");
+  HGParams p;
+  p.w = static_cast<const bf16*>(w); p.out = static_cast<bf16*>(out); p.scale = scale; p.shift = shift; p.act = act;
+  p.stat_sum = stat_sum; p.stat_sq = stat_sq;
+  p.B = batch; p.H = height; p.W = width; p.C = channels;
+  p.tiles_x = ceil_div(width, TWO);
+  p.tiles_y = ceil_div(height, GTHO);
+  CUtensorMap tmap;
+  {
+    const cuuint64_t c = channels, w_ = width, h = height, b = batch;
+    const cuuint64_t dims[4] = {c, w_, h, b};
+    const cuuint64_t strides[3] = {c * 2, w_ * c * 2, h * w_ * c * 2};
+    const cuuint32_t box[4] = {8, PW, GPH, 1};
+    int rc = encode_map(&tmap, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + static_cast<size_t>(kStagesH) * GPLANES * GPLANE_BYTES + GW_BYTES + 80 + sizeof(float) * (2 * 72 + 4 * 32 * 33) + 64;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(halo_umma_gconv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      tfpp_set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+      return TFPP_ERR_CUDA;
+    }
+    attr = true;
+  }
+  const long long tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * batch;
+  if (tiles == 0) return TFPP_OK;
+  const int slabs = channels / 72;
+  long long per_slab = TFPP_NUM_SMS / slabs;
+  if (per_slab < 1) per_slab = 1;
+  if (per_slab > tiles) per_slab = tiles;
+  dim3 grid(static_cast<unsigned>(per_slab), slabs);
+  halo_umma_gconv3x3_kernel<<<grid, kThreadsH, smem, stream>>>(tmap, p);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
 
 extern "C" int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias, void* out, int out_nchw_f32,
                                  int n_valid, int act, int act_n_limit, int batch, int height, int width, int cin,

@@ -15,11 +15,12 @@ from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_GELU, BF16, F32
 
 _PACK_CACHE = {}
 HALO_UMMA = os.environ.get('TFPP_HALO_UMMA', '0') == '1'  # experimental tcgen05 haloed-tile convs (round 2)
+HALO_UMMA_GCONV = os.environ.get('TFPP_HALO_UMMA_GCONV', '0') == '1'  # same for the RegNet group convs (never run yet)
 PARAM_EPOCH = [0]  # bumped by the fused optimizer (it updates parameter storage without touching version counters)
 
 
 # kinds whose pack is a pure gather (+ zero padding) of parameter elements: eligible for the one-kernel PackPlan
-_GATHER_KINDS = frozenset(('conv', 'gconv', 'gconv_halo', 'gconv_halo_t', 'conv_halo_umma', 'conv_halo_umma_t', 'linear', 'conv_t', 'conv_rows_pad', 'conv_dgrad_smallc', 'gconv_t', 'linear_t',
+_GATHER_KINDS = frozenset(('conv', 'gconv', 'gconv_halo', 'gconv_halo_t', 'gconv_halo_umma', 'gconv_halo_umma_t', 'conv_halo_umma', 'conv_halo_umma_t', 'linear', 'conv_t', 'conv_rows_pad', 'conv_dgrad_smallc', 'gconv_t', 'linear_t',
                            'rows_t', 'cat_linear_t', 'cat_conv_t', 'blockdiag_1x1_t', 'rows', 'rows_f32', 'cat_linear',
                            'cat_rows', 'cat_rows_f32', 'cat_f32', 'cat_conv', 'blockdiag_1x1', 'repeat_rows'))
 
@@ -31,6 +32,10 @@ def _build_pack(kind, params, extra, dtb=BF16, dtf=F32):
     return ops.pack_conv_weight(params[0], dt=dtb)
   if kind == 'gconv':
     return ops.pack_grouped_conv_weight(params[0], dt=dtb)
+  if kind == 'gconv_halo_umma':  # experimental tcgen05 group conv: (C/24, 9, 4, 32, 8)
+    return ops.pack_halo_gconv_weight(params[0], dt=dtb)
+  if kind == 'gconv_halo_umma_t':
+    return ops.pack_halo_gconv_weight(params[0], transpose=True, dt=dtb)
   if kind == 'conv_halo_umma':  # experimental tcgen05 haloed-tile conv: (9, Cin/8, extra[0], 8)
     return ops.pack_halo_umma_weight(params[0], extra[0], dt=dtb)
   if kind == 'conv_halo_umma_t':  # its input-gradient operand, K padded to extra[0]
@@ -324,7 +329,9 @@ class Engine:
     pool = self.zeros((b, cout), a.device) if want_pool else None
     if training:
       stats = self.zeros((2, cout), a.device)
-      if grouped:
+      if grouped and HALO_UMMA_GCONV and stride == 1:  # EXPERIMENTAL (TFPP_HALO_UMMA_GCONV=1)
+        raw = ops.halo_gconv3x3(a, packed(cna.conv.weight, 'gconv_halo_umma'), stats=(stats[0], stats[1]))
+      elif grouped:
         raw = ops.gconv3x3(a, w, stride, stats=(stats[0], stats[1]))
       else:
         raw = ops.conv_gemm(a, w, taps=taps, batch=batch, stats=(stats[0], stats[1]))
@@ -343,7 +350,10 @@ class Engine:
                  batch=batch, grouped=grouped, stride=stride, act=act, res=res, res_bn=res_bn)
       return (y, pool) if want_pool else y
     scale, shift = packed((bn.weight, bn.bias, bn.running_mean, bn.running_var), 'bn_eval', bn.eps)
-    if grouped:
+    if grouped and HALO_UMMA_GCONV and stride == 1:
+      assert res is None
+      y = ops.halo_gconv3x3(a, packed(cna.conv.weight, 'gconv_halo_umma'), scale=scale, shift=shift, act=act)
+    elif grouped:
       assert res is None
       y = ops.gconv3x3(a, w, stride, scale=scale, shift=shift, act=act)
     else:

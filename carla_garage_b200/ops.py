@@ -698,6 +698,32 @@ def halo_umma_supported(cin, n_pad):
   return cin in (16, 32, 64) and n_pad in (16, 32, 48, 64) and 9 * cin * n_pad * 2 + 2 * (cin // 8) * 10368 <= 220 * 1024
 
 
+def pack_halo_gconv_weight(w, transpose=False, dt=BF16):
+  """(C, 24, 3, 3) group conv weight -> (C/24, 9, 4, 32, 8) = [group][tap][k chunk][n][8 k], zero padded from 24 to 32
+  input and output channels (tfpp_halo_gconv3x3).  transpose=True: the stride-1 input-gradient operand."""
+  c, gw, kh, kw = w.shape
+  g = c // gw
+  wg = w.detach().view(g, gw, gw, kh, kw)  # [g][co][ci][ky][kx]
+  if transpose:
+    wg = wg.flip(3, 4).permute(0, 2, 1, 3, 4)  # [g][ci (new out)][co (new in)][ky'][kx']
+  wg = torch.nn.functional.pad(wg, (0, 0, 0, 0, 0, 32 - gw, 0, 32 - gw))  # [g][n 32][k 32][3][3]
+  t = wg.permute(0, 3, 4, 2, 1).reshape(g, 9, 4, 8, 32).permute(0, 1, 2, 4, 3)  # [g][tap][kc][n][8]
+  return t.to(dt).contiguous()
+
+
+def halo_gconv3x3(x, w_packed, scale=None, shift=None, act=ACT_NONE, stats=None):
+  """EXPERIMENTAL tcgen05 group conv (stride 1) over haloed planes; same contract as gconv3x3(x, w, 1, ...)."""
+  _dev(x, BF16)
+  _dev(w_packed, BF16)
+  b, h, wd, c = x.shape
+  out = torch.empty((b, h, wd, c), dtype=BF16, device=x.device)
+  check(_lib.load().tfpp_halo_gconv3x3(x.data_ptr(), w_packed.data_ptr(), out.data_ptr(), _p(scale), _p(shift), act,
+                                       _p(stats[0]) if stats is not None else None,
+                                       _p(stats[1]) if stats is not None else None, b, h, wd, c, _stream()),
+        'tfpp_halo_gconv3x3')
+  return out
+
+
 def halo_conv3x3(x, w_packed, bias=None, act=ACT_NONE, act_n_limit=0, n_valid=None, out_nchw_f32=False):
   """EXPERIMENTAL tcgen05 haloed-tile 3x3 conv (csrc/halo_umma.cu); same contract as smallc_conv3x3."""
   _dev(x, BF16)

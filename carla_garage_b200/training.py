@@ -323,7 +323,10 @@ class Backward:
       gout = st.g(conv.weight)
       ops.gconv3x3_wgrad(draw, a, gout, stride)
       wt = packed(conv.weight, 'gconv_halo_t')  # transposed + spatially flipped weights
-      da = ops.gconv3x3(draw, wt) if stride == 1 else ops.gconv3x3_dgrad_s2(draw, wt)
+      if stride == 1 and eng_mod.HALO_UMMA_GCONV:  # experimental tcgen05 path (TFPP_HALO_UMMA_GCONV=1)
+        da = ops.halo_gconv3x3(draw, packed(conv.weight, 'gconv_halo_umma_t'))
+      else:
+        da = ops.gconv3x3(draw, wt) if stride == 1 else ops.gconv3x3_dgrad_s2(draw, wt)
       if id(a) in self.G:
         ops.add_bf16(self.G[id(a)], da, out=da)
       self.G[id(a)] = da

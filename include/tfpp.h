@@ -306,6 +306,13 @@ int tfpp_gconv3x3_wgrad(const void* dy, const void* x, float* dw, float* workspa
 int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias, void* out, int out_nchw_f32, int n_valid, int act,
                       int act_n_limit, int batch, int height, int width, int cin, int cout_padded, tfpp_stream_t stream);
 
+/* EXPERIMENTAL, not yet run on a GPU (csrc/halo_umma.cu): the stride-1 RegNet group conv on tcgen05 from the haloed
+ * plane layout.  Same contract as tfpp_gconv3x3(stride 1) except the weight pack: (C/24, 9, 4, 32, 8) bf16 =
+ * [group][tap][k chunk][n][8 k], zero padded from 24 to 32 (ops.pack_halo_gconv_weight). */
+int tfpp_halo_gconv3x3(const void* x, const void* w, void* out, const float* scale, const float* shift, int act,
+                       float* stat_sum, float* stat_sq, int batch, int height, int width, int channels,
+                       tfpp_stream_t stream);
+
 /* Weight-pack refresh: out[i] = idx[i] >= 0 ? flat[idx[i]] : 0 for i < n (n % 8 == 0), cast to bf16 (out_f32 = 0) or
  * kept fp32.  One launch rebuilds every kernel-layout weight copy after the optimizer step; replaces the implicit
  * per-module weight reads of torch's conv / linear kernels (team_code/train.py:898-908 loop). */

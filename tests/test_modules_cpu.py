@@ -106,7 +106,8 @@ def test_pack_plan_index_maps_reproduce_every_gather_pack():
   cases = [('conv', (params['conv'],), ()), ('conv_t', (params['conv'],), ()), ('conv_rows_pad', (params['conv'],), (64,)),
            ('conv_dgrad_smallc', (params['conv'],), (64,)), ('gconv', (params['gconv'],), ()),
            ('gconv_t', (params['gconv'],), ()), ('gconv_halo', (params['gconv'],), ()),
-           ('gconv_halo_t', (params['gconv'],), ()), ('conv_halo_umma', (params['conv'],), (64,)),
+           ('gconv_halo_t', (params['gconv'],), ()), ('gconv_halo_umma', (params['gconv'],), ()),
+           ('gconv_halo_umma_t', (params['gconv'],), ()), ('conv_halo_umma', (params['conv'],), (64,)),
            ('conv_halo_umma_t', (params['conv'],), (48,)), ('linear', (params['lin_a'],), ()), ('linear_t', (params['lin_a'],), ()),
            ('rows', (params['lin_a'],), (8, 24)), ('rows_t', (params['lin_a'],), (8, 24)),
            ('rows_f32', (params['lin_a'],), (8, 24)), ('cat_linear', (params['lin_a'], params['lin_b']), ()),
@@ -177,3 +178,53 @@ def test_halo_umma_layout_math_reproduces_conv3x3():
   wpt = ops.pack_halo_umma_weight(wt2, cin, transpose=True, dt=torch.float32)  # (9, 16/8, cin, 8)
   w_eq = wpt.permute(2, 1, 3, 0).reshape(cin, 16, 3, 3)  # back to (out = cin, in = 16, ky, kx) of the equivalent conv
   assert torch.allclose(F.conv2d(dy, w_eq, padding=1), xg.grad, atol=1e-4)
+
+
+def test_halo_umma_gconv_layout_math_reproduces_group_conv():
+  """Host-side model of the experimental grouped halo-UMMA kernel: a 72-channel slab in ten 8-channel planes (pitch 64),
+  group g contracts planes 3g..3g+3 (K = 32, the last 8 channels meet zero weights) against its [tap][4][32][8] weight
+  block and keeps 24 of 32 output columns."""
+  import torch
+  import torch.nn.functional as F
+  from carla_garage_b200 import ops
+  g = torch.Generator().manual_seed(1)
+  c, h, w = 144, 6, 70
+  x = torch.randn(1, h, w, c, generator=g)
+  wt = torch.randn(c, 24, 3, 3, generator=g) * 0.1
+  want = F.conv2d(x.permute(0, 3, 1, 2), wt, padding=1, groups=c // 24)[0]
+  wp = ops.pack_halo_gconv_weight(wt, dt=torch.float32)  # (C/24, 9, 4, 32, 8)
+  assert wp.shape == (c // 24, 9, 4, 32, 8)
+  PW, THO, NPL = 64, 4, 10
+  PH = THO + 2
+  got = torch.zeros(c, h, w)
+  for slab in range(c // 72):
+    for y0 in range(0, h, THO):
+      for x0 in range(0, w, PW - 2):
+        planes = torch.zeros(NPL, PH * PW + 8, 8)
+        for pl in range(NPL):
+          ch0 = slab * 72 + pl * 8
+          for py in range(PH):
+            for px in range(PW):
+              yy, xx = y0 - 1 + py, x0 - 1 + px
+              if 0 <= yy < h and 0 <= xx < w and ch0 < c:   # TMA zero fill outside the tensor (also beyond C)
+                planes[pl, py * PW + px, :] = x[0, yy, xx, ch0:ch0 + 8]
+        m = torch.arange(THO * PW)
+        for grp in range(3):
+          acc = torch.zeros(THO * PW, 32)
+          for tap in range(9):
+            ky, kx = divmod(tap, 3)
+            a = planes[3 * grp:3 * grp + 4][:, m + ky * PW + kx, :]            # (4 chunks, M, 8)
+            acc += torch.einsum('cmj,cnj->mn', a, wp[slab * 3 + grp, tap])
+          for mm in range(THO * PW):
+            ty, tx = divmod(mm, PW)
+            if tx < PW - 2 and y0 + ty < h and x0 + tx < w:
+              c0 = slab * 72 + grp * 24
+              got[c0:c0 + 24, y0 + ty, x0 + tx] = acc[mm, :24]
+  assert torch.allclose(got, want, atol=1e-4), float((got - want).abs().max())
+  # the input-gradient pack is the pack of the equivalent forward conv (in/out swapped inside each group, taps flipped)
+  xg = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+  dy = torch.randn(1, c, h, w, generator=g)
+  F.conv2d(xg, wt, padding=1, groups=c // 24).backward(dy)
+  wpt = ops.pack_halo_gconv_weight(wt, transpose=True, dt=torch.float32)
+  w_eq = wpt[:, :, :3, :24, :].permute(0, 3, 2, 4, 1).reshape(c // 24, 24, 24, 3, 3).reshape(c, 24, 3, 3)
+  assert torch.allclose(F.conv2d(dy, w_eq, padding=1, groups=c // 24), xg.grad, atol=1e-4)

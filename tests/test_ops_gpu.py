@@ -526,3 +526,25 @@ def test_halo_umma_conv3x3(ops, cin, cout, n_pad, h, w):
     cin_pad = cin
     dx = ops.halo_conv3x3(dy, ops.pack_halo_umma_weight(wt, cin_pad, transpose=True))
     assert rel(dx.float().permute(0, 3, 1, 2), xg.grad) < 4e-3
+
+
+@pytest.mark.skipif(os.environ.get('TFPP_EXPERIMENTAL', '0') != '1', reason='not yet run on a GPU: opt-in (round 2)')
+@pytest.mark.parametrize('b,h,w,c', [(2, 16, 64, 72), (1, 8, 8, 216), (3, 20, 12, 144), (1, 8, 130, 1512)])
+def test_halo_umma_gconv3x3(ops, b, h, w, c):
+  """tfpp_halo_gconv3x3 (tcgen05 group conv over haloed planes) against F.conv2d(groups=C/24): raw output + BatchNorm
+  statistics, eval affine + ReLU, and the stride-1 input gradient through the transposed pack."""
+  x = bf(rnd(b, h, w, c, seed=1))
+  wt = rnd(c, 24, 3, 3, seed=2, scale=0.1)
+  want = F.conv2d(x.float().permute(0, 3, 1, 2), bf(wt).float(), padding=1, groups=c // 24)
+  st = (torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda'))
+  y = ops.halo_gconv3x3(x, ops.pack_halo_gconv_weight(wt), stats=st)
+  assert rel(y.float().permute(0, 3, 1, 2), want) < 4e-3
+  assert rel(st[0], want.sum((0, 2, 3))) < 2e-3 and rel(st[1], (want * want).sum((0, 2, 3))) < 2e-3
+  sc, sh = rnd(c, seed=3).abs() + 0.5, rnd(c, seed=4)
+  y2 = ops.halo_gconv3x3(x, ops.pack_halo_gconv_weight(wt), scale=sc, shift=sh, act=ops.ACT_RELU)
+  assert rel(y2.float().permute(0, 3, 1, 2), F.relu(want * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))) < 4e-3
+  xg = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+  dy = bf(rnd(b, h, w, c, seed=5))
+  F.conv2d(xg, bf(wt).float(), padding=1, groups=c // 24).backward(dy.float().permute(0, 3, 1, 2))
+  dx = ops.halo_gconv3x3(dy, ops.pack_halo_gconv_weight(wt, transpose=True))
+  assert rel(dx.float().permute(0, 3, 1, 2), xg.grad) < 4e-3
