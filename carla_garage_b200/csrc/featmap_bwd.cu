@@ -6,6 +6,9 @@
 #include "common.cuh"
 #include "se_kernels.cuh"
 
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 namespace {
 
 __device__ __forceinline__ void load8(const bf16* p, float* v) {
@@ -183,6 +186,158 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
       }
       store8(draw + off, o);
       if (dz_out) store8(dz_out + off, z);
+    }
+  }
+}
+
+// EXPERIMENTAL (TFPP_BN_BWD_FUSED=1, never run on a GPU yet): both passes in ONE cooperative launch for activations
+// that fit the 126 MB L2 — reduce, grid barrier, apply.  The second pass then reads from L2 instead of HBM and half of
+// the 272 BatchNorm-backward launches of a step disappear (they are latency-bound on the small stage-3/4 maps).
+// Work items = (sample, pixel chunk) pairs, the same item -> CTA mapping in both phases.
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                              const bf16* __restrict__ raw, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ gate,
+                                                              const float* __restrict__ pool_grad,
+                                                              const float* __restrict__ fscale,
+                                                              const float* __restrict__ fshift, int act, float inv_n,
+                                                              float* __restrict__ s1, float* __restrict__ s2,
+                                                              bf16* __restrict__ draw, bf16* __restrict__ dz_out, int HW,
+                                                              int C, int pix_per_block, int chunks, int B) {
+  extern __shared__ float sm[];  // [2][C]
+  float* a1 = sm;
+  float* a2 = sm + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int c8n = C / 8;
+  const int rows_pp = blockDim.x / c8n;
+  const int cgi = threadIdx.x % c8n, prow = threadIdx.x / c8n;
+  const int c0 = cgi * 8;
+  const bool active = prow < rows_pp;
+  const bool mask_from_raw = (act == ACT_RELU) && (y == nullptr);
+  const int items = chunks * B;
+  constexpr int U = 2;
+  float mu[8], is[8], fs[8], fh[8];
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = __ldg(mean + c0 + j);
+      is[j] = __ldg(invstd + c0 + j);
+      fs[j] = mask_from_raw ? __ldg(fscale + c0 + j) : 0.f;
+      fh[j] = mask_from_raw ? __ldg(fshift + c0 + j) : 0.f;
+    }
+  }
+  // ---- phase 1: s1[c] = sum dz, s2[c] = sum dz * xhat
+  if (active) {
+    float l1[8], l2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l1[j] = l2[j] = 0.f;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int b = item / chunks, chunk = item - b * chunks;
+      const int p0 = chunk * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+      const long long base = static_cast<long long>(b) * HW * C;
+      float gt[8], pg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        gt[j] = gate ? __ldg(gate + static_cast<long long>(b) * C + c0 + j) : 1.f;
+        pg[j] = pool_grad ? __ldg(pool_grad + static_cast<long long>(b) * C + c0 + j) : 0.f;
+      }
+      for (int pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+        uint4 ud[U], ur[U], uy[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int px = pix + k * rows_pp;
+          if (px < p1) {
+            const long long off = base + static_cast<long long>(px) * C + c0;
+            ud[k] = ld_stream16(dy + off);
+            ur[k] = ld_stream16(raw + off);
+            if (act == ACT_RELU && !mask_from_raw) uy[k] = ld_stream16(y + off);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          if (pix + k * rows_pp >= p1) break;
+          float d[8], yy[8], r[8];
+          unpack8(ud[k], d);
+          unpack8(ur[k], r);
+          if (act == ACT_RELU && !mask_from_raw) unpack8(uy[k], yy);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float dz = d[j] * gt[j] + pg[j];
+            if (mask_from_raw) yy[j] = fmaf(r[j], fs[j], fh[j]);
+            if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
+            l1[j] += dz;
+            l2[j] = fmaf(dz, (r[j] - mu[j]) * is[j], l2[j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&a1[c0 + j], l1[j]);
+      atomicAdd(&a2[c0 + j], l2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(s1 + i, a1[i]);
+    atomicAdd(s2 + i, a2[i]);
+  }
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  // ---- phase 2: draw = k0 * dz + k1 * raw + k2
+  if (!active) return;
+  float k0[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    k0[j] = __ldg(gamma + c) * is[j];
+    k1[j] = -k0[j] * is[j] * __ldcg(s2 + c) * inv_n;
+    k2[j] = -k0[j] * __ldcg(s1 + c) * inv_n - k1[j] * mu[j];
+  }
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / chunks, chunk = item - b * chunks;
+    const int p0 = chunk * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    const long long base = static_cast<long long>(b) * HW * C;
+    float gt[8], pg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gt[j] = gate ? __ldg(gate + static_cast<long long>(b) * C + c0 + j) : 1.f;
+      pg[j] = pool_grad ? __ldg(pool_grad + static_cast<long long>(b) * C + c0 + j) : 0.f;
+    }
+    for (int pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+      uint4 ud[U], ur[U], uy[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int px = pix + k * rows_pp;
+        if (px < p1) {
+          const long long off = base + static_cast<long long>(px) * C + c0;
+          ud[k] = ld_stream16(dy + off);
+          ur[k] = ld_stream16(raw + off);
+          if (act == ACT_RELU && !mask_from_raw) uy[k] = ld_stream16(y + off);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int px = pix + k * rows_pp;
+        if (px >= p1) break;
+        const long long off = base + static_cast<long long>(px) * C + c0;
+        float d[8], yy[8], r[8], o[8], z[8];
+        unpack8(ud[k], d);
+        unpack8(ur[k], r);
+        if (act == ACT_RELU && !mask_from_raw) unpack8(uy[k], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dz = d[j] * gt[j] + pg[j];
+          if (mask_from_raw) yy[j] = fmaf(r[j], fs[j], fh[j]);
+          if (act == ACT_RELU && !(yy[j] > 0.f)) dz = 0.f;
+          z[j] = dz;
+          o[j] = fmaf(k0[j], dz, fmaf(k1[j], r[j], k2[j]));
+        }
+        store8(draw + off, o);
+        if (dz_out) store8(dz_out + off, z);
+      }
     }
   }
 }
@@ -672,6 +827,36 @@ extern "C" int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const
   int chunks, ppb;
   chunking(batch, hw, &chunks, &ppb);
   dim3 grid(chunks, batch);
+  {
+    // EXPERIMENTAL single cooperative launch (reduce -> grid barrier -> apply) for tensors that stay in L2
+    static const bool fused_on = [] { const char* e = getenv("TFPP_BN_BWD_FUSED"); return e != nullptr && e[0] == '1'; }();
+    const size_t tensor_bytes = static_cast<size_t>(batch) * hw * channels * 2;
+    if (fused_on && tensor_bytes * (y != nullptr ? 3 : 2) <= (80u << 20)) {
+      static int max_ctas = 0;
+      if (max_ctas == 0) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel, 256, sizeof(float) * 2 * 2048);
+        max_ctas = (per_sm > 0 ? per_sm : 1) * TFPP_NUM_SMS;
+      }
+      int items = chunks * batch;
+      int nctas = items < max_ctas ? items : max_ctas;
+      const bf16* a_dy = static_cast<const bf16*>(dy);
+      const bf16* a_y = static_cast<const bf16*>(y);
+      const bf16* a_raw = static_cast<const bf16*>(raw);
+      bf16* a_draw = static_cast<bf16*>(draw);
+      bf16* a_dz = static_cast<bf16*>(dz_out);
+      float inv_n = 1.f / (static_cast<float>(batch) * hw);
+      void* args[] = {&a_dy, &a_y, &a_raw, &mean, &invstd, &gamma, &gate, &pool_grad, &fwd_scale, &fwd_shift, &act,
+                      &inv_n, &s1, &s2, &a_draw, &a_dz, &hw, &channels, &ppb, &chunks, &batch};
+      cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(bn_bwd_fused_kernel), dim3(nctas), dim3(256),
+                                                  args, sizeof(float) * 2 * channels, stream);
+      if (e != cudaSuccess) {
+        tfpp_set_error("%s:%d: cooperative launch: %s", __FILE__, __LINE__, cudaGetErrorString(e));
+        return TFPP_ERR_CUDA;
+      }
+      return TFPP_OK;
+    }
+  }
   bn_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 2 * channels, stream>>>(
       static_cast<const bf16*>(dy), static_cast<const bf16*>(y), static_cast<const bf16*>(raw), mean, invstd, gate,
       pool_grad, fwd_scale, fwd_shift, act, s1, s2, hw, channels, ppb);
