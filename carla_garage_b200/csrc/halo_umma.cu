@@ -17,6 +17,8 @@
 #include "../../include/tfpp.h"
 #include "tc_common.cuh"
 
+#include <cstdlib>
+
 using namespace tc;
 
 namespace {
@@ -41,8 +43,10 @@ struct HParams {
   int tiles_x, tiles_y;
 };
 
-__global__ void __launch_bounds__(kThreadsH, 1) halo_umma_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x,
-                                                                         const HParams p) {
+// EPI = 4 (validated) or 8 epilogue warps (two per TMEM lane quarter, alternating M blocks; not yet run)
+template <int EPI>
+__global__ void __launch_bounds__(64 + 32 * EPI, 1) halo_umma_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                            const HParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kchunks = p.K / 8;
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(kThreadsH, 1) halo_umma_conv3x3_kernel(const _
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 4);
+      mbar_init(smem_u32(&tempty_bar[s]), EPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -148,6 +152,7 @@ __global__ void __launch_bounds__(kThreadsH, 1) halo_umma_conv3x3_kernel(const _
   } else {
     // ================================================================ epilogue: lane == linear tile pixel
     const int lane_group = warp & 3;
+    const int blk0 = EPI == 8 ? ((warp - 2) >> 2) : 0;   // with 8 warps: even / odd M blocks
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(kThreadsH, 1) halo_umma_conv3x3_kernel(const _
       const int y0 = (r / p.tiles_x) * THO, x0 = (r % p.tiles_x) * TWO;
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
-      for (int blk = 0; blk < MBLK; ++blk) {
+      for (int blk = blk0; blk < MBLK; blk += (EPI == 8 ? 2 : 1)) {
         const int m = blk * 128 + lane_group * 32 + lane;   // linear pixel of the tile
         const int ty = m / PW, tx = m - ty * PW;
         const int oy = y0 + ty, ox = x0 + tx;
@@ -504,7 +509,9 @@ extern "C" int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias
   TFPP_CHECK_ARG(smem <= 227 * 1024, "shared memory budget exceeded");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(halo_umma_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(halo_umma_conv3x3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(halo_umma_conv3x3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       tfpp_set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
       return TFPP_ERR_CUDA;
@@ -514,7 +521,9 @@ extern "C" int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias
   const long long tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * batch;
   if (tiles == 0) return TFPP_OK;
   const int grid = static_cast<int>(tiles < TFPP_NUM_SMS ? tiles : TFPP_NUM_SMS);
-  halo_umma_conv3x3_kernel<<<grid, kThreadsH, smem, stream>>>(tmap, p);
+  static const bool epi8 = [] { const char* e = getenv("TFPP_HALO_UMMA_EPI8"); return e != nullptr && e[0] == '1'; }();
+  if (epi8) halo_umma_conv3x3_kernel<8><<<grid, 64 + 32 * 8, smem, stream>>>(tmap, p);
+  else halo_umma_conv3x3_kernel<4><<<grid, kThreadsH, smem, stream>>>(tmap, p);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }
