@@ -241,7 +241,16 @@ def main():
       host_pts.numel() * host_pts.element_size() + sum(v.numel() * v.element_size() for v in host_lab.values())
   loss_host = torch.zeros(10, pin_memory=True)
 
+  prefetch = use_graph and os.environ.get('TFPP_PREFETCH', '0') == '1'  # opt-in (round 2): H2D of step i+1 under step i
+  if prefetch:
+    tr.stage({k: v for k, v in host_in.items() if k != 'lidar_bev'}, host_lab, host_pts)
+
   def step_e2e():
+    if prefetch:
+      _, gl = tr.replay_staged()
+      tr.stage({k: v for k, v in host_in.items() if k != 'lidar_bev'}, host_lab, host_pts)  # next step's inputs
+      loss_host.copy_(gl, non_blocking=True)
+      return
     if use_graph:
       _, gl = tr.replay({k: v for k, v in host_in.items() if k != 'lidar_bev'}, host_lab, host_pts)
       loss_host.copy_(gl, non_blocking=True)

@@ -852,6 +852,50 @@ class Trainer:
     self.launches_per_step = _lib.launch_count()  # libtfpp kernels recorded into the graph(s)
     return self
 
+  # ---- input prefetch (opt-in; not yet run on a GPU): H2D copies of the NEXT step on a copy stream, overlapping the
+  # current replay; replay_staged() hands them to the graph's static buffers with device-to-device copies
+  def stage(self, inputs=None, labels=None, points=None):
+    """Start copying the next step's (pinned host) tensors into a second set of device buffers on a side stream."""
+    if getattr(self, '_copy_stream', None) is None:
+      self._copy_stream = torch.cuda.Stream()
+      self._stg_in = {k: torch.empty_like(v) for k, v in self._sin.items()}
+      self._stg_lab = {k: torch.empty_like(v) for k, v in self._slab.items()}
+      self._stg_pts = torch.empty_like(self._spts) if self._spts is not None else None
+      self._stg_ready = torch.cuda.Event()
+      self._stg_free = torch.cuda.Event()
+      self._stg_free.record(torch.cuda.current_stream())
+    cs = self._copy_stream
+    cs.wait_event(self._stg_free)  # the previous hand-over has read the staging buffers
+    with torch.cuda.stream(cs):
+      if inputs is not None:
+        for k, v in inputs.items():
+          if k in self._stg_in and not (k == 'lidar_bev' and self._spts is not None):
+            self._stg_in[k].copy_(v, non_blocking=True)
+      if labels is not None:
+        for k, v in labels.items():
+          self._stg_lab[k].copy_(v, non_blocking=True)
+      if points is not None:
+        self._stg_pts.copy_(points, non_blocking=True)
+      self._stg_ready.record(cs)
+    self._stg_what = (inputs is not None, labels is not None, points is not None)
+
+  def replay_staged(self):
+    """Replay the step on the tensors passed to the last stage() call."""
+    main = torch.cuda.current_stream()
+    main.wait_event(self._stg_ready)
+    has_in, has_lab, has_pts = self._stg_what
+    if has_in:
+      for k, v in self._stg_in.items():
+        if not (k == 'lidar_bev' and self._spts is not None):
+          self._sin[k].copy_(v, non_blocking=True)
+    if has_lab:
+      for k, v in self._stg_lab.items():
+        self._slab[k].copy_(v, non_blocking=True)
+    if has_pts:
+      self._spts.copy_(self._stg_pts, non_blocking=True)
+    self._stg_free.record(main)
+    return self.replay()
+
   def replay(self, inputs=None, labels=None, points=None):
     """Copy new data into the static buffers (non-blocking; pinned host tensors welcome) and replay the step."""
     if inputs is not None:

@@ -27,6 +27,7 @@ run_bench halo TFPP_HALO_UMMA=1
 run_bench halo_epi8 TFPP_HALO_UMMA=1 TFPP_HALO_UMMA_EPI8=1
 run_bench halo_gconv TFPP_HALO_UMMA_GCONV=1
 run_bench bnfused TFPP_BN_BWD_FUSED=1
+run_bench prefetch TFPP_PREFETCH=1
 # parity of the whole step with the experimental paths on
 timeout 600 env TFPP_HALO_UMMA=1 python -m pytest tests/test_model_gpu.py tests/test_train_gpu.py -q -x > gpurun_out/n2_model_tests_halo.log 2>&1
 tail -4 gpurun_out/n2_model_tests_halo.log
