@@ -17,7 +17,7 @@ run_bench() {  # name, env...
 import json
 try:
   d = json.load(open('gpurun_out/n2_bench_$name.json'))
-  print('$name', round(d['value'], 1), 'samples/s', round(d['ms_per_step'], 2), 'ms', 'fwd', round(d['inference']['fwd_ms_per_frame'], 2), 'ms/frame')
+  print('$name', round(d['value'], 1), 'samples/s', round(d['ms_per_step'], 2), 'ms', 'e2e', round(d['e2e']['value'], 1), 'fwd', round(d['inference']['fwd_ms_per_frame'], 2), 'ms/frame')
 except Exception as e:
   print('$name FAILED', e)
 PY
