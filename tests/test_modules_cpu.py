@@ -228,3 +228,22 @@ def test_halo_umma_gconv_layout_math_reproduces_group_conv():
   wpt = ops.pack_halo_gconv_weight(wt, transpose=True, dt=torch.float32)
   w_eq = wpt[:, :, :3, :24, :].permute(0, 3, 2, 4, 1).reshape(c // 24, 24, 24, 3, 3).reshape(c, 24, 3, 3)
   assert torch.allclose(F.conv2d(dy, w_eq, padding=1, groups=c // 24), xg.grad, atol=1e-4)
+
+
+def test_ensemble_reduction_matches_sensor_agent_semantics():
+  """inference.ensemble_outputs = sensor_agent.py:481-483,527-531: mean over the members of the softmaxed target-speed
+  logits and of the predicted checkpoints."""
+  import torch
+  from carla_garage_b200.inference import ensemble_outputs
+  g = torch.Generator().manual_seed(3)
+  outs = []
+  for _ in range(3):
+    o = [None] * 10
+    o[1] = torch.randn(4, 4, generator=g)
+    o[2] = torch.randn(4, 10, 2, generator=g)
+    outs.append(tuple(o))
+  probs, cps = ensemble_outputs(outs)
+  want_p = sum(torch.softmax(o[1], dim=1) for o in outs) / 3
+  want_c = sum(o[2] for o in outs) / 3
+  assert torch.allclose(probs, want_p, atol=1e-6) and torch.allclose(cps, want_c, atol=1e-6)
+  assert torch.allclose(probs.sum(1), torch.ones(4), atol=1e-6)
