@@ -241,7 +241,7 @@ def main():
       host_pts.numel() * host_pts.element_size() + sum(v.numel() * v.element_size() for v in host_lab.values())
   loss_host = torch.zeros(10, pin_memory=True)
 
-  prefetch = use_graph and os.environ.get('TFPP_PREFETCH', '0') == '1'  # opt-in (round 2): H2D of step i+1 under step i
+  prefetch = use_graph and os.environ.get('TFPP_PREFETCH', '1') == '1'  # H2D of step i+1 on a copy stream under step i (A/B on B200: e2e 521.6 -> 565.1 samples/s)
   if prefetch:
     tr.stage({k: v for k, v in host_in.items() if k != 'lidar_bev'}, host_lab, host_pts)
 

@@ -91,11 +91,11 @@ _PROTOS = {
     'tfpp_small_mha_bwd': [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, I, P],
     'tfpp_extra_sensor_token_bwd': [P, P, F, F, I, P, P, P, P, P, L, P, P, P, P, P, I, I, I, I, P],
     'tfpp_planner_head_bwd': [P] * 28 + [I, I, I, I, I, P],
-    'tfpp_ce_map_loss': [P, P, P, F, P, P, P, P, I, I, I, I, P],
-    'tfpp_l1_sigmoid_loss': [P, P, F, P, P, P, I, L, P],
+    'tfpp_ce_map_loss': [P, P, P, F, P, P, P, P, P, I, I, I, I, P],
+    'tfpp_l1_sigmoid_loss': [P, P, F, P, P, P, P, I, L, P],
     'tfpp_center_head_loss': [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
-    'tfpp_planner_loss': [P, P, P, P, P, F, F, P, P, P, I, I, I, P],
-    'tfpp_adamw_amsgrad': [P, P, P, P, P, L, F, F, F, F, F, I, F, P, P],
+    'tfpp_planner_loss': [P, P, P, P, P, F, F, P, P, P, P, I, I, I, P],
+    'tfpp_adamw_amsgrad': [P, P, P, P, P, L, F, F, F, F, F, I, F, P, P, P],
 }
 
 

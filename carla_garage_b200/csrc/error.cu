@@ -13,4 +13,4 @@ extern "C" void tfpp_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* tfpp_last_error(void) { return g_err; }
-extern "C" int tfpp_abi_version(void) { return 1; }
+extern "C" int tfpp_abi_version(void) { return 2; }

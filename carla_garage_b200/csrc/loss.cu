@@ -13,6 +13,7 @@ namespace {
 // applied by the caller through grad_scale / the loss_sum normalisation (class weights are all 1 on these maps).
 __global__ void __launch_bounds__(256) ce_map_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                                      const float* __restrict__ valid, float grad_scale,
+                                                     const float* __restrict__ w_dev,
                                                      float* __restrict__ loss_sum, bf16* __restrict__ dz_nhwc,
                                                      float* __restrict__ dz_nchw, float* __restrict__ dbias, int C,
                                                      int Cp, int HW, long long npix) {
@@ -21,6 +22,7 @@ __global__ void __launch_bounds__(256) ce_map_kernel(const float* __restrict__ l
   if (threadIdx.x < 32) sb[threadIdx.x] = 0.f;
   if (threadIdx.x == 0) sl = 0.f;
   __syncthreads();
+  if (w_dev) grad_scale *= *w_dev;  // loss weight living on the device (autograd boundary: d total / d this loss)
   float lsum = 0.f;
   float lb[16];
 #pragma unroll
@@ -87,12 +89,14 @@ __global__ void __launch_bounds__(256) ce_map_kernel(const float* __restrict__ l
 
 // depth: loss = mean |sigmoid(z) - y| (model.py:379,434); p = sigmoid(z) already computed by the conv epilogue.
 __global__ void __launch_bounds__(256) l1_sigmoid_kernel(const float* __restrict__ p, const float* __restrict__ y,
-                                                         float grad_scale, float* __restrict__ loss_sum,
+                                                         float grad_scale, const float* __restrict__ w_dev,
+                                                         float* __restrict__ loss_sum,
                                                          bf16* __restrict__ dz_nhwc, float* __restrict__ dbias, int Cp,
                                                          long long n) {
   __shared__ float sl, sb;
   if (threadIdx.x == 0) sl = sb = 0.f;
   __syncthreads();
+  if (w_dev) grad_scale *= *w_dev;
   float ls = 0.f, lb = 0.f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -100,9 +104,11 @@ __global__ void __launch_bounds__(256) l1_sigmoid_kernel(const float* __restrict
     ls += fabsf(d);
     const float gz = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * pv * (1.f - pv) * grad_scale;
     lb += gz;
-    bf16* o = dz_nhwc + i * Cp;
-    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(gz, 0.f), 0u, 0u, 0u);
-    for (int c = 8; c < Cp; c += 8) *reinterpret_cast<uint4*>(o + c) = make_uint4(0u, 0u, 0u, 0u);
+    if (dz_nhwc) {
+      bf16* o = dz_nhwc + i * Cp;
+      *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(gz, 0.f), 0u, 0u, 0u);
+      for (int c = 8; c < Cp; c += 8) *reinterpret_cast<uint4*>(o + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   ls = warp_sum(ls);
   lb = warp_sum(lb);
@@ -197,14 +203,18 @@ __global__ void __launch_bounds__(256) center_loss_kernel(
       l[4] += (ad < 1.f ? 0.5f * d * d : ad - 0.5f) * pw0 * inv_avg;
       g[ch] = (ad < 1.f ? d : (d > 0.f ? 1.f : -1.f)) * pw0 * inv_avg * w5[4];
     }
-    bf16* o = dz + i * Cp;
+    if (dz) {
+      bf16* o = dz + i * Cp;
 #pragma unroll
-    for (int c = 0; c < 24; c += 8)
-      *reinterpret_cast<uint4*>(o + c) = make_uint4(pack_bf16x2(g[c], g[c + 1]), pack_bf16x2(g[c + 2], g[c + 3]),
-                                                    pack_bf16x2(g[c + 4], g[c + 5]), pack_bf16x2(g[c + 6], g[c + 7]));
+      for (int c = 0; c < 24; c += 8)
+        *reinterpret_cast<uint4*>(o + c) = make_uint4(pack_bf16x2(g[c], g[c + 1]), pack_bf16x2(g[c + 2], g[c + 3]),
+                                                      pack_bf16x2(g[c + 4], g[c + 5]), pack_bf16x2(g[c + 6], g[c + 7]));
+    }
+    if (dbias) {
 #pragma unroll
-    for (int c = 0; c < 24; ++c)
-      if (c < C && g[c] != 0.f) atomicAdd(&sb[c], g[c]);
+      for (int c = 0; c < 24; ++c)
+        if (c < C && g[c] != 0.f) atomicAdd(&sb[c], g[c]);
+    }
   }
   for (int k = 0; k < 5; ++k) {
     const float t = warp_sum(l[k]);
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(256) center_loss_kernel(
   }
   __syncthreads();
   if (threadIdx.x < 5) atomicAdd(losses + threadIdx.x, sl[threadIdx.x]);
-  if (threadIdx.x < C) atomicAdd(dbias + threadIdx.x, sb[threadIdx.x]);
+  if (dbias && threadIdx.x < C) atomicAdd(dbias + threadIdx.x, sb[threadIdx.x]);
 }
 
 // target-speed CE with class weights (model.py:416; nn.CrossEntropyLoss(weight): sum(w_y * nll) / sum(w_y)) and
@@ -221,12 +231,17 @@ __global__ void __launch_bounds__(256) planner_loss_kernel(const float* __restri
                                                            const long long* __restrict__ labels,
                                                            const float* __restrict__ class_w,
                                                            const float* __restrict__ cp, const float* __restrict__ cp_t,
-                                                           float w_ts, float w_cp, float* __restrict__ losses,
+                                                           float w_ts, float w_cp, const float* __restrict__ w2_dev,
+                                                           float* __restrict__ losses,
                                                            float* __restrict__ dlogits, float* __restrict__ dcp, int B,
                                                            int n_cls, int n_cp) {
   __shared__ float s_w, s_l, s_c;
   if (threadIdx.x == 0) s_w = s_l = s_c = 0.f;
   __syncthreads();
+  if (w2_dev) {
+    w_ts *= w2_dev[0];
+    w_cp *= w2_dev[1];
+  }
   float lw = 0.f, ll = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const int y = static_cast<int>(labels[b]);
@@ -274,28 +289,29 @@ __global__ void __launch_bounds__(256) planner_loss_kernel(const float* __restri
 #define STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
 
 extern "C" int tfpp_ce_map_loss(const float* logits, const long long* labels, const float* valid, float grad_scale,
-                                float* loss_sum, void* dz_nhwc, float* dz_nchw, float* dbias, int batch, int classes,
+                                const float* w_dev, float* loss_sum, void* dz_nhwc, float* dz_nchw, float* dbias, int batch, int classes,
                                 int channels_padded, int hw, tfpp_stream_t stream_) {
   STREAM;
   TFPP_CHECK_ARG(classes <= 16 && channels_padded <= 16 && channels_padded % 8 == 0, "ce_map: <= 16 classes");
   const long long npix = static_cast<long long>(batch) * hw;
   long long blocks = ceil_div_ll(npix, 256);
   if (blocks > TFPP_NUM_SMS * 8) blocks = TFPP_NUM_SMS * 8;
-  ce_map_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(logits, labels, valid, grad_scale, loss_sum,
+  ce_map_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(logits, labels, valid, grad_scale, w_dev, loss_sum,
                                                               static_cast<bf16*>(dz_nhwc), dz_nchw, dbias, classes,
                                                               channels_padded, hw, npix);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }
 
-extern "C" int tfpp_l1_sigmoid_loss(const float* p, const float* target, float grad_scale, float* loss_sum,
+extern "C" int tfpp_l1_sigmoid_loss(const float* p, const float* target, float grad_scale, const float* w_dev,
+                                    float* loss_sum,
                                     void* dz_nhwc, float* dbias, int channels_padded, long long n,
                                     tfpp_stream_t stream_) {
   STREAM;
   TFPP_CHECK_ARG(channels_padded % 8 == 0 && channels_padded >= 8, "channels_padded must be a positive multiple of 8");
   long long blocks = ceil_div_ll(n, 256);
   if (blocks > TFPP_NUM_SMS * 8) blocks = TFPP_NUM_SMS * 8;
-  l1_sigmoid_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, target, grad_scale, loss_sum,
+  l1_sigmoid_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p, target, grad_scale, w_dev, loss_sum,
                                                                   static_cast<bf16*>(dz_nhwc), dbias, channels_padded, n);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
@@ -319,10 +335,10 @@ extern "C" int tfpp_center_head_loss(const float* maps, const float* t_heat, con
 }
 
 extern "C" int tfpp_planner_loss(const float* logits, const long long* labels, const float* class_w, const float* cp,
-                                 const float* cp_t, float w_ts, float w_cp, float* losses, float* dlogits, float* dcp,
-                                 int batch, int n_cls, int n_cp, tfpp_stream_t stream_) {
+                                 const float* cp_t, float w_ts, float w_cp, const float* w2_dev, float* losses,
+                                 float* dlogits, float* dcp, int batch, int n_cls, int n_cp, tfpp_stream_t stream_) {
   STREAM;
-  planner_loss_kernel<<<1, 256, 0, stream>>>(logits, labels, class_w, cp, cp_t, w_ts, w_cp, losses, dlogits, dcp, batch,
+  planner_loss_kernel<<<1, 256, 0, stream>>>(logits, labels, class_w, cp, cp_t, w_ts, w_cp, w2_dev, losses, dlogits, dcp, batch,
                                              n_cls, n_cp);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;

@@ -21,9 +21,20 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float* __restrict__ m, float* __restrict__ v,
                                                     float* __restrict__ vmax, long long n, float lr, float beta1,
                                                     float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                    float grad_scale, const float* __restrict__ dev_state) {
+                                                    float grad_scale, const float* __restrict__ dev_state,
+                                                    const unsigned char* __restrict__ flags) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
+  // per-element flags (optional): bit 0 = no weight decay (create_optimizer_groups, model.py:556-645), bit 1 = frozen
+  // (requires_grad=False, train.py:495-508): the element is left untouched
+  unsigned fl = 0u;
+  if (flags != nullptr) {
+    if (i + 4 <= n) fl = *reinterpret_cast<const unsigned*>(flags + i);
+    else for (long long j = i; j < n; ++j) fl |= static_cast<unsigned>(flags[j]) << (8 * (j - i));
+    if ((fl & 0x02020202u) == 0x02020202u) return;
+  }
+  const float wd0 = (fl & 0x00000001u) ? 0.f : wd, wd1 = (fl & 0x00000100u) ? 0.f : wd,
+              wd2 = (fl & 0x00010000u) ? 0.f : wd, wd3 = (fl & 0x01000000u) ? 0.f : wd;
   if (dev_state != nullptr) {  // CUDA-graph friendly: step count, learning rate and bias corrections live on the device
     lr = dev_state[1];
     bc1 = dev_state[2];
@@ -34,16 +45,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     const float4 gv = *reinterpret_cast<const float4*>(g + i);
     float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
     float4 xv = *reinterpret_cast<float4*>(vmax + i);
-    adamw_one(pv.x, gv.x, mv.x, vv.x, xv.x, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
-    adamw_one(pv.y, gv.y, mv.y, vv.y, xv.y, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
-    adamw_one(pv.z, gv.z, mv.z, vv.z, xv.z, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
-    adamw_one(pv.w, gv.w, mv.w, vv.w, xv.w, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    if (!(fl & 0x00000002u)) adamw_one(pv.x, gv.x, mv.x, vv.x, xv.x, lr, beta1, beta2, eps, wd0, bc1, bc2_sqrt, grad_scale);
+    if (!(fl & 0x00000200u)) adamw_one(pv.y, gv.y, mv.y, vv.y, xv.y, lr, beta1, beta2, eps, wd1, bc1, bc2_sqrt, grad_scale);
+    if (!(fl & 0x00020000u)) adamw_one(pv.z, gv.z, mv.z, vv.z, xv.z, lr, beta1, beta2, eps, wd2, bc1, bc2_sqrt, grad_scale);
+    if (!(fl & 0x02000000u)) adamw_one(pv.w, gv.w, mv.w, vv.w, xv.w, lr, beta1, beta2, eps, wd3, bc1, bc2_sqrt, grad_scale);
     *reinterpret_cast<float4*>(p + i) = pv;
     *reinterpret_cast<float4*>(m + i) = mv;
     *reinterpret_cast<float4*>(v + i) = vv;
     *reinterpret_cast<float4*>(vmax + i) = xv;
   } else {
-    for (long long j = i; j < n; ++j) adamw_one(p[j], g[j], m[j], v[j], vmax[j], lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    for (long long j = i; j < n; ++j) {
+      const unsigned f = (fl >> (8 * (j - i))) & 0xffu;
+      if (!(f & 2u)) adamw_one(p[j], g[j], m[j], v[j], vmax[j], lr, beta1, beta2, eps, (f & 1u) ? 0.f : wd, bc1, bc2_sqrt, grad_scale);
+    }
   }
 }
 // dev_state = [step, lr, 1 - beta1^step, sqrt(1 - beta2^step)]
@@ -91,7 +105,7 @@ extern "C" int tfpp_gather_pack(const float* flat, const int* idx, void* out, lo
 extern "C" int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                                   float* max_exp_avg_sq, long long n, float lr, float beta1, float beta2, float eps,
                                   float weight_decay, int step, float grad_scale, float* dev_state,
-                                  tfpp_stream_t stream_) {
+                                  const unsigned char* flags, tfpp_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TFPP_CHECK_ARG(step >= 1 || dev_state != nullptr, "step counts from 1");
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
@@ -102,7 +116,7 @@ extern "C" int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_av
   adamw_kernel<<<static_cast<int>(ceil_div_ll(ceil_div_ll(n, 4), 256)), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq,
                                                                           max_exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                           weight_decay, bc1, sqrtf(bc2), grad_scale,
-                                                                          dev_state);
+                                                                          dev_state, flags);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

@@ -7,6 +7,7 @@ in the epilogue, and small dedicated kernels for everything else.  Each step cit
 (paths relative to /root/reference/team_code).
 """
 import os
+import weakref
 
 import torch
 
@@ -205,6 +206,13 @@ class PackPlan:
     for idx_all, out_all, _ in self.segments:
       ops.gather_pack(self.flat, idx_all, out_all)
 
+  def refresh_all(self):
+    """One re-gather after the parameters were written with torch ops (torch optimizer, load_state_dict): every view
+    adopts the current version counters, so lookup() does not re-gather once per pack."""
+    self.refresh()
+    for key, hit in self.views.items():
+      self.views[key] = (tuple(p._version for p in hit[2]),) + hit[1:]  # pylint: disable=protected-access
+
 
 _PLAN = [None]  # the active PackPlan (set by training.Trainer)
 
@@ -221,13 +229,15 @@ def packed(params, kind, *extra):
       return hit
   ver = (PARAM_EPOCH[0],) + tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)  # pylint: disable=protected-access
   hit = _PACK_CACHE.get(key)
-  if hit is not None and hit[0] == ver:
+  # the key holds id()s: a hit only counts while the very same parameter objects are alive (a freed model's ids and
+  # addresses can be handed to a new one)
+  if hit is not None and hit[0] == ver and all(r() is p for r, p in zip(hit[2], params)):
     return hit[1]
   with torch.no_grad():
     out = _build_pack(kind, params, extra)
     if plan is not None:
       plan.register(key, kind, params, extra, out)
-  _PACK_CACHE[key] = (ver, out)
+  _PACK_CACHE[key] = (ver, out, tuple(weakref.ref(p) for p in params))
   return out
 
 
@@ -510,6 +520,10 @@ class Engine:
     bb, cfg = self.bb, self.cfg
     if not (image.is_cuda and lidar.is_cuda):
       raise RuntimeError('carla_garage_b200 runs on CUDA tensors only (no CPU fallback)')
+    if training:
+      # tfpp_bn_finalize / tfpp_extra_sensor_token update the running statistics through raw pointers (no version
+      # counter moves): folded eval-mode BatchNorm affines cached before this forward are stale after it
+      PARAM_EPOCH[0] += 1
     image = image.float().contiguous()
     lidar = lidar.float().contiguous()
     # Training: between two fusion points the LiDAR branch (a quarter of the image branch's pixels: kernels that cannot
@@ -726,7 +740,3 @@ class Engine:
       main.wait_stream(side)
     return (None, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth, pred_bounding_box,
             None, None, None)
-
-  def compute_loss(self, *args, **kwargs):
-    from . import losses  # pylint: disable=import-outside-toplevel
-    return losses.compute_loss(self, *args, **kwargs)

@@ -41,6 +41,30 @@ class LidarCenterNetHead(nn.Module):
                               k=self.config.top_k_center_keypoints, img_h=self.config.lidar_resolution_height,
                               img_w=self.config.lidar_resolution_width)
 
+  def loss(self, center_heatmap_pred, wh_pred, offset_pred, yaw_class_pred, yaw_res_pred, velocity_pred, brake_pred,
+           center_heatmap_target, wh_target, yaw_class_target, yaw_res_target, offset_target, velocity_target,
+           brake_target, pixel_weight, avg_factor):
+    """center_net.py:77-123 on tfpp_center_head_loss: dict of the five head losses (gaussian focal heat-map loss, masked
+    L1 wh / offset, masked CE yaw class, masked SmoothL1 yaw residual, each / sum(avg_factor)).  Values only: the
+    gradient path of the training step runs through LidarCenterNet.compute_loss (carla_garage_b200.boundary), which
+    evaluates the same kernel together with the other five losses."""
+    del velocity_pred, brake_pred, velocity_target, brake_target
+    import torch  # pylint: disable=import-outside-toplevel
+    from .. import _lib, ops  # pylint: disable=import-outside-toplevel
+    maps = torch.cat([center_heatmap_pred, wh_pred, offset_pred, yaw_class_pred, yaw_res_pred], dim=1).float().contiguous()
+    b, _, h, w = maps.shape
+    dev = maps.device
+    f = lambda t: t.to(dev, torch.float32).contiguous()
+    sums = torch.zeros(5, dtype=torch.float32, device=dev)
+    w5 = torch.ones(5, dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().tfpp_center_head_loss(
+        maps.data_ptr(), f(center_heatmap_target).data_ptr(), f(wh_target).data_ptr(), f(offset_target).data_ptr(),
+        yaw_class_target.to(dev, torch.long).contiguous().data_ptr(), f(yaw_res_target).data_ptr(),
+        f(pixel_weight).data_ptr(), f(avg_factor).data_ptr(), w5.data_ptr(), sums.data_ptr(), None, None, b, h * w,
+        self.config.num_bb_classes, self.config.num_dir_bins, 24, ops._stream()), 'center loss')  # pylint: disable=protected-access
+    keys = ('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res')
+    return {k: sums[i] for i, k in enumerate(keys)}
+
   decode_heatmap = None  # reference-internal helper; use get_bboxes
 
 

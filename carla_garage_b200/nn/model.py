@@ -224,6 +224,7 @@ class LidarCenterNet(nn.Module):
     self.loss_bev_semantic = nn.CrossEntropyLoss(weight=self.bev_semantic_weights, label_smoothing=label_smoothing,
                                                  ignore_index=-1)
     self._engine = None
+    self._boundary = None
 
   def reset_parameters(self):
     nn.init.uniform_(self.checkpoint_query)
@@ -238,7 +239,21 @@ class LidarCenterNet(nn.Module):
   def forward(self, rgb, lidar_bev, target_point, ego_vel, command):
     """model.py:279-392: returns (pred_wp, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic,
     pred_depth, pred_bounding_box, attention_weights, pred_wp_1, selected_path)."""
+    if self.training and torch.is_grad_enabled():
+      # the reference's train loop (train.py:776-820,898): outputs carry a grad_fn, loss.backward() reaches the parameters
+      return self.boundary.forward(rgb, lidar_bev, target_point, ego_vel, command)
     return self.engine.forward(rgb, lidar_bev, target_point, ego_vel, command, training=self.training)
+
+  @property
+  def boundary(self):
+    """carla_garage_b200.boundary.TrainBoundary of this model (autograd-compatible training path), built on first use."""
+    if self._boundary is None:
+      if getattr(self, '_trainer_owned', False):
+        raise RuntimeError('this model is driven by carla_garage_b200.training.Trainer (fused step); use Trainer.step() '
+                           'or build a fresh model for the autograd path')
+      from ..boundary import TrainBoundary  # pylint: disable=import-outside-toplevel
+      object.__setattr__(self, '_boundary', TrainBoundary(self))
+    return self._boundary
 
   def compute_loss(self, pred_wp, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
                    pred_bounding_box, pred_wp_1, selected_path, waypoint_label, target_speed_label, checkpoint_label,
@@ -247,10 +262,11 @@ class LidarCenterNet(nn.Module):
                    avg_factor_label):
     """model.py:394-445 (+ center_net.py:77-123) on fused loss kernels."""
     del pred_wp, pred_wp_1, selected_path, waypoint_label, velocity_label, brake_target_label
-    return self.engine.compute_loss(pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
-                                    pred_bounding_box, target_speed_label, checkpoint_label, semantic_label,
-                                    bev_semantic_label, depth_label, center_heatmap_label, wh_label, yaw_class_label,
-                                    yaw_res_label, offset_label, pixel_weight_label, avg_factor_label)
+    from ..boundary import compute_loss  # pylint: disable=import-outside-toplevel
+    return compute_loss(self, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
+                        pred_bounding_box, target_speed_label, checkpoint_label, semantic_label, bev_semantic_label,
+                        depth_label, center_heatmap_label, wh_label, yaw_class_label, yaw_res_label, offset_label,
+                        pixel_weight_label, avg_factor_label)
 
   def convert_features_to_bb_metric(self, bb_predictions):
     """model.py:447-459: decode on the GPU, threshold + image->vehicle frame on the host like the reference."""

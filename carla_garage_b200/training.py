@@ -30,9 +30,14 @@ class FlatState:
   weights / biases of every fusion attention, and the five CenterNet head convs (3x3 weights, 3x3 biases, 1x1 biases).
   """
 
-  def __init__(self, model):
+  def __init__(self, model, assign_grad=True, include_frozen=False):
+    """assign_grad: point every p.grad at its slice of the flat gradient (Trainer).  The autograd boundary leaves
+    p.grad to torch's AccumulateGrad nodes instead.  include_frozen: also adopt requires_grad=False parameters
+    (train.py:495-508 freezes sub-modules) so the backward handlers have somewhere to write; constants such as
+    valid_bev_pixels stay out."""
     self.model = model
-    params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    params = [(n, p) for n, p in model.named_parameters()
+              if p.requires_grad or (include_frozen and p.is_floating_point() and not n.startswith('valid_bev'))]
     by_name = dict(params)
     ordered, used = [], set()
 
@@ -78,7 +83,8 @@ class FlatState:
       k = p.numel()
       self.flat[off:off + k].copy_(p.detach().reshape(-1))
       p.data = self.flat[off:off + k].view(p.shape)
-      p.grad = self.grad[off:off + k].view(p.shape)
+      if assign_grad:
+        p.grad = self.grad[off:off + k].view(p.shape)
       self.offsets[id(p)] = (off, k)
     # every BatchNorm's num_batches_tracked as a view of one int64 buffer: one increment kernel per step
     counters = [(n, b) for n, b in model.named_buffers() if n.endswith('num_batches_tracked')]
@@ -95,6 +101,22 @@ class FlatState:
     self.step_count = 0
     # [step, lr, 1 - beta1^step, sqrt(1 - beta2^step)]: maintained on the device (CUDA-graph replay)
     self.dev_state = torch.zeros(4, dtype=F32, device=dev) if dev.type == 'cuda' else None
+    self.flags = None  # per-element uint8 (bit 0 no weight decay, bit 1 frozen) or None = decay everything
+    if any(not p.requires_grad for p in self.params):
+      self.set_flags()
+
+  def set_flags(self, no_decay=()):
+    """Per-element optimizer flags for the fused AdamW: ``no_decay`` = parameters of the weight_decay=0 group of
+    LidarCenterNet.create_optimizer_groups (model.py:556-645, train.py:522-525); requires_grad=False parameters
+    (train.py:495-508) are frozen."""
+    flags = torch.zeros(self.flat.numel(), dtype=torch.uint8, device=self.flat.device)
+    nd = {id(p) for p in no_decay}
+    for p in self.params:
+      off, k = self.offsets[id(p)]
+      v = (1 if id(p) in nd else 0) | (0 if p.requires_grad else 2)
+      if v:
+        flags[off:off + k] = v
+    self.flags = flags if bool(flags.any()) else None
 
   def g(self, p):
     """fp32 gradient view of parameter p (same shape)."""
@@ -130,7 +152,7 @@ class FlatState:
                                               self.exp_avg_sq.data_ptr(), self.max_exp_avg_sq.data_ptr(),
                                               self.flat.numel(), 0.0, betas[0], betas[1], eps, weight_decay,
                                               self.step_count, grad_scale, self.dev_state.data_ptr(),
-                                              ops._stream()),  # pylint: disable=protected-access
+                                              ops._p(self.flags), ops._stream()),  # pylint: disable=protected-access
                'tfpp_adamw_amsgrad')
     eng_mod.PARAM_EPOCH[0] += 1  # parameter storage changed: cached bf16 weight packs must be rebuilt
 
@@ -138,12 +160,34 @@ class FlatState:
 # ---------------------------------------------------------------------------------------------------------------
 # losses
 # ---------------------------------------------------------------------------------------------------------------
-def compute_losses(eng, st, outputs, labels, weights):
-  """Fused loss + seed-gradient kernels.  Returns (dict of 10 loss scalars (0-dim device tensors), seeds).
-  ``weights``: dict loss key -> float (train.py:452-456: 1/10 each).  seeds: id(tensor) -> gradient record."""
+def loss_bias_targets(eng, st):
+  """Where the fused loss kernels accumulate the bias gradients of the last conv of each dense head."""
+  m = eng.m
+  heads = m.head.head_names()
+  return {'semantic': st.g(m.semantic_decoder.deconv3[2].bias), 'depth': st.g(m.depth_decoder.deconv3[2].bias),
+          'center': st.g_span(getattr(m.head, heads[0])[2].bias, getattr(m.head, heads[-1])[2].bias)}
+
+
+def _base_of(t):
+  return t._base if t._base is not None else t  # pylint: disable=protected-access
+
+
+def compute_losses(eng, outputs, labels, weights=None, bias_grads=None, w_dev=None, want_seeds=True):
+  """Fused loss (+ seed-gradient) kernels: model.py:394-445 + center_net.py:77-123.
+
+  Returns (dict of 10 loss scalars (0-dim device tensors), seeds).  ``weights``: dict loss key -> float multiplied into
+  the seed gradients (train.py:452-456: 1/10 each; None = 1).  ``w_dev``: optional (10,) f32 device tensor in LOSS_KEYS
+  order multiplied in as well, read by the kernels on the device (autograd boundary: d total / d loss_k).
+  ``bias_grads``: {'semantic','depth','center'} -> fp32 tensors the kernels accumulate the last convs' bias gradients
+  into.  want_seeds=False: loss values only.  seeds: key -> gradient of the (weighted) total wrt the pre-activation of a
+  head, in the layout the backward GEMMs consume."""
   from . import _lib  # pylint: disable=import-outside-toplevel
   lib = _lib.load()
   m, cfg = eng.m, eng.cfg
+  if any(float(w) != 1.0 for w in list(cfg.semantic_weights) + list(cfg.bev_semantic_weights)):
+    raise NotImplementedError('tfpp_ce_map_loss assumes all-ones class weights on the semantic maps (config.py:163-164)')
+  weights = weights or {k: 1.0 for k in LOSS_KEYS}
+  bias_grads = bias_grads or {}
   _, pred_ts, pred_cp, pred_sem, pred_bev, pred_depth, bb = outputs[:7]
   dev = pred_ts.device
   b = pred_ts.shape[0]
@@ -151,62 +195,63 @@ def compute_losses(eng, st, outputs, labels, weights):
   stream = ops._stream()  # pylint: disable=protected-access
   seeds = {}
   losses = {}
+  wp = (lambda i: w_dev[i:].data_ptr()) if w_dev is not None else (lambda i: None)
   # target speed CE + checkpoint L1 (model.py:416-420)
+  pred_ts, pred_cp = pred_ts.contiguous(), pred_cp.contiguous()
   dlogits = torch.empty_like(pred_ts)
   dcp = torch.empty_like(pred_cp)
   _lib.check(lib.tfpp_planner_loss(pred_ts.data_ptr(), labels['target_speed'].data_ptr(),
                                    packed(m.loss_speed.weight, 'f32').data_ptr(), pred_cp.data_ptr(),
                                    labels['checkpoint'].data_ptr(), weights['loss_target_speed'],
-                                   weights['loss_checkpoint'], sums[0:2].data_ptr(), dlogits.data_ptr(), dcp.data_ptr(),
-                                   b, pred_ts.shape[1], pred_cp.shape[1] * pred_cp.shape[2], stream), 'planner_loss')
+                                   weights['loss_checkpoint'], wp(0), sums[0:2].data_ptr(), dlogits.data_ptr(),
+                                   dcp.data_ptr(), b, pred_ts.shape[1], pred_cp.shape[1] * pred_cp.shape[2], stream),
+             'planner_loss')
   losses['loss_target_speed'], losses['loss_checkpoint'] = sums[0], sums[1]
   seeds['planner'] = (dcp, dlogits)
   # semantic CE (model.py:423)
   hw = pred_sem.shape[2] * pred_sem.shape[3]
   ncls = pred_sem.shape[1]
   cp = 16  # multiple of 16: the small-channel dgrad / wgrad kernels take 16- or 32-channel gradients
-  dz = torch.empty((b, pred_sem.shape[2], pred_sem.shape[3], cp), dtype=BF16, device=dev)
-  conv = m.semantic_decoder.deconv3[2]
+  dz = torch.empty((b, pred_sem.shape[2], pred_sem.shape[3], cp), dtype=BF16, device=dev) if want_seeds else None
   _lib.check(lib.tfpp_ce_map_loss(pred_sem.data_ptr(), labels['semantic'].data_ptr(), None,
-                                  weights['loss_semantic'] / (b * hw), sums[2:3].data_ptr(), dz.data_ptr(), None,
-                                  st.g(conv.bias).data_ptr(), b, ncls, cp, hw, stream), 'ce semantic')
+                                  weights['loss_semantic'] / (b * hw), wp(2), sums[2:3].data_ptr(), ops._p(dz), None,  # pylint: disable=protected-access
+                                  ops._p(bias_grads.get('semantic')), b, ncls, cp, hw, stream), 'ce semantic')  # pylint: disable=protected-access
   losses['loss_semantic'] = sums[2] / (b * hw)
-  seeds[id(pred_sem)] = dz
+  seeds['semantic'] = dz
   # BEV semantic CE with the frustum mask as ignore_index (model.py:426-431)
   hwb = pred_bev.shape[2] * pred_bev.shape[3]
   nb = pred_bev.shape[1]
   valid = packed(m.valid_bev_pixels, 'f32')
   n_valid = eng._const('n_valid_bev', lambda: m.valid_bev_pixels.detach().sum().cpu(), 'cpu')  # pylint: disable=protected-access
   count = float(n_valid) * b
-  dbev = torch.empty_like(pred_bev)
+  dbev = torch.empty_like(pred_bev) if want_seeds else None
   _lib.check(lib.tfpp_ce_map_loss(pred_bev.data_ptr(), labels['bev_semantic'].data_ptr(), valid.data_ptr(),
-                                  weights['loss_bev_semantic'] / count, sums[3:4].data_ptr(), None, dbev.data_ptr(),
+                                  weights['loss_bev_semantic'] / count, wp(3), sums[3:4].data_ptr(), None, ops._p(dbev),  # pylint: disable=protected-access
                                   None, b, nb, 16, hwb, stream), 'ce bev')
   losses['loss_bev_semantic'] = sums[3] / count
-  seeds[id(pred_bev)] = dbev
+  seeds['bev'] = dbev
   # depth L1 on the sigmoid output (model.py:379,434)
   n = pred_depth.numel()
-  dzd = torch.empty((b, pred_depth.shape[1], pred_depth.shape[2], 16), dtype=BF16, device=dev)
-  convd = m.depth_decoder.deconv3[2]
+  dzd = torch.empty((b, pred_depth.shape[-2], pred_depth.shape[-1], 16), dtype=BF16, device=dev) if want_seeds else None
   _lib.check(lib.tfpp_l1_sigmoid_loss(pred_depth.data_ptr(), labels['depth'].data_ptr(), weights['loss_depth'] / n,
-                                      sums[4:5].data_ptr(), dzd.data_ptr(), st.g(convd.bias).data_ptr(), 16, n, stream),
-             'l1 depth')
+                                      wp(4), sums[4:5].data_ptr(), ops._p(dzd), ops._p(bias_grads.get('depth')), 16, n,  # pylint: disable=protected-access
+                                      stream), 'l1 depth')
   losses['loss_depth'] = sums[4] / n
   seeds['depth'] = dzd
   # CenterNet head losses (center_net.py:77-123)
-  maps = bb[0]._base if bb[0]._base is not None else bb[0]  # the fused (B,21,64,64) buffer  pylint: disable=protected-access
+  maps = bb if torch.is_tensor(bb) else _base_of(bb[0])  # the fused (B,21,64,64) buffer
   hwc = maps.shape[2] * maps.shape[3]
   w5 = eng._const('w5_' + repr(sorted(weights.items())), lambda: torch.tensor(  # pylint: disable=protected-access
       [weights[k] for k in ('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res')],
       dtype=F32), dev)
-  dzh = torch.empty((b, maps.shape[2], maps.shape[3], 24), dtype=BF16, device=dev)
-  heads = m.head.head_names()
-  bias_first, bias_last = getattr(m.head, heads[0])[2].bias, getattr(m.head, heads[-1])[2].bias
+  if w_dev is not None:
+    w5 = w5 * w_dev[5:10]
+  dzh = torch.empty((b, maps.shape[2], maps.shape[3], 24), dtype=BF16, device=dev) if want_seeds else None
   _lib.check(lib.tfpp_center_head_loss(maps.data_ptr(), labels['center_heatmap'].data_ptr(), labels['wh'].data_ptr(),
                                        labels['offset'].data_ptr(), labels['yaw_class'].data_ptr(),
                                        labels['yaw_res'].data_ptr(), labels['pixel_weight'].data_ptr(),
                                        labels['avg_factor'].data_ptr(), w5.data_ptr(), sums[5:10].data_ptr(),
-                                       dzh.data_ptr(), st.g_span(bias_first, bias_last).data_ptr(), b, hwc,
+                                       ops._p(dzh), ops._p(bias_grads.get('center')), b, hwc,  # pylint: disable=protected-access
                                        cfg.num_bb_classes, cfg.num_dir_bins, 24, stream), 'center loss')
   for i, k in enumerate(('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res')):
     losses[k] = sums[5 + i]
@@ -490,7 +535,7 @@ class Backward:
 
   def bev_tail(self, r, seeds):
     src, out = r['src'], r['out']
-    dbev = seeds.pop(id(out))
+    dbev = seeds.pop('bev')
     b, sh, sw, _ = src.shape
     ncls = r['ncls']
     cp = _pad8(ncls)
@@ -612,12 +657,14 @@ class Backward:
   # -- driver --------------------------------------------------------------------------------------------------
   def run(self, tape, seeds):
     eng = self.eng
-    # seeds of the perspective decoders are keyed by the output tensors of their last conv_bias records
     for r in tape:
       if r['op'] == 'planner_mem':
         self.eng_mem = r['mem'].view(-1, r['d'])
-    self._depth_seed = seeds.pop('depth', None)
-    self._depth_conv = eng.m.depth_decoder.deconv3[2] if hasattr(eng.m, 'depth_decoder') else None
+    # seeds of the perspective decoders belong to the last conv_bias record of each decoder
+    self._named_seeds = {}
+    for key, dec in (('depth', 'depth_decoder'), ('semantic', 'semantic_decoder')):
+      if key in seeds and hasattr(eng.m, dec):
+        self._named_seeds[id(getattr(eng.m, dec).deconv3[2])] = seeds.pop(key)
     if not any(r.get('side') for r in tape):
       for r in reversed(tape):
         self._dispatch(r, seeds)
@@ -685,9 +732,8 @@ class Backward:
   def _dispatch(self, r, seeds):
     op = r['op']
     if op == 'conv_bias':
-      if self._depth_seed is not None and r['conv'] is self._depth_conv:
-        seeds[id(r['y'])] = self._depth_seed
-        self._depth_seed = None
+      if id(r['conv']) in self._named_seeds:
+        seeds[id(r['y'])] = self._named_seeds.pop(id(r['conv']))
       self.conv_bias(r, seeds)
     elif op == 'conv_bn':
       self.conv_bn(r)
@@ -722,6 +768,27 @@ class Backward:
 # ---------------------------------------------------------------------------------------------------------------
 # trainer
 # ---------------------------------------------------------------------------------------------------------------
+def training_forward(eng, st, inputs):
+  """Training-mode forward with a tape (list of saved activations) for training.Backward.  Returns (outputs, tape)."""
+  eng.tape = []
+  fused = st.counter_mask is not None
+  eng.batch_counters_fused = fused
+  eng.bn_seen = None if fused else []
+  if fused:
+    st.count_batches()
+  try:
+    out = eng.forward(inputs['rgb'], inputs['lidar_bev'], inputs['target_point'], inputs['ego_vel'], inputs['command'],
+                      training=True)
+    tape = eng.tape
+  finally:
+    eng.tape = None
+    eng.batch_counters_fused = False
+    if not fused and eng.bn_seen is not None and torch.cuda.is_available() and not torch.cuda.is_current_stream_capturing():
+      st.learn_counter_mask(eng.bn_seen)
+    eng.bn_seen = None
+  return out, tape
+
+
 def allreduce_flat(grad, group, bucket_elems):
   """Sum-all-reduce a flat gradient buffer in buckets (async, then wait): DDP's exchange step (train.py:516) without
   the per-parameter hooks.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
@@ -735,10 +802,17 @@ def allreduce_flat(grad, group, bucket_elems):
 class Trainer:
   """One process per GPU.  step(batch) = forward + fused losses + backward + (bucketed all-reduce) + AdamW."""
 
-  def __init__(self, model, lr=3e-4, weight_decay=0.01, loss_weights=None, process_group=None, bucket_mb=64):
+  def __init__(self, model, lr=3e-4, weight_decay=0.01, loss_weights=None, process_group=None, bucket_mb=64,
+               use_optim_groups=False):
     self.model = model
     self.eng = model.engine
-    self.st = FlatState(model)
+    if getattr(model, '_boundary', None) is not None:
+      raise RuntimeError('this model already trains through the autograd boundary (model(...) in training mode)')
+    object.__setattr__(model, '_trainer_owned', True)
+    self.st = FlatState(model, include_frozen=True)
+    if use_optim_groups:  # train.py:522-525: decay / no-decay split by parameter name and module type
+      groups = model.create_optimizer_groups(weight_decay)
+      self.st.set_flags(no_decay=[p for g in groups if g['weight_decay'] == 0.0 for p in g['params']])
     self.lr, self.wd = lr, weight_decay
     w = loss_weights or {k: 1.0 for k in LOSS_KEYS}
     tot = sum(w.values())
@@ -747,27 +821,20 @@ class Trainer:
     self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
     self.bucket_elems = bucket_mb * 1024 * 1024 // 4
     self.plan = eng_mod.PackPlan(self.st.flat) if self.st.flat.is_cuda else None
+    if self.world > 1:
+      # DistributedDataParallel's constructor broadcasts rank 0's parameters and buffers (train.py:516): replicas that
+      # were initialised or loaded differently must not train diverged copies
+      torch.distributed.broadcast(self.st.flat, src=torch.distributed.get_global_rank(process_group, 0), group=process_group)
+      for buf in model.buffers():
+        if buf.is_floating_point():
+          torch.distributed.broadcast(buf, src=torch.distributed.get_global_rank(process_group, 0), group=process_group)
 
   def forward_backward(self, inputs, labels):
     eng, st = self.eng, self.st
     st.zero_grad()
-    eng.tape = []
-    fused = st.counter_mask is not None
-    eng.batch_counters_fused = fused
-    eng.bn_seen = None if fused else []
-    if fused:
-      st.count_batches()
-    try:
-      out = eng.forward(inputs['rgb'], inputs['lidar_bev'], inputs['target_point'], inputs['ego_vel'],
-                        inputs['command'], training=True)
-      losses, seeds = compute_losses(eng, st, out, labels, self.loss_weights)
-      Backward(eng, st).run(eng.tape, seeds)
-    finally:
-      eng.tape = None
-      eng.batch_counters_fused = False
-      if not fused and eng.bn_seen is not None and torch.cuda.is_available() and not torch.cuda.is_current_stream_capturing():
-        st.learn_counter_mask(eng.bn_seen)
-      eng.bn_seen = None
+    out, tape = training_forward(eng, st, inputs)
+    losses, seeds = compute_losses(eng, out, labels, self.loss_weights, loss_bias_targets(eng, st))
+    Backward(eng, st).run(tape, seeds)
     return out, losses
 
   def allreduce(self):
@@ -826,12 +893,28 @@ class Trainer:
       opt()
       return r
 
+    # the two warm-up steps are real optimizer steps: snapshot everything they mutate and put it back afterwards, so
+    # that capture() has no side effect on the training state
+    st = self.st
+    snap = [(t, t.clone()) for t in (st.flat, st.exp_avg, st.exp_avg_sq, st.max_exp_avg_sq, st.dev_state,
+                                     st.batch_counters)]
+    snap += [(b, b.clone()) for b in self.model.buffers() if b.is_floating_point()]
+    step_count = st.step_count
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
       for _ in range(2):
         body()
     torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+      for t, saved in snap:
+        t.copy_(saved)
+    st.step_count = step_count
+    st.dev_state[1:2].fill_(self.lr)
+    if self.plan is not None:
+      self.plan.refresh()
+    eng_mod.PARAM_EPOCH[0] += 1
     torch.cuda.synchronize()
     from . import _lib  # pylint: disable=import-outside-toplevel
     _lib.reset_launch_count()
@@ -911,4 +994,7 @@ class Trainer:
     if self.graph_opt is not None:
       self.allreduce()
       self.graph_opt.replay()
+    # the graph rewrote parameters and BatchNorm running statistics through raw pointers (no version counter moved):
+    # every cached weight pack / folded BatchNorm affine outside the PackPlan is stale now
+    eng_mod.PARAM_EPOCH[0] += 1
     return self._gout, self._gloss

@@ -264,19 +264,22 @@ int tfpp_planner_head_bwd(const float* joined, const float* target_point, const 
                           float* dw_ts0, float* db_ts0, float* dw_ts1, float* db_ts1, int batch, int n_wp, int d_model,
                           int hidden, int n_speed, tfpp_stream_t stream);
 
-/* fused losses (model.py:394-445, center_net.py:77-123): scalar loss sums + d(weighted loss)/d(pre-activation) */
+/* fused losses (model.py:394-445, center_net.py:77-123): scalar loss sums + d(weighted loss)/d(pre-activation).
+ * The gradient outputs (dz*, dbias, dlogits/dcp excepted) may be NULL: loss values only.  w_dev / w2_dev (nullable):
+ * loss weight(s) read on the device and multiplied into the gradients — the autograd boundary passes d(total)/d(loss)
+ * this way without a host round trip (train.py:889-896 forms the total from the dict compute_loss returns). */
 int tfpp_ce_map_loss(const float* logits, const long long* labels, const float* valid, float grad_scale,
-                     float* loss_sum, void* dz_nhwc, float* dz_nchw, float* dbias, int batch, int classes,
-                     int channels_padded, int hw, tfpp_stream_t stream);
-int tfpp_l1_sigmoid_loss(const float* p, const float* target, float grad_scale, float* loss_sum, void* dz_nhwc,
-                         float* dbias, int channels_padded, long long n, tfpp_stream_t stream);
+                     const float* w_dev, float* loss_sum, void* dz_nhwc, float* dz_nchw, float* dbias, int batch,
+                     int classes, int channels_padded, int hw, tfpp_stream_t stream);
+int tfpp_l1_sigmoid_loss(const float* p, const float* target, float grad_scale, const float* w_dev, float* loss_sum,
+                         void* dz_nhwc, float* dbias, int channels_padded, long long n, tfpp_stream_t stream);
 int tfpp_center_head_loss(const float* maps, const float* t_heat, const float* t_wh, const float* t_off,
                           const long long* t_ycls, const float* t_yres, const float* pix_w, const float* avg_factor,
                           const float* w5, float* losses, void* dz, float* dbias, int batch, int hw, int n_cls,
                           int n_bins, int channels_padded, tfpp_stream_t stream);
 int tfpp_planner_loss(const float* logits, const long long* labels, const float* class_w, const float* cp,
-                      const float* cp_t, float w_ts, float w_cp, float* losses, float* dlogits, float* dcp, int batch,
-                      int n_cls, int n_cp, tfpp_stream_t stream);
+                      const float* cp_t, float w_ts, float w_cp, const float* w2_dev, float* losses, float* dlogits,
+                      float* dcp, int batch, int n_cls, int n_cp, tfpp_stream_t stream);
 
 /* Grouped 3x3 convolution of the RegNetY bottleneck (timm regnet.Bottleneck.conv2, group width 24; stride 1 or 2,
  * padding 1) on a haloed shared-memory tile: x (B,H,W,C) NHWC bf16, C % 72 == 0; w (C/24, 9, 24, 24) bf16 =
@@ -322,10 +325,12 @@ int tfpp_gather_pack(const float* flat, const int* idx, void* out, long long n, 
  * all-reduce).  dev_state (optional, 4 floats on the device: [step count, learning rate, 1 - beta1^step,
  * sqrt(1 - beta2^step)]; the caller sets the first two) replaces the host-side `step` / `lr` so the launch can be
  * replayed from a CUDA graph; the count is incremented and the bias corrections refreshed by the call.
- * param / grad / state buffers 16-byte aligned. */
+ * param / grad / state buffers 16-byte aligned.  flags (optional, one byte per element): bit 0 = no weight decay
+ * (the no_decay group of create_optimizer_groups, model.py:556-645), bit 1 = frozen (requires_grad=False,
+ * train.py:495-508: element untouched). */
 int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
                        long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                       float grad_scale, float* dev_state, tfpp_stream_t stream);
+                       float grad_scale, float* dev_state, const unsigned char* flags, tfpp_stream_t stream);
 
 #ifdef __cplusplus
 }

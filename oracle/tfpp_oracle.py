@@ -308,16 +308,11 @@ def center_net_head(sd, p, feat):
           head('yaw_res_head'), None, None)
 
 
-def forward(sd, rgb, lidar_bev, target_point, ego_vel, command, cfg=None, training=False, taps=None):
-  """LidarCenterNet.forward, model.py:279-392, default GlobalConfig (transFuser backbone, decoder join, all aux
-  heads).  Returns the reference's 10-tuple."""
+def planner(sd, fused, target_point, ego_vel, command, cfg=None, training=False, taps=None):
+  """model.py:299-358: change_channel + sine position encoding -> 64 memory tokens, extra-sensor token, 6-layer decoder
+  over the 11 learned queries, GRU checkpoints + target-speed logits.  Returns (pred_checkpoint, pred_target_speed)."""
   cfg = cfg or DEFAULT_CFG
-  sd = {k: v.float() if torch.is_floating_point(v) else v for k, v in sd.items()}
-  bs = rgb.shape[0]
-  bev_feature_grid, fused, image_feature_grid = backbone_forward(sd, rgb, lidar_bev, cfg, training, taps=taps)
-  if taps is not None:
-    taps['bev_feature_grid'], taps['fused_features'], taps['image_feature_grid'] = (bev_feature_grid, fused,
-                                                                                    image_feature_grid)
+  bs = fused.shape[0]
   # model.py:301-303
   f = F.conv2d(fused, sd['change_channel.weight'], sd['change_channel.bias'])
   f = f + position_embedding_sine(bs, f.shape[2], f.shape[3], cfg['gru_input_size'] // 2)
@@ -346,6 +341,20 @@ def forward(sd, rgb, lidar_bev, target_point, ego_vel, command, cfg=None, traini
   pred_target_speed = F.linear(F.relu(F.linear(ts, sd['target_speed_network.0.weight'],
                                                sd['target_speed_network.0.bias'])),
                                sd['target_speed_network.2.weight'], sd['target_speed_network.2.bias'])
+  return pred_checkpoint, pred_target_speed
+
+
+def forward(sd, rgb, lidar_bev, target_point, ego_vel, command, cfg=None, training=False, taps=None):
+  """LidarCenterNet.forward, model.py:279-392, default GlobalConfig (transFuser backbone, decoder join, all aux
+  heads).  Returns the reference's 10-tuple."""
+  cfg = cfg or DEFAULT_CFG
+  sd = {k: v.float() if torch.is_floating_point(v) else v for k, v in sd.items()}
+  bs = rgb.shape[0]
+  bev_feature_grid, fused, image_feature_grid = backbone_forward(sd, rgb, lidar_bev, cfg, training, taps=taps)
+  if taps is not None:
+    taps['bev_feature_grid'], taps['fused_features'], taps['image_feature_grid'] = (bev_feature_grid, fused,
+                                                                                    image_feature_grid)
+  pred_checkpoint, pred_target_speed = planner(sd, fused, target_point, ego_vel, command, cfg, training, taps)
   # model.py:372-389
   pred_semantic = perspective_decoder(sd, 'semantic_decoder', image_feature_grid, cfg)
   pred_depth = torch.sigmoid(perspective_decoder(sd, 'depth_decoder', image_feature_grid, cfg)).squeeze(1)

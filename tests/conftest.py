@@ -16,6 +16,9 @@ def pytest_configure(config):
   # the CPU oracle (torch fp32) collapses when oversubscribed on many-core hosts: 16 threads are ~10x faster than 128
   import torch
   torch.set_num_threads(min(os.cpu_count() or 1, 16))
+  # "fp32 torch reference" must mean fp32: cuDNN / cuBLAS would otherwise be free to run the references in TF32
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
 
 
 @pytest.fixture(scope='session')

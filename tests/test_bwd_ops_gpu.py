@@ -1,0 +1,595 @@
+"""Op-level GPU parity of the backward / loss kernels (called through the C ABI) against torch autograd of a plain fp32 /
+fp64 restatement of the same op on the operands the kernel sees.  Complements tests/test_ops_gpu.py (forward ops, conv /
+BatchNorm / SE / attention backward) — every kernel of the training step's backward has an isolated test here or there.
+Tolerances: fp32-in / fp32-out kernels 1e-4 .. 1e-3; kernels that read or write bf16 1e-2."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+@pytest.fixture(scope='module')
+def ops():
+  if not torch.cuda.is_available():
+    pytest.skip('no CUDA device')
+  from carla_garage_b200 import ops as o
+  return o
+
+
+def rel(a, b):
+  a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
+  return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+  g = torch.Generator().manual_seed(seed)
+  return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def bf(x):
+  return x.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize('rows,c,dy_f32,with_res', [(640, 216, True, True), (352, 256, True, False), (77, 1512, False, True),
+                                                    (320, 72, False, False)])
+def test_layernorm_backward(ops, rows, c, dy_f32, with_res):
+  x = rnd(rows, c, seed=1) * 2 + 0.3
+  gamma, beta = rnd(c, seed=2).abs() + 0.5, rnd(c, seed=3)
+  dy = rnd(rows, c, seed=4)
+  dyk = dy if dy_f32 else bf(dy)
+  dres = rnd(rows, c, seed=5) if with_res else None
+  _, _, mean, rstd = ops.layernorm(x, gamma, beta, save=True)
+  dgamma, dbeta = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+  dx = ops.layernorm_bwd(dyk, x, mean, rstd, gamma, dgamma, dbeta, dres=dres)
+  xr, gr, br = (t.double().clone().requires_grad_(True) for t in (x, gamma, beta))
+  F.layer_norm(xr, (c,), gr, br, 1e-5).backward(dyk.double())
+  want = xr.grad + (dres.double() if with_res else 0)
+  tol = 1e-4 if dy_f32 else 1e-4  # the kernel computes in fp32 either way; dy itself is the shared operand
+  assert rel(dx, want) < tol and rel(dgamma, gr.grad) < tol and rel(dbeta, br.grad) < tol
+
+
+# ------------------------------------------------------------------------------------------------ bilinear / pooling
+@pytest.mark.parametrize('sh,sw,dh,dw,c', [(8, 32, 64, 256, 72), (8, 8, 16, 16, 216), (16, 16, 64, 64, 64), (8, 32, 8, 32, 1512),
+                                           (8, 32, 64, 256, 32)])
+def test_bilinear_backward(ops, sh, sw, dh, dw, c):
+  b = 2
+  dout = bf(rnd(b, dh, dw, c, seed=6))
+  src = torch.zeros(b, c, sh, sw, dtype=torch.double, device='cuda', requires_grad=True)
+  F.interpolate(src, size=(dh, dw), mode='bilinear', align_corners=False).backward(dout.double().permute(0, 3, 1, 2))
+  want = src.grad.permute(0, 2, 3, 1)
+  dsrc = torch.empty(b, sh, sw, c, dtype=torch.bfloat16, device='cuda')
+  ops.bilinear_bwd(dout, dsrc, b, sh, sw, dh, dw, c)
+  assert rel(dsrc.float(), want) < 6e-3
+  # accumulate into an existing bf16 gradient
+  base = bf(rnd(b, sh, sw, c, seed=7))
+  acc = base.clone()
+  ops.bilinear_bwd(dout, acc, b, sh, sw, dh, dw, c, accumulate=True)
+  assert rel(acc.float(), want + base.double()) < 8e-3
+  # fp32 token slab with strides (the fusion path: rows [0, sh*sw) of a (B, T, C) matrix)
+  t = sh * sw + 64
+  slab = torch.full((b, t, c), 7.0, device='cuda')
+  ops.bilinear_bwd(dout, slab, b, sh, sw, dh, dw, c, src_batch_stride=t * c, src_row_stride=c)
+  assert rel(slab[:, :sh * sw].reshape(b, sh, sw, c), want) < 1e-5
+  assert float((slab[:, sh * sw:] - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('h,w,ph,pw,c,f32', [(64, 256, 8, 32, 72, True), (16, 16, 8, 8, 576, False), (8, 32, 8, 32, 1512, True),
+                                             (32, 32, 8, 8, 216, False)])
+def test_pool_backward_add(ops, h, w, ph, pw, c, f32):
+  b, extra = 2, 64
+  t = ph * pw + extra
+  dtok = rnd(b, t, c, seed=8)
+  dtk = dtok if f32 else bf(dtok)
+  dout = bf(rnd(b, h, w, c, seed=9))
+  x = torch.zeros(b, c, h, w, dtype=torch.double, device='cuda', requires_grad=True)
+  F.adaptive_avg_pool2d(x, (ph, pw)).backward(dtk.double()[:, extra:].reshape(b, ph, pw, c).permute(0, 3, 1, 2))
+  want = x.grad.permute(0, 2, 3, 1)
+  got = ops.pool_bwd_add(None, dtk, (b, h, w, c), ph, pw, t, extra)
+  assert rel(got.float(), want) < 5e-3
+  got = ops.pool_bwd_add(dout, dtk, (b, h, w, c), ph, pw, t, extra)
+  assert rel(got.float(), want + dout.double()) < 6e-3
+
+
+def test_cast_rows_batch_reduce_add(ops):
+  g_, gr, r0, rows, c = 3, 65, 0, 64, 256
+  x = rnd(g_, gr, c, seed=10)
+  db = torch.zeros(c, device='cuda')
+  out = ops.cast_rows(x, g_, gr, r0, rows, c, dbias=db)
+  assert torch.equal(out.view(g_, rows, c), bf(x[:, r0:r0 + rows]))
+  assert rel(db, x[:, r0:r0 + rows].sum((0, 1))) < 1e-5
+  out = ops.cast_rows(x, g_, gr, 1, 64, c)
+  assert torch.equal(out.view(g_, 64, c), bf(x[:, 1:65]))
+  acc = rnd(320 * 72, seed=11)
+  want = acc + rnd(5, 320 * 72, seed=12).sum(0)
+  ops.batch_reduce(rnd(5, 320 * 72, seed=12), acc, 5)
+  assert rel(acc, want) < 1e-6
+  a, b2 = bf(rnd(1000, 24, seed=13)), bf(rnd(1000, 24, seed=14))
+  assert rel(ops.add_bf16(a, b2).float(), a.float() + b2.float()) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ planner pieces
+@pytest.mark.parametrize('tq,tk,cross', [(11, 11, False), (11, 65, True)])
+def test_small_mha_backward(ops, tq, tk, cross):
+  b, heads, hd = 3, 8, 32
+  d = heads * hd
+  if cross:
+    q, kv = bf(rnd(b, tq, d, seed=15)), bf(rnd(b, tk, 2 * d, seed=16))
+    qs, ks, vs = (tq * d, d), (tk * 2 * d, 2 * d), (tk * 2 * d, 2 * d)
+    out = ops.small_mha(q, kv, kv, b, heads, tq, tk, hd, qs, ks, vs, v_off=d)
+    qf, kf, vf = q.double(), kv.double()[..., :d], kv.double()[..., d:]
+  else:
+    qkv = bf(rnd(b, tq, 3 * d, seed=17))
+    s3 = (tq * 3 * d, 3 * d)
+    out = ops.small_mha(qkv, qkv, qkv, b, heads, tq, tq, hd, s3, s3, s3, k_off=d, v_off=2 * d)
+    qf, kf, vf = qkv.double()[..., :d], qkv.double()[..., d:2 * d], qkv.double()[..., 2 * d:]
+  qf, kf, vf = (t.clone().requires_grad_(True) for t in (qf, kf, vf))
+  split = lambda t, n: t.reshape(b, n, heads, hd).transpose(1, 2)
+  att = F.softmax(split(qf, tq) @ split(kf, tk).transpose(-2, -1) / math.sqrt(hd), -1)
+  ref = (att @ split(vf, tk)).transpose(1, 2).reshape(b * tq, d)
+  assert rel(out.float(), ref) < 5e-3
+  dout = bf(rnd(b * tq, d, seed=18))
+  ref.backward(dout.double())
+  if cross:
+    dq = torch.empty(b * tq, d, dtype=torch.bfloat16, device='cuda')
+    dkv = torch.empty_like(kv)
+    ops.small_mha_bwd(q, kv, kv, dout, dq, dkv, dkv, b, heads, tq, tk, hd, qs, ks, vs, (tq * d, d), ks, vs,
+                      offs=(0, 0, d, 0, 0, d))
+    assert rel(dq.float(), qf.grad.reshape(b * tq, d)) < 1e-2
+    assert rel(dkv.float()[..., :d], kf.grad) < 1e-2 and rel(dkv.float()[..., d:], vf.grad) < 1e-2
+  else:
+    dqkv = torch.empty_like(qkv)
+    ops.small_mha_bwd(qkv, qkv, qkv, dout, dqkv, dqkv, dqkv, b, heads, tq, tq, hd, s3, s3, s3, s3, s3, s3,
+                      offs=(0, d, 2 * d, 0, d, 2 * d))
+    want = torch.cat([qf.grad, kf.grad, vf.grad], dim=-1)
+    assert rel(dqkv.float(), want) < 1e-2
+
+
+@pytest.mark.parametrize('training', [False, True])
+def test_extra_sensor_token_backward(ops, training):
+  from carla_garage_b200 import _lib
+  b, d, hid = 5, 256, 128
+  vel = rnd(b, 1, seed=19).abs() * 4
+  cmd = F.one_hot(torch.tensor([0, 3, 5, 1, 1]), 6).float().cuda()
+  w0, b0, w1, b1, pos = rnd(hid, 7, seed=20), rnd(hid, seed=21), rnd(d, hid, seed=22, scale=0.1), rnd(d, seed=23), \
+      rnd(1, d, seed=24)
+  dmem = rnd(b, 65, d, seed=25)
+  P = [t.double().clone().requires_grad_(True) for t in (w0, b0, w1, b1, pos)]
+  vd = vel.double()
+  vn = (vd - vd.mean()) / torch.sqrt(vd.var(unbiased=False) + 1e-5) if training else (vd - 2.0) / math.sqrt(1.5 + 1e-5)
+  tok = F.relu(F.relu(torch.cat([vn, cmd.double()], 1) @ P[0].t() + P[1]) @ P[2].t() + P[3]) + P[4]
+  tok.backward(dmem[:, 64].double())
+  G = [torch.zeros_like(t) for t in (w0, b0, w1, b1, pos)]
+  _lib.check(_lib.load().tfpp_extra_sensor_token_bwd(
+      vel.data_ptr(), cmd.data_ptr(), 0.0 if training else 2.0, 1.0 if training else 1.5, int(training), w0.data_ptr(),
+      b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), dmem.data_ptr() + 4 * 64 * d, 65 * d, G[0].data_ptr(), G[1].data_ptr(),
+      G[2].data_ptr(), G[3].data_ptr(), G[4].data_ptr(), b, 6, hid, d, ops._stream()), 'extra_sensor_bwd')  # pylint: disable=protected-access
+  for got, p, name in zip(G, P, ('w0', 'b0', 'w1', 'b1', 'pos')):
+    assert rel(got, p.grad) < 1e-4, name
+
+
+def test_planner_head_backward_gru_bptt(ops):
+  """GRU back-propagation through time + cumsum + target-speed MLP vs float64 autograd of torch.nn.GRU (model.py:839-867)."""
+  from carla_garage_b200 import _lib
+  b, d, hs, n_wp, n_speed = 4, 256, 64, 10, 4
+  torch.manual_seed(4321)
+  gru = torch.nn.GRU(d, hs, batch_first=True).double()
+  enc, dec = torch.nn.Linear(2, hs).double(), torch.nn.Linear(hs, 2).double()
+  ts = torch.nn.Sequential(torch.nn.Linear(d, d), torch.nn.ReLU(), torch.nn.Linear(d, n_speed)).double()
+  joined, tp = rnd(b, n_wp + 1, d, seed=26), rnd(b, 2, seed=27) * 10
+  jc = joined.double().cpu().requires_grad_(True)
+  o, _ = gru(jc[:, :n_wp], enc(tp.double().cpu()).unsqueeze(0))
+  cp = torch.cumsum(dec(o), 1)
+  logits = ts(jc[:, n_wp])
+  dcp, dlogits = rnd(b, n_wp, 2, seed=28), rnd(b, n_speed, seed=29)
+  (cp * dcp.double().cpu()).sum().add((logits * dlogits.double().cpu()).sum()).backward()
+  f = lambda t: t.detach().float().cuda().contiguous()
+  W = dict(w_enc=f(enc.weight), b_enc=f(enc.bias), w_ih=f(gru.weight_ih_l0), w_hh=f(gru.weight_hh_l0),
+           b_ih=f(gru.bias_ih_l0), b_hh=f(gru.bias_hh_l0), w_dec=f(dec.weight), b_dec=f(dec.bias), w_ts0=f(ts[0].weight),
+           b_ts0=f(ts[0].bias), w_ts1=f(ts[2].weight), b_ts1=f(ts[2].bias))
+  got_cp, got_ts, h_all = ops.planner_head(joined, tp, W['w_enc'], W['b_enc'], W['w_ih'], W['w_hh'], W['b_ih'], W['b_hh'],
+                                           W['w_dec'], W['b_dec'], W['w_ts0'], W['b_ts0'], W['w_ts1'], W['b_ts1'],
+                                           want_h=True)
+  assert rel(got_cp, cp) < 1e-4 and rel(got_ts, logits) < 1e-4
+  G = {k: torch.zeros_like(v) for k, v in W.items()}
+  djoined = torch.empty_like(joined)
+  _lib.check(_lib.load().tfpp_planner_head_bwd(
+      joined.data_ptr(), tp.data_ptr(), h_all.data_ptr(), W['w_enc'].data_ptr(), W['b_enc'].data_ptr(),
+      W['w_ih'].data_ptr(), W['w_hh'].data_ptr(), W['b_ih'].data_ptr(), W['b_hh'].data_ptr(), W['w_dec'].data_ptr(),
+      W['w_ts0'].data_ptr(), W['b_ts0'].data_ptr(), W['w_ts1'].data_ptr(), dcp.data_ptr(), dlogits.data_ptr(),
+      djoined.data_ptr(), G['w_enc'].data_ptr(), G['b_enc'].data_ptr(), G['w_ih'].data_ptr(), G['w_hh'].data_ptr(),
+      G['b_ih'].data_ptr(), G['b_hh'].data_ptr(), G['w_dec'].data_ptr(), G['b_dec'].data_ptr(), G['w_ts0'].data_ptr(),
+      G['b_ts0'].data_ptr(), G['w_ts1'].data_ptr(), G['b_ts1'].data_ptr(), b, n_wp, d, hs, n_speed, ops._stream()),  # pylint: disable=protected-access
+      'planner_head_bwd')
+  want = dict(w_enc=enc.weight.grad, b_enc=enc.bias.grad, w_ih=gru.weight_ih_l0.grad, w_hh=gru.weight_hh_l0.grad,
+              b_ih=gru.bias_ih_l0.grad, b_hh=gru.bias_hh_l0.grad, w_dec=dec.weight.grad, b_dec=dec.bias.grad,
+              w_ts0=ts[0].weight.grad, b_ts0=ts[0].bias.grad, w_ts1=ts[2].weight.grad, b_ts1=ts[2].bias.grad)
+  assert rel(djoined, jc.grad) < 2e-4
+  for k, v in want.items():
+    assert rel(G[k], v) < 2e-4, k
+
+
+@pytest.mark.parametrize('cin,normalize', [(3, True), (1, False), (2, False)])
+def test_stem_forward_and_weight_gradient(ops, cin, normalize):
+  """timm stem conv (3x3 / stride 2) fused with normalize_imagenet; cin = 1 / 2 are the LiDAR stems (use_ground_plane)."""
+  b, h, w = 2, 32, 64
+  g = torch.Generator().manual_seed(30)
+  x = (torch.randint(0, 256, (b, cin, h, w), generator=g).float() if normalize else
+       torch.rand(b, cin, h, w, generator=g)).cuda()
+  wt = rnd(32, cin, 3, 3, seed=31, scale=0.2)
+  a = s = None
+  xn = x
+  if normalize:
+    a = torch.tensor([1 / (255 * 0.229), 1 / (255 * 0.224), 1 / (255 * 0.225)]).cuda()
+    s = torch.tensor([-0.485 / 0.229, -0.456 / 0.224, -0.406 / 0.225]).cuda()
+    xn = x * a.view(1, 3, 1, 1) + s.view(1, 3, 1, 1)
+  raw = ops.stem_conv(x, wt, a, s)
+  wr = wt.double().clone().requires_grad_(True)
+  ref = F.conv2d(xn.double(), wr, None, stride=2, padding=1)
+  assert rel(raw.float().permute(0, 3, 1, 2), ref) < 4e-3
+  draw = bf(rnd(b, h // 2, w // 2, 32, seed=32))
+  ref.backward(draw.double().permute(0, 3, 1, 2))
+  dw = torch.zeros_like(wt)
+  ops.stem_wgrad(x, draw, a, s, dw)
+  assert rel(dw, wr.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def _loss_case(b=3, seed=40):
+  from carla_garage_b200 import synth
+  g = torch.Generator().manual_seed(seed)
+  r = lambda *s: torch.randn(*s, generator=g)
+  preds = dict(ts=r(b, 4), cp=r(b, 10, 2) * 3, sem=r(b, 7, 64, 96) * 2, bev=r(b, 11, 256, 256) * 2,
+               depth=torch.sigmoid(r(b, 1, 64, 96)), maps=r(b, 21, 64, 64))
+  preds['maps'][:, :4] = torch.sigmoid(preds['maps'][:, :4] - 2)
+  lab = synth.make_labels(b, seed=seed)
+  lab['semantic'] = lab['semantic'][:, :64, :96].contiguous()
+  lab['depth'] = lab['depth'][:, :64, :96].contiguous()
+  return {k: v.cuda().contiguous() for k, v in preds.items()}, {k: v.cuda().contiguous() for k, v in lab.items()}
+
+
+def _torch_loss_dict(model, p, lab):
+  bb = (p['maps'][:, 0:4], p['maps'][:, 4:6], p['maps'][:, 6:8], p['maps'][:, 8:20], p['maps'][:, 20:21])
+  out = {}
+  out['loss_target_speed'] = F.cross_entropy(p['ts'], lab['target_speed'], weight=model.loss_speed.weight.double())
+  out['loss_checkpoint'] = (p['cp'] - lab['checkpoint']).abs().mean()
+  out['loss_semantic'] = F.cross_entropy(p['sem'], lab['semantic'])
+  valid = model.valid_bev_pixels.squeeze(1).int()
+  vis = (valid - 1) + valid * lab['bev_semantic']
+  out['loss_bev_semantic'] = F.cross_entropy(p['bev'], vis.long(), ignore_index=-1)
+  out['loss_depth'] = F.l1_loss(p['depth'].squeeze(1), lab['depth'])
+  avg = lab['avg_factor'].sum() + torch.finfo(torch.float32).eps
+  pw = lab['pixel_weight']
+  pr, t = bb[0], lab['center_heatmap']
+  focal = -(pr + 1e-12).log() * (1 - pr).pow(2) * t.eq(1).double() - (1 - pr + 1e-12).log() * pr.pow(2) * (1 - t).pow(4)
+  out['loss_center_heatmap'] = focal.sum() / avg
+  out['loss_wh'] = ((bb[1] - lab['wh']).abs() * pw).sum() / (avg * 2)
+  out['loss_offset'] = ((bb[2] - lab['offset']).abs() * pw).sum() / (avg * 2)
+  out['loss_yaw_class'] = (F.cross_entropy(bb[3], lab['yaw_class'], reduction='none') * pw[:, 0]).sum() / avg
+  out['loss_yaw_res'] = (F.smooth_l1_loss(bb[4], lab['yaw_res'].double(), reduction='none') * pw[:, 0:1]).sum() / avg
+  return out
+
+
+def test_loss_kernels_values_and_seed_gradients(ops, oracle_state):
+  """The four fused loss kernels (csrc/loss.cu): 10 loss values <= 1e-5 of a float64 torch restatement of
+  model.py:394-445 / center_net.py:77-123, seed gradients vs autograd (fp32 outputs 1e-5, bf16 seeds 4e-3 = rounding),
+  bias gradients, host weights and device-side weights."""
+  from carla_garage_b200 import training
+  from carla_garage_b200.config import GlobalConfig
+  from carla_garage_b200.nn import LidarCenterNet
+  m = LidarCenterNet(GlobalConfig())
+  m.load_state_dict(oracle_state, strict=True)
+  m = m.cuda()
+  eng = m.engine
+  preds, lab = _loss_case()
+  keys = training.LOSS_KEYS
+  wts = {k: 0.05 + 0.1 * i for i, k in enumerate(keys)}
+  # float64 reference on the pre-activations the seeds refer to
+  pd = {k: v.double().clone() for k, v in preds.items()}
+  z_depth = torch.logit(pd['depth']).requires_grad_(True)
+  z_heat = torch.logit(pd['maps'][:, :4]).requires_grad_(True)
+  rest = pd['maps'][:, 4:].clone().requires_grad_(True)
+  leaves = {k: pd[k].requires_grad_(True) for k in ('ts', 'cp', 'sem', 'bev')}
+  pr = dict(leaves, depth=torch.sigmoid(z_depth), maps=torch.cat([torch.sigmoid(z_heat), rest], 1))
+  import types
+  ns = types.SimpleNamespace(loss_speed=types.SimpleNamespace(weight=m.loss_speed.weight.detach()),
+                             valid_bev_pixels=m.valid_bev_pixels.detach())
+  ref = _torch_loss_dict(ns, pr, {k: (v.double() if v.is_floating_point() else v) for k, v in lab.items()})
+  sum(wts[k] * ref[k] for k in keys).backward()
+  outputs = (None, preds['ts'], preds['cp'], preds['sem'], preds['bev'], preds['depth'], preds['maps'])
+
+  def run(weights, w_dev):
+    bias = {'semantic': torch.zeros(7, device='cuda'), 'depth': torch.zeros(1, device='cuda'),
+            'center': torch.zeros(21, device='cuda')}
+    eng.new_arena(torch.device('cuda'), 64)
+    losses, seeds = training.compute_losses(eng, outputs, lab, weights, bias, w_dev=w_dev)
+    torch.cuda.synchronize()
+    return losses, seeds, bias
+
+  for mode in ('host', 'device'):
+    if mode == 'host':
+      losses, seeds, bias = run(wts, None)
+    else:
+      losses, seeds, bias = run(None, torch.tensor([wts[k] for k in keys], device='cuda'))
+    for k in keys:
+      assert abs(float(losses[k]) - float(ref[k])) <= 1e-5 * max(1.0, abs(float(ref[k]))), (mode, k, float(losses[k]), float(ref[k]))
+    dcp, dlogits = seeds['planner']
+    assert rel(dcp, leaves['cp'].grad) < 1e-5 and rel(dlogits, leaves['ts'].grad) < 1e-5
+    assert rel(seeds['bev'], leaves['bev'].grad) < 1e-5
+    nhwc = lambda g: g.permute(0, 2, 3, 1)
+    assert rel(seeds['semantic'].float()[..., :7], nhwc(leaves['sem'].grad)) < 4e-3
+    assert float(seeds['semantic'].float()[..., 7:].abs().max()) == 0.0
+    assert rel(seeds['depth'].float()[..., :1], nhwc(z_depth.grad)) < 4e-3
+    want_center = nhwc(torch.cat([z_heat.grad, rest.grad], 1))
+    assert rel(seeds['center'].float()[..., :21], want_center) < 4e-3
+    assert float(seeds['center'].float()[..., 21:].abs().max()) == 0.0
+    assert rel(bias['semantic'], leaves['sem'].grad.sum((0, 2, 3))) < 1e-4
+    assert rel(bias['depth'], z_depth.grad.sum((0, 2, 3))) < 1e-4
+    assert rel(bias['center'], want_center.sum((0, 1, 2))) < 1e-4
+  # values-only mode touches no gradient buffer
+  eng.new_arena(torch.device('cuda'), 64)
+  losses, seeds = training.compute_losses(eng, outputs, lab, want_seeds=False)
+  assert seeds['semantic'] is None and seeds['center'] is None
+  assert abs(float(losses['loss_yaw_res']) - float(ref['loss_yaw_res'])) <= 1e-5
+
+
+def test_output_gradient_to_seed_conversion(ops):
+  """tfpp_act_bwd layout 1 (NCHW f32 gradient of an output -> NHWC bf16 seed + bias gradient): the general autograd
+  path of carla_garage_b200.boundary for sigmoid heads (depth; heat-map channels of the CenterNet map)."""
+  b, c, h, w, cp, lim = 2, 21, 16, 24, 24, 4
+  dy, z = rnd(b, c, h, w, seed=41), rnd(b, c, h, w, seed=42)
+  y = z.clone()
+  y[:, :lim] = torch.sigmoid(z[:, :lim])
+  db = torch.zeros(c, device='cuda')
+  dz = ops.act_bwd(dy, y, ops.ACT_SIGMOID, b, h * w, c, layout=1, act_n_limit=lim, dbias=db, channels_padded=cp)
+  want = dy.clone()
+  want[:, :lim] = dy[:, :lim] * y[:, :lim] * (1 - y[:, :lim])
+  assert rel(dz.view(b, h, w, cp).float()[..., :c], want.permute(0, 2, 3, 1)) < 4e-3
+  assert float(dz.view(b, h, w, cp).float()[..., c:].abs().max()) == 0.0
+  assert rel(db, want.sum((0, 2, 3))) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ composed heads
+@pytest.fixture(scope='module')
+def trainer(oracle_state):
+  if not torch.cuda.is_available():
+    pytest.skip('no CUDA device')
+  from carla_garage_b200.config import GlobalConfig
+  from carla_garage_b200.nn import LidarCenterNet
+  from carla_garage_b200.training import Trainer
+  m = LidarCenterNet(GlobalConfig())
+  m.load_state_dict(oracle_state, strict=True)
+  return Trainer(m.cuda().train())
+
+
+def _to_dev(ops, t):
+  return ops.nchw_to_nhwc(t.detach().float().cuda().contiguous())
+
+
+def test_center_head_forward_backward(ops, trainer):
+  """LidarCenterNetHead (center_net.py:49-75) as one N=320 3x3 GEMM + block-diagonal 1x1 GEMM, and its backward, vs the
+  five nn.Sequential heads run by torch (fp32) on the same bf16-rounded input."""
+  from carla_garage_b200.training import Backward
+  net, eng, st = trainer.model, trainer.eng, trainer.st
+  head = net.head
+  feat = bf(rnd(2, 64, 64, 64, seed=43)).float().requires_grad_(True)
+  names = head.head_names()
+  ref = torch.cat([getattr(head, n)(feat) for n in names], 1)
+  ref_out = ref.clone()
+  ref_out = torch.cat([torch.sigmoid(ref[:, :4]), ref[:, 4:]], 1)
+  st.zero_grad()
+  eng.tape = []
+  try:
+    xd = _to_dev(ops, feat)
+    bb = eng.center_head_forward(xd)
+    maps = bb[0]._base  # pylint: disable=protected-access
+    assert rel(maps, ref_out) < 1e-2
+    dz = bf(rnd(2, 64, 64, 24, seed=44, scale=0.1))
+    dz[..., 21:] = 0
+    tape = eng.tape
+  finally:
+    eng.tape = None
+  for p in head.parameters():
+    p.grad = None
+  ref.backward(dz.float()[..., :21].permute(0, 3, 1, 2))
+  want = {n: p.grad.clone() for n, p in head.named_parameters()}
+  want_dx = feat.grad.clone()
+  for n, p in head.named_parameters():  # torch replaced .grad: point it back at the flat buffer view
+    p.grad = st.g(p)
+  st.zero_grad()
+  # the loss kernel normally accumulates the 1x1 bias gradients; do it here
+  st.g_span(getattr(head, names[0])[2].bias, getattr(head, names[-1])[2].bias).add_(dz.float().sum((0, 1, 2))[:21])
+  bw = Backward(eng, st)
+  bw.run(tape, {'center': dz})
+  torch.cuda.synchronize()
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), want_dx) < 1e-2
+  for n, p in head.named_parameters():
+    assert rel(st.g(p), want[n]) < 1e-2, n
+
+
+def test_fpn_top_down_and_bev_decoder(ops, trainer):
+  """top_down (transfuser.py:131-137) + bev_semantic_decoder (model.py:75-90,383-385) forward and backward vs torch."""
+  from carla_garage_b200.training import Backward
+  net, eng, st = trainer.model, trainer.eng, trainer.st
+  bb = net.backbone
+  x = bf(rnd(2, 1512, 8, 8, seed=45)).float().requires_grad_(True)
+  p5 = F.relu(bb.c5_conv(x))
+  p4 = F.relu(bb.up_conv5(F.interpolate(p5, scale_factor=2, mode='bilinear', align_corners=False)))
+  p3 = F.relu(bb.up_conv4(F.interpolate(p4, size=(64, 64), mode='bilinear', align_corners=False)))
+  dec = net.bev_semantic_decoder
+  t = dec[2](F.relu(dec[0](p3)))
+  ref = F.interpolate(t, size=(256, 256), mode='bilinear', align_corners=False) * net.valid_bev_pixels
+  mods = [bb.c5_conv, bb.up_conv5, bb.up_conv4, dec[0], dec[2]]
+  st.zero_grad()
+  eng.tape = []
+  try:
+    xd = _to_dev(ops, x)
+    cfg = eng.cfg
+    b = 2
+    q5 = eng.conv_bias(xd, bb.c5_conv, ops.ACT_RELU)
+    q5u = ops.bilinear(q5, b, 8, 8, 16, 16, q5.shape[3])
+    eng._save(op='bilinear', src=q5, out=q5u)  # pylint: disable=protected-access
+    q4 = eng.conv_bias(q5u, bb.up_conv5, ops.ACT_RELU)
+    q4u = ops.bilinear(q4, b, 16, 16, 64, 64, q4.shape[3])
+    eng._save(op='bilinear', src=q4, out=q4u)  # pylint: disable=protected-access
+    feats = eng.conv_bias(q4u, bb.up_conv4, ops.ACT_RELU)
+    y = eng.conv_bias(feats, dec[0], ops.ACT_RELU)
+    y = eng.conv_bias(y, dec[2])
+    from carla_garage_b200.engine import packed
+    out = ops.bilinear_nchw_mask(y, 11, cfg.lidar_resolution_height, cfg.lidar_resolution_width,
+                                 packed(net.valid_bev_pixels, 'f32'))
+    eng._save(op='bev_tail', src=y, out=out, ncls=11)  # pylint: disable=protected-access
+    tape = eng.tape
+  finally:
+    eng.tape = None
+  assert rel(ops.nhwc_to_nchw(feats), p3) < 1e-2
+  assert rel(out, ref) < 1.5e-2
+  dout = rnd(2, 11, 256, 256, seed=46, scale=1e-3)
+  for mod in mods:
+    for p in mod.parameters():
+      p.grad = None
+  ref.backward(dout)
+  want = {id(p): p.grad.clone() for mod in mods for p in mod.parameters()}
+  want_dx = x.grad.clone()
+  for mod in mods:
+    for p in mod.parameters():
+      p.grad = st.g(p)
+  st.zero_grad()
+  bw = Backward(eng, st)
+  bw.run(tape, {'bev': dout})
+  torch.cuda.synchronize()
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), want_dx) < 2e-2
+  for mod in mods:
+    for p in mod.parameters():
+      assert rel(st.g(p), want[id(p)]) < 2e-2, tuple(p.shape)
+
+
+@pytest.mark.parametrize('which', ['semantic', 'depth'])
+def test_perspective_decoder_forward_backward(ops, trainer, which):
+  """t_u.PerspectiveDecoder (transfuser_utils.py:668-704) forward + backward on a reduced grid vs torch."""
+  from carla_garage_b200.training import Backward
+  net, eng, st = trainer.model, trainer.eng, trainer.st
+  dec = net.semantic_decoder if which == 'semantic' else net.depth_decoder
+  x = bf(rnd(1, 1512, 4, 16, seed=47)).float().requires_grad_(True)
+  t = dec.deconv1(x)
+  t = F.interpolate(t, scale_factor=dec.scale_factor_0, mode='bilinear', align_corners=False)
+  t = dec.deconv2(t)
+  t = F.interpolate(t, scale_factor=dec.scale_factor_1, mode='bilinear', align_corners=False)
+  z = dec.deconv3(t)
+  ref = torch.sigmoid(z) if which == 'depth' else z
+  st.zero_grad()
+  eng.tape = []
+  try:
+    xd = _to_dev(ops, x)
+    out = eng.perspective_decoder(dec, xd, ops.ACT_SIGMOID if which == 'depth' else ops.ACT_NONE)
+    tape = eng.tape
+  finally:
+    eng.tape = None
+  assert rel(out, ref) < 1.5e-2
+  c = z.shape[1]
+  dzs = bf(rnd(1, z.shape[2], z.shape[3], 16, seed=48, scale=1e-2))
+  dzs[..., c:] = 0
+  for p in dec.parameters():
+    p.grad = None
+  z.backward(dzs.float()[..., :c].permute(0, 3, 1, 2))
+  want = {n: p.grad.clone() for n, p in dec.named_parameters()}
+  want_dx = x.grad.clone()
+  for p in dec.parameters():
+    p.grad = st.g(p)
+  st.zero_grad()
+  st.g(dec.deconv3[2].bias).add_(dzs.float().sum((0, 1, 2))[:c])  # normally accumulated by the loss kernel
+  bw = Backward(eng, st)
+  bw.run(tape, {which: dzs})
+  torch.cuda.synchronize()
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), want_dx) < 2e-2
+  for n, p in dec.named_parameters():
+    assert rel(st.g(p), want[n]) < 2e-2, n
+
+
+def test_planner_forward_backward(ops, trainer, oracle_state):
+  """model.py:299-358: memory tokens + 6-layer post-norm decoder + GRU / target-speed heads, forward and backward, vs
+  the oracle's fp32 restatement under torch autograd."""
+  from carla_garage_b200.training import Backward
+  from oracle import tfpp_oracle as orc
+  net, eng, st = trainer.model, trainer.eng, trainer.st
+  net.load_state_dict(oracle_state, strict=True)
+  sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v)
+        for k, v in oracle_state.items()}
+  b = 4
+  g = torch.Generator().manual_seed(49)
+  fused = bf(torch.randn(b, 1512, 8, 8, generator=g)).float().requires_grad_(True)
+  tp = torch.randn(b, 2, generator=g) * 10
+  vel = torch.rand(b, 1, generator=g) * 8
+  cmd = F.one_hot(torch.randint(0, 6, (b,), generator=g), 6).float()
+  want_cp, want_ts = orc.planner(sd, fused, tp, vel, cmd, training=True)
+  dcp, dts = torch.randn(want_cp.shape, generator=g), torch.randn(want_ts.shape, generator=g)
+  (want_cp * dcp).sum().add((want_ts * dts).sum()).backward()
+  st.zero_grad()
+  eng.tape = []
+  eng.new_arena(torch.device('cuda'))
+  try:
+    xd = _to_dev(ops, fused)
+    cp, ts = eng.planner(xd, tp.cuda(), vel.cuda(), cmd.cuda(), True)
+    tape = eng.tape
+  finally:
+    eng.tape = None
+  assert rel(cp, want_cp) < 1e-2 and rel(ts, want_ts) < 1e-2
+  bw = Backward(eng, st)
+  bw.run(tape, {'planner': (dcp.cuda(), dts.cuda())})
+  torch.cuda.synchronize()
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), fused.grad) < 3e-2
+  params = dict(net.named_parameters())
+  names = [n for n in sd if n.startswith(('join.', 'change_channel', 'checkpoint_', 'target_speed_network',
+                                          'extra_sensor_')) and sd[n].is_floating_point() and sd[n].grad is not None]
+  assert len(names) > 100
+  worst = 0.0
+  for n in names:
+    e = rel(params[n].grad, sd[n].grad)
+    worst = max(worst, e)
+    assert e < 5e-2, (n, e)
+  print(f'  planner backward: {len(names)} parameter gradients, worst rel err {worst:.2e}')
+  net.load_state_dict(oracle_state, strict=True)
+
+
+def test_downsample_stride2_block_backward(ops, trainer, oracle_state):
+  """First block of a RegNet stage (1x1 stride-2 shortcut conv + BN, stride-2 group conv): the `downsample` dgrad path."""
+  from carla_garage_b200.training import Backward
+  from oracle import tfpp_oracle as orc
+  net, eng, st = trainer.model, trainer.eng, trainer.st
+  net.load_state_dict(oracle_state, strict=True)
+  net.train()
+  sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v)
+        for k, v in oracle_state.items()}
+  g = torch.Generator().manual_seed(50)
+  x = (torch.randn(2, 216, 16, 32, generator=g).relu() + 0.1 * torch.randn(2, 216, 16, 32, generator=g))
+  x = bf(x).float().requires_grad_(True)
+  prefix = 'backbone.lidar_encoder.s3.b1'
+  want = orc.regnet_block(sd, prefix, x, True, stride=2)
+  dy = bf(torch.randn(want.shape, generator=g)).float()
+  want.backward(dy)
+  blk = net.backbone.lidar_encoder['s3'][0]
+  st.zero_grad()
+  eng.tape = []
+  eng.new_arena(torch.device('cuda'))
+  try:
+    xd = _to_dev(ops, x)
+    y = eng.regnet_block(xd, blk, True)
+    tape = eng.tape
+  finally:
+    eng.tape = None
+  assert rel(ops.nhwc_to_nchw(y), want) < 1e-2
+  bw = Backward(eng, st)
+  bw.G[id(y)] = _to_dev(ops, dy)
+  bw.run(tape, {})
+  torch.cuda.synchronize()
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), x.grad) < 0.15
+  params = dict(net.named_parameters())
+  for n in (prefix + '.downsample.conv.weight', prefix + '.downsample.bn.weight', prefix + '.downsample.bn.bias',
+            prefix + '.conv2.conv.weight', prefix + '.conv3.conv.weight', prefix + '.conv1.conv.weight'):
+    assert rel(params[n].grad, sd[n].grad) < 0.15, n
+  net.load_state_dict(oracle_state, strict=True)
