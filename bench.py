@@ -348,7 +348,7 @@ def main():
                  'global_batch': world * b, 'per_gpu_batch': b, 'parallelism': f'dp{world}',
                  'l2': 'per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed',
                  'inputs': 'rgb (B,3,256,1024) f32 + 60k-point LiDAR cloud -> (B,1,256,256) BEV (reference default use_ground_plane=0)',
-                 'dropout': 'off (see DESIGN.md)', 'cuda_graph': bool(use_graph), 'graphs': (1 if world == 1 and os.environ.get('TFPP_SPLIT_GRAPH', '0') != '1' else 2) if use_graph else 0, 'model_tflop_per_step': world * b * FLOP_PER_SAMPLE_TRAIN / 1e12},
+                 'dropout': ('on: embd/attn/resid_pdrop 0.1 + decoder 0.1, Philox4x32-10 masks regenerated in the backward kernels' if net.engine.dropout_enabled else 'off (TFPP_DROPOUT=0)'), 'cuda_graph': bool(use_graph), 'graphs': (1 if world == 1 and os.environ.get('TFPP_SPLIT_GRAPH', '0') != '1' else 2) if use_graph else 0, 'model_tflop_per_step': world * b * FLOP_PER_SAMPLE_TRAIN / 1e12},
       'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 40,
               'ms_per_step': ms_e2e / args.steps},
       'gpu_launches': launches,

@@ -27,6 +27,7 @@ class ConvGemmArgs(ctypes.Structure):
       ('r2_sb', c_ll), ('r2_sy', c_ll), ('r2_sx', c_ll), ('r2_sn', c_ll),
       ('scale', c_void_p), ('shift', c_void_p), ('act', c_int), ('act_n_limit', c_int),
       ('stat_sum', c_void_p), ('stat_sq', c_void_p),
+      ('drop_rng', c_void_p), ('drop_p', c_float), ('drop_site', ctypes.c_uint),
   ]
 
 
@@ -95,6 +96,13 @@ _PROTOS = {
     'tfpp_l1_sigmoid_loss': [P, P, F, P, P, P, P, I, L, P],
     'tfpp_center_head_loss': [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P],
     'tfpp_planner_loss': [P, P, P, P, P, F, F, P, P, P, P, I, I, I, P],
+    'tfpp_dropout': [P, I, L, P, F, I, P],
+    'tfpp_act_bwd_dropout': [P, P, I, I, I, F, P, P, I, I, I, I, P, F, I, P],
+    'tfpp_fusion_attn_dropout': [P, P, I, I, I, I, P, F, I, P],
+    'tfpp_fusion_attn_bwd_dropout': [P, P, P, P, I, I, I, I, P, F, I, P],
+    'tfpp_small_mha_dropout': [P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, P, F, I, P],
+    'tfpp_small_mha_bwd_dropout': [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, I, P, F, I,
+                                   P],
     'tfpp_adamw_amsgrad': [P, P, P, P, P, L, F, F, F, F, F, I, F, P, P, P],
 }
 

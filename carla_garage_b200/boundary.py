@@ -161,8 +161,9 @@ class _Step(torch.autograd.Function):
     st.zero_grad()
     eng.new_arena(st.flat.device)
     seeds = bnd.seeds_from(ctx.outs, gouts)
+    # the tape is read-only for Backward: it stays on ctx (freed with the autograd graph) so that
+    # loss.backward(retain_graph=True) followed by a second backward works like it does for torch modules
     bnd.with_plan(lambda: training.Backward(eng, st).run(ctx.tape, seeds))
-    ctx.tape = None
     grads = tuple(st.g(p) for p in st.params if p.requires_grad)
     return (None,) * 6 + grads
 

@@ -430,8 +430,10 @@ __global__ void __launch_bounds__(256) se_param_grad_kernel(const float* __restr
 __global__ void __launch_bounds__(256) act_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ y,
                                                       int nchw_f32, int act, int act_n_limit, float dy_scale,
                                                       bf16* __restrict__ dz, float* __restrict__ dbias, long long npix,
-                                                      int HW, int C, int Cp) {
+                                                      int HW, int C, int Cp, const unsigned long long* drop_rng,
+                                                      float drop_p, unsigned drop_site) {
   extern __shared__ float sm[];  // Cp
+  const DropCtx drop = drop_ctx(drop_rng, drop_p, drop_site);
   for (int i = threadIdx.x; i < Cp; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   const long long total = npix * Cp;
@@ -455,6 +457,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const void* __restrict__ d
         yy = y ? bf2f(static_cast<const bf16*>(y)[pix * C + c]) : 0.f;
       }
       d *= dy_scale;
+      if (drop.on) d *= drop_mult(drop, static_cast<unsigned long long>(pix) * C + c);
       const int a = (act_n_limit == 0 || c < act_n_limit) ? act : ACT_NONE;
       if (a == ACT_RELU) d = yy > 0.f ? d : 0.f;
       else if (a == ACT_SIGMOID) d = d * yy * (1.f - yy);
@@ -476,8 +479,11 @@ template <bool DY_F32>
 __global__ void __launch_bounds__(256) act_bwd_vec_kernel(const void* __restrict__ dy, const bf16* __restrict__ y, int act,
                                                           int act_n_limit, float dy_scale, bf16* __restrict__ dz,
                                                           float* __restrict__ dbias, long long npix, int C,
-                                                          int slab_groups, long long pix_per_block) {
+                                                          int slab_groups, long long pix_per_block,
+                                                          const unsigned long long* drop_rng, float drop_p,
+                                                          unsigned drop_site) {
   __shared__ float sm[2048];
+  const DropCtx drop = drop_ctx(drop_rng, drop_p, drop_site);
   const int c8n = C / 8;
   const int g0 = blockIdx.y * slab_groups;
   const int ng = min(slab_groups, c8n - g0);
@@ -522,9 +528,11 @@ __global__ void __launch_bounds__(256) act_bwd_vec_kernel(const void* __restrict
           unpack8(ud[k][0], d);
         }
         if (y) unpack8(uy[k], yy);
+        float dm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (drop.on) drop_mult8(drop, static_cast<unsigned long long>(px) * C + c0, dm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float v = d[j] * dy_scale;
+          float v = d[j] * dy_scale * dm[j];
           const int a = (act_n_limit == 0 || c0 + j < act_n_limit) ? act : ACT_NONE;
           if (a == ACT_RELU) v = yy[j] > 0.f ? v : 0.f;
           else if (a == ACT_SIGMOID) v = v * yy[j] * (1.f - yy[j]);
@@ -898,10 +906,57 @@ extern "C" int tfpp_se_bwd(const void* dout, const void* a2, const float* gate, 
   return TFPP_OK;
 }
 
+// In-place dropout over a flat tensor (GPT.drop on the token matrix, transfuser.py:325, and its adjoint).
+namespace {
+__global__ void __launch_bounds__(256) dropout_inplace_kernel(void* __restrict__ x, int f32, long long n8,
+                                                              const unsigned long long* rng, float p, unsigned site) {
+  const DropCtx drop = drop_ctx(rng, p, site);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8 || !drop.on) return;
+  float dm[8];
+  drop_mult8(drop, static_cast<unsigned long long>(i) * 8, dm);
+  if (f32) {
+    float4* q = reinterpret_cast<float4*>(x) + 2 * i;
+    float4 a = q[0], b = q[1];
+    a.x *= dm[0]; a.y *= dm[1]; a.z *= dm[2]; a.w *= dm[3];
+    b.x *= dm[4]; b.y *= dm[5]; b.z *= dm[6]; b.w *= dm[7];
+    q[0] = a;
+    q[1] = b;
+  } else {
+    float v[8];
+    load8(static_cast<const bf16*>(x) + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= dm[j];
+    store8(static_cast<bf16*>(x) + i * 8, v);
+  }
+}
+}  // namespace
+
+extern "C" int tfpp_dropout(void* x, int x_f32, long long n, const unsigned long long* rng, float p, unsigned site,
+                            tfpp_stream_t stream_) {
+  STREAM;
+  TFPP_CHECK_ARG(n % 8 == 0, "element count must be a multiple of 8");
+  TFPP_CHECK_ARG(p >= 0.f && p < 1.f, "dropout probability must be in [0, 1)");
+  if (rng == nullptr || p == 0.f || n == 0) return TFPP_OK;
+  dropout_inplace_kernel<<<static_cast<unsigned>(ceil_div_ll(n / 8, 256)), 256, 0, stream>>>(x, x_f32, n / 8, rng, p, site);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
 extern "C" int tfpp_act_bwd(const void* dy, const void* y, int nchw_f32, int act, int act_n_limit, float dy_scale,
                             void* dz, float* dbias, int batch, int hw, int channels, int channels_padded,
                             tfpp_stream_t stream_) {
+  return tfpp_act_bwd_dropout(dy, y, nchw_f32, act, act_n_limit, dy_scale, dz, dbias, batch, hw, channels,
+                              channels_padded, nullptr, 0.f, 0u, stream_);
+}
+
+extern "C" int tfpp_act_bwd_dropout(const void* dy, const void* y, int nchw_f32, int act, int act_n_limit,
+                                    float dy_scale, void* dz, float* dbias, int batch, int hw, int channels,
+                                    int channels_padded, const unsigned long long* drop_rng, float drop_p,
+                                    unsigned drop_site, tfpp_stream_t stream_) {
   STREAM;
+  TFPP_CHECK_ARG(drop_rng == nullptr || drop_p == 0.f || nchw_f32 != 1, "dropout adjoint: NHWC layouts only");
+  if (drop_p <= 0.f) drop_rng = nullptr;
   const long long npix = static_cast<long long>(batch) * hw;
   if (nchw_f32 != 1 && channels % 8 == 0 && channels_padded == channels) {
     const int c8n = channels / 8;
@@ -915,11 +970,12 @@ extern "C" int tfpp_act_bwd(const void* dy, const void* y, int nchw_f32, int act
     dim3 grid(static_cast<unsigned>(chunks), nslabs);
     if (nchw_f32 == 2)
       act_bwd_vec_kernel<true><<<grid, 256, 0, stream>>>(dy, static_cast<const bf16*>(y), act, act_n_limit, dy_scale,
-                                                         static_cast<bf16*>(dz), dbias, npix, channels, slab_groups, ppb);
+                                                         static_cast<bf16*>(dz), dbias, npix, channels, slab_groups, ppb,
+                                                         drop_rng, drop_p, drop_site);
     else
       act_bwd_vec_kernel<false><<<grid, 256, 0, stream>>>(dy, static_cast<const bf16*>(y), act, act_n_limit, dy_scale,
                                                           static_cast<bf16*>(dz), dbias, npix, channels, slab_groups,
-                                                          ppb);
+                                                          ppb, drop_rng, drop_p, drop_site);
     TFPP_CHECK_LAUNCH();
     return TFPP_OK;
   }
@@ -927,7 +983,8 @@ extern "C" int tfpp_act_bwd(const void* dy, const void* y, int nchw_f32, int act
   if (blocks > TFPP_NUM_SMS * 8) blocks = TFPP_NUM_SMS * 8;
   if (blocks < 1) blocks = 1;
   act_bwd_kernel<<<static_cast<int>(blocks), 256, sizeof(float) * channels_padded, stream>>>(
-      dy, y, nchw_f32, act, act_n_limit, dy_scale, static_cast<bf16*>(dz), dbias, npix, hw, channels, channels_padded);
+      dy, y, nchw_f32, act, act_n_limit, dy_scale, static_cast<bf16*>(dz), dbias, npix, hw, channels, channels_padded,
+      drop_rng, drop_p, drop_site);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

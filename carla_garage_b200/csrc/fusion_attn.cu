@@ -57,8 +57,19 @@ __device__ __forceinline__ void stage_chunk(uint32_t tile, const bf16* src, long
   }
 }
 
+// keep flags (bit 0 / bit 1) of the probability pair (row q, keys col, col + 1) of head (b, h); col is even
+__device__ __forceinline__ uint32_t drop_pair(const DropCtx& d, int b, int heads, int h, int T, int q, int col) {
+  const unsigned long long idx = ((static_cast<unsigned long long>(b) * heads + h) * T + q) * T + col;
+  const uint4 w = drop_words(d, idx >> 2);
+  const uint32_t w0 = (idx & 2) ? w.z : w.x, w1 = (idx & 2) ? w.w : w.y;
+  return (w0 >= d.thresh ? 1u : 0u) | (w1 >= d.thresh ? 2u : 0u);
+}
+
+template <bool DROP>
 __global__ void __launch_bounds__(256, 2) fusion_attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                                 int T, int C, int heads, float scale) {
+                                                                 int T, int C, int heads, float scale,
+                                                                 const unsigned long long* drop_rng, float drop_p,
+                                                                 unsigned drop_site) {
   extern __shared__ __align__(128) uint8_t att_smem[];
   bf16* P = reinterpret_cast<bf16*>(att_smem);                 // [64][kPitchP]
   bf16* stage0 = P + kQ * kPitchP;                             // [2][kStageElems]
@@ -170,8 +181,18 @@ __global__ void __launch_bounds__(256, 2) fusion_attn_fwd_kernel(const bf16* __r
         for (int nt = 0; nt < kNt; ++nt) {
           if (nt < 2 * npairs) {
             const int col = kh * keys_half + nt * 8 + 2 * t4;
-            *reinterpret_cast<uint32_t*>(P + r0 * kPitchP + col) = pack_bf16x2(acc[nt][0] * i0, acc[nt][1] * i0);
-            *reinterpret_cast<uint32_t*>(P + (r0 + 8) * kPitchP + col) = pack_bf16x2(acc[nt][2] * i1, acc[nt][3] * i1);
+            float p00 = acc[nt][0] * i0, p01 = acc[nt][1] * i0, p10 = acc[nt][2] * i1, p11 = acc[nt][3] * i1;
+            if (DROP) {  // attn_drop (transfuser.py:374): dropped probabilities leave the P V product; 1/(1-p) is applied to O
+              const DropCtx drop = drop_ctx(drop_rng, drop_p, drop_site);   // built here: no registers held over the main loop
+              const uint32_t k0 = drop_pair(drop, b, heads, h, T, q0 + r0, col);
+              const uint32_t k1 = drop_pair(drop, b, heads, h, T, q0 + r0 + 8, col);
+              p00 = (k0 & 1u) ? p00 : 0.f;
+              p01 = (k0 & 2u) ? p01 : 0.f;
+              p10 = (k1 & 1u) ? p10 : 0.f;
+              p11 = (k1 & 2u) ? p11 : 0.f;
+            }
+            *reinterpret_cast<uint32_t*>(P + r0 * kPitchP + col) = pack_bf16x2(p00, p01);
+            *reinterpret_cast<uint32_t*>(P + (r0 + 8) * kPitchP + col) = pack_bf16x2(p10, p11);
           }
         }
       }
@@ -196,8 +217,9 @@ __global__ void __launch_bounds__(256, 2) fusion_attn_fwd_kernel(const bf16* __r
         if (col < hd) {  // hd is even: col + 1 < hd as well
           const int qr = q0 + r0;
           bf16* op = out + (static_cast<long long>(b) * T + qr) * C + h * hd + col;
-          if (qr < T) *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(o[nt][0], o[nt][1]);
-          if (qr + 8 < T) *reinterpret_cast<uint32_t*>(op + 8ll * C) = pack_bf16x2(o[nt][2], o[nt][3]);
+          const float ik = DROP ? 1.f / (1.f - drop_p) : 1.f;
+          if (qr < T) *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(o[nt][0] * ik, o[nt][1] * ik);
+          if (qr + 8 < T) *reinterpret_cast<uint32_t*>(op + 8ll * C) = pack_bf16x2(o[nt][2] * ik, o[nt][3] * ik);
         }
       }
     }
@@ -220,9 +242,16 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(256, 2) fusion_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                  bf16* __restrict__ dqkv, float* __restrict__ dkv, int T,
-                                                                 int C, int heads, float scale) {
+                                                                 int C, int heads, float scale,
+                                                                 const unsigned long long* drop_rng, float drop_p,
+                                                                 unsigned drop_site) {
+  // Dropout on the probabilities: P is parked with the SIGN BIT as the "dropped" flag (P >= 0), so that both the
+  // undropped softmax (needed for dS) and the mask survive in the one shared-memory tile:
+  //   dV += (P o M)^T dO / (1-p);  dP' = (dO V^T) o M / (1-p);  dS = P o (dP' - rowsum(dP' o P)) * scale.
+  const float inv_keep = DROP ? 1.f / (1.f - drop_p) : 1.f;
   extern __shared__ __align__(128) uint8_t att_smem[];
   bf16* P = reinterpret_cast<bf16*>(att_smem);                 // [64][kPitchP]: P, later dS
   bf16* stage0 = P + kQ * kPitchP;                             // [2][kStageElems]: big tile [320][40] + small tile [64][40]
@@ -319,7 +348,7 @@ __global__ void __launch_bounds__(256, 2) fusion_attn_bwd_kernel(const bf16* __r
   };
   // dst[T x chunk] += (P or dS)^T small_chunk: M = keys (16-key blocks round-robin over the warps), N = the chunk's 32
   // columns, contraction over the 64 queries.  Both operands come out of row-major tiles through ldmatrix.trans.
-  auto accum_keys = [&](uint32_t big, float* dst, int d0) {
+  auto accum_keys = [&](uint32_t big, float* dst, int d0, bool masked, float out_scale) {
     const uint32_t small = big + kT * kPitchC * 2;
     uint32_t bfr[4][2][4];   // [k step][column half]: B fragments of the small tile, reused by every key block
 #pragma unroll
@@ -335,6 +364,10 @@ __global__ void __launch_bounds__(256, 2) fusion_attn_bwd_kernel(const bf16* __r
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t a[4];   // A = (P or dS)^T: m = key, k = query; stored [query][key]
         ldsm_x4_t(a, p_u + ((ks * 16 + (mat >> 1) * 8 + (lane & 7)) * kPitchP + kb * 16 + (mat & 1) * 8) * 2);
+        if (masked) {  // negative halves are dropped probabilities: they do not take part in P^T dO
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a[e] &= ~(((a[e] >> 15) & 0x00010001u) * 0xffffu);
+        }
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           mma16816(o[2 * ch], a, bfr[ks][ch][0], bfr[ks][ch][1]);
@@ -346,8 +379,8 @@ __global__ void __launch_bounds__(256, 2) fusion_attn_bwd_kernel(const bf16* __r
         const int col = nt * 8 + 2 * t4;
         if (d0 + col < hd) {
           float* op = dst + static_cast<long long>(kb * 16 + g) * (2ll * C) + col;
-          red_add_v2(op, o[nt][0], o[nt][1]);
-          red_add_v2(op + 8 * 2ll * C, o[nt][2], o[nt][3]);
+          red_add_v2(op, o[nt][0] * out_scale, o[nt][1] * out_scale);
+          red_add_v2(op + 8 * 2ll * C, o[nt][2] * out_scale, o[nt][3] * out_scale);
         }
       }
     }
@@ -396,15 +429,25 @@ __global__ void __launch_bounds__(256, 2) fusion_attn_bwd_kernel(const bf16* __r
     for (int nt = 0; nt < kNt; ++nt) {
       if (nt < 2 * npairs) {
         const int col = kh * keys_half + nt * 8 + 2 * t4;
-        *reinterpret_cast<uint32_t*>(P + r0 * kPitchP + col) = pack_bf16x2(acc[nt][0] * i0, acc[nt][1] * i0);
-        *reinterpret_cast<uint32_t*>(P + (r0 + 8) * kPitchP + col) = pack_bf16x2(acc[nt][2] * i1, acc[nt][3] * i1);
+        float p00 = acc[nt][0] * i0, p01 = acc[nt][1] * i0, p10 = acc[nt][2] * i1, p11 = acc[nt][3] * i1;
+        if (DROP) {
+          const DropCtx drop = drop_ctx(drop_rng, drop_p, drop_site);
+          const uint32_t k0 = drop_pair(drop, b, heads, h, T, q0 + r0, col);
+          const uint32_t k1 = drop_pair(drop, b, heads, h, T, q0 + r0 + 8, col);
+          p00 = (k0 & 1u) ? p00 : -p00;
+          p01 = (k0 & 2u) ? p01 : -p01;
+          p10 = (k1 & 1u) ? p10 : -p10;
+          p11 = (k1 & 2u) ? p11 : -p11;
+        }
+        *reinterpret_cast<uint32_t*>(P + r0 * kPitchP + col) = pack_bf16x2(p00, p01);
+        *reinterpret_cast<uint32_t*>(P + (r0 + 8) * kPitchP + col) = pack_bf16x2(p10, p11);
       }
     }
   }
   // ---- phase V: dV[:, chunk] += P^T dO_chunk   (begin_stage's barrier publishes P)
   for (int c = 0; c < nc; ++c) {
     const uint32_t big = begin_stage(nc + c);
-    accum_keys(big, dv_dst + c * kDC, c * kDC);
+    accum_keys(big, dv_dst + c * kDC, c * kDC, DROP, inv_keep);
     __syncthreads();
   }
   // ---- phase B: dP = dO V^T -> dS overwrites P
@@ -416,14 +459,22 @@ __global__ void __launch_bounds__(256, 2) fusion_attn_bwd_kernel(const bf16* __r
     __syncthreads();
   }
   {
-    // dS = P * (dP - rowsum(dP * P)) * scale, in place over P (a thread touches only its own fragment slots)
+    // dS = P * (dP' - rowsum(dP' * P)) * scale, in place over P (a thread touches only its own fragment slots);
+    // dP' = dP masked and scaled by the probability dropout (sign bit of the parked P = dropped)
     float part0 = 0.f, part1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < kNt; ++nt) {
       if (nt < 2 * npairs) {
         const int col = kh * keys_half + nt * 8 + 2 * t4;
-        const float2 pa = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(P + r0 * kPitchP + col));
-        const float2 pb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(P + (r0 + 8) * kPitchP + col));
+        const uint32_t ra = *reinterpret_cast<const uint32_t*>(P + r0 * kPitchP + col);
+        const uint32_t rb2 = *reinterpret_cast<const uint32_t*>(P + (r0 + 8) * kPitchP + col);
+        const float2 pa = unpack_bf16x2(ra & 0x7fff7fffu), pb = unpack_bf16x2(rb2 & 0x7fff7fffu);
+        if (DROP) {
+          acc[nt][0] = (ra & 0x00008000u) ? 0.f : acc[nt][0] * inv_keep;
+          acc[nt][1] = (ra & 0x80000000u) ? 0.f : acc[nt][1] * inv_keep;
+          acc[nt][2] = (rb2 & 0x00008000u) ? 0.f : acc[nt][2] * inv_keep;
+          acc[nt][3] = (rb2 & 0x80000000u) ? 0.f : acc[nt][3] * inv_keep;
+        }
         part0 += acc[nt][0] * pa.x + acc[nt][1] * pa.y;
         part1 += acc[nt][2] * pb.x + acc[nt][3] * pb.y;
       }
@@ -434,8 +485,8 @@ __global__ void __launch_bounds__(256, 2) fusion_attn_bwd_kernel(const bf16* __r
     for (int nt = 0; nt < kNt; ++nt) {
       if (nt < 2 * npairs) {
         const int col = kh * keys_half + nt * 8 + 2 * t4;
-        const float2 pa = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(P + r0 * kPitchP + col));
-        const float2 pb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(P + (r0 + 8) * kPitchP + col));
+        const float2 pa = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(P + r0 * kPitchP + col) & 0x7fff7fffu);
+        const float2 pb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(P + (r0 + 8) * kPitchP + col) & 0x7fff7fffu);
         *reinterpret_cast<uint32_t*>(P + r0 * kPitchP + col) =
             pack_bf16x2(pa.x * (acc[nt][0] - rs0) * scale, pa.y * (acc[nt][1] - rs0) * scale);
         *reinterpret_cast<uint32_t*>(P + (r0 + 8) * kPitchP + col) =
@@ -470,7 +521,7 @@ __global__ void __launch_bounds__(256, 2) fusion_attn_bwd_kernel(const bf16* __r
         }
       }
     }
-    accum_keys(big, dk_dst + d0, d0);
+    accum_keys(big, dk_dst + d0, d0, false, 1.f);
     __syncthreads();
   }
 }
@@ -493,14 +544,23 @@ __global__ void __launch_bounds__(256) dkv_cast_kernel(const float* __restrict__
 
 extern "C" int tfpp_fusion_attn(const void* qkv, void* out, int batch, int tokens, int channels, int heads,
                                 tfpp_stream_t stream_) {
+  return tfpp_fusion_attn_dropout(qkv, out, batch, tokens, channels, heads, nullptr, 0.f, 0u, stream_);
+}
+
+extern "C" int tfpp_fusion_attn_dropout(const void* qkv, void* out, int batch, int tokens, int channels, int heads,
+                                        const unsigned long long* drop_rng, float drop_p, unsigned drop_site,
+                                        tfpp_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TFPP_CHECK_ARG(tokens <= kT && tokens % 32 == 0, "tokens must be a multiple of 32 and <= 320");
   TFPP_CHECK_ARG(channels % heads == 0 && (channels / heads) % 2 == 0, "even head dim required");
   const size_t smem = sizeof(bf16) * (kQ * kPitchP + 2 * kStageElems) + sizeof(float) * 2 * kQ;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fusion_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fusion_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fusion_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
     if (e != cudaSuccess) {
       tfpp_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return TFPP_ERR_CUDA;
@@ -509,14 +569,27 @@ extern "C" int tfpp_fusion_attn(const void* qkv, void* out, int batch, int token
   }
   const int hd = channels / heads;
   dim3 grid(ceil_div(tokens, kQ), heads, batch);
-  fusion_attn_fwd_kernel<<<grid, 256, smem, stream>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), tokens,
-                                                      channels, heads, 1.0f / sqrtf(static_cast<float>(hd)));
+  if (drop_rng != nullptr && drop_p > 0.f)
+    fusion_attn_fwd_kernel<true><<<grid, 256, smem, stream>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out),
+                                                              tokens, channels, heads,
+                                                              1.0f / sqrtf(static_cast<float>(hd)), drop_rng, drop_p,
+                                                              drop_site);
+  else
+    fusion_attn_fwd_kernel<false><<<grid, 256, smem, stream>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out),
+                                                               tokens, channels, heads,
+                                                               1.0f / sqrtf(static_cast<float>(hd)), nullptr, 0.f, 0u);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }
 
 extern "C" int tfpp_fusion_attn_bwd(const void* qkv, const void* dout, void* dqkv, float* dkv_ws, int batch, int tokens,
                                     int channels, int heads, tfpp_stream_t stream_) {
+  return tfpp_fusion_attn_bwd_dropout(qkv, dout, dqkv, dkv_ws, batch, tokens, channels, heads, nullptr, 0.f, 0u, stream_);
+}
+
+extern "C" int tfpp_fusion_attn_bwd_dropout(const void* qkv, const void* dout, void* dqkv, float* dkv_ws, int batch,
+                                            int tokens, int channels, int heads, const unsigned long long* drop_rng,
+                                            float drop_p, unsigned drop_site, tfpp_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TFPP_CHECK_ARG(tokens <= kT && tokens % 32 == 0, "tokens must be a multiple of 32 and <= 320");
   TFPP_CHECK_ARG(channels % heads == 0 && (channels / heads) % 2 == 0 && channels % 8 == 0,
@@ -524,8 +597,11 @@ extern "C" int tfpp_fusion_attn_bwd(const void* qkv, const void* dout, void* dqk
   const size_t smem = sizeof(bf16) * (kQ * kPitchP + 2 * kStageElems) + sizeof(float) * 2 * kQ;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fusion_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fusion_attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fusion_attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
     if (e != cudaSuccess) {
       tfpp_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return TFPP_ERR_CUDA;
@@ -536,9 +612,14 @@ extern "C" int tfpp_fusion_attn_bwd(const void* qkv, const void* dout, void* dqk
   cudaMemsetAsync(dkv_ws, 0, sizeof(float) * rows * 2 * channels, stream);
   const int hd = channels / heads;
   dim3 grid(ceil_div(tokens, kQ), heads, batch);
-  fusion_attn_bwd_kernel<<<grid, 256, smem, stream>>>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout),
-                                                      static_cast<bf16*>(dqkv), dkv_ws, tokens, channels, heads,
-                                                      1.0f / sqrtf(static_cast<float>(hd)));
+  if (drop_rng != nullptr && drop_p > 0.f)
+    fusion_attn_bwd_kernel<true><<<grid, 256, smem, stream>>>(
+        static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), static_cast<bf16*>(dqkv), dkv_ws, tokens, channels,
+        heads, 1.0f / sqrtf(static_cast<float>(hd)), drop_rng, drop_p, drop_site);
+  else
+    fusion_attn_bwd_kernel<false><<<grid, 256, smem, stream>>>(
+        static_cast<const bf16*>(qkv), static_cast<const bf16*>(dout), static_cast<bf16*>(dqkv), dkv_ws, tokens, channels,
+        heads, 1.0f / sqrtf(static_cast<float>(hd)), nullptr, 0.f, 0u);
   TFPP_CHECK_LAUNCH();
   dkv_cast_kernel<<<static_cast<unsigned>(ceil_div_ll(rows * 2 * channels / 8, 256)), 256, 0, stream>>>(
       dkv_ws, static_cast<bf16*>(dqkv), rows, channels);

@@ -50,6 +50,9 @@ struct KParams {
   int act, act_n_limit;
   float* stat_sum;
   float* stat_sq;
+  const unsigned long long* drop_rng;
+  float drop_p;
+  unsigned drop_site;
   int fast_layout;   // bf16/fp32 NHWC output with unit channel stride, <= 1 residual of the same kind, none/ReLU
   int stat_floats;   // 2 * n_tiles * bn when statistics are requested, else 0
 };
@@ -200,6 +203,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool has_stats = p.stat_sum != nullptr;
     const bool has_affine = (g_scale != nullptr) || (g_shift != nullptr);
     const int act = p.act;
+    const DropCtx drop = drop_ctx(p.drop_rng, p.drop_p, p.drop_site);
     const bool fast_layout = p.fast_layout != 0;
     const bool out_f32 = p.out_f32 != 0;
     const bf16* __restrict__ res_b = (p.res1 != nullptr && !p.res1_f32) ? static_cast<const bf16*>(p.res1) : nullptr;
@@ -300,6 +304,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     v[j + 1] = fmaf(v[j + 1], a2.z, a2.w);
                   }
                 }
+                if (drop.on) {  // out = drop(act(affine(acc))) + res: activation first, residual after the mask
+                  if (act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                  }
+                  float dm[8];
+                  drop_mult8(drop, static_cast<unsigned long long>(o_base + n + q * 8), dm);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] *= dm[j];
+                }
                 if (res_b != nullptr) {
                   const uint32_t w[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
 #pragma unroll
@@ -312,7 +326,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   v[0] += rf[2 * q].x; v[1] += rf[2 * q].y; v[2] += rf[2 * q].z; v[3] += rf[2 * q].w;
                   v[4] += rf[2 * q + 1].x; v[5] += rf[2 * q + 1].y; v[6] += rf[2 * q + 1].z; v[7] += rf[2 * q + 1].w;
                 }
-                if (act == ACT_RELU) {
+                if (act == ACT_RELU && !drop.on) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
@@ -338,10 +352,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               const float2 a2 = saff[c + j];
               v = fmaf(v, a2.x, a2.y);
             }
+            const long long off = o_base + col * p.o_sn;
+            if (drop.on) {  // drop(act(.)) + residuals
+              if (act != ACT_NONE && (p.act_n_limit == 0 || col < p.act_n_limit)) v = apply_act(v, act);
+              v *= drop_mult(drop, static_cast<unsigned long long>(off));
+            }
             if (p.res1) v += load_res(p.res1, p.res1_f32, r1_base + col * p.r1_sn);
             if (p.res2) v += load_res(p.res2, p.res2_f32, r2_base + col * p.r2_sn);
-            if (act != ACT_NONE && (p.act_n_limit == 0 || col < p.act_n_limit)) v = apply_act(v, act);
-            const long long off = o_base + col * p.o_sn;
+            if (!drop.on && act != ACT_NONE && (p.act_n_limit == 0 || col < p.act_n_limit)) v = apply_act(v, act);
             if (p.out_f32)
               static_cast<float*>(p.out)[off] = v;
             else
@@ -434,6 +452,10 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
   p.act_n_limit = a->act_n_limit;
   p.stat_sum = a->stat_sum;
   p.stat_sq = a->stat_sq;
+  p.drop_rng = a->drop_p > 0.f ? a->drop_rng : nullptr;
+  p.drop_p = a->drop_p;
+  p.drop_site = a->drop_site;
+  TFPP_CHECK_ARG(a->drop_p >= 0.f && a->drop_p < 1.f, "dropout probability must be in [0, 1)");
 
   CUtensorMap tmap_a, tmap_b;
   {

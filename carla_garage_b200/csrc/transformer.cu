@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(256) small_mha_kernel(const bf16* __restrict__
                                                         const bf16* __restrict__ k, long long k_sb, long long k_sr,
                                                         const bf16* __restrict__ v, long long v_sb, long long v_sr,
                                                         bf16* __restrict__ out, long long o_sb, long long o_sr, int Tq,
-                                                        int Tk, int hd, float scale) {
+                                                        int Tk, int hd, float scale, const unsigned long long* drop_rng,
+                                                        float drop_p, unsigned drop_site) {
+  const DropCtx drop = drop_ctx(drop_rng, drop_p, drop_site);   // nn.MultiheadAttention(dropout=0.1) on the probabilities
   extern __shared__ float mha_sm[];
   float* ks = mha_sm;                    // [Tk][hd+1]
   float* vs = ks + Tk * (hd + 1);        // [Tk][hd+1]
@@ -80,6 +82,11 @@ __global__ void __launch_bounds__(256) small_mha_kernel(const bf16* __restrict__
     sum = warp_sum(sum);
     __syncwarp();
     const float inv = 1.f / sum;
+    if (drop.on) {
+      const unsigned long long base = ((static_cast<unsigned long long>(b) * gridDim.y + h) * Tq + r) * Tk;
+      for (int c = lane; c < Tk; c += 32) pw[c] *= drop_mult(drop, base + c);
+      __syncwarp();
+    }
     for (int d = lane; d < hd; d += 32) {
       float a = 0.f;
       for (int c = 0; c < Tk; ++c) a = fmaf(pw[c], vs[c * (hd + 1) + d], a);
@@ -241,10 +248,25 @@ extern "C" int tfpp_layernorm(const void* x, int x_f32, const float* gamma, cons
   return TFPP_OK;
 }
 
+extern "C" int tfpp_small_mha_dropout(const void* q, long long q_sb, long long q_sr, const void* k, long long k_sb,
+                                      long long k_sr, const void* v, long long v_sb, long long v_sr, void* out,
+                                      long long o_sb, long long o_sr, int batch, int heads, int tq, int tk, int head_dim,
+                                      const unsigned long long* drop_rng, float drop_p, unsigned drop_site,
+                                      tfpp_stream_t stream_);
+
 extern "C" int tfpp_small_mha(const void* q, long long q_sb, long long q_sr, const void* k, long long k_sb,
                               long long k_sr, const void* v, long long v_sb, long long v_sr, void* out, long long o_sb,
                               long long o_sr, int batch, int heads, int tq, int tk, int head_dim,
                               tfpp_stream_t stream_) {
+  return tfpp_small_mha_dropout(q, q_sb, q_sr, k, k_sb, k_sr, v, v_sb, v_sr, out, o_sb, o_sr, batch, heads, tq, tk,
+                                head_dim, nullptr, 0.f, 0u, stream_);
+}
+
+extern "C" int tfpp_small_mha_dropout(const void* q, long long q_sb, long long q_sr, const void* k, long long k_sb,
+                                      long long k_sr, const void* v, long long v_sb, long long v_sr, void* out,
+                                      long long o_sb, long long o_sr, int batch, int heads, int tq, int tk, int head_dim,
+                                      const unsigned long long* drop_rng, float drop_p, unsigned drop_site,
+                                      tfpp_stream_t stream_) {
   STREAM;
   TFPP_CHECK_ARG(tk <= 256 && head_dim <= 64, "small_mha: tk <= 256, head_dim <= 64");
   const size_t smem = sizeof(float) * (2 * tk * (head_dim + 1) + 8 * tk);
@@ -252,7 +274,8 @@ extern "C" int tfpp_small_mha(const void* q, long long q_sb, long long q_sr, con
   small_mha_kernel<<<grid, 256, smem, stream>>>(static_cast<const bf16*>(q), q_sb, q_sr, static_cast<const bf16*>(k),
                                                 k_sb, k_sr, static_cast<const bf16*>(v), v_sb, v_sr,
                                                 static_cast<bf16*>(out), o_sb, o_sr, tq, tk, head_dim,
-                                                1.0f / sqrtf(static_cast<float>(head_dim)));
+                                                1.0f / sqrtf(static_cast<float>(head_dim)),
+                                                drop_p > 0.f ? drop_rng : nullptr, drop_p, drop_site);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

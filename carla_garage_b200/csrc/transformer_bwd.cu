@@ -61,7 +61,11 @@ __global__ void __launch_bounds__(256) small_mha_bwd_kernel(const bf16* __restri
                                                             bf16* __restrict__ dq, long long dq_sb, long long dq_sr,
                                                             bf16* __restrict__ dk, long long dk_sb, long long dk_sr,
                                                             bf16* __restrict__ dv, long long dv_sb, long long dv_sr,
-                                                            int accumulate_kv, int Tq, int Tk, int hd, float scale) {
+                                                            int accumulate_kv, int Tq, int Tk, int hd, float scale,
+                                                            const unsigned long long* drop_rng, float drop_p,
+                                                            unsigned drop_site) {
+  // probability dropout (nn.MultiheadAttention(dropout=0.1)): dV = (P o M')^T dO, dP = (dO V^T) o M', M' = mask / (1-p)
+  const DropCtx drop = drop_ctx(drop_rng, drop_p, drop_site);
   extern __shared__ float sm[];
   const int P1 = hd + 1;
   float* qs = sm;                  // Tq x P1
@@ -105,12 +109,18 @@ __global__ void __launch_bounds__(256) small_mha_bwd_kernel(const bf16* __restri
     // dP = dO V^T ; rowsum(dP * P)
     float rsum = 0.f;
     float dpl[4];  // Tk <= 128 -> up to 4 per lane
+    float dml[4] = {1.f, 1.f, 1.f, 1.f};
     int n = 0;
+    const unsigned long long dbase = ((static_cast<unsigned long long>(b) * gridDim.y + h) * Tq + r) * Tk;
     for (int c = lane; c < Tk; c += 32, ++n) {
       float a = 0.f;
       for (int d = 0; d < hd; ++d) a = fmaf(dos[r * P1 + d], vs[c * P1 + d], a);
       const float p = pr[c] * inv;
       pr[c] = p;
+      if (drop.on) {
+        dml[n] = drop_mult(drop, dbase + c);
+        a *= dml[n];
+      }
       dpl[n] = a;
       rsum = fmaf(a, p, rsum);
     }
@@ -121,6 +131,7 @@ __global__ void __launch_bounds__(256) small_mha_bwd_kernel(const bf16* __restri
     for (int c = lane; c < Tk; c += 32, ++n) {
       const float p = pr[c];
       dpl[n] = p * (dpl[n] - rsum) * scale;  // dS
+      if (drop.on) pr[c] = p * dml[n];       // the dV pass below multiplies the DROPPED probabilities
     }
     // dV += P^T dO is accumulated after the loop (needs all rows) -> store P in place and dS in registers -> write dQ now
     __syncwarp();
@@ -403,6 +414,18 @@ extern "C" int tfpp_small_mha_bwd(const void* q, long long q_sb, long long q_sr,
                                   long long dk_sb, long long dk_sr, void* dv, long long dv_sb, long long dv_sr,
                                   int accumulate_kv, int batch, int heads, int tq, int tk, int head_dim,
                                   tfpp_stream_t stream_) {
+  return tfpp_small_mha_bwd_dropout(q, q_sb, q_sr, k, k_sb, k_sr, v, v_sb, v_sr, dout, o_sb, o_sr, dq, dq_sb, dq_sr, dk,
+                                    dk_sb, dk_sr, dv, dv_sb, dv_sr, accumulate_kv, batch, heads, tq, tk, head_dim,
+                                    nullptr, 0.f, 0u, stream_);
+}
+
+extern "C" int tfpp_small_mha_bwd_dropout(const void* q, long long q_sb, long long q_sr, const void* k, long long k_sb,
+                                          long long k_sr, const void* v, long long v_sb, long long v_sr,
+                                          const void* dout, long long o_sb, long long o_sr, void* dq, long long dq_sb,
+                                          long long dq_sr, void* dk, long long dk_sb, long long dk_sr, void* dv,
+                                          long long dv_sb, long long dv_sr, int accumulate_kv, int batch, int heads,
+                                          int tq, int tk, int head_dim, const unsigned long long* drop_rng, float drop_p,
+                                          unsigned drop_site, tfpp_stream_t stream_) {
   STREAM;
   TFPP_CHECK_ARG(tk <= 128 && tq <= 16 && head_dim <= 64, "small_mha_bwd: tq <= 16, tk <= 128, head_dim <= 64");
   const size_t smem = sizeof(float) * ((2 * tq + 2 * tk) * (head_dim + 1) + 2 * tq * tk);
@@ -411,7 +434,7 @@ extern "C" int tfpp_small_mha_bwd(const void* q, long long q_sb, long long q_sr,
       static_cast<const bf16*>(q), q_sb, q_sr, static_cast<const bf16*>(k), k_sb, k_sr, static_cast<const bf16*>(v), v_sb,
       v_sr, static_cast<const bf16*>(dout), o_sb, o_sr, static_cast<bf16*>(dq), dq_sb, dq_sr, static_cast<bf16*>(dk),
       dk_sb, dk_sr, static_cast<bf16*>(dv), dv_sb, dv_sr, accumulate_kv, tq, tk, head_dim,
-      1.0f / sqrtf(static_cast<float>(head_dim)));
+      1.0f / sqrtf(static_cast<float>(head_dim)), drop_p > 0.f ? drop_rng : nullptr, drop_p, drop_site);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

@@ -256,6 +256,11 @@ class Engine:
     self._consts = {}
     self.tape = None  # list of saved activations when a backward pass will follow
     self.debug_taps = None  # dict: name -> NHWC bf16 intermediate (tests only)
+    # training-mode dropout (transfuser.py:325,374,379,395; nn.TransformerDecoderLayer / MultiheadAttention 0.1):
+    # counter-based masks keyed by (seed, step, site, element) — see tfpp_dropout in include/tfpp.h
+    self.dropout_enabled = os.environ.get('TFPP_DROPOUT', '1') != '0'
+    self.rng = None      # int64 device tensor {seed, step}; step is bumped once per training forward
+    self._site = 0       # dropout sites are numbered in call order within one forward
 
   @classmethod
   def for_backbone(cls, backbone):
@@ -289,6 +294,26 @@ class Engine:
     if key not in self._consts:
       self._consts[key] = torch.cuda.Stream(device=device)
     return self._consts[key]
+
+  def seed_dropout(self, seed, device=None, step=0):
+    """(Re)seed the dropout stream: masks are a pure function of (seed, step, site, element index)."""
+    device = device or (self.rng.device if self.rng is not None else 'cuda')
+    self.rng = torch.tensor([int(seed) & (2**63 - 1), int(step)], dtype=torch.int64, device=device)
+
+  def begin_dropout_step(self, device):
+    """Start of a training forward: next step of the random stream, site numbering restarts."""
+    if self.rng is None or self.rng.device != device:
+      self.seed_dropout(torch.initial_seed(), device)
+    self.rng[1:2] += 1
+    self._site = 0
+
+  def drop(self, p, training=True):
+    """(rng, p, site) of the next dropout site, or None when dropout is inactive."""
+    if not (training and self.dropout_enabled and p and p > 0.0 and self.rng is not None):
+      return None
+    site = self._site
+    self._site += 1
+    return (self.rng, float(p), site)
 
   def _count_batch(self, bn):
     """BatchNorm.num_batches_tracked += 1.  Under a Trainer all the counters are views of one int64 buffer that is
@@ -466,7 +491,6 @@ class Engine:
   # ------------------------------------------------------------------------------------------------ fusion GPT
   def fuse(self, img, lid, i, training):
     """TransfuserBackbone.fuse_features + GPT.forward (transfuser.py:222-257,301-339) for scale i."""
-    del training  # dropout (embd/attn/resid_pdrop) is not applied: parity runs use p = 0
     bb, cfg = self.bb, self.cfg
     gpt = bb.transformers[i]
     b, hi, wi, c = img.shape
@@ -484,7 +508,9 @@ class Engine:
     ops.linear(lid_pool.view(b * n_lid, cl), packed(l2i.weight, 'linear'), bias=packed(l2i.bias, 'f32'),
                out=x.view(-1)[n_img * c:], row_map=(n_lid, t), res2=pos[n_img:], res2_strides=(0, 0, c, 1))
     x = x.view(b * t, c)
-    self._save(op='tokenise', img=img, lid=lid, lid_pool=lid_pool, i=i, x0=x, b=b, t=t, c=c, cl=cl)
+    d_embd = self.drop(cfg.embd_pdrop, training)  # GPT.drop on pos_emb + tokens (transfuser.py:325)
+    ops.dropout_(x, d_embd)
+    self._save(op='tokenise', img=img, lid=lid, lid_pool=lid_pool, i=i, x0=x, b=b, t=t, c=c, cl=cl, drop=d_embd)
     heads = cfg.n_head
     for blk in gpt.blocks:
       at = blk.attn
@@ -492,13 +518,18 @@ class Engine:
       wqkv = packed((at.query.weight, at.key.weight, at.value.weight), 'cat_linear')
       bqkv = packed((at.query.bias, at.key.bias, at.value.bias), 'cat_f32')
       qkv = ops.linear(h, wqkv, bias=bqkv)
-      y = ops.fusion_attn(qkv, b, t, c, heads)
-      x1 = ops.linear(y, packed(at.proj.weight, 'linear'), bias=packed(at.proj.bias, 'f32'), res=x, out_f32=True)
+      d_attn = self.drop(cfg.attn_pdrop, training)    # attn_drop on the probabilities (transfuser.py:374)
+      y = ops.fusion_attn(qkv, b, t, c, heads, drop=d_attn)
+      d_proj = self.drop(cfg.resid_pdrop, training)   # resid_drop (transfuser.py:379): x + drop(proj(y))
+      x1 = ops.linear(y, packed(at.proj.weight, 'linear'), bias=packed(at.proj.bias, 'f32'), res=x, out_f32=True,
+                      drop=d_proj)
       h2, _, mean2, rstd2 = ops.layernorm(x1, blk.ln2.weight, blk.ln2.bias, save=self.tape is not None)
       m = ops.linear(h2, packed(blk.mlp[0].weight, 'linear'), bias=packed(blk.mlp[0].bias, 'f32'), act=ACT_RELU)
-      x2 = ops.linear(m, packed(blk.mlp[2].weight, 'linear'), bias=packed(blk.mlp[2].bias, 'f32'), res=x1, out_f32=True)
+      d_mlp = self.drop(cfg.resid_pdrop, training)    # nn.Dropout closing the MLP (transfuser.py:395)
+      x2 = ops.linear(m, packed(blk.mlp[2].weight, 'linear'), bias=packed(blk.mlp[2].bias, 'f32'), res=x1, out_f32=True,
+                      drop=d_mlp)
       self._save(op='gpt_block', x=x, h=h, qkv=qkv, y=y, x1=x1, h2=h2, m=m, x2=x2, blk=blk, mean1=mean1, rstd1=rstd1,
-                 mean2=mean2, rstd2=rstd2, b=b, t=t, c=c, heads=heads)
+                 mean2=mean2, rstd2=rstd2, b=b, t=t, c=c, heads=heads, drops=(d_attn, d_proj, d_mlp))
       x = x2
     xf, _, meanf, rstdf = ops.layernorm(x, gpt.ln_f.weight, gpt.ln_f.bias, save=self.tape is not None)
     # image tokens: bilinear up-sample straight out of the token matrix + residual add (transfuser.py:239-242,254)
@@ -524,6 +555,8 @@ class Engine:
       # tfpp_bn_finalize / tfpp_extra_sensor_token update the running statistics through raw pointers (no version
       # counter moves): folded eval-mode BatchNorm affines cached before this forward are stale after it
       PARAM_EPOCH[0] += 1
+      if self.dropout_enabled:
+        self.begin_dropout_step(image.device)  # on the main stream, before the LiDAR branch forks
     image = image.float().contiguous()
     lidar = lidar.float().contiguous()
     # Training: between two fusion points the LiDAR branch (a quarter of the image branch's pixels: kernels that cannot
@@ -662,29 +695,37 @@ class Engine:
                ego_vel=ego_vel, command=command, training=training, posenc=posenc)
     for li, l in enumerate(layers):
       act = ACT_RELU if l.activation is torch.nn.functional.relu else ACT_GELU
+      # nn.TransformerDecoderLayer(dropout=0.1) (model.py:137-140): probabilities of both attentions, dropout1/2/3 on
+      # the sub-layer outputs, `dropout` after the feed-forward activation — numbered in the order torch applies them
+      dp = (self.drop(l.self_attn.dropout, training), self.drop(l.dropout1.p, training),
+            self.drop(l.multihead_attn.dropout, training), self.drop(l.dropout2.p, training),
+            self.drop(l.dropout.p, training), self.drop(l.dropout3.p, training))
+      if dp[4] is not None and act != ACT_RELU:
+        raise NotImplementedError('feed-forward dropout is fused with the ReLU mask; GELU + dropout is not built')
       qkv = ops.linear(xb, packed(l.self_attn.in_proj_weight, 'linear'), bias=packed(l.self_attn.in_proj_bias, 'f32'))
       sa = ops.small_mha(qkv, qkv, qkv, b, heads, nq, nq, hd, (nq * 3 * d, 3 * d), (nq * 3 * d, 3 * d),
-                         (nq * 3 * d, 3 * d), k_off=d, v_off=2 * d)
+                         (nq * 3 * d, 3 * d), k_off=d, v_off=2 * d, drop=dp[0])
       t1 = ops.linear(sa, packed(l.self_attn.out_proj.weight, 'linear'), bias=packed(l.self_attn.out_proj.bias, 'f32'),
-                      res=x, out_f32=True)
+                      res=x, out_f32=True, drop=dp[1])
       x1b, x1, m1, r1 = ops.layernorm(t1, l.norm1.weight, l.norm1.bias, want_f32=True, eps=l.norm1.eps,
                                       save=self.tape is not None)
       q2 = ops.linear(x1b, packed(l.multihead_attn.in_proj_weight, 'rows', 0, d),
                       bias=packed(l.multihead_attn.in_proj_bias, 'rows_f32', 0, d))
       kv = kvs[li]
       ca = ops.small_mha(q2, kv, kv, b, heads, nq, n_mem, hd, (nq * d, d), (n_mem * 2 * d, 2 * d), (n_mem * 2 * d, 2 * d),
-                         v_off=d)
+                         v_off=d, drop=dp[2])
       t2 = ops.linear(ca, packed(l.multihead_attn.out_proj.weight, 'linear'),
-                      bias=packed(l.multihead_attn.out_proj.bias, 'f32'), res=x1, out_f32=True)
+                      bias=packed(l.multihead_attn.out_proj.bias, 'f32'), res=x1, out_f32=True, drop=dp[3])
       x2b, x2, m2, r2 = ops.layernorm(t2, l.norm2.weight, l.norm2.bias, want_f32=True, eps=l.norm2.eps,
                                       save=self.tape is not None)
-      ff = ops.linear(x2b, packed(l.linear1.weight, 'linear'), bias=packed(l.linear1.bias, 'f32'), act=act)
-      t3 = ops.linear(ff, packed(l.linear2.weight, 'linear'), bias=packed(l.linear2.bias, 'f32'), res=x2, out_f32=True)
+      ff = ops.linear(x2b, packed(l.linear1.weight, 'linear'), bias=packed(l.linear1.bias, 'f32'), act=act, drop=dp[4])
+      t3 = ops.linear(ff, packed(l.linear2.weight, 'linear'), bias=packed(l.linear2.bias, 'f32'), res=x2, out_f32=True,
+                      drop=dp[5])
       x3b, x3, m3, r3 = ops.layernorm(t3, l.norm3.weight, l.norm3.bias, want_f32=True, eps=l.norm3.eps,
                                       save=self.tape is not None)
       self._save(op='dec_layer', li=li, layer=l, x_in=x, xb=xb, qkv=qkv, sa=sa, t1=t1, x1=x1, x1b=x1b, q2=q2, kv=kv, ca=ca,
                  t2=t2, x2=x2, x2b=x2b, ff=ff, t3=t3, x3=x3, stats=(m1, r1, m2, r2, m3, r3), act=act, b=b, nq=nq,
-                 n_mem=n_mem, d=d, heads=heads, hd=hd)
+                 n_mem=n_mem, d=d, heads=heads, hd=hd, drops=dp)
       x, xb = x3, x3b
     _, joined, mj, rj = ops.layernorm(x, m.join.norm.weight, m.join.norm.bias, want_bf16=False, want_f32=True,
                                       eps=m.join.norm.eps, save=self.tape is not None)

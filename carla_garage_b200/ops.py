@@ -111,7 +111,7 @@ def nchw_strides(h, w, c):
 
 def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1, k_per_tile=None, a_c_per_ntile=0, bn=None, out=None, out_f32=False,
               out_layout='nhwc', out_strides=None, res1=None, res1_strides=None, res2=None, res2_strides=None,
-              scale=None, shift=None, act=ACT_NONE, act_n_limit=0, stats=None, no_output=False):
+              scale=None, shift=None, act=ACT_NONE, act_n_limit=0, stats=None, no_output=False, drop=None):
   """out[pixel, n] = act(scale[n] * sum_{tap,c} a[pixel + tap, c] * w[n, tap, c] + shift[n] + res1 + res2).
 
   a: (Ba, H, W, C) bf16 NHWC; w: (N, taps, K) bf16.  Returns a new (B,H,W,N) bf16 / (B,N,H,W) f32 tensor unless
@@ -172,6 +172,8 @@ def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1
   args.act_n_limit = act_n_limit
   if stats is not None:
     args.stat_sum, args.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
+  if drop is not None:  # (rng tensor {seed, step}, p, site): out = drop(act(.)) + residuals
+    args.drop_rng, args.drop_p, args.drop_site = drop[0].data_ptr(), drop[1], drop[2]
   if _PROFILE is not None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -235,7 +237,7 @@ def conv_wgrad(dy, x, *, cin=None, taps=TAPS_1X1, w_taps=None, group_width=0, x_
 
 
 def linear(x, w, bias=None, act=ACT_NONE, res=None, out_f32=False, out=None, row_map=None, res2=None,
-           res2_strides=None, stats=None):
+           res2_strides=None, stats=None, drop=None):
   """x: (rows, K) bf16, w: (N, K) bf16 -> (rows, N) bf16|f32.  res: same addressing as out, added before act.
   row_map = (rows_per_group, group_stride_rows): output/res row r -> (r // rpg) * gsr + r % rpg (``out`` required)."""
   rows, k = x.shape
@@ -251,7 +253,7 @@ def linear(x, w, bias=None, act=ACT_NONE, res=None, out_f32=False, out=None, row
     st = (gsr * n, 0, n, 1)
     assert out is not None
   conv_gemm(a4, w.view(n, 1, k), shift=bias, act=act, res1=res, res1_strides=st if res is not None else None, out=out,
-            out_strides=st, res2=res2, res2_strides=res2_strides, stats=stats)
+            out_strides=st, res2=res2, res2_strides=res2_strides, stats=stats, drop=drop)
   return out
 
 
@@ -390,21 +392,37 @@ def layernorm(x, gamma, beta, want_bf16=True, want_f32=False, eps=1e-5, save=Fal
   return yb, yf, mean, rstd
 
 
-def fusion_attn(qkv, batch, tokens, channels, heads):
+def _drop_args(drop):
+  return (None, 0.0, 0) if drop is None else (drop[0].data_ptr(), float(drop[1]), int(drop[2]))
+
+
+def dropout_(x, drop):
+  """In-place dropout over a contiguous f32 / bf16 tensor (numel % 8 == 0); drop = (rng {seed, step} int64 tensor, p,
+  site).  Applying it to a gradient with the same triple is the adjoint."""
+  if drop is None:
+    return x
+  check(_lib.load().tfpp_dropout(x.data_ptr(), int(x.dtype == F32), x.numel(), *_drop_args(drop), _stream()),
+        'tfpp_dropout')
+  return x
+
+
+def fusion_attn(qkv, batch, tokens, channels, heads, drop=None):
   _dev(qkv, BF16)
   out = torch.empty((batch * tokens, channels), dtype=BF16, device=qkv.device)
-  check(_lib.load().tfpp_fusion_attn(qkv.data_ptr(), out.data_ptr(), batch, tokens, channels, heads, _stream()),
-        'tfpp_fusion_attn')
+  check(_lib.load().tfpp_fusion_attn_dropout(qkv.data_ptr(), out.data_ptr(), batch, tokens, channels, heads,
+                                             *_drop_args(drop), _stream()), 'tfpp_fusion_attn')
   return out
 
 
-def small_mha(q, k, v, batch, heads, tq, tk, head_dim, q_strides, k_strides, v_strides, q_off=0, k_off=0, v_off=0):
+def small_mha(q, k, v, batch, heads, tq, tk, head_dim, q_strides, k_strides, v_strides, q_off=0, k_off=0, v_off=0,
+              drop=None):
   """bf16 views given as (tensor, element offset, (batch stride, row stride)); returns (B*tq, heads*head_dim) bf16."""
   d = heads * head_dim
   out = torch.empty((batch * tq, d), dtype=BF16, device=q.device)
-  check(_lib.load().tfpp_small_mha(q.data_ptr() + 2 * q_off, q_strides[0], q_strides[1], k.data_ptr() + 2 * k_off,
-                                   k_strides[0], k_strides[1], v.data_ptr() + 2 * v_off, v_strides[0], v_strides[1],
-                                   out.data_ptr(), tq * d, d, batch, heads, tq, tk, head_dim, _stream()),
+  check(_lib.load().tfpp_small_mha_dropout(q.data_ptr() + 2 * q_off, q_strides[0], q_strides[1],
+                                           k.data_ptr() + 2 * k_off, k_strides[0], k_strides[1],
+                                           v.data_ptr() + 2 * v_off, v_strides[0], v_strides[1], out.data_ptr(), tq * d,
+                                           d, batch, heads, tq, tk, head_dim, *_drop_args(drop), _stream()),
         'tfpp_small_mha')
   return out
 
@@ -590,11 +608,12 @@ def se_bwd(dout, a2, gate, hidden, pool_sum, hw, w1, w2, dw1, db1, dw2, db2, zer
 
 
 def act_bwd(dy, y, act, batch, hw, channels, layout=0, act_n_limit=0, dy_scale=1.0, dbias=None, channels_padded=None,
-            want_dz=True):
+            want_dz=True, drop=None):
+  """drop = (rng, p, site) of a dropout applied to the forward output: its mask (x 1/(1-p)) multiplies dy first."""
   cp = channels if channels_padded is None else channels_padded
   dz = torch.empty((batch * hw, cp), dtype=BF16, device=dy.device) if want_dz else None
-  check(_lib.load().tfpp_act_bwd(dy.data_ptr(), _p(y), layout, act, act_n_limit, dy_scale, _p(dz), _p(dbias), batch, hw,
-                                 channels, cp, _stream()), 'tfpp_act_bwd')
+  check(_lib.load().tfpp_act_bwd_dropout(dy.data_ptr(), _p(y), layout, act, act_n_limit, dy_scale, _p(dz), _p(dbias),
+                                         batch, hw, channels, cp, *_drop_args(drop), _stream()), 'tfpp_act_bwd')
   return dz
 
 
@@ -657,24 +676,25 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
   return dx
 
 
-def fusion_attn_bwd(qkv, dout, batch, tokens, channels, heads):
+def fusion_attn_bwd(qkv, dout, batch, tokens, channels, heads, drop=None):
   dqkv = torch.empty_like(qkv)
   ws = torch.empty((batch * tokens, 2 * channels), dtype=F32, device=qkv.device)
-  check(_lib.load().tfpp_fusion_attn_bwd(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), batch, tokens,
-                                         channels, heads, _stream()), 'tfpp_fusion_attn_bwd')
+  check(_lib.load().tfpp_fusion_attn_bwd_dropout(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), batch,
+                                                 tokens, channels, heads, *_drop_args(drop), _stream()),
+        'tfpp_fusion_attn_bwd')
   return dqkv
 
 
 def small_mha_bwd(q, k, v, dout, dq, dk, dv, batch, heads, tq, tk, head_dim, q_st, k_st, v_st, dq_st, dk_st, dv_st,
-                  offs=(0, 0, 0, 0, 0, 0), accumulate_kv=False):
+                  offs=(0, 0, 0, 0, 0, 0), accumulate_kv=False, drop=None):
   """offs: element offsets of (q, k, v, dq, dk, dv) inside their buffers; *_st = (batch stride, row stride)."""
   d = heads * head_dim
   p = lambda t, o: t.data_ptr() + 2 * o
-  check(_lib.load().tfpp_small_mha_bwd(p(q, offs[0]), q_st[0], q_st[1], p(k, offs[1]), k_st[0], k_st[1], p(v, offs[2]),
-                                       v_st[0], v_st[1], dout.data_ptr(), tq * d, d, p(dq, offs[3]), dq_st[0], dq_st[1],
-                                       p(dk, offs[4]), dk_st[0], dk_st[1], p(dv, offs[5]), dv_st[0], dv_st[1],
-                                       int(accumulate_kv), batch, heads, tq, tk, head_dim, _stream()),
-        'tfpp_small_mha_bwd')
+  check(_lib.load().tfpp_small_mha_bwd_dropout(p(q, offs[0]), q_st[0], q_st[1], p(k, offs[1]), k_st[0], k_st[1],
+                                               p(v, offs[2]), v_st[0], v_st[1], dout.data_ptr(), tq * d, d,
+                                               p(dq, offs[3]), dq_st[0], dq_st[1], p(dk, offs[4]), dk_st[0], dk_st[1],
+                                               p(dv, offs[5]), dv_st[0], dv_st[1], int(accumulate_kv), batch, heads, tq,
+                                               tk, head_dim, *_drop_args(drop), _stream()), 'tfpp_small_mha_bwd')
 
 
 # ---------------------------------------------------------------------------------------------- experimental: halo UMMA

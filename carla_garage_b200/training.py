@@ -472,16 +472,17 @@ class Backward:
     dx2 = self.G.pop(id(r['x2']))
     # x2 = x1 + mlp2(m); m = relu(mlp1(h2)); h2 = LN2(x1)
     l1, l2 = blk.mlp[0], blk.mlp[2]
-    dz2 = ops.act_bwd(dx2, None, ACT_NONE, 1, rows, c, layout=2, dbias=st.g(l2.bias))
+    d_attn, d_proj, d_mlp = r.get('drops', (None, None, None))
+    dz2 = ops.act_bwd(dx2, None, ACT_NONE, 1, rows, c, layout=2, dbias=st.g(l2.bias), drop=d_mlp)
     dm = self.linear_bwd(dz2, r['m'], st.g(l2.weight), packed(l2.weight, 'linear_t'), c, 4 * c, out_f32=False)
     dzm = ops.act_bwd(dm, r['m'], ACT_RELU, 1, rows, 4 * c, dbias=st.g(l1.bias))
     dh2 = self.linear_bwd(dzm, r['h2'], st.g(l1.weight), packed(l1.weight, 'linear_t'), 4 * c, c)
     dx1 = ops.layernorm_bwd(dh2, r['x1'], r['mean2'], r['rstd2'], blk.ln2.weight, st.g(blk.ln2.weight),
                             st.g(blk.ln2.bias), dres=dx2)
     # x1 = x + proj(y); y = attn(qkv); qkv = lin(h); h = LN1(x)
-    dzp = ops.act_bwd(dx1, None, ACT_NONE, 1, rows, c, layout=2, dbias=st.g(at.proj.bias))
+    dzp = ops.act_bwd(dx1, None, ACT_NONE, 1, rows, c, layout=2, dbias=st.g(at.proj.bias), drop=d_proj)
     dy = self.linear_bwd(dzp, r['y'], st.g(at.proj.weight), packed(at.proj.weight, 'linear_t'), c, c, out_f32=False)
-    dqkv = ops.fusion_attn_bwd(r['qkv'], dy, b, t, c, r['heads'])
+    dqkv = ops.fusion_attn_bwd(r['qkv'], dy, b, t, c, r['heads'], drop=d_attn)
     ops.act_bwd(dqkv, None, ACT_NONE, 1, rows, 3 * c, dbias=st.g_span(at.query.bias, at.value.bias), want_dz=False)
     wt = packed((at.query.weight, at.key.weight, at.value.weight), 'cat_linear_t')
     dh = self.linear_bwd(dqkv, r['h'], st.g_span(at.query.weight, at.value.weight), wt, 3 * c, c)
@@ -497,6 +498,7 @@ class Backward:
     n_img = cfg.img_vert_anchors * cfg.img_horz_anchors
     n_lid = t - n_img
     dx = self.G.pop(id(r['x0']))
+    ops.dropout_(dx, r.get('drop'))  # adjoint of GPT.drop (in place: dx is ours)
     # pos_emb gradient = sum over the batch
     ops.batch_reduce(dx, st.g(gpt.pos_emb).view(-1), b)
     img, lid = r['img'], r['lid']
@@ -583,17 +585,21 @@ class Backward:
     dx3 = self.G.pop(id(r['x3']))
     # x3 = LN3(t3), t3 = x2 + lin2(ff), ff = act(lin1(x2b))
     dt3 = ops.layernorm_bwd(dx3, r['t3'], m3, r3, l.norm3.weight, g(l.norm3.weight), g(l.norm3.bias))
-    dz = ops.act_bwd(dt3, None, ACT_NONE, 1, rows, d, layout=2, dbias=g(l.linear2.bias))
+    dp = r.get('drops', (None,) * 6)
+    dz = ops.act_bwd(dt3, None, ACT_NONE, 1, rows, d, layout=2, dbias=g(l.linear2.bias), drop=dp[5])
     ffw = l.linear1.weight.shape[0]
     dff = self.linear_bwd(dz, r['ff'], g(l.linear2.weight), packed(l.linear2.weight, 'linear_t'), d, ffw, out_f32=False)
     if r['act'] != ACT_RELU:
       raise NotImplementedError('GELU decoder feed-forward backward is not built (the reference runs ReLU)')
-    dzf = ops.act_bwd(dff, r['ff'], ACT_RELU, 1, rows, ffw, dbias=g(l.linear1.bias))
+    # ff is stored AFTER its dropout: ff > 0 <=> kept and ReLU-active, so the stored tensor is the whole mask and the
+    # dropout adjoint reduces to the 1/(1-p) factor
+    dzf = ops.act_bwd(dff, r['ff'], ACT_RELU, 1, rows, ffw, dbias=g(l.linear1.bias),
+                      dy_scale=1.0 / (1.0 - dp[4][1]) if dp[4] is not None else 1.0)
     dx2 = self.linear_bwd(dzf, r['x2b'], g(l.linear1.weight), packed(l.linear1.weight, 'linear_t'), ffw, d, res=dt3)
     # x2 = LN2(t2), t2 = x1 + out_proj(ca), ca = mha(q2(x1b), kv)
     dt2 = ops.layernorm_bwd(dx2, r['t2'], m2, r2, l.norm2.weight, g(l.norm2.weight), g(l.norm2.bias))
     mh = l.multihead_attn
-    dz = ops.act_bwd(dt2, None, ACT_NONE, 1, rows, d, layout=2, dbias=g(mh.out_proj.bias))
+    dz = ops.act_bwd(dt2, None, ACT_NONE, 1, rows, d, layout=2, dbias=g(mh.out_proj.bias), drop=dp[3])
     dca = self.linear_bwd(dz, r['ca'], g(mh.out_proj.weight), packed(mh.out_proj.weight, 'linear_t'), d, d,
                           out_f32=False)
     kv = r['kv']
@@ -601,7 +607,7 @@ class Backward:
     dkv = torch.empty_like(kv)
     ops.small_mha_bwd(r['q2'], kv, kv, dca, dq2, dkv, dkv, b, heads, nq, n_mem, hd, (nq * d, d), (n_mem * 2 * d, 2 * d),
                       (n_mem * 2 * d, 2 * d), (nq * d, d), (n_mem * 2 * d, 2 * d), (n_mem * 2 * d, 2 * d),
-                      offs=(0, 0, d, 0, 0, d))
+                      offs=(0, 0, d, 0, 0, d), drop=dp[2])
     # q projection (rows [0,d) of in_proj) and k/v projections (rows [d,3d)) of the cross attention
     ipw, ipb = g(mh.in_proj_weight), g(mh.in_proj_bias)
     ops.act_bwd(dq2, None, ACT_NONE, 1, rows, d, dbias=ipb[:d], want_dz=False)
@@ -614,14 +620,14 @@ class Backward:
     # x1 = LN1(t1), t1 = x + out_proj(sa), sa = mha(qkv(xb))
     dt1 = ops.layernorm_bwd(dx1, r['t1'], m1, r1, l.norm1.weight, g(l.norm1.weight), g(l.norm1.bias))
     sa = l.self_attn
-    dz = ops.act_bwd(dt1, None, ACT_NONE, 1, rows, d, layout=2, dbias=g(sa.out_proj.bias))
+    dz = ops.act_bwd(dt1, None, ACT_NONE, 1, rows, d, layout=2, dbias=g(sa.out_proj.bias), drop=dp[1])
     dsa = self.linear_bwd(dz, r['sa'], g(sa.out_proj.weight), packed(sa.out_proj.weight, 'linear_t'), d, d,
                           out_f32=False)
     qkv = r['qkv']
     dqkv = torch.empty_like(qkv)
     s3 = (nq * 3 * d, 3 * d)
     ops.small_mha_bwd(qkv, qkv, qkv, dsa, dqkv, dqkv, dqkv, b, heads, nq, nq, hd, s3, s3, s3, s3, s3, s3,
-                      offs=(0, d, 2 * d, 0, d, 2 * d))
+                      offs=(0, d, 2 * d, 0, d, 2 * d), drop=dp[0])
     ops.act_bwd(dqkv, None, ACT_NONE, 1, rows, 3 * d, dbias=g(sa.in_proj_bias), want_dz=False)
     dx = self.linear_bwd(dqkv, r['xb'], g(sa.in_proj_weight), packed(sa.in_proj_weight, 'linear_t'), 3 * d, d, res=dt1)
     self.G[id(r['x_in'])] = dx

@@ -66,6 +66,13 @@ typedef struct {
   int act_n_limit;    /* activation applies to channels < act_n_limit (0 = all) */
   float* stat_sum;    /* optional per-channel sum / sum of squares of the raw accumulator (BatchNorm batch stats) */
   float* stat_sq;
+  /* training-mode dropout on the output (nn.Dropout of transfuser.py:379,395 and of nn.TransformerDecoderLayer,
+   * model.py:137-140), applied AFTER the activation and BEFORE the residuals are added:
+   * out = drop(act(scale*acc+shift)) + res1 + res2.  drop_rng = device pointer to {seed, step} (2 x uint64) or NULL;
+   * the word of output element e (offset in elements from `out`) comes from Philox4x32-10, see tfpp_dropout. */
+  const unsigned long long* drop_rng;
+  float drop_p;
+  unsigned drop_site;
 } tfpp_conv_gemm_args;
 
 int tfpp_conv_gemm(const tfpp_conv_gemm_args* args, tfpp_stream_t stream);
@@ -263,6 +270,37 @@ int tfpp_planner_head_bwd(const float* joined, const float* target_point, const 
                           float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, float* dw_dec, float* db_dec,
                           float* dw_ts0, float* db_ts0, float* dw_ts1, float* db_ts1, int batch, int n_wp, int d_model,
                           int hidden, int n_speed, tfpp_stream_t stream);
+
+/* ---- dropout (training mode; embd_pdrop / attn_pdrop / resid_pdrop = 0.1, config.py:364-366; decoder 0.1) -----------
+ * Counter-based: element i of dropout site `site` is dropped iff word (i % 4) of
+ * Philox4x32-10(counter = (i / 4 lo, i / 4 hi, site, step), key = seed) < p * 2^32, kept elements are scaled by
+ * 1 / (1 - p).  rng = device pointer to {seed, step} (uint64 each; the caller bumps step once per training forward,
+ * also inside a CUDA graph).  No mask is stored: backward kernels regenerate it.  rng == NULL or p == 0: identity.
+ * In place over x (n elements, f32 or bf16): GPT.drop on pos_emb + tokens (transfuser.py:325) and its adjoint. */
+int tfpp_dropout(void* x, int x_f32, long long n, const unsigned long long* rng, float p, unsigned site,
+                 tfpp_stream_t stream);
+/* tfpp_act_bwd with the mask of an output dropout multiplied in: dz = drop_mask(e) * dy_scale * dy * act'(y) where e is
+ * the element offset pixel * channels + c (layouts 0 and 2). */
+int tfpp_act_bwd_dropout(const void* dy, const void* y, int layout, int act, int act_n_limit, float dy_scale, void* dz,
+                         float* dbias, int batch, int hw, int channels, int channels_padded,
+                         const unsigned long long* rng, float p, unsigned site, tfpp_stream_t stream);
+/* attention cores with dropout on the softmax probabilities (transfuser.py:374; nn.MultiheadAttention(dropout=0.1));
+ * element index of P[b, h, q, k] = ((b * heads + h) * Tq + q) * Tk + k. */
+int tfpp_fusion_attn_dropout(const void* qkv, void* out, int batch, int tokens, int channels, int heads,
+                             const unsigned long long* rng, float p, unsigned site, tfpp_stream_t stream);
+int tfpp_fusion_attn_bwd_dropout(const void* qkv, const void* dout, void* dqkv, float* dkv_ws, int batch, int tokens,
+                                 int channels, int heads, const unsigned long long* rng, float p, unsigned site,
+                                 tfpp_stream_t stream);
+int tfpp_small_mha_dropout(const void* q, long long q_sb, long long q_sr, const void* k, long long k_sb, long long k_sr,
+                           const void* v, long long v_sb, long long v_sr, void* out, long long o_sb, long long o_sr,
+                           int batch, int heads, int tq, int tk, int head_dim, const unsigned long long* rng, float p,
+                           unsigned site, tfpp_stream_t stream);
+int tfpp_small_mha_bwd_dropout(const void* q, long long q_sb, long long q_sr, const void* k, long long k_sb,
+                               long long k_sr, const void* v, long long v_sb, long long v_sr, const void* dout,
+                               long long o_sb, long long o_sr, void* dq, long long dq_sb, long long dq_sr, void* dk,
+                               long long dk_sb, long long dk_sr, void* dv, long long dv_sb, long long dv_sr,
+                               int accumulate_kv, int batch, int heads, int tq, int tk, int head_dim,
+                               const unsigned long long* rng, float p, unsigned site, tfpp_stream_t stream);
 
 /* fused losses (model.py:394-445, center_net.py:77-123): scalar loss sums + d(weighted loss)/d(pre-activation).
  * The gradient outputs (dz*, dbias, dlogits/dcp excepted) may be NULL: loss values only.  w_dev / w2_dev (nullable):

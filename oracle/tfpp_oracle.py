@@ -127,8 +127,14 @@ def regnet_stage(sd, p, x, training):
 # ---------------------------------------------------------------------------------------------------------------
 # a5  GPT fusion transformer  (transfuser.py:301-402)
 # ---------------------------------------------------------------------------------------------------------------
-def self_attention(sd, p, x, n_head):
-  """transfuser.py:362-380 (dropout = identity: parity runs use p = 0 / eval)."""
+def _drop(dropout, t, pdrop):
+  """A dropout site.  ``dropout`` is None (eval / parity runs without dropout) or a callable (tensor, p) -> tensor that
+  applies the site's mask, e.g. oracle.philox.DropoutStream, which reproduces the engine's counter-based masks."""
+  return t if dropout is None else dropout(t, pdrop)
+
+
+def self_attention(sd, p, x, n_head, dropout=None, attn_pdrop=0.1, resid_pdrop=0.1):
+  """transfuser.py:362-380; attn_drop on the probabilities (:374), resid_drop on the projection (:379)."""
   b, t, c = x.shape
   hd = c // n_head
   k = F.linear(x, sd[p + '.key.weight'], sd[p + '.key.bias']).view(b, t, n_head, hd).transpose(1, 2)
@@ -136,29 +142,31 @@ def self_attention(sd, p, x, n_head):
   v = F.linear(x, sd[p + '.value.weight'], sd[p + '.value.bias']).view(b, t, n_head, hd).transpose(1, 2)
   att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(hd))
   att = F.softmax(att, dim=-1)
+  att = _drop(dropout, att, attn_pdrop)
   y = (att @ v).transpose(1, 2).contiguous().view(b, t, c)
-  return F.linear(y, sd[p + '.proj.weight'], sd[p + '.proj.bias'])
+  return _drop(dropout, F.linear(y, sd[p + '.proj.weight'], sd[p + '.proj.bias']), resid_pdrop)
 
 
-def gpt_block(sd, p, x, n_head):
-  """transfuser.py:398-402."""
+def gpt_block(sd, p, x, n_head, dropout=None, attn_pdrop=0.1, resid_pdrop=0.1):
+  """transfuser.py:383-402 (nn.Dropout(resid_pdrop) closes the MLP, :395)."""
   c = x.shape[-1]
   h = F.layer_norm(x, (c,), sd[p + '.ln1.weight'], sd[p + '.ln1.bias'], 1e-5)
-  x = x + self_attention(sd, p + '.attn', h, n_head)
+  x = x + self_attention(sd, p + '.attn', h, n_head, dropout, attn_pdrop, resid_pdrop)
   h = F.layer_norm(x, (c,), sd[p + '.ln2.weight'], sd[p + '.ln2.bias'], 1e-5)
   h = F.relu(F.linear(h, sd[p + '.mlp.0.weight'], sd[p + '.mlp.0.bias']))
-  return x + F.linear(h, sd[p + '.mlp.2.weight'], sd[p + '.mlp.2.bias'])
+  return x + _drop(dropout, F.linear(h, sd[p + '.mlp.2.weight'], sd[p + '.mlp.2.bias']), resid_pdrop)
 
 
-def gpt(sd, p, image_tensor, lidar_tensor, cfg):
-  """transfuser.py:301-339, non-video branch."""
+def gpt(sd, p, image_tensor, lidar_tensor, cfg, dropout=None):
+  """transfuser.py:301-339, non-video branch; self.drop on pos_emb + tokens (:325)."""
   bz, c, img_h, img_w = image_tensor.shape
   lidar_h, lidar_w = lidar_tensor.shape[2:4]
   it = image_tensor.permute(0, 2, 3, 1).contiguous().view(bz, -1, c)
   lt = lidar_tensor.permute(0, 2, 3, 1).contiguous().view(bz, -1, c)
-  x = sd[p + '.pos_emb'] + torch.cat((it, lt), dim=1)
+  x = _drop(dropout, sd[p + '.pos_emb'] + torch.cat((it, lt), dim=1), cfg.get('embd_pdrop', 0.1))
   for l in range(cfg['n_layer']):
-    x = gpt_block(sd, p + f'.blocks.{l}', x, cfg['n_head'])
+    x = gpt_block(sd, p + f'.blocks.{l}', x, cfg['n_head'], dropout, cfg.get('attn_pdrop', 0.1),
+                  cfg.get('resid_pdrop', 0.1))
   x = F.layer_norm(x, (c,), sd[p + '.ln_f.weight'], sd[p + '.ln_f.bias'], 1e-5)
   n_img = img_h * img_w
   img_out = x[:, :n_img].view(bz, img_h, img_w, -1).permute(0, 3, 1, 2).contiguous()
@@ -166,19 +174,19 @@ def gpt(sd, p, image_tensor, lidar_tensor, cfg):
   return img_out, lid_out
 
 
-def fuse_features(sd, p, image_features, lidar_features, i, cfg):
+def fuse_features(sd, p, image_features, lidar_features, i, cfg, dropout=None):
   """transfuser.py:222-257."""
   img_e = F.adaptive_avg_pool2d(image_features, (cfg['img_vert_anchors'], cfg['img_horz_anchors']))
   lid_e = F.adaptive_avg_pool2d(lidar_features, (cfg['lidar_vert_anchors'], cfg['lidar_horz_anchors']))
   lid_e = F.conv2d(lid_e, sd[p + f'.lidar_channel_to_img.{i}.weight'], sd[p + f'.lidar_channel_to_img.{i}.bias'])
-  img_l, lid_l = gpt(sd, p + f'.transformers.{i}', img_e, lid_e, cfg)
+  img_l, lid_l = gpt(sd, p + f'.transformers.{i}', img_e, lid_e, cfg, dropout)
   lid_l = F.conv2d(lid_l, sd[p + f'.img_channel_to_lidar.{i}.weight'], sd[p + f'.img_channel_to_lidar.{i}.bias'])
   img_l = F.interpolate(img_l, size=image_features.shape[2:], mode='bilinear', align_corners=False)
   lid_l = F.interpolate(lid_l, size=lidar_features.shape[2:], mode='bilinear', align_corners=False)
   return image_features + img_l, lidar_features + lid_l
 
 
-def backbone_forward(sd, image, lidar, cfg, training=False, p='backbone', taps=None):
+def backbone_forward(sd, image, lidar, cfg, training=False, p='backbone', taps=None, dropout=None):
   """TransfuserBackbone.forward, transfuser.py:139-205 (transformer_decoder_join, detect_boxes, use_semantic)."""
   x_img = normalize_imagenet(image)
   x_lid = lidar
@@ -191,7 +199,7 @@ def backbone_forward(sd, image, lidar, cfg, training=False, p='backbone', taps=N
     x_lid = regnet_stage(sd, p + f'.lidar_encoder.s{i + 1}', x_lid, training)
     if taps is not None:
       taps[f'img_s{i + 1}_pre'], taps[f'lid_s{i + 1}_pre'] = x_img, x_lid
-    x_img, x_lid = fuse_features(sd, p, x_img, x_lid, i, cfg)
+    x_img, x_lid = fuse_features(sd, p, x_img, x_lid, i, cfg, dropout)
     if taps is not None:
       taps[f'img_s{i + 1}'], taps[f'lid_s{i + 1}'] = x_img, x_lid
   # top_down, transfuser.py:131-137
@@ -225,8 +233,9 @@ def position_embedding_sine(bs, h, w, num_pos_feats=128, temperature=10000, scal
   return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
 
 
-def _mha(sd, p, q_in, kv_in, n_head):
-  """torch.nn.MultiheadAttention (batch_first, no masks, dropout off) from its in_proj/out_proj parameters."""
+def _mha(sd, p, q_in, kv_in, n_head, dropout=None, pdrop=0.1):
+  """torch.nn.MultiheadAttention (batch_first, no masks; dropout on the attention weights) from its in_proj/out_proj
+  parameters."""
   d = q_in.shape[-1]
   w, b = sd[p + '.in_proj_weight'], sd[p + '.in_proj_bias']
   q = F.linear(q_in, w[:d], b[:d])
@@ -238,12 +247,12 @@ def _mha(sd, p, q_in, kv_in, n_head):
   q = q.view(bs, tq, n_head, hd).transpose(1, 2)
   k = k.view(bs, tk, n_head, hd).transpose(1, 2)
   v = v.view(bs, tk, n_head, hd).transpose(1, 2)
-  att = F.softmax((q @ k.transpose(-2, -1)) / math.sqrt(hd), dim=-1)
+  att = _drop(dropout, F.softmax((q @ k.transpose(-2, -1)) / math.sqrt(hd), dim=-1), pdrop)
   y = (att @ v).transpose(1, 2).reshape(bs, tq, d)
   return F.linear(y, sd[p + '.out_proj.weight'], sd[p + '.out_proj.bias'])
 
 
-def decoder_layer(sd, p, x, mem, n_head, activation='relu'):
+def decoder_layer(sd, p, x, mem, n_head, activation='relu', dropout=None, pdrop=0.1):
   """nn.TransformerDecoderLayer(d, heads, activation=nn.GELU(), batch_first, norm_first=False), model.py:137-143.
 
   OBSERVED BEHAVIOUR (run here, torch 2.11, and by code inspection identical in the pinned torch 1.12.1): the
@@ -255,11 +264,14 @@ def decoder_layer(sd, p, x, mem, n_head, activation='relu'):
   option for a torch that fixes the quirk."""
   d = x.shape[-1]
   act = F.relu if activation == 'relu' else F.gelu
-  x = F.layer_norm(x + _mha(sd, p + '.self_attn', x, x, n_head), (d,), sd[p + '.norm1.weight'], sd[p + '.norm1.bias'])
-  x = F.layer_norm(x + _mha(sd, p + '.multihead_attn', x, mem, n_head), (d,), sd[p + '.norm2.weight'],
-                   sd[p + '.norm2.bias'])
-  h = F.linear(act(F.linear(x, sd[p + '.linear1.weight'], sd[p + '.linear1.bias'])), sd[p + '.linear2.weight'],
-               sd[p + '.linear2.bias'])
+  # torch TransformerDecoderLayer (norm_first=False): x = norm1(x + dropout1(sa)); x = norm2(x + dropout2(mha));
+  # x = norm3(x + dropout3(linear2(dropout(act(linear1(x)))))); the two attentions drop their probabilities too
+  sa = _drop(dropout, _mha(sd, p + '.self_attn', x, x, n_head, dropout, pdrop), pdrop)
+  x = F.layer_norm(x + sa, (d,), sd[p + '.norm1.weight'], sd[p + '.norm1.bias'])
+  ca = _drop(dropout, _mha(sd, p + '.multihead_attn', x, mem, n_head, dropout, pdrop), pdrop)
+  x = F.layer_norm(x + ca, (d,), sd[p + '.norm2.weight'], sd[p + '.norm2.bias'])
+  h = _drop(dropout, act(F.linear(x, sd[p + '.linear1.weight'], sd[p + '.linear1.bias'])), pdrop)
+  h = _drop(dropout, F.linear(h, sd[p + '.linear2.weight'], sd[p + '.linear2.bias']), pdrop)
   return F.layer_norm(x + h, (d,), sd[p + '.norm3.weight'], sd[p + '.norm3.bias'])
 
 
@@ -308,7 +320,7 @@ def center_net_head(sd, p, feat):
           head('yaw_res_head'), None, None)
 
 
-def planner(sd, fused, target_point, ego_vel, command, cfg=None, training=False, taps=None):
+def planner(sd, fused, target_point, ego_vel, command, cfg=None, training=False, taps=None, dropout=None):
   """model.py:299-358: change_channel + sine position encoding -> 64 memory tokens, extra-sensor token, 6-layer decoder
   over the 11 learned queries, GRU checkpoints + target-speed logits.  Returns (pred_checkpoint, pred_target_speed)."""
   cfg = cfg or DEFAULT_CFG
@@ -331,7 +343,8 @@ def planner(sd, fused, target_point, ego_vel, command, cfg=None, training=False,
   # model.py:352  nn.TransformerDecoder + final norm
   x = sd['checkpoint_query'].repeat(bs, 1, 1)
   for l in range(cfg['num_transformer_decoder_layers']):
-    x = decoder_layer(sd, f'join.layers.{l}', x, mem, cfg['num_decoder_heads'], cfg.get('decoder_activation', 'relu'))
+    x = decoder_layer(sd, f'join.layers.{l}', x, mem, cfg['num_decoder_heads'], cfg.get('decoder_activation', 'relu'),
+                      dropout, cfg.get('decoder_pdrop', 0.1))
   x = F.layer_norm(x, (x.shape[-1],), sd['join.norm.weight'], sd['join.norm.bias'])
   if taps is not None:
     taps['joined'] = x
@@ -344,17 +357,18 @@ def planner(sd, fused, target_point, ego_vel, command, cfg=None, training=False,
   return pred_checkpoint, pred_target_speed
 
 
-def forward(sd, rgb, lidar_bev, target_point, ego_vel, command, cfg=None, training=False, taps=None):
+def forward(sd, rgb, lidar_bev, target_point, ego_vel, command, cfg=None, training=False, taps=None, dropout=None):
   """LidarCenterNet.forward, model.py:279-392, default GlobalConfig (transFuser backbone, decoder join, all aux
   heads).  Returns the reference's 10-tuple."""
   cfg = cfg or DEFAULT_CFG
   sd = {k: v.float() if torch.is_floating_point(v) else v for k, v in sd.items()}
   bs = rgb.shape[0]
-  bev_feature_grid, fused, image_feature_grid = backbone_forward(sd, rgb, lidar_bev, cfg, training, taps=taps)
+  bev_feature_grid, fused, image_feature_grid = backbone_forward(sd, rgb, lidar_bev, cfg, training, taps=taps,
+                                                                 dropout=dropout)
   if taps is not None:
     taps['bev_feature_grid'], taps['fused_features'], taps['image_feature_grid'] = (bev_feature_grid, fused,
                                                                                     image_feature_grid)
-  pred_checkpoint, pred_target_speed = planner(sd, fused, target_point, ego_vel, command, cfg, training, taps)
+  pred_checkpoint, pred_target_speed = planner(sd, fused, target_point, ego_vel, command, cfg, training, taps, dropout)
   # model.py:372-389
   pred_semantic = perspective_decoder(sd, 'semantic_decoder', image_feature_grid, cfg)
   pred_depth = torch.sigmoid(perspective_decoder(sd, 'depth_decoder', image_feature_grid, cfg)).squeeze(1)

@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 
+# Golden vectors and oracle comparisons are dropout-free (masks cannot match torch's generator); the dropout path has
+# its own tests (tests/test_dropout_gpu.py) that switch it on per engine and feed the same masks to the oracle.
+os.environ.setdefault('TFPP_DROPOUT', '0')
+
+
 def pytest_configure(config):
   config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
   config.addinivalue_line('markers', 'reference: needs /root/reference (build container only)')

@@ -371,61 +371,83 @@ def _to_dev(ops, t):
   return ops.nchw_to_nhwc(t.detach().float().cuda().contiguous())
 
 
+def q(t):
+  """bf16 storage rounding with a straight-through gradient: the reference keeps the values the kernels actually store
+  (bf16 weights packs, bf16 feature maps), so ReLU masks agree and the comparison isolates the arithmetic."""
+  return t + (t.to(torch.bfloat16).float() - t).detach()
+
+
+def conv_q(x, conv, act=True, store=True):
+  y = F.conv2d(x, q(conv.weight), conv.bias, padding=conv.padding)
+  y = F.relu(y) if act else y
+  return q(y) if store else y
+
+
+def up_q(x, **kw):
+  return q(F.interpolate(x, mode='bilinear', align_corners=False, **kw))
+
+
+def _swap_grads(mods, st, fn):
+  """Run torch autograd (fn) with fresh .grad tensors on the modules' parameters, return them as {id(p): grad}, then point
+  .grad back at the Trainer's flat gradient views."""
+  ps = [p for mod in mods for p in mod.parameters()]
+  for p in ps:
+    p.grad = None
+  fn()
+  want = {id(p): p.grad.clone() for p in ps}
+  for p in ps:
+    p.grad = st.g(p)
+  return want
+
+
 def test_center_head_forward_backward(ops, trainer):
   """LidarCenterNetHead (center_net.py:49-75) as one N=320 3x3 GEMM + block-diagonal 1x1 GEMM, and its backward, vs the
-  five nn.Sequential heads run by torch (fp32) on the same bf16-rounded input."""
+  five nn.Sequential heads run by torch (fp32 accumulate) on the same bf16 operands."""
   from carla_garage_b200.training import Backward
   net, eng, st = trainer.model, trainer.eng, trainer.st
   head = net.head
   feat = bf(rnd(2, 64, 64, 64, seed=43)).float().requires_grad_(True)
   names = head.head_names()
-  ref = torch.cat([getattr(head, n)(feat) for n in names], 1)
-  ref_out = ref.clone()
+  seqs = [getattr(head, n) for n in names]
+  ref = torch.cat([conv_q(conv_q(feat, sq[0]), sq[2], act=False, store=False) for sq in seqs], 1)
   ref_out = torch.cat([torch.sigmoid(ref[:, :4]), ref[:, 4:]], 1)
-  st.zero_grad()
   eng.tape = []
   try:
     xd = _to_dev(ops, feat)
     bb = eng.center_head_forward(xd)
     maps = bb[0]._base  # pylint: disable=protected-access
-    assert rel(maps, ref_out) < 1e-2
-    dz = bf(rnd(2, 64, 64, 24, seed=44, scale=0.1))
-    dz[..., 21:] = 0
     tape = eng.tape
   finally:
     eng.tape = None
-  for p in head.parameters():
-    p.grad = None
-  ref.backward(dz.float()[..., :21].permute(0, 3, 1, 2))
-  want = {n: p.grad.clone() for n, p in head.named_parameters()}
-  want_dx = feat.grad.clone()
-  for n, p in head.named_parameters():  # torch replaced .grad: point it back at the flat buffer view
-    p.grad = st.g(p)
+  assert rel(maps, ref_out) < 2e-3
+  dz = bf(rnd(2, 64, 64, 24, seed=44, scale=0.1))
+  dz[..., 21:] = 0
+  want = _swap_grads(seqs, st, lambda: ref.backward(dz.float()[..., :21].permute(0, 3, 1, 2)))
   st.zero_grad()
   # the loss kernel normally accumulates the 1x1 bias gradients; do it here
-  st.g_span(getattr(head, names[0])[2].bias, getattr(head, names[-1])[2].bias).add_(dz.float().sum((0, 1, 2))[:21])
+  st.g_span(seqs[0][2].bias, seqs[-1][2].bias).add_(dz.float().sum((0, 1, 2))[:21])
   bw = Backward(eng, st)
   bw.run(tape, {'center': dz})
   torch.cuda.synchronize()
-  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), want_dx) < 1e-2
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), feat.grad) < 1e-2
   for n, p in head.named_parameters():
-    assert rel(st.g(p), want[n]) < 1e-2, n
+    assert rel(st.g(p), want[id(p)]) < 1e-2, n
 
 
 def test_fpn_top_down_and_bev_decoder(ops, trainer):
   """top_down (transfuser.py:131-137) + bev_semantic_decoder (model.py:75-90,383-385) forward and backward vs torch."""
+  from carla_garage_b200.engine import packed
   from carla_garage_b200.training import Backward
   net, eng, st = trainer.model, trainer.eng, trainer.st
   bb = net.backbone
   x = bf(rnd(2, 1512, 8, 8, seed=45)).float().requires_grad_(True)
-  p5 = F.relu(bb.c5_conv(x))
-  p4 = F.relu(bb.up_conv5(F.interpolate(p5, scale_factor=2, mode='bilinear', align_corners=False)))
-  p3 = F.relu(bb.up_conv4(F.interpolate(p4, size=(64, 64), mode='bilinear', align_corners=False)))
+  p5 = conv_q(x, bb.c5_conv)
+  p4 = conv_q(up_q(p5, scale_factor=2), bb.up_conv5)
+  p3 = conv_q(up_q(p4, size=(64, 64)), bb.up_conv4)
   dec = net.bev_semantic_decoder
-  t = dec[2](F.relu(dec[0](p3)))
+  t = conv_q(conv_q(p3, dec[0]), dec[2], act=False)
   ref = F.interpolate(t, size=(256, 256), mode='bilinear', align_corners=False) * net.valid_bev_pixels
   mods = [bb.c5_conv, bb.up_conv5, bb.up_conv4, dec[0], dec[2]]
-  st.zero_grad()
   eng.tape = []
   try:
     xd = _to_dev(ops, x)
@@ -440,33 +462,24 @@ def test_fpn_top_down_and_bev_decoder(ops, trainer):
     feats = eng.conv_bias(q4u, bb.up_conv4, ops.ACT_RELU)
     y = eng.conv_bias(feats, dec[0], ops.ACT_RELU)
     y = eng.conv_bias(y, dec[2])
-    from carla_garage_b200.engine import packed
     out = ops.bilinear_nchw_mask(y, 11, cfg.lidar_resolution_height, cfg.lidar_resolution_width,
                                  packed(net.valid_bev_pixels, 'f32'))
     eng._save(op='bev_tail', src=y, out=out, ncls=11)  # pylint: disable=protected-access
     tape = eng.tape
   finally:
     eng.tape = None
-  assert rel(ops.nhwc_to_nchw(feats), p3) < 1e-2
-  assert rel(out, ref) < 1.5e-2
+  assert rel(ops.nhwc_to_nchw(feats), p3) < 3e-3
+  assert rel(out, ref) < 3e-3
   dout = rnd(2, 11, 256, 256, seed=46, scale=1e-3)
-  for mod in mods:
-    for p in mod.parameters():
-      p.grad = None
-  ref.backward(dout)
-  want = {id(p): p.grad.clone() for mod in mods for p in mod.parameters()}
-  want_dx = x.grad.clone()
-  for mod in mods:
-    for p in mod.parameters():
-      p.grad = st.g(p)
+  want = _swap_grads(mods, st, lambda: ref.backward(dout))
   st.zero_grad()
   bw = Backward(eng, st)
   bw.run(tape, {'bev': dout})
   torch.cuda.synchronize()
-  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), want_dx) < 2e-2
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), x.grad) < 1.5e-2
   for mod in mods:
     for p in mod.parameters():
-      assert rel(st.g(p), want[id(p)]) < 2e-2, tuple(p.shape)
+      assert rel(st.g(p), want[id(p)]) < 1.5e-2, tuple(p.shape)
 
 
 @pytest.mark.parametrize('which', ['semantic', 'depth'])
@@ -476,13 +489,12 @@ def test_perspective_decoder_forward_backward(ops, trainer, which):
   net, eng, st = trainer.model, trainer.eng, trainer.st
   dec = net.semantic_decoder if which == 'semantic' else net.depth_decoder
   x = bf(rnd(1, 1512, 4, 16, seed=47)).float().requires_grad_(True)
-  t = dec.deconv1(x)
-  t = F.interpolate(t, scale_factor=dec.scale_factor_0, mode='bilinear', align_corners=False)
-  t = dec.deconv2(t)
-  t = F.interpolate(t, scale_factor=dec.scale_factor_1, mode='bilinear', align_corners=False)
-  z = dec.deconv3(t)
+  t = conv_q(conv_q(x, dec.deconv1[0]), dec.deconv1[2])
+  t = up_q(t, scale_factor=dec.scale_factor_0)
+  t = conv_q(conv_q(t, dec.deconv2[0]), dec.deconv2[2])
+  t = up_q(t, scale_factor=dec.scale_factor_1)
+  z = conv_q(conv_q(t, dec.deconv3[0]), dec.deconv3[2], act=False, store=False)
   ref = torch.sigmoid(z) if which == 'depth' else z
-  st.zero_grad()
   eng.tape = []
   try:
     xd = _to_dev(ops, x)
@@ -490,25 +502,20 @@ def test_perspective_decoder_forward_backward(ops, trainer, which):
     tape = eng.tape
   finally:
     eng.tape = None
-  assert rel(out, ref) < 1.5e-2
+  assert rel(out, ref) < 3e-3
   c = z.shape[1]
   dzs = bf(rnd(1, z.shape[2], z.shape[3], 16, seed=48, scale=1e-2))
   dzs[..., c:] = 0
-  for p in dec.parameters():
-    p.grad = None
-  z.backward(dzs.float()[..., :c].permute(0, 3, 1, 2))
-  want = {n: p.grad.clone() for n, p in dec.named_parameters()}
-  want_dx = x.grad.clone()
-  for p in dec.parameters():
-    p.grad = st.g(p)
+  mods = [dec.deconv1, dec.deconv2, dec.deconv3]
+  want = _swap_grads(mods, st, lambda: z.backward(dzs.float()[..., :c].permute(0, 3, 1, 2)))
   st.zero_grad()
   st.g(dec.deconv3[2].bias).add_(dzs.float().sum((0, 1, 2))[:c])  # normally accumulated by the loss kernel
   bw = Backward(eng, st)
   bw.run(tape, {which: dzs})
   torch.cuda.synchronize()
-  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), want_dx) < 2e-2
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), x.grad) < 2e-2
   for n, p in dec.named_parameters():
-    assert rel(st.g(p), want[n]) < 2e-2, n
+    assert rel(st.g(p), want[id(p)]) < 2e-2, n
 
 
 def test_planner_forward_backward(ops, trainer, oracle_state):
@@ -518,8 +525,10 @@ def test_planner_forward_backward(ops, trainer, oracle_state):
   from oracle import tfpp_oracle as orc
   net, eng, st = trainer.model, trainer.eng, trainer.st
   net.load_state_dict(oracle_state, strict=True)
-  sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v)
-        for k, v in oracle_state.items()}
+  # the oracle multiplies the bf16-rounded weight matrices the kernels multiply (biases / norms / queries stay fp32)
+  gemm = lambda k, v: v.dim() >= 2 and k.startswith(('join.', 'change_channel'))  # the tcgen05 GEMM operands
+  sd = {k: ((v.to(torch.bfloat16).float() if gemm(k, v) else v.clone()).requires_grad_(True)
+            if v.is_floating_point() and 'running' not in k else v) for k, v in oracle_state.items()}
   b = 4
   g = torch.Generator().manual_seed(49)
   fused = bf(torch.randn(b, 1512, 8, 8, generator=g)).float().requires_grad_(True)
@@ -542,7 +551,7 @@ def test_planner_forward_backward(ops, trainer, oracle_state):
   bw = Backward(eng, st)
   bw.run(tape, {'planner': (dcp.cuda(), dts.cuda())})
   torch.cuda.synchronize()
-  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), fused.grad) < 3e-2
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), fused.grad) < 5e-2
   params = dict(net.named_parameters())
   names = [n for n in sd if n.startswith(('join.', 'change_channel', 'checkpoint_', 'target_speed_network',
                                           'extra_sensor_')) and sd[n].is_floating_point() and sd[n].grad is not None]
@@ -551,7 +560,7 @@ def test_planner_forward_backward(ops, trainer, oracle_state):
   for n in names:
     e = rel(params[n].grad, sd[n].grad)
     worst = max(worst, e)
-    assert e < 5e-2, (n, e)
+    assert e < 6e-2, (n, e)
   print(f'  planner backward: {len(names)} parameter gradients, worst rel err {worst:.2e}')
   net.load_state_dict(oracle_state, strict=True)
 

@@ -111,3 +111,21 @@ def test_oracle_vs_live_reference(oracle_state):
   pts = synth.make_point_clouds(1, seed=3).numpy()[0]
   for gp in (False, True):
     assert np.array_equal(orc.lidar_to_histogram_features(pts, gp), net.data.lidar_to_histogram_features(pts, gp))
+
+
+def test_philox_known_answers():
+  """oracle/philox.py against the Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors)."""
+  from oracle import philox as ph
+  kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+         ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+         ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+          (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+  for ctr, key, want in kat:
+    got = ph.philox4x32_10([ctr[0]], [ctr[1]], [ctr[2]], [ctr[3]], key[0], key[1])
+    assert tuple(int(w[0]) for w in got) == want
+  m = ph.multiplier((3, 1000), 0.1, 1234, 1, 3)
+  assert abs(float((m == 0).float().mean()) - 0.1) < 0.02 and abs(float(m.max()) - 1 / 0.9) < 1e-6
+  import torch
+  t = torch.ones(2, 8)
+  s1, s2 = ph.DropoutStream(5, 1), ph.DropoutStream(5, 1)
+  assert torch.equal(s1(t, 0.5), s2(t, 0.5)) and s1.site == 1 and torch.equal(s1(t, 0.0), t) and s1.site == 1
