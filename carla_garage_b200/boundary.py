@@ -27,7 +27,7 @@ from . import engine as eng_mod
 from . import ops
 from . import training
 from .ops import ACT_NONE, ACT_SIGMOID, BF16, F32
-from .training import LOSS_KEYS
+from .training import loss_keys
 
 
 class TrainBoundary:
@@ -81,7 +81,12 @@ class TrainBoundary:
   # ------------------------------------------------------------------------------------------------ forward
   def forward(self, rgb, lidar_bev, target_point, ego_vel, command):
     ps = tuple(p for p in self.st.params if p.requires_grad)
-    ts, cp, sem, bev, depth, maps = _Step.apply(self, rgb, lidar_bev, target_point, ego_vel, command, *ps)
+    outs = _Step.apply(self, rgb, lidar_bev, target_point, ego_vel, command, *ps)
+    cfg = self.model.config
+    it = iter(outs)
+    ts, cp = (next(it), next(it)) if cfg.use_controller_input_prediction else (None, None)
+    sem, bev, depth, maps = next(it), next(it), next(it), next(it)
+    wp = next(it) if cfg.use_wp_gru else None
     head = self.model.head
     sizes = [getattr(head, n)[2].weight.shape[0] for n in head.head_names()]
     views, o = [], 0
@@ -89,13 +94,13 @@ class TrainBoundary:
       views.append(maps[:, o:o + s])
       o += s
     bb = (views[0], views[1], views[2], views[3], views[4], None, None)
-    return (None, ts, cp, sem, bev, depth.squeeze(1), bb, None, None, None)
+    return (wp, ts, cp, sem, bev, depth.squeeze(1), bb, None, None, None)
 
   def seeds_from(self, tape_out, gouts):
     """Seed gradients for training.Backward from what autograd delivered (+ what _Loss.backward parked)."""
     st, m = self.st, self.model
-    ts, cp, sem, bev, depth, maps = tape_out
-    g_ts, g_cp, g_sem, g_bev, g_depth, g_maps = gouts
+    ts, cp, sem, bev, depth, maps, wp = tape_out
+    g_ts, g_cp, g_sem, g_bev, g_depth, g_maps, g_wp = gouts
     stash, self.stash = self.stash, None
     seeds = dict(stash['seeds']) if stash is not None else {}
     if stash is not None:  # bias gradients of the heads' last convs, computed by the loss kernels
@@ -103,8 +108,12 @@ class TrainBoundary:
       for k, v in stash['bias'].items():
         tgt[k].add_(v)
     real = lambda g: g is not None and not self.is_placeholder(g)
-    b = ts.shape[0]
-    if real(g_ts) or real(g_cp) or 'planner' not in seeds:
+    b = sem.shape[0]
+    if wp is not None and (real(g_wp) or 'planner_wp' not in seeds):
+      d0 = seeds.get('planner_wp', (None, None))[0]
+      dwp = g_wp.contiguous().float() if real(g_wp) else torch.zeros_like(wp)
+      seeds['planner_wp'] = (dwp + d0 if d0 is not None else dwp, None)
+    if ts is not None and (real(g_ts) or real(g_cp) or 'planner' not in seeds):
       dcp0, dl0 = seeds.get('planner', (None, None))
       dcp = g_cp.contiguous().float() if real(g_cp) else torch.zeros_like(cp)
       dl = g_ts.contiguous().float() if real(g_ts) else torch.zeros_like(ts)
@@ -146,11 +155,11 @@ class _Step(torch.autograd.Function):
     out, tape = bnd.with_plan(lambda: training.training_forward(eng, st, dict(
         rgb=rgb, lidar_bev=lidar_bev, target_point=target_point, ego_vel=ego_vel, command=command)))
     bnd.plan.finalize()
-    ts, cp, sem, bev = out[1], out[2], out[3], out[4]
+    wp, ts, cp, sem, bev = out[0], out[1], out[2], out[3], out[4]
     depth = training._base_of(out[5])  # (B,1,H,W)  pylint: disable=protected-access
     maps = training._base_of(out[6][0])  # (B,21,64,64)  pylint: disable=protected-access
-    ctx.bnd, ctx.tape, ctx.outs = bnd, tape, (ts, cp, sem, bev, depth, maps)
-    return ts, cp, sem, bev, depth, maps
+    ctx.bnd, ctx.tape, ctx.outs = bnd, tape, (ts, cp, sem, bev, depth, maps, wp)
+    return tuple(t for t in (ts, cp, sem, bev, depth, maps, wp) if t is not None)
 
   @staticmethod
   @torch.autograd.function.once_differentiable
@@ -160,7 +169,9 @@ class _Step(torch.autograd.Function):
     bnd.pick_grad_buffer()
     st.zero_grad()
     eng.new_arena(st.flat.device)
-    seeds = bnd.seeds_from(ctx.outs, gouts)
+    it = iter(gouts)
+    full = tuple(next(it) if t is not None else None for t in ctx.outs)   # gradients in (ts, cp, sem, bev, depth, maps, wp) slots
+    seeds = bnd.seeds_from(ctx.outs, full)
     # the tape is read-only for Backward: it stays on ctx (freed with the autograd graph) so that
     # loss.backward(retain_graph=True) followed by a second backward works like it does for torch modules
     bnd.with_plan(lambda: training.Backward(eng, st).run(ctx.tape, seeds))
@@ -173,12 +184,13 @@ class _Loss(torch.autograd.Function):
   training.LOSS_KEYS order as one (10,) tensor."""
 
   @staticmethod
-  def forward(ctx, eng, bnd, labels, ts, cp, sem, bev, depth, maps):
-    outputs = (None, ts, cp, sem, bev, depth, maps)
-    losses, _ = training.compute_losses(eng, outputs, labels, want_seeds=False)
-    ctx.eng, ctx.bnd, ctx.labels = eng, bnd, labels
-    ctx.save_for_backward(ts, cp, sem, bev, depth, maps)
-    return torch.stack([losses[k] for k in LOSS_KEYS])
+  def forward(ctx, eng, bnd, labels, present, *preds):
+    it = iter(preds)
+    ts, cp, sem, bev, depth, maps, wp = (next(it) if f else None for f in present)
+    losses, _ = training.compute_losses(eng, (wp, ts, cp, sem, bev, depth, maps), labels, want_seeds=False)
+    ctx.eng, ctx.bnd, ctx.labels, ctx.present = eng, bnd, labels, present
+    ctx.save_for_backward(*preds)
+    return torch.stack([losses[k] for k in loss_keys(eng.cfg)])
 
   @staticmethod
   @torch.autograd.function.once_differentiable
@@ -186,28 +198,32 @@ class _Loss(torch.autograd.Function):
     eng, bnd = ctx.eng, ctx.bnd
     if bnd is None:
       raise RuntimeError('compute_loss().backward() needs predictions produced by this model in training mode')
-    ts, cp, sem, bev, depth, maps = ctx.saved_tensors
-    dev = ts.device
+    it = iter(ctx.saved_tensors)
+    ts, cp, sem, bev, depth, maps, wp = (next(it) if f else None for f in ctx.present)
+    dev = sem.device
     bias = {'semantic': torch.zeros(sem.shape[1], dtype=F32, device=dev), 'depth': torch.zeros(1, dtype=F32, device=dev),
             'center': torch.zeros(maps.shape[1], dtype=F32, device=dev)}
     eng.new_arena(dev, 64)
-    _, seeds = training.compute_losses(eng, (None, ts, cp, sem, bev, depth, maps), ctx.labels, bias_grads=bias,
+    _, seeds = training.compute_losses(eng, (wp, ts, cp, sem, bev, depth, maps), ctx.labels, bias_grads=bias,
                                        w_dev=gvals.contiguous().float())
     bnd.stash = {'seeds': seeds, 'bias': bias}
-    ph = bnd.placeholder
-    return None, None, None, ph(ts), ph(cp), ph(sem), ph(bev), ph(depth), ph(maps)
+    return (None, None, None, None) + tuple(bnd.placeholder(t) for t in ctx.saved_tensors)
 
 
-def compute_loss(model, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
+def compute_loss(model, pred_wp, waypoint_label, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
                  pred_bounding_box, target_speed_label, checkpoint_label, semantic_label, bev_semantic_label, depth_label,
                  center_heatmap_label, wh_label, yaw_class_label, yaw_res_label, offset_label, pixel_weight_label,
                  avg_factor_label):
   """Drop-in body of LidarCenterNet.compute_loss: dict of the 10 loss tensors (model.py:394-445)."""
   eng = model.engine
-  dev = pred_target_speed.device
-  lab = {
-      'target_speed': target_speed_label.to(dev, torch.long).contiguous(),
-      'checkpoint': checkpoint_label.to(dev, F32).contiguous(),
+  dev = pred_semantic.device
+  lab = {}
+  if pred_wp is not None:
+    lab['waypoint'] = waypoint_label.to(dev, F32).contiguous()
+  if pred_target_speed is not None:
+    lab.update(target_speed=target_speed_label.to(dev, torch.long).contiguous(),
+               checkpoint=checkpoint_label.to(dev, F32).contiguous())
+  lab.update({
       'semantic': semantic_label.to(dev, torch.long).contiguous(),
       'bev_semantic': bev_semantic_label.to(dev, torch.long).contiguous(),
       'depth': depth_label.to(dev, F32).contiguous(),
@@ -218,7 +234,7 @@ def compute_loss(model, pred_target_speed, pred_checkpoint, pred_semantic, pred_
       'yaw_res': yaw_res_label.to(dev, F32).contiguous(),
       'pixel_weight': pixel_weight_label.to(dev, F32).contiguous(),
       'avg_factor': avg_factor_label.to(dev, F32).contiguous(),
-  }
+  })
   bb = pred_bounding_box
   base = bb[0]._base  # pylint: disable=protected-access
   n_maps = sum(t.shape[1] for t in bb[:5])
@@ -230,6 +246,9 @@ def compute_loss(model, pred_target_speed, pred_checkpoint, pred_semantic, pred_
   depth = pred_depth if pred_depth.dim() == 4 else pred_depth.unsqueeze(1)
   bnd = getattr(model, '_boundary', None)
   eng.new_arena(dev, 64)
-  vals = _Loss.apply(eng, bnd, lab, pred_target_speed.contiguous(), pred_checkpoint.contiguous(),
-                     pred_semantic.contiguous(), pred_bev_semantic.contiguous(), depth.contiguous(), maps)
-  return {k: vals[i] for i, k in enumerate(LOSS_KEYS)}
+  slots = (pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, depth, maps, pred_wp)
+  present = tuple(t is not None for t in slots)
+  vals = _Loss.apply(eng, bnd, lab, present, *[t.contiguous() for t in slots if t is not None])
+  order = ('loss_wp',) + training.LOSS_KEYS   # the reference's dict order (model.py:399-443)
+  keys = loss_keys(eng.cfg)
+  return {k: vals[keys.index(k)] for k in order if k in keys}

@@ -242,8 +242,11 @@ __global__ void __launch_bounds__(256) planner_loss_kernel(const float* __restri
     w_ts *= w2_dev[0];
     w_cp *= w2_dev[1];
   }
+  // logits == nullptr: L1 part only (loss_wp of the use_wp_gru branch, model.py:400-411); cp == nullptr: CE part only
+  if (logits == nullptr) B = (cp != nullptr) ? B : 0;
+  const int Bce = logits != nullptr ? B : 0;
   float lw = 0.f, ll = 0.f;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+  for (int b = threadIdx.x; b < Bce; b += blockDim.x) {
     const int y = static_cast<int>(labels[b]);
     float m = -INFINITY;
     for (int c = 0; c < n_cls; ++c) m = fmaxf(m, logits[b * n_cls + c]);
@@ -260,7 +263,8 @@ __global__ void __launch_bounds__(256) planner_loss_kernel(const float* __restri
     atomicAdd(&s_l, ll);
   }
   float lc = 0.f;
-  for (int i = threadIdx.x; i < B * n_cp; i += blockDim.x) {
+  const int ncp_total = cp != nullptr ? B * n_cp : 0;
+  for (int i = threadIdx.x; i < ncp_total; i += blockDim.x) {
     const float d = cp[i] - cp_t[i];
     lc += fabsf(d);
     dcp[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * w_cp / static_cast<float>(B * n_cp);
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(256) planner_loss_kernel(const float* __restri
   lc = warp_sum(lc);
   if ((threadIdx.x & 31) == 0) atomicAdd(&s_c, lc);
   __syncthreads();
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+  for (int b = threadIdx.x; b < Bce; b += blockDim.x) {
     const int y = static_cast<int>(labels[b]);
     float m = -INFINITY;
     for (int c = 0; c < n_cls; ++c) m = fmaxf(m, logits[b * n_cls + c]);
@@ -279,8 +283,8 @@ __global__ void __launch_bounds__(256) planner_loss_kernel(const float* __restri
       dlogits[b * n_cls + c] = w * (__expf(logits[b * n_cls + c] - m) / s - (c == y ? 1.f : 0.f)) * w_ts;
   }
   if (threadIdx.x == 0) {
-    losses[0] = s_l / s_w;
-    losses[1] = s_c / static_cast<float>(B * n_cp);
+    if (logits != nullptr) losses[0] = s_l / s_w;
+    if (cp != nullptr) losses[1] = s_c / static_cast<float>(B * n_cp);
   }
 }
 

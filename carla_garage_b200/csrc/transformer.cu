@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(256) planner_head_kernel(
     const float* __restrict__ w_ts1, const float* __restrict__ b_ts1, float* __restrict__ checkpoints,
     float* __restrict__ speed_logits, float* __restrict__ h_all, int n_wp, int D, int HS, int n_speed) {
   extern __shared__ float gr_sm[];
+  const int n_rows = n_wp + (n_speed > 0 ? 1 : 0);   // n_speed == 0: no target-speed token (wp_decoder, model.py:165-171)
   float* x = gr_sm;                 // (n_wp + 1) * D
   float* h = x + (n_wp + 1) * D;    // HS
   float* gi = h + HS;               // 3 HS
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256) planner_head_kernel(
   float* hid = gh + 3 * HS;         // D (target-speed hidden)
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < (n_wp + 1) * D; i += blockDim.x) x[i] = joined[static_cast<long long>(b) * (n_wp + 1) * D + i];
+  for (int i = threadIdx.x; i < n_rows * D; i += blockDim.x) x[i] = joined[static_cast<long long>(b) * n_rows * D + i];
   if (threadIdx.x < HS) {
     const float tx = target_point[b * 2], ty = target_point[b * 2 + 1];
     h[threadIdx.x] = w_enc[threadIdx.x * 2] * tx + w_enc[threadIdx.x * 2 + 1] * ty + b_enc[threadIdx.x];
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(256) planner_head_kernel(
     __syncthreads();
   }
   // target speed MLP on the last query token
+  if (n_speed == 0) return;
   const float* ts = x + n_wp * D;
   for (int j = warp; j < D; j += nwarps) {
     const float a = warp_dot(w_ts0 + static_cast<long long>(j) * D, ts, D, lane);

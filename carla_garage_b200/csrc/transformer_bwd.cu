@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(256) planner_head_bwd_kernel(
   float* dout = dhid + D;                 // n_wp * 2 (grad wrt decoder outputs)
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < (n_wp + 1) * D; i += blockDim.x) x[i] = joined[static_cast<long long>(b) * (n_wp + 1) * D + i];
+  const int n_rows = n_wp + (n_speed > 0 ? 1 : 0);   // n_speed == 0: GRU only (wp_decoder), joined has n_wp rows
+  for (int i = threadIdx.x; i < n_rows * D; i += blockDim.x) x[i] = joined[static_cast<long long>(b) * n_rows * D + i];
   for (int i = threadIdx.x; i < n_wp * HS; i += blockDim.x) hs[HS + i] = h_all[static_cast<long long>(b) * n_wp * HS + i];
   if (threadIdx.x < HS) {
     const float tx = target_point[b * 2], ty = target_point[b * 2 + 1];
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(256) planner_head_bwd_kernel(
       float a = 0.f;
       const float* gi_t = dgi + t * 3 * HS;
       for (int j = 0; j < 3 * HS; ++j) a = fmaf(w_ih[static_cast<long long>(j) * D + k], gi_t[j], a);
-      djoined[(static_cast<long long>(b) * (n_wp + 1) + t) * D + k] = a;
+      djoined[(static_cast<long long>(b) * n_rows + t) * D + k] = a;
     }
     __syncthreads();
   }
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(256) planner_head_bwd_kernel(
     atomicAdd(db_hh + j, c);
   }
   // target-speed MLP backward
+  if (n_speed == 0) return;
   const float* ts = x + n_wp * D;
   for (int j = warp; j < D; j += nw) {
     const float a = wdot(w_ts0 + static_cast<long long>(j) * D, ts, D, lane);

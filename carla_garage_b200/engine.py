@@ -660,7 +660,9 @@ class Engine:
     return (views[0], views[1], views[2], views[3], views[4], None, None)
 
   def planner(self, fused, target_point, ego_vel, command, training):
-    """model.py:299-358: memory tokens, 6-layer decoder, GRU checkpoints, target-speed logits."""
+    """model.py:299-358: memory tokens, then one pass of the 6-layer decoder per query set — ``wp_query`` -> wp_decoder
+    (use_wp_gru, model.py:325-337) and ``checkpoint_query`` -> checkpoint_decoder + target-speed MLP
+    (use_controller_input_prediction, model.py:338-358).  Returns (pred_checkpoint, pred_target_speed, pred_wp)."""
     m, cfg = self.m, self.cfg
     b, fh, fw, cf = fused.shape
     dev = fused.device
@@ -681,19 +683,35 @@ class Engine:
                            packed(m.extra_sensor_pos_embed, 'f32'), mem, None, n_mem, n_pix)
     if training:
       self._count_batch(vn)
-    layers = m.join.layers
-    heads = cfg.num_decoder_heads
-    hd = d // heads
-    nq = m.checkpoint_query.shape[1]
-    x, xb = packed(m.checkpoint_query, 'repeat_rows', b)
     memf = mem.view(b * n_mem, d)
     kvs = []
-    for l in layers:  # K/V projections of the (layer-independent) memory: one small GEMM per layer
+    for l in m.join.layers:  # K/V projections of the (layer- and query-independent) memory: one small GEMM per layer
       kvs.append(ops.linear(memf, packed(l.multihead_attn.in_proj_weight, 'rows', d, 3 * d),
                             bias=packed(l.multihead_attn.in_proj_bias, 'rows_f32', d, 3 * d)))
-    self._save(op='planner_mem', fused=fused, mem=mem, kvs=kvs, b=b, n_pix=n_pix, n_mem=n_mem, d=d, x0=x,
+    self._save(op='planner_mem', fused=fused, mem=mem, kvs=kvs, b=b, n_pix=n_pix, n_mem=n_mem, d=d,
                ego_vel=ego_vel, command=command, training=training, posenc=posenc)
-    for li, l in enumerate(layers):
+    tp = target_point.float().contiguous()
+    pred_wp = pred_cp = pred_ts = None
+    if getattr(cfg, 'use_wp_gru', False):
+      joined = self._decode(m.wp_query, kvs, b, n_mem, training)
+      pred_wp = self._gru_head(joined, m.wp_decoder, None, tp, 'planner_wp')[0]
+    if cfg.use_controller_input_prediction:
+      joined = self._decode(m.checkpoint_query, kvs, b, n_mem, training)
+      pred_cp, pred_ts = self._gru_head(joined, m.checkpoint_decoder, m.target_speed_network, tp, 'planner')
+      self._tap('joined', joined[1].view(b, -1, d))
+    return pred_cp, pred_ts, pred_wp
+
+  def _decode(self, query, kvs, b, n_mem, training):
+    """nn.TransformerDecoder (post-norm layers + final LayerNorm, model.py:137-143,352) over one learned query set.
+    Returns (pre-norm x, joined f32, LayerNorm statistics)."""
+    m, cfg = self.m, self.cfg
+    d = cfg.gru_input_size
+    heads = cfg.num_decoder_heads
+    hd = d // heads
+    nq = query.shape[1]
+    x, xb = packed(query, 'repeat_rows', b)
+    self._save(op='planner_queries', x0=x, query=query, b=b)
+    for li, l in enumerate(m.join.layers):
       act = ACT_RELU if l.activation is torch.nn.functional.relu else ACT_GELU
       # nn.TransformerDecoderLayer(dropout=0.1) (model.py:137-140): probabilities of both attentions, dropout1/2/3 on
       # the sub-layer outputs, `dropout` after the feed-forward activation — numbered in the order torch applies them
@@ -729,15 +747,20 @@ class Engine:
       x, xb = x3, x3b
     _, joined, mj, rj = ops.layernorm(x, m.join.norm.weight, m.join.norm.bias, want_bf16=False, want_f32=True,
                                       eps=m.join.norm.eps, save=self.tape is not None)
-    cd = m.checkpoint_decoder
-    tsn = m.target_speed_network
-    res = ops.planner_head(joined.view(b, nq, d), target_point.float().contiguous(), cd.encoder.weight, cd.encoder.bias,
-                           cd.gru.weight_ih_l0, cd.gru.weight_hh_l0, cd.gru.bias_ih_l0, cd.gru.bias_hh_l0,
-                           cd.decoder.weight, cd.decoder.bias, tsn[0].weight, tsn[0].bias, tsn[2].weight, tsn[2].bias,
-                           want_h=self.tape is not None)
-    self._save(op='planner_head', x=x, joined=joined, stats=(mj, rj), res=res, target_point=target_point, b=b, nq=nq,
-               d=d)
-    self._tap('joined', joined.view(b, nq, d))
+    return x, joined, (mj, rj)
+
+  def _gru_head(self, dec_out, cd, tsn, target_point, seed_key):
+    """GRUWaypointsPredictorInterFuser (model.py:839-867) [+ target_speed_network on the last query, model.py:358]."""
+    x, joined, stats = dec_out
+    d = joined.shape[1]
+    b = target_point.shape[0]
+    nq = joined.shape[0] // b
+    ts_w = (tsn[0].weight, tsn[0].bias, tsn[2].weight, tsn[2].bias) if tsn is not None else (None,) * 4
+    res = ops.planner_head(joined.view(b, nq, d), target_point, cd.encoder.weight, cd.encoder.bias, cd.gru.weight_ih_l0,
+                           cd.gru.weight_hh_l0, cd.gru.bias_ih_l0, cd.gru.bias_hh_l0, cd.decoder.weight, cd.decoder.bias,
+                           *ts_w, want_h=self.tape is not None)
+    self._save(op='planner_head', x=x, joined=joined, stats=stats, res=res, target_point=target_point, b=b, nq=nq, d=d,
+               cd=cd, tsn=tsn, seed_key=seed_key)
     return res[0], res[1]
 
   # ------------------------------------------------------------------------------------------------ full model
@@ -756,12 +779,12 @@ class Engine:
       side.wait_stream(main)
       first = len(self.tape) if self.tape is not None else 0
       with torch.cuda.stream(side):
-        pred_checkpoint, pred_target_speed = self.planner(fused, tp, ev_, cmd, training)
+        pred_checkpoint, pred_target_speed, pred_wp = self.planner(fused, tp, ev_, cmd, training)
       if self.tape is not None:
         for r in self.tape[first:]:
           r['side'] = 'planner'
     else:
-      pred_checkpoint, pred_target_speed = self.planner(fused, tp, ev_, cmd, training)
+      pred_checkpoint, pred_target_speed, pred_wp = self.planner(fused, tp, ev_, cmd, training)
     pred_semantic = pred_depth = pred_bev_semantic = pred_bounding_box = None
     if cfg.use_semantic:
       pred_semantic = self.perspective_decoder(m.semantic_decoder, grid)
@@ -779,5 +802,5 @@ class Engine:
       pred_bounding_box = self.center_head_forward(feats)
     if overlap:
       main.wait_stream(side)
-    return (None, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth, pred_bounding_box,
-            None, None, None)
+    return (pred_wp, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
+            pred_bounding_box, None, None, None)

@@ -151,10 +151,12 @@ class LidarCenterNet(nn.Module):
       raise NotImplementedError(f'backbone {config.backbone} is outside the TransFuser++ hot path (SURVEY.md §8f)')
     else:
       raise ValueError('The chosen vision backbone does not exist. The options are: transFuser, aim, bev_encoder')
-    if not (config.use_controller_input_prediction and config.transformer_decoder_join) or config.use_wp_gru or \
-        config.tp_attention or config.multi_wp_output:
-      raise NotImplementedError('carla_garage_b200 builds the default TransFuser++ planner (checkpoint + target speed '
-                                'through the transformer decoder)')
+    if not config.transformer_decoder_join:
+      raise NotImplementedError('transformer_decoder_join=False (global-pool MLP join + GRUWaypointsPredictorTransFuser, '
+                                'model.py:184-209) is not built')
+    if not (config.use_controller_input_prediction or config.use_wp_gru) or config.tp_attention or config.multi_wp_output:
+      raise NotImplementedError('built planners: checkpoint + target speed (default) and / or the waypoint GRU '
+                                '(use_wp_gru) through the transformer decoder; tp_attention / multi_wp_output are not')
     target_point_size = 2 if config.use_tp else 0
     self.extra_sensors = config.use_velocity or config.use_discrete_command
     if not (config.use_velocity and config.use_discrete_command and config.use_tp):
@@ -186,8 +188,9 @@ class LidarCenterNet(nn.Module):
           scale_factor_0=self.backbone.perspective_upsample_factor // config.deconv_scale_factor_0,
           scale_factor_1=self.backbone.perspective_upsample_factor // config.deconv_scale_factor_1)
     d = config.gru_input_size
-    self.target_speed_network = nn.Sequential(nn.Linear(d, d), nn.ReLU(inplace=True),
-                                              nn.Linear(d, len(config.target_speeds)))
+    if config.use_controller_input_prediction:
+      self.target_speed_network = nn.Sequential(nn.Linear(d, d), nn.ReLU(inplace=True),
+                                                nn.Linear(d, len(config.target_speeds)))
     decoder_norm = nn.LayerNorm(d)
     # nn.GELU() module + deepcopy inside nn.TransformerDecoder => the clones run F.relu (see oracle decoder_layer());
     # the engine follows the behaviour of the container it is given.
@@ -197,10 +200,16 @@ class LidarCenterNet(nn.Module):
     self.encoder_pos_encoding = PositionEmbeddingSine(d // 2, normalize=True)
     self.extra_sensor_pos_embed = nn.Parameter(torch.zeros(1, d))
     self.change_channel = nn.Conv2d(self.backbone.num_features, d, kernel_size=1)
-    self.checkpoint_query = nn.Parameter(torch.zeros(1, config.predict_checkpoint_len + 1, d))
-    self.checkpoint_decoder = GRUWaypointsPredictorInterFuser(input_dim=d, hidden_size=config.gru_hidden_size,
-                                                              waypoints=config.predict_checkpoint_len,
-                                                              target_point_size=target_point_size)
+    if config.use_wp_gru:  # model.py:165-171
+      n_wp = config.pred_len // config.wp_dilation
+      self.wp_query = nn.Parameter(torch.zeros(1, n_wp, d))
+      self.wp_decoder = GRUWaypointsPredictorInterFuser(input_dim=d, hidden_size=config.gru_hidden_size, waypoints=n_wp,
+                                                        target_point_size=target_point_size)
+    if config.use_controller_input_prediction:  # model.py:173-180
+      self.checkpoint_query = nn.Parameter(torch.zeros(1, config.predict_checkpoint_len + 1, d))
+      self.checkpoint_decoder = GRUWaypointsPredictorInterFuser(input_dim=d, hidden_size=config.gru_hidden_size,
+                                                                waypoints=config.predict_checkpoint_len,
+                                                                target_point_size=target_point_size)
     self.reset_parameters()
     self.velocity_normalization = nn.BatchNorm1d(1, affine=False)
     self.extra_sensor_encoder = nn.Sequential(nn.Linear(7, 128), nn.ReLU(inplace=True), nn.Linear(128, d),
@@ -227,7 +236,10 @@ class LidarCenterNet(nn.Module):
     self._boundary = None
 
   def reset_parameters(self):
-    nn.init.uniform_(self.checkpoint_query)
+    if self.config.use_wp_gru:
+      nn.init.uniform_(self.wp_query)
+    if self.config.use_controller_input_prediction:
+      nn.init.uniform_(self.checkpoint_query)
     nn.init.uniform_(self.extra_sensor_pos_embed)
 
   @property
@@ -261,9 +273,9 @@ class LidarCenterNet(nn.Module):
                    yaw_res_label, offset_label, velocity_label, brake_target_label, pixel_weight_label,
                    avg_factor_label):
     """model.py:394-445 (+ center_net.py:77-123) on fused loss kernels."""
-    del pred_wp, pred_wp_1, selected_path, waypoint_label, velocity_label, brake_target_label
+    del pred_wp_1, selected_path, velocity_label, brake_target_label
     from ..boundary import compute_loss  # pylint: disable=import-outside-toplevel
-    return compute_loss(self, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
+    return compute_loss(self, pred_wp, waypoint_label, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
                         pred_bounding_box, target_speed_label, checkpoint_label, semantic_label, bev_semantic_label,
                         depth_label, center_heatmap_label, wh_label, yaw_class_label, yaw_res_label, offset_label,
                         pixel_weight_label, avg_factor_label)

@@ -441,17 +441,17 @@ def planner_head(joined, target_point, w_enc, b_enc, w_ih, w_hh, b_ih, b_hh, w_d
                  want_h=False):
   _dev(joined, F32)
   b, nq, d = joined.shape
-  n_wp = nq - 1
+  n_speed = w_ts1.shape[0] if w_ts1 is not None else 0   # no target-speed token: every query feeds the GRU (wp_decoder)
+  n_wp = nq - 1 if n_speed else nq
   hs = w_hh.shape[1]
-  n_speed = w_ts1.shape[0]
   cp = torch.empty((b, n_wp, 2), dtype=F32, device=joined.device)
-  ts = torch.empty((b, n_speed), dtype=F32, device=joined.device)
+  ts = torch.empty((b, n_speed), dtype=F32, device=joined.device) if n_speed else None
   h_all = torch.empty((b, n_wp, hs), dtype=F32, device=joined.device) if want_h else None
   check(_lib.load().tfpp_planner_head(joined.data_ptr(), target_point.data_ptr(), w_enc.data_ptr(), b_enc.data_ptr(),
                                       w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
-                                      w_dec.data_ptr(), b_dec.data_ptr(), w_ts0.data_ptr(), b_ts0.data_ptr(),
-                                      w_ts1.data_ptr(), b_ts1.data_ptr(), cp.data_ptr(), ts.data_ptr(), _p(h_all), b,
-                                      n_wp, d, hs, n_speed, _stream()), 'tfpp_planner_head')
+                                      w_dec.data_ptr(), b_dec.data_ptr(), _p(w_ts0), _p(b_ts0), _p(w_ts1), _p(b_ts1),
+                                      cp.data_ptr(), _p(ts), _p(h_all), b, n_wp, d, hs, n_speed, _stream()),
+        'tfpp_planner_head')
   return (cp, ts, h_all) if want_h else (cp, ts)
 
 

@@ -16,6 +16,13 @@ LOSS_KEYS = ('loss_target_speed', 'loss_checkpoint', 'loss_semantic', 'loss_bev_
              'loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res')
 
 
+def loss_keys(cfg):
+  """Order of the loss VECTORS (Trainer graph output, autograd boundary): the ten default losses, then the optional
+  ones.  The reference's dict (model.py:399-443) is keyed by name, so the order is ours to pick."""
+  keys = LOSS_KEYS if cfg.use_controller_input_prediction else LOSS_KEYS[2:]
+  return keys + (('loss_wp',) if getattr(cfg, 'use_wp_gru', False) else ())
+
+
 def _pad8(n):
   return n + ((-n) % 8)
 
@@ -186,35 +193,47 @@ def compute_losses(eng, outputs, labels, weights=None, bias_grads=None, w_dev=No
   m, cfg = eng.m, eng.cfg
   if any(float(w) != 1.0 for w in list(cfg.semantic_weights) + list(cfg.bev_semantic_weights)):
     raise NotImplementedError('tfpp_ce_map_loss assumes all-ones class weights on the semantic maps (config.py:163-164)')
-  weights = weights or {k: 1.0 for k in LOSS_KEYS}
+  keys = loss_keys(cfg)
+  weights = weights or {k: 1.0 for k in keys}
   bias_grads = bias_grads or {}
-  _, pred_ts, pred_cp, pred_sem, pred_bev, pred_depth, bb = outputs[:7]
-  dev = pred_ts.device
-  b = pred_ts.shape[0]
+  pred_wp, pred_ts, pred_cp, pred_sem, pred_bev, pred_depth, bb = outputs[:7]
+  dev = pred_sem.device
+  b = pred_sem.shape[0]
   sums = eng.zeros((16,), dev)
   stream = ops._stream()  # pylint: disable=protected-access
   seeds = {}
   losses = {}
-  wp = (lambda i: w_dev[i:].data_ptr()) if w_dev is not None else (lambda i: None)
-  # target speed CE + checkpoint L1 (model.py:416-420)
-  pred_ts, pred_cp = pred_ts.contiguous(), pred_cp.contiguous()
-  dlogits = torch.empty_like(pred_ts)
-  dcp = torch.empty_like(pred_cp)
-  _lib.check(lib.tfpp_planner_loss(pred_ts.data_ptr(), labels['target_speed'].data_ptr(),
-                                   packed(m.loss_speed.weight, 'f32').data_ptr(), pred_cp.data_ptr(),
-                                   labels['checkpoint'].data_ptr(), weights['loss_target_speed'],
-                                   weights['loss_checkpoint'], wp(0), sums[0:2].data_ptr(), dlogits.data_ptr(),
-                                   dcp.data_ptr(), b, pred_ts.shape[1], pred_cp.shape[1] * pred_cp.shape[2], stream),
-             'planner_loss')
-  losses['loss_target_speed'], losses['loss_checkpoint'] = sums[0], sums[1]
-  seeds['planner'] = (dcp, dlogits)
+  # w_dev follows loss_keys(cfg); the kernels take pointers to the entry (or the first of two adjacent entries)
+  wp = (lambda k: w_dev[keys.index(k):].data_ptr()) if w_dev is not None else (lambda k: None)
+  if pred_wp is not None:  # waypoint L1 of the use_wp_gru branch (model.py:409-411): the L1 half of tfpp_planner_loss
+    pred_wp = pred_wp.contiguous()
+    dwp = torch.empty_like(pred_wp)
+    wpt = wp('loss_wp')
+    _lib.check(lib.tfpp_planner_loss(None, None, None, pred_wp.data_ptr(), labels['waypoint'].data_ptr(), 0.0,
+                                     weights['loss_wp'], None if wpt is None else wpt - 4, sums[10:12].data_ptr(), None,
+                                     dwp.data_ptr(), b, 0, pred_wp.shape[1] * pred_wp.shape[2], stream), 'wp_loss')
+    losses['loss_wp'] = sums[11]
+    seeds['planner_wp'] = (dwp, None)
+  if pred_ts is not None:
+    # target speed CE + checkpoint L1 (model.py:416-420)
+    pred_ts, pred_cp = pred_ts.contiguous(), pred_cp.contiguous()
+    dlogits = torch.empty_like(pred_ts)
+    dcp = torch.empty_like(pred_cp)
+    _lib.check(lib.tfpp_planner_loss(pred_ts.data_ptr(), labels['target_speed'].data_ptr(),
+                                     packed(m.loss_speed.weight, 'f32').data_ptr(), pred_cp.data_ptr(),
+                                     labels['checkpoint'].data_ptr(), weights['loss_target_speed'],
+                                     weights['loss_checkpoint'], wp('loss_target_speed'), sums[0:2].data_ptr(),
+                                     dlogits.data_ptr(), dcp.data_ptr(), b, pred_ts.shape[1],
+                                     pred_cp.shape[1] * pred_cp.shape[2], stream), 'planner_loss')
+    losses['loss_target_speed'], losses['loss_checkpoint'] = sums[0], sums[1]
+    seeds['planner'] = (dcp, dlogits)
   # semantic CE (model.py:423)
   hw = pred_sem.shape[2] * pred_sem.shape[3]
   ncls = pred_sem.shape[1]
   cp = 16  # multiple of 16: the small-channel dgrad / wgrad kernels take 16- or 32-channel gradients
   dz = torch.empty((b, pred_sem.shape[2], pred_sem.shape[3], cp), dtype=BF16, device=dev) if want_seeds else None
   _lib.check(lib.tfpp_ce_map_loss(pred_sem.data_ptr(), labels['semantic'].data_ptr(), None,
-                                  weights['loss_semantic'] / (b * hw), wp(2), sums[2:3].data_ptr(), ops._p(dz), None,  # pylint: disable=protected-access
+                                  weights['loss_semantic'] / (b * hw), wp('loss_semantic'), sums[2:3].data_ptr(), ops._p(dz), None,  # pylint: disable=protected-access
                                   ops._p(bias_grads.get('semantic')), b, ncls, cp, hw, stream), 'ce semantic')  # pylint: disable=protected-access
   losses['loss_semantic'] = sums[2] / (b * hw)
   seeds['semantic'] = dz
@@ -226,7 +245,7 @@ def compute_losses(eng, outputs, labels, weights=None, bias_grads=None, w_dev=No
   count = float(n_valid) * b
   dbev = torch.empty_like(pred_bev) if want_seeds else None
   _lib.check(lib.tfpp_ce_map_loss(pred_bev.data_ptr(), labels['bev_semantic'].data_ptr(), valid.data_ptr(),
-                                  weights['loss_bev_semantic'] / count, wp(3), sums[3:4].data_ptr(), None, ops._p(dbev),  # pylint: disable=protected-access
+                                  weights['loss_bev_semantic'] / count, wp('loss_bev_semantic'), sums[3:4].data_ptr(), None, ops._p(dbev),  # pylint: disable=protected-access
                                   None, b, nb, 16, hwb, stream), 'ce bev')
   losses['loss_bev_semantic'] = sums[3] / count
   seeds['bev'] = dbev
@@ -234,7 +253,7 @@ def compute_losses(eng, outputs, labels, weights=None, bias_grads=None, w_dev=No
   n = pred_depth.numel()
   dzd = torch.empty((b, pred_depth.shape[-2], pred_depth.shape[-1], 16), dtype=BF16, device=dev) if want_seeds else None
   _lib.check(lib.tfpp_l1_sigmoid_loss(pred_depth.data_ptr(), labels['depth'].data_ptr(), weights['loss_depth'] / n,
-                                      wp(4), sums[4:5].data_ptr(), ops._p(dzd), ops._p(bias_grads.get('depth')), 16, n,  # pylint: disable=protected-access
+                                      wp('loss_depth'), sums[4:5].data_ptr(), ops._p(dzd), ops._p(bias_grads.get('depth')), 16, n,  # pylint: disable=protected-access
                                       stream), 'l1 depth')
   losses['loss_depth'] = sums[4] / n
   seeds['depth'] = dzd
@@ -245,7 +264,8 @@ def compute_losses(eng, outputs, labels, weights=None, bias_grads=None, w_dev=No
       [weights[k] for k in ('loss_center_heatmap', 'loss_wh', 'loss_offset', 'loss_yaw_class', 'loss_yaw_res')],
       dtype=F32), dev)
   if w_dev is not None:
-    w5 = w5 * w_dev[5:10]
+    i5 = keys.index('loss_center_heatmap')
+    w5 = w5 * w_dev[i5:i5 + 5]
   dzh = torch.empty((b, maps.shape[2], maps.shape[3], 24), dtype=BF16, device=dev) if want_seeds else None
   _lib.check(lib.tfpp_center_head_loss(maps.data_ptr(), labels['center_heatmap'].data_ptr(), labels['wh'].data_ptr(),
                                        labels['offset'].data_ptr(), labels['yaw_class'].data_ptr(),
@@ -553,28 +573,37 @@ class Backward:
   def planner_head(self, r, seeds):
     from . import _lib  # pylint: disable=import-outside-toplevel
     st, m = self.st, self.eng.m
-    dcp, dlogits = seeds.pop('planner')
+    dcp, dlogits = seeds.pop(r.get('seed_key', 'planner'))
     b, nq, d = r['b'], r['nq'], r['d']
-    cd, tsn = m.checkpoint_decoder, m.target_speed_network
+    cd, tsn = r['cd'], r['tsn']
     joined = r['joined']
     h_all = r['res'][2]
     djoined = torch.empty_like(joined)
     g = st.g
     tp = r['target_point'].float().contiguous()
+    n_speed = tsn[2].weight.shape[0] if tsn is not None else 0
+    n_wp = nq - 1 if n_speed else nq
+    P = lambda t: None if t is None else t.data_ptr()
+    tw = (tsn[0].weight, tsn[0].bias, tsn[2].weight) if tsn is not None else (None, None, None)
+    tg = (g(tsn[0].weight), g(tsn[0].bias), g(tsn[2].weight), g(tsn[2].bias)) if tsn is not None else (None,) * 4
     _lib.check(_lib.load().tfpp_planner_head_bwd(
         joined.data_ptr(), tp.data_ptr(), h_all.data_ptr(), cd.encoder.weight.data_ptr(), cd.encoder.bias.data_ptr(),
         cd.gru.weight_ih_l0.data_ptr(), cd.gru.weight_hh_l0.data_ptr(), cd.gru.bias_ih_l0.data_ptr(),
-        cd.gru.bias_hh_l0.data_ptr(), cd.decoder.weight.data_ptr(), tsn[0].weight.data_ptr(), tsn[0].bias.data_ptr(),
-        tsn[2].weight.data_ptr(), dcp.data_ptr(), dlogits.data_ptr(), djoined.data_ptr(), g(cd.encoder.weight).data_ptr(),
+        cd.gru.bias_hh_l0.data_ptr(), cd.decoder.weight.data_ptr(), P(tw[0]), P(tw[1]), P(tw[2]), dcp.data_ptr(),
+        P(dlogits), djoined.data_ptr(), g(cd.encoder.weight).data_ptr(),
         g(cd.encoder.bias).data_ptr(), g(cd.gru.weight_ih_l0).data_ptr(), g(cd.gru.weight_hh_l0).data_ptr(),
         g(cd.gru.bias_ih_l0).data_ptr(), g(cd.gru.bias_hh_l0).data_ptr(), g(cd.decoder.weight).data_ptr(),
-        g(cd.decoder.bias).data_ptr(), g(tsn[0].weight).data_ptr(), g(tsn[0].bias).data_ptr(),
-        g(tsn[2].weight).data_ptr(), g(tsn[2].bias).data_ptr(), b, nq - 1, d, cd.hidden_size, tsn[2].weight.shape[0],
+        g(cd.decoder.bias).data_ptr(), P(tg[0]), P(tg[1]), P(tg[2]), P(tg[3]), b, n_wp, d, cd.hidden_size, n_speed,
         ops._stream()), 'planner_head_bwd')  # pylint: disable=protected-access
     mj, rj = r['stats']
     dx = ops.layernorm_bwd(djoined.view(b * nq, d), r['x'], mj, rj, m.join.norm.weight, g(m.join.norm.weight),
                            g(m.join.norm.bias))
     self.G[id(r['x'])] = dx
+
+  def planner_queries(self, r):
+    # a learned query set repeated over the batch (model.py:329,349): its gradient is the sum over the batch
+    dx0 = self.G.pop(id(r['x0']))
+    ops.batch_reduce(dx0, self.st.g(r['query']).view(-1), r['b'])
 
   def dec_layer(self, r):
     st = self.st
@@ -637,10 +666,7 @@ class Backward:
     st, m = self.st, self.eng.m
     g = st.g
     b, n_pix, n_mem, d = r['b'], r['n_pix'], r['n_mem'], r['d']
-    # queries: checkpoint_query repeated over the batch
-    dx0 = self.G.pop(id(r['x0']))
-    ops.batch_reduce(dx0, g(m.checkpoint_query).view(-1), b)
-    dmem = self.G.pop('dmem')  # (B*n_mem, d) f32
+    dmem = self.G.pop('dmem')  # (B*n_mem, d) f32: accumulated over every decoder pass
     # extra sensor token = row n_pix of every sample
     ese, vn = m.extra_sensor_encoder, m.velocity_normalization
     training = r['training']
@@ -767,6 +793,8 @@ class Backward:
       self.dec_layer(r)
     elif op == 'planner_mem':
       self.planner_mem(r)
+    elif op == 'planner_queries':
+      self.planner_queries(r)
     else:
       raise RuntimeError(f'no backward handler for {op}')
 
@@ -820,7 +848,8 @@ class Trainer:
       groups = model.create_optimizer_groups(weight_decay)
       self.st.set_flags(no_decay=[p for g in groups if g['weight_decay'] == 0.0 for p in g['params']])
     self.lr, self.wd = lr, weight_decay
-    w = loss_weights or {k: 1.0 for k in LOSS_KEYS}
+    self.keys = loss_keys(model.config)
+    w = loss_weights or {k: 1.0 for k in self.keys}
     tot = sum(w.values())
     self.loss_weights = {k: v / tot for k, v in w.items()}  # train.py:452-456
     self.pg = process_group
@@ -929,11 +958,11 @@ class Trainer:
     if not self._split:
       with torch.cuda.graph(self.graph):
         out, losses = body()
-        self._gloss = torch.stack([losses[k] for k in LOSS_KEYS])
+        self._gloss = torch.stack([losses[k] for k in self.keys])
     else:
       with torch.cuda.graph(self.graph):
         out, losses = fwd_bwd()
-        self._gloss = torch.stack([losses[k] for k in LOSS_KEYS])
+        self._gloss = torch.stack([losses[k] for k in self.keys])
       self.graph_opt = torch.cuda.CUDAGraph()
       with torch.cuda.graph(self.graph_opt):
         opt()

@@ -340,12 +340,17 @@ def planner(sd, fused, target_point, ego_vel, command, cfg=None, training=False,
   mem = torch.cat((f, es.unsqueeze(2)), dim=2).permute(0, 2, 1)
   if taps is not None:
     taps['memory'] = mem
-  # model.py:352  nn.TransformerDecoder + final norm
-  x = sd['checkpoint_query'].repeat(bs, 1, 1)
-  for l in range(cfg['num_transformer_decoder_layers']):
-    x = decoder_layer(sd, f'join.layers.{l}', x, mem, cfg['num_decoder_heads'], cfg.get('decoder_activation', 'relu'),
-                      dropout, cfg.get('decoder_pdrop', 0.1))
-  x = F.layer_norm(x, (x.shape[-1],), sd['join.norm.weight'], sd['join.norm.bias'])
+  def join(queries):  # model.py:352  nn.TransformerDecoder + final norm
+    x = queries.repeat(bs, 1, 1)
+    for l in range(cfg['num_transformer_decoder_layers']):
+      x = decoder_layer(sd, f'join.layers.{l}', x, mem, cfg['num_decoder_heads'], cfg.get('decoder_activation', 'relu'),
+                        dropout, cfg.get('decoder_pdrop', 0.1))
+    return F.layer_norm(x, (x.shape[-1],), sd['join.norm.weight'], sd['join.norm.bias'])
+
+  pred_wp = None
+  if cfg.get('use_wp_gru', False):  # model.py:325-337 (single waypoint output)
+    pred_wp = gru_waypoints(sd, 'wp_decoder', join(sd['wp_query']), target_point)
+  x = join(sd['checkpoint_query'])
   if taps is not None:
     taps['joined'] = x
   n = cfg['predict_checkpoint_len']
@@ -354,6 +359,8 @@ def planner(sd, fused, target_point, ego_vel, command, cfg=None, training=False,
   pred_target_speed = F.linear(F.relu(F.linear(ts, sd['target_speed_network.0.weight'],
                                                sd['target_speed_network.0.bias'])),
                                sd['target_speed_network.2.weight'], sd['target_speed_network.2.bias'])
+  if cfg.get('use_wp_gru', False):
+    return pred_checkpoint, pred_target_speed, pred_wp
   return pred_checkpoint, pred_target_speed
 
 

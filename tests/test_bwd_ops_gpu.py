@@ -543,7 +543,7 @@ def test_planner_forward_backward(ops, trainer, oracle_state):
   eng.new_arena(torch.device('cuda'))
   try:
     xd = _to_dev(ops, fused)
-    cp, ts = eng.planner(xd, tp.cuda(), vel.cuda(), cmd.cuda(), True)
+    cp, ts, _ = eng.planner(xd, tp.cuda(), vel.cuda(), cmd.cuda(), True)
     tape = eng.tape
   finally:
     eng.tape = None
@@ -602,3 +602,66 @@ def test_downsample_stride2_block_backward(ops, trainer, oracle_state):
             prefix + '.conv2.conv.weight', prefix + '.conv3.conv.weight', prefix + '.conv1.conv.weight'):
     assert rel(params[n].grad, sd[n].grad) < 0.15, n
   net.load_state_dict(oracle_state, strict=True)
+
+
+def test_wp_gru_branch_forward_backward(ops, oracle_state):
+  """use_wp_gru=1 (model.py:150-171,325-337,409-411): a second pass of the decoder over ``wp_query`` feeding
+  ``wp_decoder`` (GRUWaypointsPredictorInterFuser over pred_len waypoints) next to the checkpoint / target-speed pass;
+  loss_wp = mean |pred_wp - waypoint_label|.  Forward + backward vs the oracle, then one fused Trainer step."""
+  from carla_garage_b200 import synth
+  from carla_garage_b200.config import GlobalConfig
+  from carla_garage_b200.nn import LidarCenterNet
+  from carla_garage_b200.training import Backward, Trainer, loss_keys
+  from oracle import tfpp_oracle as orc
+  cfg = GlobalConfig()
+  cfg.use_wp_gru = True
+  net = LidarCenterNet(cfg)
+  shapes = {k: tuple(v.shape) for k, v in net.state_dict().items() if k not in oracle_state}
+  assert set(k.split('.')[0] for k in shapes) == {'wp_query', 'wp_decoder'}
+  state = dict(oracle_state)
+  state.update(synth.make_state_dict(shapes, seed=3))
+  net.load_state_dict(state, strict=True)
+  net = net.cuda().train()
+  assert loss_keys(cfg)[-1] == 'loss_wp' and len(loss_keys(cfg)) == 11
+  tr = Trainer(net)
+  eng, st = tr.eng, tr.st
+  gemm = lambda k, v: v.dim() >= 2 and k.startswith(('join.', 'change_channel'))
+  sd = {k: ((v.to(torch.bfloat16).float() if gemm(k, v) else v.clone()).requires_grad_(True)
+            if v.is_floating_point() and 'running' not in k else v) for k, v in state.items()}
+  b = 3
+  g = torch.Generator().manual_seed(51)
+  fused = bf(torch.randn(b, 1512, 8, 8, generator=g)).float().requires_grad_(True)
+  tp, vel = torch.randn(b, 2, generator=g) * 10, torch.rand(b, 1, generator=g) * 8
+  cmd = F.one_hot(torch.randint(0, 6, (b,), generator=g), 6).float()
+  ocfg = dict(orc.DEFAULT_CFG, use_wp_gru=True)
+  want_cp, want_ts, want_wp = orc.planner(sd, fused, tp, vel, cmd, ocfg, training=True)
+  assert want_wp.shape == (b, cfg.pred_len // cfg.wp_dilation, 2)
+  dcp, dts, dwp = (torch.randn(t.shape, generator=g) for t in (want_cp, want_ts, want_wp))
+  ((want_cp * dcp).sum() + (want_ts * dts).sum() + (want_wp * dwp).sum()).backward()
+  st.zero_grad()
+  eng.tape = []
+  eng.new_arena(torch.device('cuda'))
+  try:
+    xd = _to_dev(ops, fused)
+    cp, ts, wp = eng.planner(xd, tp.cuda(), vel.cuda(), cmd.cuda(), True)
+    tape = eng.tape
+  finally:
+    eng.tape = None
+  assert rel(cp, want_cp) < 1e-2 and rel(ts, want_ts) < 1e-2 and rel(wp, want_wp) < 1e-2
+  bw = Backward(eng, st)
+  bw.run(tape, {'planner': (dcp.cuda(), dts.cuda()), 'planner_wp': (dwp.cuda(), None)})
+  torch.cuda.synchronize()
+  assert rel(ops.nhwc_to_nchw(bw.G[id(xd)]), fused.grad) < 5e-2
+  params = dict(net.named_parameters())
+  for n in [k for k in sd if k.startswith(('wp_', 'checkpoint_', 'join.', 'change_channel')) and sd[k].is_floating_point()
+            and sd[k].grad is not None]:
+    assert rel(params[n].grad, sd[n].grad) < 6e-2, n
+  # a whole fused step on the extended model: 11 losses, loss_wp agrees with torch on the step's own prediction
+  inp = {k: v.cuda() for k, v in synth.make_inputs(2, seed=11).items()}
+  lab = {k: v.cuda().contiguous() for k, v in synth.make_labels(2, seed=13).items()}
+  lab['waypoint'] = torch.cumsum(torch.rand(2, 8, 2, generator=g), 1).cuda()
+  out, losses = tr.forward_backward(inp, lab)
+  torch.cuda.synchronize()
+  assert set(losses) == set(loss_keys(cfg))
+  assert abs(float(losses['loss_wp']) - float((out[0] - lab['waypoint']).abs().mean())) < 1e-5
+  assert float(params['wp_decoder.gru.weight_ih_l0'].grad.abs().max()) > 0 and float(params['wp_query'].grad.abs().max()) > 0
