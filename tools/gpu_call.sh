@@ -19,7 +19,7 @@ PY
 }
 for leg in "$@"; do
   case $leg in
-    tests) timeout 1800 python -m pytest tests/ -q -m gpu -x > gpurun_out/${TAG}_pytest.log 2>&1; tail -8 gpurun_out/${TAG}_pytest.log;;
+    tests) timeout 1800 python -m pytest tests/ -q -m gpu > gpurun_out/${TAG}_pytest.log 2>&1; tail -8 gpurun_out/${TAG}_pytest.log;;
     ops) timeout 900 python -m pytest tests/test_ops_gpu.py -q -m gpu > gpurun_out/${TAG}_ops.log 2>&1; tail -8 gpurun_out/${TAG}_ops.log;;
     model) timeout 1200 python -m pytest tests/test_model_gpu.py tests/test_train_gpu.py -q -m gpu > gpurun_out/${TAG}_model.log 2>&1; tail -8 gpurun_out/${TAG}_model.log;;
     bench) TFPP_GEMM_DUMP=gpurun_out/${TAG}_gemm_shapes.txt timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; bench_line gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err;;
