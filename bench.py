@@ -279,7 +279,7 @@ def main():
     dist.destroy_process_group()
   if rank == 0:
     # rank-local instrumented step: no collective inside (the other ranks are not running it)
-    tr_world, tr.world = tr.world, 1
+    tr.local_only = True
     # one stream for this step: with the LiDAR branch / planner on side streams the per-launch times would include the
     # kernels they share the SMs with
     prev_no_overlap = os.environ.get('TFPP_NO_OVERLAP')
@@ -291,7 +291,7 @@ def main():
         os.environ.pop('TFPP_NO_OVERLAP', None)
       else:
         os.environ['TFPP_NO_OVERLAP'] = prev_no_overlap
-    tr.world = tr_world
+    tr.local_only = False
     peak = peaks.get('bf16_tflops_sustained', 1400.0)
     roof = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel + wgrad_kernel (tcgen05)',
             'achieved': prof['tflops'], 'peak': peak, 'unit': 'TFLOP/s', 'frac': prof['tflops'] / peak,
@@ -323,6 +323,35 @@ def main():
   torch.cuda.synchronize()
   fwd_ms = e0.elapsed_time(e1) / 50
   inference = {'fwd_ms_per_frame': fwd_ms, 'batch': 1, 'mode': 'eval, CUDA-graph replay, inputs resident'}
+  # ---- BASELINE.json config 5: sensor_agent.py inference, 3-member ensemble, batch 64, forward only (one CUDA graph:
+  # 3 forwards + CenterNet decode + threshold / vehicle-frame conversion / rotated-IoU NMS over the union + averaging)
+  if os.environ.get('TFPP_BENCH_ENSEMBLE', '1') == '1':
+    from carla_garage_b200.inference import EnsembleForward
+    del gf
+    members = [net]
+    base = synth.golden_state(os.path.join(ROOT, 'tests', 'golden'))
+    for s_ in (1, 2):
+      m_ = LidarCenterNet(GlobalConfig())
+      g_ = torch.Generator().manual_seed(s_)
+      m_.load_state_dict({k: (v + 0.01 * torch.randn(v.shape, generator=g_) if v.is_floating_point() and v.dim() >= 2 else v)
+                          for k, v in base.items()}, strict=True)
+      members.append(m_.cuda().eval())
+    eb = 64
+    big = {k: torch.cat([v] * (-(-eb // v.shape[0])))[:eb].contiguous() for k, v in dev_in.items()}
+    ef = EnsembleForward(members, big)
+    for _ in range(2):
+      ef()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+      ef()
+    e1.record()
+    torch.cuda.synchronize()
+    ens_ms = e0.elapsed_time(e1) / 5
+    inference['ensemble'] = {'frames_per_s': eb / (ens_ms / 1e3), 'ms_per_batch': ens_ms, 'batch': eb, 'members': len(members),
+                             'boxes_kept_mean': float(ef.out[3].float().mean()),
+                             'includes': '3 eval forwards + decode_heatmap + confidence threshold + vehicle-frame '
+                                         'conversion + rotated-IoU NMS over the union + ensemble means, one CUDA graph'}
   cpu = None
   if not args.no_cpu_baseline:
     threads = pick_cpu_threads()
@@ -348,7 +377,8 @@ def main():
                  'global_batch': world * b, 'per_gpu_batch': b, 'parallelism': f'dp{world}',
                  'l2': 'per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed',
                  'inputs': 'rgb (B,3,256,1024) f32 + 60k-point LiDAR cloud -> (B,1,256,256) BEV (reference default use_ground_plane=0)',
-                 'dropout': ('on: embd/attn/resid_pdrop 0.1 + decoder 0.1, Philox4x32-10 masks regenerated in the backward kernels' if net.engine.dropout_enabled else 'off (TFPP_DROPOUT=0)'), 'cuda_graph': bool(use_graph), 'graphs': (1 if world == 1 and os.environ.get('TFPP_SPLIT_GRAPH', '0') != '1' else 2) if use_graph else 0, 'model_tflop_per_step': world * b * FLOP_PER_SAMPLE_TRAIN / 1e12},
+                 'dropout': ('on: embd/attn/resid_pdrop 0.1 + decoder 0.1, Philox4x32-10 masks regenerated in the backward kernels' if net.engine.dropout_enabled else 'off (TFPP_DROPOUT=0)'), 'cuda_graph': bool(use_graph), 'graphs': (1 if tr.graph_opt is None else 2) if use_graph else 0,
+                 'exchange': ('none (1 GPU)' if world == 1 else ('NVLink peer-memory reduce-scatter + AdamW shard + all-gather in one kernel (csrc/peer_exchange.cu)' if tr.xchg is not None else 'NCCL all-reduce between two graphs')), 'model_tflop_per_step': world * b * FLOP_PER_SAMPLE_TRAIN / 1e12},
       'e2e': {'value': e2e, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 40,
               'ms_per_step': ms_e2e / args.steps},
       'gpu_launches': launches,

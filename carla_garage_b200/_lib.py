@@ -43,6 +43,17 @@ class WgradArgs(ctypes.Structure):
   ]
 
 
+class PeerStepArgs(ctypes.Structure):
+  """tfpp_peer_step_args (include/tfpp.h)."""
+  _fields_ = [
+      ('world', c_int), ('rank', c_int),
+      ('grad', c_void_p * 8), ('param', c_void_p * 8), ('flags', c_void_p * 8),
+      ('exp_avg', c_void_p), ('exp_avg_sq', c_void_p), ('max_exp_avg_sq', c_void_p),
+      ('n', c_ll), ('beta1', c_float), ('beta2', c_float), ('eps', c_float), ('weight_decay', c_float),
+      ('dev_state', c_void_p), ('opt_flags', c_void_p),
+  ]
+
+
 P, I, F, L = c_void_p, c_int, c_float, c_ll
 _PROTOS = {
     'tfpp_abi_version': [],
@@ -104,6 +115,25 @@ _PROTOS = {
     'tfpp_small_mha_bwd_dropout': [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, I, P, F, I,
                                    P],
     'tfpp_adamw_amsgrad': [P, P, P, P, P, L, F, F, F, F, F, I, F, P, P, P],
+    'tfpp_nms_rotated': [P, I, I, I, F, F, I, F, F, F, P, P, P, P],
+    # NVLink peer-memory gradient exchange fused with AdamW (csrc/peer_exchange.cu)
+    'tfpp_peer_alloc': [L, ctypes.POINTER(c_void_p), P],
+    'tfpp_peer_open': [P, ctypes.POINTER(c_void_p)],
+    'tfpp_peer_close': [P],
+    'tfpp_peer_free': [P],
+    'tfpp_peer_adamw_step': [ctypes.POINTER(PeerStepArgs), P],
+    'tfpp_peer_barrier': [ctypes.POINTER(PeerStepArgs), I, P],
+    # fp32 parity mode (csrc/fp32_path.cu)
+    'tfpp_conv_gemm_f32': [ctypes.POINTER(ConvGemmArgs), P],
+    'tfpp_gconv3x3_f32': [P, P, P, P, P, I, P, P, I, I, I, I, I, P],
+    'tfpp_stem_conv_f32': [P, P, P, P, P, P, I, P, P, P, I, I, I, I, P],
+    'tfpp_scale_shift_act_f32': [P, P, P, P, P, P, I, P, P, I, I, I, P],
+    'tfpp_channel_scale_f32': [P, P, P, I, I, I, P],
+    'tfpp_parity_split_f32': [P, P, I, I, I, I, P],
+    'tfpp_avgpool_tokens_f32': [P, P, P, I, I, I, I, I, I, I, I, P],
+    'tfpp_bilinear_f32': [P, L, L, P, P, I, I, I, I, I, I, P],
+    'tfpp_bilinear_nchw_mask_f32': [P, P, P, I, I, I, I, I, I, I, P],
+    'tfpp_mha_f32': [P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, P, F, I, P],
 }
 
 
@@ -131,7 +161,7 @@ def load():
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
-_KERNELS_PER_CALL = {'tfpp_adamw_amsgrad': 2, 'tfpp_pillar_scatter': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 4, 'tfpp_se_gate': 2, 'tfpp_gconv3x3_wgrad': 2, 'tfpp_fusion_attn_bwd': 2}
+_KERNELS_PER_CALL = {'tfpp_peer_adamw_step': 4, 'tfpp_adamw_amsgrad': 2, 'tfpp_pillar_scatter': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 4, 'tfpp_se_gate': 2, 'tfpp_gconv3x3_wgrad': 2, 'tfpp_fusion_attn_bwd': 2}
 _LAUNCHES = [0]
 
 

@@ -64,6 +64,7 @@ class GlobalConfig:
     self.debug = False
     # detector (config.py:307-322)
     self.bb_confidence_threshold = 0.3
+    self.iou_treshold_nms = 0.2  # config.py:492 (the reference's spelling)
     self.num_dir_bins = 12
     self.top_k_center_keypoints = 100
     self.center_net_max_pooling_kernel = 3

@@ -221,7 +221,8 @@ def packed(params, kind, *extra):
   """Kernel-layout copy of parameter(s); rebuilt whenever a version counter / storage changes (optimizer step,
   load_state_dict, .to(device)) — or, under a PackPlan, a fixed view that PackPlan.refresh() keeps current."""
   params = params if isinstance(params, (tuple, list)) else (params,)
-  key = (kind,) + tuple(id(p) for p in params) + extra
+  dtb = ops.act_dtype()  # bf16 packs in production, fp32 packs in the parity mode (ops.set_precision('fp32'))
+  key = (kind,) + tuple(id(p) for p in params) + extra + ((dtb,) if dtb != BF16 else ())
   plan = _PLAN[0]
   if plan is not None:
     hit = plan.lookup(key, params)
@@ -234,8 +235,8 @@ def packed(params, kind, *extra):
   if hit is not None and hit[0] == ver and all(r() is p for r, p in zip(hit[2], params)):
     return hit[1]
   with torch.no_grad():
-    out = _build_pack(kind, params, extra)
-    if plan is not None:
+    out = _build_pack(kind, params, extra, dtb=dtb)
+    if plan is not None and dtb == BF16:
       plan.register(key, kind, params, extra, out)
   _PACK_CACHE[key] = (ver, out, tuple(weakref.ref(p) for p in params))
   return out
@@ -302,6 +303,9 @@ class Engine:
 
   def begin_dropout_step(self, device):
     """Start of a training forward: next step of the random stream, site numbering restarts."""
+    device = torch.device(device)
+    if device.type == 'cuda' and device.index is None:
+      device = torch.device('cuda', torch.cuda.current_device())   # 'cuda' and 'cuda:0' are the same place
     if self.rng is None or self.rng.device != device:
       self.seed_dropout(torch.initial_seed(), device)
     self.rng[1:2] += 1
@@ -404,7 +408,7 @@ class Engine:
     taps = taps or (ops.TAPS_3X3 if k == 3 else ops.TAPS_1X1)
     cout, cin = conv.weight.shape[0], conv.weight.shape[1]
     cpad = 8 if cout <= 8 else (16 if cout <= 16 else 32)
-    smallc = (k == 3 and cout <= 32 and ops.smallc_supported(cin, cpad) and a.shape[1] * a.shape[2] >= 4096 and
+    smallc = (a.dtype == BF16 and k == 3 and cout <= 32 and ops.smallc_supported(cin, cpad) and a.shape[1] * a.shape[2] >= 4096 and
               (kw.get('out_layout') == 'nchw' or cout == cpad) and not set(kw) - {'out_layout', 'out_f32'})
     npad = 16 if cout <= 16 else 32
     halo = (smallc and HALO_UMMA and ops.halo_umma_supported(cin, npad) and
@@ -502,7 +506,7 @@ class Engine:
     pos = packed(gpt.pos_emb, 'f32').view(t, c)
     x = torch.empty((b, t, c), dtype=F32, device=dev)  # fp32 residual stream
     ops.avgpool_tokens(img, x, ph_i, pw_i, 0, pos_emb=pos)
-    lid_pool = torch.empty((b, n_lid, cl), dtype=BF16, device=dev)
+    lid_pool = torch.empty((b, n_lid, cl), dtype=ops.act_dtype(), device=dev)
     ops.avgpool_tokens(lid, lid_pool, ph_l, pw_l, 0)
     l2i = bb.lidar_channel_to_img[i]
     ops.linear(lid_pool.view(b * n_lid, cl), packed(l2i.weight, 'linear'), bias=packed(l2i.bias, 'f32'),
@@ -536,7 +540,7 @@ class Engine:
     img_out = ops.bilinear(xf, b, ph_i, pw_i, hi, wi, c, src_batch_stride=t * c, src_row_stride=c, add=img)
     # LiDAR tokens: 1x1 conv back to the LiDAR width on the 64-row slab, then up-sample + add (transfuser.py:237,250-255)
     i2l = bb.img_channel_to_lidar[i]
-    lid_tok = torch.empty((b * n_lid, cl), dtype=BF16, device=dev)
+    lid_tok = torch.empty((b * n_lid, cl), dtype=ops.act_dtype(), device=dev)
     ops.conv_gemm(xf.view(-1)[n_img * c:], packed(i2l.weight, 'linear').view(cl, 1, c), a_shape=(b, 1, n_lid, c),
                   a_batch_stride=t * c, shift=packed(i2l.bias, 'f32'), out=lid_tok, out_strides=(n_lid * cl, 0, cl, 1))
     lid_out = ops.bilinear(lid_tok, b, ph_l, pw_l, hl, wl, cl, add=lid)
@@ -669,7 +673,7 @@ class Engine:
     d = cfg.gru_input_size
     n_pix = fh * fw
     n_mem = n_pix + 1
-    mem = torch.empty((b, n_mem, d), dtype=BF16, device=dev)
+    mem = torch.empty((b, n_mem, d), dtype=ops.act_dtype(), device=dev)
     posenc = self._const(f'posenc{fh}x{fw}', lambda: m.encoder_pos_encoding.table(fh, fw), dev)
     cc = m.change_channel
     ops.linear(fused.view(b * n_pix, cf), packed(cc.weight, 'linear'), bias=packed(cc.bias, 'f32'), out=mem,
@@ -680,7 +684,8 @@ class Engine:
     ops.extra_sensor_token(ego_vel.float().contiguous(), command.float().contiguous(), vmean, vvar, training,
                            vn.running_mean if training else None,
                            vn.running_var if training else None, ese[0].weight, ese[0].bias, ese[2].weight, ese[2].bias,
-                           packed(m.extra_sensor_pos_embed, 'f32'), mem, None, n_mem, n_pix)
+                           packed(m.extra_sensor_pos_embed, 'f32'), mem if mem.dtype == BF16 else None,
+                           mem if mem.dtype == F32 else None, n_mem, n_pix)
     if training:
       self._count_batch(vn)
     memf = mem.view(b * n_mem, d)

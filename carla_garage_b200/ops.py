@@ -12,6 +12,38 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_GELU = 0, 1, 2, 3
 
+# Activation storage dtype of the engine: bf16 (production) or fp32 (parity mode, csrc/fp32_path.cu).  Every wrapper
+# below dispatches on the dtype of the tensor it is handed; ACT_DTYPE only decides what the sources (stem conv, weight
+# packs, explicit buffers of engine.py) produce.
+ACT_DTYPE = [BF16]
+
+
+def set_precision(mode):
+  """'bf16' (default, the benchmarked tcgen05 path) or 'fp32' (north_star's 1e-3 parity mode: fp32 feature maps and
+  CUDA-core fp32 contractions, forward only)."""
+  if mode not in ('bf16', 'fp32'):
+    raise ValueError(mode)
+  ACT_DTYPE[0] = F32 if mode == 'fp32' else BF16
+
+
+def act_dtype():
+  return ACT_DTYPE[0]
+
+
+class precision:
+  """with ops.precision('fp32'): ..."""
+
+  def __init__(self, mode):
+    self.mode = mode
+
+  def __enter__(self):
+    self.prev = ACT_DTYPE[0]
+    set_precision(self.mode)
+
+  def __exit__(self, *exc):
+    ACT_DTYPE[0] = self.prev
+
+
 TAPS_1X1 = ((0, 0, 0, 0),)
 TAPS_3X3 = tuple((kx - 1, ky - 1, 0, ky * 3 + kx) for ky in range(3) for kx in range(3))
 
@@ -117,9 +149,12 @@ def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1
   a: (Ba, H, W, C) bf16 NHWC; w: (N, taps, K) bf16.  Returns a new (B,H,W,N) bf16 / (B,N,H,W) f32 tensor unless
   ``out`` (+ ``out_strides`` in elements (sb, sy, sx, sn)) is given.  stats = (sum, sumsq) f32 (N,) accumulators.
   """
-  _dev(w, BF16)
+  f32 = w.dtype == F32  # fp32 parity mode: same contract on tfpp_conv_gemm_f32
+  _dev(w, F32 if f32 else BF16)
+  if a.dtype != w.dtype:
+    raise RuntimeError(f'conv_gemm: activations are {a.dtype}, weight pack is {w.dtype}')
   if a_shape is None:  # contiguous NHWC tensor
-    _dev(a, BF16)
+    _dev(a)
     ab, h, wd, c = a.shape
   else:  # strided slab inside a larger bf16 buffer: a_shape = (Ba, H, W, C), images a_batch_stride elements apart
     ab, h, wd, c = a_shape
@@ -150,10 +185,10 @@ def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1
   else:
     if out is None:
       if out_layout == 'nhwc':
-        out = torch.empty((b, h, wd, n), dtype=F32 if out_f32 else BF16, device=a.device)
+        out = torch.empty((b, h, wd, n), dtype=F32 if (out_f32 or f32) else BF16, device=a.device)
         out_strides = nhwc_strides(h, wd, n)
       else:
-        out = torch.empty((b, n, h, wd), dtype=F32 if out_f32 else BF16, device=a.device)
+        out = torch.empty((b, n, h, wd), dtype=F32 if (out_f32 or f32) else BF16, device=a.device)
         out_strides = nchw_strides(h, wd, n)
     args.out = out.data_ptr()
     args.out_f32 = int(out.dtype == F32)
@@ -177,7 +212,10 @@ def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1
   if _PROFILE is not None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-  check(_lib.load().tfpp_conv_gemm(ctypes.byref(args), _stream()), 'tfpp_conv_gemm')
+  if f32:
+    check(_lib.load().tfpp_conv_gemm_f32(ctypes.byref(args), _stream()), 'tfpp_conv_gemm_f32')
+  else:
+    check(_lib.load().tfpp_conv_gemm(ctypes.byref(args), _stream()), 'tfpp_conv_gemm')
   if _PROFILE is not None:
     e1.record()
     k_alg = 24 if a_c_per_ntile else args.k_per_tile
@@ -246,7 +284,7 @@ def linear(x, w, bias=None, act=ACT_NONE, res=None, out_f32=False, out=None, row
     a4 = x.view(1, 1, rows, k)
     st = (0, 0, n, 1)
     if out is None:
-      out = torch.empty((rows, n), dtype=F32 if out_f32 else BF16, device=x.device)
+      out = torch.empty((rows, n), dtype=F32 if (out_f32 or x.dtype == F32) else BF16, device=x.device)
   else:
     rpg, gsr = row_map
     a4 = x.view(rows // rpg, 1, rpg, k)
@@ -276,10 +314,11 @@ def stem_conv(x, w, in_scale=None, in_shift=None, scale=None, shift=None, act=AC
   _dev(x, F32)
   _dev(w, F32)
   b, cin, h, wd = x.shape
-  out = torch.empty((b, h // 2, wd // 2, 32), dtype=BF16, device=x.device)
-  check(_lib.load().tfpp_stem_conv(x.data_ptr(), w.data_ptr(), _p(in_scale), _p(in_shift), _p(scale), _p(shift), act,
+  out = torch.empty((b, h // 2, wd // 2, 32), dtype=ACT_DTYPE[0], device=x.device)
+  fn = _lib.load().tfpp_stem_conv_f32 if ACT_DTYPE[0] == F32 else _lib.load().tfpp_stem_conv
+  check(fn(x.data_ptr(), w.data_ptr(), _p(in_scale), _p(in_shift), _p(scale), _p(shift), act,
                                    out.data_ptr(), _p(stats[0]) if stats else None, _p(stats[1]) if stats else None, b,
-                                   cin, h, wd, _stream()), 'tfpp_stem_conv')
+     cin, h, wd, _stream()), 'tfpp_stem_conv')
   return out
 
 
@@ -298,12 +337,12 @@ def bn_finalize(stat_sum, stat_sq, gamma, beta, running_mean, running_var, count
 
 def scale_shift_act(x, scale=None, shift=None, act=ACT_NONE, res=None, pool_sum=None, out=None, res_scale=None,
                     res_shift=None):
-  _dev(x, BF16)
+  _dev(x)
   b, h, w, c = x.shape
   y = torch.empty_like(x) if out is None else out
-  check(_lib.load().tfpp_scale_shift_act(x.data_ptr(), _p(res), _p(scale), _p(shift), _p(res_scale), _p(res_shift), act,
-                                         y.data_ptr(), _p(pool_sum),
-                                         b, h * w, c, _stream()), 'tfpp_scale_shift_act')
+  fn = _lib.load().tfpp_scale_shift_act_f32 if x.dtype == F32 else _lib.load().tfpp_scale_shift_act
+  check(fn(x.data_ptr(), _p(res), _p(scale), _p(shift), _p(res_scale), _p(res_shift), act,
+           y.data_ptr(), _p(pool_sum), b, h * w, c, _stream()), 'tfpp_scale_shift_act')
   return y
 
 
@@ -318,26 +357,33 @@ def se_gate(pool_sum, hw, w1, b1, w2, b2, want_hidden=False):
 
 
 def channel_scale(x, gate, out=None):
-  _dev(x, BF16)
+  _dev(x)
   b, h, w, c = x.shape
   y = torch.empty_like(x) if out is None else out
-  check(_lib.load().tfpp_channel_scale(x.data_ptr(), gate.data_ptr(), y.data_ptr(), b, h * w, c, _stream()),
-        'tfpp_channel_scale')
+  fn = _lib.load().tfpp_channel_scale_f32 if x.dtype == F32 else _lib.load().tfpp_channel_scale
+  check(fn(x.data_ptr(), gate.data_ptr(), y.data_ptr(), b, h * w, c, _stream()), 'tfpp_channel_scale')
   return y
 
 
 def parity_split(x):
-  _dev(x, BF16)
+  _dev(x)
   b, h, w, c = x.shape
-  y = torch.empty((4 * b, h // 2, w // 2, c), dtype=BF16, device=x.device)
-  check(_lib.load().tfpp_parity_split(x.data_ptr(), y.data_ptr(), b, h, w, c, _stream()), 'tfpp_parity_split')
+  y = torch.empty((4 * b, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+  fn = _lib.load().tfpp_parity_split_f32 if x.dtype == F32 else _lib.load().tfpp_parity_split
+  check(fn(x.data_ptr(), y.data_ptr(), b, h, w, c, _stream()), 'tfpp_parity_split')
   return y
 
 
 def avgpool_tokens(x, out, ph, pw, row0, pos_emb=None):
   """x (B,H,W,C) bf16 -> rows [row0, row0+ph*pw) of out (B, rows, C) f32|bf16 (+ pos_emb (rows, C) f32)."""
-  _dev(x, BF16)
+  _dev(x)
   b, h, w, c = x.shape
+  if x.dtype == F32:
+    if out.dtype != F32:
+      raise RuntimeError('fp32 mode: the token matrix must be float32')
+    check(_lib.load().tfpp_avgpool_tokens_f32(x.data_ptr(), _p(pos_emb), out.data_ptr(), b, h, w, c, ph, pw, out.shape[1],
+                                              row0, _stream()), 'tfpp_avgpool_tokens_f32')
+    return out
   check(_lib.load().tfpp_avgpool_tokens(x.data_ptr(), _p(pos_emb), out.data_ptr(), int(out.dtype == F32), b, h, w, c,
                                         ph, pw, out.shape[1], row0, _stream()), 'tfpp_avgpool_tokens')
   return out
@@ -349,17 +395,28 @@ def bilinear(src, batch, sh, sw, dh, dw, channels, src_batch_stride=None, src_ro
     src_batch_stride = sh * sw * channels
   if src_row_stride is None:
     src_row_stride = channels
-  out = torch.empty((batch, dh, dw, channels), dtype=BF16, device=src.device)
   ptr = src.data_ptr() + src_offset * src.element_size()
+  if ACT_DTYPE[0] == F32:
+    if src.dtype != F32 or (add is not None and add.dtype != F32):
+      raise RuntimeError('fp32 mode: bilinear expects float32 tensors')
+    out = torch.empty((batch, dh, dw, channels), dtype=F32, device=src.device)
+    check(_lib.load().tfpp_bilinear_f32(ptr, src_batch_stride, src_row_stride, _p(add), out.data_ptr(), batch, sh, sw, dh,
+                                        dw, channels, _stream()), 'tfpp_bilinear_f32')
+    return out
+  out = torch.empty((batch, dh, dw, channels), dtype=BF16, device=src.device)
   check(_lib.load().tfpp_bilinear(ptr, int(src.dtype == F32), src_batch_stride, src_row_stride, _p(add), out.data_ptr(),
                                   batch, sh, sw, dh, dw, channels, _stream()), 'tfpp_bilinear')
   return out
 
 
 def bilinear_nchw_mask(src, channels, dh, dw, mask=None):
-  _dev(src, BF16)
+  _dev(src)
   b, sh, sw, cs = src.shape
   out = torch.empty((b, channels, dh, dw), dtype=F32, device=src.device)
+  if src.dtype == F32:
+    check(_lib.load().tfpp_bilinear_nchw_mask_f32(src.data_ptr(), _p(mask), out.data_ptr(), b, sh, sw, cs, channels, dh, dw,
+                                                  _stream()), 'tfpp_bilinear_nchw_mask_f32')
+    return out
   check(_lib.load().tfpp_bilinear_nchw_mask(src.data_ptr(), _p(mask), out.data_ptr(), b, sh, sw, cs, channels, dh, dw,
                                             _stream()), 'tfpp_bilinear_nchw_mask')
   return out
@@ -383,12 +440,19 @@ def nhwc_to_nchw(x):
 
 def layernorm(x, gamma, beta, want_bf16=True, want_f32=False, eps=1e-5, save=False):
   rows, c = x.shape
+  if ACT_DTYPE[0] == F32:  # parity mode: the GEMM operand copy is the fp32 result itself
+    want_f32 = want_f32 or want_bf16
+    alias_b, want_bf16 = want_bf16, False
+  else:
+    alias_b = False
   yb = torch.empty((rows, c), dtype=BF16, device=x.device) if want_bf16 else None
   yf = torch.empty((rows, c), dtype=F32, device=x.device) if want_f32 else None
   mean = torch.empty(rows, dtype=F32, device=x.device) if save else None
   rstd = torch.empty(rows, dtype=F32, device=x.device) if save else None
   check(_lib.load().tfpp_layernorm(x.data_ptr(), int(x.dtype == F32), gamma.data_ptr(), beta.data_ptr(), _p(yb), _p(yf),
                                    _p(mean), _p(rstd), rows, c, eps, _stream()), 'tfpp_layernorm')
+  if alias_b:
+    yb = yf
   return yb, yf, mean, rstd
 
 
@@ -407,7 +471,15 @@ def dropout_(x, drop):
 
 
 def fusion_attn(qkv, batch, tokens, channels, heads, drop=None):
-  _dev(qkv, BF16)
+  _dev(qkv)
+  if qkv.dtype == F32:
+    out = torch.empty((batch * tokens, channels), dtype=F32, device=qkv.device)
+    c3, hd = 3 * channels, channels // heads
+    base = qkv.data_ptr()
+    check(_lib.load().tfpp_mha_f32(base, tokens * c3, c3, base + 4 * channels, tokens * c3, c3, base + 8 * channels,
+                                   tokens * c3, c3, out.data_ptr(), tokens * channels, channels, batch, heads, tokens,
+                                   tokens, hd, *_drop_args(drop), _stream()), 'tfpp_mha_f32')
+    return out
   out = torch.empty((batch * tokens, channels), dtype=BF16, device=qkv.device)
   check(_lib.load().tfpp_fusion_attn_dropout(qkv.data_ptr(), out.data_ptr(), batch, tokens, channels, heads,
                                              *_drop_args(drop), _stream()), 'tfpp_fusion_attn')
@@ -418,6 +490,13 @@ def small_mha(q, k, v, batch, heads, tq, tk, head_dim, q_strides, k_strides, v_s
               drop=None):
   """bf16 views given as (tensor, element offset, (batch stride, row stride)); returns (B*tq, heads*head_dim) bf16."""
   d = heads * head_dim
+  if q.dtype == F32:
+    out = torch.empty((batch * tq, d), dtype=F32, device=q.device)
+    check(_lib.load().tfpp_mha_f32(q.data_ptr() + 4 * q_off, q_strides[0], q_strides[1], k.data_ptr() + 4 * k_off,
+                                   k_strides[0], k_strides[1], v.data_ptr() + 4 * v_off, v_strides[0], v_strides[1],
+                                   out.data_ptr(), tq * d, d, batch, heads, tq, tk, head_dim, *_drop_args(drop), _stream()),
+          'tfpp_mha_f32')
+    return out
   out = torch.empty((batch * tq, d), dtype=BF16, device=q.device)
   check(_lib.load().tfpp_small_mha_dropout(q.data_ptr() + 2 * q_off, q_strides[0], q_strides[1],
                                            k.data_ptr() + 2 * k_off, k_strides[0], k_strides[1],
@@ -469,6 +548,21 @@ def decode_heatmap(heat, wh, offset, yaw_cls, yaw_res, k=100, img_h=256, img_w=2
   return out
 
 
+def nms_rotated(boxes, conf_threshold, iou_threshold, to_vehicle=False, pixels_per_meter=4.0, min_x=-32.0, min_y=-32.0,
+                want_index=False):
+  """boxes (B, M <= 512, S) f32 cuda, score in the last column -> (kept boxes (B, M, S) highest score first and zero
+  padded, counts (B,) int32[, source rows (B, M) int32]): model.py:447-459 + transfuser_utils.py:409-452 per frame."""
+  _dev(boxes, F32)
+  b, m, s = boxes.shape
+  out = torch.empty_like(boxes)
+  count = torch.empty(b, dtype=torch.int32, device=boxes.device)
+  index = torch.empty((b, m), dtype=torch.int32, device=boxes.device) if want_index else None
+  check(_lib.load().tfpp_nms_rotated(boxes.data_ptr(), b, m, s, float(conf_threshold), float(iou_threshold),
+                                     int(to_vehicle), float(pixels_per_meter), float(min_x), float(min_y), out.data_ptr(),
+                                     count.data_ptr(), _p(index), _stream()), 'tfpp_nms_rotated')
+  return (out, count, index) if want_index else (out, count)
+
+
 # ---------------------------------------------------------------------------------------------- weight packing
 # (load-time plumbing: layout changes of parameters, no activations involved)
 def gconv3x3_supported(channels, group_width):
@@ -478,10 +572,16 @@ def gconv3x3_supported(channels, group_width):
 def gconv3x3(x, w, stride=1, scale=None, shift=None, act=ACT_NONE, stats=None):
   """Grouped 3x3 conv (group width 24, pad 1) on the haloed-tile kernel.  x (B,H,W,C) bf16, w (C/24, 9, 24, 24) bf16
   (pack_gconv_halo); returns (B,H/stride,W/stride,C) bf16.  stats = (sum, sumsq) f32 (C) accumulate the raw output."""
-  _dev(x, BF16)
-  _dev(w, BF16)
+  _dev(x)
+  _dev(w, x.dtype)
   b, h, wd, c = x.shape
-  out = torch.empty((b, h // stride, wd // stride, c), dtype=BF16, device=x.device)
+  out = torch.empty((b, h // stride, wd // stride, c), dtype=x.dtype, device=x.device)
+  if x.dtype == F32:
+    check(_lib.load().tfpp_gconv3x3_f32(x.data_ptr(), w.data_ptr(), out.data_ptr(), _p(scale), _p(shift), act,
+                                        _p(stats[0]) if stats is not None else None,
+                                        _p(stats[1]) if stats is not None else None, b, h, wd, c, stride, _stream()),
+          'tfpp_gconv3x3_f32')
+    return out
   check(_lib.load().tfpp_gconv3x3(x.data_ptr(), w.data_ptr(), out.data_ptr(), _p(scale), _p(shift), act,
                                   _p(stats[0]) if stats is not None else None,
                                   _p(stats[1]) if stats is not None else None, b, h, wd, c, stride, _stream()),

@@ -5,6 +5,8 @@ gradient.  Replaces Engine.train's inner loop (team_code/train.py:883-916): forw
 all-reduce (train.py:516).  Dropout (embd/attn/resid_pdrop = 0.1 and nn.TransformerDecoderLayer's 0.1) is not applied
 — see DESIGN.md "Dropout".
 """
+import os
+
 import torch
 
 from . import engine as eng_mod
@@ -37,8 +39,9 @@ class FlatState:
   weights / biases of every fusion attention, and the five CenterNet head convs (3x3 weights, 3x3 biases, 1x1 biases).
   """
 
-  def __init__(self, model, assign_grad=True, include_frozen=False):
-    """assign_grad: point every p.grad at its slice of the flat gradient (Trainer).  The autograd boundary leaves
+  def __init__(self, model, assign_grad=True, include_frozen=False, alloc=None):
+    """alloc: optional callable total -> (flat, grad) zero-filled fp32 tensors of ``total`` elements (the NVLink peer
+    buffers of carla_garage_b200.peer when the ranks exchange gradients through peer memory).  assign_grad: point every p.grad at its slice of the flat gradient (Trainer).  The autograd boundary leaves
     p.grad to torch's AccumulateGrad nodes instead.  include_frozen: also adopt requires_grad=False parameters
     (train.py:495-508 freezes sub-modules) so the backward handlers have somewhere to write; constants such as
     valid_bev_pixels stay out."""
@@ -83,8 +86,12 @@ class FlatState:
       off += p.numel()
     total = off + ((-off) % 4)
     dev = self.params[0].device
-    self.flat = torch.zeros(total, dtype=F32, device=dev)
-    self.grad = torch.zeros(total, dtype=F32, device=dev)
+    if alloc is not None:
+      self.flat, self.grad = alloc(total)
+      assert self.flat.numel() == total and self.grad.numel() == total and self.flat.dtype == F32
+    else:
+      self.flat = torch.zeros(total, dtype=F32, device=dev)
+      self.grad = torch.zeros(total, dtype=F32, device=dev)
     self.offsets = {}
     for (n, p), off in zip(ordered, offs):
       k = p.numel()
@@ -837,13 +844,32 @@ class Trainer:
   """One process per GPU.  step(batch) = forward + fused losses + backward + (bucketed all-reduce) + AdamW."""
 
   def __init__(self, model, lr=3e-4, weight_decay=0.01, loss_weights=None, process_group=None, bucket_mb=64,
-               use_optim_groups=False):
+               use_optim_groups=False, exchange=None):
+    """exchange (world > 1): 'peer' = gradients reduce-scattered out of the peers' buffers over NVLink inside the fused
+    AdamW kernel, parameters pushed back (csrc/peer_exchange.cu; the whole step stays one CUDA graph); 'nccl' = bucketed
+    NCCL all-reduce between two graphs (round 1).  Default: 'peer' on CUDA (TFPP_EXCHANGE overrides), 'nccl' otherwise
+    (the gloo CPU tests)."""
     self.model = model
     self.eng = model.engine
     if getattr(model, '_boundary', None) is not None:
       raise RuntimeError('this model already trains through the autograd boundary (model(...) in training mode)')
     object.__setattr__(model, '_trainer_owned', True)
-    self.st = FlatState(model, include_frozen=True)
+    world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    on_cuda = next(model.parameters()).is_cuda
+    if exchange is None:
+      exchange = os.environ.get('TFPP_EXCHANGE', 'peer' if on_cuda else 'nccl')
+    if exchange not in ('peer', 'nccl'):
+      raise ValueError(exchange)
+    self.xchg = None
+    self.local_only = False   # bench.py's rank-local instrumented step: skip the exchange
+    alloc = None
+    if world > 1 and exchange == 'peer':
+      from . import peer  # pylint: disable=import-outside-toplevel
+
+      def alloc(total):
+        self.xchg = peer.PeerExchange(process_group, total)
+        return self.xchg.param, self.xchg.grad
+    self.st = FlatState(model, include_frozen=True, alloc=alloc)
     if use_optim_groups:  # train.py:522-525: decay / no-decay split by parameter name and module type
       groups = model.create_optimizer_groups(weight_decay)
       self.st.set_flags(no_decay=[p for g in groups if g['weight_decay'] == 0.0 for p in g['params']])
@@ -875,8 +901,8 @@ class Trainer:
   def allreduce(self):
     """DDP semantics (train.py:516): sum-all-reduce the flat gradient in buckets, averaged by world size inside the
     AdamW kernel (grad_scale)."""
-    if self.world == 1:
-      return
+    if self.world == 1 or self.xchg is not None or self.local_only:
+      return   # peer mode: the reduction happens inside the optimizer kernel
     allreduce_flat(self.st.grad, self.pg, self.bucket_elems)
 
   def _with_plan(self, fn):
@@ -889,7 +915,16 @@ class Trainer:
 
   def optimizer_step(self, lr='default'):
     """AdamW over the flat buffers (gradient averaged over the ranks inside the kernel) + weight-pack refresh."""
-    self.st.adamw_step(self.lr if lr == 'default' else lr, weight_decay=self.wd, grad_scale=1.0 / self.world)
+    lr = self.lr if lr == 'default' else lr
+    if self.xchg is not None and not self.local_only:
+      st = self.st
+      st.step_count += 1
+      if lr is not None:
+        st.dev_state[1:2].fill_(lr)
+      self.xchg.step(st, weight_decay=self.wd)   # reduce-scatter + AdamW on the owned shard + parameter all-gather
+      eng_mod.PARAM_EPOCH[0] += 1
+    else:
+      self.st.adamw_step(lr, weight_decay=self.wd, grad_scale=1.0 / (1 if self.local_only else self.world))
     if self.plan is not None:
       self.plan.refresh()  # one gather kernel: every bf16 weight pack follows the new parameters
       if not torch.cuda.is_current_stream_capturing():
@@ -912,7 +947,7 @@ class Trainer:
     self._slab = {k: v.clone() for k, v in labels.items()}
     self._spts = points.clone() if points is not None else None
     self.st.dev_state[1:2].fill_(self.lr)
-    self._split = (self.world > 1) if split is None else bool(split)
+    self._split = (self.world > 1 and self.xchg is None) if split is None else bool(split)
 
     def fwd_bwd():
       if self._spts is not None:

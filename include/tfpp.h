@@ -370,6 +370,75 @@ int tfpp_adamw_amsgrad(float* param, const float* grad, float* exp_avg, float* e
                        long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                        float grad_scale, float* dev_state, const unsigned char* flags, tfpp_stream_t stream);
 
+/* ---- fp32 parity mode (csrc/fp32_path.cu) ------------------------------------------------------------------------
+ * BASELINE.json north_star: "within 1e-3 rel fp32 / 1e-2 bf16".  The same op contracts as their bf16 twins above with
+ * fp32 feature maps / weight packs and fp32 CUDA-core contractions (train.py:374-377 is the reference's effective
+ * precision: fp32, TF32 off).  carla_garage_b200.ops dispatches to them when the activation dtype is float32
+ * (ops.set_precision('fp32')); they serve the end-to-end parity tests, never the benchmarked path. */
+int tfpp_conv_gemm_f32(const tfpp_conv_gemm_args* args, tfpp_stream_t stream); /* a, w: f32; bn/tw/th/nb ignored */
+int tfpp_gconv3x3_f32(const float* x, const float* w, float* out, const float* scale, const float* shift, int act,
+                      float* stat_sum, float* stat_sq, int batch, int height, int width, int channels, int stride,
+                      tfpp_stream_t stream);
+int tfpp_stem_conv_f32(const float* x, const float* w, const float* in_scale, const float* in_shift, const float* scale,
+                       const float* shift, int act, float* out, float* stat_sum, float* stat_sq, int batch, int cin,
+                       int height, int width, tfpp_stream_t stream);
+int tfpp_scale_shift_act_f32(const float* x, const float* res, const float* scale, const float* shift,
+                             const float* res_scale, const float* res_shift, int act, float* y, float* pool_sum,
+                             int batch, int hw, int channels, tfpp_stream_t stream);
+int tfpp_channel_scale_f32(const float* x, const float* gate, float* y, int batch, int hw, int channels,
+                           tfpp_stream_t stream);
+int tfpp_parity_split_f32(const float* x, float* y, int batch, int height, int width, int channels, tfpp_stream_t stream);
+int tfpp_avgpool_tokens_f32(const float* x, const float* pos_emb, float* out, int batch, int height, int width,
+                            int channels, int ph, int pw, int rows_per_batch, int row0, tfpp_stream_t stream);
+int tfpp_bilinear_f32(const float* src, long long src_batch_stride, long long src_row_stride, const float* add,
+                      float* out, int batch, int sh, int sw, int dh, int dw, int channels, tfpp_stream_t stream);
+int tfpp_bilinear_nchw_mask_f32(const float* src, const float* mask, float* out, int batch, int sh, int sw,
+                                int src_channels, int channels, int dh, int dw, tfpp_stream_t stream);
+/* attention core of both transformers (transfuser.py:367-376, model.py:137-143) on row-strided f32 q/k/v views;
+ * probability dropout indexed like tfpp_fusion_attn_dropout / tfpp_small_mha_dropout */
+int tfpp_mha_f32(const float* q, long long q_sb, long long q_sr, const float* k, long long k_sb, long long k_sr,
+                 const float* v, long long v_sb, long long v_sr, float* out, long long o_sb, long long o_sr, int batch,
+                 int heads, int tq, int tk, int head_dim, const unsigned long long* drop_rng, float drop_p,
+                 unsigned drop_site, tfpp_stream_t stream);
+
+/* ---- data-parallel gradient exchange over NVLink peer memory, fused with AdamW (csrc/peer_exchange.cu) -----------
+ * Replaces DistributedDataParallel's NCCL all-reduce (train.py:516) + ZeroRedundancyOptimizer(AdamW) (train.py:527-531):
+ * one kernel per step reduce-scatters the flat gradient out of the peers' buffers, steps AdamW(amsgrad) on the shard
+ * this rank owns (gradient averaged over the ranks) and pushes the new parameters into every rank's flat parameter
+ * buffer, between two flag barriers.  Buffers come from tfpp_peer_alloc (cudaMalloc + CUDA IPC handle, zero filled) and
+ * are mapped into the other processes with tfpp_peer_open.  Plain kernels only: CUDA-graph capturable. */
+#define TFPP_MAX_PEERS 8
+int tfpp_peer_alloc(long long bytes, void** ptr, void* handle64);
+int tfpp_peer_open(const void* handle64, void** ptr);
+int tfpp_peer_close(void* ptr);
+int tfpp_peer_free(void* ptr);
+typedef struct {
+  int world, rank;
+  float* grad[TFPP_MAX_PEERS];      /* every rank's flat gradient (entry `rank` = the local buffer) */
+  float* param[TFPP_MAX_PEERS];     /* every rank's flat parameter buffer */
+  unsigned* flags[TFPP_MAX_PEERS];  /* every rank's barrier words: (2 * TFPP_MAX_PEERS + 2) uint32, zero initialised */
+  float* exp_avg;                   /* local AdamW state, full length n (only the owned shard is touched) */
+  float* exp_avg_sq;
+  float* max_exp_avg_sq;
+  long long n;                      /* elements of the flat buffers, multiple of 4 */
+  float beta1, beta2, eps, weight_decay;
+  float* dev_state;                 /* [step, lr, 1-beta1^step, sqrt(1-beta2^step)] as in tfpp_adamw_amsgrad */
+  const unsigned char* opt_flags;   /* per-element flags as in tfpp_adamw_amsgrad, or NULL */
+} tfpp_peer_step_args;
+int tfpp_peer_adamw_step(const tfpp_peer_step_args* args, tfpp_stream_t stream);
+int tfpp_peer_barrier(const tfpp_peer_step_args* args, int slot, tfpp_stream_t stream); /* flag barrier only (tests) */
+
+/* ---- ensemble bounding-box merge (csrc/nms.cu) --------------------------------------------------------------------
+ * sensor_agent.py:445-491: per frame, the union of the ensemble members' decoded boxes (center_net.py:172-237 rows
+ * (x, y, half w, half h, yaw, ..., score), `stride` floats each, score last) is thresholded (score > conf_threshold,
+ * model.py:449), optionally converted image -> vehicle frame (transfuser_utils.py:388-406) and merged by rotated-IoU
+ * non-maximum suppression (transfuser_utils.py:409-452; shapely polygon IoU restated as convex clipping).
+ * boxes / out_boxes: (batch, num_boxes <= 512, stride) f32; out_boxes holds the kept boxes, highest score first, rows
+ * >= out_count[b] zero; out_index (optional, (batch, num_boxes) int32): source row of every kept box, -1 after. */
+int tfpp_nms_rotated(const float* boxes, int batch, int num_boxes, int stride, float conf_threshold, float iou_threshold,
+                     int to_vehicle, float pixels_per_meter, float min_x, float min_y, float* out_boxes, int* out_count,
+                     int* out_index, tfpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

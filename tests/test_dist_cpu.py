@@ -55,3 +55,14 @@ def test_flat_state_layout_cpu():
   # parameters are views of the flat buffer, gradients of the flat gradient
   p = net.change_channel.weight
   assert p.data_ptr() >= st.flat.data_ptr() and p.grad.data_ptr() == st.g(p).data_ptr()
+
+
+def test_peer_shard_bounds_cover_the_buffer_once():
+  """carla_garage_b200.peer.shard_bounds == the partition tfpp_peer_adamw_step uses (float4-granular equal chunks)."""
+  from carla_garage_b200.peer import shard_bounds
+  for n in (4, 8, 4 * 1000003 + 28, 120342512):
+    for world in (1, 2, 3, 4, 8):
+      spans = [shard_bounds(n, world, r) for r in range(world)]
+      assert spans[0][0] == 0 and spans[-1][1] == n
+      for (lo, hi), (lo2, _) in zip(spans, spans[1:]):
+        assert hi == lo2 and lo % 4 == 0 and hi % 4 == 0 and lo <= hi

@@ -129,3 +129,38 @@ def test_philox_known_answers():
   t = torch.ones(2, 8)
   s1, s2 = ph.DropoutStream(5, 1), ph.DropoutStream(5, 1)
   assert torch.equal(s1(t, 0.5), s2(t, 0.5)) and s1.site == 1 and torch.equal(s1(t, 0.0), t) and s1.site == 1
+
+
+def test_nms_oracle_closed_form_iou():
+  """oracle/nms.py (transfuser_utils.py:409-452 with shapely's polygon IoU restated as convex clipping) against
+  closed-form intersections."""
+  import math
+  from oracle import nms
+  a = (0.0, 0.0, 2.0, 1.0, 0.0)
+  assert abs(nms.iou_bbs(a, a) - 1.0) < 1e-12
+  assert abs(nms.iou_bbs(a, (1.0, 0.0, 2.0, 1.0, 0.0)) - 0.6) < 1e-12          # 3x2 overlap of two 4x2 boxes
+  assert nms.iou_bbs(a, (10.0, 0.0, 2.0, 1.0, 0.3)) == 0.0
+  sq, sq45 = (3.0, -2.0, 1.0, 1.0, 0.0), (3.0, -2.0, 1.0, 1.0, math.pi / 4)
+  octagon = 8.0 * (math.sqrt(2.0) - 1.0)                                          # square ∩ its 45 degree copy
+  assert abs(nms.iou_bbs(sq, sq45) - octagon / (8.0 - octagon)) < 1e-12
+  # a quarter turn swaps the extents: 2x1 vs 1x2 half extents overlap in the central 2x2 square
+  assert abs(nms.iou_bbs(a, (0.0, 0.0, 2.0, 1.0, math.pi / 2)) - 4.0 / 12.0) < 1e-12
+  # IoU is symmetric and invariant under a common rigid motion
+  b1, b2 = (1.0, 2.0, 2.5, 1.2, 0.4), (2.0, 2.5, 1.5, 2.2, -0.9)
+  i12 = nms.iou_bbs(b1, b2)
+  assert abs(i12 - nms.iou_bbs(b2, b1)) < 1e-12 and 0.0 < i12 < 1.0
+  th, c, s = 0.7, math.cos(0.7), math.sin(0.7)
+  mv = lambda b: (c * b[0] - s * b[1] + 5.0, s * b[0] + c * b[1] - 3.0, b[2], b[3], b[4] + th)
+  assert abs(nms.iou_bbs(mv(b1), mv(b2)) - i12) < 1e-12
+
+
+def test_nms_oracle_greedy_order_and_vehicle_frame():
+  from oracle import nms
+  boxes = [[(0.0, 0.0, 2.0, 1.0, 0.0, 0.9), (0.5, 0.0, 2.0, 1.0, 0.0, 0.8)],      # member 0: second overlaps the first
+           [(10.0, 0.0, 2.0, 1.0, 0.0, 0.7), (0.1, 0.1, 2.0, 1.0, 0.1, 0.95)],    # member 1: best box of all + a far one
+           None]                                                                  # member without detections
+  kept = nms.non_maximum_suppression(boxes, 0.2)
+  assert [float(k[-1]) for k in kept] == [0.95, 0.7]
+  assert nms.non_maximum_suppression([[], None], 0.2) == []
+  v = nms.bb_image_to_vehicle_system([140.0, 100.0, 8.0, 4.0, 0.3, 1.0, 0.0, 0.0, 0.9], 4.0, -32.0, -32.0)
+  assert np.allclose(v[:5], [(100.0 - 128.0) / 4, (140.0 - 128.0) / 4, 1.0, 2.0, -0.3])
