@@ -115,6 +115,7 @@ _PROTOS = {
     'tfpp_small_mha_bwd_dropout': [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, I, P, F, I,
                                    P],
     'tfpp_adamw_amsgrad': [P, P, P, P, P, L, F, F, F, F, F, I, F, P, P, P],
+    'tfpp_centernet_targets': [P, P, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
     'tfpp_nms_rotated': [P, I, I, I, F, F, I, F, F, F, P, P, P, P],
     # NVLink peer-memory gradient exchange fused with AdamW (csrc/peer_exchange.cu)
     'tfpp_peer_alloc': [L, ctypes.POINTER(c_void_p), P],

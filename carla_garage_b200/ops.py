@@ -548,6 +548,32 @@ def decode_heatmap(heat, wh, offset, yaw_cls, yaw_res, k=100, img_h=256, img_w=2
   return out
 
 
+def centernet_targets(boxes, counts=None, feat_h=64, feat_w=64, img_h=256, img_w=256, num_classes=4, num_dir_bins=12):
+  """Ground-truth boxes (B, N <= 128, 8) f32 cuda (+ counts (B,) int32) -> the CenterNet label maps of
+  CARLA_Data.get_targets (data.py:698-791) as a dict keyed like training.compute_losses' labels (+ velocity, brake)."""
+  _dev(boxes, F32)
+  b, n, _ = boxes.shape
+  dev = boxes.device
+  lab = {'center_heatmap': torch.empty((b, num_classes, feat_h, feat_w), dtype=F32, device=dev),
+         'wh': torch.empty((b, 2, feat_h, feat_w), dtype=F32, device=dev),
+         'offset': torch.empty((b, 2, feat_h, feat_w), dtype=F32, device=dev),
+         'yaw_class': torch.empty((b, feat_h, feat_w), dtype=torch.int64, device=dev),
+         'yaw_res': torch.empty((b, 1, feat_h, feat_w), dtype=F32, device=dev),
+         'velocity': torch.empty((b, 1, feat_h, feat_w), dtype=F32, device=dev),
+         'brake': torch.empty((b, feat_h, feat_w), dtype=torch.int64, device=dev),
+         'pixel_weight': torch.empty((b, 2, feat_h, feat_w), dtype=F32, device=dev),
+         'avg_factor': torch.empty(b, dtype=F32, device=dev)}
+  if counts is not None:
+    counts = _dev(counts, torch.int32)
+  check(_lib.load().tfpp_centernet_targets(boxes.data_ptr(), _p(counts), b, n, feat_h, feat_w, img_h, img_w, num_classes,
+                                           num_dir_bins, lab['center_heatmap'].data_ptr(), lab['wh'].data_ptr(),
+                                           lab['offset'].data_ptr(), lab['yaw_class'].data_ptr(), lab['yaw_res'].data_ptr(),
+                                           lab['velocity'].data_ptr(), lab['brake'].data_ptr(),
+                                           lab['pixel_weight'].data_ptr(), lab['avg_factor'].data_ptr(), _stream()),
+        'tfpp_centernet_targets')
+  return lab
+
+
 def nms_rotated(boxes, conf_threshold, iou_threshold, to_vehicle=False, pixels_per_meter=4.0, min_x=-32.0, min_y=-32.0,
                 want_index=False):
   """boxes (B, M <= 512, S) f32 cuda, score in the last column -> (kept boxes (B, M, S) highest score first and zero

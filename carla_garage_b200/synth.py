@@ -143,3 +143,22 @@ def golden_state(golden_dir):
   for k in calib.files:
     sd[k] = torch.from_numpy(calib[k]).clone()
   return sd
+
+
+def make_gt_boxes(n_samples, seed=1234, max_boxes=30):
+  """Ground-truth boxes as data.py:937-1000 hands them to get_targets: per sample an (N, 8) float32 array of
+  (x, y, extent_x, extent_y, yaw, speed, brake, class) in BEV pixel coordinates of the 256 x 256 LiDAR image."""
+  g = _gen(seed, 'gt_boxes')
+  out = []
+  for _ in range(n_samples):
+    n = int(torch.randint(1, max_boxes + 1, (1,), generator=g))
+    b = torch.zeros(n, 8)
+    b[:, 0:2] = torch.rand(n, 2, generator=g) * 255.0
+    b[:, 2] = torch.rand(n, generator=g) * 14.0 + 1.5      # half extents in pixels (4 px / m)
+    b[:, 3] = torch.rand(n, generator=g) * 6.0 + 1.5
+    b[:, 4] = (torch.rand(n, generator=g) * 2 - 1) * math.pi
+    b[:, 5] = torch.rand(n, generator=g) * 10.0
+    b[:, 6] = torch.rand(n, generator=g)
+    b[:, 7] = torch.randint(0, 4, (n,), generator=g).float()
+    out.append(b.numpy().astype(np.float32))
+  return out

@@ -439,6 +439,17 @@ int tfpp_nms_rotated(const float* boxes, int batch, int num_boxes, int stride, f
                      int to_vehicle, float pixels_per_meter, float min_x, float min_y, float* out_boxes, int* out_count,
                      int* out_index, tfpp_stream_t stream);
 
+/* ---- CenterNet training targets on the device (csrc/targets.cu) ---------------------------------------------------
+ * CARLA_Data.get_targets (data.py:698-791) + gaussian_target.py:11-61,160-183 + angle2class (center_net.py:240-254):
+ * boxes (batch, max_boxes <= 128, 8) f32 = (x, y, extent_x, extent_y, yaw, speed, brake, class) in BEV pixels of the
+ * img_h x img_w LiDAR image, counts (batch) int32 valid boxes per sample (NULL = all).  Outputs in the layout the train
+ * loop moves to the device (train.py:693-766): center_heatmap (B,num_classes,H,W), wh / offset / pixel_weight (B,2,H,W),
+ * yaw_class (B,H,W) int64, yaw_res (B,1,H,W), velocity (B,1,H,W) or NULL, brake (B,H,W) int64 or NULL, avg_factor (B). */
+int tfpp_centernet_targets(const float* boxes, const int* counts, int batch, int max_boxes, int feat_h, int feat_w,
+                           int img_h, int img_w, int num_classes, int num_dir_bins, float* center_heatmap, float* wh,
+                           float* offset, long long* yaw_class, float* yaw_res, float* velocity, long long* brake,
+                           float* pixel_weight, float* avg_factor, tfpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

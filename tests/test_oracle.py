@@ -164,3 +164,22 @@ def test_nms_oracle_greedy_order_and_vehicle_frame():
   assert nms.non_maximum_suppression([[], None], 0.2) == []
   v = nms.bb_image_to_vehicle_system([140.0, 100.0, 8.0, 4.0, 0.3, 1.0, 0.0, 0.0, 0.9], 4.0, -32.0, -32.0)
   assert np.allclose(v[:5], [(100.0 - 128.0) / 4, (140.0 - 128.0) / 4, 1.0, 2.0, -0.3])
+
+
+def test_targets_oracle_vs_reference_golden():
+  """oracle/targets.py == the unmodified reference rasteriser (data.py:698-791, gaussian_target.py) on 8 cases incl.
+  borders, an empty sample and two boxes sharing a centre pixel (tests/golden/make_targets_golden.py)."""
+  from oracle import targets
+  g = np.load(os.path.join(GOLDEN, 'targets.npz'))
+  n = sum(1 for k in g.files if k.startswith('boxes'))
+  assert n == 8
+  for i in range(n):
+    t, avg = targets.get_targets(g[f'boxes{i}'])
+    assert avg == int(g[f'avg{i}']), i
+    for k, v in t.items():
+      want = g[f'{k}{i}']
+      if v.dtype.kind == 'i':
+        assert np.array_equal(v, want), (i, k)
+      else:
+        assert np.allclose(v, want, rtol=0, atol=1e-6), (i, k, float(np.abs(v - want).max()))
+    assert np.array_equal(t['center_heatmap_target'] == 1, g[f'center_heatmap_target{i}'] == 1)

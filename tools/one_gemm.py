@@ -29,5 +29,46 @@ elif which == 'ssa':
   x = torch.randn(32, 64, 256, 72, device='cuda').to(torch.bfloat16); y = torch.empty_like(x)
   sc, sh = torch.rand(72, device='cuda'), torch.rand(72, device='cuda')
   f = lambda: ops.scale_shift_act(x, sc, sh, ops.ACT_RELU, out=y)
+elif which == 'halo':
+  x = torch.randn(32, 256, 1024, 32, device='cuda').to(torch.bfloat16)
+  wp = ops.pack_halo_umma_weight(torch.randn(32, 32, 3, 3, device='cuda'), 32)
+  f = lambda: ops.halo_conv3x3(x, wp)
+elif which.startswith('attn'):
+  c = int(which[4:] or 576)
+  qkv = torch.randn(32 * 320, 3 * c, device='cuda').to(torch.bfloat16)
+  f = lambda: ops.fusion_attn(qkv, 32, 320, c, 4)
+elif which.startswith('battn'):
+  c = int(which[5:] or 576)
+  qkv = torch.randn(32 * 320, 3 * c, device='cuda').to(torch.bfloat16); do = torch.randn(32 * 320, c, device='cuda').to(torch.bfloat16)
+  f = lambda: ops.fusion_attn_bwd(qkv, do, 32, 320, c, 4)
+elif which == 'pillar':
+  from carla_garage_b200 import synth
+  pts = synth.make_point_clouds(32, seed=1).cuda()
+  f = lambda: ops.pillar_scatter(pts)
+elif which == 'nms':
+  bx = torch.rand(64, 300, 9, device='cuda'); bx[..., :2] = bx[..., :2] * 200 + 28; bx[..., 2:4] = bx[..., 2:4] * 8 + 3
+  f = lambda: ops.nms_rotated(bx, 0.3, 0.2, to_vehicle=True)
+elif which == 'targets':
+  from carla_garage_b200 import synth
+  import numpy as np
+  cs = synth.make_gt_boxes(32, seed=2)
+  bx = torch.zeros(32, 30, 8); cnt = torch.zeros(32, dtype=torch.int32)
+  for i, c_ in enumerate(cs): bx[i, :len(c_)] = torch.from_numpy(c_); cnt[i] = len(c_)
+  bx, cnt = bx.cuda(), cnt.cuda()
+  f = lambda: ops.centernet_targets(bx, cnt)
 for _ in range(4): f()
 torch.cuda.synchronize()
+if len(sys.argv) > 2 and sys.argv[2] == 'time':  # CUDA-event timing, L2 flushed between launches
+  flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+  ts = []
+  for _ in range(10):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); f(); e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+  ts.sort()
+  print(f'{which}: median {ts[len(ts) // 2]:.1f} us  min {ts[0]:.1f} us')
+else:
+  f()
+  torch.cuda.synchronize()
