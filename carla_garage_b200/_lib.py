@@ -135,6 +135,19 @@ _PROTOS = {
     'tfpp_bilinear_f32': [P, L, L, P, P, I, I, I, I, I, I, P],
     'tfpp_bilinear_nchw_mask_f32': [P, P, P, I, I, I, I, I, I, I, P],
     'tfpp_mha_f32': [P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, P, F, I, P],
+    'tfpp_conv_wgrad_f32': [ctypes.POINTER(WgradArgs), P],
+    'tfpp_gconv3x3_wgrad_f32': [P, P, P, I, I, I, I, I, P],
+    'tfpp_gconv3x3_dgrad_s2_f32': [P, P, P, I, I, I, I, P],
+    'tfpp_stem_wgrad_f32': [P, P, P, P, P, I, I, I, I, P],
+    'tfpp_bn_bwd_f32': [P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P],
+    'tfpp_se_bwd_reduce_f32': [P, P, P, I, I, I, P],
+    'tfpp_act_bwd_f32': [P, P, I, I, I, F, P, P, I, I, I, I, P, F, I, P],
+    'tfpp_bilinear_bwd_f32': [P, P, L, L, I, I, I, I, I, I, I, P],
+    'tfpp_bilinear_nchw_mask_bwd_f32': [P, P, P, I, I, I, I, I, I, I, P],
+    'tfpp_pool_bwd_add_f32': [P, P, P, I, I, I, I, I, I, I, I, P],
+    'tfpp_add_f32': [P, P, P, L, P],
+    'tfpp_copy_rows_f32': [P, P, P, I, I, I, I, I, P],
+    'tfpp_mha_bwd_f32': [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, P, F, I, P],
 }
 
 

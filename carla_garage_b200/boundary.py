@@ -127,7 +127,7 @@ class TrainBoundary:
           dz = ops.act_bwd(g.contiguous().float(), y if act != ACT_NONE else None, act, b, hw, c, layout=1,
                            act_n_limit=n_limit, dbias=bias, channels_padded=cpad).view(b, y.shape[2], y.shape[3], cpad)
         else:
-          dz = torch.zeros((b, y.shape[2], y.shape[3], cpad), dtype=BF16, device=y.device)
+          dz = torch.zeros((b, y.shape[2], y.shape[3], cpad), dtype=ops.act_dtype(), device=y.device)
         if key in seeds:
           ops.add_bf16(dz, seeds[key], out=dz)
         seeds[key] = dz

@@ -886,10 +886,12 @@ extern "C" int tfpp_se_bwd(const void* dout, const void* a2, const float* gate, 
   int chunks, ppb;
   chunking(batch, hw, &chunks, &ppb);
   dim3 grid(chunks, batch);
-  se_bwd_reduce_kernel<<<grid, 256, sizeof(float) * channels, stream>>>(static_cast<const bf16*>(dout),
-                                                                        static_cast<const bf16*>(a2), dgate_sum, hw,
-                                                                        channels, ppb);
-  TFPP_CHECK_LAUNCH();
+  if (dout != nullptr) {  // dout == NULL: dgate_sum was reduced by the caller (fp32 parity mode, tfpp_se_bwd_reduce_f32)
+    se_bwd_reduce_kernel<<<grid, 256, sizeof(float) * channels, stream>>>(static_cast<const bf16*>(dout),
+                                                                          static_cast<const bf16*>(a2), dgate_sum, hw,
+                                                                          channels, ppb);
+    TFPP_CHECK_LAUNCH();
+  }
   // workspace: ds (B,C) then dpre (B,rd)
   float* ds_ws = ws;
   float* dpre_ws = ws + static_cast<long long>(batch) * channels;

@@ -237,13 +237,16 @@ def conv_wgrad(dy, x, *, cin=None, taps=TAPS_1X1, w_taps=None, group_width=0, x_
                splits=0, out=None, out_strides=None, dy_shape=None, cout_valid=0):
   """dw[co, tap, ci] = sum_pixels dy[pixel, co] * x[pixel + tap, ci]; dy (B,H,W,Cout) bf16, x (Bx,H,W,Cx) bf16.
   Returns fp32 (Cout, w_taps, cin) (dense) or (Cout, w_taps, group_width) (grouped); accumulates into ``out``."""
+  f32 = dy.dtype == F32   # fp32 parity mode
+  if x.dtype != dy.dtype:
+    raise RuntimeError(f'conv_wgrad: dy is {dy.dtype}, x is {x.dtype}')
   if dy_shape is None:
-    _dev(dy, BF16)
+    _dev(dy)
     b, h, w, cout = dy.shape
   else:
     b, h, w, cout = dy_shape
   if x_shape is None:
-    _dev(x, BF16)
+    _dev(x)
     xb, _, _, cx = x.shape
   else:
     xb, _, _, cx = x_shape
@@ -266,7 +269,10 @@ def conv_wgrad(dy, x, *, cin=None, taps=TAPS_1X1, w_taps=None, group_width=0, x_
   if _PROFILE is not None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-  check(_lib.load().tfpp_conv_wgrad(ctypes.byref(a), _stream()), 'tfpp_conv_wgrad')
+  if f32:
+    check(_lib.load().tfpp_conv_wgrad_f32(ctypes.byref(a), _stream()), 'tfpp_conv_wgrad_f32')
+  else:
+    check(_lib.load().tfpp_conv_wgrad(ctypes.byref(a), _stream()), 'tfpp_conv_wgrad')
   if _PROFILE is not None:
     e1.record()
     _PROFILE.append((e0, e1, 2.0 * b * h * w * (cout_valid or cout) * (group_width or cin) * len(taps),
@@ -617,10 +623,14 @@ def gconv3x3(x, w, stride=1, scale=None, shift=None, act=ACT_NONE, stats=None):
 
 def gconv3x3_dgrad_s2(dy, w_t):
   """Input gradient of the stride-2 group conv: dy (B,Ho,Wo,C) bf16, w_t = pack_gconv_halo(w, transpose=True)."""
-  _dev(dy, BF16)
-  _dev(w_t, BF16)
+  _dev(dy)
+  _dev(w_t, dy.dtype)
   b, ho, wo, c = dy.shape
-  dx = torch.empty((b, 2 * ho, 2 * wo, c), dtype=BF16, device=dy.device)
+  dx = torch.empty((b, 2 * ho, 2 * wo, c), dtype=dy.dtype, device=dy.device)
+  if dy.dtype == F32:
+    check(_lib.load().tfpp_gconv3x3_dgrad_s2_f32(dy.data_ptr(), w_t.data_ptr(), dx.data_ptr(), b, ho, wo, c, _stream()),
+          'tfpp_gconv3x3_dgrad_s2_f32')
+    return dx
   check(_lib.load().tfpp_gconv3x3_dgrad_s2(dy.data_ptr(), w_t.data_ptr(), dx.data_ptr(), b, ho, wo, c, _stream()),
         'tfpp_gconv3x3_dgrad_s2')
   return dx
@@ -628,11 +638,15 @@ def gconv3x3_dgrad_s2(dy, w_t):
 
 def gconv3x3_wgrad(dy, x, dw, stride=1):
   """dw (C,24,3,3) f32 (torch layout, contiguous) += weight gradient of gconv3x3(x, w, stride) given dy."""
-  _dev(dy, BF16)
-  _dev(x, BF16)
+  _dev(dy)
+  _dev(x, dy.dtype)
   b, h, wd, c = x.shape
   assert dw.dtype == F32 and dw.is_contiguous() and dw.numel() == c * 24 * 9
   lib = _lib.load()
+  if dy.dtype == F32:
+    check(lib.tfpp_gconv3x3_wgrad_f32(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), b, h, wd, c, stride, _stream()),
+          'tfpp_gconv3x3_wgrad_f32')
+    return dw
   ws = torch.empty(lib.tfpp_gconv3x3_wgrad_workspace(b, h, wd, c, stride), dtype=F32, device=x.device)
   check(lib.tfpp_gconv3x3_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), b, h, wd, c, stride, _stream()),
         'tfpp_gconv3x3_wgrad')
@@ -712,10 +726,12 @@ def bn_bwd(dy, y, raw, mean, invstd, gamma, act, dgamma, dbeta, gate=None, pool_
   draw = torch.empty_like(raw)
   dz = torch.empty_like(raw) if want_dz else None
   fs, fh = fwd_affine if fwd_affine is not None else (None, None)
-  check(_lib.load().tfpp_bn_bwd(dy.data_ptr(), _p(y), raw.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-                                gamma.data_ptr(), _p(gate), _p(pool_grad), _p(fs), _p(fh), act, dbeta.data_ptr(),
-                                dgamma.data_ptr(),
-                                draw.data_ptr(), _p(dz), b, h * w, c, _stream()), 'tfpp_bn_bwd')
+  fn = _lib.load().tfpp_bn_bwd_f32 if raw.dtype == F32 else _lib.load().tfpp_bn_bwd
+  if dy.dtype != raw.dtype:
+    raise RuntimeError(f'bn_bwd: dy is {dy.dtype}, raw is {raw.dtype}')
+  check(fn(dy.data_ptr(), _p(y), raw.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+           gamma.data_ptr(), _p(gate), _p(pool_grad), _p(fs), _p(fh), act, dbeta.data_ptr(), dgamma.data_ptr(),
+           draw.data_ptr(), _p(dz), b, h * w, c, _stream()), 'tfpp_bn_bwd')
   return draw, dz
 
 
@@ -725,7 +741,11 @@ def se_bwd(dout, a2, gate, hidden, pool_sum, hw, w1, w2, dw1, db1, dw2, db2, zer
   dgate = zeros((b, c), gate.device) if zeros else torch.zeros((b, c), dtype=F32, device=gate.device)
   pool_grad = torch.empty((b, c), dtype=F32, device=gate.device)
   ws = torch.empty((b, c + rd), dtype=F32, device=gate.device)
-  check(_lib.load().tfpp_se_bwd(dout.data_ptr(), a2.data_ptr(), gate.data_ptr(), hidden.data_ptr(), pool_sum.data_ptr(),
+  dout_p, a2_p = dout.data_ptr(), a2.data_ptr()
+  if dout.dtype == F32:  # fp32 parity mode: the big reduction in fp32, the (B,C)-sized rest is fp32 anyway
+    check(_lib.load().tfpp_se_bwd_reduce_f32(dout_p, a2_p, dgate.data_ptr(), b, hw, c, _stream()), 'tfpp_se_bwd_reduce_f32')
+    dout_p = a2_p = None
+  check(_lib.load().tfpp_se_bwd(dout_p, a2_p, gate.data_ptr(), hidden.data_ptr(), pool_sum.data_ptr(),
                                 hw, w1.data_ptr(), w2.data_ptr(), dgate.data_ptr(), ws.data_ptr(), dw1.data_ptr(),
                                 db1.data_ptr(),
                                 dw2.data_ptr(), db2.data_ptr(), pool_grad.data_ptr(), b, c, rd, _stream()),
@@ -737,6 +757,13 @@ def act_bwd(dy, y, act, batch, hw, channels, layout=0, act_n_limit=0, dy_scale=1
             want_dz=True, drop=None):
   """drop = (rng, p, site) of a dropout applied to the forward output: its mask (x 1/(1-p)) multiplies dy first."""
   cp = channels if channels_padded is None else channels_padded
+  if ACT_DTYPE[0] == F32:
+    if dy.dtype != F32 or (y is not None and y.dtype != F32):
+      raise RuntimeError('fp32 mode: act_bwd expects float32 gradients / activations')
+    dz = torch.empty((batch * hw, cp), dtype=F32, device=dy.device) if want_dz else None
+    check(_lib.load().tfpp_act_bwd_f32(dy.data_ptr(), _p(y), int(layout == 1), act, act_n_limit, dy_scale, _p(dz), _p(dbias),
+                                       batch, hw, channels, cp, *_drop_args(drop), _stream()), 'tfpp_act_bwd_f32')
+    return dz
   dz = torch.empty((batch * hw, cp), dtype=BF16, device=dy.device) if want_dz else None
   check(_lib.load().tfpp_act_bwd_dropout(dy.data_ptr(), _p(y), layout, act, act_n_limit, dy_scale, _p(dz), _p(dbias),
                                          batch, hw, channels, cp, *_drop_args(drop), _stream()), 'tfpp_act_bwd')
@@ -750,12 +777,23 @@ def bilinear_bwd(dout, dsrc, batch, sh, sw, dh, dw, channels, src_batch_stride=N
   if src_row_stride is None:
     src_row_stride = channels
   ptr = dsrc.data_ptr() + dsrc_offset * dsrc.element_size()
+  if dout.dtype == F32:
+    if dsrc.dtype != F32:
+      raise RuntimeError('fp32 mode: bilinear_bwd expects a float32 destination')
+    check(_lib.load().tfpp_bilinear_bwd_f32(dout.data_ptr(), ptr, src_batch_stride, src_row_stride, int(accumulate), batch, sh,
+                                            sw, dh, dw, channels, _stream()), 'tfpp_bilinear_bwd_f32')
+    return dsrc
   check(_lib.load().tfpp_bilinear_bwd(dout.data_ptr(), ptr, int(dsrc.dtype == F32), src_batch_stride, src_row_stride,
                                       int(accumulate), batch, sh, sw, dh, dw, channels, _stream()), 'tfpp_bilinear_bwd')
   return dsrc
 
 
 def bilinear_nchw_mask_bwd(dout, mask, batch, sh, sw, src_channels, channels, dh, dw):
+  if ACT_DTYPE[0] == F32:
+    dsrc = torch.empty((batch, sh, sw, src_channels), dtype=F32, device=dout.device)
+    check(_lib.load().tfpp_bilinear_nchw_mask_bwd_f32(dout.data_ptr(), _p(mask), dsrc.data_ptr(), batch, sh, sw, src_channels,
+                                                      channels, dh, dw, _stream()), 'tfpp_bilinear_nchw_mask_bwd_f32')
+    return dsrc
   dsrc = torch.empty((batch, sh, sw, src_channels), dtype=BF16, device=dout.device)
   check(_lib.load().tfpp_bilinear_nchw_mask_bwd(dout.data_ptr(), _p(mask), dsrc.data_ptr(), batch, sh, sw, src_channels,
                                                 channels, dh, dw, _stream()), 'tfpp_bilinear_nchw_mask_bwd')
@@ -764,6 +802,13 @@ def bilinear_nchw_mask_bwd(dout, mask, batch, sh, sw, src_channels, channels, dh
 
 def pool_bwd_add(dout, dtok, shape, ph, pw, rows_per_batch, row0):
   b, h, w, c = shape
+  if ACT_DTYPE[0] == F32:
+    if dtok.dtype != F32 or (dout is not None and dout.dtype != F32):
+      raise RuntimeError('fp32 mode: pool_bwd_add expects float32 gradients')
+    out = torch.empty(shape, dtype=F32, device=dtok.device)
+    check(_lib.load().tfpp_pool_bwd_add_f32(_p(dout), dtok.data_ptr(), out.data_ptr(), b, h, w, c, ph, pw, rows_per_batch,
+                                            row0, _stream()), 'tfpp_pool_bwd_add_f32')
+    return out
   out = torch.empty(shape, dtype=BF16, device=dtok.device)
   check(_lib.load().tfpp_pool_bwd_add(_p(dout), dtok.data_ptr(), int(dtok.dtype == F32), out.data_ptr(), b, h, w, c, ph,
                                       pw, rows_per_batch, row0, _stream()), 'tfpp_pool_bwd_add')
@@ -772,11 +817,19 @@ def pool_bwd_add(dout, dtok, shape, ph, pw, rows_per_batch, row0):
 
 def add_bf16(a, b, out=None):
   out = torch.empty_like(a) if out is None else out
+  if a.dtype == F32:
+    check(_lib.load().tfpp_add_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), 'tfpp_add_f32')
+    return out
   check(_lib.load().tfpp_add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), 'tfpp_add_bf16')
   return out
 
 
 def cast_rows(x, groups, group_rows, row0, rows, channels, dbias=None):
+  if ACT_DTYPE[0] == F32:
+    out = torch.empty((groups * rows, channels), dtype=F32, device=x.device)
+    check(_lib.load().tfpp_copy_rows_f32(x.data_ptr(), out.data_ptr(), _p(dbias), groups, group_rows, row0, rows, channels,
+                                         _stream()), 'tfpp_copy_rows_f32')
+    return out
   out = torch.empty((groups * rows, channels), dtype=BF16, device=x.device)
   check(_lib.load().tfpp_cast_rows(x.data_ptr(), out.data_ptr(), _p(dbias), groups, group_rows, row0, rows, channels,
                                    _stream()), 'tfpp_cast_rows')
@@ -789,6 +842,10 @@ def batch_reduce(x, out, batch):
 
 def stem_wgrad(x, draw, in_scale, in_shift, dw):
   b, cin, h, w = x.shape
+  if draw.dtype == F32:
+    check(_lib.load().tfpp_stem_wgrad_f32(x.data_ptr(), draw.data_ptr(), _p(in_scale), _p(in_shift), dw.data_ptr(), b, cin, h,
+                                          w, _stream()), 'tfpp_stem_wgrad_f32')
+    return
   check(_lib.load().tfpp_stem_wgrad(x.data_ptr(), draw.data_ptr(), _p(in_scale), _p(in_shift), dw.data_ptr(), b, cin, h,
                                     w, _stream()), 'tfpp_stem_wgrad')
 
@@ -804,6 +861,16 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
 
 def fusion_attn_bwd(qkv, dout, batch, tokens, channels, heads, drop=None):
   dqkv = torch.empty_like(qkv)
+  if qkv.dtype == F32:
+    c3, hd = 3 * channels, channels // heads
+    ws = torch.empty(2 * batch * heads * tokens * tokens, dtype=F32, device=qkv.device)
+    base, dbase = qkv.data_ptr(), dqkv.data_ptr()
+    sb, sr = tokens * c3, c3
+    check(_lib.load().tfpp_mha_bwd_f32(base, sb, sr, base + 4 * channels, sb, sr, base + 8 * channels, sb, sr, dout.data_ptr(),
+                                       tokens * channels, channels, dbase, sb, sr, dbase + 4 * channels, sb, sr,
+                                       dbase + 8 * channels, sb, sr, ws.data_ptr(), 0, batch, heads, tokens, tokens, hd,
+                                       *_drop_args(drop), _stream()), 'tfpp_mha_bwd_f32')
+    return dqkv
   ws = torch.empty((batch * tokens, 2 * channels), dtype=F32, device=qkv.device)
   check(_lib.load().tfpp_fusion_attn_bwd_dropout(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), batch,
                                                  tokens, channels, heads, *_drop_args(drop), _stream()),
@@ -815,6 +882,15 @@ def small_mha_bwd(q, k, v, dout, dq, dk, dv, batch, heads, tq, tk, head_dim, q_s
                   offs=(0, 0, 0, 0, 0, 0), accumulate_kv=False, drop=None):
   """offs: element offsets of (q, k, v, dq, dk, dv) inside their buffers; *_st = (batch stride, row stride)."""
   d = heads * head_dim
+  if q.dtype == F32:
+    p4 = lambda t, o: t.data_ptr() + 4 * o
+    ws = torch.empty(2 * batch * heads * tq * tk, dtype=F32, device=q.device)
+    check(_lib.load().tfpp_mha_bwd_f32(p4(q, offs[0]), q_st[0], q_st[1], p4(k, offs[1]), k_st[0], k_st[1], p4(v, offs[2]),
+                                       v_st[0], v_st[1], dout.data_ptr(), tq * d, d, p4(dq, offs[3]), dq_st[0], dq_st[1],
+                                       p4(dk, offs[4]), dk_st[0], dk_st[1], p4(dv, offs[5]), dv_st[0], dv_st[1],
+                                       ws.data_ptr(), int(accumulate_kv), batch, heads, tq, tk, head_dim, *_drop_args(drop),
+                                       _stream()), 'tfpp_mha_bwd_f32')
+    return
   p = lambda t, o: t.data_ptr() + 2 * o
   check(_lib.load().tfpp_small_mha_bwd_dropout(p(q, offs[0]), q_st[0], q_st[1], p(k, offs[1]), k_st[0], k_st[1],
                                                p(v, offs[2]), v_st[0], v_st[1], dout.data_ptr(), tq * d, d,

@@ -238,7 +238,7 @@ def compute_losses(eng, outputs, labels, weights=None, bias_grads=None, w_dev=No
   hw = pred_sem.shape[2] * pred_sem.shape[3]
   ncls = pred_sem.shape[1]
   cp = 16  # multiple of 16: the small-channel dgrad / wgrad kernels take 16- or 32-channel gradients
-  dz = torch.empty((b, pred_sem.shape[2], pred_sem.shape[3], cp), dtype=BF16, device=dev) if want_seeds else None
+  dz = torch.empty((b, pred_sem.shape[2], pred_sem.shape[3], cp), dtype=ops.act_dtype(), device=dev) if want_seeds else None
   _lib.check(lib.tfpp_ce_map_loss(pred_sem.data_ptr(), labels['semantic'].data_ptr(), None,
                                   weights['loss_semantic'] / (b * hw), wp('loss_semantic'), sums[2:3].data_ptr(), ops._p(dz), None,  # pylint: disable=protected-access
                                   ops._p(bias_grads.get('semantic')), b, ncls, cp, hw, stream), 'ce semantic')  # pylint: disable=protected-access
@@ -258,7 +258,7 @@ def compute_losses(eng, outputs, labels, weights=None, bias_grads=None, w_dev=No
   seeds['bev'] = dbev
   # depth L1 on the sigmoid output (model.py:379,434)
   n = pred_depth.numel()
-  dzd = torch.empty((b, pred_depth.shape[-2], pred_depth.shape[-1], 16), dtype=BF16, device=dev) if want_seeds else None
+  dzd = torch.empty((b, pred_depth.shape[-2], pred_depth.shape[-1], 16), dtype=ops.act_dtype(), device=dev) if want_seeds else None
   _lib.check(lib.tfpp_l1_sigmoid_loss(pred_depth.data_ptr(), labels['depth'].data_ptr(), weights['loss_depth'] / n,
                                       wp('loss_depth'), sums[4:5].data_ptr(), ops._p(dzd), ops._p(bias_grads.get('depth')), 16, n,  # pylint: disable=protected-access
                                       stream), 'l1 depth')
@@ -273,7 +273,7 @@ def compute_losses(eng, outputs, labels, weights=None, bias_grads=None, w_dev=No
   if w_dev is not None:
     i5 = keys.index('loss_center_heatmap')
     w5 = w5 * w_dev[i5:i5 + 5]
-  dzh = torch.empty((b, maps.shape[2], maps.shape[3], 24), dtype=BF16, device=dev) if want_seeds else None
+  dzh = torch.empty((b, maps.shape[2], maps.shape[3], 24), dtype=ops.act_dtype(), device=dev) if want_seeds else None
   _lib.check(lib.tfpp_center_head_loss(maps.data_ptr(), labels['center_heatmap'].data_ptr(), labels['wh'].data_ptr(),
                                        labels['offset'].data_ptr(), labels['yaw_class'].data_ptr(),
                                        labels['yaw_res'].data_ptr(), labels['pixel_weight'].data_ptr(),
@@ -476,7 +476,7 @@ class Backward:
     hi, wi = dimg.shape[1], dimg.shape[2]
     ops.bilinear_bwd(dimg, dxf, b, cfg.img_vert_anchors, cfg.img_horz_anchors, hi, wi, c, src_batch_stride=t * c,
                      src_row_stride=c)
-    dlid_tok = torch.empty((b, cfg.lidar_vert_anchors, cfg.lidar_horz_anchors, cl), dtype=BF16, device=dimg.device)
+    dlid_tok = torch.empty((b, cfg.lidar_vert_anchors, cfg.lidar_horz_anchors, cl), dtype=ops.act_dtype(), device=dimg.device)
     ops.bilinear_bwd(dlid, dlid_tok, b, cfg.lidar_vert_anchors, cfg.lidar_horz_anchors, dlid.shape[1], dlid.shape[2], cl)
     i2l = bb.img_channel_to_lidar[i]
     dlt = dlid_tok.view(b * n_lid, cl)
@@ -639,7 +639,7 @@ class Backward:
     dca = self.linear_bwd(dz, r['ca'], g(mh.out_proj.weight), packed(mh.out_proj.weight, 'linear_t'), d, d,
                           out_f32=False)
     kv = r['kv']
-    dq2 = torch.empty((rows, d), dtype=BF16, device=kv.device)
+    dq2 = torch.empty((rows, d), dtype=ops.act_dtype(), device=kv.device)
     dkv = torch.empty_like(kv)
     ops.small_mha_bwd(r['q2'], kv, kv, dca, dq2, dkv, dkv, b, heads, nq, n_mem, hd, (nq * d, d), (n_mem * 2 * d, 2 * d),
                       (n_mem * 2 * d, 2 * d), (nq * d, d), (n_mem * 2 * d, 2 * d), (n_mem * 2 * d, 2 * d),

@@ -450,6 +450,43 @@ int tfpp_centernet_targets(const float* boxes, const int* counts, int batch, int
                            float* offset, long long* yaw_class, float* yaw_res, float* velocity, long long* brake,
                            float* pixel_weight, float* avg_factor, tfpp_stream_t stream);
 
+/* fp32 parity mode, backward half (csrc/fp32_path_bwd.cu): adjoints with fp32 gradient storage, same contracts as
+ * tfpp_conv_wgrad (dense), tfpp_gconv3x3_wgrad / _dgrad_s2, tfpp_stem_wgrad, tfpp_bn_bwd, the reduce pass of
+ * tfpp_se_bwd (then call tfpp_se_bwd with dout = NULL), tfpp_act_bwd_dropout (nchw: dy / y NCHW f32, else NHWC f32),
+ * tfpp_bilinear_bwd, tfpp_bilinear_nchw_mask_bwd, tfpp_pool_bwd_add, tfpp_add_bf16, tfpp_cast_rows, and the attention
+ * adjoint of both transformers (workspace: 2 * batch * heads * tq * tk floats). */
+int tfpp_conv_wgrad_f32(const tfpp_wgrad_args* args, tfpp_stream_t stream);
+int tfpp_gconv3x3_wgrad_f32(const float* dy, const float* x, float* dw, int batch, int height, int width, int channels,
+                            int stride, tfpp_stream_t stream);
+int tfpp_gconv3x3_dgrad_s2_f32(const float* dy, const float* w_t, float* dx, int batch, int out_height, int out_width,
+                               int channels, tfpp_stream_t stream);
+int tfpp_stem_wgrad_f32(const float* x, const float* draw, const float* in_scale, const float* in_shift, float* dw,
+                        int batch, int cin, int height, int width, tfpp_stream_t stream);
+int tfpp_bn_bwd_f32(const float* dy, const float* y, const float* raw, const float* mean, const float* invstd,
+                    const float* gamma, const float* gate, const float* pool_grad, const float* fwd_scale,
+                    const float* fwd_shift, int act, float* s1, float* s2, float* draw, float* dz_out, int batch, int hw,
+                    int channels, tfpp_stream_t stream);
+int tfpp_se_bwd_reduce_f32(const float* dout, const float* a2, float* dgate_sum, int batch, int hw, int channels,
+                           tfpp_stream_t stream);
+int tfpp_act_bwd_f32(const float* dy, const float* y, int nchw, int act, int act_n_limit, float dy_scale, float* dz,
+                     float* dbias, int batch, int hw, int channels, int channels_padded,
+                     const unsigned long long* drop_rng, float drop_p, unsigned drop_site, tfpp_stream_t stream);
+int tfpp_bilinear_bwd_f32(const float* dout, float* dsrc, long long src_batch_stride, long long src_row_stride,
+                          int accumulate, int batch, int sh, int sw, int dh, int dw, int channels, tfpp_stream_t stream);
+int tfpp_bilinear_nchw_mask_bwd_f32(const float* dout, const float* mask, float* dsrc, int batch, int sh, int sw,
+                                    int src_channels, int channels, int dh, int dw, tfpp_stream_t stream);
+int tfpp_pool_bwd_add_f32(const float* dout, const float* dtok, float* out, int batch, int height, int width,
+                          int channels, int ph, int pw, int rows_per_batch, int row0, tfpp_stream_t stream);
+int tfpp_add_f32(const float* a, const float* b, float* y, long long n, tfpp_stream_t stream);
+int tfpp_copy_rows_f32(const float* x, float* out, float* dbias, int groups, int group_rows, int row0, int rows,
+                       int channels, tfpp_stream_t stream);
+int tfpp_mha_bwd_f32(const float* q, long long q_sb, long long q_sr, const float* k, long long k_sb, long long k_sr,
+                     const float* v, long long v_sb, long long v_sr, const float* dout, long long o_sb, long long o_sr,
+                     float* dq, long long dq_sb, long long dq_sr, float* dk, long long dk_sb, long long dk_sr, float* dv,
+                     long long dv_sb, long long dv_sr, float* workspace, int accumulate_kv, int batch, int heads, int tq,
+                     int tk, int head_dim, const unsigned long long* drop_rng, float drop_p, unsigned drop_site,
+                     tfpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -247,3 +247,64 @@ def test_forward_train_mode_and_losses_fp32_vs_reference_golden(net, oracle_stat
   finally:
     net.load_state_dict(oracle_state, strict=True)
     net.eval()
+
+
+def test_train_step_gradients_fp32_vs_reference(oracle_state, fp32):
+  """The reference's train step (model(...) -> losses -> loss.backward(), train.py:776-820,883-898) through the autograd
+  boundary with the engine's hand-scheduled backward on fp32 storage: EVERY parameter gradient within 1e-3 of the
+  reference's autograd (sampled goldens from the unmodified reference, tests/golden/train_b2.npz, + all 1332-entry
+  state through the live oracle, which tests/test_oracle.py pins to the reference)."""
+  from carla_garage_b200 import synth
+  from carla_garage_b200.config import GlobalConfig
+  from carla_garage_b200.nn import LidarCenterNet
+  from oracle import tfpp_oracle as orc
+  from tests.test_boundary_gpu import _torch_losses, err, grad_scale, zero_grad_param
+  m = LidarCenterNet(GlobalConfig())
+  m.load_state_dict(oracle_state, strict=True)
+  m = m.cuda().train()
+  inp_cpu, lab_cpu = synth.make_inputs(2, seed=11), synth.make_labels(2, seed=13)
+  inp = {k: v.cuda() for k, v in inp_cpu.items()}
+  lab = {k: v.cuda().contiguous() for k, v in lab_cpu.items()}
+  out = m(**inp)                                   # training mode + grad enabled: the autograd boundary
+  assert out[3].grad_fn is not None and out[3].dtype == torch.float32
+  losses = _torch_losses(m, out, lab)              # plain torch losses: ordinary gradients arrive at the boundary
+  g = np.load(os.path.join(GOLDEN, 'train_b2.npz'))
+  for k, v in losses.items():
+    assert abs(float(v) - float(g[k])) <= TOL * max(abs(float(g[k])), 1e-6), (k, float(v), float(g[k]))
+  (sum(losses.values()) / len(losses)).backward()
+  torch.cuda.synchronize()
+  params = dict(m.named_parameters())
+  # (a) the reference's own gradients (first 256 elements + norm of 26 parameters across the whole network)
+  worst = ('', 0.0)
+  for key in g.files:
+    if not key.startswith('grad_'):
+      continue
+    n = key[5:]
+    got = params[n].grad.flatten()[:256].cpu()
+    e = rel(got, g[key])
+    nr = float(params[n].grad.norm()) / float(g['gradnorm_' + n])
+    worst = max(worst, (n, e), key=lambda t: t[1])
+    assert e < TOL and abs(nr - 1) < TOL, (n, e, nr)
+  print(f'\n  fp32 gradients vs reference goldens: worst sampled rel err {worst[1]:.2e} ({worst[0]})')
+  # (b) every parameter against the oracle's autograd
+  sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k and not k.startswith('valid_bev')
+            and not k.startswith('loss_') else v.clone()) for k, v in oracle_state.items()}
+  torch.set_num_threads(min(os.cpu_count() or 1, 16))
+  oo = orc.forward(sd, **inp_cpu, training=True)
+  orc.total_loss(orc.compute_loss(sd, oo, lab_cpu)).backward()
+  want = {n: sd[n].grad for n in params if sd[n].grad is not None}
+  scale = grad_scale(want)
+  worst, bad = ('', 0.0), []
+  for n, p in params.items():
+    if n not in want:
+      continue
+    assert p.grad is not None, n
+    # relative to |g| + 1e-3 * the network-wide gradient rms: the analytically-zero gradients (zero_grad_param) are
+    # then held to 1e-3 of the typical gradient instead of to a relative error of noise
+    e = err(p.grad, want[n], 1e-3 * scale if not zero_grad_param(n) else scale)
+    if e > worst[1]:
+      worst = (n, e)
+    if e >= TOL:
+      bad.append((n, e))
+  print(f'  fp32 gradients vs oracle autograd ({len(want)} parameters): worst {worst[1]:.2e} ({worst[0]})')
+  assert not bad, bad[:10]
