@@ -373,7 +373,7 @@ def main():
       'metric': 'train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
       'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-      'config': {'workload': WORKLOAD,
+      'config': {'workload': WORKLOAD if b == PER_GPU_BATCH else WORKLOAD.replace('batch=32', f'batch={b}') + (' (BASELINE.json config 3: DDP imitation training, batch=12/GPU)' if b == 12 else ''),
                  'global_batch': world * b, 'per_gpu_batch': b, 'parallelism': f'dp{world}',
                  'l2': 'per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed',
                  'inputs': 'rgb (B,3,256,1024) f32 + 60k-point LiDAR cloud -> (B,1,256,256) BEV (reference default use_ground_plane=0)',

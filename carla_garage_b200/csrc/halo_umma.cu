@@ -23,17 +23,20 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreadsH = 192;            // warp 0: TMA, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kThreadsH = 192;            // group conv kernel: warp 0: TMA, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kLoadWarps = 4;             // dense kernel: cp.async producer warps behind the epilogue warps
 constexpr int PW = 64;                    // plane row pitch in pixels
 constexpr int TWO = PW - 2;               // output columns per tile (62)
 constexpr int THO = 8;                    // output rows per tile
 constexpr int PH = THO + 2;
 constexpr int MBLK = THO * PW / 128;      // 4 UMMA M blocks of 128 linear pixels
-constexpr int PLANE_BYTES = (PH * PW + 8) * 16;   // + 8 pixels slack: the last taps of the last block read 2 pixels past
+constexpr int PLANE_BYTES = (PH * PW + 10) * 16;  // + slack: the last taps of the last block read 2 pixels past; 10400 B
+                                                  // = 32 (mod 128): the four planes of a pixel fall into different banks
 constexpr int kStagesH = 2;
 constexpr int kTmemColsH = 512;
 
 struct HParams {
+  const bf16* x;        // (B,H,W,K) NHWC bf16 input
   const bf16* w;        // (9, K/8, N, 8) bf16: [tap][k chunk][n][8 k] — already in the shared-memory operand layout
   const float* bias;    // optional (n_valid)
   void* out;
@@ -45,8 +48,7 @@ struct HParams {
 
 // EPI = 4 (validated) or 8 epilogue warps (two per TMEM lane quarter, alternating M blocks; not yet run)
 template <int EPI>
-__global__ void __launch_bounds__(64 + 32 * EPI, 1) halo_umma_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x,
-                                                                            const HParams p) {
+__global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_conv3x3_kernel(const HParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kchunks = p.K / 8;
@@ -59,10 +61,12 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) halo_umma_conv3x3_kernel(con
   uint64_t* tfull_bar = bars + 4;             // [2] accumulators ready
   uint64_t* tempty_bar = bars + 6;            // [2] accumulators drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sbias = reinterpret_cast<float*>(bars + 16);   // [64] per-column bias (0 beyond n_valid / without bias)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int num_tiles = tiles_per_img * p.B;
+  if (threadIdx.x < 64) sbias[threadIdx.x] = (p.bias != nullptr && static_cast<int>(threadIdx.x) < p.n_valid) ? __ldg(p.bias + threadIdx.x) : 0.f;
 
   // weights -> shared memory (generic proxy), made visible to the async proxy (UMMA) before the first MMA
   for (int i = threadIdx.x; i < w_bytes / 16; i += blockDim.x)
@@ -70,9 +74,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) halo_umma_conv3x3_kernel(con
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
     for (int s = 0; s < kStagesH; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), kLoadWarps);
       mbar_init(smem_u32(&empty_bar[s]), 1);
       mbar_init(smem_u32(&tfull_bar[s]), 1);
       mbar_init(smem_u32(&tempty_bar[s]), EPI);
@@ -90,26 +93,51 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) halo_umma_conv3x3_kernel(con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================================================================ TMA producer: one box per 8-channel plane
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_img;
-        const int r = tile - b * tiles_per_img;
-        const int y0 = (r / p.tiles_x) * THO, x0 = (r % p.tiles_x) * TWO;
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_expect_tx(fb, static_cast<uint32_t>(kchunks * PH * PW * 16));
-        uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
-        for (int c = 0; c < kchunks; ++c)
-          tma_load_4d(smem_u32(st + c * PLANE_BYTES), &tmap_x, fb, c * 8, x0 - 1, y0 - 1, b);
-        if (++stage == kStagesH) {
-          stage = 0;
-          phase ^= 1;
-        }
+  if (warp >= 2 + EPI) {
+    // ================================================================ producers: cp.async straight into the planes
+    // Round 2: the first version wrote each 8-channel plane with its own TMA box {8 ch, 64, 10, 1}, i.e. 2560 16-byte
+    // elements per tile, and the TMA engine's per-element cost (not math, not DRAM) bounded the kernel at 1.13 ms
+    // (profiles/r02_ncu_halo_conv.txt: tensor pipe 6.8 %, DRAM 11 %).  A tile row is one contiguous 64 x K x 2 B run of
+    // the NHWC input, so four warps copy it with coalesced 16-byte cp.async (zero fill outside the image = padding);
+    // consecutive lanes take consecutive 16-byte chunks of a pixel and land in consecutive planes.
+    const int pt = (warp - (2 + EPI)) * 32 + lane;
+    const int n_chunks = kchunks * PH * PW;
+    int stage = 0, prev = -1;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int r = tile - b * tiles_per_img;
+      const int y0 = (r / p.tiles_x) * THO, x0 = (r % p.tiles_x) * TWO;
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+      const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+      for (int i = pt; i < n_chunks; i += 32 * kLoadWarps) {
+        const int c = i % kchunks, pix = i / kchunks;
+        const int ty = pix / PW, tx = pix - ty * PW;
+        const int gy = y0 - 1 + ty, gx = x0 - 1 + tx;
+        const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+        const bf16* src = ok ? p.x + ((static_cast<long long>(b) * p.H + gy) * p.W + gx) * p.K + c * 8 : p.x;
+        const uint32_t dst = st + static_cast<uint32_t>(c) * PLANE_BYTES + static_cast<uint32_t>(pix) * 16;
+        const int bytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (prev >= 0) {  // the previous tile's copies have landed: publish them to the async proxy (UMMA reads)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[prev]));
+      }
+      prev = stage;
+      if (++stage == kStagesH) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (prev >= 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&full_bar[prev]));
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
@@ -118,23 +146,30 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) halo_umma_conv3x3_kernel(con
       uint32_t phase = 0, acc_phase = 0;
       const uint32_t idesc = make_idesc_bf16(128, p.N);
       const uint32_t w_u = smem_u32(wsm);
-      const uint32_t w_tap_bytes = static_cast<uint32_t>(p.K * p.N * 2);
       const uint32_t w_lbo = static_cast<uint32_t>(p.N * 16);
+      const uint64_t b0 = make_nosw_kmajor_desc(w_u, w_lbo, 128);
+      const uint64_t w_tap_16 = static_cast<uint64_t>(p.K * p.N * 2) >> 4;   // weight block of one tap, in 16-byte units
+      const uint64_t w_k_16 = static_cast<uint64_t>(2 * w_lbo) >> 4;         // 16 input channels further
+      const int ksteps = p.K / 16;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+        // one thread issues all 72 MMAs of a tile: keep its dependent instruction chain short — the two descriptors are
+        // built once per tile and only their 16-byte-granular start-address fields are advanced (no carry: all of shared
+        // memory fits the 14-bit field)
+        const uint64_t a0 = make_nosw_kmajor_desc(st, PLANE_BYTES, 128);
         for (int blk = 0; blk < MBLK; ++blk) {
           const uint32_t d_tmem = tmem_base + acc * 256 + blk * p.N;
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int ky = tap / 3, kx = tap - ky * 3;
-            const uint32_t a_start = st + static_cast<uint32_t>(blk * 128 + ky * PW + kx) * 16;
-            for (int kk = 0; kk < p.K / 16; ++kk) {
-              const uint64_t adesc = make_nosw_kmajor_desc(a_start + kk * 2 * PLANE_BYTES, PLANE_BYTES, 128);
-              const uint64_t bdesc = make_nosw_kmajor_desc(w_u + tap * w_tap_bytes + kk * 2 * w_lbo, w_lbo, 128);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | kk) ? 1u : 0u);
-            }
+            const uint64_t a_tap = a0 + static_cast<uint64_t>(blk * 128 + ky * PW + kx);
+            const uint64_t b_tap = b0 + static_cast<uint64_t>(tap) * w_tap_16;
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_bf16(d_tmem, a_tap + static_cast<uint64_t>(kk) * (2 * (PLANE_BYTES >> 4)), b_tap + static_cast<uint64_t>(kk) * w_k_16,
+                        idesc, (tap | kk) ? 1u : 0u);
           }
         }
         umma_commit(smem_u32(&empty_bar[stage]));    // the tile's planes may be overwritten
@@ -149,7 +184,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) halo_umma_conv3x3_kernel(con
         }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ================================================================ epilogue: lane == linear tile pixel
     const int lane_group = warp & 3;
     const int blk0 = EPI == 8 ? ((warp - 2) >> 2) : 0;   // with 8 warps: even / odd M blocks
@@ -167,26 +202,33 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) halo_umma_conv3x3_kernel(con
         const int oy = y0 + ty, ox = x0 + tx;
         const bool valid = tx < TWO && oy < p.H && ox < p.W;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + acc * 256 + blk * p.N;
+        // Round 2: this loop was the kernel's limiter (profiles/r02_ncu_halo_conv.txt: ~3100 instructions per warp and
+        // tile with one warp per scheduler, i.e. every latency exposed; tensor pipe 6.8 %, DRAM 11 %).  Bias from a
+        // shared-memory table, the activation decided once per 16-column chunk, no per-element branches.
+        const int act_cols = p.act == ACT_NONE ? 0 : (p.act_n_limit == 0 ? p.N : p.act_n_limit);
         for (int c = 0; c < p.N; c += 16) {
           float v[16];
           __syncwarp();
           tmem_ld16(taddr + c, v);
           if (!valid) continue;
+          const float4* bp = reinterpret_cast<const float4*>(sbias + c);
+          const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          v[8] += b2.x; v[9] += b2.y; v[10] += b2.z; v[11] += b2.w; v[12] += b3.x; v[13] += b3.y; v[14] += b3.z; v[15] += b3.w;
+          if (c + 16 <= act_cols && p.act == ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = c + j;
-            float x = v[j];
-            if (p.bias != nullptr && n < p.n_valid) x += __ldg(p.bias + n);
-            if (p.act != ACT_NONE && (p.act_n_limit == 0 || n < p.act_n_limit)) x = apply_act(x, p.act);
-            v[j] = x;
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (c < act_cols) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c + j < act_cols) v[j] = apply_act(v[j], p.act);
           }
           if (p.out_nchw_f32) {
             float* o = static_cast<float*>(p.out);
             const long long hw = static_cast<long long>(p.H) * p.W;
             const long long base = static_cast<long long>(b) * p.n_valid * hw + static_cast<long long>(oy) * p.W + ox;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c + j < p.n_valid) o[base + (c + j) * hw] = v[j];
+            const int jn = min(16, p.n_valid - c);
+            for (int j = 0; j < jn; ++j) o[base + (c + j) * hw] = v[j];
           } else {
             bf16* o = static_cast<bf16*>(p.out) + ((static_cast<long long>(b) * p.H + oy) * p.W + ox) * p.N + c;
             uint4* o4 = reinterpret_cast<uint4*>(o);
@@ -491,21 +533,13 @@ extern "C" int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias
   TFPP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(out) & 15) == 0, "operands must be 16-byte aligned");
   HParams p;
+  p.x = static_cast<const bf16*>(x);
   p.w = static_cast<const bf16*>(w); p.bias = bias; p.out = out; p.out_nchw_f32 = out_nchw_f32;
   p.n_valid = n_valid; p.act = act; p.act_n_limit = act_n_limit;
   p.B = batch; p.H = height; p.W = width; p.K = cin; p.N = cout_padded;
   p.tiles_x = ceil_div(width, TWO);
   p.tiles_y = ceil_div(height, THO);
-  CUtensorMap tmap;
-  {
-    const cuuint64_t c = cin, w_ = width, h = height, b = batch;
-    const cuuint64_t dims[4] = {c, w_, h, b};
-    const cuuint64_t strides[3] = {c * 2, w_ * c * 2, h * w_ * c * 2};
-    const cuuint32_t box[4] = {8, PW, PH, 1};
-    int rc = encode_map(&tmap, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc) return rc;
-  }
-  const size_t smem = 1024 + static_cast<size_t>(kStagesH) * (cin / 8) * PLANE_BYTES + ((9 * cin * cout_padded * 2 + 127) & ~127) + 256;
+  const size_t smem = 1024 + static_cast<size_t>(kStagesH) * (cin / 8) * PLANE_BYTES + ((9 * cin * cout_padded * 2 + 127) & ~127) + 512;
   TFPP_CHECK_ARG(smem <= 227 * 1024, "shared memory budget exceeded");
   static bool attr = false;
   if (!attr) {
@@ -522,8 +556,8 @@ extern "C" int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias
   if (tiles == 0) return TFPP_OK;
   const int grid = static_cast<int>(tiles < TFPP_NUM_SMS ? tiles : TFPP_NUM_SMS);
   static const bool epi8 = [] { const char* e = getenv("TFPP_HALO_UMMA_EPI8"); return e != nullptr && e[0] == '1'; }();
-  if (epi8) halo_umma_conv3x3_kernel<8><<<grid, 64 + 32 * 8, smem, stream>>>(tmap, p);
-  else halo_umma_conv3x3_kernel<4><<<grid, kThreadsH, smem, stream>>>(tmap, p);
+  if (epi8) halo_umma_conv3x3_kernel<8><<<grid, 64 + 32 * 8 + 32 * kLoadWarps, smem, stream>>>(p);
+  else halo_umma_conv3x3_kernel<4><<<grid, 64 + 32 * 4 + 32 * kLoadWarps, smem, stream>>>(p);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

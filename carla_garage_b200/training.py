@@ -342,8 +342,8 @@ class Backward:
       dz = seeds.pop(id(y))
     else:
       dy = self.G.pop(id(y))
-      if y.dtype == F32:  # NCHW f32 output consumed by something other than a loss
-        raise RuntimeError('unexpected f32 intermediate')
+      if r['kw'].get('out_layout') == 'nchw':  # NCHW f32 head output consumed by something other than a loss
+        raise RuntimeError('unexpected NCHW f32 intermediate')
       if r.get('smallc'):
         cp = 16 if cout <= 16 else 32
       if act == ACT_NONE and cp == cout:
