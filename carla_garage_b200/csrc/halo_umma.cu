@@ -44,6 +44,7 @@ struct HParams {
   int n_valid, act, act_n_limit;
   int B, H, W, K, N;    // K = input channels (16/32/64), N = padded output channels (16/32/48/64)
   int tiles_x, tiles_y;
+  int stages;           // input tiles in flight (2..4): DRAM latency x bandwidth needs ~100 KB per SM in flight
 };
 
 // EPI = 4 (validated) or 8 epilogue warps (two per TMEM lane quarter, alternating M blocks; not yet run)
@@ -53,14 +54,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kchunks = p.K / 8;
   const int stage_bytes = kchunks * PLANE_BYTES;
-  uint8_t* wsm = smem + kStagesH * stage_bytes;                          // [9][K/8][N][8] bf16
+  uint8_t* wsm = smem + p.stages * stage_bytes;                          // [9][K/8][N][8] bf16
   const int w_bytes = 9 * p.K * p.N * 2;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + ((w_bytes + 127) & ~127));
-  uint64_t* full_bar = bars;                  // [2] tile landed
-  uint64_t* empty_bar = bars + 2;             // [2] tile consumed by the MMAs
-  uint64_t* tfull_bar = bars + 4;             // [2] accumulators ready
-  uint64_t* tempty_bar = bars + 6;            // [2] accumulators drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* full_bar = bars;                  // [4] tile landed
+  uint64_t* empty_bar = bars + 4;             // [4] tile consumed by the MMAs
+  uint64_t* tfull_bar = bars + 8;             // [2] accumulators ready
+  uint64_t* tempty_bar = bars + 10;           // [2] accumulators drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   float* sbias = reinterpret_cast<float*>(bars + 16);   // [64] per-column bias (0 beyond n_valid / without bias)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,9 +75,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kStagesH; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(smem_u32(&full_bar[s]), kLoadWarps);
       mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
       mbar_init(smem_u32(&tempty_bar[s]), EPI);
     }
@@ -102,13 +105,26 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
     // consecutive lanes take consecutive 16-byte chunks of a pixel and land in consecutive planes.
     const int pt = (warp - (2 + EPI)) * 32 + lane;
     const int n_chunks = kchunks * PH * PW;
-    int stage = 0, prev = -1;
-    uint32_t phase = 0;
+    const int S = p.stages;
+    int issued = 0, signalled = 0;
+    auto publish = [&](int pending) {  // the oldest unpublished tile has landed once <= `pending` newer groups are in flight
+      switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> UMMA (async proxy) reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&full_bar[signalled % S]));
+      ++signalled;
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img;
       const int r = tile - b * tiles_per_img;
       const int y0 = (r / p.tiles_x) * THO, x0 = (r % p.tiles_x) * TWO;
-      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+      const int stage = issued % S;
+      mbar_wait(smem_u32(&empty_bar[stage]), ((issued / S) & 1) ^ 1);
       const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
       for (int i = pt; i < n_chunks; i += 32 * kLoadWarps) {
         const int c = i % kchunks, pix = i / kchunks;
@@ -121,24 +137,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      if (prev >= 0) {  // the previous tile's copies have landed: publish them to the async proxy (UMMA reads)
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&full_bar[prev]));
-      }
-      prev = stage;
-      if (++stage == kStagesH) {
-        stage = 0;
-        phase ^= 1;
-      }
+      ++issued;
+      if (issued - signalled == S) publish(S - 1);
     }
-    if (prev >= 0) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&full_bar[prev]));
-    }
+    while (signalled < issued) publish(issued - signalled - 1);
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     if (lane == 0) {
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
         }
         umma_commit(smem_u32(&empty_bar[stage]));    // the tile's planes may be overwritten
         umma_commit(smem_u32(&tfull_bar[acc]));      // the accumulators are complete
-        if (++stage == kStagesH) {
+        if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
         }
@@ -539,7 +541,10 @@ extern "C" int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias
   p.B = batch; p.H = height; p.W = width; p.K = cin; p.N = cout_padded;
   p.tiles_x = ceil_div(width, TWO);
   p.tiles_y = ceil_div(height, THO);
-  const size_t smem = 1024 + static_cast<size_t>(kStagesH) * (cin / 8) * PLANE_BYTES + ((9 * cin * cout_padded * 2 + 127) & ~127) + 512;
+  const size_t w_smem = ((9 * cin * cout_padded * 2 + 127) & ~127) + 512;
+  p.stages = 4;
+  while (p.stages > 2 && 1024 + static_cast<size_t>(p.stages) * (cin / 8) * PLANE_BYTES + w_smem > 227 * 1024) --p.stages;
+  const size_t smem = 1024 + static_cast<size_t>(p.stages) * (cin / 8) * PLANE_BYTES + w_smem;
   TFPP_CHECK_ARG(smem <= 227 * 1024, "shared memory budget exceeded");
   static bool attr = false;
   if (!attr) {
