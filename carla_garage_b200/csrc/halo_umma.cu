@@ -49,7 +49,7 @@ struct HParams {
 
 // EPI = 4 (validated) or 8 epilogue warps (two per TMEM lane quarter, alternating M blocks; not yet run)
 template <int EPI>
-__global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_conv3x3_kernel(const HParams p) {
+__global__ void __launch_bounds__(32 * MBLK + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_conv3x3_kernel(const HParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kchunks = p.K / 8;
@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 4; ++s) {
       mbar_init(smem_u32(&full_bar[s]), kLoadWarps);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), MBLK);     // one commit per MMA-issuing warp
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tfull_bar[s]), MBLK);
       mbar_init(smem_u32(&tempty_bar[s]), EPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -96,14 +96,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 2 + EPI) {
+  if (warp >= MBLK + EPI) {
     // ================================================================ producers: cp.async straight into the planes
     // Round 2: the first version wrote each 8-channel plane with its own TMA box {8 ch, 64, 10, 1}, i.e. 2560 16-byte
     // elements per tile, and the TMA engine's per-element cost (not math, not DRAM) bounded the kernel at 1.13 ms
     // (profiles/r02_ncu_halo_conv.txt: tensor pipe 6.8 %, DRAM 11 %).  A tile row is one contiguous 64 x K x 2 B run of
     // the NHWC input, so four warps copy it with coalesced 16-byte cp.async (zero fill outside the image = padding);
     // consecutive lanes take consecutive 16-byte chunks of a pixel and land in consecutive planes.
-    const int pt = (warp - (2 + EPI)) * 32 + lane;
+    const int pt = (warp - (MBLK + EPI)) * 32 + lane;
     const int n_chunks = kchunks * PH * PW;
     const int S = p.stages;
     int issued = 0, signalled = 0;
@@ -141,9 +141,13 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
       if (issued - signalled == S) publish(S - 1);
     }
     while (signalled < issued) publish(issued - signalled - 1);
-  } else if (warp == 1) {
-    // ================================================================ MMA issuer
+  } else if (warp < MBLK) {
+    // ================================================================ MMA issuers: warp w owns the 128-pixel M block w.
+    // With N = 32..64 a tcgen05.mma is 16-32 cycles of tensor work but ~150 cycles of dependent descriptor /
+    // uniform-register instructions to issue (profiles/r02_ncu_halo_conv_v2.txt: one issuing thread was busy 74 % of the
+    // kernel): four issuers, each with its own commits, bring the issue rate to the tensor pipe's.
     if (lane == 0) {
+      const int blk = warp;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const uint32_t idesc = make_idesc_bf16(128, p.N);
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
         // built once per tile and only their 16-byte-granular start-address fields are advanced (no carry: all of shared
         // memory fits the 14-bit field)
         const uint64_t a0 = make_nosw_kmajor_desc(st, PLANE_BYTES, 128);
-        for (int blk = 0; blk < MBLK; ++blk) {
+        {
           const uint32_t d_tmem = tmem_base + acc * 256 + blk * p.N;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -186,10 +190,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI + 32 * kLoadWarps, 1) halo_umma_
         }
       }
     }
-  } else if (warp >= 2) {
+  } else {
     // ================================================================ epilogue: lane == linear tile pixel
     const int lane_group = warp & 3;
-    const int blk0 = EPI == 8 ? ((warp - 2) >> 2) : 0;   // with 8 warps: even / odd M blocks
+    const int blk0 = EPI == 8 ? ((warp - MBLK) >> 2) : 0;   // with 8 warps: even / odd M blocks
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -561,8 +565,8 @@ extern "C" int tfpp_halo_conv3x3(const void* x, const void* w, const float* bias
   if (tiles == 0) return TFPP_OK;
   const int grid = static_cast<int>(tiles < TFPP_NUM_SMS ? tiles : TFPP_NUM_SMS);
   static const bool epi8 = [] { const char* e = getenv("TFPP_HALO_UMMA_EPI8"); return e != nullptr && e[0] == '1'; }();
-  if (epi8) halo_umma_conv3x3_kernel<8><<<grid, 64 + 32 * 8 + 32 * kLoadWarps, smem, stream>>>(p);
-  else halo_umma_conv3x3_kernel<4><<<grid, 64 + 32 * 4 + 32 * kLoadWarps, smem, stream>>>(p);
+  if (epi8) halo_umma_conv3x3_kernel<8><<<grid, 32 * MBLK + 32 * 8 + 32 * kLoadWarps, smem, stream>>>(p);
+  else halo_umma_conv3x3_kernel<4><<<grid, 32 * MBLK + 32 * 4 + 32 * kLoadWarps, smem, stream>>>(p);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }
