@@ -286,6 +286,7 @@ def main():
     os.environ['TFPP_NO_OVERLAP'] = '1'
     try:
       prof = ops.profile_gemm_launches(lambda: tr.step(dev_in, dev_lab))
+      calls = _lib.profile_calls(lambda: tr.step(dev_in, dev_lab))   # every C-ABI entry point of one eager step
     finally:
       if prev_no_overlap is None:
         os.environ.pop('TFPP_NO_OVERLAP', None)
@@ -304,6 +305,19 @@ def main():
             # serial GEMM time over the (stream-overlapped) step time: an upper bound of the family's share
             'share_of_step': prof['ms'] / (ms / args.steps),
             'algorithmic_gflop_per_step': prof['gflop']}
+    # device time of one eager single-stream step by C-ABI entry point (CUDA events around every call), largest first;
+    # HBM-bound entries with a simple byte model also get their achieved bandwidth against the measured copy peak
+    hbm_peak = peaks.get('hbm_gbs', 6500.0)
+    n_param = tr.st.flat.numel()
+    byte_model = {'tfpp_adamw_amsgrad': 36.0 * n_param,                                   # 5 reads + 4 writes of fp32
+                  'tfpp_pillar_scatter': float(host_pts.numel() * 4 + b * 2 * 256 * 256 * 4 * 2 + b * 256 * 256 * 4)}
+    tot_ms = sum(v[0] for v in calls.values())
+    roof['step_kernels'] = [dict(entry=k, ms=round(v[0], 3), calls=v[1], share=round(v[0] / tot_ms, 4),
+                                 **({'gb_s': round(byte_model[k] / (v[0] * 1e-3) / 1e9, 1),
+                                     'frac_of_hbm_peak': round(byte_model[k] / (v[0] * 1e-3) / 1e9 / hbm_peak, 3)}
+                                    if k in byte_model else {}))
+                            for k, v in sorted(calls.items(), key=lambda kv: -kv[1][0])[:16]]
+    roof['step_kernels_total_ms'] = round(tot_ms, 2)
 
   if rank != 0:
     return

@@ -170,8 +170,53 @@ def load():
     fn = getattr(lib, name)
     fn.restype = c_ll if name.endswith('_workspace') else c_int
     fn.argtypes = args
-  _lib = lib
-  return lib
+  _lib = _Timed(lib)
+  return _lib
+
+
+class _Timed:
+  """The loaded library; with ``CALL_PROFILE`` set (profile_calls) every entry point that takes a stream is bracketed by
+  CUDA events on the launching stream, so that bench.py can report where an eager step spends its device time."""
+
+  def __init__(self, lib):
+    object.__setattr__(self, '_lib', lib)
+
+  def __getattr__(self, name):
+    fn = getattr(self._lib, name)
+    if CALL_PROFILE[0] is None or not name.startswith('tfpp_') or name.endswith(('_workspace', 'last_error')) or \
+        name.startswith('tfpp_peer_') and not name.endswith(('_step', '_barrier')):
+      return fn
+
+    def timed(*args):
+      import torch  # pylint: disable=import-outside-toplevel
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      rc = fn(*args)
+      e1.record()
+      CALL_PROFILE[0].append((name, e0, e1))
+      return rc
+    return timed
+
+
+CALL_PROFILE = [None]
+
+
+def profile_calls(fn):
+  """Run fn() once with CUDA events around every C-ABI call; returns {entry point: (milliseconds, calls)}.  Meaningful on
+  ONE stream only (overlapping streams would charge a kernel for its neighbours)."""
+  import torch  # pylint: disable=import-outside-toplevel
+  CALL_PROFILE[0] = []
+  try:
+    fn()
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1 in CALL_PROFILE[0]:
+      a = agg.setdefault(name, [0.0, 0])
+      a[0] += e0.elapsed_time(e1)
+      a[1] += 1
+  finally:
+    CALL_PROFILE[0] = None
+  return {k: (v[0], v[1]) for k, v in agg.items()}
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1

@@ -64,7 +64,9 @@ __global__ void __launch_bounds__(32 * MBLK + 32 * EPI + 32 * kLoadWarps, 1) hal
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   float* sbias = reinterpret_cast<float*>(bars + 16);   // [64] per-column bias (0 beyond n_valid / without bias)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it (the
+  // M block of an MMA-issuing warp, hence its descriptors) in uniform registers instead of electing lane by lane
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int num_tiles = tiles_per_img * p.B;
   if (threadIdx.x < 64) sbias[threadIdx.x] = (p.bias != nullptr && static_cast<int>(threadIdx.x) < p.n_valid) ? __ldg(p.bias + threadIdx.x) : 0.f;
@@ -146,8 +148,11 @@ __global__ void __launch_bounds__(32 * MBLK + 32 * EPI + 32 * kLoadWarps, 1) hal
     // With N = 32..64 a tcgen05.mma is 16-32 cycles of tensor work but ~150 cycles of dependent descriptor /
     // uniform-register instructions to issue (profiles/r02_ncu_halo_conv_v2.txt: one issuing thread was busy 74 % of the
     // kernel): four issuers, each with its own commits, bring the issue rate to the tensor pipe's.
-    if (lane == 0) {
+    // The whole warp walks the loop (waits, descriptor arithmetic) so that the compiler keeps the descriptors in uniform
+    // registers; only the tcgen05 instructions themselves are issued by lane 0.
+    {
       const int blk = warp;
+      const bool leader = elect_one();
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const uint32_t idesc = make_idesc_bf16(128, p.N);
@@ -174,12 +179,16 @@ __global__ void __launch_bounds__(32 * MBLK + 32 * EPI + 32 * kLoadWarps, 1) hal
             const uint64_t a_tap = a0 + static_cast<uint64_t>(blk * 128 + ky * PW + kx);
             const uint64_t b_tap = b0 + static_cast<uint64_t>(tap) * w_tap_16;
             for (int kk = 0; kk < ksteps; ++kk)
-              umma_bf16(d_tmem, a_tap + static_cast<uint64_t>(kk) * (2 * (PLANE_BYTES >> 4)), b_tap + static_cast<uint64_t>(kk) * w_k_16,
-                        idesc, (tap | kk) ? 1u : 0u);
+              if (leader)
+                umma_bf16(d_tmem, a_tap + static_cast<uint64_t>(kk) * (2 * (PLANE_BYTES >> 4)),
+                          b_tap + static_cast<uint64_t>(kk) * w_k_16, idesc, (tap | kk) ? 1u : 0u);
           }
         }
-        umma_commit(smem_u32(&empty_bar[stage]));    // the tile's planes may be overwritten
-        umma_commit(smem_u32(&tfull_bar[acc]));      // the accumulators are complete
+        if (leader) {
+          umma_commit(smem_u32(&empty_bar[stage]));    // the tile's planes may be overwritten
+          umma_commit(smem_u32(&tfull_bar[acc]));      // the accumulators are complete
+        }
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
@@ -358,29 +367,32 @@ __global__ void __launch_bounds__(kThreadsH, 1) halo_umma_gconv3x3_kernel(const 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elected lane: descriptors stay in uniform registers (see the dense kernel)
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const uint32_t idesc = make_idesc_bf16(128, 32);
       const uint32_t w_u = smem_u32(wsm);
+      const uint64_t b0 = make_nosw_kmajor_desc(w_u, 32 * 16, 128);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+        const uint64_t a0 = make_nosw_kmajor_desc(st, GPLANE_BYTES, 128);   // start-address fields advance in 16-byte units
+#pragma unroll
         for (int g = 0; g < 3; ++g) {
+#pragma unroll
           for (int blk = 0; blk < GMBLK; ++blk) {
             const uint32_t d_tmem = tmem_base + acc * 256 + (g * GMBLK + blk) * 32;
+#pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int ky = tap / 3, kx = tap - ky * 3;
-              const uint32_t a_start = st + (g * 3) * GPLANE_BYTES + static_cast<uint32_t>(blk * 128 + ky * PW + kx) * 16;
-              const uint32_t b_start = w_u + (g * 9 + tap) * (32 * 32 * 2);
+              const uint64_t a_tap = a0 + static_cast<uint64_t>((g * 3) * (GPLANE_BYTES >> 4) + blk * 128 + ky * PW + kx);
+              const uint64_t b_tap = b0 + static_cast<uint64_t>((g * 9 + tap) * ((32 * 32 * 2) >> 4));
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t adesc = make_nosw_kmajor_desc(a_start + kk * 2 * GPLANE_BYTES, GPLANE_BYTES, 128);
-                const uint64_t bdesc = make_nosw_kmajor_desc(b_start + kk * 2 * (32 * 16), 32 * 16, 128);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | kk) ? 1u : 0u);
-              }
+              for (int kk = 0; kk < 2; ++kk)
+                umma_bf16(d_tmem, a_tap + static_cast<uint64_t>(kk * 2 * (GPLANE_BYTES >> 4)),
+                          b_tap + static_cast<uint64_t>(kk * 2 * ((32 * 16) >> 4)), idesc, (tap | kk) ? 1u : 0u);
             }
           }
         }

@@ -150,7 +150,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {  // one elected lane: the compiler keeps the descriptors in uniform registers (no per-MMA elect loop)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;

@@ -110,7 +110,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t idesc = make_idesc_bf16_mn(128, p.bn);
