@@ -115,6 +115,8 @@ _PROTOS = {
     'tfpp_small_mha_bwd_dropout': [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, I, P, F, I,
                                    P],
     'tfpp_adamw_amsgrad': [P, P, P, P, P, L, F, F, F, F, F, I, F, P, P, P],
+    'tfpp_gru_cell_head': [P, I, P] + [P] * 10 + [P, P, P, I, I, I, I, I, I, P],
+    'tfpp_gru_cell_head_bwd': [P, I, P] + [P] * 9 + [P] * 4 + [P] * 11 + [I, I, I, I, I, I, P],
     'tfpp_centernet_targets': [P, P, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P, P, P, P],
     'tfpp_nms_rotated': [P, I, I, I, F, F, I, F, F, F, P, P, P, P],
     # NVLink peer-memory gradient exchange fused with AdamW (csrc/peer_exchange.cu)

@@ -487,6 +487,27 @@ int tfpp_mha_bwd_f32(const float* q, long long q_sb, long long q_sr, const float
                      int tk, int head_dim, const unsigned long long* drop_rng, float drop_p, unsigned drop_site,
                      tfpp_stream_t stream);
 
+/* ---- the original TransFuser planner head (config.transformer_decoder_join = False; csrc/gru_cell.cu) ---------------
+ * GRUWaypointsPredictorTransFuser (model.py:870-913): hidden state h_0 = joined[:, :hidden], first input
+ * x_0 = joined[:, hidden:hidden+2] (learn_origin) or 0; per step h = GRUCell([x, target_point], h), x += Linear(h);
+ * waypoints (batch, steps, 2) = the x after every step.  Optionally the target-speed MLP (Linear-ReLU-Linear,
+ * model.py:113-118,371-376) on joined[:, :hidden] -> speed_logits (batch, n_speed).  joined rows are joined_stride
+ * floats apart.  h_all (batch, steps + 1, hidden) keeps the states for the backward pass (NULL in inference).
+ * Backward: BPTT; d_joined (batch, joined_stride) and every parameter gradient are ACCUMULATED (+=). */
+int tfpp_gru_cell_head(const float* joined, int joined_stride, const float* target_point, const float* w_ih,
+                       const float* w_hh, const float* b_ih, const float* b_hh, const float* w_out, const float* b_out,
+                       const float* w_ts0, const float* b_ts0, const float* w_ts1, const float* b_ts1, float* waypoints,
+                       float* speed_logits, float* h_all, int batch, int steps, int hidden, int input_size,
+                       int learn_origin, int n_speed, tfpp_stream_t stream);
+int tfpp_gru_cell_head_bwd(const float* joined, int joined_stride, const float* target_point, const float* w_ih,
+                           const float* w_hh, const float* b_ih, const float* b_hh, const float* w_out,
+                           const float* b_out, const float* w_ts0, const float* b_ts0, const float* w_ts1,
+                           const float* waypoints, const float* h_all, const float* d_waypoints,
+                           const float* d_speed_logits, float* d_joined, float* dw_ih, float* dw_hh, float* db_ih,
+                           float* db_hh, float* dw_out, float* db_out, float* dw_ts0, float* db_ts0, float* dw_ts1,
+                           float* db_ts1, int batch, int steps, int hidden, int input_size, int learn_origin,
+                           int n_speed, tfpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
