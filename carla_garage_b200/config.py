@@ -102,6 +102,7 @@ class GlobalConfig:
     self.wp_dilation = 1
     self.extra_sensor_channels = 128
     self.use_tp = True
+    self.learn_origin = 1  # config.py:192
     self.tp_attention = False
     self.multi_wp_output = False
     self.pred_len = int(2.0 * self.carla_fps) // self.data_save_freq

@@ -22,7 +22,7 @@ PARAM_EPOCH = [0]  # bumped by the fused optimizer (it updates parameter storage
 
 # kinds whose pack is a pure gather (+ zero padding) of parameter elements: eligible for the one-kernel PackPlan
 _GATHER_KINDS = frozenset(('conv', 'gconv', 'gconv_halo', 'gconv_halo_t', 'gconv_halo_umma', 'gconv_halo_umma_t', 'conv_halo_umma', 'conv_halo_umma_t', 'linear', 'conv_t', 'conv_rows_pad', 'conv_dgrad_smallc', 'gconv_t', 'linear_t',
-                           'rows_t', 'cat_linear_t', 'cat_conv_t', 'blockdiag_1x1_t', 'rows', 'rows_f32', 'cat_linear',
+                           'rows_t', 'cols', 'cols_t', 'cat_linear_t', 'cat_conv_t', 'blockdiag_1x1_t', 'rows', 'rows_f32', 'cat_linear',
                            'cat_rows', 'cat_rows_f32', 'cat_f32', 'cat_conv', 'blockdiag_1x1', 'repeat_rows'))
 
 
@@ -61,6 +61,12 @@ def _build_pack(kind, params, extra, dtb=BF16, dtf=F32):
     return ops.pack_grouped_conv_weight_t(params[0], dt=dtb)
   if kind == 'linear_t':  # (N,K) -> (K, N padded to 8)
     w = params[0].detach().reshape(params[0].shape[0], -1).t().to(dtb).contiguous()
+    pad = (-w.shape[1]) % 8
+    return torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
+  if kind == 'cols':  # column slice of a (N,K) matrix: the part of a Linear that multiplies one piece of a concatenated input
+    return params[0].detach()[:, extra[0]:extra[1]].to(dtb).contiguous()
+  if kind == 'cols_t':  # its input-gradient operand: (k1-k0, N padded to 8)
+    w = params[0].detach()[:, extra[0]:extra[1]].t().to(dtb).contiguous()
     pad = (-w.shape[1]) % 8
     return torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
   if kind == 'rows_t':
@@ -620,8 +626,21 @@ class Engine:
       feats = self.conv_bias(p4u, bb.up_conv4, ACT_RELU)
     grid = img if (cfg.use_semantic or cfg.use_depth) else None
     self._tap('bev_feature_grid', feats)
-    self._tap('fused_features', lid)
     self._tap('image_feature_grid', grid)
+    if not cfg.transformer_decoder_join:
+      # transfuser.py:188-197: global average pools, lidar_to_img_features_end, sum -> (B, num_features)
+      b, c, cl = img.shape[0], img.shape[3], lid.shape[3]
+      img_pool = torch.empty((b, 1, c), dtype=ops.act_dtype(), device=img.device)
+      ops.avgpool_tokens(img, img_pool, 1, 1, 0)
+      lid_pool = torch.empty((b, 1, cl), dtype=ops.act_dtype(), device=img.device)
+      ops.avgpool_tokens(lid, lid_pool, 1, 1, 0)
+      end = bb.lidar_to_img_features_end
+      fused = ops.linear(lid_pool.view(b, cl), packed(end.weight, 'linear'), bias=packed(end.bias, 'f32'),
+                         res=img_pool.view(b, c))
+      self._save(op='global_fuse', img=img, lid=lid, lid_pool=lid_pool, fused=fused, b=b, c=c, cl=cl)
+      self._tap('fused_features', fused)
+      return feats, fused, grid
+    self._tap('fused_features', lid)
     return feats, lid, grid
 
   # ------------------------------------------------------------------------------------------------ heads
@@ -706,6 +725,54 @@ class Engine:
       self._tap('joined', joined[1].view(b, -1, d))
     return pred_cp, pred_ts, pred_wp
 
+  def planner_mlp(self, fused, target_point, ego_vel, command, training):
+    """model.py:306-322,359-376 with transformer_decoder_join = False (the original TransFuser planner): extra-sensor
+    embedding ++ globally pooled features -> 3-layer MLP join -> autoregressive GRUCell heads
+    (GRUWaypointsPredictorTransFuser) + the target-speed MLP on the first gru_hidden_size features.
+    Returns (pred_checkpoint, pred_target_speed, pred_wp)."""
+    m, cfg = self.m, self.cfg
+    b, c = fused.shape
+    dev = fused.device
+    hs, e = cfg.gru_hidden_size, cfg.extra_sensor_channels
+    vn, ese = m.velocity_normalization, m.extra_sensor_encoder
+    es = torch.empty((b, 1, e), dtype=ops.act_dtype(), device=dev)
+    zero_pos = self._const(f'zeros{e}', lambda: torch.zeros(e), dev)
+    vmean, vvar = (0.0, 1.0) if training else packed((vn.running_mean, vn.running_var), 'host_floats')
+    ops.extra_sensor_token(ego_vel.float().contiguous(), command.float().contiguous(), vmean, vvar, training,
+                           vn.running_mean if training else None, vn.running_var if training else None, ese[0].weight,
+                           ese[0].bias, ese[2].weight, ese[2].bias, zero_pos, es if es.dtype == BF16 else None,
+                           es if es.dtype == F32 else None, 1, 0)
+    if training:
+      self._count_batch(vn)
+    j0, j1, j2 = m.join[0], m.join[2], m.join[4]
+    # Linear over the concatenation [fused | extra sensors] (model.py:322) = two GEMMs on the column slices of its weight
+    h1a = ops.linear(fused, packed(j0.weight, 'cols', 0, c), out_f32=True)
+    h1 = ops.linear(es.view(b, e), packed(j0.weight, 'cols', c, c + e), bias=packed(j0.bias, 'f32'), res=h1a, act=ACT_RELU)
+    h2 = ops.linear(h1, packed(j1.weight, 'linear'), bias=packed(j1.bias, 'f32'), act=ACT_RELU)
+    joined = ops.linear(h2, packed(j2.weight, 'linear'), bias=packed(j2.bias, 'f32'), act=ACT_RELU, out_f32=True)
+    self._tap('joined', joined)
+    self._save(op='mlp_join', fused=fused, es=es, h1=h1, h2=h2, joined=joined, b=b, c=c, e=e, ego_vel=ego_vel,
+               command=command, training=training)
+    tp = target_point.float().contiguous() if cfg.use_tp else None
+    pred_wp = pred_cp = pred_ts = None
+    if getattr(cfg, 'use_wp_gru', False):
+      pred_wp = self._gru_cell_head(joined, m.wp_decoder, None, tp, 'planner_wp')[0]
+    if cfg.use_controller_input_prediction:
+      pred_cp, pred_ts = self._gru_cell_head(joined, m.checkpoint_decoder, m.target_speed_network, tp, 'planner')
+    return pred_cp, pred_ts, pred_wp
+
+  def _gru_cell_head(self, joined, cd, tsn, target_point, seed_key):
+    """GRUWaypointsPredictorTransFuser.forward (model.py:886-913) [+ target_speed_network, model.py:376]."""
+    cell = cd.wp_decoder
+    ts_w = (tsn[0].weight, tsn[0].bias, tsn[2].weight, tsn[2].bias) if tsn is not None else (None,) * 4
+    wp, ts, h_all = ops.gru_cell_head(joined, target_point, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh,
+                                      cd.output.weight, cd.output.bias, *ts_w, steps=cd.prediction_len,
+                                      hidden=cd.hidden_size, learn_origin=bool(self.cfg.learn_origin),
+                                      want_h=self.tape is not None)
+    self._save(op='gru_cell_head', joined=joined, wp=wp, h_all=h_all, target_point=target_point, cd=cd, tsn=tsn,
+               seed_key=seed_key)
+    return wp, ts
+
   def _decode(self, query, kvs, b, n_mem, training):
     """nn.TransformerDecoder (post-norm layers + final LayerNorm, model.py:137-143,352) over one learned query set.
     Returns (pre-norm x, joined f32, LayerNorm statistics)."""
@@ -779,17 +846,18 @@ class Engine:
     # under CUDA-graph capture); its tape records are tagged so the backward pass can do the same
     tp, ev_, cmd = target_point.to(rgb.device), ego_vel.to(rgb.device), command.to(rgb.device)
     overlap = rgb.is_cuda and os.environ.get('TFPP_NO_OVERLAP', '0') != '1'
+    plan = self.planner if cfg.transformer_decoder_join else self.planner_mlp
     if overlap:
       main, side = torch.cuda.current_stream(), self.side_stream(rgb.device)
       side.wait_stream(main)
       first = len(self.tape) if self.tape is not None else 0
       with torch.cuda.stream(side):
-        pred_checkpoint, pred_target_speed, pred_wp = self.planner(fused, tp, ev_, cmd, training)
+        pred_checkpoint, pred_target_speed, pred_wp = plan(fused, tp, ev_, cmd, training)
       if self.tape is not None:
         for r in self.tape[first:]:
           r['side'] = 'planner'
     else:
-      pred_checkpoint, pred_target_speed, pred_wp = self.planner(fused, tp, ev_, cmd, training)
+      pred_checkpoint, pred_target_speed, pred_wp = plan(fused, tp, ev_, cmd, training)
     pred_semantic = pred_depth = pred_bev_semantic = pred_bounding_box = None
     if cfg.use_semantic:
       pred_semantic = self.perspective_decoder(m.semantic_decoder, grid)

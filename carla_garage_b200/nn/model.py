@@ -94,13 +94,17 @@ class GRUWaypointsPredictorInterFuser(regnet._NoForward):  # pylint: disable=pro
     self.waypoints = waypoints
 
 
-class GRUWaypointsPredictorTransFuser(nn.Module):
-  """model.py:870-913 — the non-decoder-join variant; not on the TransFuser++ default path."""
+class GRUWaypointsPredictorTransFuser(regnet._NoForward):  # pylint: disable=protected-access
+  """Parameter container of model.py:870-884 (the waypoint GRU of the original TransFuser: autoregressive GRUCell,
+  hidden state initialised with the scene feature); forward = tfpp_gru_cell_head."""
 
-  def __init__(self, *args, **kwargs):
+  def __init__(self, config, pred_len, hidden_size, target_point_size):
     super().__init__()
-    raise NotImplementedError('GRUWaypointsPredictorTransFuser (transformer_decoder_join=False) is not on the '
-                              'TransFuser++ default path')
+    self.wp_decoder = nn.GRUCell(input_size=2 + target_point_size, hidden_size=hidden_size)
+    self.output = nn.Linear(hidden_size, 2)
+    self.config = config
+    self.prediction_len = pred_len
+    self.hidden_size = hidden_size
 
 
 class PositionEmbeddingSine(nn.Module):
@@ -151,9 +155,6 @@ class LidarCenterNet(nn.Module):
       raise NotImplementedError(f'backbone {config.backbone} is outside the TransFuser++ hot path (SURVEY.md §8f)')
     else:
       raise ValueError('The chosen vision backbone does not exist. The options are: transFuser, aim, bev_encoder')
-    if not config.transformer_decoder_join:
-      raise NotImplementedError('transformer_decoder_join=False (global-pool MLP join + GRUWaypointsPredictorTransFuser, '
-                                'model.py:184-209) is not built')
     if not (config.use_controller_input_prediction or config.use_wp_gru) or config.tp_attention or config.multi_wp_output:
       raise NotImplementedError('built planners: checkpoint + target speed (default) and / or the waypoint GRU '
                                 '(use_wp_gru) through the transformer decoder; tp_attention / multi_wp_output are not')
@@ -188,6 +189,9 @@ class LidarCenterNet(nn.Module):
           scale_factor_0=self.backbone.perspective_upsample_factor // config.deconv_scale_factor_0,
           scale_factor_1=self.backbone.perspective_upsample_factor // config.deconv_scale_factor_1)
     d = config.gru_input_size
+    if not config.transformer_decoder_join:  # model.py:184-209: the original TransFuser planner
+      self._init_mlp_join(config, target_point_size)
+      return
     if config.use_controller_input_prediction:
       self.target_speed_network = nn.Sequential(nn.Linear(d, d), nn.ReLU(inplace=True),
                                                 nn.Linear(d, len(config.target_speeds)))
@@ -214,6 +218,32 @@ class LidarCenterNet(nn.Module):
     self.velocity_normalization = nn.BatchNorm1d(1, affine=False)
     self.extra_sensor_encoder = nn.Sequential(nn.Linear(7, 128), nn.ReLU(inplace=True), nn.Linear(128, d),
                                               nn.ReLU(inplace=True))
+    self._init_common(config)
+
+  def _init_mlp_join(self, config, target_point_size):
+    """transformer_decoder_join = False (model.py:113-118,184-209,211-221): global-pooled features ++ extra-sensor
+    embedding -> 3-layer MLP -> GRUWaypointsPredictorTransFuser heads + target-speed MLP on the first hidden_size
+    features.  Same registration order as the reference (state_dict key order)."""
+    hs = config.gru_hidden_size
+    if config.use_controller_input_prediction:
+      self.target_speed_network = nn.Sequential(nn.Linear(hs, hs), nn.ReLU(inplace=True),
+                                                nn.Linear(hs, len(config.target_speeds)))
+    join_out = hs + 2 if config.learn_origin else hs
+    self.join = nn.Sequential(nn.Linear(self.backbone.num_features + config.extra_sensor_channels, 256),
+                              nn.ReLU(inplace=True), nn.Linear(256, 128), nn.ReLU(inplace=True),
+                              nn.Linear(128, join_out), nn.ReLU(inplace=True))
+    if config.use_wp_gru:
+      self.wp_decoder = GRUWaypointsPredictorTransFuser(config, pred_len=config.pred_len // config.wp_dilation,
+                                                        hidden_size=hs, target_point_size=target_point_size)
+    if config.use_controller_input_prediction:
+      self.checkpoint_decoder = GRUWaypointsPredictorTransFuser(config, pred_len=config.predict_checkpoint_len,
+                                                                hidden_size=hs, target_point_size=target_point_size)
+    self.velocity_normalization = nn.BatchNorm1d(1, affine=False)
+    self.extra_sensor_encoder = nn.Sequential(nn.Linear(7, 128), nn.ReLU(inplace=True),
+                                              nn.Linear(128, config.extra_sensor_channels), nn.ReLU(inplace=True))
+    self._init_common(config)
+
+  def _init_common(self, config):
     self.turn_controller = PIDController(config.turn_kp, config.turn_ki, config.turn_kd, config.turn_n)
     self.speed_controller = PIDController(config.speed_kp, config.speed_ki, config.speed_kd, config.speed_n)
     self.turn_controller_direct = PIDController(config.turn_kp, config.turn_ki, config.turn_kd, config.turn_n)

@@ -103,9 +103,13 @@ class TransfuserBackbone(nn.Module):
          for i in range(4)])
     self.num_image_features = info_i[start_index + 3]['num_chs']
     self.perspective_upsample_factor = info_i[start_index + 3]['reduction'] // config.perspective_downsample_factor
-    if not config.transformer_decoder_join:
-      raise NotImplementedError('only transformer_decoder_join=True (the TransFuser++ default) is built')
-    self.num_features = info_l[start_index + 3]['num_chs']
+    if config.transformer_decoder_join:
+      self.num_features = info_l[start_index + 3]['num_chs']
+    else:  # transfuser.py:102-111: globally pooled image + LiDAR features feed an MLP join
+      if not config.add_features:
+        raise NotImplementedError('add_features=False (concatenated global features) is not built')
+      self.lidar_to_img_features_end = nn.Linear(info_l[start_index + 3]['num_chs'], info_i[start_index + 3]['num_chs'])
+      self.num_features = info_i[start_index + 3]['num_chs']
     channel = config.bev_features_chanels
     self.relu = nn.ReLU(inplace=True)
     if config.detect_boxes or config.use_bev_semantic:
@@ -124,5 +128,9 @@ class TransfuserBackbone(nn.Module):
     eng = engine.Engine.for_backbone(self)
     feats, fused, grid = eng.backbone_forward(image, lidar, training=self.training)
     from .. import ops  # pylint: disable=import-outside-toplevel
-    return (ops.nhwc_to_nchw(feats) if feats is not None else None, ops.nhwc_to_nchw(fused),
+    if not self.config.transformer_decoder_join:
+      fused = fused.float()   # (B, num_features): globally pooled image + LiDAR features (transfuser.py:188-197)
+    else:
+      fused = ops.nhwc_to_nchw(fused)
+    return (ops.nhwc_to_nchw(feats) if feats is not None else None, fused,
             ops.nhwc_to_nchw(grid) if grid is not None else None)

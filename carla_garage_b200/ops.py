@@ -540,6 +540,37 @@ def planner_head(joined, target_point, w_enc, b_enc, w_ih, w_hh, b_ih, b_hh, w_d
   return (cp, ts, h_all) if want_h else (cp, ts)
 
 
+def gru_cell_head(joined, target_point, w_ih, w_hh, b_ih, b_hh, w_out, b_out, w_ts0, b_ts0, w_ts1, b_ts1, steps, hidden,
+                  learn_origin=True, want_h=False):
+  """GRUWaypointsPredictorTransFuser (model.py:870-913) [+ target-speed MLP]: joined (B, hidden [+2]) f32 ->
+  (waypoints (B, steps, 2), speed logits (B, n_speed) | None, h_all (B, steps+1, hidden) | None)."""
+  _dev(joined, F32)
+  b = joined.shape[0]
+  n_speed = w_ts1.shape[0] if w_ts1 is not None else 0
+  wp = torch.empty((b, steps, 2), dtype=F32, device=joined.device)
+  ts = torch.empty((b, n_speed), dtype=F32, device=joined.device) if n_speed else None
+  h_all = torch.empty((b, steps + 1, hidden), dtype=F32, device=joined.device) if want_h else None
+  check(_lib.load().tfpp_gru_cell_head(joined.data_ptr(), joined.shape[1], _p(target_point), w_ih.data_ptr(),
+                                       w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), w_out.data_ptr(), b_out.data_ptr(),
+                                       _p(w_ts0), _p(b_ts0), _p(w_ts1), _p(b_ts1), wp.data_ptr(), _p(ts), _p(h_all), b, steps,
+                                       hidden, w_ih.shape[1], int(learn_origin), n_speed, _stream()), 'tfpp_gru_cell_head')
+  return wp, ts, h_all
+
+
+def gru_cell_head_bwd(joined, target_point, w_ih, w_hh, b_ih, b_hh, w_out, b_out, w_ts0, b_ts0, w_ts1, wp, h_all, dwp, dts,
+                      djoined, grads, steps, hidden, learn_origin=True):
+  """BPTT of gru_cell_head; grads = (dw_ih, dw_hh, db_ih, db_hh, dw_out, db_out, dw_ts0, db_ts0, dw_ts1, db_ts1) f32
+  tensors (the last four None without a target-speed head), all accumulated into, like djoined."""
+  b = joined.shape[0]
+  n_speed = w_ts1.shape[0] if w_ts1 is not None else 0
+  check(_lib.load().tfpp_gru_cell_head_bwd(joined.data_ptr(), joined.shape[1], _p(target_point), w_ih.data_ptr(),
+                                           w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), w_out.data_ptr(),
+                                           b_out.data_ptr(), _p(w_ts0), _p(b_ts0), _p(w_ts1), wp.data_ptr(), h_all.data_ptr(),
+                                           dwp.data_ptr(), _p(dts), djoined.data_ptr(), *[_p(g) for g in grads], b, steps,
+                                           hidden, w_ih.shape[1], int(learn_origin), n_speed, _stream()),
+        'tfpp_gru_cell_head_bwd')
+
+
 def decode_heatmap(heat, wh, offset, yaw_cls, yaw_res, k=100, img_h=256, img_w=256):
   """NCHW f32 maps (possibly channel-slice views with a batch stride) -> (B, k, 9) f32 (center_net.py:172-237)."""
   b, n_cls, h, w = heat.shape

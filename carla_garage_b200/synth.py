@@ -162,3 +162,26 @@ def make_gt_boxes(n_samples, seed=1234, max_boxes=30):
     b[:, 7] = torch.randint(0, 4, (n,), generator=g).float()
     out.append(b.numpy().astype(np.float32))
   return out
+
+
+def make_waypoint_labels(batch, n_wp, seed=1234):
+  """ego_waypoints label of train.py:797 (use_wp_gru): (B, pred_len, 2) f32, a forward-moving track."""
+  g = _gen(seed, 'waypoints')
+  return torch.cumsum(torch.rand(batch, n_wp, 2, generator=g), dim=1)
+
+
+def mlp_join_state(golden_dir):
+  """The seeded state_dict of the transformer_decoder_join = False / use_wp_gru goldens
+  (tests/golden/make_golden_mlp_join.py): make_state_dict(seed 0) over that configuration's keys + the fixed buffers."""
+  import json
+  import os
+  shapes = json.load(open(os.path.join(golden_dir, 'mlp_join_keys.json')))['shapes']
+  valid = torch.from_numpy(np.load(os.path.join(golden_dir, 'valid_bev_pixels.npz'))['valid']).float()
+  fixed = {
+      'valid_bev_pixels': valid,
+      'valid_bev_pixels_inv': 1.0 - valid,
+      'loss_speed.weight': torch.tensor([0.866605263873406, 7.4527377240841775, 1.2281629310898465, 0.5269622904065803]),
+      'loss_semantic.weight': torch.ones(7),
+      'loss_bev_semantic.weight': torch.ones(11),
+  }
+  return make_state_dict(shapes, seed=0, fixed=fixed)

@@ -607,6 +607,70 @@ class Backward:
                            g(m.join.norm.bias))
     self.G[id(r['x'])] = dx
 
+  def gru_cell_head(self, r, seeds):
+    """adjoint of Engine._gru_cell_head: BPTT through the autoregressive GRUCell (+ target-speed MLP)."""
+    st, g = self.st, self.st.g
+    dwp, dts = seeds.pop(r['seed_key'])
+    cd, tsn, joined = r['cd'], r['tsn'], r['joined']
+    cell = cd.wp_decoder
+    dj = self.G.get(id(joined))
+    if dj is None:   # the heads share the joined feature: the kernels accumulate into one zero-initialised gradient
+      dj = torch.zeros_like(joined)
+      self.G[id(joined)] = dj
+    tw = (tsn[0].weight, tsn[0].bias, tsn[2].weight) if tsn is not None else (None, None, None)
+    tg = (g(tsn[0].weight), g(tsn[0].bias), g(tsn[2].weight), g(tsn[2].bias)) if tsn is not None else (None,) * 4
+    ops.gru_cell_head_bwd(joined, r['target_point'], cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh,
+                          cd.output.weight, cd.output.bias, *tw, r['wp'], r['h_all'], dwp.contiguous(),
+                          dts.contiguous() if (dts is not None and tsn is not None) else None, dj,
+                          (g(cell.weight_ih), g(cell.weight_hh), g(cell.bias_ih), g(cell.bias_hh), g(cd.output.weight),
+                           g(cd.output.bias)) + tg, steps=cd.prediction_len, hidden=cd.hidden_size,
+                          learn_origin=bool(self.eng.cfg.learn_origin))
+
+  def mlp_join(self, r):
+    """adjoint of Engine.planner_mlp up to the joined feature (model.py:306-322,360)."""
+    from . import _lib  # pylint: disable=import-outside-toplevel
+    st, m, g = self.st, self.eng.m, self.st.g
+    b, c, e = r['b'], r['c'], r['e']
+    fused, es, h1, h2, joined = r['fused'], r['es'], r['h1'], r['h2'], r['joined']
+    j0, j1, j2 = m.join[0], m.join[2], m.join[4]
+    dj = self.G.pop(id(joined))
+    n2 = j2.weight.shape[0]
+    # joined is f32 (b, n2): with one pixel per sample the NCHW-f32 layout of act_bwd is exactly that matrix
+    dz3 = ops.act_bwd(dj, joined, ACT_RELU, b, 1, n2, layout=1, dbias=g(j2.bias), channels_padded=_pad8(n2))
+    dh2 = self.linear_bwd(dz3, h2, g(j2.weight), packed(j2.weight, 'linear_t'), n2, j2.weight.shape[1], out_f32=False,
+                          cout_valid=n2)
+    dz2 = ops.act_bwd(dh2, h2, ACT_RELU, 1, b, j1.weight.shape[0], dbias=g(j1.bias))
+    dh1 = self.linear_bwd(dz2, h1, g(j1.weight), packed(j1.weight, 'linear_t'), j1.weight.shape[0], j1.weight.shape[1],
+                          out_f32=False)
+    n0 = j0.weight.shape[0]
+    dz1 = ops.act_bwd(dh1, h1, ACT_RELU, 1, b, n0, dbias=g(j0.bias))
+    gw0 = g(j0.weight)   # (256, c + e): the two column blocks receive their own weight gradients
+    ops.conv_wgrad(dz1.view(1, 1, b, n0), fused.view(1, 1, b, c), out=gw0, out_strides=(c + e, 0, 1))
+    ops.conv_wgrad(dz1.view(1, 1, b, n0), es.view(1, 1, b, e), out=gw0[:, c:], out_strides=(c + e, 0, 1))
+    self.add(fused, ops.linear(dz1, packed(j0.weight, 'cols_t', 0, c)))
+    des = ops.linear(dz1, packed(j0.weight, 'cols_t', c, c + e), out_f32=True)
+    ese, vn = m.extra_sensor_encoder, m.velocity_normalization
+    training = r['training']
+    dpos = torch.zeros(e, dtype=F32, device=des.device)   # the kernel's positional-embedding slot: unused on this path
+    _lib.check(_lib.load().tfpp_extra_sensor_token_bwd(
+        r['ego_vel'].float().contiguous().data_ptr(), r['command'].float().contiguous().data_ptr(),
+        0.0 if training else float(vn.running_mean[0]), 1.0 if training else float(vn.running_var[0]), int(training),
+        ese[0].weight.data_ptr(), ese[0].bias.data_ptr(), ese[2].weight.data_ptr(), ese[2].bias.data_ptr(), des.data_ptr(), e,
+        g(ese[0].weight).data_ptr(), g(ese[0].bias).data_ptr(), g(ese[2].weight).data_ptr(), g(ese[2].bias).data_ptr(),
+        dpos.data_ptr(), b, r['command'].shape[1], ese[0].weight.shape[0], e, ops._stream()), 'extra_sensor_bwd')  # pylint: disable=protected-access
+
+  def global_fuse(self, r):
+    """adjoint of the global pools + lidar_to_img_features_end + sum (transfuser.py:188-197)."""
+    st, bb, g = self.st, self.eng.bb, self.st.g
+    b, c, cl = r['b'], r['c'], r['cl']
+    img, lid = r['img'], r['lid']
+    df = self.G.pop(id(r['fused']))   # (b, c)
+    end = bb.lidar_to_img_features_end
+    ops.act_bwd(df, None, ACT_NONE, 1, b, c, dbias=g(end.bias), want_dz=False)
+    dlp = self.linear_bwd(df, r['lid_pool'].view(b, cl), g(end.weight), packed(end.weight, 'linear_t'), c, cl, out_f32=False)
+    self.G[id(img)] = ops.pool_bwd_add(self.G.get(id(img)), df, tuple(img.shape), 1, 1, 1, 0)
+    self.G[id(lid)] = ops.pool_bwd_add(self.G.get(id(lid)), dlp, tuple(lid.shape), 1, 1, 1, 0)
+
   def planner_queries(self, r):
     # a learned query set repeated over the batch (model.py:329,349): its gradient is the sum over the batch
     dx0 = self.G.pop(id(r['x0']))
@@ -794,6 +858,12 @@ class Backward:
       self.center_head(r, seeds)
     elif op == 'bev_tail':
       self.bev_tail(r, seeds)
+    elif op == 'gru_cell_head':
+      self.gru_cell_head(r, seeds)
+    elif op == 'mlp_join':
+      self.mlp_join(r)
+    elif op == 'global_fuse':
+      self.global_fuse(r)
     elif op == 'planner_head':
       self.planner_head(r, seeds)
     elif op == 'dec_layer':

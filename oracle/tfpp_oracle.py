@@ -210,6 +210,12 @@ def backbone_forward(sd, image, lidar, cfg, training=False, p='backbone', taps=N
           cfg['lidar_resolution_width'] // cfg['bev_down_sample_factor'])
   p3 = F.interpolate(p4, size=size, mode='bilinear', align_corners=False)
   p3 = F.relu(F.conv2d(p3, sd[p + '.up_conv4.weight'], sd[p + '.up_conv4.bias'], padding=1))
+  if not cfg.get('transformer_decoder_join', True):
+    # transfuser.py:188-197 (add_features): global pools, lidar_to_img_features_end, sum
+    gi = torch.flatten(F.adaptive_avg_pool2d(x_img, 1), 1)
+    gl = torch.flatten(F.adaptive_avg_pool2d(x_lid, 1), 1)
+    gl = F.linear(gl, sd[p + '.lidar_to_img_features_end.weight'], sd[p + '.lidar_to_img_features_end.bias'])
+    return p3, gi + gl, x_img
   return p3, x_lid, x_img
 
 
@@ -364,6 +370,54 @@ def planner(sd, fused, target_point, ego_vel, command, cfg=None, training=False,
   return pred_checkpoint, pred_target_speed
 
 
+def gru_waypoints_transfuser(sd, p, z, target_point, steps, cfg):
+  """GRUWaypointsPredictorTransFuser.forward, model.py:886-913 (learn_origin, use_tp): autoregressive nn.GRUCell."""
+  hs = cfg['gru_hidden_size']
+  if cfg.get('learn_origin', 1):
+    x, z = z[:, hs:hs + 2], z[:, :hs]
+  else:
+    x = torch.zeros((z.shape[0], 2), dtype=z.dtype)
+  w_ih, w_hh = sd[p + '.wp_decoder.weight_ih'], sd[p + '.wp_decoder.weight_hh']
+  b_ih, b_hh = sd[p + '.wp_decoder.bias_ih'], sd[p + '.wp_decoder.bias_hh']
+  out = []
+  for _ in range(steps):
+    x_in = torch.cat([x, target_point], dim=1)
+    gi, gh = F.linear(x_in, w_ih, b_ih), F.linear(z, w_hh, b_hh)
+    i_r, i_z, i_n = gi.chunk(3, 1)
+    h_r, h_z, h_n = gh.chunk(3, 1)
+    r, u = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
+    n = torch.tanh(i_n + r * h_n)
+    z = (1 - u) * n + u * z
+    x = F.linear(z, sd[p + '.output.weight'], sd[p + '.output.bias']) + x
+    out.append(x)
+  return torch.stack(out, dim=1)
+
+
+def planner_mlp(sd, fused, target_point, ego_vel, command, cfg, training=False, taps=None):
+  """model.py:306-322,359-376 with transformer_decoder_join = False: (B, num_features) globally pooled features ++
+  extra-sensor embedding -> MLP join -> GRUCell heads + target-speed MLP.  Returns (checkpoint, speed logits, wp)."""
+  vel = F.batch_norm(ego_vel, sd['velocity_normalization.running_mean'].clone(),
+                     sd['velocity_normalization.running_var'].clone(), None, None, training=training, momentum=0.1,
+                     eps=1e-5)
+  es = torch.cat([vel, command], dim=1)
+  es = F.relu(F.linear(es, sd['extra_sensor_encoder.0.weight'], sd['extra_sensor_encoder.0.bias']))
+  es = F.relu(F.linear(es, sd['extra_sensor_encoder.2.weight'], sd['extra_sensor_encoder.2.bias']))
+  x = torch.cat((fused, es), dim=1)
+  for i in (0, 2, 4):
+    x = F.relu(F.linear(x, sd[f'join.{i}.weight'], sd[f'join.{i}.bias']))
+  if taps is not None:
+    taps['joined'] = x
+  hs = cfg['gru_hidden_size']
+  pred_wp = pred_cp = pred_ts = None
+  if cfg.get('use_wp_gru', False):
+    pred_wp = gru_waypoints_transfuser(sd, 'wp_decoder', x, target_point, cfg.get('pred_len', 8), cfg)
+  if cfg.get('use_controller_input_prediction', True):
+    pred_cp = gru_waypoints_transfuser(sd, 'checkpoint_decoder', x, target_point, cfg['predict_checkpoint_len'], cfg)
+    pred_ts = F.linear(F.relu(F.linear(x[:, :hs], sd['target_speed_network.0.weight'], sd['target_speed_network.0.bias'])),
+                       sd['target_speed_network.2.weight'], sd['target_speed_network.2.bias'])
+  return pred_cp, pred_ts, pred_wp
+
+
 def forward(sd, rgb, lidar_bev, target_point, ego_vel, command, cfg=None, training=False, taps=None, dropout=None):
   """LidarCenterNet.forward, model.py:279-392, default GlobalConfig (transFuser backbone, decoder join, all aux
   heads).  Returns the reference's 10-tuple."""
@@ -375,7 +429,13 @@ def forward(sd, rgb, lidar_bev, target_point, ego_vel, command, cfg=None, traini
   if taps is not None:
     taps['bev_feature_grid'], taps['fused_features'], taps['image_feature_grid'] = (bev_feature_grid, fused,
                                                                                     image_feature_grid)
-  pred_checkpoint, pred_target_speed = planner(sd, fused, target_point, ego_vel, command, cfg, training, taps, dropout)
+  pred_wp = None
+  if not cfg.get('transformer_decoder_join', True):
+    pred_checkpoint, pred_target_speed, pred_wp = planner_mlp(sd, fused, target_point, ego_vel, command, cfg, training, taps)
+  else:
+    pl = planner(sd, fused, target_point, ego_vel, command, cfg, training, taps, dropout)
+    pred_checkpoint, pred_target_speed = pl[0], pl[1]
+    pred_wp = pl[2] if len(pl) > 2 else None
   # model.py:372-389
   pred_semantic = perspective_decoder(sd, 'semantic_decoder', image_feature_grid, cfg)
   pred_depth = torch.sigmoid(perspective_decoder(sd, 'depth_decoder', image_feature_grid, cfg)).squeeze(1)
@@ -386,7 +446,7 @@ def forward(sd, rgb, lidar_bev, target_point, ego_vel, command, cfg=None, traini
                     align_corners=False)
   pred_bev_semantic = b * sd['valid_bev_pixels']
   pred_bounding_box = center_net_head(sd, 'head', bev_feature_grid)
-  return (None, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
+  return (pred_wp, pred_target_speed, pred_checkpoint, pred_semantic, pred_bev_semantic, pred_depth,
           pred_bounding_box, None, None, None)
 
 
@@ -460,6 +520,8 @@ def compute_loss(sd, outputs, labels, cfg=None):
   loss['loss_offset'] = (torch.abs(bb[2] - labels['offset']) * pw).sum() / (avg * 2)
   loss['loss_yaw_class'] = (F.cross_entropy(bb[3], labels['yaw_class'], reduction='none') * pw[:, 0]).sum() / avg
   loss['loss_yaw_res'] = (F.smooth_l1_loss(bb[4], labels['yaw_res'], reduction='none') * pw[:, 0:1]).sum() / avg
+  if outputs[0] is not None and 'waypoint' in labels:  # use_wp_gru, model.py:401-402
+    loss['loss_wp'] = torch.mean(torch.abs(outputs[0] - labels['waypoint']))
   return loss
 
 

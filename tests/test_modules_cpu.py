@@ -110,6 +110,7 @@ def test_pack_plan_index_maps_reproduce_every_gather_pack():
            ('gconv_halo_umma_t', (params['gconv'],), ()), ('conv_halo_umma', (params['conv'],), (64,)),
            ('conv_halo_umma_t', (params['conv'],), (48,)), ('linear', (params['lin_a'],), ()), ('linear_t', (params['lin_a'],), ()),
            ('rows', (params['lin_a'],), (8, 24)), ('rows_t', (params['lin_a'],), (8, 24)),
+           ('cols', (params['lin_a'],), (8, 24)), ('cols_t', (params['lin_a'],), (3, 24)),
            ('rows_f32', (params['lin_a'],), (8, 24)), ('cat_linear', (params['lin_a'], params['lin_b']), ()),
            ('cat_linear_t', (params['lin_a'], params['lin_b']), ()), ('cat_rows', (params['lin_a'], params['lin_b']), (0, 8)),
            ('cat_rows_f32', (params['lin_a'], params['lin_b']), (0, 8)), ('cat_f32', (params['vec'], params['lin_b']), ()),
@@ -247,3 +248,17 @@ def test_ensemble_reduction_matches_sensor_agent_semantics():
   want_c = sum(o[2] for o in outs) / 3
   assert torch.allclose(probs, want_p, atol=1e-6) and torch.allclose(cps, want_c, atol=1e-6)
   assert torch.allclose(probs.sum(1), torch.ones(4), atol=1e-6)
+
+
+def test_mlp_join_config_matches_reference_keys():
+  """transformer_decoder_join = False + use_wp_gru (the original TransFuser planner, model.py:184-209): same state_dict
+  keys, shapes and registration ORDER as the unmodified reference (tests/golden/make_golden_mlp_join.py)."""
+  from carla_garage_b200.nn import LidarCenterNet
+  ref = json.load(open(os.path.join(GOLDEN, 'mlp_join_keys.json')))
+  cfg = GlobalConfig()
+  cfg.transformer_decoder_join = False
+  cfg.use_wp_gru = True
+  sd = LidarCenterNet(cfg).state_dict()
+  assert list(sd.keys()) == ref['order']
+  for k, v in sd.items():
+    assert list(v.shape) == ref['shapes'][k], k

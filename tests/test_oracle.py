@@ -183,3 +183,38 @@ def test_targets_oracle_vs_reference_golden():
       else:
         assert np.allclose(v, want, rtol=0, atol=1e-6), (i, k, float(np.abs(v - want).max()))
     assert np.array_equal(t['center_heatmap_target'] == 1, g[f'center_heatmap_target{i}'] == 1)
+
+
+def test_oracle_mlp_join_vs_reference_golden():
+  """The oracle's restatement of the original TransFuser planner (transformer_decoder_join = False, use_wp_gru:
+  model.py:184-209,359-376,870-913; transfuser.py:188-197) against the unmodified reference: training-mode forward,
+  the eleven losses and the gradients of every planner parameter (tests/golden/make_golden_mlp_join.py)."""
+  import json
+  from carla_garage_b200 import synth
+  from oracle import tfpp_oracle as orc
+  g = np.load(os.path.join(GOLDEN, 'mlp_join_b2.npz'))
+  keys = json.load(open(os.path.join(GOLDEN, 'mlp_join_keys.json')))
+  sd = synth.mlp_join_state(GOLDEN)
+  sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k and not k.startswith(('valid_bev', 'loss_'))
+            else v.clone()) for k, v in sd.items()}
+  assert list(sd.keys()) == sorted(keys['order']) or set(sd) == set(keys['order'])
+  cfg = dict(orc.DEFAULT_CFG, transformer_decoder_join=False, use_wp_gru=True, pred_len=8)
+  inp, lab = synth.make_inputs(2, seed=11), synth.make_labels(2, seed=13)
+  lab['waypoint'] = synth.make_waypoint_labels(2, 8, seed=13)
+  out = orc.forward(sd, **inp, cfg=cfg, training=True)
+  for k, i in (('pred_wp', 0), ('pred_target_speed', 1), ('pred_checkpoint', 2)):
+    assert float((out[i] - torch.from_numpy(g[k])).norm() / torch.from_numpy(g[k]).norm()) < 2e-4, k
+  losses = orc.compute_loss(sd, out, lab, cfg)
+  assert len(losses) == 11
+  for k, v in losses.items():
+    assert abs(float(v) - float(g[k])) <= 2e-4 * max(1.0, abs(float(g[k]))), k
+  (sum(losses.values()) / len(losses)).backward()
+  n = 0
+  for key in g.files:
+    if key.startswith('grad_'):
+      name = key[5:]
+      got = sd[name].grad.flatten()[:512]
+      want = torch.from_numpy(g[key])
+      assert float((got - want).norm() / (want.norm() + 1e-30)) < 2e-3, name
+      n += 1
+  assert n >= 20
