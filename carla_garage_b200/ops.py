@@ -302,7 +302,7 @@ def linear(x, w, bias=None, act=ACT_NONE, res=None, out_f32=False, out=None, row
 
 
 def pillar_scatter(points, use_ground_plane=False, min_x=-32.0, max_x=32.0, min_y=-32.0, max_y=32.0,
-                   pixels_per_meter=4.0, hist_max=5, split_z=0.2, max_z=100.0):
+                   pixels_per_meter=4.0, hist_max=5, split_z=0.2, max_z=100.0, xform=None):
   """points (B, N, 3) f32 cuda -> (B, 1|2, 256, 256) f32 (data.py:873-906)."""
   _dev(points, F32)
   b, n, _ = points.shape
@@ -310,6 +310,13 @@ def pillar_scatter(points, use_ground_plane=False, min_x=-32.0, max_x=32.0, min_
   ny = int((max_y - min_y) * pixels_per_meter)
   counts = torch.empty((b, 2, ny, nx), dtype=torch.int32, device=points.device)
   out = torch.empty((b, 2 if use_ground_plane else 1, ny, nx), dtype=F32, device=points.device)
+  if xform is not None:  # (B, n_xforms, 4) float64 {tx, ty, tz, yaw}: CARLA_Data.align fused in (data.py:840-871)
+    xform = _dev(xform, torch.float64)
+    check(_lib.load().tfpp_pillar_scatter_aligned(points.data_ptr(), xform.data_ptr(), xform.shape[1], b, n, counts.data_ptr(),
+                                                  out.data_ptr(), int(use_ground_plane), min_x, max_x, min_y, max_y,
+                                                  pixels_per_meter, hist_max, float(split_z), max_z, _stream()),
+          'tfpp_pillar_scatter_aligned')
+    return out
   check(_lib.load().tfpp_pillar_scatter(points.data_ptr(), b, n, counts.data_ptr(), out.data_ptr(),
                                         int(use_ground_plane), min_x, max_x, min_y, max_y, pixels_per_meter, hist_max,
                                         split_z, max_z, _stream()), 'tfpp_pillar_scatter')

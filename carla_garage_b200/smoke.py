@@ -1,8 +1,10 @@
 """smoke(): one small invocation of the hot path on cuda:0, checked against the CPU oracle.
 
 1. LiDAR pillar scatter (K1) on one 60k-point cloud: bit-exact vs oracle.lidar_to_histogram_features.
-2. TransFuser++ forward, B=1, eval mode, golden state: planner outputs vs oracle.forward within the bf16 floor.
-3. One training step (forward + fused losses + backward + AdamW) at B=2: finite losses, parameters move.
+2. TransFuser++ forward, B=1, eval mode, golden state: planner outputs vs oracle.forward within the bf16 floor, and the
+   same forward in the fp32 parity mode within north_star's 1e-3.
+3. Agent-side kernels: CenterNet decode + rotated-IoU NMS vs oracle/nms.py; CenterNet target rasteriser vs oracle/targets.py.
+4. One training step (forward + fused losses + backward + AdamW) at B=2: finite losses, parameters move.
 """
 import os
 
@@ -43,6 +45,25 @@ def run():
   for i, name in ((1, 'pred_target_speed'), (2, 'pred_checkpoint'), (3, 'pred_semantic')):
     e, floor = rel(out[i], ref[i]), float(g['bf16floor_' + name])
     assert e < max(1e-2, 3 * floor), (name, e, floor)
+  with ops.precision('fp32'), torch.no_grad():   # same schedule, fp32 storage + contractions: north_star's 1e-3
+    out32 = net(**{k: v.cuda() for k, v in inp.items()})
+  for i in (1, 2, 3, 4, 5):
+    assert rel(out32[i], ref[i]) < 1e-3, ('fp32 mode', i, rel(out32[i], ref[i]))
+  for a, b in zip(out32[6][:5], ref[6][:5]):
+    assert rel(a, b) < 1e-3
+  # agent side: decode + NMS of the detections, label rasteriser
+  from oracle import nms as onms, targets as otargets  # checkers only
+  dec = net.head.get_bboxes(*out32[6])
+  kept, count = ops.nms_rotated(dec, 0.05, 0.2, to_vehicle=True)
+  want_boxes = onms.ensemble_boxes([dec[0].cpu().numpy()], 0.05, 0.2)
+  assert int(count[0]) == len(want_boxes), (int(count[0]), len(want_boxes))
+  if want_boxes:
+    assert np.allclose(kept[0, :len(want_boxes)].cpu().numpy(), np.stack(want_boxes), rtol=1e-4, atol=1e-4)
+  boxes = synth.make_gt_boxes(1, seed=9)[0]
+  lab_dev = ops.centernet_targets(torch.from_numpy(boxes)[None].cuda(), torch.tensor([len(boxes)], dtype=torch.int32).cuda())
+  want_t, want_avg = otargets.get_targets(boxes)
+  assert np.allclose(lab_dev['center_heatmap'][0].cpu().numpy(), want_t['center_heatmap_target'], atol=2e-6)
+  assert float(lab_dev['avg_factor'][0]) == float(want_avg)
   net.train()
   tr = Trainer(net)
   before = tr.st.flat[:1000].clone()

@@ -508,6 +508,15 @@ int tfpp_gru_cell_head_bwd(const float* joined, int joined_stride, const float* 
                            float* db_ts1, int batch, int steps, int hidden, int input_size, int learn_origin,
                            int n_speed, tfpp_stream_t stream);
 
+/* K1 with CARLA_Data.align / the agent's half-sweep merge fused in (data.py:840-871, sensor_agent.py:381-425,
+ * transfuser_utils.py:116-130): every point of sample b goes through n_xforms rigid transforms
+ * p' = R(yaw)^T (p - t), xform = (batch, n_xforms, 4) doubles {tx, ty, tz, yaw}, in float64 like numpy, before the
+ * float64 histogram of data.py:873-906 (split_z is the float64 lidar_split_height). */
+int tfpp_pillar_scatter_aligned(const float* points, const double* xform, int n_xforms, int batch, int n_points,
+                                unsigned int* counts, float* out, int use_ground_plane, float min_x, float max_x,
+                                float min_y, float max_y, float pixels_per_meter, int hist_max, double split_z,
+                                float max_z, tfpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

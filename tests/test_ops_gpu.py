@@ -548,3 +548,25 @@ def test_halo_umma_gconv3x3(ops, b, h, w, c):
   F.conv2d(xg, bf(wt).float(), padding=1, groups=c // 24).backward(dy.float().permute(0, 3, 1, 2))
   dx = ops.halo_gconv3x3(dy, ops.pack_halo_gconv_weight(wt, transpose=True))
   assert rel(dx.float().permute(0, 3, 1, 2), xg.grad) < 4e-3
+
+
+def test_pillar_scatter_with_fused_alignment_bit_exact(ops):
+  """tfpp_pillar_scatter_aligned == CARLA_Data.align + lidar_to_histogram_features of the unmodified reference
+  (tests/golden/make_align_golden.py): the two rigid transforms are applied per point in float64 inside K1."""
+  from carla_garage_b200 import dataio, synth
+  g = np.load(os.path.join(GOLDEN, 'align.npz'))
+  cases = g['cases']
+  pts = synth.make_point_clouds(len(cases), seed=21, n_points=20000)
+  xf = np.stack([dataio.align_transforms({'pos_global': (c[0], c[1]), 'theta': c[2]}, {'pos_global': (c[3], c[4]), 'theta': c[5]},
+                                         y_augmentation=c[6], yaw_augmentation=c[7]) for c in cases])
+  for gp in (0, 1):
+    out = ops.pillar_scatter(pts.cuda(), use_ground_plane=bool(gp), xform=torch.from_numpy(xf).cuda()).cpu().numpy()
+    for i in range(len(cases)):
+      want = g[f'hist{i}_gp{gp}'].astype(np.float32) / 5.0
+      diff = int((out[i] != want).sum())
+      assert diff == 0, (i, gp, diff)
+  # identity transform == the plain kernel except where f32 z == float32(0.2) would flip (none in this cloud)
+  ident = torch.zeros(1, 1, 4, dtype=torch.float64, device='cuda')
+  a = ops.pillar_scatter(pts[2:3].cuda(), use_ground_plane=True, xform=ident)
+  b = ops.pillar_scatter(pts[2:3].cuda(), use_ground_plane=True)
+  assert torch.equal(a, b)

@@ -218,3 +218,23 @@ def test_oracle_mlp_join_vs_reference_golden():
       assert float((got - want).norm() / (want.norm() + 1e-30)) < 2e-3, name
       n += 1
   assert n >= 20
+
+
+def test_align_transforms_reproduce_reference_align():
+  """carla_garage_b200.dataio.align_transforms (host side of tfpp_pillar_scatter_aligned) applied in float64 + the
+  oracle histogram == CARLA_Data.align + lidar_to_histogram_features of the unmodified reference
+  (tests/golden/make_align_golden.py)."""
+  from carla_garage_b200 import dataio, synth
+  from oracle import tfpp_oracle as orc
+  g = np.load(os.path.join(GOLDEN, 'align.npz'))
+  pts = synth.make_point_clouds(len(g['cases']), seed=21, n_points=20000).numpy()
+  for i, c in enumerate(g['cases']):
+    xf = dataio.align_transforms({'pos_global': (c[0], c[1]), 'theta': c[2]}, {'pos_global': (c[3], c[4]), 'theta': c[5]},
+                                 y_augmentation=c[6], yaw_augmentation=c[7])
+    p = pts[i].astype(np.float64)
+    for tx, ty, tz, yaw in xf:
+      rot = np.array([[np.cos(yaw), -np.sin(yaw), 0.0], [np.sin(yaw), np.cos(yaw), 0.0], [0.0, 0.0, 1.0]])
+      p = (rot.T @ (p - np.array([tx, ty, tz])).T).T
+    for gp in (0, 1):
+      h = orc.lidar_to_histogram_features(p, bool(gp))
+      assert np.array_equal(np.round(h * 5).astype(np.uint8), g[f'hist{i}_gp{gp}']), (i, gp)
