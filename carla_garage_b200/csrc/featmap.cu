@@ -5,6 +5,8 @@
 // Reference call sites are cited per entry point.
 #include "../../include/tfpp.h"
 #include "common.cuh"
+
+#include <cstdlib>
 #include "se_kernels.cuh"
 
 namespace {
@@ -184,6 +186,111 @@ __global__ void __launch_bounds__(256) scale_shift_act_kernel(const bf16* __rest
             const float2 f = unpack_bf16x2(rw[j]);
             v[2 * j] += f.x * rsc[2 * j] + rsh[2 * j];
             v[2 * j + 1] += f.y * rsc[2 * j + 1] + rsh[2 * j + 1];
+          }
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = pack_bf16x2(apply_act(v[2 * j], act), apply_act(v[2 * j + 1], act));
+          if (pool_sum != nullptr) {  // SE squeezes the tensor the next layer will actually read (bf16-rounded)
+            const float2 f = unpack_bf16x2(o[j]);
+            pl[2 * j] += f.x;
+            pl[2 * j + 1] += f.y;
+          }
+        }
+        *reinterpret_cast<uint4*>(y + off) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    if (pool_sum != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&spool[c0 + j], pl[j]);
+    }
+  }
+  if (pool_sum != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(pool_sum + static_cast<long long>(b) * C + i, spool[i]);
+  }
+}
+
+// Streaming variant (default): the per-channel constants live in shared memory instead of 32 registers per thread, so
+// 8 x 16-byte loads are in flight per thread without spills; the grid is one wave of equal-work CTAs (two per SM).
+__device__ __forceinline__ void lds8(const float* p, float* v) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a));
+}
+
+template <int U>
+__global__ void __launch_bounds__(256, 2) scale_shift_act_s_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res,
+                                                                   const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift,
+                                                                   const float* __restrict__ res_scale,
+                                                                   const float* __restrict__ res_shift, int act,
+                                                                   bf16* __restrict__ y, float* __restrict__ pool_sum,
+                                                                   int HW, int C, int pix_per_block) {
+  extern __shared__ __align__(16) float sm[];  // scale | shift | res_scale | res_shift | pool, C floats each
+  float* csc = sm;
+  float* csh = sm + C;
+  float* crs = sm + 2 * C;
+  float* crh = sm + 3 * C;
+  float* spool = sm + 4 * C;
+  const int b = blockIdx.y;
+  const int c8n = C / 8;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    csc[i] = scale ? __ldg(scale + i) : 1.f;
+    csh[i] = scale ? __ldg(shift + i) : 0.f;
+    if (res != nullptr) {
+      crs[i] = res_scale ? __ldg(res_scale + i) : 1.f;
+      crh[i] = res_scale ? __ldg(res_shift + i) : 0.f;
+    }
+    if (pool_sum != nullptr) spool[i] = 0.f;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const long long base = static_cast<long long>(b) * HW * C;
+  const int rows_pp = blockDim.x / c8n;
+  const int cg = threadIdx.x % c8n, prow = threadIdx.x / c8n;
+  if (prow < rows_pp) {
+    const int c0 = cg * 8;
+    float pl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pl[j] = 0.f;
+    for (int pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+      uint4 u[U], r[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int px = pix + k * rows_pp;
+        if (px < p1) {
+          const long long off = base + static_cast<long long>(px) * C + c0;
+          u[k] = ld_stream16(x + off);
+          if (res != nullptr) r[k] = ld_stream16(res + off);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int px = pix + k * rows_pp;
+        if (px >= p1) break;
+        const long long off = base + static_cast<long long>(px) * C + c0;
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        float v[8], t[8], h[8];
+        lds8(csc + c0, t);
+        lds8(csh + c0, h);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(w[j]);
+          v[2 * j] = f.x * t[2 * j] + h[2 * j];
+          v[2 * j + 1] = f.y * t[2 * j + 1] + h[2 * j + 1];
+        }
+        if (res != nullptr) {
+          const uint32_t rw[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
+          lds8(crs + c0, t);
+          lds8(crh + c0, h);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(rw[j]);
+            v[2 * j] += f.x * t[2 * j] + h[2 * j];
+            v[2 * j + 1] += f.y * t[2 * j + 1] + h[2 * j + 1];
           }
         }
         uint32_t o[4];
@@ -472,6 +579,25 @@ extern "C" int tfpp_scale_shift_act(const void* x, const void* res, const float*
   int pix_per_block = ceil_div(hw, chunks);
   if (pix_per_block < 8) pix_per_block = 8;
   chunks = ceil_div(hw, pix_per_block);
+  static const bool stream_on = [] { const char* e = getenv("TFPP_BN_STREAM"); return e == nullptr || e[0] != '0'; }();
+  if (stream_on) {
+    constexpr int U = 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(scale_shift_act_s_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 2048 * 4);
+      attr_set = true;
+    }
+    chunks = TFPP_NUM_SMS * 2 / batch;  // one wave of two resident CTAs per SM
+    if (chunks < 1) chunks = 1;
+    pix_per_block = ceil_div(hw, chunks);
+    if (pix_per_block < 8) pix_per_block = 8;
+    chunks = ceil_div(hw, pix_per_block);
+    scale_shift_act_s_kernel<U><<<dim3(chunks, batch), 256, sizeof(float) * 5 * channels, stream>>>(
+        static_cast<const bf16*>(x), static_cast<const bf16*>(res), scale, shift, res_scale, res_shift, act,
+        static_cast<bf16*>(y), pool_sum, hw, channels, pix_per_block);
+    TFPP_CHECK_LAUNCH();
+    return TFPP_OK;
+  }
   dim3 grid(chunks, batch);
   const size_t smem = pool_sum ? sizeof(float) * channels : 0;
   scale_shift_act_kernel<<<grid, 256, smem, stream>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(res), scale,

@@ -190,6 +190,225 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
   }
 }
 
+// ---- streaming variants (default): per-channel constants live in shared memory instead of 48-64 registers per thread,
+// so U = 4 pixel rows (8 x 16-byte loads in flight per thread) fit without spills at two resident CTAs per SM, and the
+// grid is ONE wave of equal-work CTAs (the constant prologue and the statistics flush are paid once per SM slot).  Same math as the kernels above; the reduce pass accumulates
+// sum dz*(raw - mean) and multiplies by invstd once per CTA at the flush.
+__device__ __forceinline__ void lds8(const float* p, float* v) {
+  // volatile: keeps the compiler from hoisting the constants back into registers
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a));
+}
+
+template <int U, int MASK, bool GATE>  // MASK: 0 none, 1 ReLU mask recomputed from raw, 2 ReLU mask from the saved output
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_s_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                                 const bf16* __restrict__ raw,
+                                                                 const float* __restrict__ mean,
+                                                                 const float* __restrict__ invstd,
+                                                                 const float* __restrict__ gate,
+                                                                 const float* __restrict__ pool_grad,
+                                                                 const float* __restrict__ fscale,
+                                                                 const float* __restrict__ fshift, int act,
+                                                                 float* __restrict__ s1, float* __restrict__ s2, int HW,
+                                                                 int C, int pix_per_block) {
+  extern __shared__ __align__(16) float sm[];  // a1 | a2 | mean | fscale | fshift | gate | pool_grad, C floats each
+  float* a1 = sm;
+  float* a2 = sm + C;
+  float* cmu = sm + 2 * C;
+  float* cfs = sm + 3 * C;
+  float* cfh = sm + 4 * C;
+  float* cgt = sm + 5 * C;
+  float* cpg = sm + 6 * C;
+  const int b = blockIdx.y, c8n = C / 8;
+  constexpr bool relu = MASK != 0;
+  constexpr bool mask_from_raw = MASK == 1;
+  constexpr bool has_gate = GATE;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    a1[i] = 0.f;
+    a2[i] = 0.f;
+    cmu[i] = __ldg(mean + i);
+    if (mask_from_raw) {
+      cfs[i] = __ldg(fscale + i);
+      cfh[i] = __ldg(fshift + i);
+    }
+    if (has_gate) {
+      cgt[i] = gate ? __ldg(gate + static_cast<long long>(b) * C + i) : 1.f;
+      cpg[i] = pool_grad ? __ldg(pool_grad + static_cast<long long>(b) * C + i) : 0.f;
+    }
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  const long long base = static_cast<long long>(b) * HW * C;
+  const int rows_pp = blockDim.x / c8n;
+  const int cg = threadIdx.x % c8n, prow = threadIdx.x / c8n;
+  if (prow < rows_pp) {
+    const int c0 = cg * 8;
+    float l1[8], l2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l1[j] = l2[j] = 0.f;
+    for (int pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+      uint4 ud[U], ur[U], uy[MASK == 2 ? U : 1];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int px = pix + k * rows_pp;
+        if (px < p1) {
+          const long long off = base + static_cast<long long>(px) * C + c0;
+          ud[k] = ld_stream16(dy + off);
+          ur[k] = ld_stream16(raw + off);
+          if (MASK == 2) uy[MASK == 2 ? k : 0] = ld_stream16(y + off);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (pix + k * rows_pp >= p1) break;
+        float d[8], r[8], t[8];
+        unpack8(ud[k], d);
+        unpack8(ur[k], r);
+        if (has_gate) {
+          lds8(cgt + c0, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] *= t[j];
+          lds8(cpg + c0, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] += t[j];
+        }
+        if (mask_from_raw) {
+          float h[8];
+          lds8(cfs + c0, t);
+          lds8(cfh + c0, h);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (!(fmaf(r[j], t[j], h[j]) > 0.f)) d[j] = 0.f;
+        } else if (relu) {
+          unpack8(uy[MASK == 2 ? k : 0], t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (!(t[j] > 0.f)) d[j] = 0.f;
+        }
+        lds8(cmu + c0, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          l1[j] += d[j];
+          l2[j] = fmaf(d[j], r[j] - t[j], l2[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&a1[c0 + j], l1[j]);
+      atomicAdd(&a2[c0 + j], l2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(s1 + i, a1[i]);
+    atomicAdd(s2 + i, a2[i] * __ldg(invstd + i));
+  }
+}
+
+template <int U, int MASK, bool GATE>
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_s_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                                const bf16* __restrict__ raw,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ s1, const float* __restrict__ s2,
+                                                                const float* __restrict__ gate,
+                                                                const float* __restrict__ pool_grad,
+                                                                const float* __restrict__ fscale,
+                                                                const float* __restrict__ fshift, int act, float inv_n,
+                                                                bf16* __restrict__ draw, bf16* __restrict__ dz_out, int HW,
+                                                                int C, int pix_per_block) {
+  //   draw = k0 * dz + k1 * raw + k2,  k0 = gamma*invstd, k1 = -k0*invstd*s2/N, k2 = -k0*s1/N - k1*mean
+  extern __shared__ __align__(16) float sm[];  // k0 | k1 | k2 | fscale | fshift | gate | pool_grad
+  float* ck0 = sm;
+  float* ck1 = sm + C;
+  float* ck2 = sm + 2 * C;
+  float* cfs = sm + 3 * C;
+  float* cfh = sm + 4 * C;
+  float* cgt = sm + 5 * C;
+  float* cpg = sm + 6 * C;
+  const int b = blockIdx.y, c8n = C / 8;
+  constexpr bool relu = MASK != 0;
+  constexpr bool mask_from_raw = MASK == 1;
+  constexpr bool has_gate = GATE;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float is = __ldg(invstd + i);
+    const float k0 = __ldg(gamma + i) * is;
+    const float k1 = -k0 * is * __ldg(s2 + i) * inv_n;
+    ck0[i] = k0;
+    ck1[i] = k1;
+    ck2[i] = -k0 * __ldg(s1 + i) * inv_n - k1 * __ldg(mean + i);
+    if (mask_from_raw) {
+      cfs[i] = __ldg(fscale + i);
+      cfh[i] = __ldg(fshift + i);
+    }
+    if (has_gate) {
+      cgt[i] = gate ? __ldg(gate + static_cast<long long>(b) * C + i) : 1.f;
+      cpg[i] = pool_grad ? __ldg(pool_grad + static_cast<long long>(b) * C + i) : 0.f;
+    }
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  const long long base = static_cast<long long>(b) * HW * C;
+  const int rows_pp = blockDim.x / c8n;
+  const int cg = threadIdx.x % c8n, prow = threadIdx.x / c8n;
+  if (prow >= rows_pp) return;
+  const int c0 = cg * 8;
+  for (int pix = p0 + prow; pix < p1; pix += rows_pp * U) {
+    uint4 ud[U], ur[U], uy[MASK == 2 ? U : 1];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int px = pix + k * rows_pp;
+      if (px < p1) {
+        const long long off = base + static_cast<long long>(px) * C + c0;
+        ud[k] = ld_stream16(dy + off);
+        ur[k] = ld_stream16(raw + off);
+        if (MASK == 2) uy[MASK == 2 ? k : 0] = ld_stream16(y + off);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int px = pix + k * rows_pp;
+      if (px >= p1) break;
+      const long long off = base + static_cast<long long>(px) * C + c0;
+      float d[8], r[8], t[8], h[8];
+      unpack8(ud[k], d);
+      unpack8(ur[k], r);
+      if (has_gate) {
+        lds8(cgt + c0, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] *= t[j];
+        lds8(cpg + c0, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += t[j];
+      }
+      if (mask_from_raw) {
+        lds8(cfs + c0, t);
+        lds8(cfh + c0, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(fmaf(r[j], t[j], h[j]) > 0.f)) d[j] = 0.f;
+      } else if (relu) {
+        unpack8(uy[MASK == 2 ? k : 0], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(t[j] > 0.f)) d[j] = 0.f;
+      }
+      if (dz_out) store8(dz_out + off, d);
+      lds8(ck1 + c0, t);
+      lds8(ck2 + c0, h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaf(t[j], r[j], h[j]);
+      lds8(ck0 + c0, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaf(t[j], d[j], r[j]);
+      store8(draw + off, r);
+    }
+  }
+}
+
 // EXPERIMENTAL (TFPP_BN_BWD_FUSED=1, never run on a GPU yet): both passes in ONE cooperative launch for activations
 // that fit the 126 MB L2 — reduce, grid barrier, apply.  The second pass then reads from L2 instead of HBM and half of
 // the 272 BatchNorm-backward launches of a step disappear (they are latency-bound on the small stage-3/4 maps).
@@ -815,13 +1034,46 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 
 #define STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
 
-static void chunking(int batch, int hw, int* chunks, int* pix_per_block) {
-  int ch = TFPP_NUM_SMS * 6 / batch;  // two full waves of three resident CTAs per SM
+static void chunking(int batch, int hw, int* chunks, int* pix_per_block, int ctas_per_sm = 6) {
+  int ch = TFPP_NUM_SMS * ctas_per_sm / batch;  // default: two full waves of three resident CTAs per SM
   if (ch < 1) ch = 1;
   int ppb = ceil_div(hw, ch);
   if (ppb < 8) ppb = 8;
   *chunks = ceil_div(hw, ppb);
   *pix_per_block = ppb;
+}
+
+template <int MASK, bool GATE>
+static int launch_bn_bwd_s2(dim3 grid, size_t smem, cudaStream_t stream, const bf16* dy, const bf16* y, const bf16* raw,
+                            const float* mean, const float* invstd, const float* gamma, const float* gate,
+                            const float* pool_grad, const float* fs, const float* fh, int act, float* s1, float* s2,
+                            float inv_n, bf16* draw, bf16* dz_out, int hw, int channels, int ppb) {
+  constexpr int U = 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(bn_bwd_reduce_s_kernel<U, MASK, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4);
+    cudaFuncSetAttribute(bn_bwd_apply_s_kernel<U, MASK, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 2048 * 4);
+    attr_set = true;
+  }
+  bn_bwd_reduce_s_kernel<U, MASK, GATE><<<grid, 256, smem, stream>>>(dy, y, raw, mean, invstd, gate, pool_grad, fs, fh, act,
+                                                                     s1, s2, hw, channels, ppb);
+  TFPP_CHECK_LAUNCH();
+  bn_bwd_apply_s_kernel<U, MASK, GATE><<<grid, 256, smem, stream>>>(dy, y, raw, mean, invstd, gamma, s1, s2, gate, pool_grad,
+                                                                    fs, fh, act, inv_n, draw, dz_out, hw, channels, ppb);
+  TFPP_CHECK_LAUNCH();
+  return TFPP_OK;
+}
+
+template <typename... A>
+static int launch_bn_bwd_s(int mask, bool gated, A... a) {
+  switch (mask * 2 + (gated ? 1 : 0)) {
+    case 0: return launch_bn_bwd_s2<0, false>(a...);
+    case 1: return launch_bn_bwd_s2<0, true>(a...);
+    case 2: return launch_bn_bwd_s2<1, false>(a...);
+    case 3: return launch_bn_bwd_s2<1, true>(a...);
+    case 4: return launch_bn_bwd_s2<2, false>(a...);
+    default: return launch_bn_bwd_s2<2, true>(a...);
+  }
 }
 
 extern "C" int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const float* mean, const float* invstd,
@@ -864,6 +1116,17 @@ extern "C" int tfpp_bn_bwd(const void* dy, const void* y, const void* raw, const
       }
       return TFPP_OK;
     }
+  }
+  static const bool stream_on = [] { const char* e = getenv("TFPP_BN_STREAM"); return e == nullptr || e[0] != '0'; }();
+  if (stream_on) {
+    chunking(batch, hw, &chunks, &ppb, 2);  // one wave, two resident CTAs per SM
+    const int mask = act != ACT_RELU ? 0 : (y == nullptr ? 1 : 2);
+    const bool gated = gate != nullptr || pool_grad != nullptr;
+    return launch_bn_bwd_s(mask, gated, dim3(chunks, batch), sizeof(float) * 7 * channels, stream,
+                           static_cast<const bf16*>(dy), static_cast<const bf16*>(y), static_cast<const bf16*>(raw), mean,
+                           invstd, gamma, gate, pool_grad, fwd_scale, fwd_shift, act, s1, s2,
+                           1.f / (static_cast<float>(batch) * hw), static_cast<bf16*>(draw), static_cast<bf16*>(dz_out), hw,
+                           channels, ppb);
   }
   bn_bwd_reduce_kernel<<<grid, 256, sizeof(float) * 2 * channels, stream>>>(
       static_cast<const bf16*>(dy), static_cast<const bf16*>(y), static_cast<const bf16*>(raw), mean, invstd, gate,

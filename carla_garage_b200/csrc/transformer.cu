@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ decoder attention
-// nn.MultiheadAttention core inside nn.TransformerDecoderLayer (model.py:137-143): Tq <= 16 queries, Tk <= 128 keys,
+// nn.MultiheadAttention core inside nn.TransformerDecoderLayer (model.py:137-143): Tq <= 16 queries, Tk <= 512 keys,
 // head_dim 32.  One CTA per (batch, head), one warp per query row.  q/k/v are row-strided f32 or bf16 views.
 __global__ void __launch_bounds__(256) small_mha_kernel(const bf16* __restrict__ q, long long q_sb, long long q_sr,
                                                         const bf16* __restrict__ k, long long k_sb, long long k_sr,
@@ -270,8 +270,13 @@ extern "C" int tfpp_small_mha_dropout(const void* q, long long q_sb, long long q
                                       const unsigned long long* drop_rng, float drop_p, unsigned drop_site,
                                       tfpp_stream_t stream_) {
   STREAM;
-  TFPP_CHECK_ARG(tk <= 256 && head_dim <= 64, "small_mha: tk <= 256, head_dim <= 64");
+  TFPP_CHECK_ARG(tk <= 512 && head_dim <= 64, "small_mha: tk <= 512, head_dim <= 64");
   const size_t smem = sizeof(float) * (2 * tk * (head_dim + 1) + 8 * tk);
+  static bool attr_set = false;
+  if (!attr_set) {  // 257 memory tokens (bev_encoder backbone) need 76 KB
+    cudaFuncSetAttribute(small_mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
   dim3 grid(batch, heads);
   small_mha_kernel<<<grid, 256, smem, stream>>>(static_cast<const bf16*>(q), q_sb, q_sr, static_cast<const bf16*>(k),
                                                 k_sb, k_sr, static_cast<const bf16*>(v), v_sb, v_sr,

@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ decoder attention bwd
-// One CTA per (batch, head); everything in fp32 shared memory (Tq <= 16, Tk <= 128, hd <= 64).
+// One CTA per (batch, head); everything in fp32 shared memory (Tq <= 16, Tk <= 32 * NPL, hd <= 64).  NPL = keys per lane:
+// 4 for the 65-token memory of the TransFuser backbone, 16 for the 257-token memory of the bev_encoder backbone.
+template <int NPL>
 __global__ void __launch_bounds__(256) small_mha_bwd_kernel(const bf16* __restrict__ q, long long q_sb, long long q_sr,
                                                             const bf16* __restrict__ k, long long k_sb, long long k_sr,
                                                             const bf16* __restrict__ v, long long v_sb, long long v_sr,
@@ -108,11 +110,16 @@ __global__ void __launch_bounds__(256) small_mha_bwd_kernel(const bf16* __restri
     __syncwarp();
     // dP = dO V^T ; rowsum(dP * P)
     float rsum = 0.f;
-    float dpl[4];  // Tk <= 128 -> up to 4 per lane
-    float dml[4] = {1.f, 1.f, 1.f, 1.f};
+    float dpl[NPL];  // Tk <= 32 * NPL -> up to NPL per lane
+    float dml[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) dml[i] = 1.f;
     int n = 0;
     const unsigned long long dbase = ((static_cast<unsigned long long>(b) * gridDim.y + h) * Tq + r) * Tk;
-    for (int c = lane; c < Tk; c += 32, ++n) {
+#pragma unroll
+    for (n = 0; n < NPL; ++n) {
+      const int c = lane + 32 * n;
+      if (c >= Tk) break;
       float a = 0.f;
       for (int d = 0; d < hd; ++d) a = fmaf(dos[r * P1 + d], vs[c * P1 + d], a);
       const float p = pr[c] * inv;
@@ -128,7 +135,10 @@ __global__ void __launch_bounds__(256) small_mha_bwd_kernel(const bf16* __restri
     n = 0;
     __syncwarp();
     // keep P in a register copy for dV: store dS in ps after use -> need P too: pack dS into a second pass
-    for (int c = lane; c < Tk; c += 32, ++n) {
+#pragma unroll
+    for (n = 0; n < NPL; ++n) {
+      const int c = lane + 32 * n;
+      if (c >= Tk) break;
       const float p = pr[c];
       dpl[n] = p * (dpl[n] - rsum) * scale;  // dS
       if (drop.on) pr[c] = p * dml[n];       // the dV pass below multiplies the DROPPED probabilities
@@ -138,8 +148,9 @@ __global__ void __launch_bounds__(256) small_mha_bwd_kernel(const bf16* __restri
     // dQ[r] = dS[r,:] K
     // stash dS into shared by swapping with P: we still need P for dV, so use two-step: write dS to a side buffer
     float* dsr = ps + Tq * Tk + r * Tk;  // second Tq x Tk block
-    n = 0;
-    for (int c = lane; c < Tk; c += 32, ++n) dsr[c] = dpl[n];
+#pragma unroll
+    for (n = 0; n < NPL; ++n)
+      if (lane + 32 * n < Tk) dsr[lane + 32 * n] = dpl[n];
     __syncwarp();
     for (int d = lane; d < hd; d += 32) {
       float a = 0.f;
@@ -429,10 +440,18 @@ extern "C" int tfpp_small_mha_bwd_dropout(const void* q, long long q_sb, long lo
                                           int tq, int tk, int head_dim, const unsigned long long* drop_rng, float drop_p,
                                           unsigned drop_site, tfpp_stream_t stream_) {
   STREAM;
-  TFPP_CHECK_ARG(tk <= 128 && tq <= 16 && head_dim <= 64, "small_mha_bwd: tq <= 16, tk <= 128, head_dim <= 64");
+  TFPP_CHECK_ARG(tk <= 512 && tq <= 16 && head_dim <= 64, "small_mha_bwd: tq <= 16, tk <= 512, head_dim <= 64");
   const size_t smem = sizeof(float) * ((2 * tq + 2 * tk) * (head_dim + 1) + 2 * tq * tk);
+  TFPP_CHECK_ARG(smem <= 200 * 1024, "small_mha_bwd: shared-memory budget exceeded");
   dim3 grid(batch, heads);
-  small_mha_bwd_kernel<<<grid, 256, smem, stream>>>(
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(small_mha_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(small_mha_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  auto kern = tk <= 128 ? small_mha_bwd_kernel<4> : small_mha_bwd_kernel<16>;
+  kern<<<grid, 256, smem, stream>>>(
       static_cast<const bf16*>(q), q_sb, q_sr, static_cast<const bf16*>(k), k_sb, k_sr, static_cast<const bf16*>(v), v_sb,
       v_sr, static_cast<const bf16*>(dout), o_sb, o_sr, static_cast<bf16*>(dq), dq_sb, dq_sr, static_cast<bf16*>(dk),
       dk_sb, dk_sr, static_cast<bf16*>(dv), dv_sb, dv_sr, accumulate_kv, tq, tk, head_dim,

@@ -56,9 +56,33 @@ elif which == 'targets':
   for i, c_ in enumerate(cs): bx[i, :len(c_)] = torch.from_numpy(c_); cnt[i] = len(c_)
   bx, cnt = bx.cuda(), cnt.cuda()
   f = lambda: ops.centernet_targets(bx, cnt)
+elif which.startswith('bnbwd_') or which.startswith('ssa_'):
+  # BatchNorm backward / forward apply at the step's shapes: i1/i2/i3 = image stages, l3 = LiDAR stage 3, g = SE-gated
+  shp = {'i1': (32, 64, 256, 72), 'i2': (32, 32, 128, 216), 'i3': (32, 16, 64, 576), 'l3': (32, 16, 16, 576),
+         'i0': (32, 128, 512, 72)}[which.split('_')[1][:2]]
+  gated = which.endswith('g')
+  c = shp[3]
+  raw = torch.randn(shp, device='cuda').to(torch.bfloat16); dy = torch.randn(shp, device='cuda').to(torch.bfloat16)
+  mean, invstd, gamma = torch.randn(c, device='cuda') * 0.1, torch.rand(c, device='cuda') + 0.5, torch.rand(c, device='cuda') + 0.5
+  fs, fh = gamma * invstd, -mean * gamma * invstd
+  gate = torch.rand(shp[0], c, device='cuda') if gated else None
+  pg = torch.randn(shp[0], c, device='cuda') * 1e-3 if gated else None
+  dg, db = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+  out = torch.empty_like(raw)
+  if which.startswith('bnbwd_'):
+    f = lambda: ops.bn_bwd(dy, None, raw, mean, invstd, gamma, ops.ACT_RELU, dg, db, gate=gate, pool_grad=pg, fwd_affine=(fs, fh))
+  else:
+    pool = torch.zeros(shp[0], c, device='cuda') if gated else None
+    f = lambda: ops.scale_shift_act(raw, fs, fh, ops.ACT_RELU, out=out, pool_sum=pool)
 for _ in range(4): f()
 torch.cuda.synchronize()
-if len(sys.argv) > 2 and sys.argv[2] == 'time':  # CUDA-event timing, L2 flushed between launches
+if len(sys.argv) > 2 and sys.argv[2] == 'warm':  # back-to-back launches, operands as warm in L2 as they fit
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(20): f()
+  e1.record(); torch.cuda.synchronize()
+  print(f'{which}: warm {e0.elapsed_time(e1) * 1e3 / 20:.1f} us per call')
+elif len(sys.argv) > 2 and sys.argv[2] == 'time':  # CUDA-event timing, L2 flushed between launches
   flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
   ts = []
   for _ in range(10):
