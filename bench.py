@@ -174,8 +174,12 @@ def main():
   warmup = max(args.warmup, 3)
   b = args.batch
   torch.manual_seed(0)
-  net = LidarCenterNet(GlobalConfig())
-  net.load_state_dict(synth.golden_state(os.path.join(ROOT, 'tests', 'golden')), strict=True)
+  cfg = GlobalConfig()
+  backbone = os.environ.get('TFPP_BENCH_BACKBONE', cfg.backbone)  # 'bev_encoder': SURVEY.md §8 f3 (not the headline config)
+  cfg.backbone = backbone
+  net = LidarCenterNet(cfg)
+  golden = os.path.join(ROOT, 'tests', 'golden')
+  net.load_state_dict(synth.bev_state(golden) if backbone == 'bev_encoder' else synth.golden_state(golden), strict=True)
   net = net.cuda().train()
   tr = Trainer(net, process_group=pg)
   host_in = {k: v.pin_memory() for k, v in synth.make_inputs(b, seed=1234 + rank).items()}
@@ -339,7 +343,7 @@ def main():
   inference = {'fwd_ms_per_frame': fwd_ms, 'batch': 1, 'mode': 'eval, CUDA-graph replay, inputs resident'}
   # ---- BASELINE.json config 5: sensor_agent.py inference, 3-member ensemble, batch 64, forward only (one CUDA graph:
   # 3 forwards + CenterNet decode + threshold / vehicle-frame conversion / rotated-IoU NMS over the union + averaging)
-  if os.environ.get('TFPP_BENCH_ENSEMBLE', '1') == '1':
+  if os.environ.get('TFPP_BENCH_ENSEMBLE', '1') == '1' and backbone == 'transFuser':
     from carla_garage_b200.inference import EnsembleForward
     del gf
     members = [net]
@@ -387,7 +391,7 @@ def main():
       'metric': 'train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
       'warmup': warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-      'config': {'workload': WORKLOAD if b == PER_GPU_BATCH else WORKLOAD.replace('batch=32', f'batch={b}') + (' (BASELINE.json config 3: DDP imitation training, batch=12/GPU)' if b == 12 else ''),
+      'config': {'workload': (WORKLOAD if backbone == 'transFuser' else WORKLOAD.replace('TransFuser++', f'LidarCenterNet(backbone={backbone})')) if b == PER_GPU_BATCH else WORKLOAD.replace('batch=32', f'batch={b}') + (' (BASELINE.json config 3: DDP imitation training, batch=12/GPU)' if b == 12 else ''),
                  'global_batch': world * b, 'per_gpu_batch': b, 'parallelism': f'dp{world}',
                  'l2': 'per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed',
                  'inputs': 'rgb (B,3,256,1024) f32 + 60k-point LiDAR cloud -> (B,1,256,256) BEV (reference default use_ground_plane=0)',

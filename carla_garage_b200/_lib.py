@@ -59,6 +59,11 @@ _PROTOS = {
     'tfpp_abi_version': [],
     'tfpp_pillar_scatter': [P, I, I, P, P, I, F, F, F, F, F, I, F, F, P],
     'tfpp_pillar_scatter_aligned': [P, P, I, I, I, P, P, I, F, F, F, F, F, I, ctypes.c_double, F, P],
+    'tfpp_instnorm_stats': [P, I, L, I, I, I, P, P, P],
+    'tfpp_instnorm_apply': [P, I, L, P, P, F, I, P, L, P, P, I, I, I, P],
+    'tfpp_instnorm_bwd': [P, L, P, I, P, P, I, P, P, P, I, I, I, P],
+    'tfpp_bev_lift': [P, I, P, P, P, P, P, I, I, I, I, I, I, P],
+    'tfpp_bev_lift_bwd': [P, I, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     'tfpp_conv_gemm': [ctypes.POINTER(ConvGemmArgs), P],
     'tfpp_conv_wgrad': [ctypes.POINTER(WgradArgs), P],
     'tfpp_smallc_conv3x3': [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
@@ -223,7 +228,7 @@ def profile_calls(fn):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
-_KERNELS_PER_CALL = {'tfpp_peer_adamw_step': 4, 'tfpp_adamw_amsgrad': 2, 'tfpp_pillar_scatter': 2, 'tfpp_pillar_scatter_aligned': 2, 'tfpp_bn_bwd': 2, 'tfpp_se_bwd': 4, 'tfpp_se_gate': 2, 'tfpp_gconv3x3_wgrad': 2, 'tfpp_fusion_attn_bwd': 2}
+_KERNELS_PER_CALL = {'tfpp_peer_adamw_step': 4, 'tfpp_adamw_amsgrad': 2, 'tfpp_pillar_scatter': 2, 'tfpp_pillar_scatter_aligned': 2, 'tfpp_bn_bwd': 2, 'tfpp_instnorm_bwd': 2, 'tfpp_bev_lift_bwd': 2, 'tfpp_se_bwd': 4, 'tfpp_se_gate': 2, 'tfpp_gconv3x3_wgrad': 2, 'tfpp_fusion_attn_bwd': 2}
 _LAUNCHES = [0]
 
 

@@ -99,6 +99,8 @@ class GlobalConfig:
     self.num_transformer_decoder_layers = 6
     self.num_decoder_heads = 8
     self.bev_grid_height_downsample_factor = 1.0
+    self.image_u_net_output_features = 512  # config.py:463-464 (bev_encoder backbone)
+    self.bev_latent_dim = 32
     self.wp_dilation = 1
     self.extra_sensor_channels = 128
     self.use_tp = True

@@ -581,10 +581,10 @@ extern "C" int tfpp_scale_shift_act(const void* x, const void* res, const float*
   chunks = ceil_div(hw, pix_per_block);
   static const bool stream_on = [] { const char* e = getenv("TFPP_BN_STREAM"); return e == nullptr || e[0] != '0'; }();
   if (stream_on) {
-    constexpr int U = 4;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(scale_shift_act_s_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 2048 * 4);
+      cudaFuncSetAttribute(scale_shift_act_s_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 2048 * 4);
+      cudaFuncSetAttribute(scale_shift_act_s_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 2048 * 4);
       attr_set = true;
     }
     chunks = TFPP_NUM_SMS * 2 / batch;  // one wave of two resident CTAs per SM
@@ -592,7 +592,9 @@ extern "C" int tfpp_scale_shift_act(const void* x, const void* res, const float*
     pix_per_block = ceil_div(hw, chunks);
     if (pix_per_block < 8) pix_per_block = 8;
     chunks = ceil_div(hw, pix_per_block);
-    scale_shift_act_s_kernel<U><<<dim3(chunks, batch), 256, sizeof(float) * 5 * channels, stream>>>(
+    // one input tensor: 8 pixel rows per trip keep the same 128 bytes per thread in flight as 4 rows of two tensors
+    auto kern = res == nullptr ? scale_shift_act_s_kernel<8> : scale_shift_act_s_kernel<4>;
+    kern<<<dim3(chunks, batch), 256, sizeof(float) * 5 * channels, stream>>>(
         static_cast<const bf16*>(x), static_cast<const bf16*>(res), scale, shift, res_scale, res_shift, act,
         static_cast<bf16*>(y), pool_sum, hw, channels, pix_per_block);
     TFPP_CHECK_LAUNCH();

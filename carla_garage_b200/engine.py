@@ -22,7 +22,7 @@ PARAM_EPOCH = [0]  # bumped by the fused optimizer (it updates parameter storage
 
 # kinds whose pack is a pure gather (+ zero padding) of parameter elements: eligible for the one-kernel PackPlan
 _GATHER_KINDS = frozenset(('conv', 'gconv', 'gconv_halo', 'gconv_halo_t', 'gconv_halo_umma', 'gconv_halo_umma_t', 'conv_halo_umma', 'conv_halo_umma_t', 'linear', 'conv_t', 'conv_rows_pad', 'conv_dgrad_smallc', 'gconv_t', 'linear_t',
-                           'rows_t', 'cols', 'cols_t', 'cat_linear_t', 'cat_conv_t', 'blockdiag_1x1_t', 'rows', 'rows_f32', 'cat_linear',
+                           'rows_t', 'cols', 'cols_t', 'conv_cin', 'conv_cin_t', 'conv_cin_pad', 'conv_cin_pad_t', 'cat_linear_t', 'cat_conv_t', 'blockdiag_1x1_t', 'rows', 'rows_f32', 'cat_linear',
                            'cat_rows', 'cat_rows_f32', 'cat_f32', 'cat_conv', 'blockdiag_1x1', 'repeat_rows'))
 
 
@@ -69,6 +69,18 @@ def _build_pack(kind, params, extra, dtb=BF16, dtf=F32):
     w = params[0].detach()[:, extra[0]:extra[1]].t().to(dtb).contiguous()
     pad = (-w.shape[1]) % 8
     return torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
+  if kind == 'conv_cin':  # input-channel slice [k0, k1) of a conv weight: (Cout, taps, k1 - k0) — one piece of a conv over a concatenation
+    return ops.pack_conv_weight(params[0].detach()[:, extra[0]:extra[1]], dt=dtb)
+  if kind == 'conv_cin_t':  # its input-gradient operand (k1 - k0, taps, Cout padded to 8)
+    w = ops.pack_conv_weight_t(params[0].detach()[:, extra[0]:extra[1]], dt=dtb)
+    pad = (-w.shape[2]) % 8
+    return torch.nn.functional.pad(w, (0, pad)).contiguous() if pad else w
+  if kind == 'conv_cin_pad':  # (Cout, Cin, kh, kw) -> (Cout, taps, Cin zero-padded to extra[0])
+    w = ops.pack_conv_weight(params[0], dt=dtb)
+    return torch.nn.functional.pad(w, (0, extra[0] - w.shape[2])).contiguous()
+  if kind == 'conv_cin_pad_t':  # its input-gradient operand (Cin padded to extra[0], taps, Cout)
+    w = ops.pack_conv_weight_t(params[0], dt=dtb)
+    return torch.nn.functional.pad(w, (0, 0, 0, 0, 0, extra[0] - w.shape[0])).contiguous()
   if kind == 'rows_t':
     return params[0].detach()[extra[0]:extra[1]].t().to(dtb).contiguous()
   if kind == 'cat_linear_t':
@@ -559,6 +571,8 @@ class Engine:
     """TransfuserBackbone.forward (transfuser.py:139-205). image (B,3,H,W) f32 0..255, lidar (B,C,256,256) f32.
     Returns NHWC bf16 (bev features (B,64,64,64), fused LiDAR features (B,8,8,1512), image grid (B,8,32,1512))."""
     bb, cfg = self.bb, self.cfg
+    if cfg.backbone == 'bev_encoder':
+      return self.bev_backbone_forward(image, lidar, training)
     if not (image.is_cuda and lidar.is_cuda):
       raise RuntimeError('carla_garage_b200 runs on CUDA tensors only (no CPU fallback)')
     if training:
@@ -642,6 +656,122 @@ class Engine:
       return feats, fused, grid
     self._tap('fused_features', lid)
     return feats, lid, grid
+
+  # ------------------------------------------------------------------------------------------------ bev_encoder
+  def conv_in(self, inputs, conv, norm, act, out=None):
+    """Conv2d(3x3, bias=False) over the channel concatenation of ``inputs`` -> nn.InstanceNorm2d -> act
+    (bev_encoder.py:126-137,253-262).  The concatenation is never built: conv(cat(a, b)) = conv_a(a) + conv_b(b) with
+    the weight sliced along Cin, partial sums in fp32.  ``out``: wider NHWC tensor whose first Cout channels receive y."""
+    raw, k0, slices = None, 0, []
+    for i, a in enumerate(inputs):
+      k1 = k0 + a.shape[3]
+      raw = ops.conv_gemm(a, packed(conv.weight, 'conv_cin', k0, k1), taps=ops.TAPS_3X3, res1=raw,
+                          out_f32=i + 1 < len(inputs))
+      slices.append((a, k0, k1))
+      k0 = k1
+    ps = out.shape[3] if out is not None else None
+    y, mean, invstd = ops.instnorm(raw, act, norm.eps, out=out, out_pix_stride=ps, zeros=self.zeros,
+                                   save=self.tape is not None)
+    self._save(op='conv_in', slices=slices, raw=raw, y=y, mean=mean, invstd=invstd, conv=conv, act=act, y_pix_stride=ps)
+    return y
+
+  def lift_tables(self, device, img_h, img_w):
+    """tfpp_bev_lift tables folded from the module's grid / normaliser / mask parameters (nn.bev_encoder.lift_tables)."""
+    bb = self.bb
+    ps = (bb.grid, bb.bev_projection_normalizer, bb.valid_bev_pixels)
+    ver = tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps) + (img_h, img_w, str(device))  # pylint: disable=protected-access
+    hit = self._consts.get('lift_tables')
+    if hit is None or hit[0] != ver:
+      from .nn.bev_encoder import lift_tables  # pylint: disable=import-outside-toplevel
+      hit = (ver, tuple(t.to(device) for t in lift_tables(*ps, img_h, img_w)))
+      self._consts['lift_tables'] = hit
+    return hit[1]
+
+  def bev_stem(self, cat, cna, training):
+    """Stem ConvNormAct of the BEV RegNet (3x3, stride 2) over [compressed camera features | LiDAR | zero padding]:
+    one implicit GEMM over the four parity planes (ops.taps_3x3_stride2) with the BatchNorm statistics in its epilogue."""
+    b, cpad = cat.shape[0], cat.shape[3]
+    planes = ops.parity_split(cat)
+    w = packed(cna.conv.weight, 'conv_cin_pad', cpad)
+    taps = ops.taps_3x3_stride2(b)
+    bn = cna.bn
+    if training:
+      stats = self.zeros((2, w.shape[0]), cat.device)
+      raw = ops.conv_gemm(planes, w, taps=taps, batch=b, stats=(stats[0], stats[1]))
+      count = raw.shape[0] * raw.shape[1] * raw.shape[2]
+      scale, shift, mean, invstd = ops.bn_finalize(stats[0], stats[1], bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                   count, eps=bn.eps, momentum=bn.momentum, save=self.tape is not None)
+      self._count_batch(bn)
+      y = ops.scale_shift_act(raw, scale, shift, ACT_RELU)
+      self._save(op='bev_stem', cat=cat, planes=planes, raw=raw, y=y, mean=mean, invstd=invstd, scale=scale, shift=shift,
+                 cna=cna)
+      return y
+    scale, shift = packed((bn.weight, bn.bias, bn.running_mean, bn.running_var), 'bn_eval', bn.eps)
+    return ops.conv_gemm(planes, w, taps=taps, batch=b, scale=scale, shift=shift, act=ACT_RELU)
+
+  def bev_backbone_forward(self, image, lidar, training):
+    """BevEncoder.forward (bev_encoder.py:146-233).  image (B,3,H,W) f32 0..255, lidar (B,C,256,256) f32.  Returns NHWC
+    (bev feature grid (B,64,64,64), fused BEV features (B,16,16,576), perspective image features (B,32,128,32))."""
+    bb, cfg = self.bb, self.cfg
+    if not (image.is_cuda and lidar.is_cuda):
+      raise RuntimeError('carla_garage_b200 runs on CUDA tensors only (no CPU fallback)')
+    if not cfg.transformer_decoder_join:
+      raise NotImplementedError('bev_encoder with the global-pool MLP join is not built')
+    if training:
+      PARAM_EPOCH[0] += 1
+      if self.dropout_enabled:
+        self.begin_dropout_step(image.device)
+    image = image.float().contiguous()
+    lidar = lidar.float().contiguous()
+    b = image.shape[0]
+    enc = bb.image_encoder
+    x = self.stem(image, enc['stem'], training, cfg.normalize_imagenet)
+    x = self.regnet_stage(x, enc['s1'], training)
+    x2 = self.regnet_stage(x, enc['s2'], training)
+    x3 = self.regnet_stage(x2, enc['s3'], training)
+    self._tap('img_s2', x2)
+    self._tap('img_s3', x3)
+    # UpsamplingConcat (bev_encoder.py:264-272) + depth_layer
+    up = ops.bilinear(x3, b, x3.shape[1], x3.shape[2], x2.shape[1], x2.shape[2], x3.shape[3])
+    self._save(op='bilinear', src=x3, out=up)
+    ul = bb.upsampling_layer.conv
+    u = self.conv_in([x2, up], ul[0], ul[1], ACT_RELU)
+    u = self.conv_in([u], ul[3], ul[4], ACT_RELU)
+    self._tap('upsampled', u)
+    feat = self.conv_bias(u, bb.depth_layer)
+    self._tap('image_features', feat)
+    # lift to BEV (bev_encoder.py:179-199) and compress (:126-137) straight into the stem's input tensor
+    depth, width = bb.grid.shape[1], bb.grid.shape[2]
+    tables = self.lift_tables(image.device, feat.shape[1], feat.shape[2])
+    bev = ops.bev_lift(feat, tables, depth, width)
+    self._save(op='bev_lift', img=feat, out=bev, tables=tables)
+    self._tap('bev_lift', bev)
+    cl, cb = lidar.shape[1], bev.shape[3]
+    cpad = (cb + cl + 7) // 8 * 8
+    cat = torch.zeros((b, width, depth, cpad), dtype=ops.act_dtype(), device=image.device)
+    comp = bb.bev_compressor
+    self.conv_in([bev], comp[0], comp[1], ACT_GELU, out=cat)
+    cat[..., cb:cb + cl].copy_(lidar.permute(0, 2, 3, 1))   # torch.cat((bev_features, lidar_features), dim=1)
+    self._tap('bev_cat', cat)
+    f = self.bev_stem(cat, bb.bev_encoder['stem'], training)
+    for i in (1, 2, 3):
+      f = self.regnet_stage(f, bb.bev_encoder[f's{i}'], training)
+      self._tap(f'bev_s{i}', f)
+    feats = None
+    if cfg.detect_boxes or cfg.use_bev_semantic:  # top_down (bev_encoder.py:139-144)
+      p5 = self.conv_bias(f, bb.c5_conv, ACT_RELU)
+      up_f = cfg.bev_upsample_factor
+      p5u = ops.bilinear(p5, b, p5.shape[1], p5.shape[2], p5.shape[1] * up_f, p5.shape[2] * up_f, p5.shape[3])
+      self._save(op='bilinear', src=p5, out=p5u)
+      p4 = self.conv_bias(p5u, bb.up_conv5, ACT_RELU)
+      th = cfg.lidar_resolution_height // cfg.bev_down_sample_factor
+      tw = cfg.lidar_resolution_width // cfg.bev_down_sample_factor
+      p4u = ops.bilinear(p4, b, p4.shape[1], p4.shape[2], th, tw, p4.shape[3])
+      self._save(op='bilinear', src=p4, out=p4u)
+      feats = self.conv_bias(p4u, bb.up_conv4, ACT_RELU)
+    self._tap('bev_feature_grid', feats)
+    self._tap('fused_features', f)
+    return feats, f, feat
 
   # ------------------------------------------------------------------------------------------------ heads
   def perspective_decoder(self, dec, grid, act_last=ACT_NONE):

@@ -151,8 +151,11 @@ class LidarCenterNet(nn.Module):
     self.make_histogram = int(os.environ.get('HISTOGRAM', 0))
     if config.backbone == 'transFuser':
       self.backbone = TransfuserBackbone(config)
-    elif config.backbone in ('aim', 'bev_encoder'):
-      raise NotImplementedError(f'backbone {config.backbone} is outside the TransFuser++ hot path (SURVEY.md §8f)')
+    elif config.backbone == 'bev_encoder':  # model.py:42-43
+      from .bev_encoder import BevEncoder  # pylint: disable=import-outside-toplevel
+      self.backbone = BevEncoder(config)
+    elif config.backbone == 'aim':
+      raise NotImplementedError('backbone aim (camera only) is not built (SURVEY.md §8 f3)')
     else:
       raise ValueError('The chosen vision backbone does not exist. The options are: transFuser, aim, bev_encoder')
     if not (config.use_controller_input_prediction or config.use_wp_gru) or config.tp_attention or config.multi_wp_output:

@@ -62,7 +62,9 @@ class _FeatureInfo:
 class RegNetY032Features(nn.ModuleDict):
   """FeatureListNet surface used by the reference: .items(), .return_layers, .feature_info.info."""
 
-  def __init__(self, in_chans=3):
+  def __init__(self, in_chans=3, num_stages=4):
+    """num_stages < 4: the later stages are never built (bev_encoder.py:35-37,85-87 delete ``s4`` after timm created
+    it; feature_info keeps all five entries, as timm's does)."""
     super().__init__()
     self['stem'] = ConvNormAct(in_chans, STEM_WIDTH, 3, stride=2)
     prev = STEM_WIDTH
@@ -73,7 +75,8 @@ class RegNetY032Features(nn.ModuleDict):
       for j in range(d):
         stage.add_module(f'b{j + 1}', Bottleneck(prev, w, 2 if j == 0 else 1))
         prev = w
-      self[f's{i + 1}'] = stage
+      if i < num_stages:
+        self[f's{i + 1}'] = stage
       red *= 2
       info.append(dict(num_chs=w, reduction=red, module=f's{i + 1}'))
     self.feature_info = _FeatureInfo(info)

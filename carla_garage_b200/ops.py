@@ -1029,3 +1029,71 @@ def smallc_wgrad3x3(dy, x, out, out_strides, co_valid):
                                          out_strides[2], co_valid, b, h, w, cop, x.shape[3], _stream()),
         'tfpp_smallc_wgrad3x3')
   return out
+
+
+# ---------------------------------------------------------------------------------------------- bev_encoder backbone
+def instnorm(x, act=ACT_NONE, eps=1e-5, out=None, out_pix_stride=None, zeros=None, save=False):
+  """nn.InstanceNorm2d(affine=False) + activation on an NHWC (B,H,W,C) bf16|f32 tensor.  ``out`` may be a wider NHWC
+  tensor (out_pix_stride elements per pixel, the C outputs go to its first C channels).  Returns (y, mean, invstd)."""
+  _dev(x)
+  b, h, w, c = x.shape
+  f32 = int(x.dtype == F32)
+  mk = zeros if zeros is not None else (lambda shape, dev: torch.zeros(shape, dtype=F32, device=dev))
+  sums = mk((2, b, c), x.device)
+  check(_lib.load().tfpp_instnorm_stats(x.data_ptr(), f32, c, b, h * w, c, sums[0].data_ptr(), sums[1].data_ptr(), _stream()),
+        'tfpp_instnorm_stats')
+  if out is None:
+    out = torch.empty_like(x)
+    out_pix_stride = c
+  else:
+    if out.dtype != x.dtype:
+      raise RuntimeError(f'instnorm: x is {x.dtype}, out is {out.dtype}')
+    out_pix_stride = out_pix_stride or out.shape[-1]
+  mean = torch.empty((b, c), dtype=F32, device=x.device) if save else None
+  invstd = torch.empty((b, c), dtype=F32, device=x.device) if save else None
+  check(_lib.load().tfpp_instnorm_apply(x.data_ptr(), f32, c, sums[0].data_ptr(), sums[1].data_ptr(), eps, act, out.data_ptr(),
+                                        out_pix_stride, _p(mean), _p(invstd), b, h * w, c, _stream()), 'tfpp_instnorm_apply')
+  return out, mean, invstd
+
+
+def instnorm_bwd(dy, x, mean, invstd, act, dy_pix_stride=None, zeros=None):
+  """Adjoint of instnorm wrt x.  dy: gradient wrt the activation output, NHWC with dy_pix_stride elements per pixel."""
+  _dev(x)
+  b, h, w, c = x.shape
+  if dy.dtype != x.dtype:
+    raise RuntimeError(f'instnorm_bwd: dy is {dy.dtype}, x is {x.dtype}')
+  mk = zeros if zeros is not None else (lambda shape, dev: torch.zeros(shape, dtype=F32, device=dev))
+  s = mk((2, b, c), x.device)
+  dx = torch.empty_like(x)
+  check(_lib.load().tfpp_instnorm_bwd(dy.data_ptr(), dy_pix_stride or c, x.data_ptr(), int(x.dtype == F32), mean.data_ptr(),
+                                      invstd.data_ptr(), act, s[0].data_ptr(), s[1].data_ptr(), dx.data_ptr(), b, h * w, c,
+                                      _stream()), 'tfpp_instnorm_bwd')
+  return dx
+
+
+def bev_lift(img, tables, depth, width):
+  """img (B,IH,IW,C) NHWC -> (B, width, depth, C) NHWC; tables = (a_rows (depth, IH) f32, x0 (depth, width) int32,
+  wl, wr (depth, width) f32) from nn.bev_encoder.lift_tables."""
+  _dev(img)
+  b, ih, iw, c = img.shape
+  a, x0, wl, wr = tables
+  out = torch.empty((b, width, depth, c), dtype=img.dtype, device=img.device)
+  check(_lib.load().tfpp_bev_lift(img.data_ptr(), int(img.dtype == F32), a.data_ptr(), x0.data_ptr(), wl.data_ptr(),
+                                  wr.data_ptr(), out.data_ptr(), b, ih, iw, c, depth, width, _stream()), 'tfpp_bev_lift')
+  return out
+
+
+def bev_lift_bwd(dout, tables, img_shape, dimg=None):
+  """Adjoint of bev_lift wrt img; accumulates into ``dimg`` when given."""
+  _dev(dout)
+  b, ih, iw, c = img_shape
+  _, width, depth, _ = dout.shape
+  a, x0, wl, wr = tables
+  ws = torch.empty((b, depth, iw, c), dtype=F32, device=dout.device)
+  acc = dimg is not None
+  if dimg is None:
+    dimg = torch.empty(img_shape, dtype=dout.dtype, device=dout.device)
+  check(_lib.load().tfpp_bev_lift_bwd(dout.data_ptr(), int(dout.dtype == F32), a.data_ptr(), x0.data_ptr(), wl.data_ptr(),
+                                      wr.data_ptr(), ws.data_ptr(), dimg.data_ptr(), int(acc), b, ih, iw, c, depth, width,
+                                      _stream()), 'tfpp_bev_lift_bwd')
+  return dimg

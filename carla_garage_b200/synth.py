@@ -185,3 +185,28 @@ def mlp_join_state(golden_dir):
       'loss_bev_semantic.weight': torch.ones(11),
   }
   return make_state_dict(shapes, seed=0, fixed=fixed)
+
+
+def bev_state(golden_dir):
+  """The seeded state_dict of the ``backbone = 'bev_encoder'`` goldens (tests/golden/make_golden_bev.py):
+  make_state_dict(seed 0) over that configuration's keys + the fixed buffers; the three geometry parameters come from
+  this package's own closed form (nn.bev_encoder.projection_grid; fingerprints of the reference's are in the golden)."""
+  import json
+  import os
+  from .config import GlobalConfig
+  from .nn.bev_encoder import projection_grid
+  shapes = json.load(open(os.path.join(golden_dir, 'bev_keys.json')))['shapes']
+  valid = torch.from_numpy(np.load(os.path.join(golden_dir, 'valid_bev_pixels.npz'))['valid']).float()
+  cfg = GlobalConfig()
+  grid, ok = projection_grid(cfg)
+  fixed = {
+      'valid_bev_pixels': valid,
+      'valid_bev_pixels_inv': 1.0 - valid,
+      'loss_speed.weight': torch.tensor([0.866605263873406, 7.4527377240841775, 1.2281629310898465, 0.5269622904065803]),
+      'loss_semantic.weight': torch.ones(7),
+      'loss_bev_semantic.weight': torch.ones(11),
+      'backbone.grid': grid,
+      'backbone.bev_projection_normalizer': torch.finfo(torch.float32).eps + torch.sum(ok, dim=3).unsqueeze(1),
+      'backbone.valid_bev_pixels': torch.transpose(torch.max(ok, dim=3)[0].unsqueeze(1), 2, 3).contiguous(),
+  }
+  return make_state_dict(shapes, seed=0, fixed=fixed)

@@ -46,8 +46,9 @@ class FlatState:
     (train.py:495-508 freezes sub-modules) so the backward handlers have somewhere to write; constants such as
     valid_bev_pixels stay out."""
     self.model = model
+    constants = ('valid_bev_pixels', 'valid_bev_pixels_inv', 'grid', 'bev_projection_normalizer')  # geometry, not weights
     params = [(n, p) for n, p in model.named_parameters()
-              if p.requires_grad or (include_frozen and p.is_floating_point() and not n.startswith('valid_bev'))]
+              if p.requires_grad or (include_frozen and p.is_floating_point() and n.rsplit('.', 1)[-1] not in constants)]
     by_name = dict(params)
     ordered, used = [], set()
 
@@ -63,7 +64,7 @@ class FlatState:
             starts.add(n)
           first = False
 
-    for i in range(4):
+    for i in range(len(getattr(model.backbone, 'transformers', ()))):  # (the bev_encoder backbone has no fusion GPTs)
       for l in range(len(model.backbone.transformers[i].blocks)):
         base = f'backbone.transformers.{i}.blocks.{l}.attn.'
         take([base + 'query.weight', base + 'key.weight', base + 'value.weight'])
@@ -671,6 +672,52 @@ class Backward:
     self.G[id(img)] = ops.pool_bwd_add(self.G.get(id(img)), df, tuple(img.shape), 1, 1, 1, 0)
     self.G[id(lid)] = ops.pool_bwd_add(self.G.get(id(lid)), dlp, tuple(lid.shape), 1, 1, 1, 0)
 
+  def conv_in(self, r):
+    """adjoint of Engine.conv_in: InstanceNorm2d + activation, then weight / input gradients of every Cin slice."""
+    st = self.st
+    conv, raw = r['conv'], r['raw']
+    dy = self.G.pop(id(r['y']))
+    draw = ops.instnorm_bwd(dy, raw, r['mean'], r['invstd'], r['act'], dy_pix_stride=r['y_pix_stride'], zeros=self.eng.zeros)
+    cin_all, k = conv.weight.shape[1], conv.weight.shape[-1]
+    gw = st.g(conv.weight).view(-1)
+    for a, k0, k1 in r['slices']:
+      ops.conv_wgrad(draw, a, cin=k1 - k0, taps=ops.TAPS_3X3, w_taps=k * k, out=gw[k0 * k * k:],
+                     out_strides=(cin_all * k * k, 1, k * k))
+      self.G[id(a)] = ops.conv_gemm(draw, packed(conv.weight, 'conv_cin_t', k0, k1), taps=ops.TAPS_3X3_DGRAD,
+                                    res1=self.G.get(id(a)))
+
+  def bev_lift(self, r):
+    img = r['img']
+    dout = self.G.pop(id(r['out']))
+    self.G[id(img)] = ops.bev_lift_bwd(dout, r['tables'], tuple(img.shape), dimg=self.G.get(id(img)))
+
+  def bev_stem(self, r):
+    """adjoint of Engine.bev_stem: BatchNorm + ReLU, the weight gradient over the parity planes, and the input gradient
+    as one implicit GEMM per parity plane written straight to its pixels of the full-resolution tensor."""
+    st = self.st
+    cna, cat, planes = r['cna'], r['cat'], r['planes']
+    conv, bn = cna.conv, cna.bn
+    dy = self.G.pop(id(r['y']))
+    draw, _ = ops.bn_bwd(dy, None, r['raw'], r['mean'], r['invstd'], bn.weight, ACT_RELU, st.g(bn.weight), st.g(bn.bias),
+                         fwd_affine=(r['scale'], r['shift']))
+    b, h, w, cpad = cat.shape
+    cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+    dw = ops.conv_wgrad(draw, planes, cin=cpad, taps=ops.taps_3x3_stride2(b), w_taps=9)      # (Cout, 9, cpad) f32
+    st.g(conv.weight).view(cout, cin, 9).add_(dw[:, :, :cin].transpose(1, 2))
+    wt = packed(conv.weight, 'conv_cin_pad_t', cpad)                                          # (cpad, 9, Cout)
+    dcat = torch.empty_like(cat)
+    flat = dcat.view(-1)
+    strides = (h * w * cpad, 2 * w * cpad, 2 * cpad, 1)
+    for py in (0, 1):
+      for px in (0, 1):
+        # input pixel (2r + py, 2c + px) is read by the taps whose parity plane is (py, px): ky = 1 for the even rows,
+        # ky in {0, 2} for the odd ones (output row r + 1 resp. r), same for columns
+        kys = ((1, 0),) if py == 0 else ((0, 1), (2, 0))
+        kxs = ((1, 0),) if px == 0 else ((0, 1), (2, 0))
+        taps = tuple((ox, oy, 0, ky * 3 + kx) for ky, oy in kys for kx, ox in kxs)
+        ops.conv_gemm(draw, wt, taps=taps, out=flat[(py * w + px) * cpad:], out_strides=strides)
+    self.G[id(cat)] = dcat
+
   def planner_queries(self, r):
     # a learned query set repeated over the batch (model.py:329,349): its gradient is the sum over the batch
     dx0 = self.G.pop(id(r['x0']))
@@ -864,6 +911,12 @@ class Backward:
       self.mlp_join(r)
     elif op == 'global_fuse':
       self.global_fuse(r)
+    elif op == 'conv_in':
+      self.conv_in(r)
+    elif op == 'bev_lift':
+      self.bev_lift(r)
+    elif op == 'bev_stem':
+      self.bev_stem(r)
     elif op == 'planner_head':
       self.planner_head(r, seeds)
     elif op == 'dec_layer':

@@ -517,6 +517,35 @@ int tfpp_pillar_scatter_aligned(const float* points, const double* xform, int n_
                                 float min_y, float max_y, float pixels_per_meter, int hist_max, double split_z,
                                 float max_z, tfpp_stream_t stream);
 
+/* ---- bev_encoder backbone (reference team_code/bev_encoder.py) --------------------------------
+ * nn.InstanceNorm2d(affine=False, eps) + activation (bev_encoder.py:126-137 bev_compressor, :253-262 UpsamplingConcat):
+ * tfpp_instnorm_stats accumulates per-(sample, channel) sum / sum of squares into zero-initialised (batch, channels)
+ * buffers; tfpp_instnorm_apply writes y = act((x - mean) * invstd) (biased variance) and, if given, mean / invstd for
+ * the backward pass; tfpp_instnorm_bwd is the adjoint (s1, s2: zero-initialised (batch, channels) workspaces).
+ * x / dx are NHWC with unit channel stride; *_pix_stride = elements between consecutive pixels (>= channels), so that
+ * y / dy may live inside a wider tensor.  f32 = 1: float32 tensors (parity mode), 0: bf16. */
+int tfpp_instnorm_stats(const void* x, int f32, long long x_pix_stride, int batch, int hw, int channels, float* sum,
+                        float* sq, tfpp_stream_t stream);
+int tfpp_instnorm_apply(const void* x, int f32, long long x_pix_stride, const float* sum, const float* sq, float eps,
+                        int act, void* y, long long y_pix_stride, float* mean, float* invstd, int batch, int hw,
+                        int channels, tfpp_stream_t stream);
+int tfpp_instnorm_bwd(const void* dy, long long dy_pix_stride, const void* x, int f32, const float* mean,
+                      const float* invstd, int act, float* s1, float* s2, void* dx, int batch, int hw, int channels,
+                      tfpp_stream_t stream);
+
+/* Camera -> BEV lift, bev_encoder.py:179-199 (F.grid_sample over the (depth, width, height) voxel grid of
+ * transfuser_utils.py:596-665, sum over height, / bev_projection_normalizer, transpose, * valid_bev_pixels) in its
+ * separable form: out[b, w, d, :] = wl[d, w] * V[b, d, x0[d, w], :] + wr[d, w] * V[b, d, x0[d, w] + 1, :],
+ * V[b, d, x, :] = sum_y a_rows[d, y] * img[b, y, x, :].  img (batch, img_h, img_w, channels) NHWC, out (batch, width,
+ * depth, channels) NHWC; a_rows (depth, img_h) f32, x0 (depth, width) int32 in [0, img_w - 2], wl / wr (depth, width)
+ * f32 with the normaliser, the visibility mask and the zero padding folded in.  tfpp_bev_lift_bwd: adjoint wrt img;
+ * ws = (batch, depth, img_w, channels) f32 workspace; accumulate = 1 adds to dimg. */
+int tfpp_bev_lift(const void* img, int f32, const float* a_rows, const int* x0, const float* wl, const float* wr,
+                  void* out, int batch, int img_h, int img_w, int channels, int depth, int width, tfpp_stream_t stream);
+int tfpp_bev_lift_bwd(const void* dout, int f32, const float* a_rows, const int* x0, const float* wl, const float* wr,
+                      float* ws, void* dimg, int accumulate, int batch, int img_h, int img_w, int channels, int depth,
+                      int width, tfpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,8 @@ def main():
   for m in net.modules():
     if isinstance(m, torch.nn.Dropout):
       m.p = 0.0
+    if isinstance(m, torch.nn.MultiheadAttention):
+      m.dropout = 0.0
   B = 2
   inp = synth.make_inputs(B, seed=11)
   lab = synth.make_labels(B, seed=13)

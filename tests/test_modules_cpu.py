@@ -116,6 +116,8 @@ def test_pack_plan_index_maps_reproduce_every_gather_pack():
            ('cat_rows_f32', (params['lin_a'], params['lin_b']), (0, 8)), ('cat_f32', (params['vec'], params['lin_b']), ()),
            ('cat_conv', (params['c1'], params['c1']), ()), ('cat_conv_t', (params['c1'], params['c1']), ()),
            ('blockdiag_1x1', (params['c1'], params['c2']), ()), ('blockdiag_1x1_t', (params['c1'], params['c2']), ()),
+           ('conv_cin', (params['conv'],), (8, 16)), ('conv_cin_t', (params['conv'],), (0, 8)),
+           ('conv_cin_pad', (params['conv'],), (24,)), ('conv_cin_pad_t', (params['conv'],), (24,)),
            ('repeat_rows', (params['pos'],), (3,))]
   assert {c[0] for c in cases} == set(E._GATHER_KINDS)  # pylint: disable=protected-access
   for kind, ps, extra in cases:
