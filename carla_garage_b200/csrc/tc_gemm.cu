@@ -16,6 +16,8 @@
 #include "../../include/tfpp.h"
 #include "tc_common.cuh"
 
+#include <cstdlib>
+
 using namespace tc;
 
 namespace {
@@ -61,10 +63,12 @@ struct TileCoord {
   int n0, x0, y0, b0, n_tile;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
+// m_mul / m_add: a CTA pair's work item covers the M tiles 2 * item + {0, 1} (an odd tail tile decodes to a batch index
+// past the end: its TMA boxes are zero-filled and its rows are masked in the epilogue)
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile, int m_mul = 1, int m_add = 0) {
   TileCoord t;
   t.n_tile = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
+  int m = (tile / p.n_tiles) * m_mul + m_add;
   t.n0 = t.n_tile * p.bn;
   t.x0 = (m % p.m_tiles_x) * p.tw;
   m /= p.m_tiles_x;
@@ -73,6 +77,10 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
   return t;
 }
 
+// PAIR: two CTAs of a cluster (cta_group::2) share one M = 256 x BN tile: CTA r stages its own 128 pixels of A and rows
+// [r * BN / 2, (r + 1) * BN / 2) of the B tile, the leader issues M = 256 MMAs that read both CTAs' shared memory, so each
+// SM pulls 16 KB + BN * 64 B per k-block through L2 instead of 16 KB + BN * 128 B (the GEMMs are L2 -> SM bound).
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const KParams p) {
@@ -95,7 +103,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.n_tiles * p.m_tiles_x * p.m_tiles_y * p.m_tiles_b;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader of the CTA pair
+  const int m_tiles = p.m_tiles_x * p.m_tiles_y * p.m_tiles_b;
+  // work items: (n tile, M tile) — or (n tile, pair of consecutive M tiles) for a CTA pair; both CTAs of a pair walk the
+  // same item sequence
+  const int num_tiles = p.n_tiles * (PAIR ? (m_tiles + 1) / 2 : m_tiles);
+  const int first_tile = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int k_iters = p.ntaps * p.kc_per_tap;
 
   if (warp == 0 && lane == 0) {
@@ -107,18 +121,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 8);
+      mbar_init(smem_u32(&tempty_bar[s]), PAIR ? 16 : 8);   // the leader's barrier collects both CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -127,16 +149,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kABytes + p.bn * kBlockK * 2;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      const int b_rows = PAIR ? p.bn / 2 : p.bn;   // B rows this CTA stages
+      const uint32_t tx_bytes = (kABytes + b_rows * kBlockK * 2) * (PAIR ? 2 : 1);   // the leader's barrier counts both CTAs
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const TileCoord t = decode_tile(p, tile, PAIR ? 2 : 1, static_cast<int>(rank));
         const int c_base = t.n_tile * p.a_c_per_ntile;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_expect_tx(fb, tx_bytes);
             uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            if (PAIR) {
+              if (rank == 0) mbar_expect_tx(fb, tx_bytes);
+              const uint32_t lb = mapa_shared(fb, 0);   // completion goes to the leader's barrier
+              tma_load_4d_pair(smem_u32(sa), &tmap_a, lb, c_base + kc * kBlockK, t.x0 + p.tap_dx[tap],
+                               t.y0 + p.tap_dy[tap], t.b0 + p.tap_db[tap]);
+              tma_load_3d_pair(smem_u32(sa + kABytes), &tmap_b, lb, kc * kBlockK, p.tap_w[tap],
+                               t.n0 + static_cast<int>(rank) * b_rows);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
+            }
+            mbar_expect_tx(fb, tx_bytes);
             tma_load_4d(smem_u32(sa), &tmap_a, fb, c_base + kc * kBlockK, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap],
                         t.b0 + p.tap_db[tap]);
             tma_load_3d(smem_u32(sa + kABytes), &tmap_b, fb, kc * kBlockK, p.tap_w[tap], t.n0);
@@ -150,13 +186,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (elect_one()) {  // one elected lane: the compiler keeps the descriptors in uniform registers (no per-MMA elect loop)
+    if (rank == 0 && elect_one()) {  // one elected lane (of the leader CTA): descriptors stay in uniform registers
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.bn);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, p.bn);
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -169,15 +205,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
             // advance 16 bf16 = 32 bytes inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) ? 1u : 0u);
+            if (PAIR)
+              umma_bf16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&empty_bar[stage]));
+          if (PAIR)
+            umma_commit_pair(smem_u32(&empty_bar[stage]));   // frees the stage in both CTAs
+          else
+            umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));
+        if (PAIR)
+          umma_commit_pair(smem_u32(&tfull_bar[acc]));       // both CTAs' epilogues may read their 128 accumulator rows
+        else
+          umma_commit(smem_u32(&tfull_bar[acc]));
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -212,8 +257,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     float* __restrict__ out_f = static_cast<float*>(p.out);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    const uint32_t tempty_leader0 = PAIR ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const TileCoord t = decode_tile(p, tile, PAIR ? 2 : 1, static_cast<int>(rank));
       const int bl = row / pix_per_img;
       const int rem = row - bl * pix_per_img;
       const int yy = t.y0 + rem / p.tw;
@@ -370,7 +416,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (lane == 0) {
+        if (PAIR)
+          mbar_arrive_cluster(tempty_leader0 + acc * 8);   // the leader's MMA thread owns the accumulator hand-back
+        else
+          mbar_arrive(smem_u32(&tempty_bar[acc]));
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -392,9 +443,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the leader's MMAs read the peer's shared memory and write its TMEM until the very end
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -437,7 +492,17 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
     p.tap_db[i] = a->tap_db[i];
     p.tap_w[i] = a->tap_w[i];
   }
-  p.b_stage_bytes = ((a->bn * kBlockK * 2 + 1023) / 1024) * 1024;
+  // CTA pairs (cta_group::2) for the wide, deep GEMMs: they are bound by the L2 -> SM operand feed and a pair halves the
+  // B bytes each SM pulls (measured on B200, B=32 step shapes: K=1512 N=6048 805 -> 975 TFLOP/s, K=6048 N=1512 1031 ->
+  // 1135; the K=576 RegNet 1x1 convs get slower — 9 k-blocks per tile do not amortise the cross-CTA hand-offs — hence the
+  // K >= 1024 rule).  TFPP_GEMM_PAIR=0 switches the path off, =2 forces it wherever the shape allows (tests).
+  static const int pair_mode = [] { const char* e = getenv("TFPP_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  const int m_tiles_total = p.m_tiles_x * p.m_tiles_y * p.m_tiles_b;
+  const long long k_total = static_cast<long long>(p.ntaps) * a->k_per_tile;
+  const bool pair = pair_mode != 0 && a->bn % 16 == 0 && a->bn >= 64 && m_tiles_total >= 2 &&
+                    (pair_mode == 2 || (a->bn >= 128 && k_total >= 1024 && m_tiles_total * p.n_tiles >= 2 * TFPP_NUM_SMS));
+  const int b_rows = pair ? a->bn / 2 : a->bn;
+  p.b_stage_bytes = ((b_rows * kBlockK * 2 + 1023) / 1024) * 1024;
   const int stage_bytes = kABytes + p.b_stage_bytes;
   p.out = a->out;
   p.out_f32 = a->out_f32;
@@ -471,7 +536,7 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
     const cuuint64_t k = a->w_kdim, t = a->w_taps, n = a->n;
     const cuuint64_t dims[3] = {k, t, n};
     const cuuint64_t strides[2] = {k * 2, t * k * 2};
-    const cuuint32_t box[3] = {kBlockK, 1, (cuuint32_t)a->bn};
+    const cuuint32_t box[3] = {kBlockK, 1, (cuuint32_t)b_rows};
     int rc = encode_map(&tmap_b, a->w, 3, dims, strides, box);
     if (rc) return rc;
   }
@@ -494,7 +559,9 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
   const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + fixed_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       tfpp_set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
       return TFPP_ERR_CUDA;
@@ -510,8 +577,30 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
     if (cached_sms == 0) cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
     if (cached_sms > 0) sms = cached_sms;
   }
+  if (pair) {
+    const int items = p.n_tiles * ((m_tiles_total + 1) / 2);
+    const int pairs = items < sms / 2 ? items : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, tmap_a, tmap_b, p);
+    if (e != cudaSuccess) {
+      tfpp_set_error("%s:%d: CUDA: %s", __FILE__, __LINE__, cudaGetErrorString(e));
+      return TFPP_ERR_CUDA;
+    }
+    return TFPP_OK;
+  }
   const int grid = num_tiles < sms ? num_tiles : sms;
-  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, p);
+  conv_gemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, p);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }
