@@ -80,7 +80,11 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile, int
 // PAIR: two CTAs of a cluster (cta_group::2) share one M = 256 x BN tile: CTA r stages its own 128 pixels of A and rows
 // [r * BN / 2, (r + 1) * BN / 2) of the B tile, the leader issues M = 256 MMAs that read both CTAs' shared memory, so each
 // SM pulls 16 KB + BN * 64 B per k-block through L2 instead of 16 KB + BN * 128 B (the GEMMs are L2 -> SM bound).
-template <bool PAIR>
+// LEAN: epilogue specialisations compiled as their own kernels (the K <= 576 layers are bound by the latency of the ten
+// warps' epilogue instruction stream, and the 168-register generic epilogue must not pay for them): 1 = bf16 NHWC output +
+// BatchNorm statistics, nothing else (RegNet convs of a training step); 2 = bf16 NHWC output + at most one bf16
+// residual (input-gradient GEMMs); 0 = everything.
+template <bool PAIR, int LEAN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const KParams p) {
@@ -287,6 +291,69 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t r[32];
         const int n = t.n0 + c;
         const int ng = min(4, (ncols - c) >> 3);   // 8-column groups of this slab that are real outputs (fast path)
+        if (LEAN != 0) {
+          uint4 rq[4];
+          const bool with_res = LEAN == 2 && res_b != nullptr;
+          if (with_res && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res_b + r1_base + n);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < ng) rq[q] = __ldg(rp + q);
+          }
+          __syncwarp();
+          tmem_ld32_issue(taddr + c, r);
+          tmem_ld_wait32(r);
+          if (LEAN == 1) {
+            const uint32_t trs = smem_u32(tr);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(trs + (lane * 33 + j) * 4), "r"(r[j]) : "memory");
+            __syncwarp();
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;   // two accumulation chains
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 2) {
+              float a0, a1;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a0) : "r"(trs + (rr * 33 + lane) * 4) : "memory");
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(trs + ((rr + 1) * 33 + lane) * 4) : "memory");
+              if (valid_mask != 0xffffffffu) {
+                a0 = ((valid_mask >> rr) & 1u) ? a0 : 0.f;
+                a1 = ((valid_mask >> (rr + 1)) & 1u) ? a1 : 0.f;
+              }
+              s0 += a0;
+              s1 += a1;
+              q0 = fmaf(a0, a0, q0);
+              q1 = fmaf(a1, a1, q1);
+            }
+            if (n + lane < nend) {
+              atomicAdd(&sstat[n + lane], s0 + s1);
+              atomicAdd(&sstat[stat_stride + n + lane], q0 + q1);
+            }
+          }
+          if (valid) {
+            bf16* op = out_b + o_base + n;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q < ng) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+                if (with_res) {
+                  const uint32_t w[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16x2(w[j]);
+                    v[2 * j] += f.x;
+                    v[2 * j + 1] += f.y;
+                  }
+                }
+                *reinterpret_cast<uint4*>(op + q * 8) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                                   pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              }
+            }
+          }
+          if (LEAN == 1) __syncwarp();   // the transpose tile is reused by the next slab
+          continue;
+        }
         // residual of this row's slab: issue the loads before the TMEM wait
         uint4 rq[4];
         float4 rf[8];
@@ -557,14 +624,26 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
   TFPP_CHECK_ARG(stages >= 2, "shared memory budget exceeded");
   p.stages = stages;
   const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + fixed_bytes;
+  static const bool lean_on = [] { const char* e = getenv("TFPP_GEMM_LEAN"); return e == nullptr || e[0] != '0'; }();
+  int lean = 0;
+  if (lean_on && p.fast_layout && !a->out_f32 && a->scale == nullptr && a->shift == nullptr && a->act == ACT_NONE &&
+      p.drop_rng == nullptr) {
+    if (a->stat_sum != nullptr && a->res1 == nullptr) lean = 1;
+    if (a->stat_sum == nullptr && (a->res1 == nullptr || !a->res1_f32)) lean = 2;
+  }
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
+  static const KernelFn kernels[2][3] = {
+      {conv_gemm_kernel<false, 0>, conv_gemm_kernel<false, 1>, conv_gemm_kernel<false, 2>},
+      {conv_gemm_kernel<true, 0>, conv_gemm_kernel<true, 1>, conv_gemm_kernel<true, 2>}};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      tfpp_set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
-      return TFPP_ERR_CUDA;
+    for (int i = 0; i < 6; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels[i / 3][i % 3]),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) {
+        tfpp_set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+        return TFPP_ERR_CUDA;
+      }
     }
     attr_set = true;
   }
@@ -592,7 +671,7 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, tmap_a, tmap_b, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernels[1][lean], tmap_a, tmap_b, p);
     if (e != cudaSuccess) {
       tfpp_set_error("%s:%d: CUDA: %s", __FILE__, __LINE__, cudaGetErrorString(e));
       return TFPP_ERR_CUDA;
@@ -600,7 +679,7 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
     return TFPP_OK;
   }
   const int grid = num_tiles < sms ? num_tiles : sms;
-  conv_gemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, p);
+  kernels[0][lean]<<<grid, kThreads, smem_bytes, stream>>>(tmap_a, tmap_b, p);
   TFPP_CHECK_LAUNCH();
   return TFPP_OK;
 }

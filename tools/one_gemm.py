@@ -6,6 +6,22 @@ which = sys.argv[1] if len(sys.argv) > 1 else 'qkv'
 if which == 'qkv':
   x = torch.randn(10240, 1512, device='cuda').to(torch.bfloat16); w = torch.randn(4536, 1512, device='cuda').to(torch.bfloat16)
   f = lambda: ops.linear(x, w)
+elif which == 'c576':  # RegNet stage-3 1x1 conv with BatchNorm statistics (the most frequent GEMM of the step)
+  x = torch.randn(32, 16, 64, 576, device='cuda').to(torch.bfloat16); w = torch.randn(576, 1, 576, device='cuda').to(torch.bfloat16)
+  st = (torch.zeros(576, device='cuda'), torch.zeros(576, device='cuda'))
+  f = lambda: ops.conv_gemm(x, w, stats=st)
+elif which == 'mlp':  # fusion MLP up-projection at scale 4: M=10240, K=1512, N=6048
+  x = torch.randn(10240, 1512, device='cuda').to(torch.bfloat16); w = torch.randn(6048, 1512, device='cuda').to(torch.bfloat16)
+  f = lambda: ops.linear(x, w)
+elif which == 'bevlift':
+  from carla_garage_b200.config import GlobalConfig
+  from carla_garage_b200.nn.bev_encoder import lift_tables, projection_grid
+  grid, ok = projection_grid(GlobalConfig())
+  norm = torch.finfo(torch.float32).eps + ok.sum(3).unsqueeze(1)
+  vbp = torch.transpose(ok.max(3)[0].unsqueeze(1), 2, 3).contiguous()
+  tables = tuple(t.cuda() for t in lift_tables(grid, norm, vbp, 32, 128))
+  img = torch.randn(32, 32, 128, 32, device='cuda').to(torch.bfloat16)
+  f = lambda: ops.bev_lift(img, tables, 256, 256)
 elif which == 'dec5':
   x = torch.randn(32, 256, 1024, 32, device='cuda').to(torch.bfloat16); w = torch.randn(32, 9, 32, device='cuda').to(torch.bfloat16)
   f = lambda: ops.conv_gemm(x, w, taps=ops.TAPS_3X3)
