@@ -211,11 +211,43 @@ __global__ void __launch_bounds__(256) instnorm_bwd_apply_kernel(const T* __rest
 // grid (D, B), 256 threads.  img (B, IH, IW, C) NHWC, out (B, W, D, C) NHWC (rows = width index, columns = depth index:
 // the transpose of bev_encoder.py:193 is folded into the store).
 template <typename T>
+struct Vec8;
+template <>
+struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <>
+struct Vec8<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                              pack_bf16x2(v[6], v[7]));
+  }
+};
+
+// a thread owns 8 channels: 16-byte loads of the feature rows, 16-byte stores of the BEV cells (C % 8 == 0)
+template <typename T>
 __global__ void __launch_bounds__(256) bev_lift_kernel(const T* __restrict__ img, const float* __restrict__ A,
                                                        const int* __restrict__ x0, const float* __restrict__ wl,
                                                        const float* __restrict__ wr, T* __restrict__ out, int IH, int IW,
                                                        int C, int D, int W) {
-  extern __shared__ float sm[];  // V[IW * C] | a[IH]
+  extern __shared__ __align__(16) float sm[];  // V[IW * C] | a[IH]
   float* V = sm;
   float* a = sm + IW * C;
   const int d = blockIdx.x, b = blockIdx.y;
@@ -223,21 +255,32 @@ __global__ void __launch_bounds__(256) bev_lift_kernel(const T* __restrict__ img
   __syncthreads();
   const int row = IW * C;
   const T* ib = img + static_cast<long long>(b) * IH * row;
-  for (int i = threadIdx.x; i < row; i += blockDim.x) {
-    float acc = 0.f;
+  for (int i = threadIdx.x * 8; i < row; i += blockDim.x * 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int y = 0; y < IH; ++y) {
       const float w = a[y];
-      if (w != 0.f) acc = fmaf(w, ldf<T>(ib + static_cast<long long>(y) * row + i), acc);
+      if (w != 0.f) {
+        float v[8];
+        Vec8<T>::load(ib + static_cast<long long>(y) * row + i, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+      }
     }
-    V[i] = acc;
+    Vec8<float>::store(V + i, acc);
   }
   __syncthreads();
-  const int c = threadIdx.x % C, wrow = threadIdx.x / C, wstep = blockDim.x / C;
-  for (int w = wrow; w < W; w += wstep) {
+  const int c8n = C / 8;
+  for (int g = threadIdx.x; g < W * c8n; g += blockDim.x) {
+    const int w = g / c8n, c = (g % c8n) * 8;
     const int t = d * W + w;
     const int xi = x0[t];
-    const float v = wl[t] * V[xi * C + c] + wr[t] * V[(xi + 1) * C + c];
-    stf<T>(out + ((static_cast<long long>(b) * W + w) * D + d) * C + c, v);
+    const float l = wl[t], r = wr[t];
+    float vl[8], vr[8], o[8];
+    Vec8<float>::load(V + xi * C + c, vl);
+    Vec8<float>::load(V + (xi + 1) * C + c, vr);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = l * vl[j] + r * vr[j];
+    Vec8<T>::store(out + ((static_cast<long long>(b) * W + w) * D + d) * C + c, o);
   }
 }
 
@@ -391,7 +434,7 @@ extern "C" int tfpp_bev_lift(const void* img, int f32, const float* a_rows, cons
                              const float* wr, void* out, int batch, int img_h, int img_w, int channels, int depth,
                              int width, tfpp_stream_t stream_) {
   STREAM;
-  TFPP_CHECK_ARG(channels >= 1 && channels <= 256 && 256 % channels == 0, "bev_lift: channels must divide 256");
+  TFPP_CHECK_ARG(channels >= 8 && channels <= 256 && 256 % channels == 0, "bev_lift: channels in {8, 16, 32, 64, 128, 256}");
   const size_t smem = sizeof(float) * (static_cast<size_t>(img_w) * channels + img_h);
   TFPP_CHECK_ARG(smem <= 48 * 1024, "bev_lift: one image row block must fit 48 KB of shared memory");
   const dim3 grid(depth, batch);

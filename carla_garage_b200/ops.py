@@ -133,6 +133,24 @@ def pick_bn(n):
   return max(bn for p, bn in cands if p <= min_pad * 1.04)
 
 
+def pick_bn_for(n, m_tiles, sms=148):
+  """N tile for a persistent GEMM over ``m_tiles`` 128-pixel tiles on ``sms`` CTAs.  The kernels are bound by the operand
+  feed (a k-block moves 128 rows of A + bn rows of B), so the time is ~ rounds * (128 + bn): problems of many rounds keep
+  pick_bn's wide tile; problems of one to three rounds (LiDAR branch, decoder / planner GEMMs) take the tile width that
+  fills the last round (e.g. n = 576 on 64 pixel tiles: bn = 144 -> 256 tiles, two full-ish rounds of narrower tiles,
+  instead of 192 -> 1.3 rounds)."""
+  wide = pick_bn(n)
+  if m_tiles * -(-n // wide) >= 4 * sms:
+    return wide
+  best, best_cost = wide, None
+  for bn in range(32, 257, 16):
+    tiles = m_tiles * -(-n // bn)
+    cost = -(-tiles // sms) * (128 + bn) * (1.0 + 0.25 * (-(-n // bn) * bn - n) / n)   # padding columns are wasted work
+    if best_cost is None or cost < best_cost - 1e-9 or (abs(cost - best_cost) <= 1e-9 and bn > best):
+      best, best_cost = bn, cost
+  return best
+
+
 def nhwc_strides(h, w, c):
   return (h * w * c, w * c, c, 1)
 
@@ -169,11 +187,7 @@ def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1
   args.k_per_tile = kd if k_per_tile is None else k_per_tile
   args.a_c_per_ntile = a_c_per_ntile
   if bn is None:
-    bn = pick_bn(n)
-    # few pixel tiles (decoder / planner GEMMs, 8x8 maps): narrower N tiles put more CTAs to work
-    m_tiles = -(-wd // tw) * -(-h // th) * -(-b // nb)
-    while bn > 32 and m_tiles * -(-n // bn) < 148 and (bn // 2) % 16 == 0:
-      bn //= 2
+    bn = pick_bn_for(n, -(-wd // tw) * -(-h // th) * -(-b // nb))
   args.bn = bn
   args.tw, args.th, args.nb = tw, th, nb
   args.ntaps = len(taps)

@@ -184,7 +184,16 @@ def mlp_join_state(golden_dir):
       'loss_semantic.weight': torch.ones(7),
       'loss_bev_semantic.weight': torch.ones(11),
   }
-  return make_state_dict(shapes, seed=0, fixed=fixed)
+  return mlp_join_tweak(make_state_dict(shapes, seed=0, fixed=fixed))
+
+
+def mlp_join_tweak(sd):
+  """The seeded state happens to put the pre-activation of hidden unit 0 of ``join.0`` at 5e-6 (scale 1.2) for sample 0
+  of the golden batch: a ReLU kink, where the gradient of ANY two implementations that differ by one rounding is either
+  of two very different vectors.  Move that one bias off the kink (generator and tests apply the same shift)."""
+  sd['join.0.bias'] = sd['join.0.bias'].clone()
+  sd['join.0.bias'][0] += 0.05
+  return sd
 
 
 def bev_state(golden_dir):

@@ -36,7 +36,7 @@ def main():
   json.dump(dict(shapes=shapes, order=list(ref_sd.keys())), open(os.path.join(OUT, 'mlp_join_keys.json'), 'w'), indent=0)
   fixed = {k: ref_sd[k] for k in ('valid_bev_pixels', 'valid_bev_pixels_inv', 'loss_speed.weight', 'loss_semantic.weight',
                                   'loss_bev_semantic.weight')}
-  sd = synth.make_state_dict(shapes, seed=0, fixed=fixed)
+  sd = synth.mlp_join_tweak(synth.make_state_dict(shapes, seed=0, fixed=fixed))   # keeps a ReLU pre-activation off 0
   net.load_state_dict(sd, strict=True)
   net.train()
   for m in net.modules():
