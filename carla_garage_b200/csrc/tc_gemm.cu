@@ -83,7 +83,7 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile, int
 // LEAN: epilogue specialisations compiled as their own kernels (the K <= 576 layers are bound by the latency of the ten
 // warps' epilogue instruction stream, and the 168-register generic epilogue must not pay for them): 1 = bf16 NHWC output +
 // BatchNorm statistics, nothing else (RegNet convs of a training step); 2 = bf16 NHWC output + at most one bf16
-// residual (input-gradient GEMMs); 0 = everything.
+// residual (input-gradient GEMMs); 3 = bf16 NHWC output + bias (+ ReLU) (convs / linears with a bias); 0 = everything.
 template <bool PAIR, int LEAN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -337,6 +337,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]);
+                if (LEAN == 3) {  // + bias[n] (staged per tile in saff as {1, bias}), optional ReLU
+#pragma unroll
+                  for (int j = 0; j < 8; j += 2) {
+                    const float4 a2 = *reinterpret_cast<const float4*>(&saff[c + q * 8 + j]);
+                    v[j] += a2.y;
+                    v[j + 1] += a2.w;
+                  }
+                  if (act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                  }
+                }
                 if (with_res) {
                   const uint32_t w[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
 #pragma unroll
@@ -624,21 +636,26 @@ extern "C" int tfpp_conv_gemm(const tfpp_conv_gemm_args* a, tfpp_stream_t stream
   TFPP_CHECK_ARG(stages >= 2, "shared memory budget exceeded");
   p.stages = stages;
   const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + fixed_bytes;
-  static const bool lean_on = [] { const char* e = getenv("TFPP_GEMM_LEAN"); return e == nullptr || e[0] != '0'; }();
+  // TFPP_GEMM_LEAN: 0 = generic epilogue everywhere, 2 = statistics / residual instantiations only, default = all
+  static const int lean_level = [] { const char* e = getenv("TFPP_GEMM_LEAN"); return e ? atoi(e) : 3; }();
+  const bool lean_on = lean_level > 0;
   int lean = 0;
   if (lean_on && p.fast_layout && !a->out_f32 && a->scale == nullptr && a->shift == nullptr && a->act == ACT_NONE &&
       p.drop_rng == nullptr) {
     if (a->stat_sum != nullptr && a->res1 == nullptr) lean = 1;
     if (a->stat_sum == nullptr && (a->res1 == nullptr || !a->res1_f32)) lean = 2;
   }
+  if (lean_level >= 3 && p.fast_layout && !a->out_f32 && a->scale == nullptr && a->shift != nullptr && p.drop_rng == nullptr &&
+      a->stat_sum == nullptr && a->res1 == nullptr)
+    lean = 3;   // bias (+ ReLU): fast_layout already restricts the activation to none / ReLU
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const KParams);
-  static const KernelFn kernels[2][3] = {
-      {conv_gemm_kernel<false, 0>, conv_gemm_kernel<false, 1>, conv_gemm_kernel<false, 2>},
-      {conv_gemm_kernel<true, 0>, conv_gemm_kernel<true, 1>, conv_gemm_kernel<true, 2>}};
+  static const KernelFn kernels[2][4] = {
+      {conv_gemm_kernel<false, 0>, conv_gemm_kernel<false, 1>, conv_gemm_kernel<false, 2>, conv_gemm_kernel<false, 3>},
+      {conv_gemm_kernel<true, 0>, conv_gemm_kernel<true, 1>, conv_gemm_kernel<true, 2>, conv_gemm_kernel<true, 3>}};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 6; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels[i / 3][i % 3]),
+    for (int i = 0; i < 8; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels[i / 4][i % 4]),
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) {
         tfpp_set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));

@@ -19,15 +19,18 @@ def _run(env_extra):
                        timeout=900, cwd=ROOT, env=env)
   assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
   line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
-  return ast.literal_eval(line)
+  first = [l for l in out.stdout.splitlines() if l.startswith('first step ')][-1][len('first step '):]
+  return ast.literal_eval(first), ast.literal_eval(line)
 
 
 def test_backward_survives_the_uncached_allocator():
   if not torch.cuda.is_available():
     pytest.skip('no CUDA device')
-  normal = _run({})
-  stressed = _run({'PYTORCH_NO_CUDA_MEMORY_CACHING': '1'})
+  (normal1, normal), (stressed1, stressed) = _run({}), _run({'PYTORCH_NO_CUDA_MEMORY_CACHING': '1'})
   assert set(normal) == set(stressed) and len(normal) == 10
   for k in normal:
-    # two runs differ by the fp32-atomics / bf16 noise floor of this network (DESIGN.md "Numerics"), never by more
-    assert abs(normal[k] - stressed[k]) <= 0.1 * max(abs(normal[k]), 0.05), (k, normal[k], stressed[k])
+    # the first step (same weights in both runs) differs by the fp32-atomics / bf16 noise of one forward only; after
+    # three optimizer steps the two trajectories have drifted apart by the noise floor of this randomly initialised
+    # network (DESIGN.md "Numerics") — a tensor freed too early shows up as NaN / garbage, not as 10 %
+    assert abs(normal1[k] - stressed1[k]) <= 0.05 * max(abs(normal1[k]), 0.05), (k, normal1[k], stressed1[k])
+    assert abs(normal[k] - stressed[k]) <= 0.3 * max(abs(normal[k]), 0.05), (k, normal[k], stressed[k])

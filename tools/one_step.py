@@ -30,10 +30,14 @@ for i, c in enumerate(boxes):
   cnt[i] = len(c)
 lab.update({k: v for k, v in ops.centernet_targets(bx.cuda(), cnt.cuda()).items() if k in lab})   # labels rasterised on the device
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+first = None
 for _ in range(steps):
   out, losses = tr.step(inp, lab)
+  if first is None:
+    first = {k: float(v) for k, v in losses.items()}
 torch.cuda.synchronize()
 vals = {k: float(v) for k, v in losses.items()}
+print('first step', first)
 print(vals)
 net.eval()
 with torch.no_grad():
