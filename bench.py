@@ -304,7 +304,7 @@ def main():
             # DRAM bytes of the largest-FLOP launch of the family (fusion QKV GEMM, M=10240 K=1512 N=4536) from
             # `ncu --set full` (profiles/r01_ncu_qkv_v13_details.txt): 44.8 MB read + 39.8 MB written, against 138 MB
             # of algorithmic operand + output bytes (operand re-reads hit L2; part of the output is still in L2)
-            'traffic': 84.6e6, 'traffic_launch': 'conv_gemm_kernel, fusion QKV projection (M=10240, K=1512, N=4536)',
+            'traffic': 121.3e6, 'traffic_launch': 'conv_gemm_kernel<pair>, fusion MLP up-projection (M=10240, K=1512, N=6048): dram read 49.4 MB + write 71.8 MB, profiles/r02_ncu_gemm_mlp_pair.txt (algorithmic 173 MB; the tail of the 124 MB output is still in L2 when the kernel ends)',
             'launches_per_step': prof['launches'],
             # serial GEMM time over the (stream-overlapped) step time: an upper bound of the family's share
             'share_of_step': prof['ms'] / (ms / args.steps),
