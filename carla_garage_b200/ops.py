@@ -159,6 +159,16 @@ def nchw_strides(h, w, c):
   return (c * h * w, w, 1, h * w)
 
 
+def taps_3x3_stride2_dgrad(py, px):
+  """Taps of the input gradient of a 3x3 / stride 2 / pad 1 conv for the input pixels of parity (py, px), as an implicit
+  GEMM over the OUTPUT-gradient map: input pixel (2r + py, 2c + px) is read by the kernel rows ky whose parity plane is py
+  — ky = 1 for even rows (output row r), ky in {0, 2} for odd rows (output rows r + 1 and r) — same for columns.
+  Returns ((dx, dy, 0, ky * 3 + kx), ...) for ops.conv_gemm over the (Cin, 9, Cout) weight pack."""
+  kys = ((1, 0),) if py == 0 else ((0, 1), (2, 0))
+  kxs = ((1, 0),) if px == 0 else ((0, 1), (2, 0))
+  return tuple((ox, oy, 0, ky * 3 + kx) for ky, oy in kys for kx, ox in kxs)
+
+
 def conv_gemm(a, w, *, a_shape=None, a_batch_stride=0, batch=None, taps=TAPS_1X1, k_per_tile=None, a_c_per_ntile=0, bn=None, out=None, out_f32=False,
               out_layout='nhwc', out_strides=None, res1=None, res1_strides=None, res2=None, res2_strides=None,
               scale=None, shift=None, act=ACT_NONE, act_n_limit=0, stats=None, no_output=False, drop=None):

@@ -710,12 +710,8 @@ class Backward:
     strides = (h * w * cpad, 2 * w * cpad, 2 * cpad, 1)
     for py in (0, 1):
       for px in (0, 1):
-        # input pixel (2r + py, 2c + px) is read by the taps whose parity plane is (py, px): ky = 1 for the even rows,
-        # ky in {0, 2} for the odd ones (output row r + 1 resp. r), same for columns
-        kys = ((1, 0),) if py == 0 else ((0, 1), (2, 0))
-        kxs = ((1, 0),) if px == 0 else ((0, 1), (2, 0))
-        taps = tuple((ox, oy, 0, ky * 3 + kx) for ky, oy in kys for kx, ox in kxs)
-        ops.conv_gemm(draw, wt, taps=taps, out=flat[(py * w + px) * cpad:], out_strides=strides)
+        ops.conv_gemm(draw, wt, taps=ops.taps_3x3_stride2_dgrad(py, px), out=flat[(py * w + px) * cpad:],
+                      out_strides=strides)
     self.G[id(cat)] = dcat
 
   def planner_queries(self, r):
