@@ -184,7 +184,7 @@ def test_train_step_fp32_all_gradients_vs_reference_golden(ops):
     """Depth-aware bound on the MEDIAN error of a parameter group (slices of 256 elements are noisy one by one)."""
     if n.startswith(('backbone.image_encoder.', 'backbone.upsampling_layer', 'backbone.depth_layer', 'backbone.bev_compressor',
                      'backbone.bev_encoder.stem', 'backbone.bev_encoder.s1', 'backbone.bev_encoder.s2')):
-      return 2e-2
+      return 3e-2   # measured medians 1.3e-2 ... 1.8e-2 (profiles/r02_bev_fp32_tests.log)
     if n.startswith('backbone.bev_encoder.s3'):
       return 1e-2
     return 1e-3
@@ -205,7 +205,7 @@ def test_train_step_fp32_all_gradients_vs_reference_golden(ops):
     prof.setdefault(grp, []).append((e, n))
     n_checked += 1
     # a wrong kernel shows up as an error of order one on its layer; ReLU-mask flips as a few per cent on single slices
-    lim = 8 * base(n) if base(n) > 1e-3 else 1e-3
+    lim = min(8 * base(n), 0.16) if base(n) > 1e-3 else 1e-3
     if e >= lim or (float(g['gradnorm_' + n]) > 1e-3 * rms and abs(nr - 1.0) > lim):
       bad.append((n, e, nr))
   print('\n' + '\n'.join(f'  fp32 bev grads {k}: max {max(v)[0]:.2e} median {sorted(v)[len(v) // 2][0]:.2e} (n={len(v)})'
