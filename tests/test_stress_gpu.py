@@ -32,5 +32,5 @@ def test_backward_survives_the_uncached_allocator():
     # the first step (same weights in both runs) differs by the fp32-atomics / bf16 noise of one forward only; after
     # three optimizer steps the two trajectories have drifted apart by the noise floor of this randomly initialised
     # network (DESIGN.md "Numerics") — a tensor freed too early shows up as NaN / garbage, not as 10 %
-    assert abs(normal1[k] - stressed1[k]) <= 0.05 * max(abs(normal1[k]), 0.05), (k, normal1[k], stressed1[k])
+    assert abs(normal1[k] - stressed1[k]) <= 0.08 * max(abs(normal1[k]), 0.05), (k, normal1[k], stressed1[k])
     assert abs(normal[k] - stressed[k]) <= 0.3 * max(abs(normal[k]), 0.05), (k, normal[k], stressed[k])
