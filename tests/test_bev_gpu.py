@@ -133,6 +133,7 @@ def test_eval_forward_fp32_vs_reference_golden(ops):
     assert v < 1e-3, (k, v)
 
 
+@pytest.mark.noisy
 def test_eval_forward_bf16_vs_reference_golden(ops):
   """Production precision: outputs within the bf16 floor of a randomly initialised network."""
   from carla_garage_b200 import synth
@@ -154,6 +155,7 @@ def _labels():
   return {k: v.cuda().contiguous() for k, v in synth.make_labels(2, seed=13).items()}
 
 
+@pytest.mark.noisy
 def test_train_step_fp32_all_gradients_vs_reference_golden(ops):
   """fp32 parity mode through the autograd boundary (model(...) -> losses -> loss.backward(), train.py:776-820,883-898):
   train-mode outputs, the ten losses and a 256-element slice + the norm of EVERY parameter gradient against the
@@ -218,6 +220,7 @@ def test_train_step_fp32_all_gradients_vs_reference_golden(ops):
       assert med < base(v[0][1]), (k, med)
 
 
+@pytest.mark.noisy
 def test_trainer_step_bf16_and_graph(ops):
   """Production precision: the fused Trainer step tracks the reference's losses within the bf16 floor, gradients of
   the late layers point the same way, and the captured CUDA graph replays the step (loss goes down on a fixed batch)."""

@@ -122,6 +122,7 @@ def trainer_grads(oracle_state):
   return {k: float(v) for k, v in losses.items()}, grads
 
 
+@pytest.mark.noisy
 def test_reference_train_loop_runs_unmodified(oracle_state, trainer_grads):
   want_losses, want_grads = trainer_grads
   m = _model(oracle_state)
@@ -193,6 +194,7 @@ def test_reference_train_loop_runs_unmodified(oracle_state, trainer_grads):
     assert rel(got[i], eval_before[i]) > 2 * rel(got[i], want[i]), (i, rel(got[i], eval_before[i]), rel(got[i], want[i]))
 
 
+@pytest.mark.noisy
 def test_general_autograd_path_torch_losses(oracle_state):
   """A user's own torch loss on the outputs (no fused loss kernels): ordinary gradients arrive at the boundary and are
   converted into seeds by tfpp_act_bwd.  Compared on ONE forward with the fused-loss path (two backward passes through
@@ -222,6 +224,7 @@ def test_general_autograd_path_torch_losses(oracle_state):
   print(f'  general vs fused seeds on one forward: worst parameter-gradient rel err {worst[1]:.2e} ({worst[0]})')
 
 
+@pytest.mark.noisy
 def test_gradient_accumulation_and_partial_losses(oracle_state):
   """Two backward passes without zero_grad accumulate (AccumulateGrad adds in place, the boundary alternates its flat
   buffers); a loss that touches only some outputs still yields a gradient for every parameter (zeros where unused)."""

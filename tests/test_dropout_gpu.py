@@ -160,6 +160,7 @@ def _grad_state(oracle_state, gemm_prefixes):
               if v.is_floating_point() and 'running' not in k else v) for k, v in oracle_state.items()}
 
 
+@pytest.mark.noisy
 def test_fusion_block_with_dropout_vs_oracle(ops, trainer, oracle_state):
   """fuse_features + GPT (transfuser.py:222-257,301-339) in training mode with all four dropout kinds active, forward and
   backward, against the fp32 oracle given the same masks."""
@@ -207,6 +208,7 @@ def test_fusion_block_with_dropout_vs_oracle(ops, trainer, oracle_state):
   assert rel(ops.nhwc_to_nchw(yi), wi0) > 3e-2
 
 
+@pytest.mark.noisy
 def test_planner_with_dropout_vs_oracle(ops, trainer, oracle_state):
   """6-layer post-norm decoder with the six dropouts of nn.TransformerDecoderLayer per layer (model.py:137-140)."""
   from carla_garage_b200.training import Backward
@@ -249,6 +251,7 @@ def test_planner_with_dropout_vs_oracle(ops, trainer, oracle_state):
   net.load_state_dict(oracle_state, strict=True)
 
 
+@pytest.mark.noisy
 def test_train_step_with_dropout_and_graph_replay(trainer, oracle_state):
   """The whole step with dropout on: every replay of the captured graph draws a new mask (the step counter lives on the
   device), eval stays deterministic, and the loss still goes down on a repeated batch."""

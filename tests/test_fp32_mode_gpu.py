@@ -249,6 +249,7 @@ def test_forward_train_mode_and_losses_fp32_vs_reference_golden(net, oracle_stat
     net.eval()
 
 
+@pytest.mark.noisy
 def test_train_step_gradients_fp32_vs_reference(oracle_state, fp32):
   """The reference's train step (model(...) -> losses -> loss.backward(), train.py:776-820,883-898) through the autograd
   boundary with the engine's hand-scheduled backward on fp32 storage: EVERY parameter gradient within 1e-3 of the

@@ -94,6 +94,7 @@ def _data():
   return inp, lab
 
 
+@pytest.mark.noisy
 def test_mlp_join_train_step_fp32_vs_reference_golden(ops):
   """fp32 parity mode through the autograd boundary: outputs, the eleven losses and the gradients of every planner
   parameter (join MLP, both GRUCell heads, target-speed MLP, extra-sensor encoder, lidar_to_img_features_end) within
@@ -129,6 +130,7 @@ def test_mlp_join_train_step_fp32_vs_reference_golden(ops):
     assert v < 1e-3, (k, v)
 
 
+@pytest.mark.noisy
 def test_mlp_join_bf16_trainer_step_and_graph(ops):
   """Production precision: the fused Trainer step (losses incl. loss_wp) tracks the reference within the bf16 floor of
   this network, and the captured graph replays it."""

@@ -40,6 +40,7 @@ def _inputs(b, seed):
   return {k: v.cuda() for k, v in synth.make_inputs(b, seed=seed).items()}
 
 
+@pytest.mark.noisy
 def test_forward_eval_vs_golden(net):
   from carla_garage_b200 import ops
   g = np.load(os.path.join(GOLDEN, 'forward_eval_b2.npz'))
@@ -81,6 +82,7 @@ def test_forward_eval_vs_golden(net):
   assert rel(boxes[..., 8], g['boxes'][..., 8]) < max(TOL, 2.5 * float(g['bf16floor_bb_heatmap']))
 
 
+@pytest.mark.noisy
 def test_forward_eval_vs_live_oracle(net, oracle_state):
   from carla_garage_b200 import synth
   from oracle import tfpp_oracle as orc
@@ -98,6 +100,7 @@ def test_forward_eval_vs_live_oracle(net, oracle_state):
     assert rel(a, b) < max(TOL, 3 * float(g['bf16floor_bb_' + n]))
 
 
+@pytest.mark.noisy
 def test_forward_train_mode_vs_golden(net, oracle_state):
   """Training-mode forward: BatchNorm batch statistics (+ running-stat update), dropout off."""
   g = np.load(os.path.join(GOLDEN, 'train_b2.npz'))

@@ -88,6 +88,7 @@ def test_nms_edge_cases_and_drop_in(ops):
   assert inference.non_maximum_suppression([[], None], 0.2) == []
 
 
+@pytest.mark.noisy
 def test_ensemble_forward_three_members(ops, oracle_state):
   """sensor_agent.py:445-552 for a small batch: three members (different weights), averaged planner outputs, merged
   boxes == the oracle merge of the three members' own decoded boxes."""

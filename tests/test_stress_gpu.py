@@ -23,6 +23,7 @@ def _run(env_extra):
   return ast.literal_eval(first), ast.literal_eval(line)
 
 
+@pytest.mark.noisy
 def test_backward_survives_the_uncached_allocator():
   if not torch.cuda.is_available():
     pytest.skip('no CUDA device')
