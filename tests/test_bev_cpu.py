@@ -128,3 +128,32 @@ def test_oracle_train_step_losses_and_gradients_vs_reference_golden():
   print('\n'.join(f'    {k:40s} max {max(v):.2e}  median {sorted(v)[len(v) // 2]:.2e}  ({len(v)})' for k, v in sorted(groups.items())))
   allv = sorted(e for v in groups.values() for e in v)
   assert n >= 700 and worst[1] < 0.2 and allv[len(allv) // 2] < 1e-2, (worst, allv[len(allv) // 2])
+
+
+def test_lift_tables_other_cameras_and_feature_sizes():
+  """The separable form holds for any pinhole camera without rotation: other field of view / mounting point / height
+  range / feature-map size, against F.grid_sample over that configuration's own grid (reference semantics restated in
+  oracle/bev_oracle.create_projection_grid)."""
+  from carla_garage_b200.config import GlobalConfig
+  from carla_garage_b200.nn.bev_encoder import lift_tables, projection_grid
+  from oracle import bev_oracle as bo
+  for fov, pos, zr, ih, iw, px in ((90, (0.5, 0.0, 1.5), (-4, 6), 16, 64, 2.0), (60, (-2.0, 0.0, 2.5), (-10, 14), 24, 40, 1.0)):
+    cfg = GlobalConfig()
+    cfg.camera_fov, cfg.camera_pos, cfg.pixels_per_meter = fov, list(pos), px
+    cfg.min_z_projection, cfg.max_z_projection = zr
+    ocfg = dict(bo.BEV_CFG, camera_fov=fov, camera_pos=pos, pixels_per_meter=px, min_z_projection=zr[0], max_z_projection=zr[1])
+    grid, ok = projection_grid(cfg)
+    ogrid, ook = bo.create_projection_grid(ocfg)
+    assert float((grid - ogrid).abs().max()) <= 1e-6 and bool((ok == ook).all())
+    norm = torch.finfo(torch.float32).eps + ok.sum(3).unsqueeze(1)
+    vbp = torch.transpose(ok.max(3)[0].unsqueeze(1), 2, 3).contiguous()
+    a, x0, wl, wr = lift_tables(grid, norm, vbp, ih, iw)
+    d, w = grid.shape[1], grid.shape[2]
+    assert int(x0.min()) >= 0 and int(x0.max()) <= iw - 2
+    img = torch.randn(1, 3, ih, iw, generator=torch.Generator().manual_seed(fov))
+    vol = F.grid_sample(img.unsqueeze(2), ogrid, align_corners=False, padding_mode='zeros')
+    want = (vol.sum(4) / norm).transpose(2, 3) * vbp
+    v = torch.einsum('dy,bcyx->bcdx', a, img)
+    idx = x0.long().view(1, 1, d, w).expand(1, 3, -1, -1)
+    got = (wl * torch.gather(v, 3, idx) + wr * torch.gather(v, 3, idx + 1)).transpose(2, 3)
+    assert rel(got, want) < 1e-5, (fov, rel(got, want))   # (fp32 grid_sample against tables folded in float64)
